@@ -1,0 +1,77 @@
+/* Additive GPU extension of the muFFT API (include/fft.h stays exactly the reference surface).
+ *
+ * fft.h has no notion of batch, stream or device (ref fft.h:86-121): one call = one transform,
+ * synchronous.  A B200 is only busy when thousands of transforms are in flight, so the entry
+ * points below run the SAME plans over a batch of independent transforms with one kernel
+ * launch, optionally asynchronously on a caller-provided CUDA stream.
+ *
+ * Memory: every pointer may be ordinary host memory, pinned host memory, CUDA managed memory
+ * (what mufft_alloc returns) or device memory.  Host memory is staged through plan-owned device
+ * buffers in pipelined chunks; device/managed memory is used in place.
+ *
+ * Strides are in BYTES between consecutive transforms; 0 selects the tight default:
+ *   C2C      in N*8 (N/2*8 with ZERO_PAD_UPPER_HALF)   out N*8
+ *   R2C      in N*4 (N/2*4 zero padded)                out (N/2+1)*8, or N*8 with FULL_R2C
+ *   C2R      in (N/2+1)*8                              out N*4
+ * Strides must be multiples of 8 bytes and buffers 8-byte aligned.
+ */
+#ifndef MUFFT_CUDA_H__
+#define MUFFT_CUDA_H__
+
+#include "fft.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Number of visible CUDA devices (0 when there is none or the driver is missing). */
+int mufft_cuda_device_count(void);
+/* Device used by plans created afterwards on this thread, and by mufft_alloc. 0 on success. */
+int mufft_cuda_set_device(int device);
+/* CUDA stream (a cudaStream_t passed as void*) used by executes issued from this thread.
+ * NULL (the default) is the legacy default stream. */
+void mufft_cuda_set_stream(void *stream);
+void *mufft_cuda_get_stream(void);
+/* Blocks until the current stream has drained.  Returns 0 or a CUDA error code. */
+int mufft_cuda_synchronize(void);
+/* Message of the last failure on this thread ("" if none).  Never NULL. */
+const char *mufft_cuda_last_error(void);
+/* Kernel launches issued by the library since the previous call with reset != 0. */
+unsigned long long mufft_cuda_launch_count(int reset);
+
+/* `batch` independent 1D transforms with the plan's kind; synchronous (returns when `output`
+ * is complete and host-visible), any memory kind. */
+int mufft_execute_plan_1d_batch(mufft_plan_1d *plan, void *output, const void *input, size_t batch,
+                                size_t output_stride_bytes, size_t input_stride_bytes);
+/* Same, but only enqueues work on the current stream; both pointers must be device-accessible
+ * (device or managed memory).  Returns 0, or nonzero if the pointers are not device-accessible
+ * or a launch failed. */
+int mufft_execute_plan_1d_batch_async(mufft_plan_1d *plan, void *output, const void *input, size_t batch,
+                                      size_t output_stride_bytes, size_t input_stride_bytes);
+
+/* `batch` independent images, tightly packed one after another (each laid out as fft.h
+ * describes for the plan's kind: [Ny][Nx] complex, R2C output / C2R input with row pitch Nx
+ * complex).  C2R output images are Nx*Ny floats each, densely packed. */
+int mufft_execute_plan_2d_batch(mufft_plan_2d *plan, void *output, const void *input, size_t batch);
+int mufft_execute_plan_2d_batch_async(mufft_plan_2d *plan, void *output, const void *input, size_t batch);
+
+/* Batched convolution stages.  Blocks are mufft_conv_get_transformed_block_size() bytes apart;
+ * inputs and outputs are tightly packed.  If second_stride_bytes is 0 every block of the batch
+ * is multiplied by the same `input_second` spectrum (one filter, many signal blocks). */
+int mufft_execute_conv_input_batch(mufft_plan_conv *plan, unsigned block, void *output, const void *input, size_t batch);
+int mufft_execute_conv_output_batch(mufft_plan_conv *plan, void *output, const void *input_first,
+                                    const void *input_second, size_t batch, size_t second_stride_bytes);
+int mufft_execute_conv_input_batch_async(mufft_plan_conv *plan, unsigned block, void *output, const void *input, size_t batch);
+int mufft_execute_conv_output_batch_async(mufft_plan_conv *plan, void *output, const void *input_first,
+                                          const void *input_second, size_t batch, size_t second_stride_bytes);
+
+/* Introspection used by tests and the bench: which path a plan takes.
+ * 1D: 1 = single-kernel shared-memory engine, 0 = multi-pass generic kernels.
+ * 2D: bit 0 = rows on the engine, bit 1 = columns on the shared-memory column kernel. */
+int mufft_cuda_plan_1d_uses_engine(const mufft_plan_1d *plan);
+int mufft_cuda_plan_2d_paths(const mufft_plan_2d *plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,139 @@
+/* Internal C ABI between the C host layer (mufft_host.c) and the CUDA translation units.
+ * Plain pointers and sizes only; every function returns 0 on success or a cudaError_t value.
+ * Nothing here is exported to users: the public surface is include/fft.h + include/mufft_cuda.h.
+ */
+#ifndef MUFFT_B200_ABI_H
+#define MUFFT_B200_ABI_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Largest transform length handled by the single-kernel shared-memory engine. */
+#define MCU_ENGINE_MAX_N 8192
+/* Largest column length handled by the shared-memory column kernel. */
+#define MCU_COLS_MAX_N 2048
+
+/* How a row transform reads its input (first pass prologue). */
+enum {
+    MCU_IN_COMPLEX = 0,   /* x[i] = in[i]                                   (C2C, and R2C: reals viewed as N/2 complex) */
+    MCU_IN_HALF = 1,      /* x[i] = i < N/2 ? in[i] : 0, upper half never read (ref kernel.c:104-122,200-226,333-387) */
+    MCU_IN_C2R = 2,       /* x[k] = (X[k]+conj X[N-k]) + (X[k]-conj X[N-k])*rtw[k]   (ref kernel.c:36-45) */
+    MCU_IN_MUL = 3,       /* x[i] = norm * in[i] * in2[i]                            (ref kernel.c:22-34) */
+    MCU_IN_MUL_C2R = 4    /* X = norm * in .* in2, then as MCU_IN_C2R */
+};
+/* How a row transform writes its output (last pass epilogue). */
+enum {
+    MCU_OUT_COMPLEX = 0,  /* out[i] = y[i] */
+    MCU_OUT_R2C = 1,      /* N+1 bins from the N-point half-length spectrum  (ref kernel.c:47-63) */
+    MCU_OUT_R2C_FULL = 2  /* all 2N bins                                      (ref kernel.c:65-82) */
+};
+
+typedef struct mcu_rows_args {
+    void *out;
+    const void *in;
+    const void *in2;       /* second operand of the spectral multiply, else NULL */
+    const void *tw;        /* engine twiddle table for n (device) */
+    const void *rtw;       /* resolve twiddles, n entries (device), or NULL */
+    size_t out_stride;     /* distance between consecutive transforms, in complex elements */
+    size_t in_stride;
+    size_t in2_stride;     /* 0 = every transform multiplies by the same spectrum */
+    size_t batch;
+    unsigned n;            /* complex transform length */
+    int direction;         /* -1 forward, +1 inverse */
+    int in_mode, out_mode;
+    float norm;
+} mcu_rows_args;
+
+typedef struct mcu_cols_args {
+    void *out;
+    const void *in;
+    const void *tw;        /* engine twiddle table for n */
+    size_t out_pitch;      /* complex elements between consecutive rows */
+    size_t in_pitch;
+    size_t out_image;      /* complex elements between consecutive images of a batch */
+    size_t in_image;
+    size_t batch;
+    unsigned n;            /* column length (rows) */
+    unsigned width;        /* number of columns to transform */
+    int direction;
+} mcu_cols_args;
+
+/* Generic one-pass Stockham kernel (any length; used beyond the engine limits). */
+typedef struct mcu_pass_args {
+    void *out;
+    const void *in;
+    const void *roots;     /* master table exp(dir*2*pi*i*j/n), j < n (device) */
+    size_t out_stride;     /* complex elements between consecutive points of one transform */
+    size_t in_stride;
+    size_t out_batch;      /* complex elements between consecutive batch entries */
+    size_t in_batch;
+    size_t batch;
+    unsigned n;            /* transform length */
+    unsigned width;        /* independent transforms side by side (columns); 1 for 1D */
+    unsigned radix, p;
+    int direction;
+    int half;              /* first pass of a zero-padded transform */
+} mcu_pass_args;
+
+/* Stand-alone resolve / multiply kernel (generic path and mufft_get_convolve_func). */
+enum { MCU_RES_R2C = 0, MCU_RES_R2C_FULL = 1, MCU_RES_C2R = 2, MCU_RES_MUL = 3, MCU_RES_MUL_C2R = 4 };
+
+typedef struct mcu_resolve_args {
+    void *out;
+    const void *in;
+    const void *in2;       /* second spectrum for the MUL modes, else NULL */
+    const void *rtw;       /* resolve twiddles, n entries (unused by MCU_RES_MUL) */
+    size_t out_stride, in_stride, in2_stride, batch; /* strides in complex elements */
+    unsigned n;            /* complex length (MCU_RES_MUL: number of samples, any value) */
+    int mode;              /* MCU_RES_* */
+    float norm;
+} mcu_resolve_args;
+
+/* ---- runtime ---------------------------------------------------------------------------- */
+int mcu_device_count(int *count);
+int mcu_set_device(int device);
+int mcu_get_device(int *device);
+int mcu_sm_count(int *count);
+const char *mcu_error_string(int err);
+
+int mcu_malloc(void **ptr, size_t bytes);
+int mcu_free(void *ptr);
+int mcu_malloc_managed(void **ptr, size_t bytes);
+int mcu_malloc_pinned(void **ptr, size_t bytes);
+int mcu_free_pinned(void *ptr);
+int mcu_memset(void *ptr, int value, size_t bytes, void *stream);
+
+/* 0 = ordinary host memory, 1 = pinned host, 2 = device, 3 = managed */
+enum { MCU_MEM_HOST = 0, MCU_MEM_PINNED = 1, MCU_MEM_DEVICE = 2, MCU_MEM_MANAGED = 3 };
+int mcu_pointer_kind(const void *ptr);
+
+int mcu_stream_create(void **stream);
+int mcu_stream_destroy(void *stream);
+int mcu_stream_sync(void *stream);
+int mcu_event_create(void **event);
+int mcu_event_destroy(void *event);
+int mcu_event_record(void *event, void *stream);
+int mcu_stream_wait_event(void *stream, void *event);
+int mcu_event_sync(void *event);
+int mcu_copy_async(void *dst, const void *src, size_t bytes, void *stream);
+int mcu_copy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t rows, void *stream);
+int mcu_prefetch(const void *ptr, size_t bytes, int to_device, void *stream);
+
+/* ---- kernels ------------------------------------------------------------------------------ */
+int mcu_launch_rows(const mcu_rows_args *args, void *stream);
+int mcu_launch_cols(const mcu_cols_args *args, void *stream);
+int mcu_launch_pass(const mcu_pass_args *args, void *stream);
+int mcu_launch_resolve(const mcu_resolve_args *args, void *stream);
+/* number of complex entries of the engine twiddle table for length n, and its host fill */
+size_t mcu_engine_table_size(unsigned n);
+void mcu_engine_table_fill(float *table, unsigned n, int direction);
+/* number of kernel launches issued through mcu_launch_* since the last reset (for bench.py) */
+unsigned long long mcu_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

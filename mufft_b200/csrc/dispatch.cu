@@ -1,0 +1,287 @@
+// C-ABI entry points of the CUDA side (see abi.h): runtime helpers, the size dispatch for the
+// row / column engine kernels, and the generic kernels used beyond the engine limits:
+//   * stockham_pass_kernel   one radix-8/4/2 Stockham pass, any length, 1D or vertical
+//                            (the role of ref kernel.c:84-453 and 455-738)
+//   * resolve_kernel         stand-alone R2C / C2R resolve and spectral multiply
+//                            (ref kernel.c:22-82); also backs mufft_get_convolve_func().
+#include "abi.h"
+#include "fft_engine.cuh"
+
+#include <atomic>
+#include <math.h>
+
+namespace mufft {
+#define MUFFT_DECLARE_ROWS(n) cudaError_t rows_launch_##n(const mcu_rows_args &, cudaStream_t);
+#define MUFFT_DECLARE_COLS(n) cudaError_t cols_launch_##n(const mcu_cols_args &, cudaStream_t);
+MUFFT_DECLARE_ROWS(2) MUFFT_DECLARE_ROWS(4) MUFFT_DECLARE_ROWS(8) MUFFT_DECLARE_ROWS(16)
+MUFFT_DECLARE_ROWS(32) MUFFT_DECLARE_ROWS(64) MUFFT_DECLARE_ROWS(128) MUFFT_DECLARE_ROWS(256)
+MUFFT_DECLARE_ROWS(512) MUFFT_DECLARE_ROWS(1024) MUFFT_DECLARE_ROWS(2048) MUFFT_DECLARE_ROWS(4096)
+MUFFT_DECLARE_ROWS(8192)
+MUFFT_DECLARE_COLS(2) MUFFT_DECLARE_COLS(4) MUFFT_DECLARE_COLS(8) MUFFT_DECLARE_COLS(16)
+MUFFT_DECLARE_COLS(32) MUFFT_DECLARE_COLS(64) MUFFT_DECLARE_COLS(128) MUFFT_DECLARE_COLS(256)
+MUFFT_DECLARE_COLS(512) MUFFT_DECLARE_COLS(1024) MUFFT_DECLARE_COLS(2048)
+
+static std::atomic<unsigned long long> g_launches{0};
+
+// ---- generic Stockham pass ----------------------------------------------------------------
+template <int RADIX, int DIR>
+__global__ void __launch_bounds__(256) stockham_pass_kernel(const mcu_pass_args a)
+{
+    const size_t q = a.n / RADIX;
+    const size_t total = q * a.width;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const size_t x = idx % a.width;
+    const size_t i = idx / a.width;
+    const size_t k = i & (size_t)(a.p - 1);
+    const size_t base = (i - k) * RADIX + k;
+    const size_t step = a.n / ((size_t)RADIX * a.p);
+    const cpx *__restrict__ roots = static_cast<const cpx *>(a.roots);
+
+    for (size_t b = blockIdx.y; b < a.batch; b += gridDim.y) {
+        const cpx *__restrict__ in = static_cast<const cpx *>(a.in) + b * a.in_batch + x;
+        cpx *__restrict__ out = static_cast<cpx *>(a.out) + b * a.out_batch + x;
+        cpx v[RADIX];
+#pragma unroll
+        for (int m = 0; m < RADIX; m++)
+            v[m] = (a.half && m >= RADIX / 2) ? make_float2(0.0f, 0.0f) : in[(i + m * q) * a.in_stride];
+        if (a.p > 1) {
+#pragma unroll
+            for (int m = 1; m < RADIX; m++) v[m] = cmul(v[m], __ldg(roots + k * m * step));
+        }
+        dft_regs<RADIX, DIR>(v);
+#pragma unroll
+        for (int r = 0; r < RADIX; r++) out[(base + (size_t)r * a.p) * a.out_stride] = v[r];
+    }
+}
+
+template <int RADIX>
+static cudaError_t launch_pass_radix(const mcu_pass_args &a, cudaStream_t stream)
+{
+    const size_t total = (size_t)(a.n / RADIX) * a.width;
+    if (total == 0 || a.batch == 0) return cudaSuccess;
+    const size_t ctas = (total + 255) / 256;
+    if (ctas > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    dim3 grid((unsigned)ctas, (unsigned)(a.batch > 65535 ? 65535 : a.batch));
+    if (a.direction < 0) stockham_pass_kernel<RADIX, -1><<<grid, 256, 0, stream>>>(a);
+    else stockham_pass_kernel<RADIX, 1><<<grid, 256, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+// ---- stand-alone resolve / multiply -----------------------------------------------------
+__global__ void __launch_bounds__(256) resolve_kernel(const mcu_resolve_args a)
+{
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.n) return;
+    const unsigned n = a.n;
+    const cpx *__restrict__ rtw = static_cast<const cpx *>(a.rtw);
+    for (size_t b = blockIdx.y; b < a.batch; b += gridDim.y) {
+        const cpx *__restrict__ in = static_cast<const cpx *>(a.in) + b * a.in_stride;
+        const cpx *__restrict__ in2 = a.in2 ? static_cast<const cpx *>(a.in2) + b * a.in2_stride : in;
+        cpx *__restrict__ out = static_cast<cpx *>(a.out) + b * a.out_stride;
+        if (a.mode == MCU_RES_MUL) {
+            out[k] = cscale(a.norm, cmul(in[k], in2[k]));
+        } else if (a.mode == MCU_RES_C2R || a.mode == MCU_RES_MUL_C2R) {
+            cpx xa = in[k], xb = in[n - k];
+            if (a.mode == MCU_RES_MUL_C2R) {
+                xa = cscale(a.norm, cmul(xa, in2[k]));
+                xb = cscale(a.norm, cmul(xb, in2[n - k]));
+            }
+            xb = cconj(xb);
+            out[k] = cadd(cadd(xa, xb), cmul(csub(xa, xb), __ldg(rtw + k)));
+        } else {
+            const cpx za = in[k];
+            if (k == 0) {
+                out[0] = make_float2(za.x + za.y, 0.0f);
+                out[n] = make_float2(za.x - za.y, 0.0f);
+            } else {
+                const cpx zb = cconj(in[n - k]);
+                const cpx fe = cadd(za, zb);
+                const cpx fo = cmul(__ldg(rtw + k), csub(za, zb));
+                out[k] = cscale(0.5f, cadd(fe, fo));
+                if (a.mode == MCU_RES_R2C_FULL) out[k + n] = cscale(0.5f, csub(fe, fo));
+            }
+        }
+    }
+}
+
+// ---- engine twiddle tables -----------------------------------------------------------------
+template <int N>
+static void fill_table(float *table, int direction)
+{
+    constexpr int passes = engine_num_passes(N);
+    for (int j = 1; j < passes; j++) {
+        const int r = engine_radix(N, j), p = engine_span(N, j);
+        float *block = table + 2 * (size_t)engine_tw_offset(N, j);
+        for (int m = 1; m < r; m++)
+            for (int k = 0; k < p; k++) {
+                // exp(dir * 2*pi*i * k*m / (r*p)), evaluated in double and rounded once, the way
+                // the reference builds its tables (ref fft.c:102-106).
+                const double phase = (M_PI * direction * 2.0 * (double)(k * m)) / (double)(r * p);
+                block[2 * ((size_t)(m - 1) * p + k) + 0] = (float)cos(phase);
+                block[2 * ((size_t)(m - 1) * p + k) + 1] = (float)sin(phase);
+            }
+    }
+}
+
+#define MUFFT_FOR_ENGINE_SIZES(X) \
+    X(2) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192)
+
+} // namespace mufft
+
+using namespace mufft;
+
+extern "C" {
+
+// ---- runtime -----------------------------------------------------------------------------
+int mcu_device_count(int *count) { return (int)cudaGetDeviceCount(count); }
+int mcu_set_device(int device) { return (int)cudaSetDevice(device); }
+int mcu_get_device(int *device) { return (int)cudaGetDevice(device); }
+int mcu_sm_count(int *count)
+{
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return (int)err;
+    return (int)cudaDeviceGetAttribute(count, cudaDevAttrMultiProcessorCount, dev);
+}
+const char *mcu_error_string(int err) { return cudaGetErrorString((cudaError_t)err); }
+
+int mcu_malloc(void **ptr, size_t bytes) { return (int)cudaMalloc(ptr, bytes ? bytes : 256); }
+int mcu_free(void *ptr) { return ptr ? (int)cudaFree(ptr) : 0; }
+int mcu_malloc_managed(void **ptr, size_t bytes) { return (int)cudaMallocManaged(ptr, bytes ? bytes : 256, cudaMemAttachGlobal); }
+int mcu_malloc_pinned(void **ptr, size_t bytes) { return (int)cudaHostAlloc(ptr, bytes ? bytes : 256, cudaHostAllocDefault); }
+int mcu_free_pinned(void *ptr) { return ptr ? (int)cudaFreeHost(ptr) : 0; }
+int mcu_memset(void *ptr, int value, size_t bytes, void *stream)
+{
+    return (int)cudaMemsetAsync(ptr, value, bytes, (cudaStream_t)stream);
+}
+
+int mcu_pointer_kind(const void *ptr)
+{
+    cudaPointerAttributes attr;
+    cudaError_t err = cudaPointerGetAttributes(&attr, ptr);
+    if (err != cudaSuccess) {
+        (void)cudaGetLastError();
+        return MCU_MEM_HOST;
+    }
+    switch (attr.type) {
+    case cudaMemoryTypeHost: return MCU_MEM_PINNED;
+    case cudaMemoryTypeDevice: return MCU_MEM_DEVICE;
+    case cudaMemoryTypeManaged: return MCU_MEM_MANAGED;
+    default: return MCU_MEM_HOST;
+    }
+}
+
+int mcu_stream_create(void **stream)
+{
+    cudaStream_t s;
+    cudaError_t err = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    *stream = (void *)s;
+    return (int)err;
+}
+int mcu_stream_destroy(void *stream) { return stream ? (int)cudaStreamDestroy((cudaStream_t)stream) : 0; }
+int mcu_stream_sync(void *stream) { return (int)cudaStreamSynchronize((cudaStream_t)stream); }
+int mcu_event_create(void **event)
+{
+    cudaEvent_t e;
+    cudaError_t err = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    *event = (void *)e;
+    return (int)err;
+}
+int mcu_event_destroy(void *event) { return event ? (int)cudaEventDestroy((cudaEvent_t)event) : 0; }
+int mcu_event_record(void *event, void *stream) { return (int)cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream); }
+int mcu_stream_wait_event(void *stream, void *event) { return (int)cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0); }
+int mcu_event_sync(void *event) { return (int)cudaEventSynchronize((cudaEvent_t)event); }
+int mcu_copy_async(void *dst, const void *src, size_t bytes, void *stream)
+{
+    if (bytes == 0) return 0;
+    return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream);
+}
+int mcu_copy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t rows, void *stream)
+{
+    if (width_bytes == 0 || rows == 0) return 0;
+    return (int)cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, rows, cudaMemcpyDefault, (cudaStream_t)stream);
+}
+int mcu_prefetch(const void *ptr, size_t bytes, int to_device, void *stream)
+{
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return (int)err;
+    err = cudaMemPrefetchAsync(ptr, bytes, to_device ? dev : cudaCpuDeviceId, (cudaStream_t)stream);
+    if (err != cudaSuccess) (void)cudaGetLastError(); // advisory only
+    return 0;
+}
+
+// ---- engine twiddle tables (see fill_table above) --------------------------------------------
+size_t mcu_engine_table_size(unsigned n)
+{
+    switch (n) {
+#define X(v) case v: return (size_t)engine_tw_total(v) + 1;
+        MUFFT_FOR_ENGINE_SIZES(X)
+#undef X
+    default: return 0;
+    }
+}
+
+void mcu_engine_table_fill(float *table, unsigned n, int direction)
+{
+    switch (n) {
+#define X(v) case v: fill_table<v>(table, direction); break;
+        MUFFT_FOR_ENGINE_SIZES(X)
+#undef X
+    default: break;
+    }
+}
+
+// ---- launches -------------------------------------------------------------------------------
+int mcu_launch_rows(const mcu_rows_args *a, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    switch (a->n) {
+#define X(v) case v: return (int)rows_launch_##v(*a, s);
+        MUFFT_FOR_ENGINE_SIZES(X)
+#undef X
+    default: return (int)cudaErrorInvalidValue;
+    }
+}
+
+int mcu_launch_cols(const mcu_cols_args *a, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    switch (a->n) {
+#define X(v) case v: return (int)cols_launch_##v(*a, s);
+        X(2) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048)
+#undef X
+    default: return (int)cudaErrorInvalidValue;
+    }
+}
+
+int mcu_launch_pass(const mcu_pass_args *a, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    switch (a->radix) {
+    case 2: return (int)launch_pass_radix<2>(*a, s);
+    case 4: return (int)launch_pass_radix<4>(*a, s);
+    case 8: return (int)launch_pass_radix<8>(*a, s);
+    default: return (int)cudaErrorInvalidValue;
+    }
+}
+
+int mcu_launch_resolve(const mcu_resolve_args *a, void *stream)
+{
+    if (a->n == 0 || a->batch == 0) return 0;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    dim3 grid((a->n + 255) / 256, (unsigned)(a->batch > 65535 ? 65535 : a->batch));
+    resolve_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
+    return (int)cudaGetLastError();
+}
+
+unsigned long long mcu_launch_count(int reset)
+{
+    return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+} // extern "C"

@@ -1,0 +1,956 @@
+/* Host layer of the B200 muFFT implementation: the fft.h entry points (plans, validation,
+ * twiddle tables, memory classification, staging) in C, calling the CUDA side only through
+ * the C ABI of abi.h.  There is no CPU compute path: every transform runs in a CUDA kernel,
+ * and plan creation fails (NULL) when no CUDA device is usable.
+ *
+ * Mapping to the reference (paths relative to /root/reference):
+ *   plan structs            fft.c:54-99      -> struct mufft_plan_1d/_2d/_conv below
+ *   build_twiddles          fft.c:102-134    -> axis_init (engine tables: dispatch.cu fill_table)
+ *   build_r2c_twiddles      fft.c:441-455    -> make_resolve_twiddles
+ *   build_plan_1d/_2d       fft.c:325-435    -> static schedule (engine: fft_engine.cuh; generic: axis_init)
+ *   mufft_execute_plan_1d   fft.c:811-850    -> exec_1d -> run_rows (one fused kernel when N <= 8192)
+ *   mufft_execute_plan_2d   fft.c:852-989    -> exec_2d -> run_2d_device (row kernel + column kernel)
+ *   conv                    fft.c:565-624, 794-809 -> multiply fused into the inverse transform's load
+ *   mufft_alloc/free        fft.c:1032-1084  -> CUDA managed memory
+ */
+#include "fft.h"
+#include "mufft_cuda.h"
+#include "abi.h"
+
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+#define MUFFT_FLAG_R2C_INTERNAL (1u << 26)
+#define MUFFT_FLAG_C2R_INTERNAL (1u << 27)
+#define MUFFT_PADDING_COMPLEX_SAMPLES 4 /* ref fft_internal.h:203 */
+
+enum { KIND_C2C = 0, KIND_R2C = 1, KIND_R2C_FULL = 2, KIND_C2R = 3 };
+
+#define CPX 8u                              /* bytes per complex sample */
+#define STAGE_SLOTS 3
+#define STAGE_CHUNK_BYTES ((size_t)32 << 20) /* per-slot staging granularity */
+#define SCRATCH_CAP_BYTES ((size_t)256 << 20)
+#define ZERO_COPY_BYTES ((size_t)64 << 10)   /* pinned buffers up to this size are used in place */
+#define MAX_STEPS 32
+
+/* ---- per-thread state --------------------------------------------------------------------- */
+static __thread void *tls_stream = NULL;
+static __thread char tls_error[256] = "";
+
+static int fail(int err, const char *what)
+{
+    if (err != 0) {
+        snprintf(tls_error, sizeof(tls_error), "%s: %s", what, mcu_error_string(err));
+        static int warned = 0;
+        if (!warned) {
+            warned = 1;
+            fprintf(stderr, "mufft_b200: %s\n", tls_error);
+        }
+    }
+    return err;
+}
+#define TRY(expr) do { int e_ = (expr); if (e_ != 0) return fail(e_, #expr); } while (0)
+
+static int have_device(void)
+{
+    int count = 0;
+    if (mcu_device_count(&count) != 0 || count <= 0) {
+        snprintf(tls_error, sizeof(tls_error), "no usable CUDA device (this library has no CPU path)");
+        static int warned = 0;
+        if (!warned) {
+            warned = 1;
+            fprintf(stderr, "mufft_b200: %s\n", tls_error);
+        }
+        return 0;
+    }
+    return 1;
+}
+
+int mufft_cuda_device_count(void)
+{
+    int count = 0;
+    if (mcu_device_count(&count) != 0) return 0;
+    return count;
+}
+int mufft_cuda_set_device(int device) { return fail(mcu_set_device(device), "cudaSetDevice"); }
+void mufft_cuda_set_stream(void *stream) { tls_stream = stream; }
+void *mufft_cuda_get_stream(void) { return tls_stream; }
+int mufft_cuda_synchronize(void) { return fail(mcu_stream_sync(tls_stream), "cudaStreamSynchronize"); }
+const char *mufft_cuda_last_error(void) { return tls_error; }
+unsigned long long mufft_cuda_launch_count(int reset) { return mcu_launch_count(reset); }
+
+/* ---- memory (ref fft.c:1032-1084) ----------------------------------------------------------- */
+void *mufft_alloc(size_t size)
+{
+    void *ptr = NULL;
+    if (!have_device()) return NULL;
+    if (fail(mcu_malloc_managed(&ptr, size), "cudaMallocManaged") != 0) return NULL;
+    return ptr;
+}
+
+void *mufft_calloc(size_t size)
+{
+    void *ptr = mufft_alloc(size);
+    if (ptr != NULL) memset(ptr, 0, size);
+    return ptr;
+}
+
+void mufft_free(void *ptr)
+{
+    if (ptr != NULL) (void)mcu_free(ptr);
+}
+
+static int is_pow2_ge2(unsigned n) { return n >= 2 && (n & (n - 1)) == 0; }
+
+static int device_visible(int kind, size_t bytes)
+{
+    if (kind == MCU_MEM_DEVICE || kind == MCU_MEM_MANAGED) return 1;
+    return kind == MCU_MEM_PINNED && bytes <= ZERO_COPY_BYTES;
+}
+
+/* Upload a host array to a fresh device allocation. */
+static void *upload(const void *host, size_t bytes)
+{
+    void *dev = NULL;
+    if (fail(mcu_malloc(&dev, bytes), "cudaMalloc") != 0) return NULL;
+    if (fail(mcu_copy_async(dev, host, bytes, NULL), "cudaMemcpyAsync") != 0 ||
+        fail(mcu_stream_sync(NULL), "cudaStreamSynchronize") != 0) {
+        mcu_free(dev);
+        return NULL;
+    }
+    return dev;
+}
+
+/* ---- one transform axis: tables and the generic-pass schedule ---------------------------------- */
+typedef struct axis {
+    unsigned n;
+    int direction;
+    void *d_engine_tw; /* engine table, n <= MCU_ENGINE_MAX_N */
+    void *d_roots;     /* exp(dir*2*pi*i*j/n), j < n: generic multi-pass kernels */
+    unsigned nsteps;
+    unsigned radix[MAX_STEPS], span[MAX_STEPS];
+} axis;
+
+static void axis_free(axis *ax)
+{
+    mcu_free(ax->d_engine_tw);
+    mcu_free(ax->d_roots);
+    memset(ax, 0, sizeof(*ax));
+}
+
+/* want_generic: also build what the multi-pass kernels need. */
+static int axis_init(axis *ax, unsigned n, int direction, int want_generic)
+{
+    memset(ax, 0, sizeof(*ax));
+    ax->n = n;
+    ax->direction = direction;
+    if (n <= MCU_ENGINE_MAX_N) {
+        size_t entries = mcu_engine_table_size(n);
+        float *host = calloc(entries ? entries : 1, CPX);
+        if (!host) return -1;
+        mcu_engine_table_fill(host, n, direction);
+        ax->d_engine_tw = upload(host, (entries ? entries : 1) * CPX);
+        free(host);
+        if (!ax->d_engine_tw) return -1;
+    }
+    if (want_generic) {
+        /* Static radix-8/4/2 decomposition: widest radix first, the remainder last. */
+        unsigned rem = n, p = 1;
+        while (rem > 1) {
+            unsigned r = rem % 8 == 0 ? 8 : (rem % 4 == 0 ? 4 : 2);
+            ax->radix[ax->nsteps] = r;
+            ax->span[ax->nsteps] = p;
+            ax->nsteps++;
+            rem /= r;
+            p *= r;
+        }
+        float *host = malloc((size_t)n * CPX);
+        if (!host) return -1;
+        for (unsigned j = 0; j < n; j++) {
+            /* double precision, rounded once (ref fft.c:104-105) */
+            double phase = (M_PI * direction * 2.0 * (double)j) / (double)n;
+            host[2 * (size_t)j + 0] = (float)cos(phase);
+            host[2 * (size_t)j + 1] = (float)sin(phase);
+        }
+        ax->d_roots = upload(host, (size_t)n * CPX);
+        free(host);
+        if (!ax->d_roots) return -1;
+    }
+    return 0;
+}
+
+/* (0 + i*dir) * exp(i*pi*dir*k/n), k < n (ref fft.c:441-455). */
+static void *make_resolve_twiddles(int direction, unsigned n)
+{
+    float *host = malloc((size_t)n * CPX);
+    if (!host) return NULL;
+    for (unsigned k = 0; k < n; k++) {
+        double phase = (M_PI * direction * (double)k) / (double)n;
+        float c = (float)cos(phase), s = (float)sin(phase);
+        /* (0, dir) * (c, s) = (-dir*s, dir*c) */
+        host[2 * (size_t)k + 0] = -(float)direction * s;
+        host[2 * (size_t)k + 1] = (float)direction * c;
+    }
+    void *dev = upload(host, (size_t)n * CPX);
+    free(host);
+    return dev;
+}
+
+/* ---- scratch and staging owned by a plan -------------------------------------------------------- */
+typedef struct scratch {
+    void *buf[2];
+    size_t bytes;
+} scratch;
+
+static int scratch_reserve(scratch *s, size_t bytes)
+{
+    if (bytes <= s->bytes) return 0;
+    for (int i = 0; i < 2; i++) {
+        mcu_free(s->buf[i]);
+        s->buf[i] = NULL;
+    }
+    s->bytes = 0;
+    for (int i = 0; i < 2; i++) TRY(mcu_malloc(&s->buf[i], bytes));
+    s->bytes = bytes;
+    return 0;
+}
+
+static void scratch_free(scratch *s)
+{
+    mcu_free(s->buf[0]);
+    mcu_free(s->buf[1]);
+    memset(s, 0, sizeof(*s));
+}
+
+typedef struct stage_slot {
+    void *stream;
+    void *d_in, *d_in2, *d_out;
+    size_t in_bytes, in2_bytes, out_bytes;
+} stage_slot;
+
+typedef struct stage {
+    stage_slot slot[STAGE_SLOTS];
+    void *d_shared;
+    size_t shared_bytes;
+    void *ev_begin;
+    int ready;
+} stage;
+
+static int grow(void **ptr, size_t *have, size_t need)
+{
+    if (need <= *have) return 0;
+    mcu_free(*ptr);
+    *ptr = NULL;
+    *have = 0;
+    TRY(mcu_malloc(ptr, need));
+    *have = need;
+    return 0;
+}
+
+static int stage_init(stage *st)
+{
+    if (st->ready) return 0;
+    for (int i = 0; i < STAGE_SLOTS; i++) TRY(mcu_stream_create(&st->slot[i].stream));
+    TRY(mcu_event_create(&st->ev_begin));
+    st->ready = 1;
+    return 0;
+}
+
+static void stage_free(stage *st)
+{
+    for (int i = 0; i < STAGE_SLOTS; i++) {
+        mcu_stream_destroy(st->slot[i].stream);
+        mcu_free(st->slot[i].d_in);
+        mcu_free(st->slot[i].d_in2);
+        mcu_free(st->slot[i].d_out);
+    }
+    mcu_free(st->d_shared);
+    mcu_event_destroy(st->ev_begin);
+    memset(st, 0, sizeof(*st));
+}
+
+/* Runs `count` units on device-visible pointers; strides in bytes. */
+typedef int (*unit_launch)(void *ctx, void *out, size_t out_stride, const void *in, size_t in_stride,
+                           const void *in2, size_t in2_stride, size_t count, void *stream);
+
+typedef struct io_desc {
+    void *out;
+    const void *in, *in2;
+    size_t out_stride, in_stride, in2_stride; /* user strides in bytes (in2_stride 0 = shared operand) */
+    size_t out_unit, in_unit, in2_unit;       /* bytes actually touched per unit (tight device pitch) */
+    size_t count;
+} io_desc;
+
+static int copy_units(void *dst, size_t dpitch, const void *src, size_t spitch, size_t unit, size_t count, void *stream)
+{
+    if (dpitch == unit && spitch == unit) return mcu_copy_async(dst, src, unit * count, stream);
+    return mcu_copy2d_async(dst, dpitch, src, spitch, unit, count, stream);
+}
+
+/* Chunked, pipelined host<->device staging: slot s handles chunks s, s+SLOTS, ... on its own
+ * stream (copy in, kernels, copy out), so the copies of one chunk overlap the kernels and the
+ * opposite-direction copies of its neighbours. */
+static int run_any(stage *st, unit_launch fn, void *ctx, const io_desc *io, int async)
+{
+    if (io->count == 0) return 0;
+    const size_t span_in = io->in_stride * (io->count - 1) + io->in_unit;
+    const size_t span_out = io->out_stride * (io->count - 1) + io->out_unit;
+    const int vis_in = device_visible(mcu_pointer_kind(io->in), span_in);
+    const int vis_out = device_visible(mcu_pointer_kind(io->out), span_out);
+    int vis_in2 = 1;
+    if (io->in2) {
+        size_t span2 = io->in2_stride ? io->in2_stride * (io->count - 1) + io->in2_unit : io->in2_unit;
+        vis_in2 = device_visible(mcu_pointer_kind(io->in2), span2);
+    }
+
+    if (vis_in && vis_out && vis_in2) {
+        TRY(fn(ctx, io->out, io->out_stride, io->in, io->in_stride, io->in2, io->in2_stride, io->count, tls_stream));
+        if (!async) TRY(mcu_stream_sync(tls_stream));
+        return 0;
+    }
+    if (async) {
+        snprintf(tls_error, sizeof(tls_error), "asynchronous execute needs device-accessible (device or managed) pointers");
+        return -1;
+    }
+
+    TRY(stage_init(st));
+    /* Work already queued on the caller's stream may produce our device-side operands. */
+    TRY(mcu_event_record(st->ev_begin, tls_stream));
+    for (int s = 0; s < STAGE_SLOTS; s++) TRY(mcu_stream_wait_event(st->slot[s].stream, st->ev_begin));
+
+    const void *in2_dev = io->in2;
+    if (io->in2 && !vis_in2 && io->in2_stride == 0) {
+        TRY(grow(&st->d_shared, &st->shared_bytes, io->in2_unit));
+        TRY(mcu_copy_async(st->d_shared, io->in2, io->in2_unit, st->slot[0].stream));
+        TRY(mcu_stream_sync(st->slot[0].stream));
+        in2_dev = st->d_shared;
+    }
+
+    size_t biggest = io->in_unit > io->out_unit ? io->in_unit : io->out_unit;
+    size_t chunk = STAGE_CHUNK_BYTES / (biggest ? biggest : 1);
+    if (chunk == 0) chunk = 1;
+    /* keep every slot busy even for mid-sized jobs */
+    if (chunk * STAGE_SLOTS > io->count) chunk = (io->count + STAGE_SLOTS - 1) / STAGE_SLOTS;
+
+    size_t done = 0;
+    for (unsigned c = 0; done < io->count; c++) {
+        stage_slot *sl = &st->slot[c % STAGE_SLOTS];
+        const size_t cnt = io->count - done < chunk ? io->count - done : chunk;
+        const char *src = (const char *)io->in + done * io->in_stride;
+        char *dst = (char *)io->out + done * io->out_stride;
+        const void *d_in = src, *d_in2 = in2_dev;
+        void *d_out = dst;
+        size_t s_in = io->in_stride, s_out = io->out_stride, s_in2 = io->in2_stride;
+
+        if (!vis_in) {
+            TRY(grow(&sl->d_in, &sl->in_bytes, cnt * io->in_unit));
+            TRY(copy_units(sl->d_in, io->in_unit, src, io->in_stride, io->in_unit, cnt, sl->stream));
+            d_in = sl->d_in;
+            s_in = io->in_unit;
+        }
+        if (io->in2 && io->in2_stride != 0) {
+            const char *src2 = (const char *)io->in2 + done * io->in2_stride;
+            d_in2 = src2;
+            if (!vis_in2) {
+                TRY(grow(&sl->d_in2, &sl->in2_bytes, cnt * io->in2_unit));
+                TRY(copy_units(sl->d_in2, io->in2_unit, src2, io->in2_stride, io->in2_unit, cnt, sl->stream));
+                d_in2 = sl->d_in2;
+                s_in2 = io->in2_unit;
+            }
+        }
+        if (!vis_out) {
+            TRY(grow(&sl->d_out, &sl->out_bytes, cnt * io->out_unit));
+            d_out = sl->d_out;
+            s_out = io->out_unit;
+        }
+        TRY(fn(ctx, d_out, s_out, d_in, s_in, d_in2, s_in2, cnt, sl->stream));
+        if (!vis_out) TRY(copy_units(dst, io->out_stride, sl->d_out, io->out_unit, io->out_unit, cnt, sl->stream));
+        done += cnt;
+    }
+    for (int s = 0; s < STAGE_SLOTS; s++) TRY(mcu_stream_sync(st->slot[s].stream));
+    return 0;
+}
+
+/* ---- 1D plans (ref fft.c:54-66, 476-547, 626-662) ------------------------------------------------ */
+struct mufft_plan_1d {
+    unsigned n; /* complex transform length (N/2 for R2C / C2R) */
+    int kind;
+    int direction;
+    int zero_pad;
+    int use_engine;
+    axis ax;
+    void *d_rtw;
+    scratch scr;
+    stage st;
+};
+
+void mufft_free_plan_1d(mufft_plan_1d *plan)
+{
+    if (plan == NULL) return;
+    axis_free(&plan->ax);
+    mcu_free(plan->d_rtw);
+    scratch_free(&plan->scr);
+    stage_free(&plan->st);
+    free(plan);
+}
+
+mufft_plan_1d *mufft_create_plan_1d_c2c(unsigned N, int direction, unsigned flags)
+{
+    /* ref fft.c:628-631 rejects non powers of two and N == 1; N == 0 is rejected here too. */
+    if (!is_pow2_ge2(N)) return NULL;
+    if (direction != MUFFT_FORWARD && direction != MUFFT_INVERSE) return NULL;
+    if (!have_device()) return NULL;
+
+    mufft_plan_1d *plan = calloc(1, sizeof(*plan));
+    if (plan == NULL) return NULL;
+    plan->n = N;
+    plan->kind = KIND_C2C;
+    plan->direction = direction;
+    plan->zero_pad = (flags & MUFFT_FLAG_ZERO_PAD_UPPER_HALF) != 0;
+    plan->use_engine = N <= MCU_ENGINE_MAX_N;
+    if (axis_init(&plan->ax, N, direction, !plan->use_engine) != 0) {
+        mufft_free_plan_1d(plan);
+        return NULL;
+    }
+    return plan;
+}
+
+mufft_plan_1d *mufft_create_plan_1d_r2c(unsigned N, unsigned flags)
+{
+    if (!is_pow2_ge2(N)) return NULL;
+    mufft_plan_1d *plan = mufft_create_plan_1d_c2c(N / 2, MUFFT_FORWARD, flags); /* NULL for N == 2 */
+    if (plan == NULL) return NULL;
+    plan->kind = (flags & MUFFT_FLAG_FULL_R2C) ? KIND_R2C_FULL : KIND_R2C;
+    plan->d_rtw = make_resolve_twiddles(MUFFT_FORWARD, N / 2);
+    if (plan->d_rtw == NULL) {
+        mufft_free_plan_1d(plan);
+        return NULL;
+    }
+    return plan;
+}
+
+mufft_plan_1d *mufft_create_plan_1d_c2r(unsigned N, unsigned flags)
+{
+    if (!is_pow2_ge2(N)) return NULL;
+    mufft_plan_1d *plan = mufft_create_plan_1d_c2c(N / 2, MUFFT_INVERSE, flags);
+    if (plan == NULL) return NULL;
+    plan->kind = KIND_C2R;
+    plan->d_rtw = make_resolve_twiddles(MUFFT_INVERSE, N / 2);
+    if (plan->d_rtw == NULL) {
+        mufft_free_plan_1d(plan);
+        return NULL;
+    }
+    return plan;
+}
+
+int mufft_cuda_plan_1d_uses_engine(const mufft_plan_1d *plan) { return plan ? plan->use_engine : 0; }
+
+/* Row transforms on device-visible memory; strides in complex elements.  One fused kernel on
+ * the engine, or pre-resolve / passes / post-resolve through scratch beyond its limit. */
+static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode, int out_mode, float norm,
+                    void *out, size_t out_stride, const void *in, size_t in_stride,
+                    const void *in2, size_t in2_stride, size_t batch, void *stream)
+{
+    const unsigned n = ax->n;
+    if (n <= MCU_ENGINE_MAX_N) {
+        mcu_rows_args a;
+        memset(&a, 0, sizeof(a));
+        a.out = out; a.in = in; a.in2 = in2; a.tw = ax->d_engine_tw; a.rtw = d_rtw;
+        a.out_stride = out_stride; a.in_stride = in_stride; a.in2_stride = in2_stride;
+        a.batch = batch; a.n = n; a.direction = ax->direction;
+        a.in_mode = in_mode; a.out_mode = out_mode; a.norm = norm;
+        return mcu_launch_rows(&a, stream);
+    }
+
+    /* Generic path: bounded scratch, so walk the batch in chunks. */
+    size_t chunk = SCRATCH_CAP_BYTES / ((size_t)n * CPX);
+    if (chunk == 0) chunk = 1;
+    if (chunk > batch) chunk = batch;
+    TRY(scratch_reserve(scr, chunk * n * CPX));
+
+    for (size_t done = 0; done < batch; done += chunk) {
+        const size_t cnt = batch - done < chunk ? batch - done : chunk;
+        const char *src = (const char *)in + done * in_stride * CPX;
+        const char *src2 = in2 ? (const char *)in2 + done * in2_stride * CPX : NULL;
+        char *dst = (char *)out + done * out_stride * CPX;
+        const void *cur = src;
+        size_t cur_stride = in_stride;
+        int half = in_mode == MCU_IN_HALF;
+
+        if (in_mode == MCU_IN_C2R || in_mode == MCU_IN_MUL || in_mode == MCU_IN_MUL_C2R) {
+            mcu_resolve_args r;
+            memset(&r, 0, sizeof(r));
+            r.out = scr->buf[1]; r.in = src; r.in2 = src2; r.rtw = d_rtw;
+            r.out_stride = n; r.in_stride = in_stride; r.in2_stride = in2_stride; r.batch = cnt; r.n = n;
+            r.mode = in_mode == MCU_IN_C2R ? MCU_RES_C2R : (in_mode == MCU_IN_MUL ? MCU_RES_MUL : MCU_RES_MUL_C2R);
+            r.norm = norm;
+            TRY(mcu_launch_resolve(&r, stream));
+            cur = scr->buf[1];
+            cur_stride = n;
+        }
+        for (unsigned s = 0; s < ax->nsteps; s++) {
+            const int last = s + 1 == ax->nsteps;
+            mcu_pass_args p;
+            memset(&p, 0, sizeof(p));
+            p.in = cur; p.in_batch = cur_stride; p.in_stride = 1;
+            if (last && out_mode == MCU_OUT_COMPLEX) { p.out = dst; p.out_batch = out_stride; }
+            else { p.out = scr->buf[s & 1]; p.out_batch = n; }
+            p.out_stride = 1;
+            p.roots = ax->d_roots; p.batch = cnt; p.n = n; p.width = 1;
+            p.radix = ax->radix[s]; p.p = ax->span[s]; p.direction = ax->direction;
+            p.half = half && s == 0;
+            TRY(mcu_launch_pass(&p, stream));
+            cur = p.out;
+            cur_stride = p.out_batch;
+        }
+        if (out_mode != MCU_OUT_COMPLEX) {
+            mcu_resolve_args r;
+            memset(&r, 0, sizeof(r));
+            r.out = dst; r.in = cur; r.rtw = d_rtw;
+            r.out_stride = out_stride; r.in_stride = cur_stride; r.batch = cnt; r.n = n;
+            r.mode = out_mode == MCU_OUT_R2C_FULL ? MCU_RES_R2C_FULL : MCU_RES_R2C;
+            TRY(mcu_launch_resolve(&r, stream));
+        }
+    }
+    return 0;
+}
+
+typedef struct rows_ctx {
+    mufft_plan_1d *plan;
+    int in_mode, out_mode;
+    float norm;
+} rows_ctx;
+
+static int rows_unit_launch(void *ctx_, void *out, size_t out_stride, const void *in, size_t in_stride,
+                            const void *in2, size_t in2_stride, size_t count, void *stream)
+{
+    rows_ctx *ctx = ctx_;
+    mufft_plan_1d *plan = ctx->plan;
+    return run_rows(&plan->ax, &plan->scr, plan->d_rtw, ctx->in_mode, ctx->out_mode, ctx->norm,
+                    out, out_stride / CPX, in, in_stride / CPX, in2, in2_stride / CPX, count, stream);
+}
+
+static size_t in_unit_bytes(unsigned n, int in_mode)
+{
+    switch (in_mode) {
+    case MCU_IN_HALF: return (size_t)(n / 2) * CPX;
+    case MCU_IN_C2R:
+    case MCU_IN_MUL_C2R: return ((size_t)n + 1) * CPX;
+    default: return (size_t)n * CPX;
+    }
+}
+
+static size_t out_unit_bytes(unsigned n, int out_mode)
+{
+    switch (out_mode) {
+    case MCU_OUT_R2C: return ((size_t)n + 1) * CPX;
+    case MCU_OUT_R2C_FULL: return (size_t)n * 2 * CPX;
+    default: return (size_t)n * CPX;
+    }
+}
+
+static void plan_modes(const mufft_plan_1d *plan, int *in_mode, int *out_mode)
+{
+    *in_mode = plan->kind == KIND_C2R ? MCU_IN_C2R : (plan->zero_pad ? MCU_IN_HALF : MCU_IN_COMPLEX);
+    *out_mode = plan->kind == KIND_R2C ? MCU_OUT_R2C : (plan->kind == KIND_R2C_FULL ? MCU_OUT_R2C_FULL : MCU_OUT_COMPLEX);
+}
+
+static int exec_1d(mufft_plan_1d *plan, int in_mode, int out_mode, float norm,
+                   void *output, size_t out_stride, const void *input, size_t in_stride,
+                   const void *input2, size_t in2_stride, size_t in2_unit, size_t batch, int async)
+{
+    rows_ctx ctx = { plan, in_mode, out_mode, norm };
+    io_desc io;
+    memset(&io, 0, sizeof(io));
+    io.out = output; io.in = input; io.in2 = input2;
+    io.in_unit = in_unit_bytes(plan->n, in_mode);
+    io.out_unit = out_unit_bytes(plan->n, out_mode);
+    io.in2_unit = in2_unit;
+    io.in_stride = in_stride ? in_stride : io.in_unit;
+    io.out_stride = out_stride ? out_stride : io.out_unit;
+    io.in2_stride = in2_stride;
+    io.count = batch;
+    if ((io.in_stride | io.out_stride | io.in2_stride) % CPX != 0 ||
+        (((uintptr_t)output | (uintptr_t)input | (uintptr_t)input2) % CPX) != 0) {
+        snprintf(tls_error, sizeof(tls_error), "buffers and strides must be multiples of 8 bytes");
+        return -1;
+    }
+    return run_any(&plan->st, rows_unit_launch, &ctx, &io, async);
+}
+
+void mufft_execute_plan_1d(mufft_plan_1d *plan, void *MUFFT_RESTRICT output, const void *MUFFT_RESTRICT input)
+{
+    int in_mode, out_mode;
+    plan_modes(plan, &in_mode, &out_mode);
+    (void)exec_1d(plan, in_mode, out_mode, 1.0f, output, 0, input, 0, NULL, 0, 0, 1, 0);
+}
+
+int mufft_execute_plan_1d_batch(mufft_plan_1d *plan, void *output, const void *input, size_t batch,
+                                size_t output_stride_bytes, size_t input_stride_bytes)
+{
+    int in_mode, out_mode;
+    plan_modes(plan, &in_mode, &out_mode);
+    return exec_1d(plan, in_mode, out_mode, 1.0f, output, output_stride_bytes, input, input_stride_bytes, NULL, 0, 0, batch, 0);
+}
+
+int mufft_execute_plan_1d_batch_async(mufft_plan_1d *plan, void *output, const void *input, size_t batch,
+                                      size_t output_stride_bytes, size_t input_stride_bytes)
+{
+    int in_mode, out_mode;
+    plan_modes(plan, &in_mode, &out_mode);
+    return exec_1d(plan, in_mode, out_mode, 1.0f, output, output_stride_bytes, input, input_stride_bytes, NULL, 0, 0, batch, 1);
+}
+
+/* ---- convolution (ref fft.c:89-99, 565-624, 794-809) --------------------------------------------- */
+struct mufft_plan_conv {
+    mufft_plan_1d *plans[2];
+    mufft_plan_1d *output_plan;
+    size_t block_size;
+    float normalization;
+    unsigned n;
+    int stereo;
+};
+
+void mufft_free_plan_conv(mufft_plan_conv *plan)
+{
+    if (plan == NULL) return;
+    mufft_free_plan_1d(plan->plans[0]);
+    mufft_free_plan_1d(plan->plans[1]);
+    mufft_free_plan_1d(plan->output_plan);
+    free(plan);
+}
+
+mufft_plan_conv *mufft_create_plan_conv(unsigned N, unsigned flags, unsigned method)
+{
+    if (!is_pow2_ge2(N)) return NULL;
+    mufft_plan_conv *conv = calloc(1, sizeof(*conv));
+    if (conv == NULL) return NULL;
+
+    const unsigned zp0 = (method & MUFFT_CONV_METHOD_FLAG_ZERO_PAD_UPPER_HALF_FIRST) ? MUFFT_FLAG_ZERO_PAD_UPPER_HALF : 0;
+    const unsigned zp1 = (method & MUFFT_CONV_METHOD_FLAG_ZERO_PAD_UPPER_HALF_SECOND) ? MUFFT_FLAG_ZERO_PAD_UPPER_HALF : 0;
+    conv->n = N;
+    conv->stereo = (method & 1u) == MUFFT_CONV_METHOD_FLAG_STEREO_MONO;
+    if (conv->stereo) {
+        conv->block_size = (size_t)N * CPX;
+        conv->plans[0] = mufft_create_plan_1d_c2c(N, MUFFT_FORWARD, flags | zp0);
+        conv->plans[1] = mufft_create_plan_1d_r2c(N, flags | zp1 | MUFFT_FLAG_FULL_R2C);
+        conv->output_plan = mufft_create_plan_1d_c2c(N, MUFFT_INVERSE, flags & ~MUFFT_FLAG_ZERO_PAD_UPPER_HALF);
+    } else {
+        /* the reference pads the block so its SIMD multiply may overrun N/2+1 (fft.c:586) */
+        conv->block_size = ((size_t)N / 2 + MUFFT_PADDING_COMPLEX_SAMPLES) * CPX;
+        conv->plans[0] = mufft_create_plan_1d_r2c(N, flags | zp0);
+        conv->plans[1] = mufft_create_plan_1d_r2c(N, flags | zp1);
+        conv->output_plan = mufft_create_plan_1d_c2r(N, flags & ~MUFFT_FLAG_ZERO_PAD_UPPER_HALF);
+    }
+    conv->normalization = 1.0f / (float)N;
+    if (conv->plans[0] == NULL || conv->plans[1] == NULL || conv->output_plan == NULL) {
+        mufft_free_plan_conv(conv);
+        return NULL;
+    }
+    return conv;
+}
+
+size_t mufft_conv_get_transformed_block_size(mufft_plan_conv *plan) { return plan->block_size; }
+
+static int conv_input(mufft_plan_conv *plan, unsigned block, void *output, const void *input, size_t batch, int async)
+{
+    mufft_plan_1d *p = plan->plans[block & 1u];
+    int in_mode, out_mode;
+    plan_modes(p, &in_mode, &out_mode);
+    return exec_1d(p, in_mode, out_mode, 1.0f, output, plan->block_size, input, 0, NULL, 0, 0, batch, async);
+}
+
+static int conv_output(mufft_plan_conv *plan, void *output, const void *first, const void *second,
+                       size_t batch, size_t second_stride, int async)
+{
+    /* The spectral multiply and the 1/N happen in the load stage of the inverse transform. */
+    const int in_mode = plan->stereo ? MCU_IN_MUL : MCU_IN_MUL_C2R;
+    const size_t used = plan->stereo ? (size_t)plan->n * CPX : ((size_t)plan->n / 2 + 1) * CPX;
+    return exec_1d(plan->output_plan, in_mode, MCU_OUT_COMPLEX, plan->normalization,
+                   output, 0, first, plan->block_size, second, second_stride, used, batch, async);
+}
+
+void mufft_execute_conv_input(mufft_plan_conv *plan, unsigned block, void *output, const void *input)
+{
+    (void)conv_input(plan, block, output, input, 1, 0);
+}
+
+void mufft_execute_conv_output(mufft_plan_conv *plan, void *output, const void *input_first, const void *input_second)
+{
+    (void)conv_output(plan, output, input_first, input_second, 1, 0, 0);
+}
+
+int mufft_execute_conv_input_batch(mufft_plan_conv *plan, unsigned block, void *output, const void *input, size_t batch)
+{
+    return conv_input(plan, block, output, input, batch, 0);
+}
+int mufft_execute_conv_input_batch_async(mufft_plan_conv *plan, unsigned block, void *output, const void *input, size_t batch)
+{
+    return conv_input(plan, block, output, input, batch, 1);
+}
+int mufft_execute_conv_output_batch(mufft_plan_conv *plan, void *output, const void *input_first,
+                                    const void *input_second, size_t batch, size_t second_stride_bytes)
+{
+    return conv_output(plan, output, input_first, input_second, batch, second_stride_bytes, 0);
+}
+int mufft_execute_conv_output_batch_async(mufft_plan_conv *plan, void *output, const void *input_first,
+                                          const void *input_second, size_t batch, size_t second_stride_bytes)
+{
+    return conv_output(plan, output, input_first, input_second, batch, second_stride_bytes, 1);
+}
+
+/* Stand-alone spectral multiply (ref fft.h:201-207, kernel.c:22-34): runs the CUDA kernel on
+ * whatever memory it is given and synchronises. */
+static __thread stage tls_mul_stage;
+
+static int mul_unit_launch(void *ctx, void *out, size_t out_stride, const void *in, size_t in_stride,
+                           const void *in2, size_t in2_stride, size_t count, void *stream)
+{
+    (void)out_stride; (void)in_stride; (void)in2_stride; (void)count;
+    mcu_resolve_args r;
+    memset(&r, 0, sizeof(r));
+    r.out = out; r.in = in; r.in2 = in2; r.batch = 1;
+    r.n = *(unsigned *)ctx;
+    r.mode = MCU_RES_MUL;
+    r.norm = ((float *)ctx)[1];
+    return mcu_launch_resolve(&r, stream);
+}
+
+static void mufft_convolve_cuda(void *output, const void *a, const void *b, float normalization, unsigned samples)
+{
+    if (samples == 0) return;
+    union { unsigned u; float f; } ctx[2];
+    ctx[0].u = samples;
+    ctx[1].f = normalization;
+    io_desc io;
+    memset(&io, 0, sizeof(io));
+    io.out = output; io.in = a; io.in2 = b;
+    io.in_unit = io.out_unit = io.in2_unit = (size_t)samples * CPX;
+    io.in_stride = io.out_stride = io.in_unit;
+    io.in2_stride = io.in2_unit;
+    io.count = 1;
+    (void)run_any(&tls_mul_stage, mul_unit_launch, ctx, &io, 0);
+}
+
+mufft_convolve_func mufft_get_convolve_func(unsigned flags)
+{
+    (void)flags;
+    if (!have_device()) return NULL;
+    return mufft_convolve_cuda;
+}
+
+/* ---- 2D plans (ref fft.c:69-86, 664-792, 852-989) --------------------------------------------------- */
+struct mufft_plan_2d {
+    unsigned nx, ny; /* nx = complex row length (Nx/2 for R2C / C2R) */
+    int kind;
+    unsigned vertical_nx;
+    axis ax_x, ax_y;
+    void *d_rtw;
+    int cols_engine;
+    scratch scr_rows;   /* generic row passes */
+    scratch scr_cols;   /* generic column passes */
+    void *d_mid;        /* intermediate image(s) between the row and the column kernel */
+    size_t mid_bytes;
+    stage st;
+};
+
+void mufft_free_plan_2d(mufft_plan_2d *plan)
+{
+    if (plan == NULL) return;
+    axis_free(&plan->ax_x);
+    axis_free(&plan->ax_y);
+    mcu_free(plan->d_rtw);
+    scratch_free(&plan->scr_rows);
+    scratch_free(&plan->scr_cols);
+    mcu_free(plan->d_mid);
+    stage_free(&plan->st);
+    free(plan);
+}
+
+static mufft_plan_2d *plan_2d_common(unsigned nx, unsigned ny, int direction, int kind)
+{
+    if (!have_device()) return NULL;
+    mufft_plan_2d *plan = calloc(1, sizeof(*plan));
+    if (plan == NULL) return NULL;
+    plan->nx = nx;
+    plan->ny = ny;
+    plan->kind = kind;
+    plan->vertical_nx = nx;
+    plan->cols_engine = ny <= MCU_COLS_MAX_N;
+    if (axis_init(&plan->ax_x, nx, direction, nx > MCU_ENGINE_MAX_N) != 0 ||
+        axis_init(&plan->ax_y, ny, direction, !plan->cols_engine) != 0) {
+        mufft_free_plan_2d(plan);
+        return NULL;
+    }
+    return plan;
+}
+
+mufft_plan_2d *mufft_create_plan_2d_c2c(unsigned Nx, unsigned Ny, int direction, unsigned flags)
+{
+    (void)flags;
+    if (!is_pow2_ge2(Nx) || !is_pow2_ge2(Ny)) return NULL;
+    if (direction != MUFFT_FORWARD && direction != MUFFT_INVERSE) return NULL;
+    return plan_2d_common(Nx, Ny, direction, KIND_C2C);
+}
+
+mufft_plan_2d *mufft_create_plan_2d_r2c(unsigned Nx, unsigned Ny, unsigned flags)
+{
+    if (!is_pow2_ge2(Nx) || !is_pow2_ge2(Ny) || !is_pow2_ge2(Nx / 2)) return NULL;
+    const int full = (flags & MUFFT_FLAG_FULL_R2C) != 0;
+    mufft_plan_2d *plan = plan_2d_common(Nx / 2, Ny, MUFFT_FORWARD, full ? KIND_R2C_FULL : KIND_R2C);
+    if (plan == NULL) return NULL;
+    plan->vertical_nx = full ? Nx : Nx / 2 + 1; /* ref fft.c:738-746 */
+    plan->d_rtw = make_resolve_twiddles(MUFFT_FORWARD, Nx / 2);
+    if (plan->d_rtw == NULL) {
+        mufft_free_plan_2d(plan);
+        return NULL;
+    }
+    return plan;
+}
+
+mufft_plan_2d *mufft_create_plan_2d_c2r(unsigned Nx, unsigned Ny, unsigned flags)
+{
+    (void)flags;
+    if (!is_pow2_ge2(Nx) || !is_pow2_ge2(Ny) || !is_pow2_ge2(Nx / 2)) return NULL;
+    mufft_plan_2d *plan = plan_2d_common(Nx / 2, Ny, MUFFT_INVERSE, KIND_C2R);
+    if (plan == NULL) return NULL;
+    plan->vertical_nx = Nx / 2 + 1;
+    plan->d_rtw = make_resolve_twiddles(MUFFT_INVERSE, Nx / 2);
+    if (plan->d_rtw == NULL) {
+        mufft_free_plan_2d(plan);
+        return NULL;
+    }
+    return plan;
+}
+
+int mufft_cuda_plan_2d_paths(const mufft_plan_2d *plan)
+{
+    if (plan == NULL) return 0;
+    return (plan->nx <= MCU_ENGINE_MAX_N ? 1 : 0) | (plan->cols_engine ? 2 : 0);
+}
+
+/* Column transforms of `images` images on device-visible memory; pitches in complex elements. */
+static int run_cols(mufft_plan_2d *plan, void *out, size_t out_pitch, size_t out_image,
+                    const void *in, size_t in_pitch, size_t in_image, unsigned width, size_t images, void *stream)
+{
+    const axis *ax = &plan->ax_y;
+    if (plan->cols_engine) {
+        mcu_cols_args a;
+        memset(&a, 0, sizeof(a));
+        a.out = out; a.in = in; a.tw = ax->d_engine_tw;
+        a.out_pitch = out_pitch; a.in_pitch = in_pitch; a.out_image = out_image; a.in_image = in_image;
+        a.batch = images; a.n = ax->n; a.width = width; a.direction = ax->direction;
+        return mcu_launch_cols(&a, stream);
+    }
+    /* Generic vertical passes, image by image, ping-ponging through scratch of pitch `width`. */
+    TRY(scratch_reserve(&plan->scr_cols, (size_t)width * ax->n * CPX));
+    for (size_t img = 0; img < images; img++) {
+        const void *cur = (const char *)in + img * in_image * CPX;
+        size_t cur_pitch = in_pitch;
+        for (unsigned s = 0; s < ax->nsteps; s++) {
+            const int last = s + 1 == ax->nsteps;
+            mcu_pass_args p;
+            memset(&p, 0, sizeof(p));
+            p.in = cur; p.in_stride = cur_pitch;
+            if (last) { p.out = (char *)out + img * out_image * CPX; p.out_stride = out_pitch; }
+            else { p.out = plan->scr_cols.buf[s & 1]; p.out_stride = width; }
+            p.roots = ax->d_roots; p.batch = 1; p.n = ax->n; p.width = width;
+            p.radix = ax->radix[s]; p.p = ax->span[s]; p.direction = ax->direction;
+            TRY(mcu_launch_pass(&p, stream));
+            cur = p.out;
+            cur_pitch = p.out_stride;
+        }
+    }
+    return 0;
+}
+
+/* Whole 2D transforms of `images` tightly packed images on device-visible memory.  The
+ * intermediate between the row and the column kernel is plan-owned and sized for a small
+ * group of images, so that on B200 it is produced and consumed inside the 126 MB L2 instead
+ * of making a round trip through HBM. */
+#define MID_GROUP_BYTES ((size_t)48 << 20)
+
+static int run_2d_device(mufft_plan_2d *plan, void *out, const void *in, size_t images, void *stream)
+{
+    const unsigned nx = plan->nx, ny = plan->ny;
+    const int real_rows = plan->kind != KIND_C2C;
+    const size_t mid_pitch = real_rows ? 2 * (size_t)nx : nx; /* ref fft.c:920 doubles the pitch for R2C */
+    const size_t mid_image = mid_pitch * ny;                  /* complex elements */
+    size_t group = MID_GROUP_BYTES / (mid_image * CPX);
+    if (group == 0) group = 1;
+    if (group > images) group = images;
+    TRY(grow(&plan->d_mid, &plan->mid_bytes, group * mid_image * CPX));
+
+    for (size_t done = 0; done < images; done += group) {
+        const size_t cnt = images - done < group ? images - done : group;
+        if (plan->kind == KIND_C2R) {
+            /* columns first (ref fft.c:863-916): input pitch 2*nx, nx+1 columns carry data */
+            const char *src = (const char *)in + done * mid_image * CPX;
+            char *dst = (char *)out + done * (size_t)nx * ny * CPX;
+            TRY(run_cols(plan, plan->d_mid, mid_pitch, mid_image, src, mid_pitch, mid_image, nx + 1, cnt, stream));
+            /* rows: C2R resolve fused into the load, result dense (pitch nx complex = Nx floats) */
+            /* (the rows of all images of the group form one batch: image stride = ny rows) */
+            TRY(run_rows(&plan->ax_x, &plan->scr_rows, plan->d_rtw, MCU_IN_C2R, MCU_OUT_COMPLEX, 1.0f,
+                         dst, nx, plan->d_mid, mid_pitch, NULL, 0, cnt * ny, stream));
+        } else {
+            const size_t in_image = (size_t)nx * ny; /* complex elements (real rows: Nx floats = nx complex) */
+            const char *src = (const char *)in + done * in_image * CPX;
+            char *dst = (char *)out + done * mid_image * CPX;
+            const int out_mode = plan->kind == KIND_R2C ? MCU_OUT_R2C : (plan->kind == KIND_R2C_FULL ? MCU_OUT_R2C_FULL : MCU_OUT_COMPLEX);
+            TRY(run_rows(&plan->ax_x, &plan->scr_rows, plan->d_rtw, MCU_IN_COMPLEX, out_mode, 1.0f,
+                         plan->d_mid, mid_pitch, src, nx, NULL, 0, cnt * ny, stream));
+            TRY(run_cols(plan, dst, mid_pitch, mid_image, plan->d_mid, mid_pitch, mid_image, plan->vertical_nx, cnt, stream));
+        }
+    }
+    return 0;
+}
+
+static int image_unit_launch(void *ctx, void *out, size_t out_stride, const void *in, size_t in_stride,
+                             const void *in2, size_t in2_stride, size_t count, void *stream)
+{
+    (void)in2; (void)in2_stride; (void)out_stride; (void)in_stride; /* images are tightly packed */
+    return run_2d_device(ctx, out, in, count, stream);
+}
+
+static int exec_2d(mufft_plan_2d *plan, void *output, const void *input, size_t batch, int async)
+{
+    const size_t nx = plan->nx, ny = plan->ny;
+    io_desc io;
+    memset(&io, 0, sizeof(io));
+    io.out = output; io.in = input;
+    switch (plan->kind) {
+    case KIND_C2C: io.in_unit = io.out_unit = nx * ny * CPX; break;
+    case KIND_C2R: io.in_unit = 2 * nx * ny * CPX; io.out_unit = nx * ny * CPX; break;
+    default: io.in_unit = nx * ny * CPX; io.out_unit = 2 * nx * ny * CPX; break;
+    }
+    io.in_stride = io.in_unit;
+    io.out_stride = io.out_unit;
+    io.count = batch;
+    if ((((uintptr_t)output | (uintptr_t)input) % CPX) != 0) {
+        snprintf(tls_error, sizeof(tls_error), "buffers must be 8-byte aligned");
+        return -1;
+    }
+    return run_any(&plan->st, image_unit_launch, plan, &io, async);
+}
+
+void mufft_execute_plan_2d(mufft_plan_2d *plan, void *MUFFT_RESTRICT output, const void *MUFFT_RESTRICT input)
+{
+    (void)exec_2d(plan, output, input, 1, 0);
+}
+
+int mufft_execute_plan_2d_batch(mufft_plan_2d *plan, void *output, const void *input, size_t batch)
+{
+    return exec_2d(plan, output, input, batch, 0);
+}
+
+int mufft_execute_plan_2d_batch_async(mufft_plan_2d *plan, void *output, const void *input, size_t batch)
+{
+    return exec_2d(plan, output, input, batch, 1);
+}
