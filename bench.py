@@ -1,0 +1,483 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 muFFT hot path (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A step is one pass of the hot path over one batch of synthetic input.  The default workload is
+BASELINE.json configs[1]: batched 1D C2C forward, N=4096, batch 262144 PER GPU (weak scaling: the
+batch is sharded by transform, no collective on the data path).  Rank 0 prints ONE JSON line.
+
+  value     GFLOP/s (muFFT's 5*N*log2 N convention) with inputs resident in HBM, CUDA-event timed
+  e2e       the same metric through the host-pointer C ABI (mufft_execute_plan_1d_batch on pinned
+            host buffers): H2D and D2H copies are inside the timed region
+  roofline  algorithmic bytes (16*N per transform) / kernel time vs the measured HBM copy peak
+  cpu_baseline / --impl reference
+            the UNMODIFIED reference (oracle/_ref/ref_bench, all host cores, one plan per thread)
+            on a bounded sample of the same workload; falls back to the C oracle port when the
+            reference build is absent.  This is the only place oracle/ is executed by bench.py.
+"""
+import argparse
+import ctypes
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "batched FFT GFLOP/s (5N log2N)"
+UNIT = "GFLOP/s"
+
+# name -> (kind, N (Nx), Ny, units per GPU)
+WORKLOADS = {
+    "c2c4096": ("c2c", 4096, 0, 262144),
+    "r2c4096": ("r2c", 4096, 0, 262144),
+    "c2r4096": ("c2r", 4096, 0, 262144),
+    "conv8192": ("conv_stereo", 8192, 0, 65536),
+    "c2c2d1024": ("c2c2d", 1024, 1024, 256),
+    "c2c64": ("c2c", 64, 0, 1 << 24),
+}
+DESCRIPTION = {
+    "c2c4096": "batched 1D C2C forward N=4096, batch 262144 per GPU (BASELINE configs[1])",
+    "r2c4096": "batched 1D R2C N=4096, batch 262144 per GPU (BASELINE configs[1])",
+    "c2r4096": "batched 1D C2R N=4096, batch 262144 per GPU (BASELINE configs[1])",
+    "conv8192": "stereo fast convolution FFT N=8192, 65536 blocks per GPU, one filter (BASELINE configs[2])",
+    "c2c2d1024": "batched 2D C2C 1024x1024, batch 256 per GPU (BASELINE configs[3])",
+    "c2c64": "batched 1D C2C forward N=64, batch 2^24 per GPU (batched form of BASELINE configs[0])",
+}
+
+
+def flops_per_unit(kind, n, ny):
+    lg = math.log2(n)
+    if kind == "c2c2d":
+        return 5.0 * n * ny * (lg + math.log2(ny))
+    if kind == "conv_stereo":
+        return 2 * 5.0 * n * lg + 6.0 * n
+    if kind in ("r2c", "c2r"):
+        return 2.5 * n * lg  # bench.c:546,567 convention for real transforms
+    return 5.0 * n * lg
+
+
+def bytes_per_unit(kind, n, ny):
+    """Algorithmic HBM bytes per unit."""
+    if kind == "c2c":
+        return 16 * n
+    if kind in ("r2c", "c2r"):
+        return 4 * n + 8 * (n // 2 + 1)
+    if kind == "conv_stereo":
+        return 28 * n  # conv_input (4N in, 8N out) + conv_output (8N + 8N), filter spectrum amortised
+    if kind == "c2c2d":
+        return 16 * n * ny  # compulsory; the row->column intermediate is meant to stay in L2
+    raise ValueError(kind)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
+# ---- clocks sampler -----------------------------------------------------------------------------
+class Clocks:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.path = tempfile.mktemp(prefix="mufft_clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    mx.append(float(parts[1]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, parts[3:7]):
+                    if val == "Active":
+                        reasons.add(name)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---- CPU reference ---------------------------------------------------------------------------------
+REF_BENCH = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
+REF_MODE = {"c2c": "c2c", "r2c": "r2c_c2r", "c2r": "r2c_c2r", "conv_stereo": "conv_stereo", "c2c2d": "c2c2d"}
+
+
+def cpu_reference_sample(kind, n, ny, seconds_of_cpu_work):
+    """Times the reference CPU implementation on a bounded sample of the workload with every host
+    core (one plan + private buffers per thread, transforms not cache-hot: each thread walks its
+    own shard like the GPU walks the batch).  Returns the cpu_baseline object."""
+    cores = os.cpu_count() or 1
+    est_us = flops_per_unit(kind, n, ny) * (2 if kind in ("r2c", "c2r") else 1) / 15e3  # ~15 GFLOP/s per core, out of cache
+    est_us = max(est_us, 0.05)
+    if kind == "c2c2d":
+        per_thread = 4
+    else:
+        per_thread = max(16, min(1 << 16, (64 << 20) // (16 * n)))  # ~64 MiB of in+out per thread
+    batch = per_thread * cores
+    repeats = max(1, int(seconds_of_cpu_work * 1e6 / (est_us * batch)))
+    if os.path.exists(REF_BENCH):
+        res = subprocess.run([REF_BENCH, REF_MODE[kind], str(n), str(ny), str(batch), str(cores), str(repeats)],
+                             capture_output=True, text=True, check=True)
+        r = json.loads(res.stdout.strip().splitlines()[-1])
+        units_per_s = r["transforms_per_s"]
+        seconds = r["seconds"]
+        if kind in ("r2c", "c2r"):
+            # ref_bench times R2C+C2R pairs (bench.c:312-344): a pair is two real transforms
+            gflops = units_per_s * 2 * flops_per_unit(kind, n, ny) * 1e-9
+            units_per_s *= 2
+        else:
+            gflops = units_per_s * flops_per_unit(kind, n, ny) * 1e-9
+        return {"value": gflops, "unit": UNIT, "cores": cores, "kind": "reference",
+                "sample": f"oracle/_ref/ref_bench {REF_MODE[kind]}: {batch} units ({per_thread}/thread, private buffers) x {repeats} sweeps, {seconds:.2f} s wall",
+                "units_per_s": units_per_s, "seconds": seconds}
+    return cpu_oracle_sample(kind, n, ny, cores, per_thread, repeats)
+
+
+def cpu_oracle_sample(kind, n, ny, cores, per_thread, repeats):
+    """Fallback when oracle/_ref is absent: our C port (scalar) of the reference algorithm."""
+    import numpy as np
+    path = os.path.join(ROOT, "oracle", "libmufft_oracle.so")
+    if not os.path.exists(path):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True)
+    lib = ctypes.CDLL(path)
+    lib.oracle_create_plan_1d_c2c.restype = ctypes.c_void_p
+    lib.oracle_create_plan_1d_c2c.argtypes = [ctypes.c_uint, ctypes.c_int, ctypes.c_uint]
+    lib.oracle_execute_plan_1d_many.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_size_t] * 3
+    nn = n if kind != "c2c2d" else n  # the port baseline only models 1D complex passes of length n
+    times = [0.0] * cores
+
+    def work(t):
+        plan = lib.oracle_create_plan_1d_c2c(nn, -1, 0)
+        x = (np.random.default_rng(t).random((per_thread, 2 * nn), np.float32) - np.float32(0.5))
+        y = np.zeros_like(x)
+        t0 = time.perf_counter()
+        for _ in range(repeats):
+            lib.oracle_execute_plan_1d_many(plan, y.ctypes.data, x.ctypes.data, per_thread, 8 * nn, 8 * nn)
+        times[t] = time.perf_counter() - t0
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(cores)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    seconds = max(times)
+    units = per_thread * cores * repeats
+    scale = {"c2c": 1.0, "r2c": 0.5, "c2r": 0.5, "conv_stereo": 2.0, "c2c2d": float(max(ny, 1)) * 2}[kind]
+    units_per_s = units / seconds / scale
+    return {"value": units_per_s * flops_per_unit(kind, n, ny) * 1e-9, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"oracle port, {units} complex N={nn} transforms over {cores} threads, {seconds:.2f} s wall",
+            "units_per_s": units_per_s, "seconds": seconds}
+
+
+def run_reference_arm(args, rank):
+    kind, n, ny, units = WORKLOADS[args.workload]
+    if rank != 0:
+        return
+    vals = []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base = cpu_reference_sample(kind, n, ny, seconds_of_cpu_work=1.0 * (os.cpu_count() or 1))
+        if i >= args.warmup:
+            vals.append(base)
+    total_s = sum(v["seconds"] for v in vals)
+    value = sum(v["value"] * v["seconds"] for v in vals) / total_s
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_s / len(vals), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": DESCRIPTION[args.workload], "n": n, "ny": ny, "step": "bounded sample, see cpu_baseline.sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": base["cores"], "kind": base["kind"], "sample": base["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- GPU arm ---------------------------------------------------------------------------------------
+class Job:
+    """Device-resident buffers + the batched async C-ABI call for one workload."""
+
+    def __init__(self, m, torch, kind, n, ny, units, dev):
+        self.m, self.torch, self.kind, self.n, self.ny, self.units = m, torch, kind, n, ny, units
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1234 + dev.index)
+
+        def rnd(*shape):
+            out = torch.empty(*shape, dtype=torch.float32, device=dev)
+            step = max(1, shape[0] // 8)
+            for lo in range(0, shape[0], step):  # chunked to bound the temporary
+                out[lo:lo + step].uniform_(-0.5, 0.5, generator=gen)
+            return out
+
+        self.extra = []
+        if kind == "c2c":
+            self.plan = m.mufft_create_plan_1d_c2c(n, m.MUFFT_FORWARD, 0)
+            self.inp = rnd(units, 2 * n)
+            self.out = torch.empty_like(self.inp)
+            self.call = lambda o, i, cnt: m.mufft_execute_plan_1d_batch_async(self.plan, o, i, cnt, 0, 0)
+            self.call_sync = lambda o, i, cnt: m.mufft_execute_plan_1d_batch(self.plan, o, i, cnt, 0, 0)
+            self.free = lambda: m.mufft_free_plan_1d(self.plan)
+        elif kind == "r2c":
+            self.plan = m.mufft_create_plan_1d_r2c(n, 0)
+            self.inp = rnd(units, n)
+            self.out = torch.empty(units, 2 * (n // 2 + 1), dtype=torch.float32, device=dev)
+            self.call = lambda o, i, cnt: m.mufft_execute_plan_1d_batch_async(self.plan, o, i, cnt, 0, 0)
+            self.call_sync = lambda o, i, cnt: m.mufft_execute_plan_1d_batch(self.plan, o, i, cnt, 0, 0)
+            self.free = lambda: m.mufft_free_plan_1d(self.plan)
+        elif kind == "c2r":
+            self.plan = m.mufft_create_plan_1d_c2r(n, 0)
+            self.inp = rnd(units, 2 * (n // 2 + 1))
+            self.out = torch.empty(units, n, dtype=torch.float32, device=dev)
+            self.call = lambda o, i, cnt: m.mufft_execute_plan_1d_batch_async(self.plan, o, i, cnt, 0, 0)
+            self.call_sync = lambda o, i, cnt: m.mufft_execute_plan_1d_batch(self.plan, o, i, cnt, 0, 0)
+            self.free = lambda: m.mufft_free_plan_1d(self.plan)
+        elif kind == "conv_stereo":
+            method = (m.MUFFT_CONV_METHOD_FLAG_STEREO_MONO | m.MUFFT_CONV_METHOD_FLAG_ZERO_PAD_UPPER_HALF_FIRST |
+                      m.MUFFT_CONV_METHOD_FLAG_ZERO_PAD_UPPER_HALF_SECOND)
+            self.plan = m.mufft_create_plan_conv(n, 0, method)
+            blk = m.mufft_conv_get_transformed_block_size(self.plan) // 4
+            self.inp = rnd(units, n)                      # n/2 stereo samples per block, zero padded to n
+            filt = rnd(1, n // 2)
+            self.fspec = torch.empty(blk, dtype=torch.float32, device=dev)
+            self.spec = torch.empty(units, blk, dtype=torch.float32, device=dev)
+            self.out = torch.empty(units, 2 * n, dtype=torch.float32, device=dev)
+            assert m.mufft_execute_conv_input_batch(self.plan, 1, self.fspec.data_ptr(), filt.data_ptr(), 1) == 0
+
+            def call(o, i, cnt, sync=False):
+                f_in = m.mufft_execute_conv_input_batch if sync else m.mufft_execute_conv_input_batch_async
+                f_out = m.mufft_execute_conv_output_batch if sync else m.mufft_execute_conv_output_batch_async
+                return (f_in(self.plan, 0, self.spec.data_ptr(), i, cnt) or
+                        f_out(self.plan, o, self.spec.data_ptr(), self.fspec.data_ptr(), cnt, 0))
+            self.call = call
+            self.call_sync = lambda o, i, cnt: call(o, i, cnt, True)
+            self.free = lambda: m.mufft_free_plan_conv(self.plan)
+        elif kind == "c2c2d":
+            self.plan = m.mufft_create_plan_2d_c2c(n, ny, m.MUFFT_FORWARD, 0)
+            self.inp = rnd(units, ny * n * 2)
+            self.out = torch.empty_like(self.inp)
+            self.call = lambda o, i, cnt: m.mufft_execute_plan_2d_batch_async(self.plan, o, i, cnt)
+            self.call_sync = lambda o, i, cnt: m.mufft_execute_plan_2d_batch(self.plan, o, i, cnt)
+            self.free = lambda: m.mufft_free_plan_2d(self.plan)
+        else:
+            raise ValueError(kind)
+        if not self.plan:
+            raise RuntimeError("plan creation failed: " + m.mufft_cuda_last_error().decode())
+
+    def step(self):
+        err = self.call(self.out.data_ptr(), self.inp.data_ptr(), self.units)
+        if err:
+            raise RuntimeError("execute failed: " + self.m.mufft_cuda_last_error().decode())
+
+
+def time_steps(torch, dist, job, warmup, steps):
+    """CUDA-event timing on the launching stream; returns (total ms max over ranks, per-step ms list)."""
+    for _ in range(warmup):
+        job.step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+        torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for k in range(steps):
+        job.step()
+        ev[k + 1].record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    total = ev[0].elapsed_time(ev[steps])
+    per = [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]
+    if dist is not None:
+        t = torch.tensor([total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total = float(t.item())
+    return total, per
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2c4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--units", type=int, default=0, help="override units per GPU (debug; invalidates the headline)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--also", default="r2c4096,c2r4096,conv8192,c2c2d1024,c2c64",
+                    help="comma separated extra workloads reported under 'also' (N=1 only); '' disables")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the muFFT B200 library has no CPU path "
+                         "(use --impl reference for the CPU reference arm)")
+    import mufft_b200 as m
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    assert m.mufft_cuda_set_device(local) == 0
+    m.mufft_cuda_set_stream(torch.cuda.current_stream().cuda_stream or None)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist_mod.init_process_group("nccl", device_id=dev)
+        dist = dist_mod
+    n_gpus = world
+
+    kind, n, ny, units = WORKLOADS[args.workload]
+    if args.units:
+        units = args.units
+    job = Job(m, torch, kind, n, ny, units, dev)
+
+    clocks = Clocks(local) if rank == 0 else None
+    m.mufft_cuda_launch_count(1)
+    total_ms, per = time_steps(torch, dist, job, args.warmup, args.steps)
+    launches_total = m.mufft_cuda_launch_count(1)
+    launches = launches_total * args.steps // (args.steps + args.warmup)
+    clock_info = clocks.stop() if clocks else None
+
+    ms_per_step = total_ms / args.steps
+    fl, by = flops_per_unit(kind, n, ny), bytes_per_unit(kind, n, ny)
+    value = n_gpus * units * fl / (ms_per_step * 1e-3) * 1e-9
+    peak, peak_src = measured_peak()
+    # dominant kernel: at N<=8192 a step is one fused kernel launch (two for conv / 2D), so the
+    # kernel's mean duration is the step's event time divided by the launches it contains
+    achieved = units * by / (ms_per_step * 1e-3) * 1e-9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": units * by, "kernel_ms": ms_per_step,
+                "median_step_ms": sorted(per)[len(per) // 2], "min_step_ms": min(per)}
+
+    # ---- e2e: host-pointer C ABI, pinned host buffers, copies inside the timed region -----------
+    e2e = None
+    if not args.no_e2e:
+        host_in = torch.empty(job.inp.shape, dtype=torch.float32, pin_memory=True)
+        host_out = torch.empty(job.out.shape, dtype=torch.float32, pin_memory=True)
+        host_in.copy_(job.inp)
+        torch.cuda.synchronize()
+        e2e_steps = max(1, min(args.steps, 5))
+        for _ in range(1):
+            assert job.call_sync(host_out.data_ptr(), host_in.data_ptr(), units) == 0, m.mufft_cuda_last_error()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            assert job.call_sync(host_out.data_ptr(), host_in.data_ptr(), units) == 0
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        # result check of the host path against the device-resident path (same kernels, same input)
+        job.step()
+        torch.cuda.synchronize()
+        probe = slice(0, min(units, 64))
+        same = bool(torch.equal(host_out[probe].to(dev), job.out[probe]))
+        e2e = {"value": n_gpus * units * fl / (dt / e2e_steps) * 1e-9, "unit": UNIT,
+               "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
+               "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
+               "api": "mufft_execute_plan_1d_batch(host pinned in/out)" if kind in ("c2c", "r2c", "c2r") else "host-pointer batch API",
+               "matches_device_path": same}
+        del host_in, host_out
+
+    also = {}
+    job.free()
+    del job
+    torch.cuda.empty_cache()
+    if world == 1 and args.also and not args.units:
+        for name in [w for w in args.also.split(",") if w and w != args.workload]:
+            k2, n2, ny2, u2 = WORKLOADS[name]
+            j2 = Job(m, torch, k2, n2, ny2, u2, dev)
+            m.mufft_cuda_launch_count(1)
+            t_ms, per2 = time_steps(torch, None, j2, 3, 10)
+            l2 = m.mufft_cuda_launch_count(1) * 10 // 13
+            ms2 = t_ms / 10
+            also[name] = {"workload": DESCRIPTION[name], "gflops": u2 * flops_per_unit(k2, n2, ny2) / (ms2 * 1e-3) * 1e-9,
+                          "units_per_s": u2 / (ms2 * 1e-3), "ms_per_step": ms2,
+                          "hbm_gbs_algorithmic": u2 * bytes_per_unit(k2, n2, ny2) / (ms2 * 1e-3) * 1e-9,
+                          "roofline_frac": u2 * bytes_per_unit(k2, n2, ny2) / (ms2 * 1e-3) * 1e-9 / peak,
+                          "gpu_launches": l2}
+            j2.free()
+            del j2
+            torch.cuda.empty_cache()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_reference_sample(kind, n, ny, seconds_of_cpu_work=20.0)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": DESCRIPTION[args.workload], "n": n, "ny": ny, "units_per_gpu": units,
+                       "global_units": units * n_gpus, "parallelism": f"batch-sharded x{n_gpus}, no collective",
+                       "l2": "inputs+outputs per step (%.1f GiB per GPU) exceed the 126 MB L2; no flush needed" %
+                             (units * by / 2**30)},
+            "transforms_per_s": n_gpus * units / (ms_per_step * 1e-3),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clock_info, "also": also,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
