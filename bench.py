@@ -262,18 +262,22 @@ class Job:
             self.call_sync = lambda o, i, cnt: m.mufft_execute_plan_1d_batch(self.plan, o, i, cnt, 0, 0)
             self.free = lambda: m.mufft_free_plan_1d(self.plan)
         elif kind == "r2c":
+            # spectra rows: N/2+1 bins at a pitch of N/2+4 complex (16-byte aligned rows; the same
+            # padded pitch the CPU reference driver oracle/ref_bench.c uses)
+            pitch = 8 * (n // 2 + 4)
             self.plan = m.mufft_create_plan_1d_r2c(n, 0)
             self.inp = rnd(units, n)
-            self.out = torch.empty(units, 2 * (n // 2 + 1), dtype=torch.float32, device=dev)
-            self.call = lambda o, i, cnt: m.mufft_execute_plan_1d_batch_async(self.plan, o, i, cnt, 0, 0)
-            self.call_sync = lambda o, i, cnt: m.mufft_execute_plan_1d_batch(self.plan, o, i, cnt, 0, 0)
+            self.out = torch.empty(units, pitch // 4, dtype=torch.float32, device=dev)
+            self.call = lambda o, i, cnt: m.mufft_execute_plan_1d_batch_async(self.plan, o, i, cnt, pitch, 0)
+            self.call_sync = lambda o, i, cnt: m.mufft_execute_plan_1d_batch(self.plan, o, i, cnt, pitch, 0)
             self.free = lambda: m.mufft_free_plan_1d(self.plan)
         elif kind == "c2r":
+            pitch = 8 * (n // 2 + 4)
             self.plan = m.mufft_create_plan_1d_c2r(n, 0)
-            self.inp = rnd(units, 2 * (n // 2 + 1))
+            self.inp = rnd(units, pitch // 4)
             self.out = torch.empty(units, n, dtype=torch.float32, device=dev)
-            self.call = lambda o, i, cnt: m.mufft_execute_plan_1d_batch_async(self.plan, o, i, cnt, 0, 0)
-            self.call_sync = lambda o, i, cnt: m.mufft_execute_plan_1d_batch(self.plan, o, i, cnt, 0, 0)
+            self.call = lambda o, i, cnt: m.mufft_execute_plan_1d_batch_async(self.plan, o, i, cnt, 0, pitch)
+            self.call_sync = lambda o, i, cnt: m.mufft_execute_plan_1d_batch(self.plan, o, i, cnt, 0, pitch)
             self.free = lambda: m.mufft_free_plan_1d(self.plan)
         elif kind == "conv_stereo":
             method = (m.MUFFT_CONV_METHOD_FLAG_STEREO_MONO | m.MUFFT_CONV_METHOD_FLAG_ZERO_PAD_UPPER_HALF_FIRST |
@@ -370,6 +374,8 @@ def main():
     dev = torch.device("cuda", local)
     assert m.mufft_cuda_set_device(local) == 0
     m.mufft_cuda_set_stream(torch.cuda.current_stream().cuda_stream or None)
+    if os.environ.get("MUFFT_BENCH_FUSED_2D"):
+        m.mufft_cuda_set_fused_2d(int(os.environ["MUFFT_BENCH_FUSED_2D"]))
     dist = None
     if world > 1:
         import torch.distributed as dist_mod

@@ -65,6 +65,14 @@ int mufft_execute_conv_input_batch_async(mufft_plan_conv *plan, unsigned block, 
 int mufft_execute_conv_output_batch_async(mufft_plan_conv *plan, void *output, const void *input_first,
                                           const void *input_second, size_t batch, size_t second_stride_bytes);
 
+/* Row-transform kernel flavour: 0 = direct loads (default), 1 = persistent CTAs with bulk-copy
+ * prefetch into shared memory when the input rows are 16-byte aligned.  Same results either way. */
+void mufft_cuda_set_prefetch(int enable);
+/* 2D C2C transforms of 256..2048 points per side: 1 (default) = one persistent kernel does rows
+ * and columns of the whole batch with the intermediate kept in L2, 0 = separate row and column
+ * kernels per group of images (what every other 2D shape uses).  Same results either way. */
+void mufft_cuda_set_fused_2d(int enable);
+
 /* Introspection used by tests and the bench: which path a plan takes.
  * 1D: 1 = single-kernel shared-memory engine, 0 = multi-pass generic kernels.
  * 2D: bit 0 = rows on the engine, bit 1 = columns on the shared-memory column kernel. */

@@ -45,6 +45,7 @@ typedef struct mcu_rows_args {
     int direction;         /* -1 forward, +1 inverse */
     int in_mode, out_mode;
     float norm;
+    int prefetch;          /* 1 = use the persistent bulk-copy prefetch kernel when the input allows it */
 } mcu_rows_args;
 
 typedef struct mcu_cols_args {
@@ -60,6 +61,18 @@ typedef struct mcu_cols_args {
     unsigned width;        /* number of columns to transform */
     int direction;
 } mcu_cols_args;
+
+/* Fused 2D C2C kernel (fft2d_kernel.cuh): whole batch in one persistent launch. */
+typedef struct mcu_2d_args {
+    void *out;             /* [batch][ny][nx] complex; also holds the row-transformed intermediate */
+    const void *in;
+    const void *tw_x, *tw_y; /* engine twiddle tables of nx and ny */
+    unsigned *counters;    /* 1 + batch zero-initialised words: ticket counter, rows-done per image */
+    size_t out_image, in_image; /* complex elements between consecutive images */
+    size_t batch;
+    unsigned nx, ny;
+    int direction;
+} mcu_2d_args;
 
 /* Generic one-pass Stockham kernel (any length; used beyond the engine limits). */
 typedef struct mcu_pass_args {
@@ -126,6 +139,9 @@ int mcu_prefetch(const void *ptr, size_t bytes, int to_device, void *stream);
 int mcu_launch_rows(const mcu_rows_args *args, void *stream);
 int mcu_launch_cols(const mcu_cols_args *args, void *stream);
 int mcu_launch_pass(const mcu_pass_args *args, void *stream);
+/* 1 if the fused 2D kernel exists for this image shape */
+int mcu_2d_fused_supported(unsigned nx, unsigned ny);
+int mcu_launch_2d_fused(const mcu_2d_args *args, void *stream);
 int mcu_launch_resolve(const mcu_resolve_args *args, void *stream);
 /* number of complex entries of the engine twiddle table for length n, and its host fill */
 size_t mcu_engine_table_size(unsigned n);

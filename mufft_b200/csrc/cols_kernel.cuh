@@ -12,17 +12,20 @@
 
 namespace mufft {
 
-// Columns per tile: as many as keep the CTA at <= 512 threads, at most 16 (= 128-byte segments).
+// Columns per tile: as many as keep the CTA at <= 512 threads and its exchange area within
+// shared memory, at most 16 (= 128-byte row segments).
 __host__ __device__ constexpr int cols_tile(int n)
 {
     int t = n / engine_regs(n);
     int tc = 512 / t;
-    return tc > 16 ? 16 : (tc < 1 ? 1 : tc);
+    tc = tc > 16 ? 16 : (tc < 1 ? 1 : tc);
+    while (tc > 1 && (size_t)tc * engine_smem_elems(n) * sizeof(float2) > 160 * 1024) tc /= 2;
+    return tc;
 }
 __host__ __device__ constexpr int cols_cta_threads(int n) { return cols_tile(n) * (n / engine_regs(n)); }
 __host__ __device__ constexpr size_t cols_smem_bytes(int n)
 {
-    return (size_t)cols_tile(n) * (n + (n >> engine_pad_shift(n)) + 1) * sizeof(float2);
+    return (size_t)cols_tile(n) * engine_smem_elems(n) * sizeof(float2);
 }
 
 template <int N, int DIR>
@@ -31,7 +34,7 @@ __global__ void __launch_bounds__(cols_cta_threads(N)) fft_cols_kernel(const mcu
     constexpr int R = engine_regs(N);
     constexpr int T = N / R;
     constexpr int TC = cols_tile(N);
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const int tid = threadIdx.x;
     const int c = tid % TC;  // column inside the tile: fastest, so a warp reads whole row segments
@@ -49,7 +52,7 @@ __global__ void __launch_bounds__(cols_cta_threads(N)) fft_cols_kernel(const mcu
         for (int e = 0; e < R; e++)
             v[e] = active ? in[(size_t)(t + e * T) * a.in_pitch] : make_float2(0.0f, 0.0f);
 
-        engine_run<N, DIR, TC>(v, sm, tw, t);
+        engine_run<N, DIR, TC, cols_cta_threads(N), 1>(v, sm, tw, t, 0);
 
         if (active) {
 #pragma unroll

@@ -11,7 +11,7 @@
 #include <math.h>
 
 namespace mufft {
-#define MUFFT_DECLARE_ROWS(n) cudaError_t rows_launch_##n(const mcu_rows_args &, cudaStream_t);
+#define MUFFT_DECLARE_ROWS(n) cudaError_t rows_launch_##n##_fwd(const mcu_rows_args &, cudaStream_t); cudaError_t rows_launch_##n##_inv(const mcu_rows_args &, cudaStream_t);
 #define MUFFT_DECLARE_COLS(n) cudaError_t cols_launch_##n(const mcu_cols_args &, cudaStream_t);
 MUFFT_DECLARE_ROWS(2) MUFFT_DECLARE_ROWS(4) MUFFT_DECLARE_ROWS(8) MUFFT_DECLARE_ROWS(16)
 MUFFT_DECLARE_ROWS(32) MUFFT_DECLARE_ROWS(64) MUFFT_DECLARE_ROWS(128) MUFFT_DECLARE_ROWS(256)
@@ -20,6 +20,11 @@ MUFFT_DECLARE_ROWS(8192)
 MUFFT_DECLARE_COLS(2) MUFFT_DECLARE_COLS(4) MUFFT_DECLARE_COLS(8) MUFFT_DECLARE_COLS(16)
 MUFFT_DECLARE_COLS(32) MUFFT_DECLARE_COLS(64) MUFFT_DECLARE_COLS(128) MUFFT_DECLARE_COLS(256)
 MUFFT_DECLARE_COLS(512) MUFFT_DECLARE_COLS(1024) MUFFT_DECLARE_COLS(2048)
+
+#define MUFFT_F2D_SIZES(X, nx) X(nx, 256) X(nx, 512) X(nx, 1024) X(nx, 2048)
+#define MUFFT_F2D_SHAPES(X) MUFFT_F2D_SIZES(X, 256) MUFFT_F2D_SIZES(X, 512) MUFFT_F2D_SIZES(X, 1024) MUFFT_F2D_SIZES(X, 2048)
+#define MUFFT_DECLARE_F2D(pw, ph) cudaError_t f2d_launch_##pw##x##ph(const mcu_2d_args &, cudaStream_t);
+MUFFT_F2D_SHAPES(MUFFT_DECLARE_F2D)
 
 static std::atomic<unsigned long long> g_launches{0};
 
@@ -239,7 +244,7 @@ int mcu_launch_rows(const mcu_rows_args *a, void *stream)
     cudaStream_t s = (cudaStream_t)stream;
     g_launches.fetch_add(1, std::memory_order_relaxed);
     switch (a->n) {
-#define X(v) case v: return (int)rows_launch_##v(*a, s);
+#define X(v) case v: return (int)(a->direction < 0 ? rows_launch_##v##_fwd(*a, s) : rows_launch_##v##_inv(*a, s));
         MUFFT_FOR_ENGINE_SIZES(X)
 #undef X
     default: return (int)cudaErrorInvalidValue;
@@ -256,6 +261,23 @@ int mcu_launch_cols(const mcu_cols_args *a, void *stream)
 #undef X
     default: return (int)cudaErrorInvalidValue;
     }
+}
+
+int mcu_2d_fused_supported(unsigned nx, unsigned ny)
+{
+#define X(pw, ph) if (nx == pw && ny == ph) return 1;
+    MUFFT_F2D_SHAPES(X)
+#undef X
+    return 0;
+}
+
+int mcu_launch_2d_fused(const mcu_2d_args *a, void *stream)
+{
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+#define X(pw, ph) if (a->nx == pw && a->ny == ph) return (int)f2d_launch_##pw##x##ph(*a, (cudaStream_t)stream);
+    MUFFT_F2D_SHAPES(X)
+#undef X
+    return (int)cudaErrorInvalidValue;
 }
 
 int mcu_launch_pass(const mcu_pass_args *a, void *stream)

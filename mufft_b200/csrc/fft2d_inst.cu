@@ -1,0 +1,46 @@
+// One translation unit per image shape: compiled with -DF2D_NX=<nx> -DF2D_NY=<ny>.  Exposes
+// f2d_launch_<nx>x<ny>(args, stream) (both directions) to dispatch.cu.
+#include "fft2d_kernel.cuh"
+
+#if !defined(F2D_NX) || !defined(F2D_NY)
+#error "compile with -DF2D_NX=<nx> -DF2D_NY=<ny>"
+#endif
+
+#define MUFFT_CAT4_(a, b, c, d) a##b##c##d
+#define MUFFT_CAT4(a, b, c, d) MUFFT_CAT4_(a, b, c, d)
+
+namespace mufft {
+
+static_assert(f2d_supported(F2D_NX, F2D_NY), "shape not supported by the fused 2D kernel");
+
+template <int DIR>
+static cudaError_t launch_dir(const mcu_2d_args &a, cudaStream_t stream)
+{
+    static int ctas = 0; // per direction
+    auto kernel = fft2d_fused_kernel<F2D_NX, F2D_NY, DIR>;
+    constexpr size_t smem = f2d_smem_bytes(F2D_NX, F2D_NY);
+    if (ctas == 0) {
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        int dev = 0, sms = 0, per_sm = 0;
+        if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
+        if ((err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return err;
+        if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, MUFFT_F2D_THREADS, smem)) != cudaSuccess) return err;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        ctas = sms * per_sm;
+    }
+    if (a.batch == 0) return cudaSuccess;
+    const unsigned long long tickets = (unsigned long long)a.batch *
+        (F2D_NY / f2d_rows_per_tile(F2D_NX) + F2D_NX / f2d_cols_per_tile(F2D_NY));
+    if (tickets + (unsigned long long)ctas >= 0xffffffffull) return cudaErrorInvalidConfiguration;
+    const unsigned grid = tickets < (unsigned long long)ctas ? (unsigned)tickets : (unsigned)ctas;
+    kernel<<<grid, MUFFT_F2D_THREADS, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t MUFFT_CAT4(f2d_launch_, F2D_NX, x, F2D_NY)(const mcu_2d_args &a, cudaStream_t stream)
+{
+    return a.direction < 0 ? launch_dir<-1>(a, stream) : launch_dir<1>(a, stream);
+}
+
+} // namespace mufft

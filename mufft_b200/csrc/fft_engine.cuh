@@ -7,6 +7,12 @@
 // butterflies entirely in registers; between passes the values are exchanged through padded
 // shared memory (scatter to the Stockham output position, gather back at t + e*T).
 //
+// The shape table below picks R and the radix list per length.  The load/store pipe (LSU) is
+// the busiest unit of this kernel family on B200 (ncu: profiles/r01_rows4096_c2c_v0.txt), and
+// every exchange costs 16 bytes of shared-memory traffic per element, so shapes minimise the
+// number of passes: up to 64 values per thread and radix-64 butterflies (4096 = 64 x 64 is two
+// passes, one exchange).
+//
 // What this replaces in the reference: the chain of per-pass kernels of kernel.c:84-453 and
 // x86/kernel.h:216-667, each of which streams the whole array through memory
 // (fft.c:811-850).  Here a transform is read once and written once.
@@ -17,6 +23,8 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
+#include <utility>
 
 namespace mufft {
 
@@ -31,26 +39,82 @@ __device__ __forceinline__ cpx cmul(cpx a, cpx b)
 __device__ __forceinline__ cpx cconj(cpx a) { return make_float2(a.x, -a.y); }
 __device__ __forceinline__ cpx cscale(float s, cpx a) { return make_float2(a.x * s, a.y * s); }
 
+// Compile-time loop: f(std::integral_constant<int, I>) for I in [0, N).
+template <int N, typename F, int... I>
+__device__ __forceinline__ void static_for_impl(F &&f, std::integer_sequence<int, I...>)
+{
+    (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, typename F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    static_for_impl<N>(static_cast<F &&>(f), std::make_integer_sequence<int, N>{});
+}
+
 // ---- compile-time schedule ----------------------------------------------------------------
-// R (values per thread) and the radix list for a transform length.  Radix-R passes first, the
-// left-over small radix last: the first pass (p == 1) needs no twiddles, so it should be the
-// widest one.
-__host__ __device__ constexpr int engine_regs(int n)
+#define MUFFT_ENGINE_MAX_PASSES 4
+#ifndef MUFFT_ROWS_CTA_THREADS
+#define MUFFT_ROWS_CTA_THREADS 256
+#endif
+#ifndef MUFFT_ROWS_MIN_BLOCKS
+#define MUFFT_ROWS_MIN_BLOCKS 1
+#endif
+#ifndef MUFFT_SHAPE_R1
+#define MUFFT_SHAPE_R1 1
+#endif
+#ifndef MUFFT_SHAPE_R2
+#define MUFFT_SHAPE_R2 1
+#endif
+#ifndef MUFFT_SHAPE_R3
+#define MUFFT_SHAPE_R3 1
+#endif
+struct engine_shape_t {
+    int regs;   // R: complex values per thread
+    int passes;
+    int radix[MUFFT_ENGINE_MAX_PASSES];
+    int cta_threads; // row kernels: threads per CTA (several transforms share a CTA when N/R is smaller)
+    int min_blocks;  // row kernels: __launch_bounds__ minimum CTAs per SM
+};
+
+// Widest radix first: the first pass (p == 1) needs no twiddles.  Every radix divides R.
+// cta_threads / min_blocks are __launch_bounds__ of the row kernels: min_blocks is really a
+// register cap (65536 / (cta_threads * min_blocks) per thread) and decides how many CTAs share
+// an SM; the entries are the best of the sweeps in profiles/r01_shape_sweeps.txt.
+// -DMUFFT_SHAPE_N=<n> -DMUFFT_SHAPE_R=<R> -DMUFFT_SHAPE_R0=<r0> [-DMUFFT_SHAPE_R1=<r1> ...] overrides
+// one entry (used by tools/tune_shapes.sh to measure alternatives on the GPU).
+__host__ __device__ constexpr engine_shape_t engine_shape(int n)
 {
-    return n >= 256 ? 16 : (n >= 64 ? 8 : (n >= 16 ? 4 : 2));
+#ifdef MUFFT_SHAPE_N
+    if (n == MUFFT_SHAPE_N) {
+        constexpr int r[] = { MUFFT_SHAPE_R0, MUFFT_SHAPE_R1, MUFFT_SHAPE_R2, MUFFT_SHAPE_R3 };
+        int passes = 0, prod = 1;
+        while (prod < MUFFT_SHAPE_N) prod *= r[passes++];
+        return { MUFFT_SHAPE_R, passes, { r[0], r[1], r[2], r[3] }, MUFFT_ROWS_CTA_THREADS, MUFFT_ROWS_MIN_BLOCKS };
+    }
+#endif
+    switch (n) {
+    case 2: return { 2, 1, { 2, 1, 1, 1 } , 256, 1 };
+    case 4: return { 4, 1, { 4, 1, 1, 1 } , 256, 1 };
+    case 8: return { 4, 2, { 4, 2, 1, 1 } , 256, 1 };
+    case 16: return { 4, 2, { 4, 4, 1, 1 } , 256, 1 };
+    case 32: return { 4, 3, { 4, 4, 2, 1 } , 256, 1 };
+    case 64: return { 8, 2, { 8, 8, 1, 1 } , 256, 1 };
+    case 128: return { 8, 3, { 8, 8, 2, 1 } , 256, 1 };
+    case 256: return { 16, 2, { 16, 16, 1, 1 } , 256, 1 };
+    case 512: return { 16, 3, { 16, 16, 2, 1 } , 256, 1 };
+    case 1024: return { 32, 2, { 32, 32, 1, 1 }, 128, 1 };
+    case 2048: return { 32, 3, { 32, 32, 2, 1 }, 64, 1 };
+    case 4096: return { 16, 3, { 16, 16, 16, 1 }, 256, 3 };
+    case 8192: return { 32, 3, { 32, 16, 16, 1 }, 256, 2 };
+    default: return { 0, 0, { 1, 1, 1, 1 }, 256, 1 };
+    }
 }
-__host__ __device__ constexpr int engine_num_passes(int n)
-{
-    int r = engine_regs(n), rem = n, c = 0;
-    while (rem >= r) { rem /= r; c++; }
-    return c + (rem > 1 ? 1 : 0);
-}
-__host__ __device__ constexpr int engine_radix(int n, int pass)
-{
-    int r = engine_regs(n), rem = n;
-    for (int j = 0; j < pass; j++) rem /= r;
-    return rem >= r ? r : rem;
-}
+__host__ __device__ constexpr int engine_regs(int n) { return engine_shape(n).regs; }
+__host__ __device__ constexpr int engine_num_passes(int n) { return engine_shape(n).passes; }
+__host__ __device__ constexpr int engine_radix(int n, int pass) { return engine_shape(n).radix[pass]; }
+__host__ __device__ constexpr int engine_threads(int n) { return n / engine_regs(n); }
+__host__ __device__ constexpr int engine_cta_threads(int n) { return engine_shape(n).cta_threads; }
+__host__ __device__ constexpr int engine_min_blocks(int n) { return engine_shape(n).min_blocks; }
 __host__ __device__ constexpr int engine_span(int n, int pass)
 {
     int p = 1;
@@ -66,72 +130,138 @@ __host__ __device__ constexpr int engine_tw_offset(int n, int pass)
     return off;
 }
 __host__ __device__ constexpr int engine_tw_total(int n) { return engine_tw_offset(n, engine_num_passes(n)); }
-__host__ __device__ constexpr int engine_pad_shift(int n) { return engine_regs(n) >= 16 ? 4 : 3; }
-// Shared-memory footprint of one transform's exchange area, in cpx.
-__host__ __device__ constexpr int engine_smem_elems(int n)
+// One padding element after every 2^shift elements.  The first scatter writes with an element
+// stride of radix[0] across lanes, so the pad period is radix[0] (at least 8): lane l then hits
+// bank pair (radix[0] + 1) * l, distinct for 16 consecutive lanes.
+__host__ __device__ constexpr int engine_pad_shift(int n)
 {
-    return engine_num_passes(n) > 1 ? n + (n >> engine_pad_shift(n)) : 0;
+    int r = engine_radix(n, 0), s = 0;
+    while ((1 << s) < r) s++;
+    return s < 3 ? 3 : s;
 }
+// Shared-memory footprint of one transform's exchange area, in cpx.
+__host__ __device__ constexpr int engine_smem_elems(int n) { return n + (n >> engine_pad_shift(n)) + 1; }
 
 // ---- small DFTs in registers -----------------------------------------------------------------
-// v * exp(DIR*2*pi*i*J/16) for a compile-time J in [0, 8).
-template <int DIR, int J>
-__device__ __forceinline__ cpx mul_w16(cpx v)
+// cos(2*pi*j/64), j = 0..16
+constexpr float kCos64[17] = {
+    1.0f, 0.99518472667219693f, 0.98078528040323043f, 0.95694033573220882f, 0.92387953251128674f,
+    0.88192126434835505f, 0.83146961230254524f, 0.77301045336273699f, 0.70710678118654757f,
+    0.63439328416364549f, 0.55557023301960229f, 0.47139673682599781f, 0.38268343236508984f,
+    0.29028467725446233f, 0.19509032201612833f, 0.09801714032956077f, 0.0f };
+__host__ __device__ constexpr float cos64(int j)
 {
-    constexpr float H = 0.70710678118654752440f;
-    constexpr float C1 = 0.92387953251128675613f; // cos(pi/8)
-    constexpr float S1 = 0.38268343236508977173f; // sin(pi/8)
+    j &= 63;
+    return j <= 16 ? kCos64[j] : j <= 32 ? -kCos64[32 - j] : j <= 48 ? -kCos64[j - 32] : kCos64[64 - j];
+}
+__host__ __device__ constexpr float sin64(int j) { return cos64(j - 16); }
+
+// v * exp(DIR*2*pi*i*J/64) for a compile-time J.
+template <int DIR, int J64>
+__device__ __forceinline__ cpx mul_w64(cpx v)
+{
+    constexpr int J = ((J64 % 64) + 64) % 64;
     constexpr float D = (float)DIR;
+    constexpr float H = 0.70710678118654752440f;
     if constexpr (J == 0) return v;
-    else if constexpr (J == 4) return make_float2(-D * v.y, D * v.x);
-    else if constexpr (J == 2) return make_float2(H * (v.x - D * v.y), H * (v.y + D * v.x));
-    else if constexpr (J == 6) return make_float2(-H * (v.x + D * v.y), H * (D * v.x - v.y));
+    else if constexpr (J == 16) return make_float2(-D * v.y, D * v.x);
+    else if constexpr (J == 32) return make_float2(-v.x, -v.y);
+    else if constexpr (J == 48) return make_float2(D * v.y, -D * v.x);
+    else if constexpr (J == 8) return make_float2(H * (v.x - D * v.y), H * (v.y + D * v.x));
+    else if constexpr (J == 24) return make_float2(-H * (v.x + D * v.y), H * (D * v.x - v.y));
+    else if constexpr (J == 40) return make_float2(-H * (v.x - D * v.y), -H * (v.y + D * v.x));
+    else if constexpr (J == 56) return make_float2(H * (v.x + D * v.y), -H * (D * v.x - v.y));
     else {
-        constexpr float c = (J == 1) ? C1 : (J == 3) ? S1 : (J == 5) ? -S1 : -C1;
-        constexpr float s = D * ((J == 1 || J == 7) ? S1 : C1);
+        constexpr float c = cos64(J);
+        constexpr float s = D * sin64(J);
         return make_float2(fmaf(v.x, c, -(v.y * s)), fmaf(v.x, s, v.y * c));
     }
 }
 
-// One radix-2 Stockham stage inside the register file: span P, transform length R.
-template <int R, int P, int DIR, int I>
-struct RegStage {
-    static __device__ __forceinline__ void run(cpx (&out)[R], const cpx (&in)[R])
+// Natural-order in, natural-order out DFT of R in {2,4,8,16,32,64} register values:
+// X[k] = sum_n x[n] exp(DIR*2*pi*i*n*k/R).  Composite sizes use the Cooley-Tukey split R = A*B
+// with n = n1 + A*n2, k = B*k1 + k2: B-point DFTs over the stride-A subsequences, constant
+// twiddles exp(DIR*2*pi*i*n1*k2/R), then A-point DFTs across n1.
+template <int R, int DIR>
+struct RegDft;
+
+template <int DIR>
+struct RegDft<2, DIR> {
+    static __device__ __forceinline__ void run(cpx (&x)[2])
     {
-        constexpr int k = I & (P - 1);
-        constexpr int J = k * (8 / P); // exp(DIR*2*pi*i*k/(2P)) on the 16th-root grid (P <= 8)
-        const cpx a = in[I];
-        const cpx b = mul_w16<DIR, J>(in[I + R / 2]);
-        out[(I - k) * 2 + k] = cadd(a, b);
-        out[(I - k) * 2 + k + P] = csub(a, b);
-        if constexpr (I + 1 < R / 2) RegStage<R, P, DIR, I + 1>::run(out, in);
+        const cpx a = x[0], b = x[1];
+        x[0] = cadd(a, b);
+        x[1] = csub(a, b);
     }
 };
 
-// Natural-order in, natural-order out DFT of R in {2,4,8,16} register values.
+template <int DIR>
+struct RegDft<4, DIR> {
+    static __device__ __forceinline__ void run(cpx (&x)[4])
+    {
+        const cpx t0 = cadd(x[0], x[2]), t1 = csub(x[0], x[2]);
+        const cpx t2 = cadd(x[1], x[3]), t3 = mul_w64<DIR, 16>(csub(x[1], x[3]));
+        x[0] = cadd(t0, t2);
+        x[1] = cadd(t1, t3);
+        x[2] = csub(t0, t2);
+        x[3] = csub(t1, t3);
+    }
+};
+
+__host__ __device__ constexpr int dft_split_a(int r) { return r == 8 ? 2 : r == 16 ? 4 : r == 32 ? 4 : 8; }
+
 template <int R, int DIR>
-__device__ __forceinline__ void dft_regs(cpx (&v)[R])
+struct RegDft {
+    static __device__ __forceinline__ void run(cpx (&x)[R])
+    {
+        constexpr int A = dft_split_a(R), B = R / A;
+        static_assert(A * B == R && R <= 64, "register DFT sizes are 2..64");
+        static_for<A>([&](auto n1c) {
+            constexpr int n1 = decltype(n1c)::value;
+            cpx s[B];
+            static_for<B>([&](auto n2c) { constexpr int n2 = decltype(n2c)::value; s[n2] = x[n1 + A * n2]; });
+            RegDft<B, DIR>::run(s);
+            static_for<B>([&](auto k2c) {
+                constexpr int k2 = decltype(k2c)::value;
+                x[n1 + A * k2] = mul_w64<DIR, n1 * k2 * (64 / R)>(s[k2]);
+            });
+        });
+        static_for<B>([&](auto k2c) {
+            constexpr int k2 = decltype(k2c)::value;
+            cpx s[A];
+            static_for<A>([&](auto n1c) { constexpr int n1 = decltype(n1c)::value; s[n1] = x[n1 + A * k2]; });
+            RegDft<A, DIR>::run(s);
+            static_for<A>([&](auto k1c) { constexpr int k1 = decltype(k1c)::value; x[n1_slot<A, B>(k1, k2)] = s[k1]; });
+        });
+        // The second stage left X[B*k1 + k2] in slot k1 + A*k2; put it in natural order.
+        if constexpr (A != 1 && B != 1) {
+            cpx y[R];
+            static_for<R>([&](auto ic) { constexpr int i = decltype(ic)::value; y[i] = x[i]; });
+            static_for<A>([&](auto k1c) {
+                constexpr int k1 = decltype(k1c)::value;
+                static_for<B>([&](auto k2c) { constexpr int k2 = decltype(k2c)::value; x[B * k1 + k2] = y[k1 + A * k2]; });
+            });
+        }
+    }
+    template <int A_, int B_>
+    static __host__ __device__ constexpr int n1_slot(int k1, int k2) { return k1 + A_ * k2; }
+};
+
+template <int R, int DIR>
+__device__ __forceinline__ void dft_regs(cpx (&v)[R]) { RegDft<R, DIR>::run(v); }
+
+// ---- synchronisation of the threads of one transform ---------------------------------------
+// T threads share a transform.  T <= 32: they sit in one warp.  Otherwise a named barrier
+// (id 1 + slot) when the CTA holds several transforms, or the CTA barrier when it holds one.
+template <int T, int SLOTS>
+__device__ __forceinline__ void engine_sync(int slot)
 {
-    cpx w[R];
-    if constexpr (R == 2) {
-        RegStage<2, 1, DIR, 0>::run(w, v);
-#pragma unroll
-        for (int i = 0; i < 2; i++) v[i] = w[i];
-    } else if constexpr (R == 4) {
-        RegStage<4, 1, DIR, 0>::run(w, v);
-        RegStage<4, 2, DIR, 0>::run(v, w);
-    } else if constexpr (R == 8) {
-        RegStage<8, 1, DIR, 0>::run(w, v);
-        RegStage<8, 2, DIR, 0>::run(v, w);
-        RegStage<8, 4, DIR, 0>::run(w, v);
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = w[i];
+    if constexpr (T <= 32) {
+        __syncwarp();
+    } else if constexpr (SLOTS == 1) {
+        __syncthreads();
     } else {
-        static_assert(R == 16, "register DFT sizes are 2, 4, 8, 16");
-        RegStage<16, 1, DIR, 0>::run(w, v);
-        RegStage<16, 2, DIR, 0>::run(v, w);
-        RegStage<16, 4, DIR, 0>::run(w, v);
-        RegStage<16, 8, DIR, 0>::run(v, w);
+        asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(T) : "memory");
     }
 }
 
@@ -150,6 +280,7 @@ __device__ __forceinline__ void engine_butterflies(cpx (&v)[engine_regs(N)], con
     constexpr int r = engine_radix(N, PASS);
     constexpr int p = engine_span(N, PASS);
     constexpr int NB = R / r;
+    static_assert(NB * r == R, "every pass radix must divide the values per thread");
 #pragma unroll
     for (int u = 0; u < NB; u++) {
         cpx x[r];
@@ -212,18 +343,19 @@ __device__ __forceinline__ void engine_scatter_natural(const cpx (&v)[engine_reg
     for (int e = 0; e < R; e++) sm[pad_pos<SH>(t + e * T) * CS] = v[e];
 }
 
-// All passes of an N-point transform.  Every thread of the CTA must call this (it contains
-// __syncthreads()); `sm` may be anything when the transform has a single pass.
-template <int N, int DIR, int CS, int PASS = 0>
-__device__ __forceinline__ void engine_run(cpx (&v)[engine_regs(N)], cpx *sm, const cpx *__restrict__ tw, int t)
+// All passes of an N-point transform.  Every thread of the transform must call this (it
+// synchronises them); SYNC_T / SLOTS say how (see engine_sync): the row kernel passes the
+// threads of one transform, the column kernel passes the whole CTA.
+template <int N, int DIR, int CS, int SYNC_T, int SLOTS, int PASS = 0>
+__device__ __forceinline__ void engine_run(cpx (&v)[engine_regs(N)], cpx *sm, const cpx *__restrict__ tw, int t, int slot)
 {
     engine_butterflies<N, DIR, PASS>(v, tw, t);
     if constexpr (PASS + 1 < engine_num_passes(N)) {
-        if constexpr (PASS > 0) __syncthreads(); // previous gather must be complete (WAR)
+        if constexpr (PASS > 0) engine_sync<SYNC_T, SLOTS>(slot); // previous gather must be complete (WAR)
         engine_scatter<N, PASS, CS>(v, sm, t);
-        __syncthreads();
+        engine_sync<SYNC_T, SLOTS>(slot);
         engine_gather<N, CS>(v, sm, t);
-        engine_run<N, DIR, CS, PASS + 1>(v, sm, tw, t);
+        engine_run<N, DIR, CS, SYNC_T, SLOTS, PASS + 1>(v, sm, tw, t, slot);
     }
 }
 

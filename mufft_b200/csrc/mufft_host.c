@@ -40,6 +40,23 @@ enum { KIND_C2C = 0, KIND_R2C = 1, KIND_R2C_FULL = 2, KIND_C2R = 3 };
 #define ZERO_COPY_BYTES ((size_t)64 << 10)   /* pinned buffers up to this size are used in place */
 #define MAX_STEPS 32
 
+/* Row transforms have two kernels (rows_kernel.cuh): direct loads, and persistent CTAs whose
+ * inputs are prefetched into shared memory by bulk async copies.  0 = direct (default: it is the
+ * faster one at the tuned occupancies, profiles/r01_shape_sweeps.txt), 1 = prefetch whenever the
+ * input rows are 16-byte aligned.  MUFFT_CUDA_PREFETCH in the environment sets the initial value,
+ * mufft_cuda_set_prefetch() changes it. */
+static int g_prefetch = 0;
+__attribute__((constructor)) static void read_env(void)
+{
+    const char *e = getenv("MUFFT_CUDA_PREFETCH");
+    if (e != NULL) g_prefetch = e[0] == '1';
+}
+void mufft_cuda_set_prefetch(int enable) { g_prefetch = enable != 0; }
+/* 2D C2C: 1 (default) = the fused persistent kernel when the shape has one, 0 = row kernel +
+ * column kernel per group of images (the path every other shape and R2C/C2R take). */
+static int g_fused_2d = 1;
+void mufft_cuda_set_fused_2d(int enable) { g_fused_2d = enable != 0; }
+
 /* ---- per-thread state --------------------------------------------------------------------- */
 static __thread void *tls_stream = NULL;
 static __thread char tls_error[256] = "";
@@ -466,6 +483,7 @@ static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode
         a.out_stride = out_stride; a.in_stride = in_stride; a.in2_stride = in2_stride;
         a.batch = batch; a.n = n; a.direction = ax->direction;
         a.in_mode = in_mode; a.out_mode = out_mode; a.norm = norm;
+        a.prefetch = g_prefetch;
         return mcu_launch_rows(&a, stream);
     }
 
@@ -758,6 +776,8 @@ struct mufft_plan_2d {
     scratch scr_cols;   /* generic column passes */
     void *d_mid;        /* intermediate image(s) between the row and the column kernel */
     size_t mid_bytes;
+    void *d_counters;   /* fused kernel: ticket counter + rows-done counter per image */
+    size_t counters_bytes;
     stage st;
 };
 
@@ -770,6 +790,7 @@ void mufft_free_plan_2d(mufft_plan_2d *plan)
     scratch_free(&plan->scr_rows);
     scratch_free(&plan->scr_cols);
     mcu_free(plan->d_mid);
+    mcu_free(plan->d_counters);
     stage_free(&plan->st);
     free(plan);
 }
@@ -880,6 +901,17 @@ static int run_cols(mufft_plan_2d *plan, void *out, size_t out_pitch, size_t out
 static int run_2d_device(mufft_plan_2d *plan, void *out, const void *in, size_t images, void *stream)
 {
     const unsigned nx = plan->nx, ny = plan->ny;
+    if (plan->kind == KIND_C2C && g_fused_2d && mcu_2d_fused_supported(nx, ny)) {
+        /* one persistent launch for the whole batch; the row->column intermediate lives in `out` */
+        mcu_2d_args f;
+        memset(&f, 0, sizeof(f));
+        TRY(grow(&plan->d_counters, &plan->counters_bytes, (images + 1) * sizeof(unsigned)));
+        TRY(mcu_memset(plan->d_counters, 0, (images + 1) * sizeof(unsigned), stream));
+        f.out = out; f.in = in; f.tw_x = plan->ax_x.d_engine_tw; f.tw_y = plan->ax_y.d_engine_tw;
+        f.counters = plan->d_counters; f.out_image = (size_t)nx * ny; f.in_image = (size_t)nx * ny;
+        f.batch = images; f.nx = nx; f.ny = ny; f.direction = plan->ax_x.direction;
+        return mcu_launch_2d_fused(&f, stream);
+    }
     const int real_rows = plan->kind != KIND_C2C;
     const size_t mid_pitch = real_rows ? 2 * (size_t)nx : nx; /* ref fft.c:920 doubles the pitch for R2C */
     const size_t mid_image = mid_pitch * ny;                  /* complex elements */

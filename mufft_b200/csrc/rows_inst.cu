@@ -1,37 +1,93 @@
-// One translation unit per transform length (compiled with -DROWS_N=<n>) so that the 13 sizes
-// build in parallel.  Exposes rows_launch_<n>(args, stream) to dispatch.cu.
+// One translation unit per (transform length, direction): compiled with -DROWS_N=<n> -DROWS_DIR=<-1|1>
+// so that the sizes build in parallel.  Exposes rows_launch_<n>_{fwd,inv}(args, stream) to dispatch.cu.
+//
+// Every (input mode, output mode) pair the host layer can ask for is a separate kernel
+// instantiation, in two flavours: direct loads (any 8-byte aligned input) and the persistent
+// bulk-copy prefetch kernel (16-byte aligned inputs, see rows_kernel.cuh).
 #include "rows_kernel.cuh"
 
-#ifndef ROWS_N
-#error "compile with -DROWS_N=<power of two between 2 and 8192>"
+#if !defined(ROWS_N) || !defined(ROWS_DIR)
+#error "compile with -DROWS_N=<power of two between 2 and 8192> -DROWS_DIR=<-1 or 1>"
 #endif
 
-#define MUFFT_CAT_(a, b) a##b
-#define MUFFT_CAT(a, b) MUFFT_CAT_(a, b)
+#define MUFFT_CAT_(a, b, c) a##b##c
+#define MUFFT_CAT(a, b, c) MUFFT_CAT_(a, b, c)
 
 namespace mufft {
 
-template <int DIR>
-static cudaError_t launch_dir(const mcu_rows_args &a, cudaStream_t stream)
+static int g_sm_count = 0;
+
+template <int IN_MODE, int OUT_MODE>
+static cudaError_t launch_mode(const mcu_rows_args &a, cudaStream_t stream)
 {
     constexpr int N = ROWS_N;
-    static bool configured = false; // per direction; the attribute call is idempotent, so a race is harmless
-    auto kernel = fft_rows_kernel<N, DIR>;
+    constexpr int DIR = ROWS_DIR;
+    constexpr int TPC = rows_per_cta(N);
+    const size_t groups = (a.batch + TPC - 1) / TPC;
+    if (groups == 0) return cudaSuccess;
+
+    if constexpr (rows_tma_supported(N, IN_MODE)) {
+        // whole 16-byte chunks from 16-byte aligned rows; C2R rows are read 2 elements beyond bin N/2
+        const bool aligned = ((uintptr_t)a.in % 16 == 0) && ((a.in_stride * sizeof(float2)) % 16 == 0) &&
+                             a.in_stride * sizeof(float2) >= (size_t)rows_land_bytes(N, IN_MODE);
+        if (aligned && a.prefetch) {
+            static int blocks_per_sm = 0; // per instantiation
+            auto kernel = fft_rows_tma_kernel<N, DIR, IN_MODE, OUT_MODE>;
+            constexpr size_t smem = rows_tma_smem_bytes(N, IN_MODE);
+            if (blocks_per_sm == 0) {
+                cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (err != cudaSuccess) return err;
+                int dev = 0, per_sm = 0;
+                if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
+                if ((err = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return err;
+                if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, rows_cta_threads(N), smem)) != cudaSuccess) return err;
+                if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+                blocks_per_sm = per_sm;
+            }
+            size_t ctas = (size_t)g_sm_count * blocks_per_sm;
+            if (ctas > groups) ctas = groups;
+            kernel<<<(unsigned)ctas, rows_cta_threads(N), smem, stream>>>(a);
+            return cudaGetLastError();
+        }
+    }
+    static bool configured = false; // the attribute call is idempotent, so a race is harmless
+    auto kernel = fft_rows_kernel<N, DIR, IN_MODE, OUT_MODE>;
     if (!configured) {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem_bytes(N));
         if (err != cudaSuccess) return err;
         configured = true;
     }
-    const size_t ctas = (a.batch + rows_per_cta(N) - 1) / rows_per_cta(N);
-    if (ctas == 0) return cudaSuccess;
-    if (ctas > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-    kernel<<<(unsigned)ctas, rows_cta_threads(N), rows_smem_bytes(N), stream>>>(a);
+    if (groups > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    kernel<<<(unsigned)groups, rows_cta_threads(N), rows_smem_bytes(N), stream>>>(a);
     return cudaGetLastError();
 }
 
-cudaError_t MUFFT_CAT(rows_launch_, ROWS_N)(const mcu_rows_args &a, cudaStream_t stream)
+#if ROWS_DIR < 0
+cudaError_t MUFFT_CAT(rows_launch_, ROWS_N, _fwd)(const mcu_rows_args &a, cudaStream_t s)
 {
-    return a.direction < 0 ? launch_dir<-1>(a, stream) : launch_dir<1>(a, stream);
+    switch (a.in_mode * 8 + a.out_mode) {
+    case MCU_IN_COMPLEX * 8 + MCU_OUT_COMPLEX: return launch_mode<MCU_IN_COMPLEX, MCU_OUT_COMPLEX>(a, s);
+    case MCU_IN_COMPLEX * 8 + MCU_OUT_R2C: return launch_mode<MCU_IN_COMPLEX, MCU_OUT_R2C>(a, s);
+    case MCU_IN_COMPLEX * 8 + MCU_OUT_R2C_FULL: return launch_mode<MCU_IN_COMPLEX, MCU_OUT_R2C_FULL>(a, s);
+    case MCU_IN_HALF * 8 + MCU_OUT_COMPLEX: return launch_mode<MCU_IN_HALF, MCU_OUT_COMPLEX>(a, s);
+    case MCU_IN_HALF * 8 + MCU_OUT_R2C: return launch_mode<MCU_IN_HALF, MCU_OUT_R2C>(a, s);
+    case MCU_IN_HALF * 8 + MCU_OUT_R2C_FULL: return launch_mode<MCU_IN_HALF, MCU_OUT_R2C_FULL>(a, s);
+    default: return cudaErrorInvalidValue;
+    }
 }
+#else
+cudaError_t MUFFT_CAT(rows_launch_, ROWS_N, _inv)(const mcu_rows_args &a, cudaStream_t s)
+{
+    if (a.out_mode != MCU_OUT_COMPLEX) return cudaErrorInvalidValue;
+    switch (a.in_mode) {
+    case MCU_IN_COMPLEX: return launch_mode<MCU_IN_COMPLEX, MCU_OUT_COMPLEX>(a, s);
+    case MCU_IN_HALF: return launch_mode<MCU_IN_HALF, MCU_OUT_COMPLEX>(a, s);
+    case MCU_IN_C2R: return launch_mode<MCU_IN_C2R, MCU_OUT_COMPLEX>(a, s);
+    case MCU_IN_MUL: return launch_mode<MCU_IN_MUL, MCU_OUT_COMPLEX>(a, s);
+    case MCU_IN_MUL_C2R: return launch_mode<MCU_IN_MUL_C2R, MCU_OUT_COMPLEX>(a, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+#endif
 
 } // namespace mufft

@@ -1,0 +1,227 @@
+"""Batched entry points of include/mufft_cuda.h against the oracle: device-resident, strided,
+pinned-host and pageable-host buffers.  Batches are large enough that the persistent prefetch
+kernel (rows_kernel.cuh: fft_rows_tma_kernel) runs several groups per CTA, and ragged enough that
+the last group has idle transform slots."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+
+from cpu_libs import FLAG_FULL_R2C, FLAG_ZERO_PAD, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", params=["direct", "prefetch"])
+def m(request):
+    """The library with the row kernels in direct-load or bulk-copy prefetch flavour."""
+    import mufft_b200
+    if mufft_b200.mufft_cuda_device_count() < 1:
+        pytest.fail("no CUDA device visible")
+    mufft_b200.mufft_cuda_set_prefetch(request.param == "prefetch")
+    yield mufft_b200
+    mufft_b200.mufft_cuda_set_prefetch(0)
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    return torch
+
+
+def tol(n):
+    return 1e-6 * max(1.0, math.log2(n))
+
+
+def sample_indices(batch, count=24, seed=0):
+    rng = np.random.default_rng(seed)
+    idx = set(range(min(batch, 4))) | set(range(max(0, batch - 4), batch))
+    idx |= set(int(i) for i in rng.integers(0, batch, size=min(count, batch)))
+    return sorted(idx)
+
+
+def dev_random(torch, shape, seed):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    return torch.rand(shape, dtype=torch.float32, device="cuda", generator=g) - 0.5
+
+
+def batch_for(n):
+    """Enough transforms for > 3 groups per persistent CTA on a 148-SM part, not a multiple of anything."""
+    return max(7, min(300000, (6 << 20) // n + 13))
+
+
+@pytest.mark.parametrize("n", [2, 4, 16, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+@pytest.mark.parametrize("direction", [-1, 1])
+def test_c2c_batch_device(m, torch, oracle, n, direction):
+    batch = batch_for(n)
+    x = dev_random(torch, (batch, 2 * n), n + direction)
+    y = torch.zeros_like(x)
+    plan = m.mufft_create_plan_1d_c2c(n, direction, 0)
+    assert plan
+    assert m.mufft_execute_plan_1d_batch(plan, y.data_ptr(), x.data_ptr(), batch, 0, 0) == 0, m.mufft_cuda_last_error()
+    # secondary check on every transform (cuFFT through torch), primary on a sample (oracle)
+    xc = torch.view_as_complex(x.view(batch, n, 2))
+    ref = torch.fft.fft(xc, dim=1) if direction < 0 else torch.fft.ifft(xc, dim=1, norm="forward")
+    yc = torch.view_as_complex(y.view(batch, n, 2))
+    err = (torch.linalg.vector_norm(yc - ref, dim=1) / torch.linalg.vector_norm(ref, dim=1)).max().item()
+    assert err <= tol(n), f"worst transform rel L2 {err:.3e}"
+    idx = sample_indices(batch)
+    xs, ys = x[idx].cpu().numpy().view(np.complex64), y[idx].cpu().numpy().view(np.complex64)
+    for i in range(len(idx)):
+        assert rel_l2(ys[i], oracle.c2c(xs[i], direction)) <= tol(n)
+    # async flavour on the current stream gives the same bits
+    y2 = torch.zeros_like(x)
+    assert m.mufft_execute_plan_1d_batch_async(plan, y2.data_ptr(), x.data_ptr(), batch, 0, 0) == 0
+    assert m.mufft_cuda_synchronize() == 0
+    assert torch.equal(y, y2)
+    m.mufft_free_plan_1d(plan)
+
+
+@pytest.mark.parametrize("n", [64, 1024, 4096])
+def test_c2c_batch_strided_and_zero_pad(m, torch, oracle, n):
+    batch = 1500
+    in_pitch, out_pitch = n // 2 + 6, n + 10  # complex elements; input rows are only N/2 long (zero pad)
+    x = dev_random(torch, (batch, 2 * in_pitch), 5)
+    y = torch.full((batch, 2 * out_pitch), 7.0, dtype=torch.float32, device="cuda")
+    plan = m.mufft_create_plan_1d_c2c(n, -1, FLAG_ZERO_PAD)
+    assert m.mufft_execute_plan_1d_batch(plan, y.data_ptr(), x.data_ptr(), batch, out_pitch * 8, in_pitch * 8) == 0
+    m.mufft_free_plan_1d(plan)
+    assert torch.all(y[:, 2 * n:] == 7.0), "wrote beyond N outputs of a row"
+    idx = sample_indices(batch)
+    xs = x[idx].cpu().numpy().view(np.complex64)[:, : n // 2]
+    ys = y[idx].cpu().numpy().view(np.complex64)[:, :n]
+    for i in range(len(idx)):
+        assert rel_l2(ys[i], oracle.c2c(xs[i], -1, FLAG_ZERO_PAD, n=n)) <= tol(n)
+
+
+@pytest.mark.parametrize("n", [4, 16, 128, 1024, 4096, 8192, 16384, 32768])
+@pytest.mark.parametrize("flags", [0, FLAG_FULL_R2C, FLAG_ZERO_PAD])
+@pytest.mark.parametrize("pitch", ["tight", "aligned"])
+def test_r2c_c2r_batch_device(m, torch, oracle, n, flags, pitch):
+    batch = batch_for(n // 2)
+    n_in = n // 2 if flags & FLAG_ZERO_PAD else n
+    bins = n if flags & FLAG_FULL_R2C else n // 2 + 1
+    spec_pitch = bins if pitch == "tight" else (bins + 3) // 2 * 2  # complex elements, even = 16-byte rows
+    x = dev_random(torch, (batch, n_in), n)
+    spec = torch.zeros((batch, 2 * spec_pitch), dtype=torch.float32, device="cuda")
+    fwd = m.mufft_create_plan_1d_r2c(n, flags)
+    assert fwd
+    assert m.mufft_execute_plan_1d_batch(fwd, spec.data_ptr(), x.data_ptr(), batch, spec_pitch * 8, 0) == 0
+    m.mufft_free_plan_1d(fwd)
+    idx = sample_indices(batch)
+    xs = x[idx].cpu().numpy()
+    ss = spec[idx].cpu().numpy().view(np.complex64)[:, :bins]
+    for i in range(len(idx)):
+        assert rel_l2(ss[i], oracle.r2c(xs[i], flags, n=n)) <= tol(n)
+    if flags == 0:
+        back = torch.zeros((batch, n), dtype=torch.float32, device="cuda")
+        inv = m.mufft_create_plan_1d_c2r(n, 0)
+        assert m.mufft_execute_plan_1d_batch(inv, back.data_ptr(), spec.data_ptr(), batch, 0, spec_pitch * 8) == 0
+        m.mufft_free_plan_1d(inv)
+        bs = back[idx].cpu().numpy()
+        for i in range(len(idx)):
+            assert rel_l2(bs[i], oracle.c2r(ss[i], n)) <= tol(n)
+        # round trip, every transform: C2R(R2C(x)) = N x  (ref fft.md:108-113, unnormalised)
+        err = (torch.linalg.vector_norm(back / n - x, dim=1) / torch.linalg.vector_norm(x, dim=1)).max().item()
+        assert err <= 2 * tol(n)
+
+
+@pytest.mark.parametrize("kind", ["pinned", "pageable"])
+@pytest.mark.parametrize("n", [256, 4096])
+def test_c2c_batch_host_memory(m, torch, oracle, n, kind):
+    """Host buffers are staged through the plan's device buffers in pipelined chunks."""
+    batch = (80 << 20) // (8 * n) + 5  # > 2 staging chunks
+    x = (np.random.default_rng(3).random((batch, 2 * n), np.float32) - np.float32(0.5))
+    if kind == "pinned":
+        xt = torch.from_numpy(x).pin_memory()
+        yt = torch.zeros((batch, 2 * n), dtype=torch.float32).pin_memory()
+        xp, yp = xt.data_ptr(), yt.data_ptr()
+    else:
+        y = np.zeros_like(x)
+        xp, yp = x.ctypes.data, y.ctypes.data
+    plan = m.mufft_create_plan_1d_c2c(n, -1, 0)
+    assert m.mufft_execute_plan_1d_batch(plan, yp, xp, batch, 0, 0) == 0, m.mufft_cuda_last_error()
+    # the async flavour must refuse pointers the device cannot reach
+    if kind == "pageable":
+        assert m.mufft_execute_plan_1d_batch_async(plan, yp, xp, batch, 0, 0) != 0
+    m.mufft_free_plan_1d(plan)
+    got = (yt.numpy() if kind == "pinned" else y).view(np.complex64)
+    xd = torch.from_numpy(x).cuda()
+    ref = torch.fft.fft(torch.view_as_complex(xd.view(batch, n, 2)), dim=1).cpu().numpy()
+    assert rel_l2(got, ref) <= tol(n)
+    for i in sample_indices(batch, 8):
+        assert rel_l2(got[i], oracle.c2c(x[i].view(np.complex64), -1)) <= tol(n)
+
+
+@pytest.mark.parametrize("n", [64, 2048, 8192, 32768])
+@pytest.mark.parametrize("stereo", [0, 1])
+def test_conv_batch_device(m, torch, oracle, n, stereo):
+    method = stereo | 4 | 8  # both inputs zero padded, as bench.c:243-310 uses the API
+    batch = batch_for(n) // 2 + 3
+    plan = m.mufft_create_plan_conv(n, 0, method)
+    assert plan
+    blk = m.mufft_conv_get_transformed_block_size(plan) // 8
+    a = dev_random(torch, (batch, n if stereo else n // 2), 11)       # n/2 stereo (complex) or mono samples
+    filt = dev_random(torch, (1, n // 2), 12)
+    sa = torch.zeros((batch, 2 * blk), dtype=torch.float32, device="cuda")
+    sf = torch.zeros((1, 2 * blk), dtype=torch.float32, device="cuda")
+    out = torch.zeros((batch, 2 * n if stereo else n), dtype=torch.float32, device="cuda")
+    assert m.mufft_execute_conv_input_batch(plan, 1, sf.data_ptr(), filt.data_ptr(), 1) == 0
+    assert m.mufft_execute_conv_input_batch(plan, 0, sa.data_ptr(), a.data_ptr(), batch) == 0
+    assert m.mufft_execute_conv_output_batch(plan, out.data_ptr(), sa.data_ptr(), sf.data_ptr(), batch, 0) == 0
+    m.mufft_free_plan_conv(plan)
+    f = filt[0].cpu().numpy()
+    idx = sample_indices(batch, 10)
+    as_, os_ = a[idx].cpu().numpy(), out[idx].cpu().numpy()
+    for i in range(len(idx)):
+        ai = as_[i].view(np.complex64) if stereo else as_[i]
+        want, _, _ = oracle.conv(ai, f, n, method)
+        got = os_[i].view(np.complex64) if stereo else os_[i]
+        assert rel_l2(got, want) <= 2 * tol(n)
+        assert np.max(np.abs(got - want)) < 2e-6 * math.sqrt(n)  # test.c:431,474
+
+
+@pytest.mark.parametrize("nx,ny", [(64, 64), (256, 128), (256, 256), (512, 2048), (2048, 256), (1024, 1024), (128, 2048),
+                                   (8192, 8), (16, 4096)])
+@pytest.mark.parametrize("fused", [1, 0])
+def test_c2c_2d_batch_device(m, torch, oracle, nx, ny, fused):
+    """fused=1: one persistent kernel for the whole batch where the shape has one (256..2048 per
+    side); fused=0: row kernel + column kernel per group of images."""
+    m.mufft_cuda_set_fused_2d(fused)
+    batch = max(3, min(40, (64 << 20) // (8 * nx * ny)))
+    x = dev_random(torch, (batch, ny, nx, 2), nx + ny)
+    y = torch.zeros_like(x)
+    for direction in (-1, 1):
+        plan = m.mufft_create_plan_2d_c2c(nx, ny, direction, 0)
+        assert plan
+        assert m.mufft_execute_plan_2d_batch(plan, y.data_ptr(), x.data_ptr(), batch) == 0, m.mufft_cuda_last_error()
+        m.mufft_free_plan_2d(plan)
+        xc = torch.view_as_complex(x)
+        ref = torch.fft.fft2(xc) if direction < 0 else torch.fft.ifft2(xc, norm="forward")
+        yc = torch.view_as_complex(y)
+        err = (torch.linalg.vector_norm((yc - ref).reshape(batch, -1), dim=1) /
+               torch.linalg.vector_norm(ref.reshape(batch, -1), dim=1)).max().item()
+        assert err <= tol(nx * ny)
+        for i in (0, batch - 1):
+            want = oracle.c2c_2d(xc[i].cpu().numpy(), direction)
+            assert rel_l2(yc[i].cpu().numpy(), want) <= tol(nx * ny)
+    m.mufft_cuda_set_fused_2d(1)
+
+
+def test_linearity_and_parseval_at_full_size(m, torch):
+    """Size-independent properties at the BASELINE configs[1] shape (N=4096) on a 64 Ki batch:
+    FFT(a x + y) = a FFT(x) + FFT(y), and sum |X|^2 = N sum |x|^2."""
+    n, batch = 4096, 65536
+    x, y = dev_random(torch, (batch, 2 * n), 1), dev_random(torch, (batch, 2 * n), 2)
+    plan = m.mufft_create_plan_1d_c2c(n, -1, 0)
+    fx, fy, fz = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    for dst, src in ((fx, x), (fy, y), (fz, 0.5 * x + y)):
+        assert m.mufft_execute_plan_1d_batch(plan, dst.data_ptr(), src.data_ptr(), batch, 0, 0) == 0
+    m.mufft_free_plan_1d(plan)
+    lin = torch.linalg.vector_norm(fz - (0.5 * fx + fy)) / torch.linalg.vector_norm(fz)
+    assert lin.item() <= tol(n)
+    e_in = (x.double() ** 2).sum(dim=1)
+    e_out = (fx.double() ** 2).sum(dim=1)
+    assert torch.max(torch.abs(e_out / (n * e_in) - 1)).item() < 1e-5
