@@ -72,6 +72,7 @@ typedef struct mcu_2d_args {
     size_t batch;
     unsigned nx, ny;
     int direction;
+    unsigned lag;          /* column tickets run this many images behind the row tickets (set by the launcher) */
 } mcu_2d_args;
 
 /* Generic one-pass Stockham kernel (any length; used beyond the engine limits). */

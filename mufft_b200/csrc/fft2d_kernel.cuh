@@ -37,11 +37,18 @@ __host__ __device__ constexpr size_t f2d_smem_bytes(int nx, int ny)
     return (r > c ? r : c) * sizeof(float2) + 16;
 }
 
-__device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
+// Polling load (no L1 invalidation per iteration; the acquire fence follows once, after success).
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned *p)
 {
     unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+// Release increment: the CTA's row stores (ordered before it by the preceding bar.sync) become
+// visible to whoever acquires the counter.
+__device__ __forceinline__ void red_release_add(unsigned *p, unsigned v)
+{
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 template <int NX, int NY, int DIR>
@@ -52,7 +59,7 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, 2) fft2d_fused_kernel(const
     constexpr unsigned NR = NY / ROWS; // row tickets per image
     constexpr unsigned NC = NX / COLS; // column tickets per image
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ unsigned s_ticket;
+    __shared__ unsigned s_ticket[2];
     cpx *smem = reinterpret_cast<cpx *>(smem_raw);
 
     const int tid = threadIdx.x;
@@ -62,25 +69,53 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, 2) fft2d_fused_kernel(const
     unsigned *rows_done = a.counters + 1;
     const unsigned long long total = (unsigned long long)a.batch * (NR + NC);
 
-    for (;;) {
-        __syncthreads(); // the previous ticket's readers of s_ticket and of the exchange area are done
-        if (tid == 0) s_ticket = atomicAdd(ticket_counter, 1u);
-        __syncthreads();
-        const unsigned k = s_ticket;
-        if (k >= total) break;
+    // Column tickets of image i are issued `lag` images after its row tickets, far enough that the
+    // row tiles (taken by other CTAs) have normally finished when a column ticket is drawn.
+    const unsigned lag = a.lag < a.batch ? a.lag : (unsigned)a.batch;
+    const unsigned long long head = (unsigned long long)lag * NR;                  // rows only
+    const unsigned long long body = (unsigned long long)(a.batch - lag) * (NR + NC); // rows + lagged columns
 
-        // ticket -> (image, phase, tile)
-        unsigned image, tile;
-        bool is_rows;
-        if (k < NR) {
-            image = 0; tile = k; is_rows = true;
-        } else {
-            const unsigned kk = k - NR;
-            const unsigned s = 1 + kk / (NR + NC), j = kk % (NR + NC);
-            if (s < a.batch && j < NR) { image = s; tile = j; is_rows = true; }
-            else if (s < a.batch) { image = s - 1; tile = j - NR; is_rows = false; }
-            else { image = (unsigned)a.batch - 1; tile = j; is_rows = false; }
+    // ticket -> (image, phase, tile)
+    auto decode = [&](unsigned k, unsigned &image, unsigned &tile) -> bool {
+        if (k < head) {
+            image = k / NR; tile = k % NR;
+            return true;
+        } else if (k - head < body) {
+            const unsigned long long kk = k - head;
+            const unsigned s = lag + (unsigned)(kk / (NR + NC)), j = (unsigned)(kk % (NR + NC));
+            if (j < NR) { image = s; tile = j; return true; }
+            image = s - lag; tile = j - NR;
+            return false;
         }
+        const unsigned long long kk = k - head - body;
+        image = (unsigned)a.batch - lag + (unsigned)(kk / NC); tile = (unsigned)(kk % NC);
+        return false;
+    };
+    // Thread 0 publishes a ticket to the CTA only once its dependency is met (a column ticket
+    // needs all row tickets of its image), so one CTA barrier per ticket is enough.
+    auto publish = [&](unsigned k, int slot) {
+        unsigned image, tile;
+        if (k < total && !decode(k, image, tile)) {
+            unsigned ns = 32;
+            while (ld_relaxed(rows_done + image) < (unsigned)NY) {
+                __nanosleep(ns);
+                if (ns < 1024) ns *= 2;
+            }
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        }
+        s_ticket[slot] = k;
+    };
+
+    unsigned next_ticket = 0;
+    if (tid == 0) publish(atomicAdd(ticket_counter, 1u), 0);
+    for (int it = 0;; it++) {
+        __syncthreads(); // ticket visible; the previous ticket's users of the exchange area are done
+        const unsigned k = s_ticket[it & 1];
+        if (k >= total) break;
+        // draw the next ticket now; its round trip to L2 overlaps this tile
+        if (tid == 0) next_ticket = atomicAdd(ticket_counter, 1u);
+        unsigned image, tile;
+        const bool is_rows = decode(k, image, tile);
 
         cpx *__restrict__ out = static_cast<cpx *>(a.out) + (size_t)image * a.out_image;
         if (is_rows) {
@@ -90,22 +125,22 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, 2) fft2d_fused_kernel(const
             cpx v[RX];
 #pragma unroll
             for (int e = 0; e < RX; e++) v[e] = __ldcs(in + t + e * TX); // streamed: read once
+            // pull the same tile of the next image into L2 (one bulk prefetch of the tile's
+            // contiguous ROWS*NX*8 bytes): that tile is about one wave of tickets ahead
+            if (tid == 0 && image + 1 < a.batch) {
+                const cpx *nxt = static_cast<const cpx *>(a.in) + (size_t)(image + 1) * a.in_image + (size_t)tile * ROWS * NX;
+                if ((reinterpret_cast<uintptr_t>(nxt) & 15) == 0)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt), "r"((unsigned)(ROWS * NX * sizeof(cpx))) : "memory");
+            }
             engine_run<NX, DIR, 1, TX, ROWS>(v, smem + slot * engine_smem_elems(NX), twx, t, slot);
             cpx *__restrict__ o = out + row * NX;
 #pragma unroll
             for (int e = 0; e < RX; e++) o[t + e * TX] = v[e];
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) atomicAdd(rows_done + image, 1u);
+            // each row signals on its own: the threads of one transform meet, then one of them
+            // releases the row (no CTA barrier on the row path)
+            engine_sync<TX, ROWS>(slot);
+            if (t == 0) red_release_add(rows_done + image, 1u);
         } else {
-            if (tid == 0) {
-                unsigned ns = 32;
-                while (ld_acquire(rows_done + image) < NR) {
-                    __nanosleep(ns);
-                    if (ns < 1024) ns *= 2;
-                }
-            }
-            __syncthreads();
             const int c = tid % COLS, t = tid / COLS;
             cpx *__restrict__ col = out + (size_t)tile * COLS + c;
             cpx v[RY];
@@ -115,6 +150,7 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, 2) fft2d_fused_kernel(const
 #pragma unroll
             for (int e = 0; e < RY; e++) __stcs(col + (size_t)(t + e * TY) * NX, v[e]);
         }
+        if (tid == 0) publish(next_ticket, (it + 1) & 1);
     }
 }
 
