@@ -41,6 +41,10 @@ WORKLOADS = {
     "conv8192": ("conv_stereo", 8192, 0, 65536),
     "c2c2d1024": ("c2c2d", 1024, 1024, 256),
     "c2c64": ("c2c", 64, 0, 1 << 24),
+    "c2c32768": ("c2c", 32768, 0, 16384),
+    "c2c1m": ("c2c", 1 << 20, 0, 512),
+    "slab2d": ("slab2d", 32768, 32768, 1),
+    "slab2d8k": ("slab2d", 8192, 8192, 1),
 }
 DESCRIPTION = {
     "c2c4096": "batched 1D C2C forward N=4096, batch 262144 per GPU (BASELINE configs[1])",
@@ -49,12 +53,16 @@ DESCRIPTION = {
     "conv8192": "stereo fast convolution FFT N=8192, 65536 blocks per GPU, one filter (BASELINE configs[2])",
     "c2c2d1024": "batched 2D C2C 1024x1024, batch 256 per GPU (BASELINE configs[3])",
     "c2c64": "batched 1D C2C forward N=64, batch 2^24 per GPU (batched form of BASELINE configs[0])",
+    "c2c32768": "batched 1D C2C forward N=32768, batch 16384 per GPU (row length of BASELINE configs[4])",
+    "c2c1m": "batched 1D C2C forward N=2^20, batch 512 per GPU",
+    "slab2d": "single 2D C2C 32768x32768, row slabs over the GPUs, all-to-all transpose over NVLink, transposed-out (BASELINE configs[4])",
+    "slab2d8k": "single 2D C2C 8192x8192, row slabs over the GPUs, all-to-all transpose, transposed-out",
 }
 
 
 def flops_per_unit(kind, n, ny):
     lg = math.log2(n)
-    if kind == "c2c2d":
+    if kind in ("c2c2d", "slab2d"):
         return 5.0 * n * ny * (lg + math.log2(ny))
     if kind == "conv_stereo":
         return 2 * 5.0 * n * lg + 6.0 * n
@@ -71,7 +79,7 @@ def bytes_per_unit(kind, n, ny):
         return 4 * n + 8 * (n // 2 + 1)
     if kind == "conv_stereo":
         return 28 * n  # conv_input (4N in, 8N out) + conv_output (8N + 8N), filter spectrum amortised
-    if kind == "c2c2d":
+    if kind in ("c2c2d", "slab2d"):
         return 16 * n * ny  # compulsory; the row->column intermediate is meant to stay in L2
     raise ValueError(kind)
 
@@ -299,6 +307,23 @@ class Job:
             self.call = call
             self.call_sync = lambda o, i, cnt: call(o, i, cnt, True)
             self.free = lambda: m.mufft_free_plan_conv(self.plan)
+        elif kind == "slab2d":
+            import torch.distributed as dist_mod
+            from mufft_b200.slab import SlabFFT2D
+            if not dist_mod.is_initialized():  # single GPU: a one-rank group
+                os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+                os.environ.setdefault("MASTER_PORT", "29577")
+                dist_mod.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+            world = dist_mod.get_world_size()
+            self.slab = SlabFFT2D(n, ny, m.MUFFT_FORWARD, device=dev, chunks=int(os.environ.get("MUFFT_SLAB_CHUNKS", "8")))
+            self.inp = torch.view_as_complex(rnd(ny // world, n * 2).view(ny // world, n, 2))
+            self.out = torch.empty((ny, n // world), dtype=torch.complex64, device=dev)
+            self.buf = self.slab.buffers()
+            self.plan = 1
+            self.units = 1.0 / world  # this rank's share of the one transform
+            self.call = None
+            self.call_sync = None
+            self.free = self.slab.close
         elif kind == "c2c2d":
             self.plan = m.mufft_create_plan_2d_c2c(n, ny, m.MUFFT_FORWARD, 0)
             self.inp = rnd(units, ny * n * 2)
@@ -312,6 +337,9 @@ class Job:
             raise RuntimeError("plan creation failed: " + m.mufft_cuda_last_error().decode())
 
     def step(self):
+        if self.kind == "slab2d":
+            self.slab.execute(self.out, self.inp, buf=self.buf)
+            return
         err = self.call(self.out.data_ptr(), self.inp.data_ptr(), self.units)
         if err:
             raise RuntimeError("execute failed: " + self.m.mufft_cuda_last_error().decode())
@@ -388,6 +416,10 @@ def main():
     if args.units:
         units = args.units
     job = Job(m, torch, kind, n, ny, units, dev)
+    if kind == "slab2d":
+        units = job.units
+        args.no_e2e = True
+        args.no_cpu = True  # the CPU reference for one 32768^2 image is a 33 s, 24 GiB single-thread job
 
     clocks = Clocks(local) if rank == 0 else None
     m.mufft_cuda_launch_count(1)
@@ -469,7 +501,7 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if kind == "slab2d" else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": DESCRIPTION[args.workload], "n": n, "ny": ny, "units_per_gpu": units,
                        "global_units": units * n_gpus, "parallelism": f"batch-sharded x{n_gpus}, no collective",

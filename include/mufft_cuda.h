@@ -49,6 +49,12 @@ int mufft_execute_plan_1d_batch(mufft_plan_1d *plan, void *output, const void *i
 int mufft_execute_plan_1d_batch_async(mufft_plan_1d *plan, void *output, const void *input, size_t batch,
                                       size_t output_stride_bytes, size_t input_stride_bytes);
 
+/* The plan's N-point C2C transform applied down the COLUMNS of a row-major [N][width] complex
+ * matrix (pitches in bytes between consecutive rows), device-accessible pointers, enqueued on the
+ * current stream.  This is the column pass of a slab-decomposed 2D transform (mufft_b200/slab.py). */
+int mufft_execute_plan_1d_columns(mufft_plan_1d *plan, void *output, const void *input, size_t width,
+                                  size_t output_pitch_bytes, size_t input_pitch_bytes);
+
 /* `batch` independent images, tightly packed one after another (each laid out as fft.h
  * describes for the plan's kind: [Ny][Nx] complex, R2C output / C2R input with row pitch Nx
  * complex).  C2R output images are Nx*Ny floats each, densely packed. */
@@ -72,6 +78,9 @@ void mufft_cuda_set_prefetch(int enable);
  * and columns of the whole batch with the intermediate kept in L2, 0 = separate row and column
  * kernels per group of images (what every other 2D shape uses).  Same results either way. */
 void mufft_cuda_set_fused_2d(int enable);
+/* Transform lengths 16384 .. 2097152: 1 (default) = two kernels (N = N1*N2: column transforms, then
+ * twiddle + row transforms with a transposed store), 0 = one generic radix pass per kernel. */
+void mufft_cuda_set_two_kernel(int enable);
 
 /* Introspection used by tests and the bench: which path a plan takes.
  * 1D: 1 = single-kernel shared-memory engine, 0 = multi-pass generic kernels.

@@ -64,6 +64,7 @@ SIGNATURES = {
     "mufft_cuda_launch_count": (C.c_ulonglong, [_i]),
     "mufft_execute_plan_1d_batch": (_i, [_vp, _vp, _vp, _sz, _sz, _sz]),
     "mufft_execute_plan_1d_batch_async": (_i, [_vp, _vp, _vp, _sz, _sz, _sz]),
+    "mufft_execute_plan_1d_columns": (_i, [_vp, _vp, _vp, _sz, _sz, _sz]),
     "mufft_execute_plan_2d_batch": (_i, [_vp, _vp, _vp, _sz]),
     "mufft_execute_plan_2d_batch_async": (_i, [_vp, _vp, _vp, _sz]),
     "mufft_execute_conv_input_batch": (_i, [_vp, _u, _vp, _vp, _sz]),
@@ -72,6 +73,7 @@ SIGNATURES = {
     "mufft_execute_conv_output_batch_async": (_i, [_vp, _vp, _vp, _vp, _sz, _sz]),
     "mufft_cuda_set_prefetch": (None, [_i]),
     "mufft_cuda_set_fused_2d": (None, [_i]),
+    "mufft_cuda_set_two_kernel": (None, [_i]),
     "mufft_cuda_plan_1d_uses_engine": (_i, [_vp]),
     "mufft_cuda_plan_2d_paths": (_i, [_vp]),
 }

@@ -60,7 +60,22 @@ typedef struct mcu_cols_args {
     unsigned n;            /* column length (rows) */
     unsigned width;        /* number of columns to transform */
     int direction;
+    unsigned rows_valid;   /* rows >= rows_valid are taken as zero and never read (0 = all n rows valid) */
+    const void *roots;     /* NULL, or exp(dir*2*pi*i*j/n_total): element (image, row) is multiplied by */
+    unsigned root_mask;    /* roots[(image*row) & root_mask] before the transform (n = 256, 512, 1024 only) */
 } mcu_cols_args;
+
+/* Second kernel of the two-kernel transform for n = n1 * n2 > MCU_ENGINE_MAX_N (rowst_kernel.cuh). */
+typedef struct mcu_rowst_args {
+    void *out;             /* X[k1 + n1*k2] */
+    const void *in;        /* Y[k1][n2], rows contiguous */
+    const void *tw;        /* engine twiddle table of n2 */
+    const void *roots;     /* exp(dir*2*pi*i*j/n), j < n */
+    size_t out_batch, in_batch; /* complex elements between consecutive transforms */
+    size_t batch;
+    unsigned n, n1, n2;
+    int direction;
+} mcu_rowst_args;
 
 /* Fused 2D C2C kernel (fft2d_kernel.cuh): whole batch in one persistent launch. */
 typedef struct mcu_2d_args {
@@ -140,6 +155,9 @@ int mcu_prefetch(const void *ptr, size_t bytes, int to_device, void *stream);
 int mcu_launch_rows(const mcu_rows_args *args, void *stream);
 int mcu_launch_cols(const mcu_cols_args *args, void *stream);
 int mcu_launch_pass(const mcu_pass_args *args, void *stream);
+/* n2 of the two-kernel split of n (0 = n is outside its range and takes the generic passes) */
+unsigned mcu_split_n2(unsigned n);
+int mcu_launch_rowst(const mcu_rowst_args *args, void *stream);
 /* 1 if the fused 2D kernel exists for this image shape */
 int mcu_2d_fused_supported(unsigned nx, unsigned ny);
 int mcu_launch_2d_fused(const mcu_2d_args *args, void *stream);

@@ -10,12 +10,12 @@
 
 namespace mufft {
 
-template <int DIR>
+template <int DIR, bool TWIDDLE>
 static cudaError_t launch_dir(const mcu_cols_args &a, cudaStream_t stream)
 {
     constexpr int N = COLS_N;
     static bool configured = false;
-    auto kernel = fft_cols_kernel<N, DIR>;
+    auto kernel = fft_cols_kernel<N, DIR, TWIDDLE>;
     if (!configured) {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem_bytes(N));
         if (err != cudaSuccess) return err;
@@ -31,7 +31,12 @@ static cudaError_t launch_dir(const mcu_cols_args &a, cudaStream_t stream)
 
 cudaError_t MUFFT_CAT(cols_launch_, COLS_N)(const mcu_cols_args &a, cudaStream_t stream)
 {
-    return a.direction < 0 ? launch_dir<-1>(a, stream) : launch_dir<1>(a, stream);
+#if COLS_N == 256 || COLS_N == 512 || COLS_N == 1024
+    if (a.roots != nullptr) return a.direction < 0 ? launch_dir<-1, true>(a, stream) : launch_dir<1, true>(a, stream);
+#else
+    if (a.roots != nullptr) return cudaErrorInvalidValue;
+#endif
+    return a.direction < 0 ? launch_dir<-1, false>(a, stream) : launch_dir<1, false>(a, stream);
 }
 
 } // namespace mufft

@@ -28,7 +28,10 @@ __host__ __device__ constexpr size_t cols_smem_bytes(int n)
     return (size_t)cols_tile(n) * engine_smem_elems(n) * sizeof(float2);
 }
 
-template <int N, int DIR>
+// TWIDDLE: multiply element (image, row) by roots[(image * row) mod n_total] before the
+// transform: the inter-stage twiddle when a long column transform is split in two (the "image"
+// index is then the first-stage output index k1, see mufft_host.c: run_cols).
+template <int N, int DIR, bool TWIDDLE>
 __global__ void __launch_bounds__(cols_cta_threads(N)) fft_cols_kernel(const mcu_cols_args a)
 {
     constexpr int R = engine_regs(N);
@@ -42,6 +45,7 @@ __global__ void __launch_bounds__(cols_cta_threads(N)) fft_cols_kernel(const mcu
     const size_t col = (size_t)blockIdx.x * TC + c;
     const bool active = col < a.width;
     const cpx *__restrict__ tw = static_cast<const cpx *>(a.tw);
+    const unsigned rows_valid = a.rows_valid ? a.rows_valid : (unsigned)N;
     cpx *sm = reinterpret_cast<cpx *>(smem_raw) + c;
 
     for (size_t image = blockIdx.y; image < a.batch; image += gridDim.y) {
@@ -50,7 +54,13 @@ __global__ void __launch_bounds__(cols_cta_threads(N)) fft_cols_kernel(const mcu
         cpx v[R];
 #pragma unroll
         for (int e = 0; e < R; e++)
-            v[e] = active ? in[(size_t)(t + e * T) * a.in_pitch] : make_float2(0.0f, 0.0f);
+            v[e] = (active && (unsigned)(t + e * T) < rows_valid) ? in[(size_t)(t + e * T) * a.in_pitch] : make_float2(0.0f, 0.0f);
+        if constexpr (TWIDDLE) {
+            const cpx *__restrict__ roots = static_cast<const cpx *>(a.roots);
+#pragma unroll
+            for (int e = 0; e < R; e++)
+                v[e] = cmul(v[e], __ldg(roots + (((unsigned)image * (unsigned)(t + e * T)) & a.root_mask)));
+        }
 
         engine_run<N, DIR, TC, cols_cta_threads(N), 1>(v, sm, tw, t, 0);
 

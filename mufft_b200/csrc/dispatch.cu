@@ -26,6 +26,10 @@ MUFFT_DECLARE_COLS(512) MUFFT_DECLARE_COLS(1024) MUFFT_DECLARE_COLS(2048)
 #define MUFFT_DECLARE_F2D(pw, ph) cudaError_t f2d_launch_##pw##x##ph(const mcu_2d_args &, cudaStream_t);
 MUFFT_F2D_SHAPES(MUFFT_DECLARE_F2D)
 
+cudaError_t rowst_launch_256(const mcu_rowst_args &, cudaStream_t);
+cudaError_t rowst_launch_512(const mcu_rowst_args &, cudaStream_t);
+cudaError_t rowst_launch_1024(const mcu_rowst_args &, cudaStream_t);
+
 static std::atomic<unsigned long long> g_launches{0};
 
 // ---- generic Stockham pass ----------------------------------------------------------------
@@ -278,6 +282,27 @@ int mcu_launch_2d_fused(const mcu_2d_args *a, void *stream)
     MUFFT_F2D_SHAPES(X)
 #undef X
     return (int)cudaErrorInvalidValue;
+}
+
+// n = n1 * n2 with n1 <= 2048 (column kernel) and n2 in {256, 512, 1024} (row kernel B)
+unsigned mcu_split_n2(unsigned n)
+{
+    if (n <= MCU_COLS_MAX_N || (n & (n - 1)) != 0) return 0;
+    if (n <= 2048u * 256u) return 256;
+    if (n <= 2048u * 512u) return 512;
+    if (n <= 2048u * 1024u) return 1024;
+    return 0;
+}
+
+int mcu_launch_rowst(const mcu_rowst_args *a, void *stream)
+{
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    switch (a->n2) {
+    case 256: return (int)rowst_launch_256(*a, (cudaStream_t)stream);
+    case 512: return (int)rowst_launch_512(*a, (cudaStream_t)stream);
+    case 1024: return (int)rowst_launch_1024(*a, (cudaStream_t)stream);
+    default: return (int)cudaErrorInvalidValue;
+    }
 }
 
 int mcu_launch_pass(const mcu_pass_args *a, void *stream)

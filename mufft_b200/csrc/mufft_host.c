@@ -36,7 +36,7 @@ enum { KIND_C2C = 0, KIND_R2C = 1, KIND_R2C_FULL = 2, KIND_C2R = 3 };
 #define CPX 8u                              /* bytes per complex sample */
 #define STAGE_SLOTS 3
 #define STAGE_CHUNK_BYTES ((size_t)32 << 20) /* per-slot staging granularity */
-#define SCRATCH_CAP_BYTES ((size_t)256 << 20)
+#define SCRATCH_CAP_BYTES ((size_t)1 << 30)
 #define ZERO_COPY_BYTES ((size_t)64 << 10)   /* pinned buffers up to this size are used in place */
 #define MAX_STEPS 32
 
@@ -52,6 +52,10 @@ __attribute__((constructor)) static void read_env(void)
     if (e != NULL) g_prefetch = e[0] == '1';
 }
 void mufft_cuda_set_prefetch(int enable) { g_prefetch = enable != 0; }
+/* Lengths above MCU_ENGINE_MAX_N: 1 (default) = two kernels (column transforms of length N1, then
+ * twiddle + row transforms of length N2 with a transposed store), 0 = one generic pass per radix. */
+static int g_two_kernel = 1;
+void mufft_cuda_set_two_kernel(int enable) { g_two_kernel = enable != 0; }
 /* 2D C2C: 1 (default) = the fused persistent kernel when the shape has one, 0 = row kernel +
  * column kernel per group of images (the path every other shape and R2C/C2R take). */
 static int g_fused_2d = 1;
@@ -150,7 +154,9 @@ typedef struct axis {
     unsigned n;
     int direction;
     void *d_engine_tw; /* engine table, n <= MCU_ENGINE_MAX_N */
-    void *d_roots;     /* exp(dir*2*pi*i*j/n), j < n: generic multi-pass kernels */
+    void *d_roots;     /* exp(dir*2*pi*i*j/n), j < n: generic multi-pass kernels, two-kernel split */
+    unsigned n1, n2;   /* two-kernel split n = n1 * n2 (0 = not used) */
+    void *d_tw_n1, *d_tw_n2; /* engine tables of the two factors */
     unsigned nsteps;
     unsigned radix[MAX_STEPS], span[MAX_STEPS];
 } axis;
@@ -159,7 +165,20 @@ static void axis_free(axis *ax)
 {
     mcu_free(ax->d_engine_tw);
     mcu_free(ax->d_roots);
+    mcu_free(ax->d_tw_n1);
+    mcu_free(ax->d_tw_n2);
     memset(ax, 0, sizeof(*ax));
+}
+
+static void *make_engine_table(unsigned n, int direction)
+{
+    size_t entries = mcu_engine_table_size(n);
+    float *host = calloc(entries ? entries : 1, CPX);
+    if (!host) return NULL;
+    mcu_engine_table_fill(host, n, direction);
+    void *dev = upload(host, (entries ? entries : 1) * CPX);
+    free(host);
+    return dev;
 }
 
 /* want_generic: also build what the multi-pass kernels need. */
@@ -169,13 +188,15 @@ static int axis_init(axis *ax, unsigned n, int direction, int want_generic)
     ax->n = n;
     ax->direction = direction;
     if (n <= MCU_ENGINE_MAX_N) {
-        size_t entries = mcu_engine_table_size(n);
-        float *host = calloc(entries ? entries : 1, CPX);
-        if (!host) return -1;
-        mcu_engine_table_fill(host, n, direction);
-        ax->d_engine_tw = upload(host, (entries ? entries : 1) * CPX);
-        free(host);
+        ax->d_engine_tw = make_engine_table(n, direction);
         if (!ax->d_engine_tw) return -1;
+    }
+    if (want_generic && mcu_split_n2(n) != 0) { /* rows use it above MCU_ENGINE_MAX_N, columns above MCU_COLS_MAX_N */
+        ax->n2 = mcu_split_n2(n);
+        ax->n1 = n / ax->n2;
+        ax->d_tw_n1 = make_engine_table(ax->n1, direction);
+        ax->d_tw_n2 = make_engine_table(ax->n2, direction);
+        if (!ax->d_tw_n1 || !ax->d_tw_n2) return -1;
     }
     if (want_generic) {
         /* Static radix-8/4/2 decomposition: widest radix first, the remainder last. */
@@ -403,8 +424,10 @@ struct mufft_plan_1d {
     int zero_pad;
     int use_engine;
     axis ax;
+    axis ax_cols;      /* tables for mufft_execute_plan_1d_columns, built on first use */
     void *d_rtw;
     scratch scr;
+    scratch scr_cols;
     stage st;
 };
 
@@ -412,6 +435,8 @@ void mufft_free_plan_1d(mufft_plan_1d *plan)
 {
     if (plan == NULL) return;
     axis_free(&plan->ax);
+    axis_free(&plan->ax_cols);
+    scratch_free(&plan->scr_cols);
     mcu_free(plan->d_rtw);
     scratch_free(&plan->scr);
     stage_free(&plan->st);
@@ -513,6 +538,26 @@ static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode
             cur = scr->buf[1];
             cur_stride = n;
         }
+        if (ax->n2 != 0 && g_two_kernel) {
+            /* two kernels: N2 column transforms of length N1 on the [N1][N2] view into scratch,
+             * then twiddle + N1 row transforms of length N2 with the transposed store */
+            mcu_cols_args ca;
+            memset(&ca, 0, sizeof(ca));
+            ca.out = scr->buf[0]; ca.in = cur; ca.tw = ax->d_tw_n1;
+            ca.out_pitch = ax->n2; ca.in_pitch = ax->n2; ca.out_image = n; ca.in_image = cur_stride;
+            ca.batch = cnt; ca.n = ax->n1; ca.width = ax->n2; ca.direction = ax->direction;
+            ca.rows_valid = half ? ax->n1 / 2 : 0;
+            TRY(mcu_launch_cols(&ca, stream));
+            mcu_rowst_args ra;
+            memset(&ra, 0, sizeof(ra));
+            ra.in = scr->buf[0]; ra.in_batch = n; ra.tw = ax->d_tw_n2; ra.roots = ax->d_roots;
+            if (out_mode == MCU_OUT_COMPLEX) { ra.out = dst; ra.out_batch = out_stride; }
+            else { ra.out = scr->buf[1]; ra.out_batch = n; }
+            ra.batch = cnt; ra.n = n; ra.n1 = ax->n1; ra.n2 = ax->n2; ra.direction = ax->direction;
+            TRY(mcu_launch_rowst(&ra, stream));
+            cur = ra.out;
+            cur_stride = ra.out_batch;
+        } else
         for (unsigned s = 0; s < ax->nsteps; s++) {
             const int last = s + 1 == ax->nsteps;
             mcu_pass_args p;
@@ -624,6 +669,31 @@ int mufft_execute_plan_1d_batch_async(mufft_plan_1d *plan, void *output, const v
     int in_mode, out_mode;
     plan_modes(plan, &in_mode, &out_mode);
     return exec_1d(plan, in_mode, out_mode, 1.0f, output, output_stride_bytes, input, input_stride_bytes, NULL, 0, 0, batch, 1);
+}
+
+static int run_cols_axis(const axis *ax, scratch *scr_cols, void *out, size_t out_pitch, size_t out_image,
+                         const void *in, size_t in_pitch, size_t in_image, unsigned width, size_t images, void *stream);
+
+/* The plan's C2C transform applied down the columns of a row-major [N][width] matrix on device
+ * memory (what the column pass of a slab-decomposed 2D transform needs: mufft_b200/slab.py).
+ * Enqueued on the current stream. */
+int mufft_execute_plan_1d_columns(mufft_plan_1d *plan, void *output, const void *input, size_t width,
+                                  size_t output_pitch_bytes, size_t input_pitch_bytes)
+{
+    if (plan == NULL || plan->kind != KIND_C2C || plan->zero_pad || width == 0 || width > 0xffffffffu ||
+        (output_pitch_bytes | input_pitch_bytes) % CPX != 0) {
+        snprintf(tls_error, sizeof(tls_error), "columns: needs a plain C2C plan and pitches that are multiples of 8 bytes");
+        return -1;
+    }
+    const size_t span_in = input_pitch_bytes * ((size_t)plan->n - 1) + width * CPX;
+    const size_t span_out = output_pitch_bytes * ((size_t)plan->n - 1) + width * CPX;
+    if (!device_visible(mcu_pointer_kind(input), span_in) || !device_visible(mcu_pointer_kind(output), span_out)) {
+        snprintf(tls_error, sizeof(tls_error), "columns: needs device-accessible (device or managed) pointers");
+        return -1;
+    }
+    if (plan->ax_cols.n == 0 && axis_init(&plan->ax_cols, plan->n, plan->direction, plan->n > MCU_COLS_MAX_N) != 0) return -1;
+    return run_cols_axis(&plan->ax_cols, &plan->scr_cols, output, output_pitch_bytes / CPX, 0, input, input_pitch_bytes / CPX, 0,
+                         (unsigned)width, 1, tls_stream);
 }
 
 /* ---- convolution (ref fft.c:89-99, 565-624, 794-809) --------------------------------------------- */
@@ -858,11 +928,10 @@ int mufft_cuda_plan_2d_paths(const mufft_plan_2d *plan)
 }
 
 /* Column transforms of `images` images on device-visible memory; pitches in complex elements. */
-static int run_cols(mufft_plan_2d *plan, void *out, size_t out_pitch, size_t out_image,
-                    const void *in, size_t in_pitch, size_t in_image, unsigned width, size_t images, void *stream)
+static int run_cols_axis(const axis *ax, scratch *scr_cols, void *out, size_t out_pitch, size_t out_image,
+                         const void *in, size_t in_pitch, size_t in_image, unsigned width, size_t images, void *stream)
 {
-    const axis *ax = &plan->ax_y;
-    if (plan->cols_engine) {
+    if (ax->n <= MCU_COLS_MAX_N) {
         mcu_cols_args a;
         memset(&a, 0, sizeof(a));
         a.out = out; a.in = in; a.tw = ax->d_engine_tw;
@@ -870,8 +939,33 @@ static int run_cols(mufft_plan_2d *plan, void *out, size_t out_pitch, size_t out
         a.batch = images; a.n = ax->n; a.width = width; a.direction = ax->direction;
         return mcu_launch_cols(&a, stream);
     }
+    if (ax->n2 != 0 && g_two_kernel) {
+        /* Long columns, n = n1 * n2 (row y = y1*n2 + y2, output row k = k1 + n1*k2), two sweeps of
+         * the column kernel per image:
+         *   A  n2 "images" (one per y2) of n1-point column transforms -> scratch [k1][y2][c]
+         *   B  n1 "images" (one per k1) of n2-point column transforms with the twiddle
+         *      w_n^(k1*y2) fused into the load -> out rows k1 + n1*k2 */
+        const unsigned n1 = ax->n1, n2 = ax->n2;
+        TRY(scratch_reserve(scr_cols, (size_t)width * ax->n * CPX));
+        for (size_t img = 0; img < images; img++) {
+            mcu_cols_args ca;
+            memset(&ca, 0, sizeof(ca));
+            ca.in = (const char *)in + img * in_image * CPX; ca.in_pitch = (size_t)n2 * in_pitch; ca.in_image = in_pitch;
+            ca.out = scr_cols->buf[0]; ca.out_pitch = (size_t)n2 * width; ca.out_image = width;
+            ca.tw = ax->d_tw_n1; ca.batch = n2; ca.n = n1; ca.width = width; ca.direction = ax->direction;
+            TRY(mcu_launch_cols(&ca, stream));
+            mcu_cols_args cb;
+            memset(&cb, 0, sizeof(cb));
+            cb.in = scr_cols->buf[0]; cb.in_pitch = width; cb.in_image = (size_t)n2 * width;
+            cb.out = (char *)out + img * out_image * CPX; cb.out_pitch = (size_t)n1 * out_pitch; cb.out_image = out_pitch;
+            cb.tw = ax->d_tw_n2; cb.batch = n1; cb.n = n2; cb.width = width; cb.direction = ax->direction;
+            cb.roots = ax->d_roots; cb.root_mask = ax->n - 1;
+            TRY(mcu_launch_cols(&cb, stream));
+        }
+        return 0;
+    }
     /* Generic vertical passes, image by image, ping-ponging through scratch of pitch `width`. */
-    TRY(scratch_reserve(&plan->scr_cols, (size_t)width * ax->n * CPX));
+    TRY(scratch_reserve(scr_cols, (size_t)width * ax->n * CPX));
     for (size_t img = 0; img < images; img++) {
         const void *cur = (const char *)in + img * in_image * CPX;
         size_t cur_pitch = in_pitch;
@@ -881,7 +975,7 @@ static int run_cols(mufft_plan_2d *plan, void *out, size_t out_pitch, size_t out
             memset(&p, 0, sizeof(p));
             p.in = cur; p.in_stride = cur_pitch;
             if (last) { p.out = (char *)out + img * out_image * CPX; p.out_stride = out_pitch; }
-            else { p.out = plan->scr_cols.buf[s & 1]; p.out_stride = width; }
+            else { p.out = scr_cols->buf[s & 1]; p.out_stride = width; }
             p.roots = ax->d_roots; p.batch = 1; p.n = ax->n; p.width = width;
             p.radix = ax->radix[s]; p.p = ax->span[s]; p.direction = ax->direction;
             TRY(mcu_launch_pass(&p, stream));
@@ -890,6 +984,12 @@ static int run_cols(mufft_plan_2d *plan, void *out, size_t out_pitch, size_t out
         }
     }
     return 0;
+}
+
+static int run_cols(mufft_plan_2d *plan, void *out, size_t out_pitch, size_t out_image,
+                    const void *in, size_t in_pitch, size_t in_image, unsigned width, size_t images, void *stream)
+{
+    return run_cols_axis(&plan->ax_y, &plan->scr_cols, out, out_pitch, out_image, in, in_pitch, in_image, width, images, stream);
 }
 
 /* Whole 2D transforms of `images` tightly packed images on device-visible memory.  The

@@ -1,0 +1,153 @@
+"""Slab-decomposed 2D C2C transform of ONE large [Ny][Nx] array over the ranks of a
+torch.distributed group (BASELINE configs[4]).
+
+The reference has no distributed path: `mufft_execute_plan_2d` (ref fft.c:852-989) runs the row
+pass, then the column pass, on one array in one address space.  Here rank g owns rows
+[g*Ny/G, (g+1)*Ny/G).  The row pass is local; one all-to-all block transpose (NCCL over
+NVLink/NVSwitch: rank g sends the (Ny/G x Nx/G) tile of columns [p*Nx/G, (p+1)*Nx/G) to rank p)
+turns row slabs into column slabs; the column pass is local again.  Result layout
+("transposed-out", the usual contract of slab FFTs): rank g holds columns
+[g*Nx/G, (g+1)*Nx/G) of the spectrum as a row-major [Ny][Nx/G] array.  `natural=True` adds a
+second all-to-all that brings the spectrum back to row slabs [Ny/G][Nx].
+
+The local transforms go through the C ABI (`mufft_execute_plan_1d_batch_async` for rows,
+`mufft_execute_plan_1d_columns` for columns, both hand-written CUDA); `local_rows` /
+`local_cols` can be injected so the exchange logic is testable on CPU with the gloo backend.
+
+The row pass is cut into `chunks` blocks of rows; the all-to-all of block c runs on a side
+stream while block c+1 is being transformed, so most of the NVLink time hides behind the row
+pass (and, with `natural=True`, the return exchange behind nothing - it is pure communication).
+"""
+import torch
+import torch.distributed as dist
+
+
+class SlabFFT2D:
+    def __init__(self, nx, ny, direction, group=None, device=None, chunks=4, local_rows=None, local_cols=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        g = self.world
+        if nx % g or ny % g:
+            raise ValueError("Nx and Ny must be divisible by the number of ranks")
+        self.nx, self.ny, self.direction = nx, ny, direction
+        self.rows_local, self.cols_local = ny // g, nx // g
+        self.device = torch.device(device) if device is not None else torch.device("cpu")
+        self.chunks = max(1, min(chunks, self.rows_local))
+        while self.rows_local % self.chunks:
+            self.chunks -= 1
+        self._plans = None
+        if local_rows is None or local_cols is None:
+            import mufft_b200 as m  # the CUDA library; fails loudly when it is not built
+            if self.device.type != "cuda":
+                raise RuntimeError("SlabFFT2D runs its transforms on a CUDA device (there is no CPU path)")
+            self._m = m
+            px = m.mufft_create_plan_1d_c2c(nx, direction, 0)
+            py = m.mufft_create_plan_1d_c2c(ny, direction, 0)
+            if not px or not py:
+                raise RuntimeError("plan creation failed: " + m.mufft_cuda_last_error().decode())
+            self._plans = (px, py)
+            local_rows, local_cols = self._cuda_rows, self._cuda_cols
+        self.local_rows, self.local_cols = local_rows, local_cols
+        self._side = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+
+    def close(self):
+        if self._plans:
+            for p in self._plans:
+                self._m.mufft_free_plan_1d(p)
+            self._plans = None
+
+    # ---- local passes through the C ABI --------------------------------------------------------
+    def _use_current_stream(self):
+        self._m.mufft_cuda_set_stream(torch.cuda.current_stream(self.device).cuda_stream or None)
+
+    def _cuda_rows(self, out, inp):
+        """out[r, :] = FFT(inp[r, :]) for a block of rows ([rows][Nx] complex64 each)."""
+        self._use_current_stream()
+        err = self._m.mufft_execute_plan_1d_batch_async(self._plans[0], out.data_ptr(), inp.data_ptr(), inp.shape[0], 0, 0)
+        if err:
+            raise RuntimeError(self._m.mufft_cuda_last_error().decode())
+
+    def _cuda_cols(self, out, inp):
+        """out[:, c] = FFT(inp[:, c]) for a [Ny][W] column slab."""
+        self._use_current_stream()
+        w = inp.shape[1]
+        err = self._m.mufft_execute_plan_1d_columns(self._plans[1], out.data_ptr(), inp.data_ptr(), w, w * 8, w * 8)
+        if err:
+            raise RuntimeError(self._m.mufft_cuda_last_error().decode())
+
+    # ---- the distributed transform ---------------------------------------------------------------
+    def buffers(self):
+        """Work buffers (allocate once, reuse across executes)."""
+        c64 = dict(dtype=torch.complex64, device=self.device)
+        g, rl, cl = self.world, self.rows_local, self.cols_local
+        return {
+            "rows": torch.empty((rl, self.nx), **c64),          # row-transformed slab
+            "send": torch.empty((g, rl, cl), **c64),            # per-peer tiles, contiguous
+            "recv": torch.empty((self.ny, cl), **c64),          # = [G][rows_local][cols_local]: the column slab
+        }
+
+    def execute(self, out, inp, buf=None, natural=False):
+        """inp: this rank's [Ny/G][Nx] complex64 row slab.  out: [Ny][Nx/G] (transposed-out) or, with
+        natural=True, [Ny/G][Nx].  Returns out."""
+        g, rl, cl = self.world, self.rows_local, self.cols_local
+        buf = buf or self.buffers()
+        rows, send, recv = buf["rows"], buf["send"], buf["recv"]
+        recv_tiles = recv.view(g, rl, cl)
+        rc = rl // self.chunks
+        works = []
+        for c in range(self.chunks):
+            lo, hi = c * rc, (c + 1) * rc
+            self.local_rows(rows[lo:hi], inp[lo:hi])
+            # pack: tile for peer p = columns [p*cl, (p+1)*cl) of this block of rows
+            send[:, lo:hi, :].copy_(rows[lo:hi].view(rc, g, cl).permute(1, 0, 2))
+            if g == 1:
+                recv_tiles[:, lo:hi, :].copy_(send[:, lo:hi, :])
+                continue
+            ins = [send[p, lo:hi, :] for p in range(g)]
+            outs = [recv_tiles[s, lo:hi, :] for s in range(g)]
+            if self._side is not None:
+                self._side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(self._side):
+                    works.append(dist.all_to_all(outs, ins, group=self.group, async_op=True))
+            elif dist.get_backend(self.group) == "gloo":
+                self._gloo_all_to_all(outs, ins)
+            else:
+                dist.all_to_all(outs, ins, group=self.group)
+        for w in works:
+            w.wait()
+        if self._side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
+        if not natural:
+            self.local_cols(out, recv)
+            return out
+        self.local_cols(recv, recv)
+        # second exchange: back to row slabs.  Tile for peer p = rows [p*rl, (p+1)*rl) of the column slab.
+        back = send  # [G][rl][cl], reused
+        if g == 1:
+            back.copy_(recv_tiles)
+        else:
+            ins = [recv_tiles[p] for p in range(g)]
+            outs = [back[s] for s in range(g)]
+            if dist.get_backend(self.group) == "gloo":
+                self._gloo_all_to_all(outs, ins)
+            else:
+                dist.all_to_all(outs, ins, group=self.group)
+        out.view(rl, g, cl).copy_(back.permute(1, 0, 2))
+        return out
+
+    def _gloo_all_to_all(self, outs, ins):
+        """gloo has no all_to_all: pairwise exchange (CPU tests only)."""
+        g, me = self.world, self.rank
+        outs[me].copy_(ins[me])
+        reqs = []
+        for p in range(g):
+            if p != me:
+                reqs.append(dist.isend(ins[p].contiguous(), p, group=self.group))
+        for s in range(g):
+            if s != me:
+                tmp = torch.empty_like(outs[s])
+                dist.recv(tmp, s, group=self.group)
+                outs[s].copy_(tmp)
+        for r in reqs:
+            r.wait()

@@ -184,7 +184,7 @@ def test_conv_batch_device(m, torch, oracle, n, stereo):
 
 
 @pytest.mark.parametrize("nx,ny", [(64, 64), (256, 128), (256, 256), (512, 2048), (2048, 256), (1024, 1024), (128, 2048),
-                                   (8192, 8), (16, 4096)])
+                                   (8192, 8), (16, 4096), (32, 16384), (16384, 32), (64, 8192)])
 @pytest.mark.parametrize("fused", [1, 0])
 def test_c2c_2d_batch_device(m, torch, oracle, nx, ny, fused):
     """fused=1: one persistent kernel for the whole batch where the shape has one (256..2048 per
@@ -208,6 +208,59 @@ def test_c2c_2d_batch_device(m, torch, oracle, nx, ny, fused):
             want = oracle.c2c_2d(xc[i].cpu().numpy(), direction)
             assert rel_l2(yc[i].cpu().numpy(), want) <= tol(nx * ny)
     m.mufft_cuda_set_fused_2d(1)
+
+
+@pytest.mark.parametrize("n", [16384, 65536, 1 << 18, 1 << 19, 1 << 20, 1 << 21, 1 << 22])
+@pytest.mark.parametrize("two_kernel", [1, 0])
+def test_large_n(m, torch, oracle, n, two_kernel):
+    """N above the single-kernel limit: two-kernel split (N = N1*N2) up to 2^21, generic radix
+    passes beyond and when the split is switched off; C2C both directions, zero pad, R2C and C2R."""
+    if two_kernel == 0 and n > (1 << 19):
+        pytest.skip("generic passes are covered at the smaller lengths")
+    m.mufft_cuda_set_two_kernel(two_kernel)
+    try:
+        batch = 3
+        x = dev_random(torch, (batch, 2 * n), n)
+        y = torch.zeros_like(x)
+        xc = torch.view_as_complex(x.view(batch, n, 2))
+        for direction in (-1, 1):
+            plan = m.mufft_create_plan_1d_c2c(n, direction, 0)
+            assert plan
+            assert m.mufft_execute_plan_1d_batch(plan, y.data_ptr(), x.data_ptr(), batch, 0, 0) == 0
+            m.mufft_free_plan_1d(plan)
+            ref = torch.fft.fft(xc, dim=1) if direction < 0 else torch.fft.ifft(xc, dim=1, norm="forward")
+            yc = torch.view_as_complex(y.view(batch, n, 2))
+            err = (torch.linalg.vector_norm(yc - ref, dim=1) / torch.linalg.vector_norm(ref, dim=1)).max().item()
+            assert err <= tol(n)
+            if n <= (1 << 20):
+                got = yc[batch - 1].cpu().numpy()
+                assert rel_l2(got, oracle.c2c(xc[batch - 1].cpu().numpy(), direction)) <= tol(n)
+        # zero-padded forward: the input rows really are N/2 long
+        xh = dev_random(torch, (batch, n), 7)
+        plan = m.mufft_create_plan_1d_c2c(n, -1, FLAG_ZERO_PAD)
+        assert m.mufft_execute_plan_1d_batch(plan, y.data_ptr(), xh.data_ptr(), batch, 0, 0) == 0
+        m.mufft_free_plan_1d(plan)
+        xp = torch.zeros((batch, n), dtype=torch.complex64, device="cuda")
+        xp[:, : n // 2] = torch.view_as_complex(xh.view(batch, n // 2, 2))
+        ref = torch.fft.fft(xp, dim=1)
+        yc = torch.view_as_complex(y.view(batch, n, 2))
+        assert (torch.linalg.vector_norm(yc - ref) / torch.linalg.vector_norm(ref)).item() <= tol(n)
+        # R2C + C2R of real length 2N (complex engine length N)
+        r = dev_random(torch, (batch, 2 * n), 9)
+        spec = torch.zeros((batch, 2 * (n + 1)), dtype=torch.float32, device="cuda")
+        fwd = m.mufft_create_plan_1d_r2c(2 * n, 0)
+        assert m.mufft_execute_plan_1d_batch(fwd, spec.data_ptr(), r.data_ptr(), batch, 0, 0) == 0
+        m.mufft_free_plan_1d(fwd)
+        ref = torch.fft.rfft(r, dim=1)
+        sc = torch.view_as_complex(spec.view(batch, n + 1, 2))
+        assert (torch.linalg.vector_norm(sc - ref) / torch.linalg.vector_norm(ref)).item() <= tol(2 * n)
+        back = torch.zeros_like(r)
+        inv = m.mufft_create_plan_1d_c2r(2 * n, 0)
+        assert m.mufft_execute_plan_1d_batch(inv, back.data_ptr(), spec.data_ptr(), batch, 0, 0) == 0
+        m.mufft_free_plan_1d(inv)
+        assert (torch.linalg.vector_norm(back / (2 * n) - r) / torch.linalg.vector_norm(r)).item() <= 2 * tol(2 * n)
+    finally:
+        m.mufft_cuda_set_two_kernel(1)
 
 
 def test_linearity_and_parseval_at_full_size(m, torch):

@@ -1,0 +1,75 @@
+"""CPU test (gloo, world_size 2 and 4) of the slab decomposition's exchange logic
+(mufft_b200/slab.py): partitioning, packing, the all-to-all placement and both output layouts.  The
+local row/column transforms are injected (torch CPU FFT here); on the GPU box the same class runs
+them through the CUDA library (tests/test_slab_gpu.py)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, nx, ny, chunks, natural, direction, result):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mufft_b200.slab import SlabFFT2D
+        g = torch.Generator().manual_seed(1234)
+        full = torch.complex(torch.rand(ny, nx, generator=g) - 0.5, torch.rand(ny, nx, generator=g) - 0.5)
+        fft = (lambda x, dim: torch.fft.fft(x, dim=dim)) if direction < 0 else (lambda x, dim: torch.fft.ifft(x, dim=dim, norm="forward"))
+
+        def rows(out, inp):
+            out.copy_(fft(inp, 1))
+
+        def cols(out, inp):
+            out.copy_(fft(inp, 0))
+        plan = SlabFFT2D(nx, ny, direction, chunks=chunks, local_rows=rows, local_cols=cols)
+        rl, cl = ny // world, nx // world
+        mine = full[rank * rl:(rank + 1) * rl].contiguous()
+        out = torch.empty((rl, nx) if natural else (ny, cl), dtype=torch.complex64)
+        plan.execute(out, mine, natural=natural)
+        ref = fft(fft(full, 1), 0)
+        want = ref[rank * rl:(rank + 1) * rl] if natural else ref[:, rank * cl:(rank + 1) * cl]
+        err = (torch.linalg.vector_norm(out - want) / torch.linalg.vector_norm(want)).item()
+        result[rank] = err
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("natural", [False, True])
+@pytest.mark.parametrize("nx,ny,chunks", [(16, 8, 1), (32, 64, 4), (64, 16, 3)])
+def test_slab_exchange_gloo(world, natural, nx, ny, chunks):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    result = ctx.Manager().dict()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nx, ny, chunks, natural, -1, result)) for r in range(world)]
+    [p.start() for p in procs]
+    [p.join(120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert len(result) == world and max(result.values()) < 1e-5, dict(result)
+
+
+def test_slab_rejects_indivisible_shapes():
+    port = _free_port()
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        from mufft_b200.slab import SlabFFT2D
+        plan = SlabFFT2D(8, 8, -1, local_rows=lambda o, i: o.copy_(torch.fft.fft(i, dim=1)), local_cols=lambda o, i: o.copy_(torch.fft.fft(i, dim=0)))
+        x = torch.complex(torch.rand(8, 8), torch.rand(8, 8))
+        out = torch.empty(8, 8, dtype=torch.complex64)
+        plan.execute(out, x)
+        assert torch.allclose(out, torch.fft.fft2(x), atol=1e-4)
+    finally:
+        dist.destroy_process_group()

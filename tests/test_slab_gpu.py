@@ -1,0 +1,68 @@
+"""Slab-decomposed 2D transform on the GPU(s): local passes through the CUDA library, exchange
+over NCCL.  With one visible GPU the group has one rank (the pack / column-slab path still runs);
+with two or more the test spawns one process per GPU (up to 4)."""
+import math
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, nx, ny, natural, direction, result):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import mufft_b200
+        from mufft_b200.slab import SlabFFT2D
+        assert mufft_b200.mufft_cuda_set_device(rank) == 0
+        g = torch.Generator(device="cpu").manual_seed(7)
+        full = torch.complex(torch.rand(ny, nx, generator=g) - 0.5, torch.rand(ny, nx, generator=g) - 0.5)
+        rl, cl = ny // world, nx // world
+        plan = SlabFFT2D(nx, ny, direction, device=dev, chunks=4)
+        mine = full[rank * rl:(rank + 1) * rl].contiguous().to(dev)
+        out = torch.empty((rl, nx) if natural else (ny, cl), dtype=torch.complex64, device=dev)
+        buf = plan.buffers()
+        for _ in range(2):  # buffers are reusable
+            plan.execute(out, mine, buf=buf, natural=natural)
+        torch.cuda.synchronize()
+        fulld = full.to(dev).to(torch.complex128)
+        ref = torch.fft.fft2(fulld) if direction < 0 else torch.fft.ifft2(fulld, norm="forward")
+        want = ref[rank * rl:(rank + 1) * rl] if natural else ref[:, rank * cl:(rank + 1) * cl]
+        result[rank] = (torch.linalg.vector_norm(out.to(torch.complex128) - want) / torch.linalg.vector_norm(want)).item()
+        plan.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nx,ny", [(256, 128), (2048, 4096), (16384, 512), (1024, 32768)])
+@pytest.mark.parametrize("natural", [False, True])
+def test_slab_2d(nx, ny, natural):
+    import torch
+    import torch.multiprocessing as mp
+    world = min(4, torch.cuda.device_count())
+    while world & (world - 1):
+        world -= 1
+    assert world >= 1, "no CUDA device visible"
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    result = ctx.Manager().dict()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nx, ny, natural, -1, result)) for r in range(world)]
+    [p.start() for p in procs]
+    [p.join(300) for p in procs]
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    tol = 1e-6 * math.log2(nx * ny)
+    assert len(result) == world and max(result.values()) <= tol, dict(result)
