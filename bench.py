@@ -41,6 +41,18 @@ WORKLOADS = {
     "conv8192": ("conv_stereo", 8192, 0, 65536),
     "c2c2d1024": ("c2c2d", 1024, 1024, 256),
     "c2c64": ("c2c", 64, 0, 1 << 24),
+    "c2c256": ("c2c", 256, 0, 1 << 22),
+    "c2c1024": ("c2c", 1024, 0, 1 << 20),
+    "c2c2048": ("c2c", 2048, 0, 1 << 19),
+    "c2c8192": ("c2c", 8192, 0, 1 << 17),
+    "r2c2048": ("r2c", 2048, 0, 1 << 19),
+    "c2r2048": ("c2r", 2048, 0, 1 << 19),
+    "r2c8192": ("r2c", 8192, 0, 1 << 17),
+    "c2r8192": ("c2r", 8192, 0, 1 << 17),
+    "r2c16384": ("r2c", 16384, 0, 1 << 16),
+    "c2r16384": ("c2r", 16384, 0, 1 << 16),
+    "c2c2d512": ("c2c2d", 512, 512, 1024),
+    "c2c2d2048": ("c2c2d", 2048, 2048, 64),
     "c2c32768": ("c2c", 32768, 0, 16384),
     "c2c1m": ("c2c", 1 << 20, 0, 512),
     "slab2d": ("slab2d", 32768, 32768, 1),
@@ -54,6 +66,18 @@ DESCRIPTION = {
     "c2c2d1024": "batched 2D C2C 1024x1024, batch 256 per GPU (BASELINE configs[3])",
     "c2c64": "batched 1D C2C forward N=64, batch 2^24 per GPU (batched form of BASELINE configs[0])",
     "c2c32768": "batched 1D C2C forward N=32768, batch 16384 per GPU (row length of BASELINE configs[4])",
+    "c2c256": "batched 1D C2C forward N=256, batch 2^22 per GPU",
+    "c2c1024": "batched 1D C2C forward N=1024, batch 2^20 per GPU",
+    "c2c2048": "batched 1D C2C forward N=2048, batch 2^19 per GPU",
+    "c2c8192": "batched 1D C2C forward N=8192, batch 2^17 per GPU",
+    "r2c2048": "batched 1D R2C N=2048, batch 2^19 per GPU",
+    "c2r2048": "batched 1D C2R N=2048, batch 2^19 per GPU",
+    "r2c8192": "batched 1D R2C N=8192, batch 2^17 per GPU",
+    "c2r8192": "batched 1D C2R N=8192, batch 2^17 per GPU",
+    "r2c16384": "batched 1D R2C N=16384, batch 2^16 per GPU",
+    "c2r16384": "batched 1D C2R N=16384, batch 2^16 per GPU",
+    "c2c2d512": "batched 2D C2C 512x512, batch 1024 per GPU",
+    "c2c2d2048": "batched 2D C2C 2048x2048, batch 64 per GPU",
     "c2c1m": "batched 1D C2C forward N=2^20, batch 512 per GPU",
     "slab2d": "single 2D C2C 32768x32768, row slabs over the GPUs, all-to-all transpose over NVLink, transposed-out (BASELINE configs[4])",
     "slab2d8k": "single 2D C2C 8192x8192, row slabs over the GPUs, all-to-all transpose, transposed-out",

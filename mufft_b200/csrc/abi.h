@@ -162,9 +162,13 @@ int mcu_launch_rowst(const mcu_rowst_args *args, void *stream);
 int mcu_2d_fused_supported(unsigned nx, unsigned ny);
 int mcu_launch_2d_fused(const mcu_2d_args *args, void *stream);
 int mcu_launch_resolve(const mcu_resolve_args *args, void *stream);
+/* Engine shape variant the row kernel of (n, in_mode, out_mode) uses: 0 general, 1 / 2 the
+ * mirrored-pass shapes of the real transforms (fft_engine.cuh).  The twiddle table passed in
+ * mcu_rows_args.tw must be the one of that variant. */
+int mcu_rows_variant(unsigned n, int in_mode, int out_mode);
 /* number of complex entries of the engine twiddle table for length n, and its host fill */
-size_t mcu_engine_table_size(unsigned n);
-void mcu_engine_table_fill(float *table, unsigned n, int direction);
+size_t mcu_engine_table_size(unsigned n, int variant);
+void mcu_engine_table_fill(float *table, unsigned n, int direction, int variant);
 /* number of kernel launches issued through mcu_launch_* since the last reset (for bench.py) */
 unsigned long long mcu_launch_count(int reset);
 

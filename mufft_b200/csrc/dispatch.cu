@@ -115,13 +115,13 @@ __global__ void __launch_bounds__(256) resolve_kernel(const mcu_resolve_args a)
 }
 
 // ---- engine twiddle tables -----------------------------------------------------------------
-template <int N>
+template <int N, int V>
 static void fill_table(float *table, int direction)
 {
-    constexpr int passes = engine_num_passes(N);
+    constexpr int passes = engine_num_passes(N, V);
     for (int j = 1; j < passes; j++) {
-        const int r = engine_radix(N, j), p = engine_span(N, j);
-        float *block = table + 2 * (size_t)engine_tw_offset(N, j);
+        const int r = engine_radix(N, j, V), p = engine_span(N, j, V);
+        float *block = table + 2 * (size_t)engine_tw_offset(N, j, V);
         for (int m = 1; m < r; m++)
             for (int k = 0; k < p; k++) {
                 // exp(dir * 2*pi*i * k*m / (r*p)), evaluated in double and rounded once, the way
@@ -131,6 +131,14 @@ static void fill_table(float *table, int direction)
                 block[2 * ((size_t)(m - 1) * p + k) + 1] = (float)sin(phase);
             }
     }
+}
+
+template <int N>
+static void fill_table_variant(float *table, int direction, int variant)
+{
+    if (variant == 1) { if constexpr (engine_variant_exists(N, 1)) fill_table<N, 1>(table, direction); }
+    else if (variant == 2) { if constexpr (engine_variant_exists(N, 2)) fill_table<N, 2>(table, direction); }
+    else fill_table<N, 0>(table, direction);
 }
 
 #define MUFFT_FOR_ENGINE_SIZES(X) \
@@ -222,20 +230,33 @@ int mcu_prefetch(const void *ptr, size_t bytes, int to_device, void *stream)
 }
 
 // ---- engine twiddle tables (see fill_table above) --------------------------------------------
-size_t mcu_engine_table_size(unsigned n)
+int mcu_rows_variant(unsigned n, int in_mode, int out_mode)
 {
+    const bool r2c = out_mode == MCU_OUT_R2C || out_mode == MCU_OUT_R2C_FULL;
+    const bool c2r = in_mode == MCU_IN_C2R || in_mode == MCU_IN_MUL_C2R;
     switch (n) {
-#define X(v) case v: return (size_t)engine_tw_total(v) + 1;
+#define X(v) case v: return r2c && engine_variant_exists(v, MUFFT_VARIANT_MIRROR_LAST) ? MUFFT_VARIANT_MIRROR_LAST \
+                          : (c2r && engine_variant_exists(v, MUFFT_VARIANT_MIRROR_FIRST) ? MUFFT_VARIANT_MIRROR_FIRST : MUFFT_VARIANT_GENERAL);
         MUFFT_FOR_ENGINE_SIZES(X)
 #undef X
     default: return 0;
     }
 }
 
-void mcu_engine_table_fill(float *table, unsigned n, int direction)
+size_t mcu_engine_table_size(unsigned n, int variant)
 {
     switch (n) {
-#define X(v) case v: fill_table<v>(table, direction); break;
+#define X(v) case v: return (size_t)(variant == 1 ? engine_tw_total(v, 1) : variant == 2 ? engine_tw_total(v, 2) : engine_tw_total(v, 0)) + 1;
+        MUFFT_FOR_ENGINE_SIZES(X)
+#undef X
+    default: return 0;
+    }
+}
+
+void mcu_engine_table_fill(float *table, unsigned n, int direction, int variant)
+{
+    switch (n) {
+#define X(v) case v: fill_table_variant<v>(table, direction, variant); break;
         MUFFT_FOR_ENGINE_SIZES(X)
 #undef X
     default: break;

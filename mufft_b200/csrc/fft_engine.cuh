@@ -32,6 +32,22 @@ typedef float2 cpx;
 
 __device__ __forceinline__ cpx cadd(cpx a, cpx b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ cpx csub(cpx a, cpx b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Blackwell packed FP32 (add.f32x2 -> one FADD2 per complex add instead of two FADD): a complex
+// value is a natural (re, im) register pair.  PK = false keeps the scalar form; which is faster
+// depends on the register pressure of the kernel (pairs must sit in aligned registers), so it
+// is a per-shape choice (engine_shape_t::packed, measured in profiles/).
+template <bool PK>
+__device__ __forceinline__ cpx caddp(cpx a, cpx b)
+{
+    if constexpr (PK) return __fadd2_rn(a, b);
+    else return cadd(a, b);
+}
+template <bool PK>
+__device__ __forceinline__ cpx csubp(cpx a, cpx b)
+{
+    if constexpr (PK) return __fadd2_rn(a, make_float2(-b.x, -b.y));
+    else return csub(a, b);
+}
 __device__ __forceinline__ cpx cmul(cpx a, cpx b)
 {
     return make_float2(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x));
@@ -74,73 +90,138 @@ struct engine_shape_t {
     int radix[MUFFT_ENGINE_MAX_PASSES];
     int cta_threads; // row kernels: threads per CTA (several transforms share a CTA when N/R is smaller)
     int min_blocks;  // row kernels: __launch_bounds__ minimum CTAs per SM
+    int pad_shift;   // one padding element per 2^pad_shift elements of the exchange area (0 = derive from radix[0])
+    int packed;      // 1 = complex adds as packed FP32x2 instructions (FADD2), see caddp
 };
 
-// Widest radix first: the first pass (p == 1) needs no twiddles.  Every radix divides R.
+// Shape variants.  Variant 0 is the general one.  Variants 1 and 2 exist for the real transforms:
+// in ONE pass thread t owns butterfly i together with its mirror image q0 - i (q0 = N/r butterflies
+// per pass), so that the bins k and N-k of the half-length spectrum sit in the same thread:
+//   variant 1 (R2C): the LAST pass is mirrored; the resolve X[k] <- Z[k], Z[N-k] (ref kernel.c:47-82)
+//                    happens in registers on the way out, with no extra trip through shared memory;
+//   variant 2 (C2R): the FIRST pass is mirrored; X[k] and X[N-k] are loaded once, by the thread that
+//                    needs both (ref kernel.c:36-45).
+// The mirrored pass needs an even number (>= 2) of butterflies per thread, R / radix >= 2.
+// tools/mirror_model.py is the numpy model of these index maps and of their bank conflicts.
+#define MUFFT_VARIANT_GENERAL 0
+#define MUFFT_VARIANT_MIRROR_LAST 1
+#define MUFFT_VARIANT_MIRROR_FIRST 2
+#ifndef MUFFT_SHAPE_V
+#define MUFFT_SHAPE_V 0
+#endif
+#ifndef MUFFT_SHAPE_PAD
+#define MUFFT_SHAPE_PAD 0
+#endif
+#ifndef MUFFT_SHAPE_PACKED
+#define MUFFT_SHAPE_PACKED 1
+#endif
+// -DMUFFT_PACKED=<0|1> forces the packed flag of every shape (A/B measurements)
+
+// Widest radix first in variant 0: the first pass (p == 1) needs no twiddles.  Every radix divides R.
 // cta_threads / min_blocks are __launch_bounds__ of the row kernels: min_blocks is really a
 // register cap (65536 / (cta_threads * min_blocks) per thread) and decides how many CTAs share
-// an SM; the entries are the best of the sweeps in profiles/r01_shape_sweeps.txt.
-// -DMUFFT_SHAPE_N=<n> -DMUFFT_SHAPE_R=<R> -DMUFFT_SHAPE_R0=<r0> [-DMUFFT_SHAPE_R1=<r1> ...] overrides
-// one entry (used by tools/tune_shapes.sh to measure alternatives on the GPU).
-__host__ __device__ constexpr engine_shape_t engine_shape(int n)
+// an SM; the entries are the best of the sweeps in profiles/.
+// -DMUFFT_SHAPE_N=<n> [-DMUFFT_SHAPE_V=<variant>] -DMUFFT_SHAPE_R=<R> -DMUFFT_SHAPE_R0=<r0> [-DMUFFT_SHAPE_R1=<r1> ...]
+// overrides one entry (used by tools/ab.sh to measure alternatives on the GPU).
+__host__ __device__ constexpr engine_shape_t engine_shape(int n, int variant = 0)
 {
 #ifdef MUFFT_SHAPE_N
-    if (n == MUFFT_SHAPE_N) {
+    if (n == MUFFT_SHAPE_N && variant == MUFFT_SHAPE_V) {
         constexpr int r[] = { MUFFT_SHAPE_R0, MUFFT_SHAPE_R1, MUFFT_SHAPE_R2, MUFFT_SHAPE_R3 };
         int passes = 0, prod = 1;
         while (prod < MUFFT_SHAPE_N) prod *= r[passes++];
-        return { MUFFT_SHAPE_R, passes, { r[0], r[1], r[2], r[3] }, MUFFT_ROWS_CTA_THREADS, MUFFT_ROWS_MIN_BLOCKS };
+        return { MUFFT_SHAPE_R, passes, { r[0], r[1], r[2], r[3] }, MUFFT_ROWS_CTA_THREADS, MUFFT_ROWS_MIN_BLOCKS, MUFFT_SHAPE_PAD, MUFFT_SHAPE_PACKED };
     }
 #endif
+    if (variant == MUFFT_VARIANT_MIRROR_LAST) {
+        switch (n) {
+        case 512: return { 16, 3, { 16, 16, 2, 1 }, 256, 1, 4, 1 };
+        case 2048: return { 32, 3, { 32, 32, 2, 1 }, 64, 1, 5, 1 };
+        case 8192: return { 32, 3, { 32, 16, 16, 1 }, 256, 2, 5, 0 };
+        default: return { 0, 0, { 1, 1, 1, 1 }, 256, 1, 0, 1 };
+        }
+    }
+    if (variant == MUFFT_VARIANT_MIRROR_FIRST) {
+        switch (n) {
+        case 512: return { 16, 3, { 2, 16, 16, 1 }, 256, 1, 4, 1 };
+        case 2048: return { 16, 3, { 8, 16, 16, 1 }, 128, 6, 4, 1 };
+        case 8192: return { 32, 3, { 16, 16, 32, 1 }, 256, 2, 4, 0 };
+        default: return { 0, 0, { 1, 1, 1, 1 }, 256, 1, 0, 1 };
+        }
+    }
     switch (n) {
-    case 2: return { 2, 1, { 2, 1, 1, 1 } , 256, 1 };
-    case 4: return { 4, 1, { 4, 1, 1, 1 } , 256, 1 };
-    case 8: return { 4, 2, { 4, 2, 1, 1 } , 256, 1 };
-    case 16: return { 4, 2, { 4, 4, 1, 1 } , 256, 1 };
-    case 32: return { 4, 3, { 4, 4, 2, 1 } , 256, 1 };
-    case 64: return { 8, 2, { 8, 8, 1, 1 } , 256, 1 };
-    case 128: return { 8, 3, { 8, 8, 2, 1 } , 256, 1 };
-    case 256: return { 16, 2, { 16, 16, 1, 1 } , 256, 1 };
-    case 512: return { 16, 3, { 16, 16, 2, 1 } , 256, 1 };
-    case 1024: return { 32, 2, { 32, 32, 1, 1 }, 128, 1 };
-    case 2048: return { 32, 3, { 32, 32, 2, 1 }, 64, 1 };
-    case 4096: return { 16, 3, { 16, 16, 16, 1 }, 256, 3 };
-    case 8192: return { 32, 3, { 32, 16, 16, 1 }, 256, 2 };
-    default: return { 0, 0, { 1, 1, 1, 1 }, 256, 1 };
+    case 2: return { 2, 1, { 2, 1, 1, 1 } , 256, 1, 0, 1 };
+    case 4: return { 4, 1, { 4, 1, 1, 1 } , 256, 1, 0, 1 };
+    case 8: return { 4, 2, { 4, 2, 1, 1 } , 256, 1, 0, 1 };
+    case 16: return { 4, 2, { 4, 4, 1, 1 } , 256, 1, 0, 1 };
+    case 32: return { 4, 3, { 4, 4, 2, 1 } , 256, 1, 0, 1 };
+    case 64: return { 8, 2, { 8, 8, 1, 1 } , 256, 1, 0, 1 };
+    case 128: return { 8, 3, { 8, 8, 2, 1 } , 256, 1, 0, 1 };
+    case 256: return { 16, 2, { 16, 16, 1, 1 } , 256, 1, 0, 1 };
+    case 512: return { 16, 3, { 16, 16, 2, 1 } , 256, 1, 0, 1 };
+    case 1024: return { 32, 2, { 32, 32, 1, 1 }, 128, 1, 0, 0 };
+    case 2048: return { 32, 3, { 32, 32, 2, 1 }, 64, 1, 0, 1 };
+    case 4096: return { 16, 3, { 16, 16, 16, 1 }, 256, 3, 0, 1 };
+    case 8192: return { 32, 3, { 32, 16, 16, 1 }, 256, 2, 0, 0 };
+    default: return { 0, 0, { 1, 1, 1, 1 }, 256, 1, 0, 1 };
     }
 }
-__host__ __device__ constexpr int engine_regs(int n) { return engine_shape(n).regs; }
-__host__ __device__ constexpr int engine_num_passes(int n) { return engine_shape(n).passes; }
-__host__ __device__ constexpr int engine_radix(int n, int pass) { return engine_shape(n).radix[pass]; }
-__host__ __device__ constexpr int engine_threads(int n) { return n / engine_regs(n); }
-__host__ __device__ constexpr int engine_cta_threads(int n) { return engine_shape(n).cta_threads; }
-__host__ __device__ constexpr int engine_min_blocks(int n) { return engine_shape(n).min_blocks; }
-__host__ __device__ constexpr int engine_span(int n, int pass)
+__host__ __device__ constexpr int engine_regs(int n, int v = 0) { return engine_shape(n, v).regs; }
+__host__ __device__ constexpr bool engine_packed(int n, int v = 0)
+{
+#ifdef MUFFT_PACKED
+    return MUFFT_PACKED != 0;
+#else
+    return engine_shape(n, v).packed != 0;
+#endif
+}
+__host__ __device__ constexpr int engine_num_passes(int n, int v = 0) { return engine_shape(n, v).passes; }
+__host__ __device__ constexpr int engine_radix(int n, int pass, int v = 0) { return engine_shape(n, v).radix[pass]; }
+__host__ __device__ constexpr int engine_threads(int n, int v = 0) { return n / engine_regs(n, v); }
+__host__ __device__ constexpr int engine_cta_threads(int n, int v = 0) { return engine_shape(n, v).cta_threads; }
+__host__ __device__ constexpr int engine_min_blocks(int n, int v = 0) { return engine_shape(n, v).min_blocks; }
+__host__ __device__ constexpr int engine_span(int n, int pass, int v = 0)
 {
     int p = 1;
-    for (int j = 0; j < pass; j++) p *= engine_radix(n, j);
+    for (int j = 0; j < pass; j++) p *= engine_radix(n, j, v);
     return p;
+}
+// Is pass `pass` of variant v the mirrored one?
+__host__ __device__ constexpr bool engine_pass_mirrored(int n, int pass, int v)
+{
+    return (v == MUFFT_VARIANT_MIRROR_LAST && pass == engine_num_passes(n, v) - 1) ||
+           (v == MUFFT_VARIANT_MIRROR_FIRST && pass == 0);
+}
+// Does variant v exist for length n?
+__host__ __device__ constexpr bool engine_variant_exists(int n, int v)
+{
+    if (engine_regs(n, v) == 0) return false;
+    if (v == MUFFT_VARIANT_GENERAL) return true;
+    const int pass = v == MUFFT_VARIANT_MIRROR_LAST ? engine_num_passes(n, v) - 1 : 0;
+    const int nb = engine_regs(n, v) / engine_radix(n, pass, v);
+    return engine_num_passes(n, v) >= 2 && nb >= 2 && nb % 2 == 0;
 }
 // Offset (in cpx) of a pass's twiddle block inside the engine table; block layout is
 // [m-1][k], m = 1..r-1, k < p, value exp(dir*2*pi*i*k*m/(r*p)).  Pass 0 has no block.
-__host__ __device__ constexpr int engine_tw_offset(int n, int pass)
+__host__ __device__ constexpr int engine_tw_offset(int n, int pass, int v = 0)
 {
     int off = 0;
-    for (int j = 1; j < pass; j++) off += (engine_radix(n, j) - 1) * engine_span(n, j);
+    for (int j = 1; j < pass; j++) off += (engine_radix(n, j, v) - 1) * engine_span(n, j, v);
     return off;
 }
-__host__ __device__ constexpr int engine_tw_total(int n) { return engine_tw_offset(n, engine_num_passes(n)); }
+__host__ __device__ constexpr int engine_tw_total(int n, int v = 0) { return engine_tw_offset(n, engine_num_passes(n, v), v); }
 // One padding element after every 2^shift elements.  The first scatter writes with an element
-// stride of radix[0] across lanes, so the pad period is radix[0] (at least 8): lane l then hits
-// bank pair (radix[0] + 1) * l, distinct for 16 consecutive lanes.
-__host__ __device__ constexpr int engine_pad_shift(int n)
+// stride of radix[0] across lanes, so the default pad period is radix[0] (at least 8): lane l then
+// hits bank pair (radix[0] + 1) * l, distinct for 16 consecutive lanes.
+__host__ __device__ constexpr int engine_pad_shift(int n, int v = 0)
 {
-    int r = engine_radix(n, 0), s = 0;
+    if (engine_shape(n, v).pad_shift != 0) return engine_shape(n, v).pad_shift;
+    int r = engine_radix(n, 0, v), s = 0;
     while ((1 << s) < r) s++;
     return s < 3 ? 3 : s;
 }
 // Shared-memory footprint of one transform's exchange area, in cpx.
-__host__ __device__ constexpr int engine_smem_elems(int n) { return n + (n >> engine_pad_shift(n)) + 1; }
+__host__ __device__ constexpr int engine_smem_elems(int n, int v = 0) { return n + (n >> engine_pad_shift(n, v)) + 1; }
 
 // ---- small DFTs in registers -----------------------------------------------------------------
 // cos(2*pi*j/64), j = 0..16
@@ -182,35 +263,35 @@ __device__ __forceinline__ cpx mul_w64(cpx v)
 // X[k] = sum_n x[n] exp(DIR*2*pi*i*n*k/R).  Composite sizes use the Cooley-Tukey split R = A*B
 // with n = n1 + A*n2, k = B*k1 + k2: B-point DFTs over the stride-A subsequences, constant
 // twiddles exp(DIR*2*pi*i*n1*k2/R), then A-point DFTs across n1.
-template <int R, int DIR>
+template <int R, int DIR, bool PK>
 struct RegDft;
 
-template <int DIR>
-struct RegDft<2, DIR> {
+template <int DIR, bool PK>
+struct RegDft<2, DIR, PK> {
     static __device__ __forceinline__ void run(cpx (&x)[2])
     {
         const cpx a = x[0], b = x[1];
-        x[0] = cadd(a, b);
-        x[1] = csub(a, b);
+        x[0] = caddp<PK>(a, b);
+        x[1] = csubp<PK>(a, b);
     }
 };
 
-template <int DIR>
-struct RegDft<4, DIR> {
+template <int DIR, bool PK>
+struct RegDft<4, DIR, PK> {
     static __device__ __forceinline__ void run(cpx (&x)[4])
     {
-        const cpx t0 = cadd(x[0], x[2]), t1 = csub(x[0], x[2]);
-        const cpx t2 = cadd(x[1], x[3]), t3 = mul_w64<DIR, 16>(csub(x[1], x[3]));
-        x[0] = cadd(t0, t2);
-        x[1] = cadd(t1, t3);
-        x[2] = csub(t0, t2);
-        x[3] = csub(t1, t3);
+        const cpx t0 = caddp<PK>(x[0], x[2]), t1 = csubp<PK>(x[0], x[2]);
+        const cpx t2 = caddp<PK>(x[1], x[3]), t3 = mul_w64<DIR, 16>(csubp<PK>(x[1], x[3]));
+        x[0] = caddp<PK>(t0, t2);
+        x[1] = caddp<PK>(t1, t3);
+        x[2] = csubp<PK>(t0, t2);
+        x[3] = csubp<PK>(t1, t3);
     }
 };
 
 __host__ __device__ constexpr int dft_split_a(int r) { return r == 8 ? 2 : r == 16 ? 4 : r == 32 ? 4 : 8; }
 
-template <int R, int DIR>
+template <int R, int DIR, bool PK>
 struct RegDft {
     static __device__ __forceinline__ void run(cpx (&x)[R])
     {
@@ -220,7 +301,7 @@ struct RegDft {
             constexpr int n1 = decltype(n1c)::value;
             cpx s[B];
             static_for<B>([&](auto n2c) { constexpr int n2 = decltype(n2c)::value; s[n2] = x[n1 + A * n2]; });
-            RegDft<B, DIR>::run(s);
+            RegDft<B, DIR, PK>::run(s);
             static_for<B>([&](auto k2c) {
                 constexpr int k2 = decltype(k2c)::value;
                 x[n1 + A * k2] = mul_w64<DIR, n1 * k2 * (64 / R)>(s[k2]);
@@ -230,7 +311,7 @@ struct RegDft {
             constexpr int k2 = decltype(k2c)::value;
             cpx s[A];
             static_for<A>([&](auto n1c) { constexpr int n1 = decltype(n1c)::value; s[n1] = x[n1 + A * k2]; });
-            RegDft<A, DIR>::run(s);
+            RegDft<A, DIR, PK>::run(s);
             static_for<A>([&](auto k1c) { constexpr int k1 = decltype(k1c)::value; x[n1_slot<A, B>(k1, k2)] = s[k1]; });
         });
         // The second stage left X[B*k1 + k2] in slot k1 + A*k2; put it in natural order.
@@ -247,8 +328,8 @@ struct RegDft {
     static __host__ __device__ constexpr int n1_slot(int k1, int k2) { return k1 + A_ * k2; }
 };
 
-template <int R, int DIR>
-__device__ __forceinline__ void dft_regs(cpx (&v)[R]) { RegDft<R, DIR>::run(v); }
+template <int R, int DIR, bool PK = false>
+__device__ __forceinline__ void dft_regs(cpx (&v)[R]) { RegDft<R, DIR, PK>::run(v); }
 
 // ---- synchronisation of the threads of one transform ---------------------------------------
 // T threads share a transform.  T <= 32: they sit in one warp.  Otherwise a named barrier
@@ -270,15 +351,35 @@ __device__ __forceinline__ void engine_sync(int slot)
 template <int SHIFT>
 __device__ __forceinline__ int pad_pos(int pos) { return pos + (pos >> SHIFT); }
 
+// Butterfly of pass PASS that thread t runs in register group u (u < NB = R / r).  In general
+// t + u*T.  In a mirrored pass groups u < NB/2 hold i0 = t + u*T and group u + NB/2 holds its
+// mirror image q0 - i0 (q0 = N/r butterflies per pass); butterflies 0 and q0/2 are their own
+// images and share thread 0.
+template <int N, int PASS, int V>
+__device__ __forceinline__ int engine_bfly(int t, int u)
+{
+    constexpr int R = engine_regs(N, V);
+    constexpr int T = N / R;
+    if constexpr (engine_pass_mirrored(N, PASS, V)) {
+        constexpr int r = engine_radix(N, PASS, V);
+        constexpr int H = R / r / 2;
+        constexpr int Q0 = N / r;
+        if (u < H) return t + u * T;
+        const int i0 = t + (u - H) * T;
+        return i0 == 0 ? Q0 / 2 : Q0 - i0;
+    } else {
+        return t + u * T;
+    }
+}
+
 // Butterflies of pass PASS for thread t, in place: inputs v[u + m*NB] (m < r) become outputs
 // v[u + q*NB] (q < r).  `tw` points at the engine twiddle table of this transform length.
-template <int N, int DIR, int PASS>
-__device__ __forceinline__ void engine_butterflies(cpx (&v)[engine_regs(N)], const cpx *__restrict__ tw, int t)
+template <int N, int DIR, int PASS, int V = 0>
+__device__ __forceinline__ void engine_butterflies(cpx (&v)[engine_regs(N, V)], const cpx *__restrict__ tw, int t)
 {
-    constexpr int R = engine_regs(N);
-    constexpr int T = N / R;
-    constexpr int r = engine_radix(N, PASS);
-    constexpr int p = engine_span(N, PASS);
+    constexpr int R = engine_regs(N, V);
+    constexpr int r = engine_radix(N, PASS, V);
+    constexpr int p = engine_span(N, PASS, V);
     constexpr int NB = R / r;
     static_assert(NB * r == R, "every pass radix must divide the values per thread");
 #pragma unroll
@@ -287,12 +388,12 @@ __device__ __forceinline__ void engine_butterflies(cpx (&v)[engine_regs(N)], con
 #pragma unroll
         for (int m = 0; m < r; m++) x[m] = v[u + m * NB];
         if constexpr (PASS > 0) {
-            const int k = (t + u * T) & (p - 1);
-            const cpx *w = tw + engine_tw_offset(N, PASS) + k;
+            const int k = engine_bfly<N, PASS, V>(t, u) & (p - 1);
+            const cpx *w = tw + engine_tw_offset(N, PASS, V) + k;
 #pragma unroll
             for (int m = 1; m < r; m++) x[m] = cmul(x[m], __ldg(w + (m - 1) * p));
         }
-        dft_regs<r, DIR>(x);
+        dft_regs<r, DIR, engine_packed(N, V)>(x);
 #pragma unroll
         for (int q = 0; q < r; q++) v[u + q * NB] = x[q];
     }
@@ -301,18 +402,17 @@ __device__ __forceinline__ void engine_butterflies(cpx (&v)[engine_regs(N)], con
 // Scatter the outputs of pass PASS to shared memory.  `sm` is this transform's exchange area;
 // CS is the element stride between consecutive positions (1 for row transforms, the number of
 // columns in the tile for column transforms).
-template <int N, int PASS, int CS>
-__device__ __forceinline__ void engine_scatter(const cpx (&v)[engine_regs(N)], cpx *sm, int t)
+template <int N, int PASS, int CS, int V = 0>
+__device__ __forceinline__ void engine_scatter(const cpx (&v)[engine_regs(N, V)], cpx *sm, int t)
 {
-    constexpr int R = engine_regs(N);
-    constexpr int T = N / R;
-    constexpr int r = engine_radix(N, PASS);
-    constexpr int p = engine_span(N, PASS);
+    constexpr int R = engine_regs(N, V);
+    constexpr int r = engine_radix(N, PASS, V);
+    constexpr int p = engine_span(N, PASS, V);
     constexpr int NB = R / r;
-    constexpr int SH = engine_pad_shift(N);
+    constexpr int SH = engine_pad_shift(N, V);
 #pragma unroll
     for (int u = 0; u < NB; u++) {
-        const int i = t + u * T;
+        const int i = engine_bfly<N, PASS, V>(t, u);
         const int k = i & (p - 1);
         const int base = (i - k) * r + k;
 #pragma unroll
@@ -320,25 +420,38 @@ __device__ __forceinline__ void engine_scatter(const cpx (&v)[engine_regs(N)], c
     }
 }
 
-// Gather element t + e*T into slot e.
-template <int N, int CS>
-__device__ __forceinline__ void engine_gather(cpx (&v)[engine_regs(N)], const cpx *sm, int t)
+// Gather the inputs of pass PASS: element i + m*(N/r) of butterfly i into slot u + m*NB.  For an
+// ordinary pass that is element t + e*T into slot e.
+template <int N, int CS, int PASS = 1, int V = 0>
+__device__ __forceinline__ void engine_gather(cpx (&v)[engine_regs(N, V)], const cpx *sm, int t)
 {
-    constexpr int R = engine_regs(N);
+    constexpr int R = engine_regs(N, V);
     constexpr int T = N / R;
-    constexpr int SH = engine_pad_shift(N);
+    constexpr int SH = engine_pad_shift(N, V);
+    if constexpr (engine_pass_mirrored(N, PASS, V)) {
+        constexpr int r = engine_radix(N, PASS, V);
+        constexpr int NB = R / r;
+        constexpr int Q0 = N / r;
 #pragma unroll
-    for (int e = 0; e < R; e++) v[e] = sm[pad_pos<SH>(t + e * T) * CS];
+        for (int u = 0; u < NB; u++) {
+            const int i = engine_bfly<N, PASS, V>(t, u);
+#pragma unroll
+            for (int m = 0; m < r; m++) v[u + m * NB] = sm[pad_pos<SH>(i + m * Q0) * CS];
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < R; e++) v[e] = sm[pad_pos<SH>(t + e * T) * CS];
+    }
 }
 
-// Natural-order scatter (slot e -> element t + e*T); used by the R2C epilogue, which needs
-// Z[k] and Z[N-k] from different threads.
-template <int N, int CS>
-__device__ __forceinline__ void engine_scatter_natural(const cpx (&v)[engine_regs(N)], cpx *sm, int t)
+// Natural-order scatter (slot e -> element t + e*T); used by the R2C epilogue of variant 0,
+// which needs Z[k] and Z[N-k] from different threads.
+template <int N, int CS, int V = 0>
+__device__ __forceinline__ void engine_scatter_natural(const cpx (&v)[engine_regs(N, V)], cpx *sm, int t)
 {
-    constexpr int R = engine_regs(N);
+    constexpr int R = engine_regs(N, V);
     constexpr int T = N / R;
-    constexpr int SH = engine_pad_shift(N);
+    constexpr int SH = engine_pad_shift(N, V);
 #pragma unroll
     for (int e = 0; e < R; e++) sm[pad_pos<SH>(t + e * T) * CS] = v[e];
 }
@@ -346,16 +459,16 @@ __device__ __forceinline__ void engine_scatter_natural(const cpx (&v)[engine_reg
 // All passes of an N-point transform.  Every thread of the transform must call this (it
 // synchronises them); SYNC_T / SLOTS say how (see engine_sync): the row kernel passes the
 // threads of one transform, the column kernel passes the whole CTA.
-template <int N, int DIR, int CS, int SYNC_T, int SLOTS, int PASS = 0>
-__device__ __forceinline__ void engine_run(cpx (&v)[engine_regs(N)], cpx *sm, const cpx *__restrict__ tw, int t, int slot)
+template <int N, int DIR, int CS, int SYNC_T, int SLOTS, int PASS = 0, int V = 0>
+__device__ __forceinline__ void engine_run(cpx (&v)[engine_regs(N, V)], cpx *sm, const cpx *__restrict__ tw, int t, int slot)
 {
-    engine_butterflies<N, DIR, PASS>(v, tw, t);
-    if constexpr (PASS + 1 < engine_num_passes(N)) {
+    engine_butterflies<N, DIR, PASS, V>(v, tw, t);
+    if constexpr (PASS + 1 < engine_num_passes(N, V)) {
         if constexpr (PASS > 0) engine_sync<SYNC_T, SLOTS>(slot); // previous gather must be complete (WAR)
-        engine_scatter<N, PASS, CS>(v, sm, t);
+        engine_scatter<N, PASS, CS, V>(v, sm, t);
         engine_sync<SYNC_T, SLOTS>(slot);
-        engine_gather<N, CS>(v, sm, t);
-        engine_run<N, DIR, CS, SYNC_T, SLOTS, PASS + 1>(v, sm, tw, t, slot);
+        engine_gather<N, CS, PASS + 1, V>(v, sm, t);
+        engine_run<N, DIR, CS, SYNC_T, SLOTS, PASS + 1, V>(v, sm, tw, t, slot);
     }
 }
 

@@ -154,6 +154,7 @@ typedef struct axis {
     unsigned n;
     int direction;
     void *d_engine_tw; /* engine table, n <= MCU_ENGINE_MAX_N */
+    void *d_engine_tw_real; /* table of the mirrored-pass shape the R2C (forward) / C2R (inverse) row kernel uses, or NULL */
     void *d_roots;     /* exp(dir*2*pi*i*j/n), j < n: generic multi-pass kernels, two-kernel split */
     unsigned n1, n2;   /* two-kernel split n = n1 * n2 (0 = not used) */
     void *d_tw_n1, *d_tw_n2; /* engine tables of the two factors */
@@ -164,18 +165,19 @@ typedef struct axis {
 static void axis_free(axis *ax)
 {
     mcu_free(ax->d_engine_tw);
+    mcu_free(ax->d_engine_tw_real);
     mcu_free(ax->d_roots);
     mcu_free(ax->d_tw_n1);
     mcu_free(ax->d_tw_n2);
     memset(ax, 0, sizeof(*ax));
 }
 
-static void *make_engine_table(unsigned n, int direction)
+static void *make_engine_table(unsigned n, int direction, int variant)
 {
-    size_t entries = mcu_engine_table_size(n);
+    size_t entries = mcu_engine_table_size(n, variant);
     float *host = calloc(entries ? entries : 1, CPX);
     if (!host) return NULL;
-    mcu_engine_table_fill(host, n, direction);
+    mcu_engine_table_fill(host, n, direction, variant);
     void *dev = upload(host, (entries ? entries : 1) * CPX);
     free(host);
     return dev;
@@ -188,14 +190,20 @@ static int axis_init(axis *ax, unsigned n, int direction, int want_generic)
     ax->n = n;
     ax->direction = direction;
     if (n <= MCU_ENGINE_MAX_N) {
-        ax->d_engine_tw = make_engine_table(n, direction);
+        ax->d_engine_tw = make_engine_table(n, direction, 0);
         if (!ax->d_engine_tw) return -1;
+        /* the real transforms may run on a different engine shape (abi.h: mcu_rows_variant) */
+        const int variant = direction < 0 ? mcu_rows_variant(n, MCU_IN_COMPLEX, MCU_OUT_R2C) : mcu_rows_variant(n, MCU_IN_C2R, MCU_OUT_COMPLEX);
+        if (variant != 0) {
+            ax->d_engine_tw_real = make_engine_table(n, direction, variant);
+            if (!ax->d_engine_tw_real) return -1;
+        }
     }
     if (want_generic && mcu_split_n2(n) != 0) { /* rows use it above MCU_ENGINE_MAX_N, columns above MCU_COLS_MAX_N */
         ax->n2 = mcu_split_n2(n);
         ax->n1 = n / ax->n2;
-        ax->d_tw_n1 = make_engine_table(ax->n1, direction);
-        ax->d_tw_n2 = make_engine_table(ax->n2, direction);
+        ax->d_tw_n1 = make_engine_table(ax->n1, direction, 0);
+        ax->d_tw_n2 = make_engine_table(ax->n2, direction, 0);
         if (!ax->d_tw_n1 || !ax->d_tw_n2) return -1;
     }
     if (want_generic) {
@@ -504,7 +512,8 @@ static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode
     if (n <= MCU_ENGINE_MAX_N) {
         mcu_rows_args a;
         memset(&a, 0, sizeof(a));
-        a.out = out; a.in = in; a.in2 = in2; a.tw = ax->d_engine_tw; a.rtw = d_rtw;
+        a.out = out; a.in = in; a.in2 = in2; a.rtw = d_rtw;
+        a.tw = mcu_rows_variant(n, in_mode, out_mode) != 0 ? ax->d_engine_tw_real : ax->d_engine_tw;
         a.out_stride = out_stride; a.in_stride = in_stride; a.in2_stride = in2_stride;
         a.batch = batch; a.n = n; a.direction = ax->direction;
         a.in_mode = in_mode; a.out_mode = out_mode; a.norm = norm;

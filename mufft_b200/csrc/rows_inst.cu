@@ -22,43 +22,44 @@ static cudaError_t launch_mode(const mcu_rows_args &a, cudaStream_t stream)
 {
     constexpr int N = ROWS_N;
     constexpr int DIR = ROWS_DIR;
-    constexpr int TPC = rows_per_cta(N);
+    constexpr int V = rows_variant(N, IN_MODE, OUT_MODE);
+    constexpr int TPC = rows_per_cta(N, V);
     const size_t groups = (a.batch + TPC - 1) / TPC;
     if (groups == 0) return cudaSuccess;
 
-    if constexpr (rows_tma_supported(N, IN_MODE)) {
+    if constexpr (rows_tma_supported(N, IN_MODE, V)) {
         // whole 16-byte chunks from 16-byte aligned rows; C2R rows are read 2 elements beyond bin N/2
         const bool aligned = ((uintptr_t)a.in % 16 == 0) && ((a.in_stride * sizeof(float2)) % 16 == 0) &&
                              a.in_stride * sizeof(float2) >= (size_t)rows_land_bytes(N, IN_MODE);
         if (aligned && a.prefetch) {
             static int blocks_per_sm = 0; // per instantiation
             auto kernel = fft_rows_tma_kernel<N, DIR, IN_MODE, OUT_MODE>;
-            constexpr size_t smem = rows_tma_smem_bytes(N, IN_MODE);
+            constexpr size_t smem = rows_tma_smem_bytes(N, IN_MODE, V);
             if (blocks_per_sm == 0) {
                 cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (err != cudaSuccess) return err;
                 int dev = 0, per_sm = 0;
                 if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
                 if ((err = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return err;
-                if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, rows_cta_threads(N), smem)) != cudaSuccess) return err;
+                if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, rows_cta_threads(N, V), smem)) != cudaSuccess) return err;
                 if (per_sm < 1) return cudaErrorLaunchOutOfResources;
                 blocks_per_sm = per_sm;
             }
             size_t ctas = (size_t)g_sm_count * blocks_per_sm;
             if (ctas > groups) ctas = groups;
-            kernel<<<(unsigned)ctas, rows_cta_threads(N), smem, stream>>>(a);
+            kernel<<<(unsigned)ctas, rows_cta_threads(N, V), smem, stream>>>(a);
             return cudaGetLastError();
         }
     }
     static bool configured = false; // the attribute call is idempotent, so a race is harmless
     auto kernel = fft_rows_kernel<N, DIR, IN_MODE, OUT_MODE>;
     if (!configured) {
-        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem_bytes(N));
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem_bytes(N, V));
         if (err != cudaSuccess) return err;
         configured = true;
     }
     if (groups > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-    kernel<<<(unsigned)groups, rows_cta_threads(N), rows_smem_bytes(N), stream>>>(a);
+    kernel<<<(unsigned)groups, rows_cta_threads(N, V), rows_smem_bytes(N, V), stream>>>(a);
     return cudaGetLastError();
 }
 

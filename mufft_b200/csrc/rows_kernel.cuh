@@ -21,24 +21,47 @@
 
 namespace mufft {
 
-// Threads of one CTA and transforms per CTA for row transforms of length n.
-__host__ __device__ constexpr int rows_threads_per_transform(int n) { return n / engine_regs(n); }
-__host__ __device__ constexpr int rows_per_cta(int n)
+// Engine shape variant used by a (length, input mode, output mode) combination: the real
+// transforms take the mirrored-pass variants where the shape table has them (fft_engine.cuh).
+__host__ __device__ constexpr int rows_variant(int n, int in_mode, int out_mode)
 {
-    return rows_threads_per_transform(n) >= engine_cta_threads(n) ? 1 : engine_cta_threads(n) / rows_threads_per_transform(n);
+    if ((out_mode == MCU_OUT_R2C || out_mode == MCU_OUT_R2C_FULL) && engine_variant_exists(n, MUFFT_VARIANT_MIRROR_LAST))
+        return MUFFT_VARIANT_MIRROR_LAST;
+    if ((in_mode == MCU_IN_C2R || in_mode == MCU_IN_MUL_C2R) && engine_variant_exists(n, MUFFT_VARIANT_MIRROR_FIRST))
+        return MUFFT_VARIANT_MIRROR_FIRST;
+    return MUFFT_VARIANT_GENERAL;
 }
-__host__ __device__ constexpr int rows_cta_threads(int n) { return rows_threads_per_transform(n) * rows_per_cta(n); }
-// Exchange area per transform (also used by the R2C epilogue, so never zero).
-__host__ __device__ constexpr int rows_smem_elems(int n) { return engine_smem_elems(n); }
-__host__ __device__ constexpr size_t rows_smem_bytes(int n) { return (size_t)rows_per_cta(n) * rows_smem_elems(n) * sizeof(float2); }
 
-// ---- prologue: registers <- input, element k = t + e*T in slot e ---------------------------------
+// Threads of one CTA and transforms per CTA for row transforms of length n.
+__host__ __device__ constexpr int rows_threads_per_transform(int n, int v = 0) { return n / engine_regs(n, v); }
+__host__ __device__ constexpr int rows_per_cta(int n, int v = 0)
+{
+    return rows_threads_per_transform(n, v) >= engine_cta_threads(n, v) ? 1 : engine_cta_threads(n, v) / rows_threads_per_transform(n, v);
+}
+__host__ __device__ constexpr int rows_cta_threads(int n, int v = 0) { return rows_threads_per_transform(n, v) * rows_per_cta(n, v); }
+// Exchange area per transform (also used by the R2C epilogue, so never zero).
+__host__ __device__ constexpr int rows_smem_elems(int n, int v = 0) { return engine_smem_elems(n, v); }
+__host__ __device__ constexpr size_t rows_smem_bytes(int n, int v = 0) { return (size_t)rows_per_cta(n, v) * rows_smem_elems(n, v) * sizeof(float2); }
+
+// C2R resolve of one bin pair (ref kernel.c:36-45): given X[k], X[N-k] and rtw[k] returns z[k] and,
+// through `zm`, z[N-k] (rtw[N-k] = conj rtw[k], so the second costs no extra twiddle).
+__device__ __forceinline__ cpx c2r_pair(cpx xa, cpx xb, cpx w, cpx &zm)
+{
+    const cpx cb = cconj(xb);
+    const cpx a = cadd(xa, cb);
+    const cpx b = cmul(csub(xa, cb), w);
+    zm = cconj(csub(a, b));
+    return cadd(a, b);
+}
+
+// ---- prologue: registers <- input ------------------------------------------------------------------
+// Variant 0 / 1: element k = t + e*T in slot e.  Variant 2: the slots of the mirrored first pass.
 // `in` may point to global memory or to a shared-memory landing buffer.
-template <int N, int IN_MODE, typename Ptr>
-__device__ __forceinline__ void rows_load(cpx (&v)[engine_regs(N)], Ptr in, const cpx *__restrict__ in2,
+template <int N, int IN_MODE, int V, typename Ptr>
+__device__ __forceinline__ void rows_load(cpx (&v)[engine_regs(N, V)], Ptr in, const cpx *__restrict__ in2,
                                           const cpx *__restrict__ rtw, float norm, int t)
 {
-    constexpr int R = engine_regs(N);
+    constexpr int R = engine_regs(N, V);
     constexpr int T = N / R;
     if constexpr (IN_MODE == MCU_IN_COMPLEX) {
 #pragma unroll
@@ -55,6 +78,59 @@ __device__ __forceinline__ void rows_load(cpx (&v)[engine_regs(N)], Ptr in, cons
         for (int e = 0; e < R; e++) v[e] = in[t + e * T];
 #pragma unroll
         for (int e = 0; e < R; e++) v[e] = cscale(norm, cmul(v[e], w[e]));
+    } else if constexpr (V == MUFFT_VARIANT_MIRROR_FIRST) {
+        // C2R resolve, optionally on the product of two spectra, feeding the mirrored first pass:
+        // group u holds butterfly i0 (bins i0 + m*Q0), group u + H its image Q0 - i0 (bins
+        // Q0 - i0 + m*Q0); bin N - (i0 + m*Q0) is input r-1-m of the image.
+        constexpr bool mul = IN_MODE == MCU_IN_MUL_C2R;
+        constexpr int r = engine_radix(N, 0, V);
+        constexpr int NB = R / r;
+        constexpr int H = NB / 2;
+        constexpr int Q0 = N / r;
+        auto fetch = [&](int k) {
+            cpx x = in[k];
+            if constexpr (mul) x = cscale(norm, cmul(x, __ldg(in2 + k)));
+            return x;
+        };
+#pragma unroll
+        for (int u = 0; u < H; u++) {
+            const int i0 = t + u * T;
+            if (u == 0 && i0 == 0) {
+                // butterflies 0 and Q0/2 are their own images: bin m*Q0 pairs with (r-m)*Q0 (and 0
+                // with N), bin Q0/2 + m*Q0 with Q0/2 + (r-1-m)*Q0
+                cpx a[r + 1], b[r];
+#pragma unroll
+                for (int m = 0; m <= r; m++) a[m] = fetch(m * Q0);
+#pragma unroll
+                for (int m = 0; m < r; m++) b[m] = fetch(Q0 / 2 + m * Q0);
+#pragma unroll
+                for (int m = 0; m <= r / 2; m++) {
+                    cpx zm;
+                    const cpx z = c2r_pair(a[m], a[r - m], __ldg(rtw + m * Q0), zm);
+                    v[m * NB] = z;
+                    if (m != 0 && m != r - m) v[(r - m) * NB] = zm;
+                }
+#pragma unroll
+                for (int m = 0; m < r / 2; m++) {
+                    cpx zm;
+                    const cpx z = c2r_pair(b[m], b[r - 1 - m], __ldg(rtw + Q0 / 2 + m * Q0), zm);
+                    v[H + m * NB] = z;
+                    v[H + (r - 1 - m) * NB] = zm;
+                }
+            } else {
+                cpx a[r], b[r];
+#pragma unroll
+                for (int m = 0; m < r; m++) a[m] = fetch(i0 + m * Q0);
+#pragma unroll
+                for (int m = 0; m < r; m++) b[m] = fetch(Q0 - i0 + m * Q0);
+#pragma unroll
+                for (int m = 0; m < r; m++) {
+                    cpx zm;
+                    v[u + m * NB] = c2r_pair(a[m], b[r - 1 - m], __ldg(rtw + i0 + m * Q0), zm);
+                    v[u + H + (r - 1 - m) * NB] = zm;
+                }
+            }
+        }
     } else {
         // C2R resolve, optionally on the product of two spectra.  Reads bins k and N-k.
         constexpr bool mul = IN_MODE == MCU_IN_MUL_C2R;
@@ -73,25 +149,74 @@ __device__ __forceinline__ void rows_load(cpx (&v)[engine_regs(N)], Ptr in, cons
     }
 }
 
+// R2C resolve of one bin pair (ref kernel.c:47-82): from Z[k], Z[N-k] and rtw[k], X[k] and X[N-k]
+// (rtw[N-k] = conj rtw[k]); with FULL also X[k+N] and X[2N-k].
+template <bool FULL>
+__device__ __forceinline__ void r2c_pair_store(cpx *__restrict__ out, int k, int n, cpx za, cpx zb, cpx w)
+{
+    const cpx cb = cconj(zb);
+    const cpx fe = cadd(za, cb);
+    const cpx fo = cmul(w, csub(za, cb));
+    const cpx xk = cscale(0.5f, cadd(fe, fo));
+    const cpx xn = cscale(0.5f, csub(fe, fo)); // = conj X[N-k] = X[k+N]
+    out[k] = xk;
+    if (k != n - k) out[n - k] = cconj(xn);
+    if constexpr (FULL) {
+        out[k + n] = xn;
+        if (k != n - k) out[2 * n - k] = cconj(xk);
+    }
+}
+
 // ---- epilogue: output <- registers -----------------------------------------------------------------
-template <int N, int OUT_MODE, int T_SYNC, int SLOTS>
-__device__ __forceinline__ void rows_store(cpx (&v)[engine_regs(N)], cpx *__restrict__ out, cpx *sm,
+template <int N, int OUT_MODE, int T_SYNC, int SLOTS, int V>
+__device__ __forceinline__ void rows_store(cpx (&v)[engine_regs(N, V)], cpx *__restrict__ out, cpx *sm,
                                            const cpx *__restrict__ rtw, int t, int slot, bool active)
 {
-    constexpr int R = engine_regs(N);
+    constexpr int R = engine_regs(N, V);
     constexpr int T = N / R;
-    constexpr int SH = engine_pad_shift(N);
+    constexpr int SH = engine_pad_shift(N, V);
     if constexpr (OUT_MODE == MCU_OUT_COMPLEX) {
         if (active) {
 #pragma unroll
             for (int e = 0; e < R; e++) out[t + e * T] = v[e];
         }
+    } else if constexpr (V == MUFFT_VARIANT_MIRROR_LAST) {
+        // The mirrored last pass left Z[i0 + q*Q0] in slot u + q*NB and Z[Q0 - i0 + q*Q0] in slot
+        // u + H + q*NB; the partner of bin i0 + q*Q0 is output r-1-q of the image butterfly.
+        constexpr bool full = OUT_MODE == MCU_OUT_R2C_FULL;
+        constexpr int r = engine_radix(N, engine_num_passes(N, V) - 1, V);
+        constexpr int NB = R / r;
+        constexpr int H = NB / 2;
+        constexpr int Q0 = N / r;
+        if (!active) return;
+#pragma unroll
+        for (int u = 0; u < H; u++) {
+            const int i0 = t + u * T;
+            if (u == 0 && i0 == 0) {
+                // butterflies 0 and Q0/2 are their own images
+                out[0] = make_float2(v[0].x + v[0].y, 0.0f);
+                out[N] = make_float2(v[0].x - v[0].y, 0.0f);
+                if constexpr (full) {
+                    // bin 2N - 0 does not exist; X[N] is written above
+                }
+#pragma unroll
+                for (int q = 1; q <= r / 2; q++)
+                    r2c_pair_store<full>(out, q * Q0, N, v[q * NB], v[(r - q) * NB], __ldg(rtw + q * Q0));
+#pragma unroll
+                for (int q = 0; q < r / 2; q++)
+                    r2c_pair_store<full>(out, Q0 / 2 + q * Q0, N, v[H + q * NB], v[H + (r - 1 - q) * NB], __ldg(rtw + Q0 / 2 + q * Q0));
+            } else {
+#pragma unroll
+                for (int q = 0; q < r; q++)
+                    r2c_pair_store<full>(out, i0 + q * Q0, N, v[u + q * NB], v[u + H + (r - 1 - q) * NB], __ldg(rtw + i0 + q * Q0));
+            }
+        }
     } else {
         // X[k] = 1/2 ((Z[k] + conj Z[N-k]) + rtw[k] (Z[k] - conj Z[N-k])); Z[N-k] lives in another
         // thread, so the half-length spectrum makes one more trip through shared memory.
         constexpr bool full = OUT_MODE == MCU_OUT_R2C_FULL;
-        if constexpr (engine_num_passes(N) > 1) engine_sync<T_SYNC, SLOTS>(slot);
-        engine_scatter_natural<N, 1>(v, sm, t);
+        if constexpr (engine_num_passes(N, V) > 1) engine_sync<T_SYNC, SLOTS>(slot);
+        engine_scatter_natural<N, 1, V>(v, sm, t);
         engine_sync<T_SYNC, SLOTS>(slot);
         if (active) {
 #pragma unroll
@@ -115,11 +240,13 @@ __device__ __forceinline__ void rows_store(cpx (&v)[engine_regs(N)], cpx *__rest
 
 // ---- kernel 1: one group per CTA, direct loads ---------------------------------------------------
 template <int N, int DIR, int IN_MODE, int OUT_MODE>
-__global__ void __launch_bounds__(rows_cta_threads(N), engine_min_blocks(N)) fft_rows_kernel(const mcu_rows_args a)
+__global__ void __launch_bounds__(rows_cta_threads(N, rows_variant(N, IN_MODE, OUT_MODE)), engine_min_blocks(N, rows_variant(N, IN_MODE, OUT_MODE)))
+fft_rows_kernel(const mcu_rows_args a)
 {
-    constexpr int R = engine_regs(N);
+    constexpr int V = rows_variant(N, IN_MODE, OUT_MODE);
+    constexpr int R = engine_regs(N, V);
     constexpr int T = N / R;
-    constexpr int TPC = rows_per_cta(N);
+    constexpr int TPC = rows_per_cta(N, V);
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const int tid = threadIdx.x;
@@ -129,17 +256,17 @@ __global__ void __launch_bounds__(rows_cta_threads(N), engine_min_blocks(N)) fft
     const bool active = b < a.batch;
     if (!active) b = a.batch - 1; // keep the thread in step with the barriers; it stores nothing
 
-    cpx *sm = reinterpret_cast<cpx *>(smem_raw) + slot * rows_smem_elems(N);
+    cpx *sm = reinterpret_cast<cpx *>(smem_raw) + slot * rows_smem_elems(N, V);
     const cpx *__restrict__ tw = static_cast<const cpx *>(a.tw);
     const cpx *__restrict__ rtw = static_cast<const cpx *>(a.rtw);
     const cpx *__restrict__ in = static_cast<const cpx *>(a.in) + b * a.in_stride;
     const cpx *__restrict__ in2 = static_cast<const cpx *>(a.in2) + b * a.in2_stride;
 
     cpx v[R];
-    rows_load<N, IN_MODE>(v, in, in2, rtw, a.norm, t);
-    engine_run<N, DIR, 1, T, TPC>(v, sm, tw, t, slot);
+    rows_load<N, IN_MODE, V>(v, in, in2, rtw, a.norm, t);
+    engine_run<N, DIR, 1, T, TPC, 0, V>(v, sm, tw, t, slot);
     cpx *__restrict__ out = static_cast<cpx *>(a.out) + b * a.out_stride;
-    rows_store<N, OUT_MODE, T, TPC>(v, out, sm, rtw, t, slot, active);
+    rows_store<N, OUT_MODE, T, TPC, V>(v, out, sm, rtw, t, slot, active);
 }
 
 // ---- kernel 2: persistent, inputs prefetched into shared memory by bulk async copies ------------
@@ -176,23 +303,25 @@ __host__ __device__ constexpr int rows_land_bytes(int n, int in_mode)
 {
     return in_mode == MCU_IN_HALF ? n * 4 : (in_mode == MCU_IN_C2R || in_mode == MCU_IN_MUL_C2R) ? (n + 2) * 8 : n * 8;
 }
-__host__ __device__ constexpr size_t rows_tma_smem_bytes(int n, int in_mode)
+__host__ __device__ constexpr size_t rows_tma_smem_bytes(int n, int in_mode, int v = 0)
 {
-    return 128 + (size_t)rows_per_cta(n) * (MUFFT_TMA_STAGES * (size_t)rows_land_bytes(n, in_mode) + rows_smem_elems(n) * sizeof(float2));
+    return 128 + (size_t)rows_per_cta(n, v) * (MUFFT_TMA_STAGES * (size_t)rows_land_bytes(n, in_mode) + rows_smem_elems(n, v) * sizeof(float2));
 }
 // The bulk-copy path needs whole 16-byte chunks.
-__host__ __device__ constexpr bool rows_tma_supported(int n, int in_mode)
+__host__ __device__ constexpr bool rows_tma_supported(int n, int in_mode, int v = 0)
 {
-    return n >= 64 && rows_land_bytes(n, in_mode) % 16 == 0 && rows_tma_smem_bytes(n, in_mode) <= 227 * 1024 &&
-           MUFFT_TMA_STAGES * rows_per_cta(n) * 8 <= 128;
+    return n >= 64 && rows_land_bytes(n, in_mode) % 16 == 0 && rows_tma_smem_bytes(n, in_mode, v) <= 227 * 1024 &&
+           MUFFT_TMA_STAGES * rows_per_cta(n, v) * 8 <= 128;
 }
 
 template <int N, int DIR, int IN_MODE, int OUT_MODE>
-__global__ void __launch_bounds__(rows_cta_threads(N), engine_min_blocks(N)) fft_rows_tma_kernel(const mcu_rows_args a)
+__global__ void __launch_bounds__(rows_cta_threads(N, rows_variant(N, IN_MODE, OUT_MODE)), engine_min_blocks(N, rows_variant(N, IN_MODE, OUT_MODE)))
+fft_rows_tma_kernel(const mcu_rows_args a)
 {
-    constexpr int R = engine_regs(N);
+    constexpr int V = rows_variant(N, IN_MODE, OUT_MODE);
+    constexpr int R = engine_regs(N, V);
     constexpr int T = N / R;
-    constexpr int TPC = rows_per_cta(N);
+    constexpr int TPC = rows_per_cta(N, V);
     constexpr int STAGES = MUFFT_TMA_STAGES;
     constexpr int LAND = rows_land_bytes(N, IN_MODE);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -202,7 +331,7 @@ __global__ void __launch_bounds__(rows_cta_threads(N), engine_min_blocks(N)) fft
     const int t = tid - slot * T;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw) + slot * STAGES;
     unsigned char *land = smem_raw + 128 + (size_t)slot * STAGES * LAND;
-    cpx *sm = reinterpret_cast<cpx *>(smem_raw + 128 + (size_t)TPC * STAGES * LAND) + slot * rows_smem_elems(N);
+    cpx *sm = reinterpret_cast<cpx *>(smem_raw + 128 + (size_t)TPC * STAGES * LAND) + slot * rows_smem_elems(N, V);
     const cpx *__restrict__ tw = static_cast<const cpx *>(a.tw);
     const cpx *__restrict__ rtw = static_cast<const cpx *>(a.rtw);
     const size_t groups = (a.batch + TPC - 1) / TPC;
@@ -236,7 +365,7 @@ __global__ void __launch_bounds__(rows_cta_threads(N), engine_min_blocks(N)) fft
 
         cpx v[R];
         if (active) mbar_wait(bars + stage, parity);
-        rows_load<N, IN_MODE>(v, reinterpret_cast<const cpx *>(land + stage * LAND), in2, rtw, a.norm, t);
+        rows_load<N, IN_MODE, V>(v, reinterpret_cast<const cpx *>(land + stage * LAND), in2, rtw, a.norm, t);
         // Order this thread's generic-proxy reads of the landing buffer before the async-proxy
         // (bulk copy) write that refills it: without the fence a queued LDS can still be reading
         // when the next copy lands (seen as rare wrong transforms in long persistent loops).
@@ -246,9 +375,9 @@ __global__ void __launch_bounds__(rows_cta_threads(N), engine_min_blocks(N)) fft
         engine_sync<T, TPC>(slot);
         if (t == 0) issue(stage, g + (size_t)STAGES * gridDim.x);
 
-        engine_run<N, DIR, 1, T, TPC>(v, sm, tw, t, slot);
+        engine_run<N, DIR, 1, T, TPC, 0, V>(v, sm, tw, t, slot);
         cpx *__restrict__ out = static_cast<cpx *>(a.out) + b * a.out_stride;
-        rows_store<N, OUT_MODE, T, TPC>(v, out, sm, rtw, t, slot, active);
+        rows_store<N, OUT_MODE, T, TPC, V>(v, out, sm, rtw, t, slot, active);
 
         if (++stage == STAGES) {
             stage = 0;
