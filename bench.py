@@ -339,7 +339,8 @@ class Job:
                 os.environ.setdefault("MASTER_PORT", "29577")
                 dist_mod.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
             world = dist_mod.get_world_size()
-            self.slab = SlabFFT2D(n, ny, m.MUFFT_FORWARD, device=dev, chunks=int(os.environ.get("MUFFT_SLAB_CHUNKS", "8")))
+            self.slab = SlabFFT2D(n, ny, m.MUFFT_FORWARD, device=dev, chunks=int(os.environ.get("MUFFT_SLAB_CHUNKS", "8")),
+                                  exchange=os.environ.get("MUFFT_SLAB_EXCHANGE") or None)
             self.inp = torch.view_as_complex(rnd(ny // world, n * 2).view(ny // world, n, 2))
             self.out = torch.empty((ny, n // world), dtype=torch.complex64, device=dev)
             self.buf = self.slab.buffers()

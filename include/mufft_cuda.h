@@ -55,6 +55,27 @@ int mufft_execute_plan_1d_batch_async(mufft_plan_1d *plan, void *output, const v
 int mufft_execute_plan_1d_columns(mufft_plan_1d *plan, void *output, const void *input, size_t width,
                                   size_t output_pitch_bytes, size_t input_pitch_bytes);
 
+/* Row pass and exchange step of a slab-decomposed 2D transform in ONE kernel: `batch` rows are
+ * transformed with the plan (plain C2C, length N) and element x of row b is stored to device
+ * p = x / (N / peers), at peer_outputs[p] + ((dest_row0 + b) * (N / peers) + x % (N / peers)) complex
+ * elements - i.e. into the [rows][N / peers] column slab of device p.  The pointers are device
+ * pointers valid in this process: local memory for the own slab, peer memory mapped with
+ * mufft_cuda_ipc_import for the others, so the kernel's stores are the all-to-all transpose and
+ * travel over NVLink; no pack pass, no separate collective.  `peers` must be a power of two that
+ * divides N.  Enqueued on the current stream; the caller synchronises the devices (any barrier
+ * ordered after this call on every device) before reading the slabs. */
+int mufft_execute_plan_1d_batch_scatter_async(mufft_plan_1d *plan, void *const *peer_outputs, unsigned peers,
+                                              size_t dest_row0, const void *input, size_t batch, size_t input_stride_bytes);
+
+/* Plain device memory (cudaMalloc) that can be shared between the processes of one node, and
+ * CUDA IPC handles (64 bytes) for it.  mufft_cuda_ipc_import maps another process's allocation
+ * into this one (peer access over NVLink is enabled on demand). */
+void *mufft_cuda_device_alloc(size_t size);
+void mufft_cuda_device_free(void *ptr);
+int mufft_cuda_ipc_export(void *handle64, void *device_ptr);
+void *mufft_cuda_ipc_import(const void *handle64);
+int mufft_cuda_ipc_close(void *ptr);
+
 /* `batch` independent images, tightly packed one after another (each laid out as fft.h
  * describes for the plan's kind: [Ny][Nx] complex, R2C output / C2R input with row pitch Nx
  * complex).  C2R output images are Nx*Ny floats each, densely packed. */

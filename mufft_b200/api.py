@@ -65,6 +65,12 @@ SIGNATURES = {
     "mufft_execute_plan_1d_batch": (_i, [_vp, _vp, _vp, _sz, _sz, _sz]),
     "mufft_execute_plan_1d_batch_async": (_i, [_vp, _vp, _vp, _sz, _sz, _sz]),
     "mufft_execute_plan_1d_columns": (_i, [_vp, _vp, _vp, _sz, _sz, _sz]),
+    "mufft_execute_plan_1d_batch_scatter_async": (_i, [_vp, C.POINTER(C.c_void_p), _u, _sz, _vp, _sz, _sz]),
+    "mufft_cuda_device_alloc": (_vp, [_sz]),
+    "mufft_cuda_device_free": (None, [_vp]),
+    "mufft_cuda_ipc_export": (_i, [_vp, _vp]),
+    "mufft_cuda_ipc_import": (_vp, [_vp]),
+    "mufft_cuda_ipc_close": (_i, [_vp]),
     "mufft_execute_plan_2d_batch": (_i, [_vp, _vp, _vp, _sz]),
     "mufft_execute_plan_2d_batch_async": (_i, [_vp, _vp, _vp, _sz]),
     "mufft_execute_conv_input_batch": (_i, [_vp, _u, _vp, _vp, _sz]),

@@ -28,8 +28,21 @@ enum {
 enum {
     MCU_OUT_COMPLEX = 0,  /* out[i] = y[i] */
     MCU_OUT_R2C = 1,      /* N+1 bins from the N-point half-length spectrum  (ref kernel.c:47-63) */
-    MCU_OUT_R2C_FULL = 2  /* all 2N bins                                      (ref kernel.c:65-82) */
+    MCU_OUT_R2C_FULL = 2, /* all 2N bins                                      (ref kernel.c:65-82) */
+    MCU_OUT_PEERS = 3     /* out[i] = y[i], scattered over the column slabs of several devices (mcu_peer_dest) */
 };
+
+/* Destination of a row transform whose output is the exchange step of a slab-decomposed 2D
+ * transform: element x of transform b goes to device p = x >> shift, into
+ * base[p] + (row0 + b) * pitch + (x & ((1 << shift) - 1)), all in complex elements.  The bases are
+ * device pointers valid in this process (local memory or peer memory mapped through CUDA IPC),
+ * so the stores of the row kernel ARE the all-to-all transpose: they travel over NVLink. */
+#define MCU_MAX_PEERS 16
+typedef struct mcu_peer_dest {
+    void *base[MCU_MAX_PEERS];
+    size_t row0, pitch;
+    unsigned shift;       /* log2(columns per device) */
+} mcu_peer_dest;
 
 typedef struct mcu_rows_args {
     void *out;
@@ -46,6 +59,7 @@ typedef struct mcu_rows_args {
     int in_mode, out_mode;
     float norm;
     int prefetch;          /* 1 = use the persistent bulk-copy prefetch kernel when the input allows it */
+    mcu_peer_dest peers;   /* out_mode == MCU_OUT_PEERS only */
 } mcu_rows_args;
 
 typedef struct mcu_cols_args {
@@ -75,6 +89,8 @@ typedef struct mcu_rowst_args {
     size_t batch;
     unsigned n, n1, n2;
     int direction;
+    int to_peers;          /* 1 = scatter X over the devices of `peers` instead of writing `out` */
+    mcu_peer_dest peers;
 } mcu_rowst_args;
 
 /* Fused 2D C2C kernel (fft2d_kernel.cuh): whole batch in one persistent launch. */
@@ -128,6 +144,10 @@ int mcu_get_device(int *device);
 int mcu_sm_count(int *count);
 const char *mcu_error_string(int err);
 
+/* CUDA IPC: 64-byte handle of a cudaMalloc allocation / mapping of another process's allocation */
+int mcu_ipc_export(void *handle64, void *ptr);
+int mcu_ipc_import(void **ptr, const void *handle64);
+int mcu_ipc_close(void *ptr);
 int mcu_malloc(void **ptr, size_t bytes);
 int mcu_free(void *ptr);
 int mcu_malloc_managed(void **ptr, size_t bytes);

@@ -9,6 +9,7 @@
 
 #include <atomic>
 #include <math.h>
+#include <string.h>
 
 namespace mufft {
 #define MUFFT_DECLARE_ROWS(n) cudaError_t rows_launch_##n##_fwd(const mcu_rows_args &, cudaStream_t); cudaError_t rows_launch_##n##_inv(const mcu_rows_args &, cudaStream_t);
@@ -163,6 +164,18 @@ int mcu_sm_count(int *count)
 }
 const char *mcu_error_string(int err) { return cudaGetErrorString((cudaError_t)err); }
 
+int mcu_ipc_export(void *handle64, void *ptr)
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    return (int)cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t *>(handle64), ptr);
+}
+int mcu_ipc_import(void **ptr, const void *handle64)
+{
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    return (int)cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+}
+int mcu_ipc_close(void *ptr) { return ptr ? (int)cudaIpcCloseMemHandle(ptr) : 0; }
 int mcu_malloc(void **ptr, size_t bytes) { return (int)cudaMalloc(ptr, bytes ? bytes : 256); }
 int mcu_free(void *ptr) { return ptr ? (int)cudaFree(ptr) : 0; }
 int mcu_malloc_managed(void **ptr, size_t bytes) { return (int)cudaMallocManaged(ptr, bytes ? bytes : 256, cudaMemAttachGlobal); }

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, 2) fft2d_fused_kernel(const
     constexpr unsigned NR = NY / ROWS; // row tickets per image
     constexpr unsigned NC = NX / COLS; // column tickets per image
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ unsigned s_ticket[2];
+    __shared__ unsigned s_ticket[2], s_wait[2];
     cpx *smem = reinterpret_cast<cpx *>(smem_raw);
 
     const int tid = threadIdx.x;
@@ -91,19 +91,44 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, 2) fft2d_fused_kernel(const
         image = (unsigned)a.batch - lag + (unsigned)(kk / NC); tile = (unsigned)(kk % NC);
         return false;
     };
-    // Thread 0 publishes a ticket to the CTA only once its dependency is met (a column ticket
-    // needs all row tickets of its image), so one CTA barrier per ticket is enough.
+    // Rows of a finished row tile are announced LATE: a release needs the tile's stores to have
+    // reached L2 (fence), and waiting for that right after issuing them would put a full store
+    // round trip on the critical path of every row tile.  Thread 0 remembers the image instead
+    // (`pending`) and releases it while the NEXT tile's loads are in flight, when the stores have
+    // long landed.  (All threads' stores precede the CTA barrier at the top of the next
+    // iteration, thread 0's fence follows it: fence cumulativity covers them.)
+    unsigned pending = ~0u; // thread 0 only
+    auto release_pending = [&]() {
+        if (pending != ~0u) {
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(rows_done + pending), "r"((unsigned)ROWS) : "memory");
+            pending = ~0u;
+        }
+    };
+    auto wait_rows = [&](unsigned image) {
+        unsigned ns = 32;
+        while (ld_relaxed(rows_done + image) < (unsigned)NY) {
+            __nanosleep(ns);
+            if (ns < 1024) ns *= 2;
+        }
+    };
+    // Thread 0 publishes a ticket to the CTA once its dependency is met (a column ticket needs all
+    // row tickets of its image), so one CTA barrier per ticket is enough.  The exception: the
+    // dependency is not met yet AND this CTA still holds back the rows of the tile it has just
+    // stored (they may be the very rows it would wait for, and they cannot be released before the
+    // next CTA barrier has covered every thread's stores).  Then the ticket is published with the
+    // wait flag set and the wait happens after that barrier.
     auto publish = [&](unsigned k, int slot) {
-        unsigned image, tile;
+        unsigned image, tile, wait = 0;
         if (k < total && !decode(k, image, tile)) {
-            unsigned ns = 32;
-            while (ld_relaxed(rows_done + image) < (unsigned)NY) {
-                __nanosleep(ns);
-                if (ns < 1024) ns *= 2;
+            if (ld_relaxed(rows_done + image) < (unsigned)NY) {
+                if (pending != ~0u) wait = 1;
+                else wait_rows(image);
             }
             asm volatile("fence.acq_rel.gpu;" ::: "memory");
         }
         s_ticket[slot] = k;
+        s_wait[slot] = wait;
     };
 
     unsigned next_ticket = 0;
@@ -111,7 +136,20 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, 2) fft2d_fused_kernel(const
     for (int it = 0;; it++) {
         __syncthreads(); // ticket visible; the previous ticket's users of the exchange area are done
         const unsigned k = s_ticket[it & 1];
-        if (k >= total) break;
+        if (k >= total) {
+            if (tid == 0) release_pending();
+            break;
+        }
+        if (s_wait[it & 1]) { // rare: see publish
+            if (tid == 0) {
+                unsigned image, tile;
+                decode(k, image, tile);
+                release_pending();
+                wait_rows(image);
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            }
+            __syncthreads();
+        }
         // draw the next ticket now; its round trip to L2 overlaps this tile
         if (tid == 0) next_ticket = atomicAdd(ticket_counter, 1u);
         unsigned image, tile;
@@ -132,20 +170,19 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, 2) fft2d_fused_kernel(const
                 if ((reinterpret_cast<uintptr_t>(nxt) & 15) == 0)
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt), "r"((unsigned)(ROWS * NX * sizeof(cpx))) : "memory");
             }
+            if (tid == 0) release_pending(); // the previous row tile, while this one's loads fly
             engine_run<NX, DIR, 1, TX, ROWS>(v, smem + slot * engine_smem_elems(NX), twx, t, slot);
             cpx *__restrict__ o = out + row * NX;
 #pragma unroll
             for (int e = 0; e < RX; e++) o[t + e * TX] = v[e];
-            // each row signals on its own: the threads of one transform meet, then one of them
-            // releases the row (no CTA barrier on the row path)
-            engine_sync<TX, ROWS>(slot);
-            if (t == 0) red_release_add(rows_done + image, 1u);
+            if (tid == 0) pending = image;
         } else {
             const int c = tid % COLS, t = tid / COLS;
             cpx *__restrict__ col = out + (size_t)tile * COLS + c;
             cpx v[RY];
 #pragma unroll
             for (int e = 0; e < RY; e++) v[e] = __ldcg(col + (size_t)(t + e * TY) * NX); // written by other SMs: L2 only
+            if (tid == 0) release_pending();
             engine_run<NY, DIR, COLS, MUFFT_F2D_THREADS, 1>(v, smem + c, twy, t, 0);
 #pragma unroll
             for (int e = 0; e < RY; e++) __stcs(col + (size_t)(t + e * TY) * NX, v[e]);

@@ -34,8 +34,13 @@
 enum { KIND_C2C = 0, KIND_R2C = 1, KIND_R2C_FULL = 2, KIND_C2R = 3 };
 
 #define CPX 8u                              /* bytes per complex sample */
-#define STAGE_SLOTS 3
-#define STAGE_CHUNK_BYTES ((size_t)32 << 20) /* per-slot staging granularity */
+#define STAGE_SLOTS_MAX 8
+/* Staging pipeline of the host-pointer path: number of slots (streams) and bytes per chunk.
+ * MUFFT_CUDA_STAGE_SLOTS / MUFFT_CUDA_STAGE_CHUNK_MB in the environment override them (tuning). */
+static int g_stage_slots = 3;
+static size_t g_stage_chunk_bytes = (size_t)64 << 20;
+#define STAGE_SLOTS g_stage_slots
+#define STAGE_CHUNK_BYTES g_stage_chunk_bytes
 #define SCRATCH_CAP_BYTES ((size_t)1 << 30)
 #define ZERO_COPY_BYTES ((size_t)64 << 10)   /* pinned buffers up to this size are used in place */
 #define MAX_STEPS 32
@@ -50,6 +55,10 @@ __attribute__((constructor)) static void read_env(void)
 {
     const char *e = getenv("MUFFT_CUDA_PREFETCH");
     if (e != NULL) g_prefetch = e[0] == '1';
+    e = getenv("MUFFT_CUDA_STAGE_SLOTS");
+    if (e != NULL && atoi(e) >= 1 && atoi(e) <= STAGE_SLOTS_MAX) g_stage_slots = atoi(e);
+    e = getenv("MUFFT_CUDA_STAGE_CHUNK_MB");
+    if (e != NULL && atoi(e) >= 1 && atoi(e) <= 1024) g_stage_chunk_bytes = (size_t)atoi(e) << 20;
 }
 void mufft_cuda_set_prefetch(int enable) { g_prefetch = enable != 0; }
 /* Lengths above MCU_ENGINE_MAX_N: 1 (default) = two kernels (column transforms of length N1, then
@@ -282,7 +291,7 @@ typedef struct stage_slot {
 } stage_slot;
 
 typedef struct stage {
-    stage_slot slot[STAGE_SLOTS];
+    stage_slot slot[STAGE_SLOTS_MAX];
     void *d_shared;
     size_t shared_bytes;
     void *ev_begin;
@@ -311,7 +320,7 @@ static int stage_init(stage *st)
 
 static void stage_free(stage *st)
 {
-    for (int i = 0; i < STAGE_SLOTS; i++) {
+    for (int i = 0; i < STAGE_SLOTS_MAX; i++) {
         mcu_stream_destroy(st->slot[i].stream);
         mcu_free(st->slot[i].d_in);
         mcu_free(st->slot[i].d_in2);
@@ -502,6 +511,9 @@ mufft_plan_1d *mufft_create_plan_1d_c2r(unsigned N, unsigned flags)
 
 int mufft_cuda_plan_1d_uses_engine(const mufft_plan_1d *plan) { return plan ? plan->use_engine : 0; }
 
+/* Destination of MCU_OUT_PEERS row transforms (set by mufft_execute_plan_1d_batch_scatter_async). */
+static __thread const mcu_peer_dest *tls_peers = NULL;
+
 /* Row transforms on device-visible memory; strides in complex elements.  One fused kernel on
  * the engine, or pre-resolve / passes / post-resolve through scratch beyond its limit. */
 static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode, int out_mode, float norm,
@@ -518,7 +530,12 @@ static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode
         a.batch = batch; a.n = n; a.direction = ax->direction;
         a.in_mode = in_mode; a.out_mode = out_mode; a.norm = norm;
         a.prefetch = g_prefetch;
+        if (out_mode == MCU_OUT_PEERS) a.peers = *tls_peers;
         return mcu_launch_rows(&a, stream);
+    }
+    if (out_mode == MCU_OUT_PEERS && !(ax->n2 != 0 && g_two_kernel)) {
+        snprintf(tls_error, sizeof(tls_error), "scatter: this length has no two-kernel path");
+        return -1;
     }
 
     /* Generic path: bounded scratch, so walk the batch in chunks. */
@@ -561,6 +578,7 @@ static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode
             memset(&ra, 0, sizeof(ra));
             ra.in = scr->buf[0]; ra.in_batch = n; ra.tw = ax->d_tw_n2; ra.roots = ax->d_roots;
             if (out_mode == MCU_OUT_COMPLEX) { ra.out = dst; ra.out_batch = out_stride; }
+            else if (out_mode == MCU_OUT_PEERS) { ra.to_peers = 1; ra.peers = *tls_peers; ra.peers.row0 += done; }
             else { ra.out = scr->buf[1]; ra.out_batch = n; }
             ra.batch = cnt; ra.n = n; ra.n1 = ax->n1; ra.n2 = ax->n2; ra.direction = ax->direction;
             TRY(mcu_launch_rowst(&ra, stream));
@@ -582,7 +600,7 @@ static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode
             cur = p.out;
             cur_stride = p.out_batch;
         }
-        if (out_mode != MCU_OUT_COMPLEX) {
+        if (out_mode != MCU_OUT_COMPLEX && out_mode != MCU_OUT_PEERS) {
             mcu_resolve_args r;
             memset(&r, 0, sizeof(r));
             r.out = dst; r.in = cur; r.rtw = d_rtw;
@@ -679,6 +697,52 @@ int mufft_execute_plan_1d_batch_async(mufft_plan_1d *plan, void *output, const v
     plan_modes(plan, &in_mode, &out_mode);
     return exec_1d(plan, in_mode, out_mode, 1.0f, output, output_stride_bytes, input, input_stride_bytes, NULL, 0, 0, batch, 1);
 }
+
+/* Exchange step of a slab-decomposed 2D transform fused into the row pass (see mufft_cuda.h). */
+int mufft_execute_plan_1d_batch_scatter_async(mufft_plan_1d *plan, void *const *peer_outputs, unsigned peers,
+                                              size_t dest_row0, const void *input, size_t batch, size_t input_stride_bytes)
+{
+    if (plan == NULL || plan->kind != KIND_C2C || plan->zero_pad || peers == 0 || peers > MCU_MAX_PEERS ||
+        (peers & (peers - 1)) != 0 || plan->n % peers != 0 || input_stride_bytes % CPX != 0) {
+        snprintf(tls_error, sizeof(tls_error), "scatter: needs a plain C2C plan and a power-of-two number of devices dividing N");
+        return -1;
+    }
+    const size_t in_stride = input_stride_bytes ? input_stride_bytes : (size_t)plan->n * CPX;
+    if (batch == 0) return 0;
+    if (!device_visible(mcu_pointer_kind(input), in_stride * (batch - 1) + (size_t)plan->n * CPX)) {
+        snprintf(tls_error, sizeof(tls_error), "scatter: needs device-accessible (device or managed) pointers");
+        return -1;
+    }
+    mcu_peer_dest d;
+    memset(&d, 0, sizeof(d));
+    const unsigned cols = plan->n / peers;
+    for (unsigned p = 0; p < peers; p++) d.base[p] = peer_outputs[p];
+    d.row0 = dest_row0;
+    d.pitch = cols;
+    while ((1u << d.shift) < cols) d.shift++;
+    tls_peers = &d;
+    int err = run_rows(&plan->ax, &plan->scr, NULL, MCU_IN_COMPLEX, MCU_OUT_PEERS, 1.0f, NULL, 0, input, in_stride / CPX,
+                       NULL, 0, batch, tls_stream);
+    tls_peers = NULL;
+    return err;
+}
+
+void *mufft_cuda_device_alloc(size_t size)
+{
+    void *ptr = NULL;
+    if (!have_device()) return NULL;
+    if (fail(mcu_malloc(&ptr, size), "cudaMalloc") != 0) return NULL;
+    return ptr;
+}
+void mufft_cuda_device_free(void *ptr) { (void)mcu_free(ptr); }
+int mufft_cuda_ipc_export(void *handle64, void *device_ptr) { return fail(mcu_ipc_export(handle64, device_ptr), "cudaIpcGetMemHandle"); }
+void *mufft_cuda_ipc_import(const void *handle64)
+{
+    void *ptr = NULL;
+    if (fail(mcu_ipc_import(&ptr, handle64), "cudaIpcOpenMemHandle") != 0) return NULL;
+    return ptr;
+}
+int mufft_cuda_ipc_close(void *ptr) { return fail(mcu_ipc_close(ptr), "cudaIpcCloseMemHandle"); }
 
 static int run_cols_axis(const axis *ax, scratch *scr_cols, void *out, size_t out_pitch, size_t out_image,
                          const void *in, size_t in_pitch, size_t in_image, unsigned width, size_t images, void *stream);

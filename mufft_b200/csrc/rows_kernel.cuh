@@ -167,6 +167,24 @@ __device__ __forceinline__ void r2c_pair_store(cpx *__restrict__ out, int k, int
     }
 }
 
+// Exchange-step epilogue (MCU_OUT_PEERS): element x of transform b goes to the column slab of
+// device x >> shift.  Consecutive lanes hold consecutive x, so every warp store is a contiguous
+// run inside one device's slab (local memory or NVLink peer memory).
+template <int N, int V>
+__device__ __forceinline__ void rows_store_peers(const cpx (&v)[engine_regs(N, V)], const mcu_peer_dest &d, size_t b, int t)
+{
+    constexpr int R = engine_regs(N, V);
+    constexpr int T = N / R;
+    const size_t row = (d.row0 + b) * d.pitch;
+    const unsigned mask = (1u << d.shift) - 1u;
+#pragma unroll
+    for (int e = 0; e < R; e++) {
+        const unsigned x = (unsigned)(t + e * T);
+        cpx *dst = static_cast<cpx *>(d.base[x >> d.shift]) + row + (x & mask);
+        *dst = v[e];
+    }
+}
+
 // ---- epilogue: output <- registers -----------------------------------------------------------------
 template <int N, int OUT_MODE, int T_SYNC, int SLOTS, int V>
 __device__ __forceinline__ void rows_store(cpx (&v)[engine_regs(N, V)], cpx *__restrict__ out, cpx *sm,
@@ -265,8 +283,12 @@ fft_rows_kernel(const mcu_rows_args a)
     cpx v[R];
     rows_load<N, IN_MODE, V>(v, in, in2, rtw, a.norm, t);
     engine_run<N, DIR, 1, T, TPC, 0, V>(v, sm, tw, t, slot);
-    cpx *__restrict__ out = static_cast<cpx *>(a.out) + b * a.out_stride;
-    rows_store<N, OUT_MODE, T, TPC, V>(v, out, sm, rtw, t, slot, active);
+    if constexpr (OUT_MODE == MCU_OUT_PEERS) {
+        if (active) rows_store_peers<N, V>(v, a.peers, b, t);
+    } else {
+        cpx *__restrict__ out = static_cast<cpx *>(a.out) + b * a.out_stride;
+        rows_store<N, OUT_MODE, T, TPC, V>(v, out, sm, rtw, t, slot, active);
+    }
 }
 
 // ---- kernel 2: persistent, inputs prefetched into shared memory by bulk async copies ------------

@@ -76,9 +76,20 @@ __global__ void __launch_bounds__(rowst_cta_threads(N2)) fft_rowst_kernel(const 
 #pragma unroll
         for (int e = 0; e < R; e++) v[e] = sm2[pad_pos<SH>(t2 + e * T)];
         engine_butterflies<N2, DIR, NP - 1>(v, tw, t2);
-        cpx *__restrict__ out = static_cast<cpx *>(a.out) + b * a.out_batch + (size_t)blockIdx.x * TR + slot2;
+        if (a.to_peers) {
+            // exchange step of a slab 2D transform: X[x] goes to the column slab of device x >> shift
+            const size_t row = (a.peers.row0 + b) * a.peers.pitch;
+            const unsigned cmask = (1u << a.peers.shift) - 1u;
 #pragma unroll
-        for (int e = 0; e < R; e++) out[(size_t)(t2 + e * T) * n1] = v[e];
+            for (int e = 0; e < R; e++) {
+                const unsigned x = (unsigned)(t2 + e * T) * n1 + blockIdx.x * TR + slot2;
+                static_cast<cpx *>(a.peers.base[x >> a.peers.shift])[row + (x & cmask)] = v[e];
+            }
+        } else {
+            cpx *__restrict__ out = static_cast<cpx *>(a.out) + b * a.out_batch + (size_t)blockIdx.x * TR + slot2;
+#pragma unroll
+            for (int e = 0; e < R; e++) out[(size_t)(t2 + e * T) * n1] = v[e];
+        }
         __syncthreads(); // the exchange area is reused by the next transform of the batch
     }
 }

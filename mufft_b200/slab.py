@@ -14,16 +14,35 @@ The local transforms go through the C ABI (`mufft_execute_plan_1d_batch_async` f
 `mufft_execute_plan_1d_columns` for columns, both hand-written CUDA); `local_rows` /
 `local_cols` can be injected so the exchange logic is testable on CPU with the gloo backend.
 
-The row pass is cut into `chunks` blocks of rows; the all-to-all of block c runs on a side
-stream while block c+1 is being transformed, so most of the NVLink time hides behind the row
-pass (and, with `natural=True`, the return exchange behind nothing - it is pure communication).
+Two exchange paths:
+
+* ``exchange="p2p"`` (default on CUDA when the ranks share a node): the column-slab buffers are
+  plain device allocations mapped into every rank through CUDA IPC, and the row kernel itself
+  stores element x of every row straight into the slab of device x // (Nx/G)
+  (`mufft_execute_plan_1d_batch_scatter_async`: the kernel's stores ARE the all-to-all and travel
+  over NVLink).  No pack pass, no NCCL call on the data path; one tiny all-reduce orders the
+  devices before the column pass.
+* ``exchange="nccl"``: the row pass is cut into `chunks` blocks of rows; block c is packed into
+  per-peer tiles and its all-to-all (NCCL) runs on a side stream while block c+1 is being
+  transformed.  This is also the path of the gloo CPU tests.
+
+With `natural=True` the return exchange is pure communication (NCCL) in both cases.
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
 
 
+class _DeviceArray:
+    """A raw device allocation exposed to torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<c8", "data": (int(ptr), False), "version": 3}
+
+
 class SlabFFT2D:
-    def __init__(self, nx, ny, direction, group=None, device=None, chunks=4, local_rows=None, local_cols=None):
+    def __init__(self, nx, ny, direction, group=None, device=None, chunks=4, local_rows=None, local_cols=None, exchange=None):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -50,8 +69,23 @@ class SlabFFT2D:
             local_rows, local_cols = self._cuda_rows, self._cuda_cols
         self.local_rows, self.local_cols = local_rows, local_cols
         self._side = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        if exchange is None:
+            exchange = "p2p" if (self._plans is not None and g > 1) else "nccl"
+        if exchange == "p2p" and (self._plans is None or g & (g - 1)):
+            raise ValueError("the p2p exchange needs the CUDA library and a power-of-two number of ranks")
+        self.exchange = exchange
+        self._ipc = None  # (own allocation, [peer pointers], flag tensor)
 
     def close(self):
+        if self._ipc is not None:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)  # nobody may still be writing into a slab that is about to go away
+            own, peers, _ = self._ipc
+            for r, p in enumerate(peers):
+                if r != self.rank:
+                    self._m.mufft_cuda_ipc_close(p)
+            self._m.mufft_cuda_device_free(own)
+            self._ipc = None
         if self._plans:
             for p in self._plans:
                 self._m.mufft_free_plan_1d(p)
@@ -77,10 +111,39 @@ class SlabFFT2D:
             raise RuntimeError(self._m.mufft_cuda_last_error().decode())
 
     # ---- the distributed transform ---------------------------------------------------------------
+    def _p2p_setup(self):
+        """Allocates this rank's column slab as a shareable device allocation and maps everybody else's."""
+        m = self._m
+        nbytes = self.ny * self.cols_local * 8
+        own = m.mufft_cuda_device_alloc(nbytes)
+        if not own:
+            raise RuntimeError("cudaMalloc failed: " + m.mufft_cuda_last_error().decode())
+        handle = ctypes.create_string_buffer(64)
+        if m.mufft_cuda_ipc_export(handle, own):
+            raise RuntimeError(m.mufft_cuda_last_error().decode())
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=self.group)
+        peers = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                peers.append(own)
+            else:
+                p = m.mufft_cuda_ipc_import(ctypes.create_string_buffer(h, 64))
+                if not p:
+                    raise RuntimeError("cudaIpcOpenMemHandle failed: " + m.mufft_cuda_last_error().decode())
+                peers.append(p)
+        self._ipc = (own, peers, torch.zeros(1, dtype=torch.float32, device=self.device))
+        self._peer_array = (ctypes.c_void_p * self.world)(*peers)
+
     def buffers(self):
         """Work buffers (allocate once, reuse across executes)."""
         c64 = dict(dtype=torch.complex64, device=self.device)
         g, rl, cl = self.world, self.rows_local, self.cols_local
+        if self.exchange == "p2p":
+            if self._ipc is None:
+                self._p2p_setup()
+            recv = torch.as_tensor(_DeviceArray(self._ipc[0], (self.ny, cl)), device=self.device)
+            return {"recv": recv, "send": None, "rows": None}
         return {
             "rows": torch.empty((rl, self.nx), **c64),          # row-transformed slab
             "send": torch.empty((g, rl, cl), **c64),            # per-peer tiles, contiguous
@@ -92,6 +155,8 @@ class SlabFFT2D:
         natural=True, [Ny/G][Nx].  Returns out."""
         g, rl, cl = self.world, self.rows_local, self.cols_local
         buf = buf or self.buffers()
+        if self.exchange == "p2p":
+            return self._execute_p2p(out, inp, buf, natural)
         rows, send, recv = buf["rows"], buf["send"], buf["recv"]
         recv_tiles = recv.view(g, rl, cl)
         rc = rl // self.chunks
@@ -133,6 +198,31 @@ class SlabFFT2D:
                 self._gloo_all_to_all(outs, ins)
             else:
                 dist.all_to_all(outs, ins, group=self.group)
+        out.view(rl, g, cl).copy_(back.permute(1, 0, 2))
+        return out
+
+    def _execute_p2p(self, out, inp, buf, natural):
+        """Row pass with the exchange fused into its stores, device barrier, column pass."""
+        m, g, rl, cl = self._m, self.world, self.rows_local, self.cols_local
+        recv = buf["recv"]
+        flag = self._ipc[2]
+        # (1) nobody may still be reading its slab from the previous execute when we overwrite it
+        dist.all_reduce(flag, group=self.group)
+        self._use_current_stream()
+        err = m.mufft_execute_plan_1d_batch_scatter_async(self._plans[0], self._peer_array, g, self.rank * rl, inp.data_ptr(), rl, 0)
+        if err:
+            raise RuntimeError(m.mufft_cuda_last_error().decode())
+        # (2) every rank's row kernel (and with it its remote stores) has completed
+        dist.all_reduce(flag, group=self.group)
+        if not natural:
+            self.local_cols(out, recv)
+            return out
+        self.local_cols(recv, recv)
+        recv_tiles = recv.view(g, rl, cl)
+        back = buf.get("back")
+        if back is None:
+            back = buf["back"] = torch.empty((g, rl, cl), dtype=torch.complex64, device=self.device)
+        dist.all_to_all([back[s] for s in range(g)], [recv_tiles[p] for p in range(g)], group=self.group)
         out.view(rl, g, cl).copy_(back.permute(1, 0, 2))
         return out
 

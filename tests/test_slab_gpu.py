@@ -17,7 +17,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, nx, ny, natural, direction, result):
+def _worker(rank, world, port, nx, ny, natural, direction, exchange, result):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -32,7 +32,7 @@ def _worker(rank, world, port, nx, ny, natural, direction, result):
         g = torch.Generator(device="cpu").manual_seed(7)
         full = torch.complex(torch.rand(ny, nx, generator=g) - 0.5, torch.rand(ny, nx, generator=g) - 0.5)
         rl, cl = ny // world, nx // world
-        plan = SlabFFT2D(nx, ny, direction, device=dev, chunks=4)
+        plan = SlabFFT2D(nx, ny, direction, device=dev, chunks=4, exchange=exchange if world > 1 else "nccl")
         mine = full[rank * rl:(rank + 1) * rl].contiguous().to(dev)
         out = torch.empty((rl, nx) if natural else (ny, cl), dtype=torch.complex64, device=dev)
         buf = plan.buffers()
@@ -50,7 +50,8 @@ def _worker(rank, world, port, nx, ny, natural, direction, result):
 
 @pytest.mark.parametrize("nx,ny", [(256, 128), (2048, 4096), (16384, 512), (1024, 32768)])
 @pytest.mark.parametrize("natural", [False, True])
-def test_slab_2d(nx, ny, natural):
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_slab_2d(nx, ny, natural, exchange):
     import torch
     import torch.multiprocessing as mp
     world = min(4, torch.cuda.device_count())
@@ -60,7 +61,7 @@ def test_slab_2d(nx, ny, natural):
     port = _free_port()
     ctx = mp.get_context("spawn")
     result = ctx.Manager().dict()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, nx, ny, natural, -1, result)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nx, ny, natural, -1, exchange, result)) for r in range(world)]
     [p.start() for p in procs]
     [p.join(300) for p in procs]
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
