@@ -51,6 +51,8 @@ WORKLOADS = {
     "c2r8192": ("c2r", 8192, 0, 1 << 17),
     "r2c16384": ("r2c", 16384, 0, 1 << 16),
     "c2r16384": ("c2r", 16384, 0, 1 << 16),
+    "r2c2d1024": ("r2c2d", 1024, 1024, 256),
+    "c2r2d1024": ("c2r2d", 1024, 1024, 256),
     "c2c2d512": ("c2c2d", 512, 512, 1024),
     "c2c2d2048": ("c2c2d", 2048, 2048, 64),
     "c2c32768": ("c2c", 32768, 0, 16384),
@@ -76,6 +78,8 @@ DESCRIPTION = {
     "c2r8192": "batched 1D C2R N=8192, batch 2^17 per GPU",
     "r2c16384": "batched 1D R2C N=16384, batch 2^16 per GPU",
     "c2r16384": "batched 1D C2R N=16384, batch 2^16 per GPU",
+    "r2c2d1024": "batched 2D R2C 1024x1024, batch 256 per GPU",
+    "c2r2d1024": "batched 2D C2R 1024x1024, batch 256 per GPU",
     "c2c2d512": "batched 2D C2C 512x512, batch 1024 per GPU",
     "c2c2d2048": "batched 2D C2C 2048x2048, batch 64 per GPU",
     "c2c1m": "batched 1D C2C forward N=2^20, batch 512 per GPU",
@@ -88,6 +92,8 @@ def flops_per_unit(kind, n, ny):
     lg = math.log2(n)
     if kind in ("c2c2d", "slab2d"):
         return 5.0 * n * ny * (lg + math.log2(ny))
+    if kind in ("r2c2d", "c2r2d"):
+        return 2.5 * n * ny * (lg + math.log2(ny))  # bench.c:546,567
     if kind == "conv_stereo":
         return 2 * 5.0 * n * lg + 6.0 * n
     if kind in ("r2c", "c2r"):
@@ -105,6 +111,8 @@ def bytes_per_unit(kind, n, ny):
         return 28 * n  # conv_input (4N in, 8N out) + conv_output (8N + 8N), filter spectrum amortised
     if kind in ("c2c2d", "slab2d"):
         return 16 * n * ny  # compulsory; the row->column intermediate is meant to stay in L2
+    if kind in ("r2c2d", "c2r2d"):
+        return 4 * n * ny + 8 * (n // 2 + 1) * ny  # real image + the N/2+1 meaningful columns of the spectrum
     raise ValueError(kind)
 
 
@@ -349,6 +357,19 @@ class Job:
             self.call = None
             self.call_sync = None
             self.free = self.slab.close
+        elif kind in ("r2c2d", "c2r2d"):
+            # spectrum images keep the reference's pitch of Nx complex per row (fft.h:238-257)
+            if kind == "r2c2d":
+                self.plan = m.mufft_create_plan_2d_r2c(n, ny, 0)
+                self.inp = rnd(units, ny * n)
+                self.out = torch.empty(units, ny * n * 2, dtype=torch.float32, device=dev)
+            else:
+                self.plan = m.mufft_create_plan_2d_c2r(n, ny, 0)
+                self.inp = rnd(units, ny * n * 2)
+                self.out = torch.empty(units, ny * n, dtype=torch.float32, device=dev)
+            self.call = lambda o, i, cnt: m.mufft_execute_plan_2d_batch_async(self.plan, o, i, cnt)
+            self.call_sync = lambda o, i, cnt: m.mufft_execute_plan_2d_batch(self.plan, o, i, cnt)
+            self.free = lambda: m.mufft_free_plan_2d(self.plan)
         elif kind == "c2c2d":
             self.plan = m.mufft_create_plan_2d_c2c(n, ny, m.MUFFT_FORWARD, 0)
             self.inp = rnd(units, ny * n * 2)
@@ -517,6 +538,23 @@ def main():
             j2.free()
             del j2
             torch.cuda.empty_cache()
+
+    if world == 1 and args.also and not args.units and "c2c64" in args.also:
+        # BASELINE configs[0] as the reference runs it (`muFFT-bench 1000000 64`): ONE 64-point transform
+        # per mufft_execute_plan_1d call on mufft_alloc'd memory; each call is a launch + a sync
+        plan = m.mufft_create_plan_1d_c2c(64, m.MUFFT_FORWARD, 0)
+        a_in, a_out = m.mufft_calloc(64 * 8), m.mufft_alloc(64 * 8)
+        for _ in range(200):
+            m.mufft_execute_plan_1d(plan, a_out, a_in)
+        iters = 5000
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            m.mufft_execute_plan_1d(plan, a_out, a_in)
+        us = (time.perf_counter() - t0) / iters * 1e6
+        also["c2c64_single_call"] = {"workload": "1D C2C forward N=64, one transform per mufft_execute_plan_1d call (BASELINE configs[0])",
+                                     "us_per_call": us, "gflops": 5 * 64 * 6 / us * 1e-3,
+                                     "note": "launch + synchronise per call; the batched form of the same transform is 'c2c64'"}
+        m.mufft_free(a_in); m.mufft_free(a_out); m.mufft_free_plan_1d(plan)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

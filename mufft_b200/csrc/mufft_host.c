@@ -37,6 +37,12 @@ enum { KIND_C2C = 0, KIND_R2C = 1, KIND_R2C_FULL = 2, KIND_C2R = 3 };
 #define STAGE_SLOTS_MAX 8
 /* Staging pipeline of the host-pointer path: number of slots (streams) and bytes per chunk.
  * MUFFT_CUDA_STAGE_SLOTS / MUFFT_CUDA_STAGE_CHUNK_MB in the environment override them (tuning). */
+/* Two-kernel transforms (lengths above the on-chip limit) go through scratch between their two
+ * kernels; the batch is walked in chunks of this many bytes.  L2-sized chunks (8..64 MiB, so that
+ * the second kernel would read the scratch from the 126 MB L2) were measured and LOSE: the many
+ * short launches cost more in launch gaps and wave tails than the L2 hits save
+ * (profiles/README.md, "large N").  MUFFT_CUDA_L2_CHUNK_MB overrides it. */
+static size_t g_l2_chunk_bytes = (size_t)1 << 30;
 static int g_stage_slots = 3;
 static size_t g_stage_chunk_bytes = (size_t)64 << 20;
 #define STAGE_SLOTS g_stage_slots
@@ -55,6 +61,8 @@ __attribute__((constructor)) static void read_env(void)
 {
     const char *e = getenv("MUFFT_CUDA_PREFETCH");
     if (e != NULL) g_prefetch = e[0] == '1';
+    e = getenv("MUFFT_CUDA_L2_CHUNK_MB");
+    if (e != NULL && atoi(e) >= 1 && atoi(e) <= 4096) g_l2_chunk_bytes = (size_t)atoi(e) << 20;
     e = getenv("MUFFT_CUDA_STAGE_SLOTS");
     if (e != NULL && atoi(e) >= 1 && atoi(e) <= STAGE_SLOTS_MAX) g_stage_slots = atoi(e);
     e = getenv("MUFFT_CUDA_STAGE_CHUNK_MB");
@@ -538,8 +546,9 @@ static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode
         return -1;
     }
 
-    /* Generic path: bounded scratch, so walk the batch in chunks. */
-    size_t chunk = SCRATCH_CAP_BYTES / ((size_t)n * CPX);
+    /* Generic path: bounded scratch, so walk the batch in chunks (L2-sized for the two-kernel path). */
+    const int two_kernel = ax->n2 != 0 && g_two_kernel;
+    size_t chunk = (two_kernel ? g_l2_chunk_bytes : SCRATCH_CAP_BYTES) / ((size_t)n * CPX);
     if (chunk == 0) chunk = 1;
     if (chunk > batch) chunk = batch;
     TRY(scratch_reserve(scr, chunk * n * CPX));
@@ -1019,21 +1028,28 @@ static int run_cols_axis(const axis *ax, scratch *scr_cols, void *out, size_t ou
          *   B  n1 "images" (one per k1) of n2-point column transforms with the twiddle
          *      w_n^(k1*y2) fused into the load -> out rows k1 + n1*k2 */
         const unsigned n1 = ax->n1, n2 = ax->n2;
-        TRY(scratch_reserve(scr_cols, (size_t)width * ax->n * CPX));
+        /* blocks of columns whose scratch ([k1][y2][block]) stays in L2 between the two sweeps */
+        size_t wb = g_l2_chunk_bytes / ((size_t)ax->n * CPX);
+        wb = wb < 16 ? 16 : wb - wb % 16;
+        if (wb > width) wb = width;
+        TRY(scratch_reserve(scr_cols, wb * ax->n * CPX));
         for (size_t img = 0; img < images; img++) {
-            mcu_cols_args ca;
-            memset(&ca, 0, sizeof(ca));
-            ca.in = (const char *)in + img * in_image * CPX; ca.in_pitch = (size_t)n2 * in_pitch; ca.in_image = in_pitch;
-            ca.out = scr_cols->buf[0]; ca.out_pitch = (size_t)n2 * width; ca.out_image = width;
-            ca.tw = ax->d_tw_n1; ca.batch = n2; ca.n = n1; ca.width = width; ca.direction = ax->direction;
-            TRY(mcu_launch_cols(&ca, stream));
-            mcu_cols_args cb;
-            memset(&cb, 0, sizeof(cb));
-            cb.in = scr_cols->buf[0]; cb.in_pitch = width; cb.in_image = (size_t)n2 * width;
-            cb.out = (char *)out + img * out_image * CPX; cb.out_pitch = (size_t)n1 * out_pitch; cb.out_image = out_pitch;
-            cb.tw = ax->d_tw_n2; cb.batch = n1; cb.n = n2; cb.width = width; cb.direction = ax->direction;
-            cb.roots = ax->d_roots; cb.root_mask = ax->n - 1;
-            TRY(mcu_launch_cols(&cb, stream));
+            for (size_t c0 = 0; c0 < width; c0 += wb) {
+                const unsigned w = (unsigned)(width - c0 < wb ? width - c0 : wb);
+                mcu_cols_args ca;
+                memset(&ca, 0, sizeof(ca));
+                ca.in = (const char *)in + (img * in_image + c0) * CPX; ca.in_pitch = (size_t)n2 * in_pitch; ca.in_image = in_pitch;
+                ca.out = scr_cols->buf[0]; ca.out_pitch = (size_t)n2 * w; ca.out_image = w;
+                ca.tw = ax->d_tw_n1; ca.batch = n2; ca.n = n1; ca.width = w; ca.direction = ax->direction;
+                TRY(mcu_launch_cols(&ca, stream));
+                mcu_cols_args cb;
+                memset(&cb, 0, sizeof(cb));
+                cb.in = scr_cols->buf[0]; cb.in_pitch = w; cb.in_image = (size_t)n2 * w;
+                cb.out = (char *)out + (img * out_image + c0) * CPX; cb.out_pitch = (size_t)n1 * out_pitch; cb.out_image = out_pitch;
+                cb.tw = ax->d_tw_n2; cb.batch = n1; cb.n = n2; cb.width = w; cb.direction = ax->direction;
+                cb.roots = ax->d_roots; cb.root_mask = ax->n - 1;
+                TRY(mcu_launch_cols(&cb, stream));
+            }
         }
         return 0;
     }
