@@ -24,7 +24,7 @@ MUFFT_DECLARE_COLS(512) MUFFT_DECLARE_COLS(1024) MUFFT_DECLARE_COLS(2048)
 
 #define MUFFT_F2D_SIZES(X, nx) X(nx, 256) X(nx, 512) X(nx, 1024) X(nx, 2048)
 #define MUFFT_F2D_SHAPES(X) MUFFT_F2D_SIZES(X, 256) MUFFT_F2D_SIZES(X, 512) MUFFT_F2D_SIZES(X, 1024) MUFFT_F2D_SIZES(X, 2048)
-#define MUFFT_DECLARE_F2D(pw, ph) cudaError_t f2d_launch_##pw##x##ph(const mcu_2d_args &, cudaStream_t);
+#define MUFFT_DECLARE_F2D(pw, ph) cudaError_t f2d_launch_##pw##x##ph(const mcu_2d_args &, cudaStream_t); bool f2d_supported_##pw##x##ph();
 MUFFT_F2D_SHAPES(MUFFT_DECLARE_F2D)
 
 cudaError_t rowst_launch_256(const mcu_rowst_args &, cudaStream_t);
@@ -303,7 +303,7 @@ int mcu_launch_cols(const mcu_cols_args *a, void *stream)
 
 int mcu_2d_fused_supported(unsigned nx, unsigned ny)
 {
-#define X(pw, ph) if (nx == pw && ny == ph) return 1;
+#define X(pw, ph) if (nx == pw && ny == ph) return f2d_supported_##pw##x##ph() ? 1 : 0;
     MUFFT_F2D_SHAPES(X)
 #undef X
     return 0;

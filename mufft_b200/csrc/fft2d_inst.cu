@@ -11,11 +11,16 @@
 
 namespace mufft {
 
-static_assert(f2d_supported(F2D_NX, F2D_NY), "shape not supported by the fused 2D kernel");
 
+// Shapes the fused kernel cannot take with the configured CTA size report "unsupported" to the
+// host layer (which then uses the row kernel + column kernel path) instead of failing the build.
 template <int DIR>
 static cudaError_t launch_dir(const mcu_2d_args &a, cudaStream_t stream)
 {
+  if constexpr (!f2d_supported(F2D_NX, F2D_NY)) {
+    (void)a; (void)stream;
+    return cudaErrorInvalidValue;
+  } else {
     static int ctas = 0; // per direction
     auto kernel = fft2d_fused_kernel<F2D_NX, F2D_NY, DIR>;
     constexpr size_t smem = f2d_smem_bytes(F2D_NX, F2D_NY);
@@ -41,7 +46,10 @@ static cudaError_t launch_dir(const mcu_2d_args &a, cudaStream_t stream)
     if (b.lag == 0) b.lag = 1 + (3 * grid / 2 + per_image - 1) / per_image;
     kernel<<<grid, MUFFT_F2D_THREADS, smem, stream>>>(b);
     return cudaGetLastError();
+  }
 }
+
+bool MUFFT_CAT4(f2d_supported_, F2D_NX, x, F2D_NY)() { return f2d_supported(F2D_NX, F2D_NY); }
 
 cudaError_t MUFFT_CAT4(f2d_launch_, F2D_NX, x, F2D_NY)(const mcu_2d_args &a, cudaStream_t stream)
 {

@@ -20,7 +20,12 @@
 
 namespace mufft {
 
+#ifndef MUFFT_F2D_THREADS
 #define MUFFT_F2D_THREADS 256
+#endif
+#ifndef MUFFT_F2D_MIN_BLOCKS
+#define MUFFT_F2D_MIN_BLOCKS 2
+#endif
 
 __host__ __device__ constexpr int f2d_rows_per_tile(int nx) { return MUFFT_F2D_THREADS / engine_threads(nx); }
 __host__ __device__ constexpr int f2d_cols_per_tile(int ny) { return MUFFT_F2D_THREADS / engine_threads(ny); }
@@ -52,7 +57,7 @@ __device__ __forceinline__ void red_release_add(unsigned *p, unsigned v)
 }
 
 template <int NX, int NY, int DIR>
-__global__ void __launch_bounds__(MUFFT_F2D_THREADS, 2) fft2d_fused_kernel(const mcu_2d_args a)
+__global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d_fused_kernel(const mcu_2d_args a)
 {
     constexpr int RX = engine_regs(NX), TX = NX / RX, ROWS = f2d_rows_per_tile(NX);
     constexpr int RY = engine_regs(NY), TY = NY / RY, COLS = f2d_cols_per_tile(NY);

@@ -137,6 +137,7 @@ __host__ __device__ constexpr engine_shape_t engine_shape(int n, int variant = 0
         switch (n) {
         case 512: return { 16, 3, { 16, 16, 2, 1 }, 256, 1, 4, 1 };
         case 2048: return { 32, 3, { 32, 32, 2, 1 }, 64, 1, 5, 1 };
+        case 4096: return { 32, 3, { 16, 16, 16, 1 }, 128, 4, 4, 1 };
         case 8192: return { 32, 3, { 32, 16, 16, 1 }, 256, 2, 5, 0 };
         default: return { 0, 0, { 1, 1, 1, 1 }, 256, 1, 0, 1 };
         }
@@ -145,7 +146,8 @@ __host__ __device__ constexpr engine_shape_t engine_shape(int n, int variant = 0
         switch (n) {
         case 512: return { 16, 3, { 2, 16, 16, 1 }, 256, 1, 4, 1 };
         case 2048: return { 16, 3, { 8, 16, 16, 1 }, 128, 6, 4, 1 };
-        case 8192: return { 32, 3, { 16, 16, 32, 1 }, 256, 2, 4, 0 };
+        case 4096: return { 32, 3, { 16, 16, 16, 1 }, 128, 4, 4, 1 };
+        case 8192: return { 32, 3, { 16, 16, 32, 1 }, 256, 2, 4, 1 };
         default: return { 0, 0, { 1, 1, 1, 1 }, 256, 1, 0, 1 };
         }
     }
