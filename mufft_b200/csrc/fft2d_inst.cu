@@ -36,12 +36,12 @@ static cudaError_t launch_dir(const mcu_2d_args &a, cudaStream_t stream)
     }
     if (a.batch == 0) return cudaSuccess;
     const unsigned long long tickets = (unsigned long long)a.batch *
-        (F2D_NY / f2d_rows_per_tile(F2D_NX) + F2D_NX / f2d_cols_per_tile(F2D_NY));
+        (F2D_NY / (f2d_rows_per_tile(F2D_NX) * f2d_row_repeat(F2D_NX, F2D_NY)) + F2D_NX / f2d_cols_per_tile(F2D_NY));
     if (tickets + (unsigned long long)ctas >= 0xffffffffull) return cudaErrorInvalidConfiguration;
     const unsigned grid = tickets < (unsigned long long)ctas ? (unsigned)tickets : (unsigned)ctas;
     // lag L: the last row ticket of image i and its first column ticket are L*(NR+NC)-NR tickets
     // apart; keep that above ~1.5x the tickets in flight (one per CTA)
-    constexpr unsigned per_image = F2D_NY / f2d_rows_per_tile(F2D_NX) + F2D_NX / f2d_cols_per_tile(F2D_NY);
+    constexpr unsigned per_image = F2D_NY / (f2d_rows_per_tile(F2D_NX) * f2d_row_repeat(F2D_NX, F2D_NY)) + F2D_NX / f2d_cols_per_tile(F2D_NY);
     mcu_2d_args b = a;
     if (b.lag == 0) b.lag = 1 + (3 * grid / 2 + per_image - 1) / per_image;
     kernel<<<grid, MUFFT_F2D_THREADS, smem, stream>>>(b);

@@ -29,11 +29,24 @@ namespace mufft {
 
 __host__ __device__ constexpr int f2d_rows_per_tile(int nx) { return MUFFT_F2D_THREADS / engine_threads(nx); }
 __host__ __device__ constexpr int f2d_cols_per_tile(int ny) { return MUFFT_F2D_THREADS / engine_threads(ny); }
+// A row ticket covers f2d_row_repeat() consecutive groups of f2d_rows_per_tile() rows, each warp
+// working through its rows back to back without a CTA-wide barrier in between.  Measured on B200
+// (profiles/README.md): 4 groups per ticket is SLOWER than 1 for 1024^2 x 256 (1.65 ms vs 1.27 ms;
+// coarser tickets balance worse against the column tickets), so the default is 1; the knob stays
+// for other shapes.  At least 16 row tickets per image are kept for load balance.
+#ifndef MUFFT_F2D_ROW_REPEAT
+#define MUFFT_F2D_ROW_REPEAT 1
+#endif
+__host__ __device__ constexpr int f2d_row_repeat(int nx, int ny)
+{
+    int k = ny / (16 * f2d_rows_per_tile(nx));
+    return k < 1 ? 1 : (k > MUFFT_F2D_ROW_REPEAT ? MUFFT_F2D_ROW_REPEAT : k);
+}
 __host__ __device__ constexpr bool f2d_supported(int nx, int ny)
 {
     return engine_regs(nx) > 0 && engine_regs(ny) > 0 && engine_threads(nx) <= MUFFT_F2D_THREADS &&
            engine_threads(ny) * 4 <= MUFFT_F2D_THREADS && (engine_threads(nx) <= 32 || f2d_rows_per_tile(nx) <= 15) &&
-           ny % f2d_rows_per_tile(nx) == 0 && nx % f2d_cols_per_tile(ny) == 0;
+           ny % (f2d_rows_per_tile(nx) * f2d_row_repeat(nx, ny)) == 0 && nx % f2d_cols_per_tile(ny) == 0;
 }
 __host__ __device__ constexpr size_t f2d_smem_bytes(int nx, int ny)
 {
@@ -61,7 +74,8 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d
 {
     constexpr int RX = engine_regs(NX), TX = NX / RX, ROWS = f2d_rows_per_tile(NX);
     constexpr int RY = engine_regs(NY), TY = NY / RY, COLS = f2d_cols_per_tile(NY);
-    constexpr unsigned NR = NY / ROWS; // row tickets per image
+    constexpr int REP = f2d_row_repeat(NX, NY);
+    constexpr unsigned NR = NY / (ROWS * REP); // row tickets per image
     constexpr unsigned NC = NX / COLS; // column tickets per image
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned s_ticket[2], s_wait[2];
@@ -106,7 +120,7 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d
     auto release_pending = [&]() {
         if (pending != ~0u) {
             asm volatile("fence.acq_rel.gpu;" ::: "memory");
-            asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(rows_done + pending), "r"((unsigned)ROWS) : "memory");
+            asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(rows_done + pending), "r"((unsigned)(ROWS * REP)) : "memory");
             pending = ~0u;
         }
     };
@@ -161,25 +175,37 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d
         const bool is_rows = decode(k, image, tile);
 
         cpx *__restrict__ out = static_cast<cpx *>(a.out) + (size_t)image * a.out_image;
+#ifdef MUFFT_F2D_DIAG
+        // diagnostic builds (tools/ab.sh): 1 = row tiles only, 2 = column tiles only (results are wrong)
+        if ((MUFFT_F2D_DIAG == 1 && !is_rows) || (MUFFT_F2D_DIAG == 2 && is_rows)) {
+            if (is_rows && tid == 0) { release_pending(); pending = image; release_pending(); }
+            if (tid == 0) publish(next_ticket, (it + 1) & 1);
+            continue;
+        }
+#endif
         if (is_rows) {
             const int slot = tid / TX, t = tid - slot * TX;
-            const size_t row = (size_t)tile * ROWS + slot;
-            const cpx *__restrict__ in = static_cast<const cpx *>(a.in) + (size_t)image * a.in_image + row * NX;
-            cpx v[RX];
-#pragma unroll
-            for (int e = 0; e < RX; e++) v[e] = __ldcs(in + t + e * TX); // streamed: read once
-            // pull the same tile of the next image into L2 (one bulk prefetch of the tile's
-            // contiguous ROWS*NX*8 bytes): that tile is about one wave of tickets ahead
+            // pull the same rows of the next image into L2 (one bulk prefetch of the ticket's
+            // contiguous REP*ROWS*NX*8 bytes): that ticket is about one wave of tickets ahead
             if (tid == 0 && image + 1 < a.batch) {
-                const cpx *nxt = static_cast<const cpx *>(a.in) + (size_t)(image + 1) * a.in_image + (size_t)tile * ROWS * NX;
+                const cpx *nxt = static_cast<const cpx *>(a.in) + (size_t)(image + 1) * a.in_image + (size_t)tile * (REP * ROWS) * NX;
                 if ((reinterpret_cast<uintptr_t>(nxt) & 15) == 0)
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt), "r"((unsigned)(ROWS * NX * sizeof(cpx))) : "memory");
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt), "r"((unsigned)(REP * ROWS * NX * sizeof(cpx))) : "memory");
             }
-            if (tid == 0) release_pending(); // the previous row tile, while this one's loads fly
-            engine_run<NX, DIR, 1, TX, ROWS>(v, smem + slot * engine_smem_elems(NX), twx, t, slot);
-            cpx *__restrict__ o = out + row * NX;
+#pragma unroll 1
+            for (int rep = 0; rep < REP; rep++) {
+                const size_t row = ((size_t)tile * REP + rep) * ROWS + slot;
+                const cpx *__restrict__ in = static_cast<const cpx *>(a.in) + (size_t)image * a.in_image + row * NX;
+                cpx v[RX];
 #pragma unroll
-            for (int e = 0; e < RX; e++) o[t + e * TX] = v[e];
+                for (int e = 0; e < RX; e++) v[e] = __ldcs(in + t + e * TX); // streamed: read once
+                if (rep == 0 && tid == 0) release_pending(); // the previous row ticket, while this one's loads fly
+                engine_run<NX, DIR, 1, TX, ROWS>(v, smem + slot * engine_smem_elems(NX), twx, t, slot);
+                cpx *__restrict__ o = out + row * NX;
+#pragma unroll
+                for (int e = 0; e < RX; e++) o[t + e * TX] = v[e];
+                if (REP > 1) engine_sync<TX, ROWS>(slot); // the exchange area is reused by the next row
+            }
             if (tid == 0) pending = image;
         } else {
             const int c = tid % COLS, t = tid / COLS;
