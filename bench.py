@@ -136,50 +136,114 @@ def ncu_traffic(workload):
 
 # ---- clocks sampler -----------------------------------------------------------------------------
 class Clocks:
+    """SM clock and throttle reasons sampled DURING the timed region.  The timed region of the
+    default run is ~50 ms, far shorter than nvidia-smi's start-up, so the sampler is an NVML thread
+    (the same counters nvidia-smi prints: clocks.sm, clocks.max.sm, clocks_event_reasons.*) polling
+    every 2 ms; `nvidia-smi -lms` is the fallback when the NVML binding is missing."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    # nvml.h nvmlClocksEventReasons bit masks
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        self.path = tempfile.mktemp(prefix="mufft_clocks_", suffix=".csv")
+        self.samples = []  # (sm_mhz, reasons bitmask, power_w)
+        self.max_mhz = None
+        self.stop_flag = threading.Event()
+        self.thread = None
         self.proc = None
+        self.path = None
+        self.source = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = index
+            if visible:
+                ids = [v.strip() for v in visible.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def poll():
+                while not self.stop_flag.is_set():
+                    try:
+                        mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        try:
+                            mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        except Exception:
+                            mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        try:
+                            watts = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                        except Exception:
+                            watts = None
+                        self.samples.append((mhz, mask, watts))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            self.source = "nvml thread, 2 ms period"
+            return
+        except Exception:
+            self.thread = None
+        self.path = tempfile.mktemp(prefix="mufft_clocks_", suffix=".csv")
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            self.source = "nvidia-smi -lms 20"
+            # nvidia-smi needs a moment before its first sample; do not start timing without it
+            t_end = time.time() + 5.0
+            while time.time() < t_end and os.path.getsize(self.path) == 0:
+                time.sleep(0.05)
         except OSError:
             self.proc = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        try:
-            for line in open(self.path):
-                parts = [p.strip() for p in line.split(",")]
-                if len(parts) < 7:
-                    continue
-                try:
-                    sm.append(float(parts[0]))
-                    mx.append(float(parts[1]))
-                except ValueError:
-                    continue
-                for name, val in zip(names, parts[3:7]):
-                    if val == "Active":
+        sm, mx, reasons, watts = [], [], set(), []
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            for mhz, mask, w in self.samples:
+                sm.append(mhz)
+                if w is not None:
+                    watts.append(w)
+                for name, bit in self.REASONS:
+                    if mask & bit:
                         reasons.add(name)
-            os.unlink(self.path)
-        except OSError:
-            pass
+            mx = [self.max_mhz]
+        elif self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            names = [n for n, _ in self.REASONS]
+            try:
+                for line in open(self.path):
+                    parts = [p.strip() for p in line.split(",")]
+                    if len(parts) < 7:
+                        continue
+                    try:
+                        sm.append(float(parts[0]))
+                        mx.append(float(parts[1]))
+                        watts.append(float(parts[2]))
+                    except ValueError:
+                        continue
+                    for name, val in zip(names, parts[3:7]):
+                        if val == "Active":
+                            reasons.add(name)
+                os.unlink(self.path)
+            except OSError:
+                pass
         if sm:
             sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(watts) if watts else None, source=self.source)
         return out
 
 
