@@ -39,6 +39,7 @@ WORKLOADS = {
     "r2c4096": ("r2c", 4096, 0, 262144),
     "c2r4096": ("c2r", 4096, 0, 262144),
     "conv8192": ("conv_stereo", 8192, 0, 65536),
+    "conv8192_fused": ("conv_stereo_fused", 8192, 0, 65536),
     "c2c2d1024": ("c2c2d", 1024, 1024, 256),
     "c2c64": ("c2c", 64, 0, 1 << 24),
     "c2c256": ("c2c", 256, 0, 1 << 22),
@@ -59,12 +60,16 @@ WORKLOADS = {
     "c2c1m": ("c2c", 1 << 20, 0, 512),
     "slab2d": ("slab2d", 32768, 32768, 1),
     "slab2d8k": ("slab2d", 8192, 8192, 1),
+    "slab2d_r2c": ("slabr2d", 32768, 32768, 1),
+    "slab2d8k_r2c": ("slabr2d", 8192, 8192, 1),
 }
 DESCRIPTION = {
     "c2c4096": "batched 1D C2C forward N=4096, batch 262144 per GPU (BASELINE configs[1])",
     "r2c4096": "batched 1D R2C N=4096, batch 262144 per GPU (BASELINE configs[1])",
     "c2r4096": "batched 1D C2R N=4096, batch 262144 per GPU (BASELINE configs[1])",
     "conv8192": "stereo fast convolution FFT N=8192, 65536 blocks per GPU, one filter (BASELINE configs[2])",
+    "conv8192_fused": "stereo fast convolution FFT N=8192, 65536 blocks per GPU, one filter, whole convolution in one kernel "
+                      "(mufft_execute_conv_batch extension: 12N bytes per block instead of the API sequence's 28N)",
     "c2c2d1024": "batched 2D C2C 1024x1024, batch 256 per GPU (BASELINE configs[3])",
     "c2c64": "batched 1D C2C forward N=64, batch 2^24 per GPU (batched form of BASELINE configs[0])",
     "c2c32768": "batched 1D C2C forward N=32768, batch 16384 per GPU (row length of BASELINE configs[4])",
@@ -85,6 +90,8 @@ DESCRIPTION = {
     "c2c1m": "batched 1D C2C forward N=2^20, batch 512 per GPU",
     "slab2d": "single 2D C2C 32768x32768, row slabs over the GPUs, all-to-all transpose over NVLink, transposed-out (BASELINE configs[4])",
     "slab2d8k": "single 2D C2C 8192x8192, row slabs over the GPUs, all-to-all transpose, transposed-out",
+    "slab2d_r2c": "single 2D R2C 32768x32768, real row slabs over the GPUs, R2C rows first (half the exchange volume), all-to-all transpose over NVLink, transposed-out (BASELINE configs[4])",
+    "slab2d8k_r2c": "single 2D R2C 8192x8192, real row slabs over the GPUs, all-to-all transpose, transposed-out",
 }
 
 
@@ -92,9 +99,9 @@ def flops_per_unit(kind, n, ny):
     lg = math.log2(n)
     if kind in ("c2c2d", "slab2d"):
         return 5.0 * n * ny * (lg + math.log2(ny))
-    if kind in ("r2c2d", "c2r2d"):
+    if kind in ("r2c2d", "c2r2d", "slabr2d"):
         return 2.5 * n * ny * (lg + math.log2(ny))  # bench.c:546,567
-    if kind == "conv_stereo":
+    if kind in ("conv_stereo", "conv_stereo_fused"):
         return 2 * 5.0 * n * lg + 6.0 * n
     if kind in ("r2c", "c2r"):
         return 2.5 * n * lg  # bench.c:546,567 convention for real transforms
@@ -109,9 +116,11 @@ def bytes_per_unit(kind, n, ny):
         return 4 * n + 8 * (n // 2 + 1)
     if kind == "conv_stereo":
         return 28 * n  # conv_input (4N in, 8N out) + conv_output (8N + 8N), filter spectrum amortised
+    if kind == "conv_stereo_fused":
+        return 12 * n  # zero-padded block in (4N), convolved block out (8N); the spectrum stays on chip
     if kind in ("c2c2d", "slab2d"):
         return 16 * n * ny  # compulsory; the row->column intermediate is meant to stay in L2
-    if kind in ("r2c2d", "c2r2d"):
+    if kind in ("r2c2d", "c2r2d", "slabr2d"):
         return 4 * n * ny + 8 * (n // 2 + 1) * ny  # real image + the N/2+1 meaningful columns of the spectrum
     raise ValueError(kind)
 
@@ -249,7 +258,7 @@ class Clocks:
 
 # ---- CPU reference ---------------------------------------------------------------------------------
 REF_BENCH = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
-REF_MODE = {"c2c": "c2c", "r2c": "r2c_c2r", "c2r": "r2c_c2r", "conv_stereo": "conv_stereo", "c2c2d": "c2c2d"}
+REF_MODE = {"c2c": "c2c", "r2c": "r2c_c2r", "c2r": "r2c_c2r", "conv_stereo": "conv_stereo", "conv_stereo_fused": "conv_stereo", "c2c2d": "c2c2d"}
 
 
 def cpu_reference_sample(kind, n, ny, seconds_of_cpu_work):
@@ -310,7 +319,7 @@ def cpu_oracle_sample(kind, n, ny, cores, per_thread, repeats):
     [t.join() for t in threads]
     seconds = max(times)
     units = per_thread * cores * repeats
-    scale = {"c2c": 1.0, "r2c": 0.5, "c2r": 0.5, "conv_stereo": 2.0, "c2c2d": float(max(ny, 1)) * 2}[kind]
+    scale = {"c2c": 1.0, "r2c": 0.5, "c2r": 0.5, "conv_stereo": 2.0, "conv_stereo_fused": 2.0, "c2c2d": float(max(ny, 1)) * 2}[kind]
     units_per_s = units / seconds / scale
     return {"value": units_per_s * flops_per_unit(kind, n, ny) * 1e-9, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"oracle port, {units} complex N={nn} transforms over {cores} threads, {seconds:.2f} s wall",
@@ -403,6 +412,19 @@ class Job:
             self.call = call
             self.call_sync = lambda o, i, cnt: call(o, i, cnt, True)
             self.free = lambda: m.mufft_free_plan_conv(self.plan)
+        elif kind == "conv_stereo_fused":
+            method = (m.MUFFT_CONV_METHOD_FLAG_STEREO_MONO | m.MUFFT_CONV_METHOD_FLAG_ZERO_PAD_UPPER_HALF_FIRST |
+                      m.MUFFT_CONV_METHOD_FLAG_ZERO_PAD_UPPER_HALF_SECOND)
+            self.plan = m.mufft_create_plan_conv(n, 0, method)
+            blk = m.mufft_conv_get_transformed_block_size(self.plan) // 4
+            self.inp = rnd(units, n)
+            filt = rnd(1, n // 2)
+            self.fspec = torch.empty(blk, dtype=torch.float32, device=dev)
+            self.out = torch.empty(units, 2 * n, dtype=torch.float32, device=dev)
+            assert m.mufft_execute_conv_input_batch(self.plan, 1, self.fspec.data_ptr(), filt.data_ptr(), 1) == 0
+            self.call = lambda o, i, cnt: m.mufft_execute_conv_batch_async(self.plan, o, i, self.fspec.data_ptr(), cnt, 0)
+            self.call_sync = lambda o, i, cnt: m.mufft_execute_conv_batch(self.plan, o, i, self.fspec.data_ptr(), cnt, 0)
+            self.free = lambda: m.mufft_free_plan_conv(self.plan)
         elif kind == "slab2d":
             import torch.distributed as dist_mod
             from mufft_b200.slab import SlabFFT2D
@@ -418,6 +440,23 @@ class Job:
             self.buf = self.slab.buffers()
             self.plan = 1
             self.units = 1.0 / world  # this rank's share of the one transform
+            self.call = None
+            self.call_sync = None
+            self.free = self.slab.close
+        elif kind == "slabr2d":
+            import torch.distributed as dist_mod
+            from mufft_b200.slab import SlabRFFT2D
+            if not dist_mod.is_initialized():
+                os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+                os.environ.setdefault("MASTER_PORT", "29577")
+                dist_mod.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+            world = dist_mod.get_world_size()
+            self.slab = SlabRFFT2D(n, ny, device=dev, chunks=int(os.environ.get("MUFFT_SLAB_CHUNKS", "8")))
+            self.inp = rnd(ny // world, n)
+            self.out = torch.empty((ny, self.slab.cols_local), dtype=torch.complex64, device=dev)
+            self.buf = self.slab.buffers()
+            self.plan = 1
+            self.units = 1.0 / world
             self.call = None
             self.call_sync = None
             self.free = self.slab.close
@@ -449,6 +488,9 @@ class Job:
     def step(self):
         if self.kind == "slab2d":
             self.slab.execute(self.out, self.inp, buf=self.buf)
+            return
+        if self.kind == "slabr2d":
+            self.slab.forward(self.out, self.inp, buf=self.buf)
             return
         err = self.call(self.out.data_ptr(), self.inp.data_ptr(), self.units)
         if err:
@@ -490,7 +532,7 @@ def main():
     ap.add_argument("--units", type=int, default=0, help="override units per GPU (debug; invalidates the headline)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--also", default="r2c4096,c2r4096,conv8192,c2c2d1024,c2c64",
+    ap.add_argument("--also", default="r2c4096,c2r4096,conv8192,conv8192_fused,c2c2d1024,c2c64",
                     help="comma separated extra workloads reported under 'also' (N=1 only); '' disables")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -526,7 +568,7 @@ def main():
     if args.units:
         units = args.units
     job = Job(m, torch, kind, n, ny, units, dev)
-    if kind == "slab2d":
+    if kind in ("slab2d", "slabr2d"):
         units = job.units
         args.no_e2e = True
         args.no_cpu = True  # the CPU reference for one 32768^2 image is a 33 s, 24 GiB single-thread job
@@ -628,7 +670,7 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if kind == "slab2d" else "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if kind in ("slab2d", "slabr2d") else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": DESCRIPTION[args.workload], "n": n, "ny": ny, "units_per_gpu": units,
                        "global_units": units * n_gpus, "parallelism": f"batch-sharded x{n_gpus}, no collective",

@@ -92,6 +92,21 @@ int mufft_execute_conv_input_batch_async(mufft_plan_conv *plan, unsigned block, 
 int mufft_execute_conv_output_batch_async(mufft_plan_conv *plan, void *output, const void *input_first,
                                           const void *input_second, size_t batch, size_t second_stride_bytes);
 
+/* Whole convolution of `batch` blocks in one call: output[b] = IFFT(FFT(input_first[b]) .* filter / N),
+ * i.e. mufft_execute_conv_input(plan, MUFFT_CONV_BLOCK_FIRST, ...) followed by
+ * mufft_execute_conv_output(...) for every block, with `filter_spectrum` exactly what
+ * mufft_execute_conv_input(plan, MUFFT_CONV_BLOCK_SECOND, filter_spectrum, taps) produced
+ * (mufft_conv_get_transformed_block_size() bytes).  When the transform fits the on-chip engine
+ * (stereo N <= 8192, mono N <= 16384) this is ONE kernel and the block spectrum never reaches HBM:
+ * a zero-padded stereo block moves 12N bytes instead of the 28N of the two-call sequence.
+ * Inputs are tightly packed blocks laid out as conv_input(FIRST) expects them, outputs as
+ * conv_output writes them (stereo N complex, mono N floats per block).  filter_stride_bytes 0 =
+ * one filter for every block, else one spectrum per block that many bytes apart. */
+int mufft_execute_conv_batch(mufft_plan_conv *plan, void *output, const void *input_first,
+                             const void *filter_spectrum, size_t batch, size_t filter_stride_bytes);
+int mufft_execute_conv_batch_async(mufft_plan_conv *plan, void *output, const void *input_first,
+                                   const void *filter_spectrum, size_t batch, size_t filter_stride_bytes);
+
 /* Row-transform kernel flavour: 0 = direct loads (default), 1 = persistent CTAs with bulk-copy
  * prefetch into shared memory when the input rows are 16-byte aligned.  Same results either way. */
 void mufft_cuda_set_prefetch(int enable);

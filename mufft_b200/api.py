@@ -77,6 +77,8 @@ SIGNATURES = {
     "mufft_execute_conv_output_batch": (_i, [_vp, _vp, _vp, _vp, _sz, _sz]),
     "mufft_execute_conv_input_batch_async": (_i, [_vp, _u, _vp, _vp, _sz]),
     "mufft_execute_conv_output_batch_async": (_i, [_vp, _vp, _vp, _vp, _sz, _sz]),
+    "mufft_execute_conv_batch": (_i, [_vp, _vp, _vp, _vp, _sz, _sz]),
+    "mufft_execute_conv_batch_async": (_i, [_vp, _vp, _vp, _vp, _sz, _sz]),
     "mufft_cuda_set_prefetch": (None, [_i]),
     "mufft_cuda_set_fused_2d": (None, [_i]),
     "mufft_cuda_set_two_kernel": (None, [_i]),

@@ -79,6 +79,22 @@ typedef struct mcu_cols_args {
     unsigned root_mask;    /* roots[(image*row) & root_mask] before the transform (n = 256, 512, 1024 only) */
 } mcu_cols_args;
 
+/* Fused convolution kernel (conv_kernel.cuh): forward transform, spectral multiply, inverse
+ * transform of every block in one launch; n <= MCU_ENGINE_MAX_N only. */
+typedef struct mcu_conv_args {
+    void *out;             /* stereo: n complex per block; mono: 2n floats (= n complex) per block */
+    const void *in;        /* stereo: n (n/2 when zero padded) complex; mono: 2n (n) floats */
+    const void *filter;    /* filter spectrum: stereo n bins, mono n+1 bins */
+    const void *tw_fwd, *tw_inv;   /* engine tables (variant 0) of n, forward and inverse */
+    const void *rtw_fwd, *rtw_inv; /* mono: resolve twiddles of both directions, n entries each */
+    size_t out_stride, in_stride, filter_stride; /* complex elements between blocks (filter_stride 0 = one filter) */
+    size_t batch;
+    unsigned n;            /* complex transform length (stereo: N, mono: N/2) */
+    int in_mode;           /* MCU_IN_COMPLEX or MCU_IN_HALF */
+    int mono;
+    float norm;
+} mcu_conv_args;
+
 /* Second kernel of the two-kernel transform for n = n1 * n2 > MCU_ENGINE_MAX_N (rowst_kernel.cuh). */
 typedef struct mcu_rowst_args {
     void *out;             /* X[k1 + n1*k2] */
@@ -182,6 +198,7 @@ int mcu_launch_rowst(const mcu_rowst_args *args, void *stream);
 int mcu_2d_fused_supported(unsigned nx, unsigned ny);
 int mcu_launch_2d_fused(const mcu_2d_args *args, void *stream);
 int mcu_launch_resolve(const mcu_resolve_args *args, void *stream);
+int mcu_launch_conv(const mcu_conv_args *args, void *stream);
 /* Engine shape variant the row kernel of (n, in_mode, out_mode) uses: 0 general, 1 / 2 the
  * mirrored-pass shapes of the real transforms (fft_engine.cuh).  The twiddle table passed in
  * mcu_rows_args.tw must be the one of that variant. */

@@ -18,6 +18,11 @@ MUFFT_DECLARE_ROWS(2) MUFFT_DECLARE_ROWS(4) MUFFT_DECLARE_ROWS(8) MUFFT_DECLARE_
 MUFFT_DECLARE_ROWS(32) MUFFT_DECLARE_ROWS(64) MUFFT_DECLARE_ROWS(128) MUFFT_DECLARE_ROWS(256)
 MUFFT_DECLARE_ROWS(512) MUFFT_DECLARE_ROWS(1024) MUFFT_DECLARE_ROWS(2048) MUFFT_DECLARE_ROWS(4096)
 MUFFT_DECLARE_ROWS(8192)
+#define MUFFT_DECLARE_CONV(n) cudaError_t conv_launch_##n(const mcu_conv_args &, cudaStream_t);
+MUFFT_DECLARE_CONV(2) MUFFT_DECLARE_CONV(4) MUFFT_DECLARE_CONV(8) MUFFT_DECLARE_CONV(16)
+MUFFT_DECLARE_CONV(32) MUFFT_DECLARE_CONV(64) MUFFT_DECLARE_CONV(128) MUFFT_DECLARE_CONV(256)
+MUFFT_DECLARE_CONV(512) MUFFT_DECLARE_CONV(1024) MUFFT_DECLARE_CONV(2048) MUFFT_DECLARE_CONV(4096)
+MUFFT_DECLARE_CONV(8192)
 MUFFT_DECLARE_COLS(2) MUFFT_DECLARE_COLS(4) MUFFT_DECLARE_COLS(8) MUFFT_DECLARE_COLS(16)
 MUFFT_DECLARE_COLS(32) MUFFT_DECLARE_COLS(64) MUFFT_DECLARE_COLS(128) MUFFT_DECLARE_COLS(256)
 MUFFT_DECLARE_COLS(512) MUFFT_DECLARE_COLS(1024) MUFFT_DECLARE_COLS(2048)
@@ -283,6 +288,18 @@ int mcu_launch_rows(const mcu_rows_args *a, void *stream)
     g_launches.fetch_add(1, std::memory_order_relaxed);
     switch (a->n) {
 #define X(v) case v: return (int)(a->direction < 0 ? rows_launch_##v##_fwd(*a, s) : rows_launch_##v##_inv(*a, s));
+        MUFFT_FOR_ENGINE_SIZES(X)
+#undef X
+    default: return (int)cudaErrorInvalidValue;
+    }
+}
+
+int mcu_launch_conv(const mcu_conv_args *a, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    switch (a->n) {
+#define X(v) case v: return (int)conv_launch_##v(*a, s);
         MUFFT_FOR_ENGINE_SIZES(X)
 #undef X
     default: return (int)cudaErrorInvalidValue;

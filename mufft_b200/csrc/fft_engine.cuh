@@ -376,7 +376,9 @@ __device__ __forceinline__ int engine_bfly(int t, int u)
 
 // Butterflies of pass PASS for thread t, in place: inputs v[u + m*NB] (m < r) become outputs
 // v[u + q*NB] (q < r).  `tw` points at the engine twiddle table of this transform length.
-template <int N, int DIR, int PASS, int V = 0>
+// PK: -1 = the shape's packed flag, 0 / 1 = the caller's choice (kernels whose prologue or epilogue
+// changes the register pressure measure differently from the plain transform of the same shape).
+template <int N, int DIR, int PASS, int V = 0, int PK = -1>
 __device__ __forceinline__ void engine_butterflies(cpx (&v)[engine_regs(N, V)], const cpx *__restrict__ tw, int t)
 {
     constexpr int R = engine_regs(N, V);
@@ -395,7 +397,7 @@ __device__ __forceinline__ void engine_butterflies(cpx (&v)[engine_regs(N, V)], 
 #pragma unroll
             for (int m = 1; m < r; m++) x[m] = cmul(x[m], __ldg(w + (m - 1) * p));
         }
-        dft_regs<r, DIR, engine_packed(N, V)>(x);
+        dft_regs<r, DIR, (PK < 0 ? engine_packed(N, V) : PK != 0)>(x);
 #pragma unroll
         for (int q = 0; q < r; q++) v[u + q * NB] = x[q];
     }
@@ -461,16 +463,16 @@ __device__ __forceinline__ void engine_scatter_natural(const cpx (&v)[engine_reg
 // All passes of an N-point transform.  Every thread of the transform must call this (it
 // synchronises them); SYNC_T / SLOTS say how (see engine_sync): the row kernel passes the
 // threads of one transform, the column kernel passes the whole CTA.
-template <int N, int DIR, int CS, int SYNC_T, int SLOTS, int PASS = 0, int V = 0>
+template <int N, int DIR, int CS, int SYNC_T, int SLOTS, int PASS = 0, int V = 0, int PK = -1>
 __device__ __forceinline__ void engine_run(cpx (&v)[engine_regs(N, V)], cpx *sm, const cpx *__restrict__ tw, int t, int slot)
 {
-    engine_butterflies<N, DIR, PASS, V>(v, tw, t);
+    engine_butterflies<N, DIR, PASS, V, PK>(v, tw, t);
     if constexpr (PASS + 1 < engine_num_passes(N, V)) {
         if constexpr (PASS > 0) engine_sync<SYNC_T, SLOTS>(slot); // previous gather must be complete (WAR)
         engine_scatter<N, PASS, CS, V>(v, sm, t);
         engine_sync<SYNC_T, SLOTS>(slot);
         engine_gather<N, CS, PASS + 1, V>(v, sm, t);
-        engine_run<N, DIR, CS, SYNC_T, SLOTS, PASS + 1, V>(v, sm, tw, t, slot);
+        engine_run<N, DIR, CS, SYNC_T, SLOTS, PASS + 1, V, PK>(v, sm, tw, t, slot);
     }
 }
 

@@ -786,6 +786,8 @@ struct mufft_plan_conv {
     float normalization;
     unsigned n;
     int stereo;
+    void *d_spectra;      /* mufft_execute_conv_batch beyond the engine limit: block spectra of one chunk */
+    size_t spectra_bytes;
 };
 
 void mufft_free_plan_conv(mufft_plan_conv *plan)
@@ -794,6 +796,7 @@ void mufft_free_plan_conv(mufft_plan_conv *plan)
     mufft_free_plan_1d(plan->plans[0]);
     mufft_free_plan_1d(plan->plans[1]);
     mufft_free_plan_1d(plan->output_plan);
+    mcu_free(plan->d_spectra);
     free(plan);
 }
 
@@ -874,6 +877,84 @@ int mufft_execute_conv_output_batch_async(mufft_plan_conv *plan, void *output, c
                                           const void *input_second, size_t batch, size_t second_stride_bytes)
 {
     return conv_output(plan, output, input_first, input_second, batch, second_stride_bytes, 1);
+}
+
+/* ---- whole convolution in one call (additive; mufft_cuda.h) -------------------------------------
+ * conv_input(FIRST) + conv_output per block without the block spectrum ever reaching HBM when the
+ * transform fits the on-chip engine (one kernel: conv_kernel.cuh); beyond it the two library
+ * steps run back to back through plan-owned scratch, chunk by chunk. */
+typedef struct conv_ctx {
+    mufft_plan_conv *plan;
+} conv_ctx;
+
+static int conv_unit_launch(void *ctx_, void *out, size_t out_stride, const void *in, size_t in_stride,
+                            const void *in2, size_t in2_stride, size_t count, void *stream)
+{
+    mufft_plan_conv *plan = ((conv_ctx *)ctx_)->plan;
+    mufft_plan_1d *fwd = plan->plans[0], *inv = plan->output_plan;
+    int in_mode, out_mode;
+    plan_modes(fwd, &in_mode, &out_mode);
+    if (fwd->use_engine) {
+        mcu_conv_args a;
+        memset(&a, 0, sizeof(a));
+        a.out = out; a.in = in; a.filter = in2;
+        a.tw_fwd = fwd->ax.d_engine_tw; a.tw_inv = inv->ax.d_engine_tw;
+        a.rtw_fwd = fwd->d_rtw; a.rtw_inv = inv->d_rtw;
+        a.out_stride = out_stride / CPX; a.in_stride = in_stride / CPX; a.filter_stride = in2_stride / CPX;
+        a.batch = count; a.n = fwd->n; a.in_mode = in_mode; a.mono = !plan->stereo;
+        a.norm = plan->normalization;
+        return mcu_launch_conv(&a, stream);
+    }
+    /* long transforms: the spectra of a chunk of blocks (<= 256 MiB) go through plan-owned scratch */
+    size_t chunk = ((size_t)256 << 20) / plan->block_size;
+    if (chunk == 0) chunk = 1;
+    if (chunk > count) chunk = count;
+    TRY(grow(&plan->d_spectra, &plan->spectra_bytes, chunk * plan->block_size));
+    const int mul_mode = plan->stereo ? MCU_IN_MUL : MCU_IN_MUL_C2R;
+    for (size_t done = 0; done < count; done += chunk) {
+        const size_t cnt = count - done < chunk ? count - done : chunk;
+        TRY(run_rows(&fwd->ax, &fwd->scr, fwd->d_rtw, in_mode, out_mode, 1.0f, plan->d_spectra, plan->block_size / CPX,
+                     (const char *)in + done * in_stride, in_stride / CPX, NULL, 0, cnt, stream));
+        TRY(run_rows(&inv->ax, &inv->scr, inv->d_rtw, mul_mode, MCU_OUT_COMPLEX, plan->normalization,
+                     (char *)out + done * out_stride, out_stride / CPX, plan->d_spectra, plan->block_size / CPX,
+                     in2_stride ? (const char *)in2 + done * in2_stride : (const char *)in2, in2_stride / CPX, cnt, stream));
+    }
+    return 0;
+}
+
+static int conv_fused(mufft_plan_conv *plan, void *output, const void *input, const void *filter,
+                      size_t batch, size_t filter_stride, int async)
+{
+    if (plan == NULL) return -1;
+    conv_ctx ctx = { plan };
+    int in_mode, out_mode;
+    plan_modes(plan->plans[0], &in_mode, &out_mode);
+    io_desc io;
+    memset(&io, 0, sizeof(io));
+    io.out = output; io.in = input; io.in2 = filter;
+    io.in_unit = in_unit_bytes(plan->plans[0]->n, in_mode);
+    io.out_unit = (size_t)plan->output_plan->n * CPX; /* stereo: N complex; mono: N floats */
+    io.in2_unit = plan->stereo ? (size_t)plan->n * CPX : ((size_t)plan->n / 2 + 1) * CPX;
+    io.in_stride = io.in_unit;
+    io.out_stride = io.out_unit;
+    io.in2_stride = filter_stride;
+    io.count = batch;
+    if (filter_stride % CPX != 0 || (((uintptr_t)output | (uintptr_t)input | (uintptr_t)filter) % CPX) != 0) {
+        snprintf(tls_error, sizeof(tls_error), "buffers and strides must be multiples of 8 bytes");
+        return -1;
+    }
+    return run_any(&plan->plans[0]->st, conv_unit_launch, &ctx, &io, async);
+}
+
+int mufft_execute_conv_batch(mufft_plan_conv *plan, void *output, const void *input_first,
+                             const void *filter_spectrum, size_t batch, size_t filter_stride_bytes)
+{
+    return conv_fused(plan, output, input_first, filter_spectrum, batch, filter_stride_bytes, 0);
+}
+int mufft_execute_conv_batch_async(mufft_plan_conv *plan, void *output, const void *input_first,
+                                   const void *filter_spectrum, size_t batch, size_t filter_stride_bytes)
+{
+    return conv_fused(plan, output, input_first, filter_spectrum, batch, filter_stride_bytes, 1);
 }
 
 /* Stand-alone spectral multiply (ref fft.h:201-207, kernel.c:22-34): runs the CUDA kernel on

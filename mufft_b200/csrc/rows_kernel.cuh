@@ -32,6 +32,18 @@ __host__ __device__ constexpr int rows_variant(int n, int in_mode, int out_mode)
     return MUFFT_VARIANT_GENERAL;
 }
 
+// Packed-FP32 choice per kernel (-1 = the shape's flag).  Measured on B200 (profiles/README.md, A/B
+// "c8k_pk"): at N = 8192 the convolution stages (zero-padded load, spectral multiply) gain 2-7 %
+// from packed complex adds while the plain C2C transform of the same shape loses 3 %.
+__host__ __device__ constexpr int rows_packed(int n, int in_mode, int out_mode)
+{
+#ifdef MUFFT_PACKED
+    return -1;
+#else
+    return (n == 8192 && out_mode == MCU_OUT_COMPLEX && (in_mode == MCU_IN_HALF || in_mode == MCU_IN_MUL)) ? 1 : -1;
+#endif
+}
+
 // Threads of one CTA and transforms per CTA for row transforms of length n.
 __host__ __device__ constexpr int rows_threads_per_transform(int n, int v = 0) { return n / engine_regs(n, v); }
 __host__ __device__ constexpr int rows_per_cta(int n, int v = 0)
@@ -282,7 +294,7 @@ fft_rows_kernel(const mcu_rows_args a)
 
     cpx v[R];
     rows_load<N, IN_MODE, V>(v, in, in2, rtw, a.norm, t);
-    engine_run<N, DIR, 1, T, TPC, 0, V>(v, sm, tw, t, slot);
+    engine_run<N, DIR, 1, T, TPC, 0, V, rows_packed(N, IN_MODE, OUT_MODE)>(v, sm, tw, t, slot);
     if constexpr (OUT_MODE == MCU_OUT_PEERS) {
         if (active) rows_store_peers<N, V>(v, a.peers, b, t);
     } else {
@@ -397,7 +409,7 @@ fft_rows_tma_kernel(const mcu_rows_args a)
         engine_sync<T, TPC>(slot);
         if (t == 0) issue(stage, g + (size_t)STAGES * gridDim.x);
 
-        engine_run<N, DIR, 1, T, TPC, 0, V>(v, sm, tw, t, slot);
+        engine_run<N, DIR, 1, T, TPC, 0, V, rows_packed(N, IN_MODE, OUT_MODE)>(v, sm, tw, t, slot);
         cpx *__restrict__ out = static_cast<cpx *>(a.out) + b * a.out_stride;
         rows_store<N, OUT_MODE, T, TPC, V>(v, out, sm, rtw, t, slot, active);
 

@@ -241,3 +241,154 @@ class SlabFFT2D:
                 outs[s].copy_(tmp)
         for r in reqs:
             r.wait()
+
+
+class SlabRFFT2D:
+    """Slab-decomposed 2D REAL transform pair of one large [Ny][Nx] array (BASELINE configs[4], R2C).
+
+    forward (R2C, ref fft.c:918-989 order: real row transforms, then complex column transforms):
+      rank g holds real rows [g*Ny/G, (g+1)*Ny/G) as float32 [Ny/G][Nx].  The local row pass is the
+      library's R2C kernel (Nx/2+1 bins per row), which HALVES the exchanged volume; one all-to-all
+      turns the row slabs of the half spectrum into column slabs; the local column pass is C2C.
+      Result, transposed-out: rank g holds columns [g*H/G, (g+1)*H/G) of the H = Nx/2 lower bins as
+      [Ny][H/G] complex64; the Nyquist column (bin Nx/2) rides with the LAST rank, whose slab is
+      [Ny][H/G + 1].
+    inverse (C2R, ref fft.c:861-916 order: columns first, then the real row transforms): takes
+      exactly that column-slab layout, runs the inverse column pass, the reverse all-to-all, and the
+      library's C2R row kernel; result float32 [Ny/G][Nx], unnormalised like the reference
+      (inverse(forward(x)) = Nx*Ny*x).
+
+    The exchange is NCCL all-to-all with per-peer tiles (uneven for the last rank), block c in
+    flight on a side stream while block c+1 of rows is transformed; the local passes go through
+    the C ABI.  `local_*` hooks let the exchange logic run on CPU under gloo.
+    """
+
+    def __init__(self, nx, ny, group=None, device=None, chunks=4, local_r2c_rows=None, local_c2r_rows=None, local_cols=None):
+        self.group = group
+        self.world = g = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if nx % (2 * g) or ny % g or nx < 4:
+            raise ValueError("Nx/2 and Ny must be divisible by the number of ranks")
+        self.nx, self.ny, self.h = nx, ny, nx // 2
+        self.rows_local, self.cols_even = ny // g, self.h // g
+        self.widths = [self.cols_even] * (g - 1) + [self.cols_even + 1]  # the Nyquist column goes to the last rank
+        self.cols_local = self.widths[self.rank]
+        self.device = torch.device(device) if device is not None else torch.device("cpu")
+        self.chunks = max(1, min(chunks, self.rows_local))
+        while self.rows_local % self.chunks:
+            self.chunks -= 1
+        self._plans = None
+        if local_r2c_rows is None or local_c2r_rows is None or local_cols is None:
+            import mufft_b200 as m
+            if self.device.type != "cuda":
+                raise RuntimeError("SlabRFFT2D runs its transforms on a CUDA device (there is no CPU path)")
+            self._m = m
+            plans = (m.mufft_create_plan_1d_r2c(nx, 0), m.mufft_create_plan_1d_c2r(nx, 0),
+                     m.mufft_create_plan_1d_c2c(ny, m.MUFFT_FORWARD, 0), m.mufft_create_plan_1d_c2c(ny, m.MUFFT_INVERSE, 0))
+            if not all(plans):
+                raise RuntimeError("plan creation failed: " + m.mufft_cuda_last_error().decode())
+            self._plans = plans
+            local_r2c_rows, local_c2r_rows, local_cols = self._cuda_r2c_rows, self._cuda_c2r_rows, self._cuda_cols
+        self.local_r2c_rows, self.local_c2r_rows, self.local_cols = local_r2c_rows, local_c2r_rows, local_cols
+        self._side = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+
+    def close(self):
+        if self._plans:
+            for p in self._plans:
+                self._m.mufft_free_plan_1d(p)
+            self._plans = None
+
+    def _use_current_stream(self):
+        self._m.mufft_cuda_set_stream(torch.cuda.current_stream(self.device).cuda_stream or None)
+
+    def _check(self, err):
+        if err:
+            raise RuntimeError(self._m.mufft_cuda_last_error().decode())
+
+    def _cuda_r2c_rows(self, out, inp):
+        """out[r, :Nx/2+1] = R2C(inp[r, :]); out rows are Nx/2+1 complex apart."""
+        self._use_current_stream()
+        self._check(self._m.mufft_execute_plan_1d_batch_async(self._plans[0], out.data_ptr(), inp.data_ptr(), inp.shape[0],
+                                                              out.stride(0) * 8, inp.stride(0) * 4))
+
+    def _cuda_c2r_rows(self, out, inp):
+        self._use_current_stream()
+        self._check(self._m.mufft_execute_plan_1d_batch_async(self._plans[1], out.data_ptr(), inp.data_ptr(), inp.shape[0],
+                                                              out.stride(0) * 4, inp.stride(0) * 8))
+
+    def _cuda_cols(self, out, inp, direction):
+        self._use_current_stream()
+        w = inp.shape[1]
+        plan = self._plans[2] if direction < 0 else self._plans[3]
+        self._check(self._m.mufft_execute_plan_1d_columns(plan, out.data_ptr(), inp.data_ptr(), w, out.stride(0) * 8, inp.stride(0) * 8))
+
+    def buffers(self):
+        c64 = dict(dtype=torch.complex64, device=self.device)
+        g, rl = self.world, self.rows_local
+        return {
+            "rows": torch.empty((rl, self.h + 1), **c64),                              # half spectra of the local rows
+            "send": [torch.empty((rl, w), **c64) for w in self.widths],                # tile for peer p: its columns of my rows
+            "recv": [torch.empty((rl, self.cols_local), **c64) for _ in range(g)],     # tile from peer s: my columns of its rows
+            "slab": torch.empty((self.ny, self.cols_local), **c64),
+        }
+
+    def _col_range(self, p):
+        lo = p * self.cols_even
+        return lo, lo + self.widths[p]
+
+    def _all_to_all(self, outs, ins, works):
+        if self.world == 1:
+            outs[0].copy_(ins[0])
+        elif dist.get_backend(self.group) == "gloo":
+            SlabFFT2D._gloo_all_to_all(self, outs, ins)
+        elif self._side is not None and works is not None:
+            self._side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self._side):
+                works.append(dist.all_to_all(outs, ins, group=self.group, async_op=True))
+        else:
+            dist.all_to_all(outs, ins, group=self.group)
+
+    def _drain(self, works):
+        for w in works:
+            w.wait()
+        if self._side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
+
+    def forward(self, out, inp, buf=None):
+        """inp float32 [Ny/G][Nx] -> out complex64 [Ny][cols_local] (this rank's columns of the half spectrum)."""
+        g, rl = self.world, self.rows_local
+        buf = buf or self.buffers()
+        rows, send, recv = buf["rows"], buf["send"], buf["recv"]
+        rc = rl // self.chunks
+        works = []
+        for c in range(self.chunks):
+            lo, hi = c * rc, (c + 1) * rc
+            self.local_r2c_rows(rows[lo:hi], inp[lo:hi])
+            for p in range(g):
+                a, b = self._col_range(p)
+                send[p][lo:hi].copy_(rows[lo:hi, a:b])
+            self._all_to_all([recv[s][lo:hi] for s in range(g)], [send[p][lo:hi] for p in range(g)], works)
+        self._drain(works)
+        slab = buf["slab"]
+        for s in range(g):
+            slab[s * rl:(s + 1) * rl].copy_(recv[s])
+        self.local_cols(out, slab, -1)
+        return out
+
+    def inverse(self, out, inp, buf=None):
+        """inp complex64 [Ny][cols_local] (the layout forward() produced) -> out float32 [Ny/G][Nx]."""
+        g, rl = self.world, self.rows_local
+        buf = buf or self.buffers()
+        rows, send, recv, slab = buf["rows"], buf["send"], buf["recv"], buf["slab"]
+        self.local_cols(slab, inp, +1)
+        # tile for peer p = its rows of my columns; arrives as my rows of peer s's columns
+        ins = [slab[p * rl:(p + 1) * rl] for p in range(g)]
+        outs = [send[s] for s in range(g)]  # send[s] has exactly the shape [rl][widths[s]]
+        works = []
+        self._all_to_all(outs, ins, works)
+        self._drain(works)
+        for s in range(g):
+            a, b = self._col_range(s)
+            rows[:, a:b].copy_(outs[s])
+        self.local_c2r_rows(out, rows)
+        return out

@@ -183,6 +183,68 @@ def test_conv_batch_device(m, torch, oracle, n, stereo):
         assert np.max(np.abs(got - want)) < 2e-6 * math.sqrt(n)  # test.c:431,474
 
 
+@pytest.mark.parametrize("n", [4, 8, 64, 1024, 2048, 8192, 16384, 32768])
+@pytest.mark.parametrize("stereo", [0, 1])
+@pytest.mark.parametrize("padded", [1, 0])
+def test_conv_fused_batch_device(m, torch, oracle, n, stereo, padded):
+    """mufft_execute_conv_batch (one kernel per batch up to the engine limit, the two library steps
+    through scratch beyond it) against the oracle's conv_input + conv_output of every sampled block,
+    with the reference's own criterion (test.c:431,474) and against the two-call GPU path."""
+    method = stereo | (12 if padded else 0)
+    batch = batch_for(n) // 2 + 3
+    plan = m.mufft_create_plan_conv(n, 0, method)
+    assert plan
+    blk = m.mufft_conv_get_transformed_block_size(plan) // 8
+    samples = n // 2 if padded else n
+    a = dev_random(torch, (batch, 2 * samples if stereo else samples), 21)
+    filt = dev_random(torch, (1, samples), 22)
+    sf = torch.zeros((1, 2 * blk), dtype=torch.float32, device="cuda")
+    out = torch.zeros((batch, 2 * n if stereo else n), dtype=torch.float32, device="cuda")
+    assert m.mufft_execute_conv_input_batch(plan, 1, sf.data_ptr(), filt.data_ptr(), 1) == 0
+    assert m.mufft_execute_conv_batch(plan, out.data_ptr(), a.data_ptr(), sf.data_ptr(), batch, 0) == 0, m.mufft_cuda_last_error()
+    # the two-call path on the same inputs
+    sa = torch.zeros((batch, 2 * blk), dtype=torch.float32, device="cuda")
+    out2 = torch.zeros_like(out)
+    assert m.mufft_execute_conv_input_batch(plan, 0, sa.data_ptr(), a.data_ptr(), batch) == 0
+    assert m.mufft_execute_conv_output_batch(plan, out2.data_ptr(), sa.data_ptr(), sf.data_ptr(), batch, 0) == 0
+    # one filter per block (stride = block size) must give the same as the shared filter
+    if batch <= 4096:
+        sfs = sf.repeat(batch, 1).contiguous()
+        out3 = torch.zeros_like(out)
+        assert m.mufft_execute_conv_batch(plan, out3.data_ptr(), a.data_ptr(), sfs.data_ptr(), batch, blk * 8) == 0
+        assert torch.equal(out3, out)
+    m.mufft_free_plan_conv(plan)
+    scale = float(out2.abs().max())
+    assert float((out - out2).abs().max()) <= 4e-6 * math.sqrt(n) * max(scale, 1e-3) + 1e-7
+    f = filt[0].cpu().numpy()
+    idx = sample_indices(batch, 10)
+    as_, os_ = a[idx].cpu().numpy(), out[idx].cpu().numpy()
+    for i in range(len(idx)):
+        ai = as_[i].view(np.complex64) if stereo else as_[i]
+        want, _, _ = oracle.conv(ai, f, n, method)
+        got = os_[i].view(np.complex64) if stereo else os_[i]
+        assert rel_l2(got, want) <= 2 * tol(n)
+        assert np.max(np.abs(got - want)) < 2e-6 * math.sqrt(n) * (1 if padded else 2)
+
+
+def test_conv_fused_batch_host_memory(m, torch, oracle):
+    """Pageable host buffers go through the staged path (chunks over several streams)."""
+    n, batch, method = 1024, 3000, 1 | 4 | 8
+    plan = m.mufft_create_plan_conv(n, 0, method)
+    blk = m.mufft_conv_get_transformed_block_size(plan) // 8
+    rng = np.random.default_rng(5)
+    a = (rng.random((batch, n), np.float32) - np.float32(0.5))          # n/2 complex per block
+    taps = (rng.random(n // 2, np.float32) - np.float32(0.5))
+    sf = np.zeros(2 * blk, np.float32)
+    out = np.zeros((batch, 2 * n), np.float32)
+    m.mufft_execute_conv_input(plan, 1, sf.ctypes.data, taps.ctypes.data)
+    assert m.mufft_execute_conv_batch(plan, out.ctypes.data, a.ctypes.data, sf.ctypes.data, batch, 0) == 0, m.mufft_cuda_last_error()
+    m.mufft_free_plan_conv(plan)
+    for i in (0, 1, batch // 2, batch - 1):
+        want, _, _ = oracle.conv(a[i].view(np.complex64), taps, n, method)
+        assert rel_l2(out[i].view(np.complex64), want) <= 2 * tol(n)
+
+
 @pytest.mark.parametrize("nx,ny", [(64, 64), (256, 128), (256, 256), (512, 2048), (2048, 256), (1024, 1024), (128, 2048),
                                    (8192, 8), (16, 4096), (32, 16384), (16384, 32), (64, 8192)])
 @pytest.mark.parametrize("fused", [1, 0])

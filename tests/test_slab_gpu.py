@@ -67,3 +67,59 @@ def test_slab_2d(nx, ny, natural, exchange):
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     tol = 1e-6 * math.log2(nx * ny)
     assert len(result) == world and max(result.values()) <= tol, dict(result)
+
+
+def _rworker(rank, world, port, nx, ny, result):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import mufft_b200
+        from mufft_b200.slab import SlabRFFT2D
+        assert mufft_b200.mufft_cuda_set_device(rank) == 0
+        g = torch.Generator(device="cpu").manual_seed(11)
+        full = torch.rand(ny, nx, generator=g) - 0.5
+        rl = ny // world
+        plan = SlabRFFT2D(nx, ny, device=dev, chunks=4)
+        mine = full[rank * rl:(rank + 1) * rl].contiguous().to(dev)
+        spec = torch.empty((ny, plan.cols_local), dtype=torch.complex64, device=dev)
+        back = torch.empty((rl, nx), dtype=torch.float32, device=dev)
+        buf = plan.buffers()
+        for _ in range(2):
+            plan.forward(spec, mine, buf=buf)
+            plan.inverse(back, spec, buf=buf)
+        torch.cuda.synchronize()
+        ref = torch.fft.rfft2(full.to(dev).to(torch.float64))
+        lo = rank * plan.cols_even
+        want = ref[:, lo:lo + plan.cols_local]
+        e1 = (torch.linalg.vector_norm(spec.to(torch.complex128) - want) / torch.linalg.vector_norm(want)).item()
+        e2 = (torch.linalg.vector_norm(back.double() / (nx * ny) - mine.double()) / torch.linalg.vector_norm(mine.double())).item()
+        result[rank] = max(e1, e2)
+        plan.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nx,ny", [(256, 128), (4096, 2048), (32768, 512), (1024, 16384)])
+def test_slab_2d_real(nx, ny):
+    """R2C forward + C2R inverse of one large real image over the visible GPUs (1, 2 or 4 ranks):
+    half spectrum against float64 rfft2, and inverse(forward(x)) = Nx*Ny*x."""
+    import torch
+    import torch.multiprocessing as mp
+    world = min(4, torch.cuda.device_count())
+    while world & (world - 1):
+        world -= 1
+    assert world >= 1, "no CUDA device visible"
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    result = ctx.Manager().dict()
+    procs = [ctx.Process(target=_rworker, args=(r, world, port, nx, ny, result)) for r in range(world)]
+    [p.start() for p in procs]
+    [p.join(300) for p in procs]
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    tol = 1e-6 * math.log2(nx * ny)
+    assert len(result) == world and max(result.values()) <= tol, dict(result)
