@@ -56,6 +56,7 @@ WORKLOADS = {
     "c2r2d1024": ("c2r2d", 1024, 1024, 256),
     "c2c2d512": ("c2c2d", 512, 512, 1024),
     "c2c2d2048": ("c2c2d", 2048, 2048, 64),
+    "c2c16384": ("c2c", 16384, 0, 32768),
     "c2c32768": ("c2c", 32768, 0, 16384),
     "c2c1m": ("c2c", 1 << 20, 0, 512),
     "slab2d": ("slab2d", 32768, 32768, 1),
@@ -72,6 +73,7 @@ DESCRIPTION = {
                       "(mufft_execute_conv_batch extension: 12N bytes per block instead of the API sequence's 28N)",
     "c2c2d1024": "batched 2D C2C 1024x1024, batch 256 per GPU (BASELINE configs[3])",
     "c2c64": "batched 1D C2C forward N=64, batch 2^24 per GPU (batched form of BASELINE configs[0])",
+    "c2c16384": "batched 1D C2C forward N=16384, batch 32768 per GPU (first length on the two-kernel split)",
     "c2c32768": "batched 1D C2C forward N=32768, batch 16384 per GPU (row length of BASELINE configs[4])",
     "c2c256": "batched 1D C2C forward N=256, batch 2^22 per GPU",
     "c2c1024": "batched 1D C2C forward N=1024, batch 2^20 per GPU",

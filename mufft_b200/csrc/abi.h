@@ -191,8 +191,9 @@ int mcu_prefetch(const void *ptr, size_t bytes, int to_device, void *stream);
 int mcu_launch_rows(const mcu_rows_args *args, void *stream);
 int mcu_launch_cols(const mcu_cols_args *args, void *stream);
 int mcu_launch_pass(const mcu_pass_args *args, void *stream);
-/* n2 of the two-kernel split of n (0 = n is outside its range and takes the generic passes) */
-unsigned mcu_split_n2(unsigned n);
+/* n2 of the two-kernel split of n for a row (columns = 0) or column (columns = 1) transform
+ * (0 = n is outside its range and takes the generic passes) */
+unsigned mcu_split_n2(unsigned n, int columns);
 int mcu_launch_rowst(const mcu_rowst_args *args, void *stream);
 /* 1 if the fused 2D kernel exists for this image shape */
 int mcu_2d_fused_supported(unsigned nx, unsigned ny);

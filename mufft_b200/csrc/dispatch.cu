@@ -9,6 +9,7 @@
 
 #include <atomic>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace mufft {
@@ -336,9 +337,16 @@ int mcu_launch_2d_fused(const mcu_2d_args *a, void *stream)
 }
 
 // n = n1 * n2 with n1 <= 2048 (column kernel) and n2 in {256, 512, 1024} (row kernel B)
-unsigned mcu_split_n2(unsigned n)
+unsigned mcu_split_n2(unsigned n, int columns)
 {
     if (n <= MCU_COLS_MAX_N || (n & (n - 1)) != 0) return 0;
+    // MUFFT_CUDA_SPLIT_N2=<256|512|1024>: measurement knob, overrides the choice where it is legal
+    static const unsigned forced = [] { const char *e = getenv("MUFFT_CUDA_SPLIT_N2"); return e ? (unsigned)atoi(e) : 0u; }();
+    if ((forced == 256 || forced == 512 || forced == 1024) && n / forced >= 2 && n / forced <= MCU_COLS_MAX_N) return forced;
+    // Row transforms: the widest second factor wins from 32768 points on (measured on B200,
+    // profiles/README.md section 3: N = 32768 4.06 -> 3.52 ms, N = 2^20 6.00 -> 4.27 ms with 1024 instead
+    // of 256 / 512).  Column transforms keep the narrow split they were measured with.
+    if (!columns && n >= 32768u && n <= 2048u * 1024u) return 1024;
     if (n <= 2048u * 256u) return 256;
     if (n <= 2048u * 512u) return 512;
     if (n <= 2048u * 1024u) return 1024;

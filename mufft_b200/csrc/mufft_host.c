@@ -43,6 +43,12 @@ enum { KIND_C2C = 0, KIND_R2C = 1, KIND_R2C_FULL = 2, KIND_C2R = 3 };
  * short launches cost more in launch gaps and wave tails than the L2 hits save
  * (profiles/README.md, "large N").  MUFFT_CUDA_L2_CHUNK_MB overrides it. */
 static size_t g_l2_chunk_bytes = (size_t)1 << 30;
+/* 2D transforms on the row kernel + column kernel path (R2C, C2R, shapes without the fused kernel):
+ * images per launch pair, as bytes of row->column intermediate.  Groups small enough to keep the
+ * intermediate in the 126 MB L2 (48 MiB) measured SLOWER on B200 than whole-batch launches
+ * (profiles/README.md section 3: 2D R2C 1024^2 x 256 1.40 ms with 86 launches against 0.92 ms with 2), so the
+ * cap only bounds the plan-owned scratch.  MUFFT_CUDA_MID_GROUP_MB overrides. */
+static size_t g_mid_group_bytes = (size_t)2048 << 20;
 static int g_stage_slots = 3;
 static size_t g_stage_chunk_bytes = (size_t)64 << 20;
 #define STAGE_SLOTS g_stage_slots
@@ -53,7 +59,7 @@ static size_t g_stage_chunk_bytes = (size_t)64 << 20;
 
 /* Row transforms have two kernels (rows_kernel.cuh): direct loads, and persistent CTAs whose
  * inputs are prefetched into shared memory by bulk async copies.  0 = direct (default: it is the
- * faster one at the tuned occupancies, profiles/r01_shape_sweeps.txt), 1 = prefetch whenever the
+ * faster one at the tuned occupancies, profiles/README.md), 1 = prefetch whenever the
  * input rows are 16-byte aligned.  MUFFT_CUDA_PREFETCH in the environment sets the initial value,
  * mufft_cuda_set_prefetch() changes it. */
 static int g_prefetch = 0;
@@ -63,6 +69,8 @@ __attribute__((constructor)) static void read_env(void)
     if (e != NULL) g_prefetch = e[0] == '1';
     e = getenv("MUFFT_CUDA_L2_CHUNK_MB");
     if (e != NULL && atoi(e) >= 1 && atoi(e) <= 4096) g_l2_chunk_bytes = (size_t)atoi(e) << 20;
+    e = getenv("MUFFT_CUDA_MID_GROUP_MB");
+    if (e != NULL && atoi(e) >= 1 && atoi(e) <= 65536) g_mid_group_bytes = (size_t)atoi(e) << 20;
     e = getenv("MUFFT_CUDA_STAGE_SLOTS");
     if (e != NULL && atoi(e) >= 1 && atoi(e) <= STAGE_SLOTS_MAX) g_stage_slots = atoi(e);
     e = getenv("MUFFT_CUDA_STAGE_CHUNK_MB");
@@ -200,9 +208,12 @@ static void *make_engine_table(unsigned n, int direction, int variant)
     return dev;
 }
 
-/* want_generic: also build what the multi-pass kernels need. */
+/* want_generic: also build what the multi-pass kernels need (AXIS_ROWS / AXIS_COLS: which
+ * two-kernel split the axis takes); 0 = the axis runs on the single-kernel engine only. */
+enum { AXIS_ROWS = 1, AXIS_COLS = 2 };
 static int axis_init(axis *ax, unsigned n, int direction, int want_generic)
 {
+    const int columns = want_generic == AXIS_COLS;
     memset(ax, 0, sizeof(*ax));
     ax->n = n;
     ax->direction = direction;
@@ -216,8 +227,8 @@ static int axis_init(axis *ax, unsigned n, int direction, int want_generic)
             if (!ax->d_engine_tw_real) return -1;
         }
     }
-    if (want_generic && mcu_split_n2(n) != 0) { /* rows use it above MCU_ENGINE_MAX_N, columns above MCU_COLS_MAX_N */
-        ax->n2 = mcu_split_n2(n);
+    if (want_generic && mcu_split_n2(n, columns) != 0) { /* rows use it above MCU_ENGINE_MAX_N, columns above MCU_COLS_MAX_N */
+        ax->n2 = mcu_split_n2(n, columns);
         ax->n1 = n / ax->n2;
         ax->d_tw_n1 = make_engine_table(ax->n1, direction, 0);
         ax->d_tw_n2 = make_engine_table(ax->n2, direction, 0);
@@ -303,6 +314,7 @@ typedef struct stage {
     void *d_shared;
     size_t shared_bytes;
     void *ev_begin;
+    void *ev_kernels;   /* recorded after the kernels of each chunk: the next chunk's kernels wait for it */
     int ready;
 } stage;
 
@@ -322,6 +334,7 @@ static int stage_init(stage *st)
     if (st->ready) return 0;
     for (int i = 0; i < STAGE_SLOTS; i++) TRY(mcu_stream_create(&st->slot[i].stream));
     TRY(mcu_event_create(&st->ev_begin));
+    TRY(mcu_event_create(&st->ev_kernels));
     st->ready = 1;
     return 0;
 }
@@ -336,6 +349,7 @@ static void stage_free(stage *st)
     }
     mcu_free(st->d_shared);
     mcu_event_destroy(st->ev_begin);
+    mcu_event_destroy(st->ev_kernels);
     memset(st, 0, sizeof(*st));
 }
 
@@ -433,7 +447,12 @@ static int run_any(stage *st, unit_launch fn, void *ctx, const io_desc *io, int 
             d_out = sl->d_out;
             s_out = io->out_unit;
         }
+        /* The kernels of consecutive chunks run on different streams but may share plan-owned
+         * scratch (2D intermediates and ticket counters, two-kernel transforms, convolution
+         * spectra): chain them.  The copies on either side still overlap the neighbours' kernels. */
+        if (c > 0) TRY(mcu_stream_wait_event(sl->stream, st->ev_kernels));
         TRY(fn(ctx, d_out, s_out, d_in, s_in, d_in2, s_in2, cnt, sl->stream));
+        TRY(mcu_event_record(st->ev_kernels, sl->stream));
         if (!vis_out) TRY(copy_units(dst, io->out_stride, sl->d_out, io->out_unit, io->out_unit, cnt, sl->stream));
         done += cnt;
     }
@@ -482,7 +501,7 @@ mufft_plan_1d *mufft_create_plan_1d_c2c(unsigned N, int direction, unsigned flag
     plan->direction = direction;
     plan->zero_pad = (flags & MUFFT_FLAG_ZERO_PAD_UPPER_HALF) != 0;
     plan->use_engine = N <= MCU_ENGINE_MAX_N;
-    if (axis_init(&plan->ax, N, direction, !plan->use_engine) != 0) {
+    if (axis_init(&plan->ax, N, direction, plan->use_engine ? 0 : AXIS_ROWS) != 0) {
         mufft_free_plan_1d(plan);
         return NULL;
     }
@@ -773,7 +792,7 @@ int mufft_execute_plan_1d_columns(mufft_plan_1d *plan, void *output, const void 
         snprintf(tls_error, sizeof(tls_error), "columns: needs device-accessible (device or managed) pointers");
         return -1;
     }
-    if (plan->ax_cols.n == 0 && axis_init(&plan->ax_cols, plan->n, plan->direction, plan->n > MCU_COLS_MAX_N) != 0) return -1;
+    if (plan->ax_cols.n == 0 && axis_init(&plan->ax_cols, plan->n, plan->direction, plan->n > MCU_COLS_MAX_N ? AXIS_COLS : 0) != 0) return -1;
     return run_cols_axis(&plan->ax_cols, &plan->scr_cols, output, output_pitch_bytes / CPX, 0, input, input_pitch_bytes / CPX, 0,
                          (unsigned)width, 1, tls_stream);
 }
@@ -1038,8 +1057,8 @@ static mufft_plan_2d *plan_2d_common(unsigned nx, unsigned ny, int direction, in
     plan->kind = kind;
     plan->vertical_nx = nx;
     plan->cols_engine = ny <= MCU_COLS_MAX_N;
-    if (axis_init(&plan->ax_x, nx, direction, nx > MCU_ENGINE_MAX_N) != 0 ||
-        axis_init(&plan->ax_y, ny, direction, !plan->cols_engine) != 0) {
+    if (axis_init(&plan->ax_x, nx, direction, nx > MCU_ENGINE_MAX_N ? AXIS_ROWS : 0) != 0 ||
+        axis_init(&plan->ax_y, ny, direction, plan->cols_engine ? 0 : AXIS_COLS) != 0) {
         mufft_free_plan_2d(plan);
         return NULL;
     }
@@ -1166,7 +1185,7 @@ static int run_cols(mufft_plan_2d *plan, void *out, size_t out_pitch, size_t out
  * intermediate between the row and the column kernel is plan-owned and sized for a small
  * group of images, so that on B200 it is produced and consumed inside the 126 MB L2 instead
  * of making a round trip through HBM. */
-#define MID_GROUP_BYTES ((size_t)48 << 20)
+#define MID_GROUP_BYTES g_mid_group_bytes
 
 static int run_2d_device(mufft_plan_2d *plan, void *out, const void *in, size_t images, void *stream)
 {

@@ -272,6 +272,59 @@ def test_c2c_2d_batch_device(m, torch, oracle, nx, ny, fused):
     m.mufft_cuda_set_fused_2d(1)
 
 
+@pytest.mark.parametrize("case", ["c2c2d-fused", "c2c2d-separate", "r2c2d", "c2r2d", "c2c-long"])
+def test_staged_host_batches_that_share_plan_scratch(m, torch, oracle, case):
+    """Pageable host buffers, batches long enough for several staging chunks on different streams:
+    the kernels of consecutive chunks share plan-owned scratch (2D intermediate, ticket counters,
+    two-kernel scratch), so they must be chained.  Every image / transform is checked against the
+    device-resident result of the same call."""
+    rng = np.random.default_rng(17)
+    if case == "c2c-long":
+        n, batch = 32768, 600
+        plan = m.mufft_create_plan_1d_c2c(n, -1, 0)
+        x = rng.random((batch, 2 * n), np.float32) - np.float32(0.5)
+        out = np.zeros_like(x)
+        assert m.mufft_execute_plan_1d_batch(plan, out.ctypes.data, x.ctypes.data, batch, 0, 0) == 0
+        xd = torch.from_numpy(x).cuda()
+        od = torch.zeros_like(xd)
+        assert m.mufft_execute_plan_1d_batch(plan, od.data_ptr(), xd.data_ptr(), batch, 0, 0) == 0
+        m.mufft_free_plan_1d(plan)
+        assert np.array_equal(out, od.cpu().numpy())
+        want = oracle.c2c(x[batch - 1].view(np.complex64), -1)
+        assert rel_l2(out[batch - 1].view(np.complex64), want) <= tol(n)
+        return
+    nx = ny = 256
+    batch = 500
+    if case.startswith("c2c2d"):
+        m.mufft_cuda_set_fused_2d(1 if case == "c2c2d-fused" else 0)
+        plan = m.mufft_create_plan_2d_c2c(nx, ny, -1, 0)
+        x = rng.random((batch, ny * nx * 2), np.float32) - np.float32(0.5)
+        out = np.zeros_like(x)
+    elif case == "r2c2d":
+        plan = m.mufft_create_plan_2d_r2c(nx, ny, 0)
+        x = rng.random((batch, ny * nx), np.float32) - np.float32(0.5)
+        out = np.zeros((batch, ny * nx * 2), np.float32)
+    else:
+        plan = m.mufft_create_plan_2d_c2r(nx, ny, 0)
+        spec = np.fft.rfft2(rng.random((batch, ny, nx)) - 0.5).astype(np.complex64)
+        x = np.zeros((batch, ny, nx), np.complex64)
+        x[:, :, : nx // 2 + 1] = spec
+        x = x.view(np.float32).reshape(batch, -1)
+        out = np.zeros((batch, ny * nx), np.float32)
+    try:
+        assert m.mufft_execute_plan_2d_batch(plan, out.ctypes.data, x.ctypes.data, batch) == 0, m.mufft_cuda_last_error()
+        xd = torch.from_numpy(x).cuda()
+        od = torch.zeros(out.shape, dtype=torch.float32, device="cuda")
+        assert m.mufft_execute_plan_2d_batch(plan, od.data_ptr(), xd.data_ptr(), batch) == 0
+    finally:
+        m.mufft_cuda_set_fused_2d(1)
+        m.mufft_free_plan_2d(plan)
+    got, dev = out.reshape(batch, ny, -1), od.cpu().numpy().reshape(batch, ny, -1)
+    if case == "r2c2d":  # only columns 0..Nx/2 of the pitch-Nx complex rows are defined
+        got, dev = got[:, :, : 2 * (nx // 2 + 1)], dev[:, :, : 2 * (nx // 2 + 1)]
+    assert np.array_equal(got, dev)
+
+
 @pytest.mark.parametrize("n", [16384, 65536, 1 << 18, 1 << 19, 1 << 20, 1 << 21, 1 << 22])
 @pytest.mark.parametrize("two_kernel", [1, 0])
 def test_large_n(m, torch, oracle, n, two_kernel):

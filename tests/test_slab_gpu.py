@@ -1,5 +1,6 @@
 """Slab-decomposed 2D transform on the GPU(s): local passes through the CUDA library, exchange
-over NCCL.  With one visible GPU the group has one rank (the pack / column-slab path still runs);
+over NCCL or the row kernel's peer stores.  With one visible GPU the group has one rank (the pack /
+peer-scatter / column-slab paths still run);
 with two or more the test spawns one process per GPU (up to 4)."""
 import math
 import os
@@ -32,7 +33,8 @@ def _worker(rank, world, port, nx, ny, natural, direction, exchange, result):
         g = torch.Generator(device="cpu").manual_seed(7)
         full = torch.complex(torch.rand(ny, nx, generator=g) - 0.5, torch.rand(ny, nx, generator=g) - 0.5)
         rl, cl = ny // world, nx // world
-        plan = SlabFFT2D(nx, ny, direction, device=dev, chunks=4, exchange=exchange if world > 1 else "nccl")
+        # with one rank the p2p path still runs the row kernel's peer-scatter epilogue (one "peer": itself)
+        plan = SlabFFT2D(nx, ny, direction, device=dev, chunks=4, exchange=exchange)
         mine = full[rank * rl:(rank + 1) * rl].contiguous().to(dev)
         out = torch.empty((rl, nx) if natural else (ny, cl), dtype=torch.complex64, device=dev)
         buf = plan.buffers()
