@@ -686,6 +686,10 @@ def main():
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    elif kind in ("slab2d", "slabr2d"):
+        import torch.distributed as dist_mod
+        if dist_mod.is_initialized():  # the one-rank group a single-GPU slab job created
+            dist_mod.destroy_process_group()
 
 
 if __name__ == "__main__":
