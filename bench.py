@@ -40,6 +40,7 @@ WORKLOADS = {
     "c2r4096": ("c2r", 4096, 0, 262144),
     "conv8192": ("conv_stereo", 8192, 0, 65536),
     "conv8192_fused": ("conv_stereo_fused", 8192, 0, 65536),
+    "conv8192_part8": ("conv_stereo_part8", 8192, 0, 32768),
     "c2c2d1024": ("c2c2d", 1024, 1024, 256),
     "c2c64": ("c2c", 64, 0, 1 << 24),
     "c2c256": ("c2c", 256, 0, 1 << 22),
@@ -71,6 +72,8 @@ DESCRIPTION = {
     "conv8192": "stereo fast convolution FFT N=8192, 65536 blocks per GPU, one filter (BASELINE configs[2])",
     "conv8192_fused": "stereo fast convolution FFT N=8192, 65536 blocks per GPU, one filter, whole convolution in one kernel "
                       "(mufft_execute_conv_batch extension: 12N bytes per block instead of the API sequence's 28N)",
+    "conv8192_part8": "stereo fast convolution FFT N=8192 with a LARGE filter (8 partitions = 32768 taps), 32768 blocks per GPU: "
+                      "conv_input per block + one partitioned conv_output (8 spectral products summed in front of one inverse FFT)",
     "c2c2d1024": "batched 2D C2C 1024x1024, batch 256 per GPU (BASELINE configs[3])",
     "c2c64": "batched 1D C2C forward N=64, batch 2^24 per GPU (batched form of BASELINE configs[0])",
     "c2c16384": "batched 1D C2C forward N=16384, batch 32768 per GPU (first length on the two-kernel split)",
@@ -105,6 +108,8 @@ def flops_per_unit(kind, n, ny):
         return 2.5 * n * ny * (lg + math.log2(ny))  # bench.c:546,567
     if kind in ("conv_stereo", "conv_stereo_fused"):
         return 2 * 5.0 * n * lg + 6.0 * n
+    if kind == "conv_stereo_part8":
+        return 2 * 5.0 * n * lg + 8 * 8.0 * n  # two transforms + 8 complex multiply-adds per bin
     if kind in ("r2c", "c2r"):
         return 2.5 * n * lg  # bench.c:546,567 convention for real transforms
     return 5.0 * n * lg
@@ -118,6 +123,8 @@ def bytes_per_unit(kind, n, ny):
         return 4 * n + 8 * (n // 2 + 1)
     if kind == "conv_stereo":
         return 28 * n  # conv_input (4N in, 8N out) + conv_output (8N + 8N), filter spectrum amortised
+    if kind == "conv_stereo_part8":
+        return 28 * n  # as conv_stereo: every block spectrum is written once and read from HBM once (its 7 re-reads hit L2)
     if kind == "conv_stereo_fused":
         return 12 * n  # zero-padded block in (4N), convolved block out (8N); the spectrum stays on chip
     if kind in ("c2c2d", "slab2d"):
@@ -260,7 +267,7 @@ class Clocks:
 
 # ---- CPU reference ---------------------------------------------------------------------------------
 REF_BENCH = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
-REF_MODE = {"c2c": "c2c", "r2c": "r2c_c2r", "c2r": "r2c_c2r", "conv_stereo": "conv_stereo", "conv_stereo_fused": "conv_stereo", "c2c2d": "c2c2d"}
+REF_MODE = {"c2c": "c2c", "r2c": "r2c_c2r", "c2r": "r2c_c2r", "conv_stereo": "conv_stereo", "conv_stereo_fused": "conv_stereo", "conv_stereo_part8": "conv_stereo", "c2c2d": "c2c2d"}
 
 
 def cpu_reference_sample(kind, n, ny, seconds_of_cpu_work):
@@ -321,7 +328,7 @@ def cpu_oracle_sample(kind, n, ny, cores, per_thread, repeats):
     [t.join() for t in threads]
     seconds = max(times)
     units = per_thread * cores * repeats
-    scale = {"c2c": 1.0, "r2c": 0.5, "c2r": 0.5, "conv_stereo": 2.0, "conv_stereo_fused": 2.0, "c2c2d": float(max(ny, 1)) * 2}[kind]
+    scale = {"c2c": 1.0, "r2c": 0.5, "c2r": 0.5, "conv_stereo": 2.0, "conv_stereo_fused": 2.0, "conv_stereo_part8": 2.0, "c2c2d": float(max(ny, 1)) * 2}[kind]
     units_per_s = units / seconds / scale
     return {"value": units_per_s * flops_per_unit(kind, n, ny) * 1e-9, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"oracle port, {units} complex N={nn} transforms over {cores} threads, {seconds:.2f} s wall",
@@ -411,6 +418,27 @@ class Job:
                 f_out = m.mufft_execute_conv_output_batch if sync else m.mufft_execute_conv_output_batch_async
                 return (f_in(self.plan, 0, self.spec.data_ptr(), i, cnt) or
                         f_out(self.plan, o, self.spec.data_ptr(), self.fspec.data_ptr(), cnt, 0))
+            self.call = call
+            self.call_sync = lambda o, i, cnt: call(o, i, cnt, True)
+            self.free = lambda: m.mufft_free_plan_conv(self.plan)
+        elif kind == "conv_stereo_part8":
+            parts = 8
+            method = (m.MUFFT_CONV_METHOD_FLAG_STEREO_MONO | m.MUFFT_CONV_METHOD_FLAG_ZERO_PAD_UPPER_HALF_FIRST |
+                      m.MUFFT_CONV_METHOD_FLAG_ZERO_PAD_UPPER_HALF_SECOND)
+            self.plan = m.mufft_create_plan_conv(n, 0, method)
+            blk = m.mufft_conv_get_transformed_block_size(self.plan) // 4
+            self.inp = rnd(units, n)
+            taps = rnd(parts, n // 2)
+            self.fspec = torch.empty(parts, blk, dtype=torch.float32, device=dev)
+            self.spec = torch.zeros(units + parts - 1, blk, dtype=torch.float32, device=dev)  # parts-1 blocks of (zero) history in front
+            self.out = torch.empty(units, 2 * n, dtype=torch.float32, device=dev)
+            assert m.mufft_execute_conv_input_batch(self.plan, 1, self.fspec.data_ptr(), taps.data_ptr(), parts) == 0
+            first = self.spec.data_ptr() + (parts - 1) * blk * 4
+
+            def call(o, i, cnt, sync=False):
+                f_in = m.mufft_execute_conv_input_batch if sync else m.mufft_execute_conv_input_batch_async
+                f_out = m.mufft_execute_conv_output_partitioned_batch if sync else m.mufft_execute_conv_output_partitioned_batch_async
+                return f_in(self.plan, 0, first, i, cnt) or f_out(self.plan, o, first, self.fspec.data_ptr(), parts, cnt)
             self.call = call
             self.call_sync = lambda o, i, cnt: call(o, i, cnt, True)
             self.free = lambda: m.mufft_free_plan_conv(self.plan)
@@ -570,6 +598,8 @@ def main():
     if args.units:
         units = args.units
     job = Job(m, torch, kind, n, ny, units, dev)
+    if kind == "conv_stereo_part8":
+        args.no_e2e = True  # the partitioned output stage takes device-accessible memory only
     if kind in ("slab2d", "slabr2d"):
         units = job.units
         args.no_e2e = True

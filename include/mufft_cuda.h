@@ -107,6 +107,25 @@ int mufft_execute_conv_batch(mufft_plan_conv *plan, void *output, const void *in
 int mufft_execute_conv_batch_async(mufft_plan_conv *plan, void *output, const void *input_first,
                                    const void *filter_spectrum, size_t batch, size_t filter_stride_bytes);
 
+/* Uniformly partitioned convolution for filters longer than one block (frequency-domain delay
+ * line).  The reference leaves the accumulation over filter partitions to the caller
+ * (ref fft.h:170-174: one mufft_execute_conv_output per partition, outputs added in the time
+ * domain); here the products are summed in front of ONE inverse transform per block:
+ *     output[b] = IFFT( sum_{p < parts} S[b - p] .* F[p] ) / N,      b = 0 .. batch-1
+ * S[j]: block spectra in time order (what mufft_execute_conv_input(plan, MUFFT_CONV_BLOCK_FIRST, ..)
+ * wrote), mufft_conv_get_transformed_block_size() bytes apart; `spectra` points at S[0], and the
+ * parts-1 blocks in front of it (S[-1] .. S[-(parts-1)]: the tail of the previous call, zeros at the
+ * start of a stream) must be valid memory.  F[p]: spectra of the filter partitions
+ * (mufft_execute_conv_input(plan, MUFFT_CONV_BLOCK_SECOND, ..) of taps [p*L, (p+1)*L)), the same
+ * distance apart.  Outputs as mufft_execute_conv_output writes them, tightly packed; the caller
+ * overlap-adds consecutive output blocks exactly as with a one-block filter.  Device-accessible
+ * (device or managed) memory only; the transform must fit the on-chip engine (stereo N <= 8192,
+ * mono N <= 16384), otherwise nonzero is returned. */
+int mufft_execute_conv_output_partitioned_batch(mufft_plan_conv *plan, void *output, const void *spectra,
+                                                const void *filter_spectra, unsigned parts, size_t batch);
+int mufft_execute_conv_output_partitioned_batch_async(mufft_plan_conv *plan, void *output, const void *spectra,
+                                                      const void *filter_spectra, unsigned parts, size_t batch);
+
 /* Row-transform kernel flavour: 0 = direct loads (default), 1 = persistent CTAs with bulk-copy
  * prefetch into shared memory when the input rows are 16-byte aligned.  Same results either way. */
 void mufft_cuda_set_prefetch(int enable);

@@ -79,6 +79,8 @@ SIGNATURES = {
     "mufft_execute_conv_output_batch_async": (_i, [_vp, _vp, _vp, _vp, _sz, _sz]),
     "mufft_execute_conv_batch": (_i, [_vp, _vp, _vp, _vp, _sz, _sz]),
     "mufft_execute_conv_batch_async": (_i, [_vp, _vp, _vp, _vp, _sz, _sz]),
+    "mufft_execute_conv_output_partitioned_batch": (_i, [_vp, _vp, _vp, _vp, _u, _sz]),
+    "mufft_execute_conv_output_partitioned_batch_async": (_i, [_vp, _vp, _vp, _vp, _u, _sz]),
     "mufft_cuda_set_prefetch": (None, [_i]),
     "mufft_cuda_set_fused_2d": (None, [_i]),
     "mufft_cuda_set_two_kernel": (None, [_i]),

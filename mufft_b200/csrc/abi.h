@@ -22,7 +22,11 @@ enum {
     MCU_IN_HALF = 1,      /* x[i] = i < N/2 ? in[i] : 0, upper half never read (ref kernel.c:104-122,200-226,333-387) */
     MCU_IN_C2R = 2,       /* x[k] = (X[k]+conj X[N-k]) + (X[k]-conj X[N-k])*rtw[k]   (ref kernel.c:36-45) */
     MCU_IN_MUL = 3,       /* x[i] = norm * in[i] * in2[i]                            (ref kernel.c:22-34) */
-    MCU_IN_MUL_C2R = 4    /* X = norm * in .* in2, then as MCU_IN_C2R */
+    MCU_IN_MUL_C2R = 4,   /* X = norm * in .* in2, then as MCU_IN_C2R */
+    /* Partitioned convolution (frequency-domain delay line): the product is summed over `parts`
+     * (spectrum, filter-partition) pairs before the transform, see mcu_rows_args.parts */
+    MCU_IN_MULACC = 5,    /* x[i] = norm * sum_p in[p*in_part_stride + i] * in2[p*in2_part_stride + i] */
+    MCU_IN_MULACC_C2R = 6 /* X = that sum, then as MCU_IN_C2R */
 };
 /* How a row transform writes its output (last pass epilogue). */
 enum {
@@ -59,6 +63,9 @@ typedef struct mcu_rows_args {
     int in_mode, out_mode;
     float norm;
     int prefetch;          /* 1 = use the persistent bulk-copy prefetch kernel when the input allows it */
+    unsigned parts;        /* MCU_IN_MULACC*: number of (spectrum, filter partition) pairs summed per transform */
+    long long in_part_stride;  /* complex elements from the spectrum of pair p to that of pair p+1 (may be negative) */
+    long long in2_part_stride; /* same for the filter partitions */
     mcu_peer_dest peers;   /* out_mode == MCU_OUT_PEERS only */
 } mcu_rows_args;
 

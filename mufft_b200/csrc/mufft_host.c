@@ -543,11 +543,21 @@ static __thread const mcu_peer_dest *tls_peers = NULL;
 
 /* Row transforms on device-visible memory; strides in complex elements.  One fused kernel on
  * the engine, or pre-resolve / passes / post-resolve through scratch beyond its limit. */
+typedef struct part_desc {
+    unsigned parts;
+    long long in_step, in2_step; /* complex elements between consecutive (spectrum, filter partition) pairs */
+} part_desc;
+
 static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode, int out_mode, float norm,
                     void *out, size_t out_stride, const void *in, size_t in_stride,
-                    const void *in2, size_t in2_stride, size_t batch, void *stream)
+                    const void *in2, size_t in2_stride, size_t batch, void *stream, const part_desc *pd)
 {
     const unsigned n = ax->n;
+    if ((in_mode == MCU_IN_MULACC || in_mode == MCU_IN_MULACC_C2R) && (pd == NULL || n > MCU_ENGINE_MAX_N)) {
+        snprintf(tls_error, sizeof(tls_error), "partitioned convolution needs a transform that fits the on-chip engine "
+                 "(stereo N <= %u, mono N <= %u)", MCU_ENGINE_MAX_N, 2 * MCU_ENGINE_MAX_N);
+        return -1;
+    }
     if (n <= MCU_ENGINE_MAX_N) {
         mcu_rows_args a;
         memset(&a, 0, sizeof(a));
@@ -558,6 +568,7 @@ static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode
         a.in_mode = in_mode; a.out_mode = out_mode; a.norm = norm;
         a.prefetch = g_prefetch;
         if (out_mode == MCU_OUT_PEERS) a.peers = *tls_peers;
+        if (pd != NULL) { a.parts = pd->parts; a.in_part_stride = pd->in_step; a.in2_part_stride = pd->in2_step; }
         return mcu_launch_rows(&a, stream);
     }
     if (out_mode == MCU_OUT_PEERS && !(ax->n2 != 0 && g_two_kernel)) {
@@ -652,7 +663,7 @@ static int rows_unit_launch(void *ctx_, void *out, size_t out_stride, const void
     rows_ctx *ctx = ctx_;
     mufft_plan_1d *plan = ctx->plan;
     return run_rows(&plan->ax, &plan->scr, plan->d_rtw, ctx->in_mode, ctx->out_mode, ctx->norm,
-                    out, out_stride / CPX, in, in_stride / CPX, in2, in2_stride / CPX, count, stream);
+                    out, out_stride / CPX, in, in_stride / CPX, in2, in2_stride / CPX, count, stream, NULL);
 }
 
 static size_t in_unit_bytes(unsigned n, int in_mode)
@@ -750,7 +761,7 @@ int mufft_execute_plan_1d_batch_scatter_async(mufft_plan_1d *plan, void *const *
     while ((1u << d.shift) < cols) d.shift++;
     tls_peers = &d;
     int err = run_rows(&plan->ax, &plan->scr, NULL, MCU_IN_COMPLEX, MCU_OUT_PEERS, 1.0f, NULL, 0, input, in_stride / CPX,
-                       NULL, 0, batch, tls_stream);
+                       NULL, 0, batch, tls_stream, NULL);
     tls_peers = NULL;
     return err;
 }
@@ -933,10 +944,10 @@ static int conv_unit_launch(void *ctx_, void *out, size_t out_stride, const void
     for (size_t done = 0; done < count; done += chunk) {
         const size_t cnt = count - done < chunk ? count - done : chunk;
         TRY(run_rows(&fwd->ax, &fwd->scr, fwd->d_rtw, in_mode, out_mode, 1.0f, plan->d_spectra, plan->block_size / CPX,
-                     (const char *)in + done * in_stride, in_stride / CPX, NULL, 0, cnt, stream));
+                     (const char *)in + done * in_stride, in_stride / CPX, NULL, 0, cnt, stream, NULL));
         TRY(run_rows(&inv->ax, &inv->scr, inv->d_rtw, mul_mode, MCU_OUT_COMPLEX, plan->normalization,
                      (char *)out + done * out_stride, out_stride / CPX, plan->d_spectra, plan->block_size / CPX,
-                     in2_stride ? (const char *)in2 + done * in2_stride : (const char *)in2, in2_stride / CPX, cnt, stream));
+                     in2_stride ? (const char *)in2 + done * in2_stride : (const char *)in2, in2_stride / CPX, cnt, stream, NULL));
     }
     return 0;
 }
@@ -974,6 +985,52 @@ int mufft_execute_conv_batch_async(mufft_plan_conv *plan, void *output, const vo
                                    const void *filter_spectrum, size_t batch, size_t filter_stride_bytes)
 {
     return conv_fused(plan, output, input_first, filter_spectrum, batch, filter_stride_bytes, 1);
+}
+
+/* ---- partitioned convolution: filters longer than one block (additive; mufft_cuda.h) --------------
+ * The reference leaves the accumulation over filter partitions to the caller (fft.h:170-174): P
+ * conv_output calls and P-1 time-domain additions per block.  Here the P spectral products are
+ * summed in the load stage of ONE inverse transform (frequency-domain delay line). */
+static int conv_partitioned(mufft_plan_conv *plan, void *output, const void *spectra, const void *filter_spectra,
+                            unsigned parts, size_t batch, int async)
+{
+    if (plan == NULL || parts == 0) {
+        snprintf(tls_error, sizeof(tls_error), "partitioned convolution: needs a plan and at least one partition");
+        return -1;
+    }
+    if (batch == 0) return 0;
+    const size_t blk = plan->block_size;
+    const size_t out_unit = (size_t)plan->output_plan->n * CPX;
+    if ((((uintptr_t)output | (uintptr_t)spectra | (uintptr_t)filter_spectra) % CPX) != 0) {
+        snprintf(tls_error, sizeof(tls_error), "buffers must be 8-byte aligned");
+        return -1;
+    }
+    /* the history blocks in front of `spectra` are read too: classify the whole range */
+    const char *first = (const char *)spectra - (size_t)(parts - 1) * blk;
+    if (!device_visible(mcu_pointer_kind(first), (batch + parts - 1) * blk) ||
+        !device_visible(mcu_pointer_kind(spectra), batch * blk) ||
+        !device_visible(mcu_pointer_kind(filter_spectra), (size_t)parts * blk) ||
+        !device_visible(mcu_pointer_kind(output), batch * out_unit)) {
+        snprintf(tls_error, sizeof(tls_error), "partitioned convolution needs device-accessible (device or managed) pointers");
+        return -1;
+    }
+    part_desc pd = { parts, -(long long)(blk / CPX), (long long)(blk / CPX) };
+    mufft_plan_1d *inv = plan->output_plan;
+    TRY(run_rows(&inv->ax, &inv->scr, inv->d_rtw, plan->stereo ? MCU_IN_MULACC : MCU_IN_MULACC_C2R, MCU_OUT_COMPLEX,
+                 plan->normalization, output, out_unit / CPX, spectra, blk / CPX, filter_spectra, 0, batch, tls_stream, &pd));
+    if (!async) TRY(mcu_stream_sync(tls_stream));
+    return 0;
+}
+
+int mufft_execute_conv_output_partitioned_batch(mufft_plan_conv *plan, void *output, const void *spectra,
+                                                const void *filter_spectra, unsigned parts, size_t batch)
+{
+    return conv_partitioned(plan, output, spectra, filter_spectra, parts, batch, 0);
+}
+int mufft_execute_conv_output_partitioned_batch_async(mufft_plan_conv *plan, void *output, const void *spectra,
+                                                      const void *filter_spectra, unsigned parts, size_t batch)
+{
+    return conv_partitioned(plan, output, spectra, filter_spectra, parts, batch, 1);
 }
 
 /* Stand-alone spectral multiply (ref fft.h:201-207, kernel.c:22-34): runs the CUDA kernel on
@@ -1219,14 +1276,14 @@ static int run_2d_device(mufft_plan_2d *plan, void *out, const void *in, size_t 
             /* rows: C2R resolve fused into the load, result dense (pitch nx complex = Nx floats) */
             /* (the rows of all images of the group form one batch: image stride = ny rows) */
             TRY(run_rows(&plan->ax_x, &plan->scr_rows, plan->d_rtw, MCU_IN_C2R, MCU_OUT_COMPLEX, 1.0f,
-                         dst, nx, plan->d_mid, mid_pitch, NULL, 0, cnt * ny, stream));
+                         dst, nx, plan->d_mid, mid_pitch, NULL, 0, cnt * ny, stream, NULL));
         } else {
             const size_t in_image = (size_t)nx * ny; /* complex elements (real rows: Nx floats = nx complex) */
             const char *src = (const char *)in + done * in_image * CPX;
             char *dst = (char *)out + done * mid_image * CPX;
             const int out_mode = plan->kind == KIND_R2C ? MCU_OUT_R2C : (plan->kind == KIND_R2C_FULL ? MCU_OUT_R2C_FULL : MCU_OUT_COMPLEX);
             TRY(run_rows(&plan->ax_x, &plan->scr_rows, plan->d_rtw, MCU_IN_COMPLEX, out_mode, 1.0f,
-                         plan->d_mid, mid_pitch, src, nx, NULL, 0, cnt * ny, stream));
+                         plan->d_mid, mid_pitch, src, nx, NULL, 0, cnt * ny, stream, NULL));
             TRY(run_cols(plan, dst, mid_pitch, mid_image, plan->d_mid, mid_pitch, mid_image, plan->vertical_nx, cnt, stream));
         }
     }

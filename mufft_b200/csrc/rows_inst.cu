@@ -88,6 +88,8 @@ cudaError_t MUFFT_CAT(rows_launch_, ROWS_N, _inv)(const mcu_rows_args &a, cudaSt
     case MCU_IN_C2R: return launch_mode<MCU_IN_C2R, MCU_OUT_COMPLEX>(a, s);
     case MCU_IN_MUL: return launch_mode<MCU_IN_MUL, MCU_OUT_COMPLEX>(a, s);
     case MCU_IN_MUL_C2R: return launch_mode<MCU_IN_MUL_C2R, MCU_OUT_COMPLEX>(a, s);
+    case MCU_IN_MULACC: return launch_mode<MCU_IN_MULACC, MCU_OUT_COMPLEX>(a, s);
+    case MCU_IN_MULACC_C2R: return launch_mode<MCU_IN_MULACC_C2R, MCU_OUT_COMPLEX>(a, s);
     default: return cudaErrorInvalidValue;
     }
 }

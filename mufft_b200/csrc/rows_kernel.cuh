@@ -27,7 +27,7 @@ __host__ __device__ constexpr int rows_variant(int n, int in_mode, int out_mode)
 {
     if ((out_mode == MCU_OUT_R2C || out_mode == MCU_OUT_R2C_FULL) && engine_variant_exists(n, MUFFT_VARIANT_MIRROR_LAST))
         return MUFFT_VARIANT_MIRROR_LAST;
-    if ((in_mode == MCU_IN_C2R || in_mode == MCU_IN_MUL_C2R) && engine_variant_exists(n, MUFFT_VARIANT_MIRROR_FIRST))
+    if ((in_mode == MCU_IN_C2R || in_mode == MCU_IN_MUL_C2R || in_mode == MCU_IN_MULACC_C2R) && engine_variant_exists(n, MUFFT_VARIANT_MIRROR_FIRST))
         return MUFFT_VARIANT_MIRROR_FIRST;
     return MUFFT_VARIANT_GENERAL;
 }
@@ -66,12 +66,34 @@ __device__ __forceinline__ cpx c2r_pair(cpx xa, cpx xb, cpx w, cpx &zm)
     return cadd(a, b);
 }
 
+// Partitioned convolution (MCU_IN_MULACC*): the spectral product is a sum over `parts` pairs of
+// (block spectrum, filter-partition spectrum), `in_step` / `in2_step` complex elements apart.
+struct rows_parts {
+    unsigned parts;
+    long long in_step, in2_step;
+};
+
+// sum_p in[p*in_step + k] * in2[p*in2_step + k]
+template <typename Ptr>
+__device__ __forceinline__ cpx mulacc_at(Ptr in, const cpx *__restrict__ in2, int k, const rows_parts &pp)
+{
+    cpx acc = make_float2(0.0f, 0.0f);
+#pragma unroll 2
+    for (unsigned p = 0; p < pp.parts; p++) {
+        const cpx x = in[(long long)p * pp.in_step + k];
+        const cpx w = __ldg(in2 + (long long)p * pp.in2_step + k);
+        acc.x = fmaf(x.x, w.x, fmaf(-x.y, w.y, acc.x));
+        acc.y = fmaf(x.x, w.y, fmaf(x.y, w.x, acc.y));
+    }
+    return acc;
+}
+
 // ---- prologue: registers <- input ------------------------------------------------------------------
 // Variant 0 / 1: element k = t + e*T in slot e.  Variant 2: the slots of the mirrored first pass.
 // `in` may point to global memory or to a shared-memory landing buffer.
 template <int N, int IN_MODE, int V, typename Ptr>
 __device__ __forceinline__ void rows_load(cpx (&v)[engine_regs(N, V)], Ptr in, const cpx *__restrict__ in2,
-                                          const cpx *__restrict__ rtw, float norm, int t)
+                                          const cpx *__restrict__ rtw, float norm, int t, const rows_parts pp = { 1, 0, 0 })
 {
     constexpr int R = engine_regs(N, V);
     constexpr int T = N / R;
@@ -90,19 +112,43 @@ __device__ __forceinline__ void rows_load(cpx (&v)[engine_regs(N, V)], Ptr in, c
         for (int e = 0; e < R; e++) v[e] = in[t + e * T];
 #pragma unroll
         for (int e = 0; e < R; e++) v[e] = cscale(norm, cmul(v[e], w[e]));
+    } else if constexpr (IN_MODE == MCU_IN_MULACC) {
+        // partition loop outermost: every partition is one coalesced sweep over the block spectrum
+#pragma unroll
+        for (int e = 0; e < R; e++) v[e] = make_float2(0.0f, 0.0f);
+#pragma unroll 1
+        for (unsigned p = 0; p < pp.parts; p++) {
+            const cpx *__restrict__ f = in2 + (long long)p * pp.in2_step;
+            cpx w[R];
+#pragma unroll
+            for (int e = 0; e < R; e++) w[e] = __ldg(f + t + e * T);
+#pragma unroll
+            for (int e = 0; e < R; e++) {
+                const cpx x = in[(long long)p * pp.in_step + t + e * T];
+                v[e].x = fmaf(x.x, w[e].x, fmaf(-x.y, w[e].y, v[e].x));
+                v[e].y = fmaf(x.x, w[e].y, fmaf(x.y, w[e].x, v[e].y));
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < R; e++) v[e] = cscale(norm, v[e]);
     } else if constexpr (V == MUFFT_VARIANT_MIRROR_FIRST) {
         // C2R resolve, optionally on the product of two spectra, feeding the mirrored first pass:
         // group u holds butterfly i0 (bins i0 + m*Q0), group u + H its image Q0 - i0 (bins
         // Q0 - i0 + m*Q0); bin N - (i0 + m*Q0) is input r-1-m of the image.
         constexpr bool mul = IN_MODE == MCU_IN_MUL_C2R;
+        constexpr bool mulacc = IN_MODE == MCU_IN_MULACC_C2R;
         constexpr int r = engine_radix(N, 0, V);
         constexpr int NB = R / r;
         constexpr int H = NB / 2;
         constexpr int Q0 = N / r;
         auto fetch = [&](int k) {
-            cpx x = in[k];
-            if constexpr (mul) x = cscale(norm, cmul(x, __ldg(in2 + k)));
-            return x;
+            if constexpr (mulacc) {
+                return cscale(norm, mulacc_at(in, in2, k, pp));
+            } else {
+                cpx x = in[k];
+                if constexpr (mul) x = cscale(norm, cmul(x, __ldg(in2 + k)));
+                return x;
+            }
         };
 #pragma unroll
         for (int u = 0; u < H; u++) {
@@ -146,11 +192,18 @@ __device__ __forceinline__ void rows_load(cpx (&v)[engine_regs(N, V)], Ptr in, c
     } else {
         // C2R resolve, optionally on the product of two spectra.  Reads bins k and N-k.
         constexpr bool mul = IN_MODE == MCU_IN_MUL_C2R;
+        constexpr bool mulacc = IN_MODE == MCU_IN_MULACC_C2R;
 #pragma unroll
         for (int e = 0; e < R; e++) {
             const int k = t + e * T;
-            cpx xa = in[k];
-            cpx xb = in[N - k];
+            cpx xa, xb;
+            if constexpr (mulacc) {
+                xa = cscale(norm, mulacc_at(in, in2, k, pp));
+                xb = cscale(norm, mulacc_at(in, in2, N - k, pp));
+            } else {
+                xa = in[k];
+                xb = in[N - k];
+            }
             if constexpr (mul) {
                 xa = cscale(norm, cmul(xa, __ldg(in2 + k)));
                 xb = cscale(norm, cmul(xb, __ldg(in2 + N - k)));
@@ -293,7 +346,10 @@ fft_rows_kernel(const mcu_rows_args a)
     const cpx *__restrict__ in2 = static_cast<const cpx *>(a.in2) + b * a.in2_stride;
 
     cpx v[R];
-    rows_load<N, IN_MODE, V>(v, in, in2, rtw, a.norm, t);
+    if constexpr (IN_MODE == MCU_IN_MULACC || IN_MODE == MCU_IN_MULACC_C2R)
+        rows_load<N, IN_MODE, V>(v, in, static_cast<const cpx *>(a.in2), rtw, a.norm, t, rows_parts{ a.parts, a.in_part_stride, a.in2_part_stride });
+    else
+        rows_load<N, IN_MODE, V>(v, in, in2, rtw, a.norm, t);
     engine_run<N, DIR, 1, T, TPC, 0, V, rows_packed(N, IN_MODE, OUT_MODE)>(v, sm, tw, t, slot);
     if constexpr (OUT_MODE == MCU_OUT_PEERS) {
         if (active) rows_store_peers<N, V>(v, a.peers, b, t);
@@ -344,7 +400,7 @@ __host__ __device__ constexpr size_t rows_tma_smem_bytes(int n, int in_mode, int
 // The bulk-copy path needs whole 16-byte chunks.
 __host__ __device__ constexpr bool rows_tma_supported(int n, int in_mode, int v = 0)
 {
-    return n >= 64 && rows_land_bytes(n, in_mode) % 16 == 0 && rows_tma_smem_bytes(n, in_mode, v) <= 227 * 1024 &&
+    return n >= 64 && in_mode <= MCU_IN_MUL_C2R && rows_land_bytes(n, in_mode) % 16 == 0 && rows_tma_smem_bytes(n, in_mode, v) <= 227 * 1024 &&
            MUFFT_TMA_STAGES * rows_per_cta(n, v) * 8 <= 128;
 }
 

@@ -227,6 +227,51 @@ def test_conv_fused_batch_device(m, torch, oracle, n, stereo, padded):
         assert np.max(np.abs(got - want)) < 2e-6 * math.sqrt(n) * (1 if padded else 2)
 
 
+@pytest.mark.parametrize("n,parts", [(64, 1), (64, 5), (2048, 3), (8192, 8), (16384, 4)])
+@pytest.mark.parametrize("stereo", [0, 1])
+def test_conv_partitioned_device(m, torch, oracle, n, parts, stereo):
+    """Uniformly partitioned convolution (filter of parts * N/2 taps): one inverse transform per block
+    on the sum of `parts` spectral products, against the oracle's per-partition
+    conv_input + conv_output results added up in float64 (what a caller of the reference does,
+    fft.h:170-174)."""
+    method = stereo | 4 | 8
+    batch = min(batch_for(n) // 4 + 3, 2000)
+    plan = m.mufft_create_plan_conv(n, 0, method)
+    assert plan
+    blk = m.mufft_conv_get_transformed_block_size(plan) // 8
+    half = n // 2
+    total = batch + parts - 1                                  # parts-1 blocks of history in front
+    x = dev_random(torch, (total, 2 * half if stereo else half), 31)
+    taps = dev_random(torch, (parts, half), 32)
+    spectra = torch.zeros((total, 2 * blk), dtype=torch.float32, device="cuda")
+    fspec = torch.zeros((parts, 2 * blk), dtype=torch.float32, device="cuda")
+    out = torch.zeros((batch, 2 * n if stereo else n), dtype=torch.float32, device="cuda")
+    assert m.mufft_execute_conv_input_batch(plan, 0, spectra.data_ptr(), x.data_ptr(), total) == 0
+    assert m.mufft_execute_conv_input_batch(plan, 1, fspec.data_ptr(), taps.data_ptr(), parts) == 0
+    first = spectra.data_ptr() + (parts - 1) * blk * 8
+    err = m.mufft_execute_conv_output_partitioned_batch(plan, out.data_ptr(), first, fspec.data_ptr(), parts, batch)
+    if stereo and n > 8192:
+        assert err != 0 and b"on-chip engine" in m.mufft_cuda_last_error()
+        m.mufft_free_plan_conv(plan)
+        return
+    assert err == 0, m.mufft_cuda_last_error()
+    if parts == 1:  # one partition = plain conv_output
+        out1 = torch.zeros_like(out)
+        assert m.mufft_execute_conv_output_batch(plan, out1.data_ptr(), first, fspec.data_ptr(), batch, 0) == 0
+        assert float((out - out1).abs().max()) <= 1e-5
+    m.mufft_free_plan_conv(plan)
+    xs, hs = x.cpu().numpy(), taps.cpu().numpy()
+    for b in sample_indices(batch, 3, seed=n):
+        want = np.zeros(n, np.complex128 if stereo else np.float64)
+        for p in range(parts):
+            blk_in = xs[b + parts - 1 - p]
+            piece, _, _ = oracle.conv(blk_in.view(np.complex64) if stereo else blk_in, hs[p], n, method)
+            want += piece
+        got = out[b].cpu().numpy()
+        got = got.view(np.complex64) if stereo else got
+        assert rel_l2(got, want) <= 2 * tol(n)
+
+
 def test_conv_fused_batch_host_memory(m, torch, oracle):
     """Pageable host buffers go through the staged path (chunks over several streams)."""
     n, batch, method = 1024, 3000, 1 | 4 | 8
