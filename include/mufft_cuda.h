@@ -133,6 +133,13 @@ void mufft_cuda_set_prefetch(int enable);
  * and columns of the whole batch with the intermediate kept in L2, 0 = separate row and column
  * kernels per group of images (what every other 2D shape uses).  Same results either way. */
 void mufft_cuda_set_fused_2d(int enable);
+/* Longest row transform done by ONE kernel, for plans created afterwards: 8192 (default) or 16384
+ * (one 512-thread CTA per 16384-point transform, read once and written once, instead of the
+ * two-kernel split; affects 1D plans of 16384 complex / 32768 real points and 2D plans with such
+ * rows).  Other values are rounded down to one of the two.  Same results either way.
+ * MUFFT_CUDA_ONCHIP_LIMIT in the environment sets the initial value. */
+void mufft_cuda_set_onchip_limit(unsigned n);
+unsigned mufft_cuda_get_onchip_limit(void);
 /* Transform lengths 16384 .. 2097152: 1 (default) = two kernels (N = N1*N2: column transforms, then
  * twiddle + row transforms with a transposed store), 0 = one generic radix pass per kernel. */
 void mufft_cuda_set_two_kernel(int enable);

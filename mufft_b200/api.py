@@ -84,6 +84,8 @@ SIGNATURES = {
     "mufft_cuda_set_prefetch": (None, [_i]),
     "mufft_cuda_set_fused_2d": (None, [_i]),
     "mufft_cuda_set_two_kernel": (None, [_i]),
+    "mufft_cuda_set_onchip_limit": (None, [_u]),
+    "mufft_cuda_get_onchip_limit": (_u, []),
     "mufft_cuda_plan_1d_uses_engine": (_i, [_vp]),
     "mufft_cuda_plan_2d_paths": (_i, [_vp]),
 }

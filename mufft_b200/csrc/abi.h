@@ -13,6 +13,10 @@ extern "C" {
 
 /* Largest transform length handled by the single-kernel shared-memory engine. */
 #define MCU_ENGINE_MAX_N 8192
+/* Row kernels are also built for this length (one 512-thread CTA per transform, one CTA per SM);
+ * the host layer uses them instead of the two-kernel split only when asked to
+ * (mufft_cuda_set_onchip_limit / MUFFT_CUDA_ONCHIP_LIMIT), until the choice has been measured. */
+#define MCU_ENGINE_BIG_N 16384
 /* Largest column length handled by the shared-memory column kernel. */
 #define MCU_COLS_MAX_N 2048
 

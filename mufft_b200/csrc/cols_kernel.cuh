@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(cols_cta_threads(N)) fft_cols_kernel(const mcu
     constexpr int R = engine_regs(N);
     constexpr int T = N / R;
     constexpr int TC = cols_tile(N);
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    MUFFT_DYNAMIC_SMEM(smem_raw);
 
     const int tid = threadIdx.x;
     const int c = tid % TC;  // column inside the tile: fastest, so a warp reads whole row segments

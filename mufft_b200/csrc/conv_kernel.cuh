@@ -31,7 +31,7 @@ fft_conv_fused_kernel(const mcu_conv_args a)
     constexpr int TPC = rows_per_cta(N, 0);
     constexpr int SH = engine_pad_shift(N, 0);
     constexpr int PK = N == 8192 ? 1 : -1; // packed complex adds: measured 2.79 -> 2.60 ms on the stereo N = 8192 workload
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    MUFFT_DYNAMIC_SMEM(smem_raw);
 
     const int tid = threadIdx.x;
     const int slot = tid / T;

@@ -18,7 +18,7 @@ namespace mufft {
 MUFFT_DECLARE_ROWS(2) MUFFT_DECLARE_ROWS(4) MUFFT_DECLARE_ROWS(8) MUFFT_DECLARE_ROWS(16)
 MUFFT_DECLARE_ROWS(32) MUFFT_DECLARE_ROWS(64) MUFFT_DECLARE_ROWS(128) MUFFT_DECLARE_ROWS(256)
 MUFFT_DECLARE_ROWS(512) MUFFT_DECLARE_ROWS(1024) MUFFT_DECLARE_ROWS(2048) MUFFT_DECLARE_ROWS(4096)
-MUFFT_DECLARE_ROWS(8192)
+MUFFT_DECLARE_ROWS(8192) MUFFT_DECLARE_ROWS(16384)
 #define MUFFT_DECLARE_CONV(n) cudaError_t conv_launch_##n(const mcu_conv_args &, cudaStream_t);
 MUFFT_DECLARE_CONV(2) MUFFT_DECLARE_CONV(4) MUFFT_DECLARE_CONV(8) MUFFT_DECLARE_CONV(16)
 MUFFT_DECLARE_CONV(32) MUFFT_DECLARE_CONV(64) MUFFT_DECLARE_CONV(128) MUFFT_DECLARE_CONV(256)
@@ -148,8 +148,10 @@ static void fill_table_variant(float *table, int direction, int variant)
     else fill_table<N, 0>(table, direction);
 }
 
-#define MUFFT_FOR_ENGINE_SIZES(X) \
+#define MUFFT_FOR_CONV_SIZES(X) \
     X(2) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192)
+// row kernels also exist for MCU_ENGINE_BIG_N
+#define MUFFT_FOR_ENGINE_SIZES(X) MUFFT_FOR_CONV_SIZES(X) X(16384)
 
 } // namespace mufft
 
@@ -301,7 +303,7 @@ int mcu_launch_conv(const mcu_conv_args *a, void *stream)
     g_launches.fetch_add(1, std::memory_order_relaxed);
     switch (a->n) {
 #define X(v) case v: return (int)conv_launch_##v(*a, s);
-        MUFFT_FOR_ENGINE_SIZES(X)
+        MUFFT_FOR_CONV_SIZES(X)
 #undef X
     default: return (int)cudaErrorInvalidValue;
     }

@@ -58,15 +58,48 @@ __host__ __device__ constexpr size_t f2d_smem_bytes(int nx, int ny)
 // Polling load (no L1 invalidation per iteration; the acquire fence follows once, after success).
 __device__ __forceinline__ unsigned ld_relaxed(const unsigned *p)
 {
+#ifdef MUFFT_EMU
+    return __atomic_load_n(p, __ATOMIC_RELAXED);
+#else
     unsigned v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+#endif
 }
 // Release increment: the CTA's row stores (ordered before it by the preceding bar.sync) become
 // visible to whoever acquires the counter.
 __device__ __forceinline__ void red_release_add(unsigned *p, unsigned v)
 {
+#ifdef MUFFT_EMU
+    __atomic_fetch_add(p, v, __ATOMIC_RELEASE);
+#else
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ void red_relaxed_add(unsigned *p, unsigned v)
+{
+#ifdef MUFFT_EMU
+    __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
+#else
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ void fence_acq_rel_gpu()
+{
+#ifdef MUFFT_EMU
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+#else
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
+}
+// Pull `bytes` (a multiple of 16, 16-byte aligned) into L2 ahead of use.
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
+{
+#ifdef MUFFT_EMU
+    (void)p; (void)bytes;
+#else
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#endif
 }
 
 template <int NX, int NY, int DIR>
@@ -77,8 +110,9 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d
     constexpr int REP = f2d_row_repeat(NX, NY);
     constexpr unsigned NR = NY / (ROWS * REP); // row tickets per image
     constexpr unsigned NC = NX / COLS; // column tickets per image
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ unsigned s_ticket[2], s_wait[2];
+    MUFFT_DYNAMIC_SMEM(smem_raw);
+    MUFFT_STATIC_SMEM_U32(s_ticket, 2);
+    MUFFT_STATIC_SMEM_U32(s_wait, 2);
     cpx *smem = reinterpret_cast<cpx *>(smem_raw);
 
     const int tid = threadIdx.x;
@@ -119,8 +153,8 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d
     unsigned pending = ~0u; // thread 0 only
     auto release_pending = [&]() {
         if (pending != ~0u) {
-            asm volatile("fence.acq_rel.gpu;" ::: "memory");
-            asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(rows_done + pending), "r"((unsigned)(ROWS * REP)) : "memory");
+            fence_acq_rel_gpu();
+            red_relaxed_add(rows_done + pending, (unsigned)(ROWS * REP));
             pending = ~0u;
         }
     };
@@ -144,7 +178,7 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d
                 if (pending != ~0u) wait = 1;
                 else wait_rows(image);
             }
-            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            fence_acq_rel_gpu();
         }
         s_ticket[slot] = k;
         s_wait[slot] = wait;
@@ -165,7 +199,7 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d
                 decode(k, image, tile);
                 release_pending();
                 wait_rows(image);
-                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                fence_acq_rel_gpu();
             }
             __syncthreads();
         }
@@ -190,7 +224,7 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d
             if (tid == 0 && image + 1 < a.batch) {
                 const cpx *nxt = static_cast<const cpx *>(a.in) + (size_t)(image + 1) * a.in_image + (size_t)tile * (REP * ROWS) * NX;
                 if ((reinterpret_cast<uintptr_t>(nxt) & 15) == 0)
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt), "r"((unsigned)(REP * ROWS * NX * sizeof(cpx))) : "memory");
+                    prefetch_l2_bulk(nxt, (unsigned)(REP * ROWS * NX * sizeof(cpx)));
             }
 #pragma unroll 1
             for (int rep = 0; rep < REP; rep++) {

@@ -21,10 +21,24 @@
 // numpy.fft) and the bank-conflict count that picked the padding.
 #pragma once
 
+#ifdef MUFFT_EMU
+#include "cuda_emu.h" // tests/emu: CPU emulation of the execution model, test builds only
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <type_traits>
 #include <utility>
+
+// Shared-memory declarations, spelled through macros so that tests/emu can give every emulated
+// CTA its own storage; in the CUDA build they are the plain declarations.
+#ifdef MUFFT_EMU
+#define MUFFT_DYNAMIC_SMEM(name) unsigned char *name = emu::dyn_smem()
+#define MUFFT_STATIC_SMEM_U32(name, count) unsigned *name = emu::static_smem<unsigned>(count)
+#else
+#define MUFFT_DYNAMIC_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#define MUFFT_STATIC_SMEM_U32(name, count) __shared__ unsigned name[count]
+#endif
 
 namespace mufft {
 
@@ -139,6 +153,7 @@ __host__ __device__ constexpr engine_shape_t engine_shape(int n, int variant = 0
         case 2048: return { 32, 3, { 32, 32, 2, 1 }, 64, 1, 5, 1 };
         case 4096: return { 32, 3, { 16, 16, 16, 1 }, 128, 4, 4, 1 };
         case 8192: return { 32, 3, { 32, 16, 16, 1 }, 256, 2, 5, 0 };
+        case 16384: return { 32, 3, { 32, 32, 16, 1 }, 512, 1, 5, 0 };
         default: return { 0, 0, { 1, 1, 1, 1 }, 256, 1, 0, 1 };
         }
     }
@@ -148,6 +163,7 @@ __host__ __device__ constexpr engine_shape_t engine_shape(int n, int variant = 0
         case 2048: return { 16, 3, { 8, 16, 16, 1 }, 128, 6, 4, 1 };
         case 4096: return { 32, 3, { 16, 16, 16, 1 }, 128, 4, 4, 1 };
         case 8192: return { 32, 3, { 16, 16, 32, 1 }, 256, 2, 4, 1 };
+        case 16384: return { 32, 3, { 16, 32, 32, 1 }, 512, 1, 4, 1 };
         default: return { 0, 0, { 1, 1, 1, 1 }, 256, 1, 0, 1 };
         }
     }
@@ -165,6 +181,10 @@ __host__ __device__ constexpr engine_shape_t engine_shape(int n, int variant = 0
     case 2048: return { 32, 3, { 32, 32, 2, 1 }, 64, 1, 0, 1 };
     case 4096: return { 16, 3, { 16, 16, 16, 1 }, 256, 3, 0, 1 };
     case 8192: return { 32, 3, { 32, 16, 16, 1 }, 256, 2, 0, 0 };
+    // One CTA of 512 threads per transform, the whole register file of an SM (128 registers per
+    // thread) and 132 KiB of exchange area: one CTA per SM.  Opt-in until measured (abi.h:
+    // MCU_ENGINE_BIG_N); the default for this length is the two-kernel split.
+    case 16384: return { 32, 3, { 32, 32, 16, 1 }, 512, 1, 0, 0 };
     default: return { 0, 0, { 1, 1, 1, 1 }, 256, 1, 0, 1 };
     }
 }
@@ -344,7 +364,11 @@ __device__ __forceinline__ void engine_sync(int slot)
     } else if constexpr (SLOTS == 1) {
         __syncthreads();
     } else {
+#ifdef MUFFT_EMU
+        emu::bar_sync(slot + 1, T);
+#else
         asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(T) : "memory");
+#endif
     }
 }
 

@@ -63,10 +63,18 @@ static size_t g_stage_chunk_bytes = (size_t)64 << 20;
  * input rows are 16-byte aligned.  MUFFT_CUDA_PREFETCH in the environment sets the initial value,
  * mufft_cuda_set_prefetch() changes it. */
 static int g_prefetch = 0;
+/* Longest row transform that plans created from now on run in ONE kernel: MCU_ENGINE_MAX_N
+ * (default) or MCU_ENGINE_BIG_N (16384 points: one 512-thread CTA per transform instead of the
+ * two-kernel split; opt-in until measured on the GPU). */
+static unsigned g_onchip_limit = MCU_ENGINE_MAX_N;
+void mufft_cuda_set_onchip_limit(unsigned n) { g_onchip_limit = n >= MCU_ENGINE_BIG_N ? MCU_ENGINE_BIG_N : MCU_ENGINE_MAX_N; }
+unsigned mufft_cuda_get_onchip_limit(void) { return g_onchip_limit; }
 __attribute__((constructor)) static void read_env(void)
 {
     const char *e = getenv("MUFFT_CUDA_PREFETCH");
     if (e != NULL) g_prefetch = e[0] == '1';
+    e = getenv("MUFFT_CUDA_ONCHIP_LIMIT");
+    if (e != NULL) g_onchip_limit = atoi(e) >= MCU_ENGINE_BIG_N ? MCU_ENGINE_BIG_N : MCU_ENGINE_MAX_N;
     e = getenv("MUFFT_CUDA_L2_CHUNK_MB");
     if (e != NULL && atoi(e) >= 1 && atoi(e) <= 4096) g_l2_chunk_bytes = (size_t)atoi(e) << 20;
     e = getenv("MUFFT_CUDA_MID_GROUP_MB");
@@ -178,7 +186,7 @@ static void *upload(const void *host, size_t bytes)
 typedef struct axis {
     unsigned n;
     int direction;
-    void *d_engine_tw; /* engine table, n <= MCU_ENGINE_MAX_N */
+    void *d_engine_tw; /* engine table: non-NULL = row transforms of this axis run in one kernel */
     void *d_engine_tw_real; /* table of the mirrored-pass shape the R2C (forward) / C2R (inverse) row kernel uses, or NULL */
     void *d_roots;     /* exp(dir*2*pi*i*j/n), j < n: generic multi-pass kernels, two-kernel split */
     unsigned n1, n2;   /* two-kernel split n = n1 * n2 (0 = not used) */
@@ -217,7 +225,7 @@ static int axis_init(axis *ax, unsigned n, int direction, int want_generic)
     memset(ax, 0, sizeof(*ax));
     ax->n = n;
     ax->direction = direction;
-    if (n <= MCU_ENGINE_MAX_N) {
+    if (n <= g_onchip_limit) {
         ax->d_engine_tw = make_engine_table(n, direction, 0);
         if (!ax->d_engine_tw) return -1;
         /* the real transforms may run on a different engine shape (abi.h: mcu_rows_variant) */
@@ -500,7 +508,7 @@ mufft_plan_1d *mufft_create_plan_1d_c2c(unsigned N, int direction, unsigned flag
     plan->kind = KIND_C2C;
     plan->direction = direction;
     plan->zero_pad = (flags & MUFFT_FLAG_ZERO_PAD_UPPER_HALF) != 0;
-    plan->use_engine = N <= MCU_ENGINE_MAX_N;
+    plan->use_engine = N <= g_onchip_limit;
     if (axis_init(&plan->ax, N, direction, plan->use_engine ? 0 : AXIS_ROWS) != 0) {
         mufft_free_plan_1d(plan);
         return NULL;
@@ -553,12 +561,12 @@ static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode
                     const void *in2, size_t in2_stride, size_t batch, void *stream, const part_desc *pd)
 {
     const unsigned n = ax->n;
-    if ((in_mode == MCU_IN_MULACC || in_mode == MCU_IN_MULACC_C2R) && (pd == NULL || n > MCU_ENGINE_MAX_N)) {
+    if ((in_mode == MCU_IN_MULACC || in_mode == MCU_IN_MULACC_C2R) && (pd == NULL || ax->d_engine_tw == NULL)) {
         snprintf(tls_error, sizeof(tls_error), "partitioned convolution needs a transform that fits the on-chip engine "
                  "(stereo N <= %u, mono N <= %u)", MCU_ENGINE_MAX_N, 2 * MCU_ENGINE_MAX_N);
         return -1;
     }
-    if (n <= MCU_ENGINE_MAX_N) {
+    if (ax->d_engine_tw != NULL) {
         mcu_rows_args a;
         memset(&a, 0, sizeof(a));
         a.out = out; a.in = in; a.in2 = in2; a.rtw = d_rtw;
@@ -924,7 +932,7 @@ static int conv_unit_launch(void *ctx_, void *out, size_t out_stride, const void
     mufft_plan_1d *fwd = plan->plans[0], *inv = plan->output_plan;
     int in_mode, out_mode;
     plan_modes(fwd, &in_mode, &out_mode);
-    if (fwd->use_engine) {
+    if (fwd->use_engine && fwd->n <= MCU_ENGINE_MAX_N) { /* the one-kernel convolution stops at MCU_ENGINE_MAX_N */
         mcu_conv_args a;
         memset(&a, 0, sizeof(a));
         a.out = out; a.in = in; a.filter = in2;
@@ -1114,7 +1122,7 @@ static mufft_plan_2d *plan_2d_common(unsigned nx, unsigned ny, int direction, in
     plan->kind = kind;
     plan->vertical_nx = nx;
     plan->cols_engine = ny <= MCU_COLS_MAX_N;
-    if (axis_init(&plan->ax_x, nx, direction, nx > MCU_ENGINE_MAX_N ? AXIS_ROWS : 0) != 0 ||
+    if (axis_init(&plan->ax_x, nx, direction, nx > g_onchip_limit ? AXIS_ROWS : 0) != 0 ||
         axis_init(&plan->ax_y, ny, direction, plan->cols_engine ? 0 : AXIS_COLS) != 0) {
         mufft_free_plan_2d(plan);
         return NULL;
@@ -1163,7 +1171,7 @@ mufft_plan_2d *mufft_create_plan_2d_c2r(unsigned Nx, unsigned Ny, unsigned flags
 int mufft_cuda_plan_2d_paths(const mufft_plan_2d *plan)
 {
     if (plan == NULL) return 0;
-    return (plan->nx <= MCU_ENGINE_MAX_N ? 1 : 0) | (plan->cols_engine ? 2 : 0);
+    return (plan->ax_x.d_engine_tw != NULL ? 1 : 0) | (plan->cols_engine ? 2 : 0);
 }
 
 /* Column transforms of `images` images on device-visible memory; pitches in complex elements. */

@@ -330,7 +330,7 @@ fft_rows_kernel(const mcu_rows_args a)
     constexpr int R = engine_regs(N, V);
     constexpr int T = N / R;
     constexpr int TPC = rows_per_cta(N, V);
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    MUFFT_DYNAMIC_SMEM(smem_raw);
 
     const int tid = threadIdx.x;
     const int slot = tid / T;
@@ -360,6 +360,7 @@ fft_rows_kernel(const mcu_rows_args a)
 }
 
 // ---- kernel 2: persistent, inputs prefetched into shared memory by bulk async copies ------------
+#ifndef MUFFT_EMU // bulk async copies and mbarriers are not emulated (tests/emu)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
@@ -387,6 +388,8 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t b
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+#endif // MUFFT_EMU
+
 #define MUFFT_TMA_STAGES 2
 // Bytes a landing buffer receives per transform (a multiple of 16).
 __host__ __device__ constexpr int rows_land_bytes(int n, int in_mode)
@@ -404,6 +407,7 @@ __host__ __device__ constexpr bool rows_tma_supported(int n, int in_mode, int v 
            MUFFT_TMA_STAGES * rows_per_cta(n, v) * 8 <= 128;
 }
 
+#ifndef MUFFT_EMU
 template <int N, int DIR, int IN_MODE, int OUT_MODE>
 __global__ void __launch_bounds__(rows_cta_threads(N, rows_variant(N, IN_MODE, OUT_MODE)), engine_min_blocks(N, rows_variant(N, IN_MODE, OUT_MODE)))
 fft_rows_tma_kernel(const mcu_rows_args a)
@@ -414,7 +418,7 @@ fft_rows_tma_kernel(const mcu_rows_args a)
     constexpr int TPC = rows_per_cta(N, V);
     constexpr int STAGES = MUFFT_TMA_STAGES;
     constexpr int LAND = rows_land_bytes(N, IN_MODE);
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    MUFFT_DYNAMIC_SMEM(smem_raw);
 
     const int tid = threadIdx.x;
     const int slot = tid / T;
@@ -475,5 +479,7 @@ fft_rows_tma_kernel(const mcu_rows_args a)
         }
     }
 }
+
+#endif // MUFFT_EMU
 
 } // namespace mufft

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(rowst_cta_threads(N2)) fft_rowst_kernel(const 
     constexpr int SH = engine_pad_shift(N2);
     constexpr int SE = engine_smem_elems(N2);
     static_assert(NP >= 2, "the mapping switch needs an exchange");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    MUFFT_DYNAMIC_SMEM(smem_raw);
     cpx *smem = reinterpret_cast<cpx *>(smem_raw);
 
     const int tid = threadIdx.x;

@@ -1,0 +1,24 @@
+// TEST INFRASTRUCTURE ONLY: the fused 2D kernel of mufft_b200/csrc/fft2d_kernel.cuh compiled for the
+// CPU emulation at one image shape (-DEMU_NX=<nx> -DEMU_NY=<ny>).  `ctas` CTAs run concurrently
+// (all resident, as the persistent launch on the GPU), so the ticket / rows-done protocol between
+// CTAs is exercised for real.
+#include "fft2d_kernel.cuh"
+
+using namespace mufft;
+#define EMU_CAT_(a, b, c, d) a##b##c##d
+#define EMU_CAT(a, b, c, d) EMU_CAT_(a, b, c, d)
+
+extern "C" int EMU_CAT(emu_2d_fused_, EMU_NX, x, EMU_NY)(int direction, void *out, const void *in, const void *tw_x, const void *tw_y,
+                                                        unsigned *counters, size_t batch, unsigned lag, unsigned ctas)
+{
+    constexpr int NX = EMU_NX, NY = EMU_NY;
+    if (!f2d_supported(NX, NY)) return -3;
+    mcu_2d_args a;
+    memset(&a, 0, sizeof(a));
+    a.out = out; a.in = in; a.tw_x = tw_x; a.tw_y = tw_y; a.counters = counters;
+    a.out_image = (size_t)NX * NY; a.in_image = (size_t)NX * NY; a.batch = batch; a.nx = NX; a.ny = NY;
+    a.direction = direction; a.lag = lag;
+    if (direction < 0) emu::launch(emu::idx3{ ctas, 1, 1 }, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, -1>(a); });
+    else emu::launch(emu::idx3{ ctas, 1, 1 }, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, 1>(a); });
+    return 0;
+}

@@ -1,0 +1,163 @@
+"""The CUDA kernel templates run on the CPU emulation of tests/emu (one OS thread per CUDA thread,
+real barriers, per-CTA shared memory) and checked against the oracle.
+
+This is a test of the kernels' LOGIC - index maps of every engine shape, prologue / epilogue
+modes, barrier placement, the ticket protocol of the fused 2D kernel - in the suite that runs
+where no GPU exists.  It is not a product path: libmufft_emu.so lives under tests/emu/_build, is
+loaded by this file only, and the twiddle tables it is fed come from the real library's host code.
+Kernels already verified on the GPU double as the check of the emulation itself.
+"""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cpu_libs
+
+EMU_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+IN_COMPLEX, IN_HALF, IN_C2R, IN_MUL, IN_MUL_C2R = 0, 1, 2, 3, 4
+OUT_COMPLEX, OUT_R2C, OUT_R2C_FULL = 0, 1, 2
+vp, sz = C.c_void_p, C.c_size_t
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run(["make", "-s", "-C", EMU_DIR, "-j", str(min(8, os.cpu_count() or 1))], check=True)
+    return C.CDLL(os.path.join(EMU_DIR, "_build", "libmufft_emu.so"), mode=os.RTLD_LOCAL)
+
+
+@pytest.fixture(scope="module")
+def host():
+    """Host-side helpers of the real library (pure CPU code): engine twiddle tables and the variant choice."""
+    import mufft_b200
+    lib = mufft_b200.lib
+    lib.mcu_engine_table_size.restype, lib.mcu_engine_table_size.argtypes = sz, [C.c_uint, C.c_int]
+    lib.mcu_engine_table_fill.restype, lib.mcu_engine_table_fill.argtypes = None, [vp, C.c_uint, C.c_int, C.c_int]
+    lib.mcu_rows_variant.restype, lib.mcu_rows_variant.argtypes = C.c_int, [C.c_uint, C.c_int, C.c_int]
+    return lib
+
+
+def engine_table(host, n, direction, variant=0):
+    entries = host.mcu_engine_table_size(n, variant)
+    assert entries > 0, f"no engine shape for n={n} variant={variant}"
+    table = np.zeros(max(entries, 1), np.complex64)
+    host.mcu_engine_table_fill(table.ctypes.data, n, direction, variant)
+    return table
+
+
+def resolve_twiddles(direction, n):
+    """(0 + i*dir) * exp(i*pi*dir*k/n), k < n, in double then rounded (mufft_host.c: make_resolve_twiddles, ref fft.c:441-455)."""
+    k = np.arange(n, dtype=np.float64)
+    c, s = np.cos(np.pi * direction * k / n).astype(np.float32), np.sin(np.pi * direction * k / n).astype(np.float32)
+    return (-np.float32(direction) * s + 1j * np.float32(direction) * c).astype(np.complex64)
+
+
+def rows(emu, host, n, direction, in_mode, out_mode, x, out_elems, in2=None, norm=1.0, rtw=None):
+    """Runs the emulated row kernel of complex length n on the rows of x; returns [batch][out_elems] complex."""
+    fn = getattr(emu, f"emu_rows_{n}")
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, sz, sz, sz, sz, C.c_float]
+    variant = host.mcu_rows_variant(n, in_mode, out_mode)
+    tw = engine_table(host, n, direction, variant)
+    x = np.ascontiguousarray(x, np.complex64)
+    batch = x.shape[0]
+    out = np.full((batch, out_elems), np.nan + 1j * np.nan, np.complex64)
+    rc = fn(direction, in_mode, out_mode, out.ctypes.data, x.ctypes.data, None if in2 is None else in2.ctypes.data,
+            tw.ctypes.data, None if rtw is None else rtw.ctypes.data, out_elems, x.shape[1], 0, batch, norm)
+    assert rc == 0, f"emu_rows_{n} returned {rc}"
+    return out
+
+
+def rnd(rng, *shape):
+    return rng.random(shape, np.float32) - np.float32(0.5)
+
+
+def crnd(rng, *shape):
+    return (rnd(rng, *shape) + 1j * rnd(rng, *shape)).astype(np.complex64)
+
+
+def tol(n):
+    return 1e-6 * math.log2(n)
+
+
+# 64: several transforms per CTA in sub-warp groups; 512: one warp per transform + mirrored shapes;
+# 2048 / 4096: CTA-wide exchanges, mirrored shapes; 16384: the 512-thread one-CTA-per-SM shape
+# (MCU_ENGINE_BIG_N) that has not run on a GPU yet.
+ROWS_SIZES = [64, 512, 2048, 4096, 16384]
+
+
+@pytest.mark.parametrize("n", ROWS_SIZES)
+@pytest.mark.parametrize("direction", [-1, 1])
+def test_rows_c2c(emu, host, oracle, n, direction):
+    rng = np.random.default_rng(n + direction)
+    batch = 3 if n <= 4096 else 2  # 3 leaves a partly filled CTA at n = 64
+    x = crnd(rng, batch, n)
+    got = rows(emu, host, n, direction, IN_COMPLEX, OUT_COMPLEX, x, n)
+    for b in range(batch):
+        assert cpu_libs.rel_l2(got[b], oracle.c2c(x[b], direction)) <= tol(n)
+
+
+@pytest.mark.parametrize("n", ROWS_SIZES)
+def test_rows_zero_padded(emu, host, oracle, n):
+    rng = np.random.default_rng(n)
+    x = crnd(rng, 2, n // 2)
+    got = rows(emu, host, n, -1, IN_HALF, OUT_COMPLEX, x, n)
+    for b in range(2):
+        assert cpu_libs.rel_l2(got[b], oracle.c2c(x[b], -1, cpu_libs.FLAG_ZERO_PAD, n=n)) <= tol(n)
+
+
+@pytest.mark.parametrize("n", ROWS_SIZES)
+@pytest.mark.parametrize("full", [False, True])
+def test_rows_r2c(emu, host, oracle, n, full):
+    """Real transform of 2n points on the complex engine of length n (mirrored last pass where the shape has one)."""
+    rng = np.random.default_rng(2 * n + full)
+    r = rnd(rng, 2, 2 * n)
+    elems = 2 * n if full else n + 1
+    got = rows(emu, host, n, -1, IN_COMPLEX, OUT_R2C_FULL if full else OUT_R2C, r.view(np.complex64), elems, rtw=resolve_twiddles(-1, n))
+    for b in range(2):
+        want = oracle.r2c(r[b], cpu_libs.FLAG_FULL_R2C if full else 0)
+        assert cpu_libs.rel_l2(got[b], want) <= tol(2 * n)
+
+
+@pytest.mark.parametrize("n", ROWS_SIZES)
+def test_rows_c2r(emu, host, oracle, n):
+    rng = np.random.default_rng(3 * n)
+    spec = np.stack([oracle.r2c(rnd(rng, 2 * n)) for _ in range(2)])  # [2][n+1]
+    got = rows(emu, host, n, 1, IN_C2R, OUT_COMPLEX, spec, n, rtw=resolve_twiddles(1, n))
+    for b in range(2):
+        assert cpu_libs.rel_l2(got[b].view(np.float32), oracle.c2r(spec[b], 2 * n)) <= tol(2 * n)
+
+
+@pytest.mark.parametrize("n", [512, 16384])
+def test_rows_spectral_multiply(emu, host, n):
+    """Load stage of mufft_execute_conv_output: norm * a .* b, then the inverse transform (ref kernel.c:22-34)."""
+    rng = np.random.default_rng(5 * n)
+    a, f = crnd(rng, 2, n), crnd(rng, n)
+    got = rows(emu, host, n, 1, IN_MUL, OUT_COMPLEX, a, n, in2=f, norm=1.0 / n)
+    want = np.fft.ifft(a.astype(np.complex128) * f.astype(np.complex128), axis=1)
+    for b in range(2):
+        assert cpu_libs.rel_l2(got[b], want[b]) <= tol(n)
+
+
+@pytest.mark.parametrize("ctas", [1, 3])
+@pytest.mark.parametrize("direction", [-1, 1])
+def test_fused_2d(emu, host, oracle, ctas, direction):
+    """The persistent fused 2D kernel with CTAs really running side by side: row tickets, lagged column
+    tickets, the rows-done counters and the deferred release (fft2d_kernel.cuh)."""
+    nx = ny = 256
+    batch = 3
+    fn = emu.emu_2d_fused_256x256
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, vp, vp, vp, vp, vp, sz, C.c_uint, C.c_uint]
+    rng = np.random.default_rng(11 + ctas)
+    x = crnd(rng, batch, ny, nx)
+    out = np.full((batch, ny, nx), np.nan, np.complex64)
+    counters = np.zeros(1 + batch, np.uint32)
+    tw = engine_table(host, 256, direction)
+    assert fn(direction, out.ctypes.data, x.ctypes.data, tw.ctypes.data, tw.ctypes.data, counters.ctypes.data, batch, 1, ctas) == 0
+    for b in range(batch):
+        assert cpu_libs.rel_l2(out[b], oracle.c2c_2d(x[b], direction)) <= tol(nx * ny)
+    assert list(counters[1:]) == [ny] * batch
