@@ -130,9 +130,12 @@ int mufft_execute_conv_output_partitioned_batch_async(mufft_plan_conv *plan, voi
  * prefetch into shared memory when the input rows are 16-byte aligned.  Same results either way. */
 void mufft_cuda_set_prefetch(int enable);
 /* 2D C2C transforms of 256..2048 points per side: 1 (default) = one persistent kernel does rows
- * and columns of the whole batch with the intermediate kept in L2, 0 = separate row and column
- * kernels per group of images (what every other 2D shape uses).  Same results either way. */
-void mufft_cuda_set_fused_2d(int enable);
+ * and columns of the whole batch with the intermediate kept in L2; 2 = the same scheme with every
+ * tile brought into shared memory by the TMA unit one tile ahead of the butterflies (bulk copy for
+ * row tiles, 2D tensor-map boxes for column tiles; opt-in until measured on the GPU); 0 = separate
+ * row and column kernels per group of images (what every other 2D shape uses).  Same results in
+ * all modes.  MUFFT_CUDA_FUSED_2D in the environment sets the initial value. */
+void mufft_cuda_set_fused_2d(int mode);
 /* Longest row transform done by ONE kernel, for plans created afterwards: 8192 (default) or 16384
  * (one 512-thread CTA per 16384-point transform, read once and written once, instead of the
  * two-kernel split; affects 1D plans of 16384 complex / 32768 real points and 2D plans with such

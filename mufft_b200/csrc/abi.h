@@ -131,6 +131,8 @@ typedef struct mcu_2d_args {
     unsigned nx, ny;
     int direction;
     unsigned lag;          /* column tickets run this many images behind the row tickets (set by the launcher) */
+    int tma;               /* 1 = tiles are brought into shared memory by bulk async copies one tile ahead
+                            * (fft2d_tma_kernel.cuh) when shape and alignment allow, 0 = direct loads */
 } mcu_2d_args;
 
 /* Generic one-pass Stockham kernel (any length; used beyond the engine limits). */

@@ -500,4 +500,59 @@ __device__ __forceinline__ void engine_run(cpx (&v)[engine_regs(N, V)], cpx *sm,
     }
 }
 
+// ---- exchange through HALF the shared memory: real and imaginary planes one after the other -----
+// The exchange area holds one float per element instead of a complex value, and every exchange
+// runs twice (scatter re, gather re, scatter im, gather im).  Same number of shared-memory
+// wavefronts (32-bit accesses move half the bytes per instruction), twice the barriers; what it buys
+// is room: kernels that also keep a bulk-copy landing buffer in shared memory (fft2d_tma_kernel.cuh)
+// stay at two CTAs per SM.  General shapes only (variant 0).
+template <int N, int PASS, int CS, int PLANE>
+__device__ __forceinline__ void engine_scatter_plane(const cpx (&v)[engine_regs(N, 0)], float *sm, int t)
+{
+    constexpr int R = engine_regs(N, 0);
+    constexpr int T = N / R;
+    constexpr int r = engine_radix(N, PASS, 0);
+    constexpr int p = engine_span(N, PASS, 0);
+    constexpr int NB = R / r;
+    constexpr int SH = engine_pad_shift(N, 0);
+#pragma unroll
+    for (int u = 0; u < NB; u++) {
+        const int i = t + u * T;
+        const int k = i & (p - 1);
+        const int base = (i - k) * r + k;
+#pragma unroll
+        for (int q = 0; q < r; q++) sm[pad_pos<SH>(base + q * p) * CS] = PLANE ? v[u + q * NB].y : v[u + q * NB].x;
+    }
+}
+template <int N, int CS, int PLANE>
+__device__ __forceinline__ void engine_gather_plane(cpx (&v)[engine_regs(N, 0)], const float *sm, int t)
+{
+    constexpr int R = engine_regs(N, 0);
+    constexpr int T = N / R;
+    constexpr int SH = engine_pad_shift(N, 0);
+#pragma unroll
+    for (int e = 0; e < R; e++) {
+        const float f = sm[pad_pos<SH>(t + e * T) * CS];
+        if constexpr (PLANE) v[e].y = f;
+        else v[e].x = f;
+    }
+}
+// As engine_run, with the split exchange; `sm` holds engine_smem_elems(N) * CS floats.
+template <int N, int DIR, int CS, int SYNC_T, int SLOTS, int PASS = 0, int PK = -1>
+__device__ __forceinline__ void engine_run_split(cpx (&v)[engine_regs(N, 0)], float *sm, const cpx *__restrict__ tw, int t, int slot)
+{
+    engine_butterflies<N, DIR, PASS, 0, PK>(v, tw, t);
+    if constexpr (PASS + 1 < engine_num_passes(N, 0)) {
+        if constexpr (PASS > 0) engine_sync<SYNC_T, SLOTS>(slot); // previous gather must be complete (WAR)
+        engine_scatter_plane<N, PASS, CS, 0>(v, sm, t);
+        engine_sync<SYNC_T, SLOTS>(slot);
+        engine_gather_plane<N, CS, 0>(v, sm, t);
+        engine_sync<SYNC_T, SLOTS>(slot);
+        engine_scatter_plane<N, PASS, CS, 1>(v, sm, t);
+        engine_sync<SYNC_T, SLOTS>(slot);
+        engine_gather_plane<N, CS, 1>(v, sm, t);
+        engine_run_split<N, DIR, CS, SYNC_T, SLOTS, PASS + 1, PK>(v, sm, tw, t, slot);
+    }
+}
+
 } // namespace mufft

@@ -75,6 +75,8 @@ __attribute__((constructor)) static void read_env(void)
     if (e != NULL) g_prefetch = e[0] == '1';
     e = getenv("MUFFT_CUDA_ONCHIP_LIMIT");
     if (e != NULL) g_onchip_limit = atoi(e) >= MCU_ENGINE_BIG_N ? MCU_ENGINE_BIG_N : MCU_ENGINE_MAX_N;
+    e = getenv("MUFFT_CUDA_FUSED_2D");
+    if (e != NULL) mufft_cuda_set_fused_2d(atoi(e));
     e = getenv("MUFFT_CUDA_L2_CHUNK_MB");
     if (e != NULL && atoi(e) >= 1 && atoi(e) <= 4096) g_l2_chunk_bytes = (size_t)atoi(e) << 20;
     e = getenv("MUFFT_CUDA_MID_GROUP_MB");
@@ -92,7 +94,7 @@ void mufft_cuda_set_two_kernel(int enable) { g_two_kernel = enable != 0; }
 /* 2D C2C: 1 (default) = the fused persistent kernel when the shape has one, 0 = row kernel +
  * column kernel per group of images (the path every other shape and R2C/C2R take). */
 static int g_fused_2d = 1;
-void mufft_cuda_set_fused_2d(int enable) { g_fused_2d = enable != 0; }
+void mufft_cuda_set_fused_2d(int mode) { g_fused_2d = mode <= 0 ? 0 : (mode >= 2 ? 2 : 1); }
 
 /* ---- per-thread state --------------------------------------------------------------------- */
 static __thread void *tls_stream = NULL;
@@ -1264,6 +1266,7 @@ static int run_2d_device(mufft_plan_2d *plan, void *out, const void *in, size_t 
         f.out = out; f.in = in; f.tw_x = plan->ax_x.d_engine_tw; f.tw_y = plan->ax_y.d_engine_tw;
         f.counters = plan->d_counters; f.out_image = (size_t)nx * ny; f.in_image = (size_t)nx * ny;
         f.batch = images; f.nx = nx; f.ny = ny; f.direction = plan->ax_x.direction;
+        f.tma = g_fused_2d == 2;
         return mcu_launch_2d_fused(&f, stream);
     }
     const int real_rows = plan->kind != KIND_C2C;

@@ -161,3 +161,32 @@ def test_fused_2d(emu, host, oracle, ctas, direction):
     for b in range(batch):
         assert cpu_libs.rel_l2(out[b], oracle.c2c_2d(x[b], direction)) <= tol(nx * ny)
     assert list(counters[1:]) == [ny] * batch
+
+
+@pytest.mark.parametrize("nx,ny,batch,ctas,lag", [
+    (256, 256, 3, 1, 1),    # one CTA walks every ticket alone
+    (256, 256, 4, 3, 1),    # CTAs side by side, column tiles right behind their rows (deferred-copy path gets exercised)
+    (256, 256, 2, 5, 2),    # lag >= batch: all rows first
+    (512, 256, 2, 2, 1),    # rectangular: different row / column tile shapes, named barriers for the rows
+    (1024, 1024, 2, 2, 1),  # the BASELINE configs[3] image shape: 64 KiB tiles, four tensor boxes per column tile
+])
+@pytest.mark.parametrize("direction", [-1, 1])
+def test_fused_2d_tma(emu, host, oracle, nx, ny, batch, ctas, lag, direction):
+    """fft2d_tma_kernel.cuh: tiles land in shared memory through (emulated) bulk copies one tile ahead
+    of the butterflies, exchanges run plane by plane in a half-size area."""
+    if nx == 1024 and direction == 1:
+        pytest.skip("one direction is enough at the large shape")
+    fn = getattr(emu, f"emu_2d_tma_{nx}x{ny}")
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, vp, vp, vp, vp, vp, sz, C.c_uint, C.c_uint]
+    rng = np.random.default_rng(nx + ny + batch + ctas)
+    x = crnd(rng, batch, ny, nx)
+    out = np.full((batch, ny, nx), np.nan, np.complex64)
+    counters = np.zeros(1 + batch, np.uint32)
+    assert fn(direction, out.ctypes.data, x.ctypes.data, engine_table(host, nx, direction).ctypes.data,
+              engine_table(host, ny, direction).ctypes.data, counters.ctypes.data, batch, lag, ctas) == 0
+    want = np.fft.fft2(x.astype(np.complex128)) if direction < 0 else np.fft.ifft2(x.astype(np.complex128), norm="forward")
+    for b in range(batch):
+        assert cpu_libs.rel_l2(out[b], want[b]) <= tol(nx * ny)
+    assert cpu_libs.rel_l2(out[0], oracle.c2c_2d(x[0], direction)) <= tol(nx * ny)
+    assert list(counters[1:]) == [ny] * batch
