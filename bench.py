@@ -76,8 +76,8 @@ DESCRIPTION = {
                       "conv_input per block + one partitioned conv_output (8 spectral products summed in front of one inverse FFT)",
     "c2c2d1024": "batched 2D C2C 1024x1024, batch 256 per GPU (BASELINE configs[3])",
     "c2c64": "batched 1D C2C forward N=64, batch 2^24 per GPU (batched form of BASELINE configs[0])",
-    "c2c16384": "batched 1D C2C forward N=16384, batch 32768 per GPU (first length on the two-kernel split)",
-    "c2c32768": "batched 1D C2C forward N=32768, batch 16384 per GPU (row length of BASELINE configs[4])",
+    "c2c16384": "batched 1D C2C forward N=16384, batch 32768 per GPU (longest single-kernel length: one 512-thread CTA per transform)",
+    "c2c32768": "batched 1D C2C forward N=32768, batch 16384 per GPU (first length on the two-kernel split; row length of BASELINE configs[4])",
     "c2c256": "batched 1D C2C forward N=256, batch 2^22 per GPU",
     "c2c1024": "batched 1D C2C forward N=1024, batch 2^20 per GPU",
     "c2c2048": "batched 1D C2C forward N=2048, batch 2^19 per GPU",
@@ -562,7 +562,7 @@ def main():
     ap.add_argument("--units", type=int, default=0, help="override units per GPU (debug; invalidates the headline)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--also", default="r2c4096,c2r4096,conv8192,conv8192_fused,c2c2d1024,c2c64",
+    ap.add_argument("--also", default="r2c4096,c2r4096,conv8192,conv8192_fused,c2c2d1024,c2c64,c2c16384",
                     help="comma separated extra workloads reported under 'also' (N=1 only); '' disables")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -119,8 +119,8 @@ int mufft_execute_conv_batch_async(mufft_plan_conv *plan, void *output, const vo
  * (mufft_execute_conv_input(plan, MUFFT_CONV_BLOCK_SECOND, ..) of taps [p*L, (p+1)*L)), the same
  * distance apart.  Outputs as mufft_execute_conv_output writes them, tightly packed; the caller
  * overlap-adds consecutive output blocks exactly as with a one-block filter.  Device-accessible
- * (device or managed) memory only; the transform must fit the on-chip engine (stereo N <= 8192,
- * mono N <= 16384), otherwise nonzero is returned. */
+ * (device or managed) memory only; the transform must fit the on-chip engine (stereo N <= 16384,
+ * mono N <= 32768 with the default mufft_cuda_set_onchip_limit), otherwise nonzero is returned. */
 int mufft_execute_conv_output_partitioned_batch(mufft_plan_conv *plan, void *output, const void *spectra,
                                                 const void *filter_spectra, unsigned parts, size_t batch);
 int mufft_execute_conv_output_partitioned_batch_async(mufft_plan_conv *plan, void *output, const void *spectra,
@@ -129,21 +129,27 @@ int mufft_execute_conv_output_partitioned_batch_async(mufft_plan_conv *plan, voi
 /* Row-transform kernel flavour: 0 = direct loads (default), 1 = persistent CTAs with bulk-copy
  * prefetch into shared memory when the input rows are 16-byte aligned.  Same results either way. */
 void mufft_cuda_set_prefetch(int enable);
-/* 2D C2C transforms of 256..2048 points per side: 1 (default) = one persistent kernel does rows
- * and columns of the whole batch with the intermediate kept in L2; 2 = the same scheme with every
- * tile brought into shared memory by the TMA unit one tile ahead of the butterflies (bulk copy for
- * row tiles, 2D tensor-map boxes for column tiles; opt-in until measured on the GPU); 0 = separate
- * row and column kernels per group of images (what every other 2D shape uses).  Same results in
- * all modes.  MUFFT_CUDA_FUSED_2D in the environment sets the initial value. */
+/* 2D C2C transforms of 256..2048 points per side.
+ *   1 (default)  one persistent kernel does rows and columns of the whole batch with the intermediate
+ *                kept in L2, in the flavour measured fastest for the shape;
+ *   0            separate row and column kernels per group of images (what every other 2D shape uses);
+ *   2..8         that kernel in one fixed flavour, for measurements and tests: 8 plain; 7 one-sided
+ *                (release / acquire) fences in the ticket protocol; 3 = 7 + twiddle tables staged in
+ *                shared memory; 6 = 7 + only the power-of-two twiddles loaded, the rest derived;
+ *                5 = 3 + 6; 2 / 4 = tiles brought into shared memory by the TMA unit one tile ahead
+ *                (bulk copy for row tiles, 2D tensor-map boxes for column tiles), plain / as 3 -
+ *                measured slower than direct loads on B200, kept as an experiment.
+ * Same results (within rounding of the derived twiddles) in all modes.  MUFFT_CUDA_FUSED_2D in the
+ * environment sets the initial value. */
 void mufft_cuda_set_fused_2d(int mode);
-/* Longest row transform done by ONE kernel, for plans created afterwards: 8192 (default) or 16384
- * (one 512-thread CTA per 16384-point transform, read once and written once, instead of the
- * two-kernel split; affects 1D plans of 16384 complex / 32768 real points and 2D plans with such
- * rows).  Other values are rounded down to one of the two.  Same results either way.
- * MUFFT_CUDA_ONCHIP_LIMIT in the environment sets the initial value. */
+/* Longest row transform done by ONE kernel, for plans created afterwards: 16384 (default: one
+ * 512-thread CTA per 16384-point transform, read once and written once) or 8192 (16384 points take
+ * the two-kernel split; measured 1.8x slower, kept for comparison).  Affects 1D plans of 16384
+ * complex / 32768 real points and 2D plans with such rows.  Other values are rounded down to one of
+ * the two.  Same results either way.  MUFFT_CUDA_ONCHIP_LIMIT in the environment sets the initial value. */
 void mufft_cuda_set_onchip_limit(unsigned n);
 unsigned mufft_cuda_get_onchip_limit(void);
-/* Transform lengths 16384 .. 2097152: 1 (default) = two kernels (N = N1*N2: column transforms, then
+/* Transform lengths beyond the single-kernel limit, up to 2097152: 1 (default) = two kernels (N = N1*N2: column transforms, then
  * twiddle + row transforms with a transposed store), 0 = one generic radix pass per kernel. */
 void mufft_cuda_set_two_kernel(int enable);
 

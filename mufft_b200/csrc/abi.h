@@ -14,8 +14,9 @@ extern "C" {
 /* Largest transform length handled by the single-kernel shared-memory engine. */
 #define MCU_ENGINE_MAX_N 8192
 /* Row kernels are also built for this length (one 512-thread CTA per transform, one CTA per SM);
- * the host layer uses them instead of the two-kernel split only when asked to
- * (mufft_cuda_set_onchip_limit / MUFFT_CUDA_ONCHIP_LIMIT), until the choice has been measured. */
+ * the host layer prefers them to the two-kernel split unless told otherwise
+ * (mufft_cuda_set_onchip_limit / MUFFT_CUDA_ONCHIP_LIMIT).  Convolution in one kernel and the column
+ * kernels stop at MCU_ENGINE_MAX_N / MCU_COLS_MAX_N. */
 #define MCU_ENGINE_BIG_N 16384
 /* Largest column length handled by the shared-memory column kernel. */
 #define MCU_COLS_MAX_N 2048
@@ -133,6 +134,9 @@ typedef struct mcu_2d_args {
     unsigned lag;          /* column tickets run this many images behind the row tickets (set by the launcher) */
     int tma;               /* 1 = tiles are brought into shared memory by bulk async copies one tile ahead
                             * (fft2d_tma_kernel.cuh) when shape and alignment allow, 0 = direct loads */
+    int flags;             /* kernel flavour, F2D_* bits of fft2d_kernel.cuh: 1 twiddle tables in shared memory,
+                            * 2 one-sided fences, 4 derived twiddles (the TMA kernel knows 0 and 3 only);
+                            * -1 = the launcher's measured choice for the shape */
 } mcu_2d_args;
 
 /* Generic one-pass Stockham kernel (any length; used beyond the engine limits). */

@@ -6,6 +6,7 @@
 //                            (ref kernel.c:22-82); also backs mufft_get_convolve_func().
 #include "abi.h"
 #include "fft_engine.cuh"
+#include "rows_kernel.cuh"
 
 #include <atomic>
 #include <math.h>
@@ -253,11 +254,10 @@ int mcu_prefetch(const void *ptr, size_t bytes, int to_device, void *stream)
 // ---- engine twiddle tables (see fill_table above) --------------------------------------------
 int mcu_rows_variant(unsigned n, int in_mode, int out_mode)
 {
-    const bool r2c = out_mode == MCU_OUT_R2C || out_mode == MCU_OUT_R2C_FULL;
-    const bool c2r = in_mode == MCU_IN_C2R || in_mode == MCU_IN_MUL_C2R;
+    // the kernels' own choice (rows_kernel.cuh), so that the table handed to a kernel is always the
+    // one of the shape it was compiled for
     switch (n) {
-#define X(v) case v: return r2c && engine_variant_exists(v, MUFFT_VARIANT_MIRROR_LAST) ? MUFFT_VARIANT_MIRROR_LAST \
-                          : (c2r && engine_variant_exists(v, MUFFT_VARIANT_MIRROR_FIRST) ? MUFFT_VARIANT_MIRROR_FIRST : MUFFT_VARIANT_GENERAL);
+#define X(v) case v: return rows_variant(v, in_mode, out_mode);
         MUFFT_FOR_ENGINE_SIZES(X)
 #undef X
     default: return 0;

@@ -32,7 +32,7 @@ static tensor_map_encode_fn tensor_map_encoder()
 
 // TMA-fed variant (fft2d_tma_kernel.cuh).  Returns cudaErrorNotSupported when shape, alignment or
 // driver rule it out; the caller then takes the direct-load kernel.
-template <int DIR>
+template <int DIR, bool LITE>
 static cudaError_t launch_tma(const mcu_2d_args &a, cudaStream_t stream)
 {
   if constexpr (!f2t_supported(F2D_NX, F2D_NY)) {
@@ -46,9 +46,9 @@ static cudaError_t launch_tma(const mcu_2d_args &a, cudaStream_t stream)
     tensor_map_encode_fn encode = tensor_map_encoder();
     if (encode == nullptr) return cudaErrorNotSupported;
 
-    static int ctas = 0; // per direction
-    auto kernel = fft2d_tma_kernel<F2D_NX, F2D_NY, DIR>;
-    constexpr size_t smem = f2t_smem_bytes(F2D_NX, F2D_NY);
+    static int ctas = 0; // per instantiation
+    auto kernel = fft2d_tma_kernel<F2D_NX, F2D_NY, DIR, LITE>;
+    constexpr size_t smem = f2t_smem_bytes(F2D_NX, F2D_NY, LITE);
     if (ctas == 0) {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
@@ -86,7 +86,7 @@ static cudaError_t launch_tma(const mcu_2d_args &a, cudaStream_t stream)
 
 // Shapes the fused kernel cannot take with the configured CTA size report "unsupported" to the
 // host layer (which then uses the row kernel + column kernel path) instead of failing the build.
-template <int DIR>
+template <int DIR, int FLAGS>
 static cudaError_t launch_dir(const mcu_2d_args &a, cudaStream_t stream)
 {
   if constexpr (!f2d_supported(F2D_NX, F2D_NY)) {
@@ -94,12 +94,12 @@ static cudaError_t launch_dir(const mcu_2d_args &a, cudaStream_t stream)
     return cudaErrorInvalidValue;
   } else {
     if (a.tma) {
-        const cudaError_t err = launch_tma<DIR>(a, stream);
+        const cudaError_t err = launch_tma<DIR, FLAGS == F2D_LITE>(a, stream);
         if (err != cudaErrorNotSupported) return err;
     }
-    static int ctas = 0; // per direction
-    auto kernel = fft2d_fused_kernel<F2D_NX, F2D_NY, DIR>;
-    constexpr size_t smem = f2d_smem_bytes(F2D_NX, F2D_NY);
+    static int ctas = 0; // per instantiation
+    auto kernel = fft2d_fused_kernel<F2D_NX, F2D_NY, DIR, FLAGS>;
+    constexpr size_t smem = f2d_smem_bytes(F2D_NX, F2D_NY, (FLAGS & F2D_SMEM_TW) != 0);
     if (ctas == 0) {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
@@ -129,7 +129,20 @@ bool MUFFT_CAT4(f2d_supported_, F2D_NX, x, F2D_NY)() { return f2d_supported(F2D_
 
 cudaError_t MUFFT_CAT4(f2d_launch_, F2D_NX, x, F2D_NY)(const mcu_2d_args &a, cudaStream_t stream)
 {
-    return a.direction < 0 ? launch_dir<-1>(a, stream) : launch_dir<1>(a, stream);
+    // Measured on B200 over all 16 shapes (profiles/README.md, round-1 flavour table): one-sided fences
+    // + derived twiddles is the best or within 1.5 % of the best flavour everywhere except 1024 x 1024
+    // (BASELINE configs[3]), where the twiddle tables in shared memory win: 1.279 ms plain, 1.194 / 1.209.
+    const int flags = a.flags >= 0 ? a.flags : (F2D_NX == 1024 && F2D_NY == 1024 ? F2D_LITE : (F2D_ONE_SIDED | F2D_DERIVE));
+    switch (flags) {
+#define MUFFT_F2D_FLAVOUR(f) case f: return a.direction < 0 ? launch_dir<-1, f>(a, stream) : launch_dir<1, f>(a, stream);
+        MUFFT_F2D_FLAVOUR(0)
+        MUFFT_F2D_FLAVOUR(F2D_ONE_SIDED)
+        MUFFT_F2D_FLAVOUR(F2D_LITE)
+        MUFFT_F2D_FLAVOUR(F2D_ONE_SIDED | F2D_DERIVE)
+        MUFFT_F2D_FLAVOUR(F2D_LITE | F2D_DERIVE)
+#undef MUFFT_F2D_FLAVOUR
+    default: return cudaErrorInvalidValue;
+    }
 }
 
 } // namespace mufft

@@ -48,11 +48,15 @@ __host__ __device__ constexpr bool f2d_supported(int nx, int ny)
            engine_threads(ny) * 4 <= MUFFT_F2D_THREADS && (engine_threads(nx) <= 32 || f2d_rows_per_tile(nx) <= 15) &&
            ny % (f2d_rows_per_tile(nx) * f2d_row_repeat(nx, ny)) == 0 && nx % f2d_cols_per_tile(ny) == 0;
 }
-__host__ __device__ constexpr size_t f2d_smem_bytes(int nx, int ny)
+__host__ __device__ constexpr size_t f2d_xch_elems(int nx, int ny)
 {
     size_t r = (size_t)f2d_rows_per_tile(nx) * engine_smem_elems(nx);
     size_t c = (size_t)f2d_cols_per_tile(ny) * engine_smem_elems(ny);
-    return (r > c ? r : c) * sizeof(float2) + 16;
+    return r > c ? r : c;
+}
+__host__ __device__ constexpr size_t f2d_smem_bytes(int nx, int ny, bool lite = false)
+{
+    return f2d_xch_elems(nx, ny) * sizeof(float2) + 16 + (lite ? (size_t)(engine_tw_total(nx) + (nx != ny ? engine_tw_total(ny) : 0)) * sizeof(float2) : 0);
 }
 
 // Polling load (no L1 invalidation per iteration; the acquire fence follows once, after success).
@@ -92,6 +96,48 @@ __device__ __forceinline__ void fence_acq_rel_gpu()
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
 #endif
 }
+// One-sided fences.  fence.acq_rel.gpu is MEMBAR.ALL.GPU + CCTL.IVALL in SASS: the second half throws
+// away the SM's whole L1 - twiddle tables included - which a RELEASE does not need, and the first
+// half waits for this thread's outstanding writes, which an ACQUIRE does not need.
+__device__ __forceinline__ void fence_release_gpu()
+{
+#ifdef MUFFT_EMU
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+#else
+    asm volatile("fence.release.gpu;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void fence_acquire_gpu()
+{
+#ifdef MUFFT_EMU
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+#else
+    asm volatile("fence.acquire.gpu;" ::: "memory");
+#endif
+}
+// LITE kernels: one-sided fences and twiddle tables in shared memory (see fft2d_fused_kernel).
+template <bool LITE>
+__device__ __forceinline__ void f2d_fence_release()
+{
+    if constexpr (LITE) fence_release_gpu();
+    else fence_acq_rel_gpu();
+}
+template <bool LITE>
+__device__ __forceinline__ void f2d_fence_acquire()
+{
+    if constexpr (LITE) fence_acquire_gpu();
+    else fence_acq_rel_gpu();
+}
+// Twiddle tables of both axes in shared memory (one table when the sides are equal), in cpx.
+__host__ __device__ constexpr int f2d_tw_elems(int nx, int ny) { return engine_tw_total(nx) + (nx != ny ? engine_tw_total(ny) : 0); }
+// Copies them behind `dst`; the caller's next CTA barrier publishes them.
+template <int NX, int NY>
+__device__ __forceinline__ void f2d_stage_twiddles(cpx *dst, const cpx *__restrict__ twx, const cpx *__restrict__ twy, int tid, int threads)
+{
+    for (int i = tid; i < engine_tw_total(NX); i += threads) dst[i] = __ldg(twx + i);
+    if constexpr (NX != NY)
+        for (int i = tid; i < engine_tw_total(NY); i += threads) dst[engine_tw_total(NX) + i] = __ldg(twy + i);
+}
 // Pull `bytes` (a multiple of 16, 16-byte aligned) into L2 ahead of use.
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
 {
@@ -102,7 +148,19 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
 #endif
 }
 
-template <int NX, int NY, int DIR>
+// FLAGS (kernel flavours, chosen per shape by the launcher from measurements):
+//   F2D_SMEM_TW    twiddle tables staged in shared memory once per CTA.  ncu on the plain kernel
+//                  (profiles/r01c_c2c2d1024_full.txt) shows the twiddle loads missing L1 more often
+//                  than not - every fence.acq_rel.gpu of the ticket protocol invalidates it - so that
+//                  they pull as many sectors from L2 as a whole pass over the data;
+//   F2D_ONE_SIDED  release / acquire fences instead of fence.acq_rel.gpu in the ticket protocol;
+//   F2D_DERIVE     only the power-of-two twiddles are loaded, the rest derived (MUFFT_TW_DERIVE).
+#define F2D_SMEM_TW 1
+#define F2D_ONE_SIDED 2
+#define F2D_DERIVE 4
+#define F2D_LITE (F2D_SMEM_TW | F2D_ONE_SIDED)
+__host__ __device__ constexpr int f2d_twm(int flags) { return ((flags & F2D_SMEM_TW) ? MUFFT_TW_SMEM : 0) | ((flags & F2D_DERIVE) ? MUFFT_TW_DERIVE : 0); }
+template <int NX, int NY, int DIR, int FLAGS = 0>
 __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d_fused_kernel(const mcu_2d_args a)
 {
     constexpr int RX = engine_regs(NX), TX = NX / RX, ROWS = f2d_rows_per_tile(NX);
@@ -118,6 +176,13 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d
     const int tid = threadIdx.x;
     const cpx *__restrict__ twx = static_cast<const cpx *>(a.tw_x);
     const cpx *__restrict__ twy = static_cast<const cpx *>(a.tw_y);
+    constexpr bool LITE = (FLAGS & F2D_ONE_SIDED) != 0; // fences
+    if constexpr ((FLAGS & F2D_SMEM_TW) != 0) {
+        cpx *tws = smem + f2d_xch_elems(NX, NY) + 2; // behind the exchange area (+16 bytes)
+        f2d_stage_twiddles<NX, NY>(tws, twx, twy, tid, MUFFT_F2D_THREADS);
+        twx = tws;
+        twy = NX != NY ? tws + engine_tw_total(NX) : tws;
+    }
     unsigned *ticket_counter = a.counters;
     unsigned *rows_done = a.counters + 1;
     const unsigned long long total = (unsigned long long)a.batch * (NR + NC);
@@ -153,7 +218,7 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d
     unsigned pending = ~0u; // thread 0 only
     auto release_pending = [&]() {
         if (pending != ~0u) {
-            fence_acq_rel_gpu();
+            f2d_fence_release<LITE>();
             red_relaxed_add(rows_done + pending, (unsigned)(ROWS * REP));
             pending = ~0u;
         }
@@ -178,7 +243,7 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d
                 if (pending != ~0u) wait = 1;
                 else wait_rows(image);
             }
-            fence_acq_rel_gpu();
+            f2d_fence_acquire<LITE>();
         }
         s_ticket[slot] = k;
         s_wait[slot] = wait;
@@ -199,7 +264,7 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d
                 decode(k, image, tile);
                 release_pending();
                 wait_rows(image);
-                fence_acq_rel_gpu();
+                f2d_fence_acquire<LITE>();
             }
             __syncthreads();
         }
@@ -234,7 +299,7 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d
 #pragma unroll
                 for (int e = 0; e < RX; e++) v[e] = __ldcs(in + t + e * TX); // streamed: read once
                 if (rep == 0 && tid == 0) release_pending(); // the previous row ticket, while this one's loads fly
-                engine_run<NX, DIR, 1, TX, ROWS>(v, smem + slot * engine_smem_elems(NX), twx, t, slot);
+                engine_run<NX, DIR, 1, TX, ROWS, 0, 0, -1, f2d_twm(FLAGS)>(v, smem + slot * engine_smem_elems(NX), twx, t, slot);
                 cpx *__restrict__ o = out + row * NX;
 #pragma unroll
                 for (int e = 0; e < RX; e++) o[t + e * TX] = v[e];
@@ -248,7 +313,7 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d
 #pragma unroll
             for (int e = 0; e < RY; e++) v[e] = __ldcg(col + (size_t)(t + e * TY) * NX); // written by other SMs: L2 only
             if (tid == 0) release_pending();
-            engine_run<NY, DIR, COLS, MUFFT_F2D_THREADS, 1>(v, smem + c, twy, t, 0);
+            engine_run<NY, DIR, COLS, MUFFT_F2D_THREADS, 1, 0, 0, -1, f2d_twm(FLAGS)>(v, smem + c, twy, t, 0);
 #pragma unroll
             for (int e = 0; e < RY; e++) __stcs(col + (size_t)(t + e * TY) * NX, v[e]);
         }

@@ -41,19 +41,23 @@ __host__ __device__ constexpr size_t f2t_xch_floats(int nx, int ny)
     size_t r = (size_t)f2d_rows_per_tile(nx) * engine_smem_elems(nx), c = (size_t)f2d_cols_per_tile(ny) * engine_smem_elems(ny);
     return r > c ? r : c;
 }
-// [mbarrier, padded to 128 bytes][landing buffer][exchange area, floats]
-__host__ __device__ constexpr size_t f2t_smem_bytes(int nx, int ny) { return 128 + f2t_land_bytes(nx, ny) + f2t_xch_floats(nx, ny) * sizeof(float); }
+// [mbarrier, padded to 128 bytes][landing buffer][exchange area, floats][LITE: twiddle tables]
+__host__ __device__ constexpr size_t f2t_smem_bytes(int nx, int ny, bool lite = false)
+{
+    return 128 + f2t_land_bytes(nx, ny) + ((f2t_xch_floats(nx, ny) + 1) & ~(size_t)1) * sizeof(float) + (lite ? (size_t)f2d_tw_elems(nx, ny) * sizeof(float2) : 0);
+}
 __host__ __device__ constexpr bool f2t_supported(int nx, int ny)
 {
     return f2d_supported(nx, ny) && f2d_row_repeat(nx, ny) == 1 && ny % f2t_box_rows(ny) == 0 &&
-           f2d_cols_per_tile(ny) * sizeof(float2) >= 16 && f2t_smem_bytes(nx, ny) <= 227 * 1024 &&
+           f2d_cols_per_tile(ny) * sizeof(float2) >= 16 && f2t_smem_bytes(nx, ny, true) <= 227 * 1024 &&
            (size_t)f2d_rows_per_tile(nx) * nx * sizeof(float2) < (1u << 20) && (size_t)f2d_cols_per_tile(ny) * ny * sizeof(float2) < (1u << 20);
 }
 
 // `tmap`: the OUTPUT buffer as a row-major [batch * NY][NX] array of 8-byte elements, box
 // f2d_cols_per_tile(NY) x f2t_box_rows(NY).  Requirements checked by the launcher: input images
 // 16-byte aligned, images tightly packed in the output.
-template <int NX, int NY, int DIR>
+// LITE: as in fft2d_fused_kernel - twiddle tables in shared memory, one-sided fences.
+template <int NX, int NY, int DIR, bool LITE = false>
 __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS)
 fft2d_tma_kernel(const mcu_2d_args a, const MUFFT_GRID_CONSTANT tensor_map_t tmap)
 {
@@ -74,6 +78,12 @@ fft2d_tma_kernel(const mcu_2d_args a, const MUFFT_GRID_CONSTANT tensor_map_t tma
     const int tid = threadIdx.x;
     const cpx *__restrict__ twx = static_cast<const cpx *>(a.tw_x);
     const cpx *__restrict__ twy = static_cast<const cpx *>(a.tw_y);
+    if constexpr (LITE) {
+        cpx *tws = reinterpret_cast<cpx *>(xch + ((f2t_xch_floats(NX, NY) + 1) & ~(size_t)1));
+        f2d_stage_twiddles<NX, NY>(tws, twx, twy, tid, MUFFT_F2D_THREADS);
+        twx = tws;
+        twy = NX != NY ? tws + engine_tw_total(NX) : tws;
+    }
     unsigned *ticket_counter = a.counters;
     unsigned *rows_done = a.counters + 1;
     const unsigned long long total = (unsigned long long)a.batch * (NR + NC);
@@ -102,7 +112,7 @@ fft2d_tma_kernel(const mcu_2d_args a, const MUFFT_GRID_CONSTANT tensor_map_t tma
     unsigned pending = ~0u;
     auto release_pending = [&]() {
         if (pending != ~0u) {
-            fence_acq_rel_gpu();
+            f2d_fence_release<LITE>();
             red_relaxed_add(rows_done + pending, (unsigned)ROWS);
             pending = ~0u;
         }
@@ -143,7 +153,7 @@ fft2d_tma_kernel(const mcu_2d_args a, const MUFFT_GRID_CONSTANT tensor_map_t tma
             unsigned image, tile;
             if (!decode(k0, image, tile)) {
                 wait_rows(image); // nothing of ours is pending: every wait is on tickets already running elsewhere
-                fence_acq_rel_gpu();
+                f2d_fence_acquire<LITE>();
             }
             issue(k0);
         }
@@ -166,7 +176,7 @@ fft2d_tma_kernel(const mcu_2d_args a, const MUFFT_GRID_CONSTANT tensor_map_t tma
             // so its copy has not been started.  Everything this CTA stored is covered by (A).
             release_pending();
             wait_rows(image);
-            fence_acq_rel_gpu();
+            f2d_fence_acquire<LITE>();
             issue(k);
         }
         tma_mbar_wait(full, parity);
@@ -187,7 +197,7 @@ fft2d_tma_kernel(const mcu_2d_args a, const MUFFT_GRID_CONSTANT tensor_map_t tma
                 if (kn < total) {
                     if (!decode(kn, image2, tile2)) {
                         if (ld_relaxed(rows_done + image2) < (unsigned)NY) wait = 1;
-                        else fence_acq_rel_gpu();
+                        else f2d_fence_acquire<LITE>();
                     }
                     if (!wait) issue(kn);
                 }
@@ -195,7 +205,7 @@ fft2d_tma_kernel(const mcu_2d_args a, const MUFFT_GRID_CONSTANT tensor_map_t tma
                 s_wait[(it + 1) & 1] = wait;
                 next_ticket = atomicAdd(ticket_counter, 1u);
             }
-            engine_run_split<NX, DIR, 1, TX, ROWS>(v, xch + slot * engine_smem_elems(NX), twx, t, slot);
+            engine_run_split<NX, DIR, 1, TX, ROWS, 0, -1, LITE>(v, xch + slot * engine_smem_elems(NX), twx, t, slot);
             cpx *__restrict__ o = out + ((size_t)tile * ROWS + slot) * NX;
 #pragma unroll
             for (int e = 0; e < RX; e++) o[t + e * TX] = v[e];
@@ -214,7 +224,7 @@ fft2d_tma_kernel(const mcu_2d_args a, const MUFFT_GRID_CONSTANT tensor_map_t tma
                 if (kn < total) {
                     if (!decode(kn, image2, tile2)) {
                         if (ld_relaxed(rows_done + image2) < (unsigned)NY) wait = 1;
-                        else fence_acq_rel_gpu();
+                        else f2d_fence_acquire<LITE>();
                     }
                     if (!wait) issue(kn);
                 }
@@ -222,7 +232,7 @@ fft2d_tma_kernel(const mcu_2d_args a, const MUFFT_GRID_CONSTANT tensor_map_t tma
                 s_wait[(it + 1) & 1] = wait;
                 next_ticket = atomicAdd(ticket_counter, 1u);
             }
-            engine_run_split<NY, DIR, COLS, MUFFT_F2D_THREADS, 1>(v, xch + c, twy, t, 0);
+            engine_run_split<NY, DIR, COLS, MUFFT_F2D_THREADS, 1, 0, -1, LITE>(v, xch + c, twy, t, 0);
             cpx *__restrict__ col = out + (size_t)tile * COLS + c;
 #pragma unroll
             for (int e = 0; e < RY; e++) __stcs(col + (size_t)(t + e * TY) * NX, v[e]);

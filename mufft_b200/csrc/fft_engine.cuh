@@ -402,7 +402,34 @@ __device__ __forceinline__ int engine_bfly(int t, int u)
 // v[u + q*NB] (q < r).  `tw` points at the engine twiddle table of this transform length.
 // PK: -1 = the shape's packed flag, 0 / 1 = the caller's choice (kernels whose prologue or epilogue
 // changes the register pressure measure differently from the plain transform of the same shape).
-template <int N, int DIR, int PASS, int V = 0, int PK = -1>
+// Twiddle handling of a pass (TWM, a bit mask):
+//   MUFFT_TW_SMEM    `tw` points into SHARED memory (plain loads) instead of global memory (read-only
+//                    cache loads);
+//   MUFFT_TW_DERIVE  radix >= 8: only the log2(r) power-of-two entries w^(k 2^j) are loaded, the other
+//                    r-1-log2(r) twiddles are products of them (at most log2(r)-1 multiplications deep).
+//                    26 loads less and 26 complex multiplications more per radix-32 butterfly: for
+//                    kernels bound by the load/store pipe, not for those bound by instruction issue.
+#define MUFFT_TW_SMEM 1
+#define MUFFT_TW_DERIVE 2
+__host__ __device__ constexpr int ilog2(int r) { int s = 0; while ((1 << s) < r) s++; return s; }
+
+// x[IDX + j] *= cur * (product of b[l] over the set bits l <= LEVEL of j), for every j below 2^(LEVEL+1):
+// a depth-first walk over the bits of the twiddle exponent, one live product per level.
+template <int R, int LG, int LEVEL, int IDX, bool ONE>
+struct TwTree {
+    static __device__ __forceinline__ void run(cpx (&x)[R], const cpx (&b)[LG], cpx cur)
+    {
+        if constexpr (LEVEL < 0) {
+            if constexpr (!ONE) x[IDX] = cmul(x[IDX], cur);
+        } else {
+            TwTree<R, LG, LEVEL - 1, IDX, ONE>::run(x, b, cur);
+            if constexpr (ONE) TwTree<R, LG, LEVEL - 1, IDX + (1 << LEVEL), false>::run(x, b, b[LEVEL]);
+            else TwTree<R, LG, LEVEL - 1, IDX + (1 << LEVEL), false>::run(x, b, cmul(cur, b[LEVEL]));
+        }
+    }
+};
+
+template <int N, int DIR, int PASS, int V = 0, int PK = -1, int TWM = 0>
 __device__ __forceinline__ void engine_butterflies(cpx (&v)[engine_regs(N, V)], const cpx *__restrict__ tw, int t)
 {
     constexpr int R = engine_regs(N, V);
@@ -418,8 +445,22 @@ __device__ __forceinline__ void engine_butterflies(cpx (&v)[engine_regs(N, V)], 
         if constexpr (PASS > 0) {
             const int k = engine_bfly<N, PASS, V>(t, u) & (p - 1);
             const cpx *w = tw + engine_tw_offset(N, PASS, V) + k;
+            if constexpr ((TWM & MUFFT_TW_DERIVE) != 0 && r >= 8) {
+                constexpr int LG = ilog2(r);
+                cpx b[LG];
 #pragma unroll
-            for (int m = 1; m < r; m++) x[m] = cmul(x[m], __ldg(w + (m - 1) * p));
+                for (int j = 0; j < LG; j++) {
+                    if constexpr ((TWM & MUFFT_TW_SMEM) != 0) b[j] = w[((1 << j) - 1) * p];
+                    else b[j] = __ldg(w + ((1 << j) - 1) * p);
+                }
+                TwTree<r, LG, LG - 1, 0, true>::run(x, b, make_float2(1.0f, 0.0f));
+            } else {
+#pragma unroll
+                for (int m = 1; m < r; m++) {
+                    if constexpr ((TWM & MUFFT_TW_SMEM) != 0) x[m] = cmul(x[m], w[(m - 1) * p]);
+                    else x[m] = cmul(x[m], __ldg(w + (m - 1) * p));
+                }
+            }
         }
         dft_regs<r, DIR, (PK < 0 ? engine_packed(N, V) : PK != 0)>(x);
 #pragma unroll
@@ -487,16 +528,16 @@ __device__ __forceinline__ void engine_scatter_natural(const cpx (&v)[engine_reg
 // All passes of an N-point transform.  Every thread of the transform must call this (it
 // synchronises them); SYNC_T / SLOTS say how (see engine_sync): the row kernel passes the
 // threads of one transform, the column kernel passes the whole CTA.
-template <int N, int DIR, int CS, int SYNC_T, int SLOTS, int PASS = 0, int V = 0, int PK = -1>
+template <int N, int DIR, int CS, int SYNC_T, int SLOTS, int PASS = 0, int V = 0, int PK = -1, int TWM = 0>
 __device__ __forceinline__ void engine_run(cpx (&v)[engine_regs(N, V)], cpx *sm, const cpx *__restrict__ tw, int t, int slot)
 {
-    engine_butterflies<N, DIR, PASS, V, PK>(v, tw, t);
+    engine_butterflies<N, DIR, PASS, V, PK, TWM>(v, tw, t);
     if constexpr (PASS + 1 < engine_num_passes(N, V)) {
         if constexpr (PASS > 0) engine_sync<SYNC_T, SLOTS>(slot); // previous gather must be complete (WAR)
         engine_scatter<N, PASS, CS, V>(v, sm, t);
         engine_sync<SYNC_T, SLOTS>(slot);
         engine_gather<N, CS, PASS + 1, V>(v, sm, t);
-        engine_run<N, DIR, CS, SYNC_T, SLOTS, PASS + 1, V, PK>(v, sm, tw, t, slot);
+        engine_run<N, DIR, CS, SYNC_T, SLOTS, PASS + 1, V, PK, TWM>(v, sm, tw, t, slot);
     }
 }
 
@@ -538,10 +579,10 @@ __device__ __forceinline__ void engine_gather_plane(cpx (&v)[engine_regs(N, 0)],
     }
 }
 // As engine_run, with the split exchange; `sm` holds engine_smem_elems(N) * CS floats.
-template <int N, int DIR, int CS, int SYNC_T, int SLOTS, int PASS = 0, int PK = -1>
+template <int N, int DIR, int CS, int SYNC_T, int SLOTS, int PASS = 0, int PK = -1, int TWM = 0>
 __device__ __forceinline__ void engine_run_split(cpx (&v)[engine_regs(N, 0)], float *sm, const cpx *__restrict__ tw, int t, int slot)
 {
-    engine_butterflies<N, DIR, PASS, 0, PK>(v, tw, t);
+    engine_butterflies<N, DIR, PASS, 0, PK, TWM>(v, tw, t);
     if constexpr (PASS + 1 < engine_num_passes(N, 0)) {
         if constexpr (PASS > 0) engine_sync<SYNC_T, SLOTS>(slot); // previous gather must be complete (WAR)
         engine_scatter_plane<N, PASS, CS, 0>(v, sm, t);
@@ -551,7 +592,7 @@ __device__ __forceinline__ void engine_run_split(cpx (&v)[engine_regs(N, 0)], fl
         engine_scatter_plane<N, PASS, CS, 1>(v, sm, t);
         engine_sync<SYNC_T, SLOTS>(slot);
         engine_gather_plane<N, CS, 1>(v, sm, t);
-        engine_run_split<N, DIR, CS, SYNC_T, SLOTS, PASS + 1, PK>(v, sm, tw, t, slot);
+        engine_run_split<N, DIR, CS, SYNC_T, SLOTS, PASS + 1, PK, TWM>(v, sm, tw, t, slot);
     }
 }
 

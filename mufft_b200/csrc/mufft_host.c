@@ -63,10 +63,11 @@ static size_t g_stage_chunk_bytes = (size_t)64 << 20;
  * input rows are 16-byte aligned.  MUFFT_CUDA_PREFETCH in the environment sets the initial value,
  * mufft_cuda_set_prefetch() changes it. */
 static int g_prefetch = 0;
-/* Longest row transform that plans created from now on run in ONE kernel: MCU_ENGINE_MAX_N
- * (default) or MCU_ENGINE_BIG_N (16384 points: one 512-thread CTA per transform instead of the
- * two-kernel split; opt-in until measured on the GPU). */
-static unsigned g_onchip_limit = MCU_ENGINE_MAX_N;
+/* Longest row transform that plans created from now on run in ONE kernel: MCU_ENGINE_BIG_N
+ * (default; 16384 points = one 512-thread CTA per transform) or MCU_ENGINE_MAX_N (16384 points take
+ * the two-kernel split).  Measured on B200 (profiles/README.md): C2C 16384 x 16384 1.88 -> 1.05 ms,
+ * R2C / C2R 32768 x 16384 2.94 -> 1.16 / 1.22 ms with the single kernel. */
+static unsigned g_onchip_limit = MCU_ENGINE_BIG_N;
 void mufft_cuda_set_onchip_limit(unsigned n) { g_onchip_limit = n >= MCU_ENGINE_BIG_N ? MCU_ENGINE_BIG_N : MCU_ENGINE_MAX_N; }
 unsigned mufft_cuda_get_onchip_limit(void) { return g_onchip_limit; }
 __attribute__((constructor)) static void read_env(void)
@@ -94,7 +95,7 @@ void mufft_cuda_set_two_kernel(int enable) { g_two_kernel = enable != 0; }
 /* 2D C2C: 1 (default) = the fused persistent kernel when the shape has one, 0 = row kernel +
  * column kernel per group of images (the path every other shape and R2C/C2R take). */
 static int g_fused_2d = 1;
-void mufft_cuda_set_fused_2d(int mode) { g_fused_2d = mode <= 0 ? 0 : (mode >= 2 ? 2 : 1); }
+void mufft_cuda_set_fused_2d(int mode) { g_fused_2d = mode <= 0 ? 0 : (mode > 8 ? 1 : mode); }
 
 /* ---- per-thread state --------------------------------------------------------------------- */
 static __thread void *tls_stream = NULL;
@@ -565,7 +566,7 @@ static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode
     const unsigned n = ax->n;
     if ((in_mode == MCU_IN_MULACC || in_mode == MCU_IN_MULACC_C2R) && (pd == NULL || ax->d_engine_tw == NULL)) {
         snprintf(tls_error, sizeof(tls_error), "partitioned convolution needs a transform that fits the on-chip engine "
-                 "(stereo N <= %u, mono N <= %u)", MCU_ENGINE_MAX_N, 2 * MCU_ENGINE_MAX_N);
+                 "(stereo N <= %u, mono N <= %u)", g_onchip_limit, 2 * g_onchip_limit);
         return -1;
     }
     if (ax->d_engine_tw != NULL) {
@@ -1266,7 +1267,11 @@ static int run_2d_device(mufft_plan_2d *plan, void *out, const void *in, size_t 
         f.out = out; f.in = in; f.tw_x = plan->ax_x.d_engine_tw; f.tw_y = plan->ax_y.d_engine_tw;
         f.counters = plan->d_counters; f.out_image = (size_t)nx * ny; f.in_image = (size_t)nx * ny;
         f.batch = images; f.nx = nx; f.ny = ny; f.direction = plan->ax_x.direction;
-        f.tma = g_fused_2d == 2;
+        {   /* mode -> (TMA-fed kernel?, F2D_* flavour bits): see mufft_cuda_set_fused_2d in mufft_cuda.h */
+            static const int tma_of[9] = { 0, 0, 1, 0, 1, 0, 0, 0, 0 }, flags_of[9] = { 0, -1, 0, 3, 3, 7, 6, 2, 0 };
+            f.tma = tma_of[g_fused_2d];
+            f.flags = flags_of[g_fused_2d];
+        }
         return mcu_launch_2d_fused(&f, stream);
     }
     const int real_rows = plan->kind != KIND_C2C;

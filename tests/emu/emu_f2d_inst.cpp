@@ -9,7 +9,7 @@ using namespace mufft;
 #define EMU_CAT(a, b, c, d) EMU_CAT_(a, b, c, d)
 
 extern "C" int EMU_CAT(emu_2d_fused_, EMU_NX, x, EMU_NY)(int direction, void *out, const void *in, const void *tw_x, const void *tw_y,
-                                                        unsigned *counters, size_t batch, unsigned lag, unsigned ctas)
+                                                        unsigned *counters, size_t batch, unsigned lag, unsigned ctas, int lite)
 {
     constexpr int NX = EMU_NX, NY = EMU_NY;
     if (!f2d_supported(NX, NY)) return -3;
@@ -18,7 +18,19 @@ extern "C" int EMU_CAT(emu_2d_fused_, EMU_NX, x, EMU_NY)(int direction, void *ou
     a.out = out; a.in = in; a.tw_x = tw_x; a.tw_y = tw_y; a.counters = counters;
     a.out_image = (size_t)NX * NY; a.in_image = (size_t)NX * NY; a.batch = batch; a.nx = NX; a.ny = NY;
     a.direction = direction; a.lag = lag;
-    if (direction < 0) emu::launch(emu::idx3{ ctas, 1, 1 }, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, -1>(a); });
-    else emu::launch(emu::idx3{ ctas, 1, 1 }, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, 1>(a); });
+    const emu::idx3 grid{ ctas, 1, 1 };
+    if (lite == 1) { // twiddle tables in shared memory + one-sided fences
+        if (direction < 0) emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY, true), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, -1, F2D_LITE>(a); });
+        else emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY, true), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, 1, F2D_LITE>(a); });
+    } else if (lite == 2) { // ... + derived twiddles
+        if (direction < 0) emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY, true), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, -1, F2D_LITE | F2D_DERIVE>(a); });
+        else emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY, true), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, 1, F2D_LITE | F2D_DERIVE>(a); });
+    } else if (lite == 3) { // derived twiddles from the global table
+        if (direction < 0) emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, -1, F2D_ONE_SIDED | F2D_DERIVE>(a); });
+        else emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, 1, F2D_ONE_SIDED | F2D_DERIVE>(a); });
+    } else {
+        if (direction < 0) emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, -1>(a); });
+        else emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, 1>(a); });
+    }
     return 0;
 }

@@ -8,7 +8,7 @@ using namespace mufft;
 #define EMU_CAT(a, b, c, d) EMU_CAT_(a, b, c, d)
 
 extern "C" int EMU_CAT(emu_2d_tma_, EMU_NX, x, EMU_NY)(int direction, void *out, const void *in, const void *tw_x, const void *tw_y,
-                                                      unsigned *counters, size_t batch, unsigned lag, unsigned ctas)
+                                                      unsigned *counters, size_t batch, unsigned lag, unsigned ctas, int lite)
 {
     constexpr int NX = EMU_NX, NY = EMU_NY;
     if (!f2t_supported(NX, NY)) return -3;
@@ -22,7 +22,13 @@ extern "C" int EMU_CAT(emu_2d_tma_, EMU_NX, x, EMU_NY)(int direction, void *out,
     map.pitch_bytes = (size_t)NX * 8;
     map.box_w = f2d_cols_per_tile(NY);
     map.box_h = f2t_box_rows(NY);
-    if (direction < 0) emu::launch(emu::idx3{ ctas, 1, 1 }, MUFFT_F2D_THREADS, f2t_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_tma_kernel<NX, NY, -1>(a, map); });
-    else emu::launch(emu::idx3{ ctas, 1, 1 }, MUFFT_F2D_THREADS, f2t_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_tma_kernel<NX, NY, 1>(a, map); });
+    const emu::idx3 grid{ ctas, 1, 1 };
+    if (lite) {
+        if (direction < 0) emu::launch(grid, MUFFT_F2D_THREADS, f2t_smem_bytes(NX, NY, true), ctas, 1, [&] { fft2d_tma_kernel<NX, NY, -1, true>(a, map); });
+        else emu::launch(grid, MUFFT_F2D_THREADS, f2t_smem_bytes(NX, NY, true), ctas, 1, [&] { fft2d_tma_kernel<NX, NY, 1, true>(a, map); });
+    } else {
+        if (direction < 0) emu::launch(grid, MUFFT_F2D_THREADS, f2t_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_tma_kernel<NX, NY, -1>(a, map); });
+        else emu::launch(grid, MUFFT_F2D_THREADS, f2t_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_tma_kernel<NX, NY, 1>(a, map); });
+    }
     return 0;
 }

@@ -22,6 +22,33 @@ int run(const mcu_rows_args &a)
 }
 } // namespace
 
+static int dispatch(const mcu_rows_args &a)
+{
+    if (a.direction < 0) {
+        switch (a.in_mode * 8 + a.out_mode) {
+        case MCU_IN_COMPLEX * 8 + MCU_OUT_COMPLEX: return run<-1, MCU_IN_COMPLEX, MCU_OUT_COMPLEX>(a);
+        case MCU_IN_COMPLEX * 8 + MCU_OUT_PEERS: return run<-1, MCU_IN_COMPLEX, MCU_OUT_PEERS>(a);
+        case MCU_IN_COMPLEX * 8 + MCU_OUT_R2C: return run<-1, MCU_IN_COMPLEX, MCU_OUT_R2C>(a);
+        case MCU_IN_COMPLEX * 8 + MCU_OUT_R2C_FULL: return run<-1, MCU_IN_COMPLEX, MCU_OUT_R2C_FULL>(a);
+        case MCU_IN_HALF * 8 + MCU_OUT_COMPLEX: return run<-1, MCU_IN_HALF, MCU_OUT_COMPLEX>(a);
+        case MCU_IN_HALF * 8 + MCU_OUT_R2C: return run<-1, MCU_IN_HALF, MCU_OUT_R2C>(a);
+        case MCU_IN_HALF * 8 + MCU_OUT_R2C_FULL: return run<-1, MCU_IN_HALF, MCU_OUT_R2C_FULL>(a);
+        default: return -1;
+        }
+    }
+    if (a.out_mode == MCU_OUT_PEERS && a.in_mode == MCU_IN_COMPLEX) return run<1, MCU_IN_COMPLEX, MCU_OUT_PEERS>(a);
+    if (a.out_mode != MCU_OUT_COMPLEX) return -1;
+    switch (a.in_mode) {
+    case MCU_IN_COMPLEX: return run<1, MCU_IN_COMPLEX, MCU_OUT_COMPLEX>(a);
+    case MCU_IN_C2R: return run<1, MCU_IN_C2R, MCU_OUT_COMPLEX>(a);
+    case MCU_IN_MUL: return run<1, MCU_IN_MUL, MCU_OUT_COMPLEX>(a);
+    case MCU_IN_MUL_C2R: return run<1, MCU_IN_MUL_C2R, MCU_OUT_COMPLEX>(a);
+    case MCU_IN_MULACC: return run<1, MCU_IN_MULACC, MCU_OUT_COMPLEX>(a);
+    case MCU_IN_MULACC_C2R: return run<1, MCU_IN_MULACC_C2R, MCU_OUT_COMPLEX>(a);
+    default: return -1;
+    }
+}
+
 extern "C" int EMU_CAT(emu_rows_, EMU_N)(int direction, int in_mode, int out_mode, void *out, const void *in, const void *in2,
                                          const void *tw, const void *rtw, size_t out_stride, size_t in_stride, size_t in2_stride,
                                          size_t batch, float norm)
@@ -31,21 +58,32 @@ extern "C" int EMU_CAT(emu_rows_, EMU_N)(int direction, int in_mode, int out_mod
     a.out = out; a.in = in; a.in2 = in2; a.tw = tw; a.rtw = rtw;
     a.out_stride = out_stride; a.in_stride = in_stride; a.in2_stride = in2_stride;
     a.batch = batch; a.n = EMU_N; a.direction = direction; a.in_mode = in_mode; a.out_mode = out_mode; a.norm = norm;
-    if (direction < 0) {
-        switch (in_mode * 8 + out_mode) {
-        case MCU_IN_COMPLEX * 8 + MCU_OUT_COMPLEX: return run<-1, MCU_IN_COMPLEX, MCU_OUT_COMPLEX>(a);
-        case MCU_IN_COMPLEX * 8 + MCU_OUT_R2C: return run<-1, MCU_IN_COMPLEX, MCU_OUT_R2C>(a);
-        case MCU_IN_COMPLEX * 8 + MCU_OUT_R2C_FULL: return run<-1, MCU_IN_COMPLEX, MCU_OUT_R2C_FULL>(a);
-        case MCU_IN_HALF * 8 + MCU_OUT_COMPLEX: return run<-1, MCU_IN_HALF, MCU_OUT_COMPLEX>(a);
-        default: return -1;
-        }
-    }
-    if (out_mode != MCU_OUT_COMPLEX) return -1;
-    switch (in_mode) {
-    case MCU_IN_COMPLEX: return run<1, MCU_IN_COMPLEX, MCU_OUT_COMPLEX>(a);
-    case MCU_IN_C2R: return run<1, MCU_IN_C2R, MCU_OUT_COMPLEX>(a);
-    case MCU_IN_MUL: return run<1, MCU_IN_MUL, MCU_OUT_COMPLEX>(a);
-    case MCU_IN_MUL_C2R: return run<1, MCU_IN_MUL_C2R, MCU_OUT_COMPLEX>(a);
-    default: return -1;
-    }
+    return dispatch(a);
+}
+
+// Partitioned convolution load stage (MCU_IN_MULACC*): sum over `parts` (spectrum, filter) pairs.
+extern "C" int EMU_CAT(emu_rows_parts_, EMU_N)(int in_mode, void *out, const void *in, const void *in2, const void *tw, const void *rtw,
+                                               size_t out_stride, size_t in_stride, size_t batch, float norm, unsigned parts,
+                                               long long in_part_stride, long long in2_part_stride)
+{
+    mcu_rows_args a;
+    memset(&a, 0, sizeof(a));
+    a.out = out; a.in = in; a.in2 = in2; a.tw = tw; a.rtw = rtw;
+    a.out_stride = out_stride; a.in_stride = in_stride;
+    a.batch = batch; a.n = EMU_N; a.direction = 1; a.in_mode = in_mode; a.out_mode = MCU_OUT_COMPLEX; a.norm = norm;
+    a.parts = parts; a.in_part_stride = in_part_stride; a.in2_part_stride = in2_part_stride;
+    return dispatch(a);
+}
+
+// Exchange-step epilogue (MCU_OUT_PEERS): element x of row b goes to slab x >> shift.
+extern "C" int EMU_CAT(emu_rows_peers_, EMU_N)(int direction, void *const *bases, unsigned peers, unsigned shift, size_t row0, size_t pitch,
+                                               const void *in, const void *tw, size_t in_stride, size_t batch)
+{
+    mcu_rows_args a;
+    memset(&a, 0, sizeof(a));
+    a.in = in; a.tw = tw; a.in_stride = in_stride; a.batch = batch; a.n = EMU_N; a.direction = direction;
+    a.in_mode = MCU_IN_COMPLEX; a.out_mode = MCU_OUT_PEERS; a.norm = 1.0f;
+    for (unsigned p = 0; p < peers && p < MCU_MAX_PEERS; p++) a.peers.base[p] = bases[p];
+    a.peers.row0 = row0; a.peers.pitch = pitch; a.peers.shift = shift;
+    return dispatch(a);
 }

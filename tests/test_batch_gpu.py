@@ -227,7 +227,7 @@ def test_conv_fused_batch_device(m, torch, oracle, n, stereo, padded):
         assert np.max(np.abs(got - want)) < 2e-6 * math.sqrt(n) * (1 if padded else 2)
 
 
-@pytest.mark.parametrize("n,parts", [(64, 1), (64, 5), (2048, 3), (8192, 8), (16384, 4)])
+@pytest.mark.parametrize("n,parts", [(64, 1), (64, 5), (1024, 2), (2048, 3), (8192, 8), (16384, 4), (32768, 2)])
 @pytest.mark.parametrize("stereo", [0, 1])
 def test_conv_partitioned_device(m, torch, oracle, n, parts, stereo):
     """Uniformly partitioned convolution (filter of parts * N/2 taps): one inverse transform per block
@@ -250,7 +250,7 @@ def test_conv_partitioned_device(m, torch, oracle, n, parts, stereo):
     assert m.mufft_execute_conv_input_batch(plan, 1, fspec.data_ptr(), taps.data_ptr(), parts) == 0
     first = spectra.data_ptr() + (parts - 1) * blk * 8
     err = m.mufft_execute_conv_output_partitioned_batch(plan, out.data_ptr(), first, fspec.data_ptr(), parts, batch)
-    if stereo and n > 8192:
+    if stereo and n > m.mufft_cuda_get_onchip_limit():
         assert err != 0 and b"on-chip engine" in m.mufft_cuda_last_error()
         m.mufft_free_plan_conv(plan)
         return
@@ -317,6 +317,35 @@ def test_c2c_2d_batch_device(m, torch, oracle, nx, ny, fused):
     m.mufft_cuda_set_fused_2d(1)
 
 
+@pytest.mark.parametrize("nx,ny", [(256, 256), (512, 2048), (1024, 1024), (2048, 256)])
+@pytest.mark.parametrize("mode", [2, 3, 4, 5, 6, 7, 8])
+def test_c2c_2d_fused_flavours(m, torch, oracle, nx, ny, mode):
+    """Every fixed flavour of the fused 2D kernel (mufft_cuda_set_fused_2d 2..8: TMA-fed tiles, twiddle
+    tables in shared memory, one-sided fences, derived twiddles, plain); mode 1, the per-shape default,
+    is what test_c2c_2d_batch_device runs."""
+    m.mufft_cuda_set_fused_2d(mode)
+    try:
+        batch = max(5, min(40, (96 << 20) // (8 * nx * ny)))
+        x = dev_random(torch, (batch, ny, nx, 2), nx + ny + mode)
+        y = torch.zeros_like(x)
+        xc = torch.view_as_complex(x)
+        for direction in (-1, 1):
+            plan = m.mufft_create_plan_2d_c2c(nx, ny, direction, 0)
+            assert plan
+            m.mufft_cuda_launch_count(1)
+            assert m.mufft_execute_plan_2d_batch(plan, y.data_ptr(), x.data_ptr(), batch) == 0, m.mufft_cuda_last_error()
+            assert m.mufft_cuda_launch_count(1) == 1, "the fused path is one launch for the whole batch"
+            m.mufft_free_plan_2d(plan)
+            ref = torch.fft.fft2(xc) if direction < 0 else torch.fft.ifft2(xc, norm="forward")
+            yc = torch.view_as_complex(y)
+            err = (torch.linalg.vector_norm((yc - ref).reshape(batch, -1), dim=1) /
+                   torch.linalg.vector_norm(ref.reshape(batch, -1), dim=1)).max().item()
+            assert err <= tol(nx * ny)
+            assert rel_l2(yc[batch - 1].cpu().numpy(), oracle.c2c_2d(xc[batch - 1].cpu().numpy(), direction)) <= tol(nx * ny)
+    finally:
+        m.mufft_cuda_set_fused_2d(1)
+
+
 @pytest.mark.parametrize("case", ["c2c2d-fused", "c2c2d-separate", "r2c2d", "c2r2d", "c2c-long"])
 def test_staged_host_batches_that_share_plan_scratch(m, torch, oracle, case):
     """Pageable host buffers, batches long enough for several staging chunks on different streams:
@@ -378,6 +407,8 @@ def test_large_n(m, torch, oracle, n, two_kernel):
     if two_kernel == 0 and n > (1 << 19):
         pytest.skip("generic passes are covered at the smaller lengths")
     m.mufft_cuda_set_two_kernel(two_kernel)
+    # 16384 points fit ONE kernel by default (tests above); here they take the paths of the longer lengths
+    m.mufft_cuda_set_onchip_limit(8192)
     try:
         batch = 3
         x = dev_random(torch, (batch, 2 * n), n)
@@ -421,6 +452,32 @@ def test_large_n(m, torch, oracle, n, two_kernel):
         assert (torch.linalg.vector_norm(back / (2 * n) - r) / torch.linalg.vector_norm(r)).item() <= 2 * tol(2 * n)
     finally:
         m.mufft_cuda_set_two_kernel(1)
+        m.mufft_cuda_set_onchip_limit(16384)
+
+
+def test_onchip_limit_knob(m, torch):
+    """mufft_cuda_set_onchip_limit: 16384-point plans run in one kernel by default and on the two-kernel
+    split when the limit is lowered; both give the same transform."""
+    n, batch = 16384, 37
+    x = dev_random(torch, (batch, 2 * n), 3)
+    outs = []
+    try:
+        for limit, engine in ((16384, 1), (8192, 0), (12345, 0), (1 << 20, 1)):
+            m.mufft_cuda_set_onchip_limit(limit)
+            assert m.mufft_cuda_get_onchip_limit() == (16384 if engine else 8192)
+            plan = m.mufft_create_plan_1d_c2c(n, -1, 0)
+            assert m.mufft_cuda_plan_1d_uses_engine(plan) == engine
+            y = torch.zeros_like(x)
+            m.mufft_cuda_launch_count(1)
+            assert m.mufft_execute_plan_1d_batch(plan, y.data_ptr(), x.data_ptr(), batch, 0, 0) == 0
+            assert m.mufft_cuda_launch_count(1) == (1 if engine else 2)
+            m.mufft_free_plan_1d(plan)
+            outs.append(torch.view_as_complex(y.view(batch, n, 2)))
+    finally:
+        m.mufft_cuda_set_onchip_limit(16384)
+    ref = torch.fft.fft(torch.view_as_complex(x.view(batch, n, 2)), dim=1)
+    for y in outs:
+        assert (torch.linalg.vector_norm(y - ref) / torch.linalg.vector_norm(ref)).item() <= tol(n)
 
 
 def test_linearity_and_parseval_at_full_size(m, torch):

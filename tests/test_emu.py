@@ -122,6 +122,74 @@ def test_rows_r2c(emu, host, oracle, n, full):
         assert cpu_libs.rel_l2(got[b], want) <= tol(2 * n)
 
 
+@pytest.mark.parametrize("n", [512, 16384])
+@pytest.mark.parametrize("full", [False, True])
+def test_rows_zero_padded_r2c(emu, host, oracle, n, full):
+    """Zero-padded load stage and R2C epilogue in the same kernel (2n-point real transform of n reals)."""
+    rng = np.random.default_rng(7 * n + full)
+    r = rnd(rng, 2, n)
+    elems = 2 * n if full else n + 1
+    got = rows(emu, host, n, -1, IN_HALF, OUT_R2C_FULL if full else OUT_R2C, r.view(np.complex64), elems, rtw=resolve_twiddles(-1, n))
+    flags = cpu_libs.FLAG_ZERO_PAD | (cpu_libs.FLAG_FULL_R2C if full else 0)
+    for b in range(2):
+        assert cpu_libs.rel_l2(got[b], oracle.r2c(r[b], flags, n=2 * n)) <= tol(2 * n)
+
+
+@pytest.mark.parametrize("n", [512, 16384])
+@pytest.mark.parametrize("direction", [-1, 1])
+def test_rows_scatter_to_peer_slabs(emu, host, n, direction):
+    """MCU_OUT_PEERS: the row kernel's stores are the exchange step of a slab 2D transform - element x
+    of row b lands in the column slab of device x / (n / peers), at row row0 + b."""
+    peers, batch, row0, rows_total = 4, 3, 2, 6
+    width = n // peers
+    rng = np.random.default_rng(n + 99)
+    x = crnd(rng, batch, n)
+    slabs = [np.full((rows_total, width), np.nan, np.complex64) for _ in range(peers)]
+    bases = (C.c_void_p * peers)(*[s_.ctypes.data for s_ in slabs])
+    fn = getattr(emu, f"emu_rows_peers_{n}")
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_uint, C.c_uint, sz, sz, vp, vp, sz, sz]
+    tw = engine_table(host, n, direction)
+    assert fn(direction, bases, peers, int(math.log2(width)), row0, width, x.ctypes.data, tw.ctypes.data, n, batch) == 0
+    want = np.fft.fft(x.astype(np.complex128), axis=1) if direction < 0 else np.fft.ifft(x.astype(np.complex128), axis=1, norm="forward")
+    for p_ in range(peers):
+        assert np.all(np.isnan(slabs[p_][:row0].real)) and np.all(np.isnan(slabs[p_][row0 + batch:].real)), "wrote outside its rows"
+        for b in range(batch):
+            assert cpu_libs.rel_l2(slabs[p_][row0 + b], want[b, p_ * width:(p_ + 1) * width]) <= 2 * tol(n)
+
+
+@pytest.mark.parametrize("n", [512, 16384])
+@pytest.mark.parametrize("mono", [False, True])
+def test_rows_partitioned_multiply(emu, host, oracle, n, mono):
+    """MCU_IN_MULACC / MCU_IN_MULACC_C2R: output block b = IFFT(sum_p S[b - p] .* F[p]) / N, the load stage of
+    mufft_execute_conv_output_partitioned_batch (stereo: n-point complex; mono: C2R resolve of n + 1 bins)."""
+    parts, batch = 3, 2
+    rng = np.random.default_rng(n + 5 + mono)
+    bins = n + 1 if mono else n
+    if mono:  # spectra of real signals, so that the C2R result is the real convolution
+        spectra = np.stack([np.fft.rfft(rnd(rng, 2 * n).astype(np.float64)) for _ in range(batch + parts - 1)]).astype(np.complex64)
+        filt = np.stack([np.fft.rfft(rnd(rng, 2 * n).astype(np.float64)) for _ in range(parts)]).astype(np.complex64)
+    else:
+        spectra, filt = crnd(rng, batch + parts - 1, bins), crnd(rng, parts, bins)
+    fn = getattr(emu, f"emu_rows_parts_{n}")
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, vp, vp, vp, vp, vp, sz, sz, sz, C.c_float, C.c_uint, C.c_longlong, C.c_longlong]
+    mode = 6 if mono else 5
+    variant = host.mcu_rows_variant(n, mode, OUT_COMPLEX)
+    tw = engine_table(host, n, 1, variant)
+    rtw = resolve_twiddles(1, n)
+    out = np.full((batch, n), np.nan, np.complex64)
+    norm = 1.0 / (2 * n if mono else n)
+    first = spectra[parts - 1:]  # S[0]; S[-1], S[-2] sit in front of it
+    assert fn(mode, out.ctypes.data, first.ctypes.data, filt.ctypes.data, tw.ctypes.data, rtw.ctypes.data, n, bins, batch, norm,
+              parts, -bins, bins) == 0
+    for b in range(batch):
+        acc = sum(spectra[parts - 1 + b - p_].astype(np.complex128) * filt[p_].astype(np.complex128) for p_ in range(parts))
+        want = np.fft.irfft(acc, 2 * n) if mono else np.fft.ifft(acc)
+        got = out[b].view(np.float32) if mono else out[b]
+        assert cpu_libs.rel_l2(got, want) <= 2 * tol(n)
+
+
 @pytest.mark.parametrize("n", ROWS_SIZES)
 def test_rows_c2r(emu, host, oracle, n):
     rng = np.random.default_rng(3 * n)
@@ -142,22 +210,24 @@ def test_rows_spectral_multiply(emu, host, n):
         assert cpu_libs.rel_l2(got[b], want[b]) <= tol(n)
 
 
-@pytest.mark.parametrize("ctas", [1, 3])
+@pytest.mark.parametrize("lite", [0, 1, 2, 3])
+@pytest.mark.parametrize("nx,ny,ctas", [(256, 256, 1), (256, 256, 3), (512, 256, 2)])
 @pytest.mark.parametrize("direction", [-1, 1])
-def test_fused_2d(emu, host, oracle, ctas, direction):
+def test_fused_2d(emu, host, oracle, nx, ny, ctas, direction, lite):
     """The persistent fused 2D kernel with CTAs really running side by side: row tickets, lagged column
-    tickets, the rows-done counters and the deferred release (fft2d_kernel.cuh)."""
-    nx = ny = 256
+    tickets, the rows-done counters and the deferred release (fft2d_kernel.cuh); lite 1 = twiddle tables
+    in shared memory (two tables when the sides differ) and one-sided fences, 2 = that with derived
+    twiddles, 3 = derived twiddles from the global table."""
     batch = 3
-    fn = emu.emu_2d_fused_256x256
+    fn = getattr(emu, f"emu_2d_fused_{nx}x{ny}")
     fn.restype = C.c_int
-    fn.argtypes = [C.c_int, vp, vp, vp, vp, vp, sz, C.c_uint, C.c_uint]
+    fn.argtypes = [C.c_int, vp, vp, vp, vp, vp, sz, C.c_uint, C.c_uint, C.c_int]
     rng = np.random.default_rng(11 + ctas)
     x = crnd(rng, batch, ny, nx)
     out = np.full((batch, ny, nx), np.nan, np.complex64)
     counters = np.zeros(1 + batch, np.uint32)
-    tw = engine_table(host, 256, direction)
-    assert fn(direction, out.ctypes.data, x.ctypes.data, tw.ctypes.data, tw.ctypes.data, counters.ctypes.data, batch, 1, ctas) == 0
+    assert fn(direction, out.ctypes.data, x.ctypes.data, engine_table(host, nx, direction).ctypes.data,
+              engine_table(host, ny, direction).ctypes.data, counters.ctypes.data, batch, 1, ctas, lite) == 0
     for b in range(batch):
         assert cpu_libs.rel_l2(out[b], oracle.c2c_2d(x[b], direction)) <= tol(nx * ny)
     assert list(counters[1:]) == [ny] * batch
@@ -171,20 +241,21 @@ def test_fused_2d(emu, host, oracle, ctas, direction):
     (1024, 1024, 2, 2, 1),  # the BASELINE configs[3] image shape: 64 KiB tiles, four tensor boxes per column tile
 ])
 @pytest.mark.parametrize("direction", [-1, 1])
-def test_fused_2d_tma(emu, host, oracle, nx, ny, batch, ctas, lag, direction):
+@pytest.mark.parametrize("lite", [0, 1])
+def test_fused_2d_tma(emu, host, oracle, nx, ny, batch, ctas, lag, direction, lite):
     """fft2d_tma_kernel.cuh: tiles land in shared memory through (emulated) bulk copies one tile ahead
     of the butterflies, exchanges run plane by plane in a half-size area."""
     if nx == 1024 and direction == 1:
         pytest.skip("one direction is enough at the large shape")
     fn = getattr(emu, f"emu_2d_tma_{nx}x{ny}")
     fn.restype = C.c_int
-    fn.argtypes = [C.c_int, vp, vp, vp, vp, vp, sz, C.c_uint, C.c_uint]
+    fn.argtypes = [C.c_int, vp, vp, vp, vp, vp, sz, C.c_uint, C.c_uint, C.c_int]
     rng = np.random.default_rng(nx + ny + batch + ctas)
     x = crnd(rng, batch, ny, nx)
     out = np.full((batch, ny, nx), np.nan, np.complex64)
     counters = np.zeros(1 + batch, np.uint32)
     assert fn(direction, out.ctypes.data, x.ctypes.data, engine_table(host, nx, direction).ctypes.data,
-              engine_table(host, ny, direction).ctypes.data, counters.ctypes.data, batch, lag, ctas) == 0
+              engine_table(host, ny, direction).ctypes.data, counters.ctypes.data, batch, lag, ctas, lite) == 0
     want = np.fft.fft2(x.astype(np.complex128)) if direction < 0 else np.fft.ifft2(x.astype(np.complex128), norm="forward")
     for b in range(batch):
         assert cpu_libs.rel_l2(out[b], want[b]) <= tol(nx * ny)

@@ -1,0 +1,185 @@
+"""Quick GPU check of the opt-in paths (no torch import: ctypes + numpy on mufft_alloc memory):
+  * 16384-point row transforms in one kernel (mufft_cuda_set_onchip_limit) vs the two-kernel split;
+  * TMA-fed fused 2D kernel (mufft_cuda_set_fused_2d(2)) vs the direct-load fused kernel.
+Each line of gpurun_out/probe_optin.jsonl: parity against numpy float64 on a few transforms and the
+wall-clock time of synchronous calls (kernels of a millisecond or more, so the launch + sync overhead
+of ~20 us does not matter).  Usage: python tools/probe_optin.py [quick]
+"""
+import ctypes as C
+import json
+import math
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import mufft_b200 as m  # noqa: E402
+
+OUT = os.path.join(ROOT, "gpurun_out")
+os.makedirs(OUT, exist_ok=True)
+LOG = open(os.path.join(OUT, "probe_optin.jsonl"), "a")
+QUICK = len(sys.argv) > 1 and sys.argv[1] == "quick"
+# mufft_cuda_set_fused_2d: 1 direct loads, 2 TMA-fed, 3 / 4 the same with smem twiddles + one-sided fences,
+# 5 = 3 + derived twiddles, 6 = one-sided fences + derived twiddles (global table), 7 = one-sided fences only
+MODES = (1, 3, 5, 6, 7)
+ARG = sys.argv[1] if len(sys.argv) > 1 else ""
+
+
+def emit(**kw):
+    line = json.dumps(kw)
+    print(line, flush=True)
+    LOG.write(line + "\n")
+    LOG.flush()
+    os.fsync(LOG.fileno())
+
+
+def managed(count_floats):
+    ptr = m.mufft_alloc(count_floats * 4)
+    assert ptr
+    return ptr, np.ctypeslib.as_array((C.c_float * count_floats).from_address(ptr))
+
+
+def fill(arr, seed, unit):
+    """Random data in the first and the last `unit` floats (the transforms that get checked); the rest
+    stays untouched (zero pages populated on the device at first use) - timing does not depend on values."""
+    rng = np.random.default_rng(seed)
+    arr[:unit] = rng.random(unit, np.float32) - np.float32(0.5)
+    arr[-unit:] = rng.random(unit, np.float32) - np.float32(0.5)
+
+
+def rel_l2(a, b):
+    a = np.asarray(a).astype(np.complex128).ravel()
+    b = np.asarray(b).astype(np.complex128).ravel()
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def timed(call, reps):
+    call()  # warm-up: page migration of the managed buffers, attribute calls
+    call()
+    best = 1e9
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        call()
+        best = min(best, time.perf_counter() - t0)
+    return best * 1e3
+
+
+def probe_1d(n, batch):
+    pin, x = managed(2 * n * batch)
+    pout, y = managed(2 * n * batch)
+    fill(x, n, 2 * n)
+    xc = x.view(np.complex64).reshape(batch, n)
+    yc = y.view(np.complex64).reshape(batch, n)
+    for limit in (8192, 16384):
+        m.mufft_cuda_set_onchip_limit(limit)
+        for direction in (-1, 1):
+            plan = m.mufft_create_plan_1d_c2c(n, direction, 0)
+            assert plan
+            y[:64] = 0
+            ms = timed(lambda: m.mufft_execute_plan_1d_batch(plan, pout, pin, batch, 0, 0), 3)
+            want = np.fft.fft(xc[[0, batch - 1]].astype(np.complex128), axis=1) if direction < 0 else \
+                np.fft.ifft(xc[[0, batch - 1]].astype(np.complex128), axis=1, norm="forward")
+            err = max(rel_l2(yc[0], want[0]), rel_l2(yc[batch - 1], want[1]))
+            emit(what="c2c1d", n=n, batch=batch, direction=direction, onchip_limit=limit, uses_engine=m.mufft_cuda_plan_1d_uses_engine(plan),
+                 ms=round(ms, 4), gbs=round(16 * n * batch / ms / 1e6, 1), rel_l2=err, ok=bool(err <= 1e-6 * math.log2(n)),
+                 last_error=m.mufft_cuda_last_error().decode())
+            m.mufft_free_plan_1d(plan)
+        # real transforms of 2n points on the same engine length
+        rplan, cplan = m.mufft_create_plan_1d_r2c(2 * n, 0), m.mufft_create_plan_1d_c2r(2 * n, 0)
+        rb = batch
+        pspec, spec = managed(2 * (n + 1) * rb)
+        ms_r = timed(lambda: m.mufft_execute_plan_1d_batch(rplan, pspec, pin, rb, 0, 0), 3)
+        r = x.reshape(rb, 2 * n)
+        sc = spec.view(np.complex64).reshape(rb, n + 1)
+        err_r = max(rel_l2(sc[b], np.fft.rfft(r[b].astype(np.float64))) for b in (0, rb - 1))
+        ms_c = timed(lambda: m.mufft_execute_plan_1d_batch(cplan, pout, pspec, rb, 0, 0), 3)
+        back = y.reshape(rb, 2 * n)
+        err_c = max(rel_l2(back[b] / (2 * n), r[b]) for b in (0, rb - 1))
+        emit(what="r2c_c2r", n=2 * n, batch=rb, onchip_limit=limit, ms_r2c=round(ms_r, 4), ms_c2r=round(ms_c, 4),
+             gbs_r2c=round((8 * n + 8 * (n + 1)) * rb / ms_r / 1e6, 1), rel_l2_r2c=err_r, rel_l2_c2r=err_c,
+             ok=bool(err_r <= 1e-6 * math.log2(2 * n) and err_c <= 2e-6 * math.log2(2 * n)))
+        # zero-padded forward transform (input rows really n/2 long)
+        zplan = m.mufft_create_plan_1d_c2c(n, -1, m.MUFFT_FLAG_ZERO_PAD_UPPER_HALF)
+        assert m.mufft_execute_plan_1d_batch(zplan, pout, pin, 4, 0, 0) == 0
+        xh = x.view(np.complex64)[: n // 2]
+        want = np.fft.fft(np.concatenate([xh, np.zeros(n // 2, np.complex64)]).astype(np.complex128))
+        err_z = rel_l2(yc[0], want)
+        m.mufft_free_plan_1d(zplan)
+        # stereo convolution at this length: conv_input (zero padded) + conv_output (multiply in the load stage)
+        method = m.MUFFT_CONV_METHOD_FLAG_STEREO_MONO | m.MUFFT_CONV_METHOD_FLAG_ZERO_PAD_UPPER_HALF_FIRST | m.MUFFT_CONV_METHOD_FLAG_ZERO_PAD_UPPER_HALF_SECOND
+        cp = m.mufft_create_plan_conv(n, 0, method)
+        blk = m.mufft_conv_get_transformed_block_size(cp)
+        pf, f = managed(blk // 4)
+        ps, sp = managed(blk // 4)
+        taps = x[n // 2: n].copy()  # inside the first (random) row
+        ptaps, tp = managed(n // 2)
+        tp[:] = taps
+        m.mufft_execute_conv_input(cp, 1, pf, ptaps)
+        m.mufft_execute_conv_input(cp, 0, ps, pin)
+        m.mufft_execute_conv_output(cp, pout, ps, pf)
+        a = np.concatenate([xh, np.zeros(n // 2, np.complex64)]).astype(np.complex128)
+        b = np.concatenate([taps, np.zeros(n // 2, np.float32)]).astype(np.complex128)
+        err_v = rel_l2(yc[0], np.fft.ifft(np.fft.fft(a) * np.fft.fft(b)))
+        m.mufft_free_plan_conv(cp)
+        for q in (pf, ps, ptaps):
+            m.mufft_free(q)
+        emit(what="zero_pad_and_conv", n=n, onchip_limit=limit, rel_l2_zero_pad=err_z, rel_l2_conv=err_v,
+             ok=bool(err_z <= 1e-6 * math.log2(n) and err_v <= 2e-6 * math.log2(n)))
+        m.mufft_free_plan_1d(rplan)
+        m.mufft_free_plan_1d(cplan)
+        m.mufft_free(pspec)
+    m.mufft_cuda_set_onchip_limit(8192)
+    m.mufft_free(pin)
+    m.mufft_free(pout)
+
+
+def probe_2d(nx, ny, batch, modes=None, direction=-1, tag=""):
+    modes = modes or MODES
+    pin, x = managed(2 * nx * ny * batch)
+    pout, y = managed(2 * nx * ny * batch)
+    fill(x, nx + ny, 2 * nx * ny)
+    xc = x.view(np.complex64).reshape(batch, ny, nx)
+    yc = y.view(np.complex64).reshape(batch, ny, nx)
+    for mode in modes:
+        m.mufft_cuda_set_fused_2d(mode)
+        plan = m.mufft_create_plan_2d_c2c(nx, ny, direction, 0)
+        assert plan
+        m.mufft_cuda_launch_count(1)
+        ms = timed(lambda: m.mufft_execute_plan_2d_batch(plan, pout, pin, batch), 5)
+        launches = m.mufft_cuda_launch_count(1)
+        checks = (0, batch - 1) if nx * ny <= 512 * 512 else (batch - 1,)
+        f2 = (lambda z: np.fft.fft2(z)) if direction < 0 else (lambda z: np.fft.ifft2(z, norm="forward"))
+        err = max(rel_l2(yc[b], f2(xc[b].astype(np.complex128))) for b in checks)
+        emit(what="c2c2d" + tag, nx=nx, ny=ny, batch=batch, direction=direction, fused_mode=mode, paths=m.mufft_cuda_plan_2d_paths(plan), ms=round(ms, 4), gbs=round(16 * nx * ny * batch / ms / 1e6, 1),
+             launches_per_call=launches / 7, rel_l2=err, ok=bool(err <= 1e-6 * math.log2(nx * ny)), last_error=m.mufft_cuda_last_error().decode())
+        m.mufft_free_plan_2d(plan)
+    m.mufft_cuda_set_fused_2d(1)
+    m.mufft_free(pin)
+    m.mufft_free(pout)
+
+
+if __name__ == "__main__":
+    assert m.mufft_cuda_device_count() >= 1 and m.mufft_cuda_set_device(0) == 0
+    emit(what="start", arg=ARG)
+    if ARG == "variant":  # a library built with other CTA shapes (tools/ab_build.sh), copied over the product one by the caller
+        for shape in ((1024, 1024, 256), (256, 256, 4096), (512, 512, 1024)):
+            probe_2d(*shape, modes=(1, 3, 5), tag="_variant")
+    elif ARG == "quick":
+        probe_2d(1024, 1024, 32)
+        probe_1d(16384, 2048)
+    else:
+        probe_2d(1024, 1024, 256)
+        probe_2d(1024, 1024, 256, modes=(1, 3, 5), direction=1)
+        # rows of 16384 points inside a 2D plan, with and without the single-kernel row transform
+        for limit in (8192, 16384):
+            m.mufft_cuda_set_onchip_limit(limit)
+            probe_2d(16384, 256, 16, modes=(1,), tag=f"_rows16k_limit{limit}")
+        m.mufft_cuda_set_onchip_limit(8192)
+        sides = (256, 512, 1024, 2048)
+        shapes = [(512, 512), (256, 256), (2048, 2048)] + [(nx, ny) for nx in sides for ny in sides if nx != ny]
+        for nx, ny in shapes:
+            probe_2d(nx, ny, max(1, (1 << 30) // (nx * ny * 8)))
+    emit(what="done")
