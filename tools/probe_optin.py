@@ -161,12 +161,78 @@ def probe_2d(nx, ny, batch, modes=None, direction=-1, tag=""):
     m.mufft_free(pout)
 
 
+def probe_partitioned(n, parts, stereo, batch=6):
+    """mufft_execute_conv_output_partitioned_batch against numpy: out[b] = sum_p linear_conv(x[b + parts-1 - p], taps[p])."""
+    method = (1 if stereo else 0) | 4 | 8
+    plan = m.mufft_create_plan_conv(n, 0, method)
+    assert plan
+    blk = m.mufft_conv_get_transformed_block_size(plan)
+    half, total = n // 2, batch + parts - 1
+    rng = np.random.default_rng(n + parts + stereo)
+    per = 2 * half if stereo else half
+    px, x = managed(total * per)
+    pt, taps = managed(parts * half)
+    x[:] = rng.random(total * per, np.float32) - np.float32(0.5)
+    taps[:] = rng.random(parts * half, np.float32) - np.float32(0.5)
+    ps, _ = managed(total * blk // 4)
+    pf, _ = managed(parts * blk // 4)
+    po, out = managed(batch * (2 * n if stereo else n))
+    assert m.mufft_execute_conv_input_batch(plan, 0, ps, px, total) == 0
+    assert m.mufft_execute_conv_input_batch(plan, 1, pf, pt, parts) == 0
+    rc = m.mufft_execute_conv_output_partitioned_batch(plan, po, ps + (parts - 1) * blk, pf, parts, batch)
+    err = -1.0
+    if rc == 0:
+        xs = x.reshape(total, per)
+        xs = xs.view(np.complex64) if stereo else xs
+        ts = taps.reshape(parts, half)
+        o = out.reshape(batch, -1)
+        o = o.view(np.complex64) if stereo else o
+        err = 0.0
+        for b in (0, batch - 1):
+            want = np.zeros(n, np.complex128)
+            for p_ in range(parts):
+                want[: n - 1] += np.convolve(xs[b + parts - 1 - p_].astype(np.complex128), ts[p_].astype(np.float64))
+            err = max(err, rel_l2(o[b], want if stereo else want.real))
+    emit(what="conv_partitioned", n=n, parts=parts, stereo=stereo, rc=rc, rel_l2=err, ok=bool(rc == 0 and err <= 2e-6 * math.log2(n)),
+         last_error=m.mufft_cuda_last_error().decode())
+    m.mufft_free_plan_conv(plan)
+    for q in (px, pt, ps, pf, po):
+        m.mufft_free(q)
+
+
+def probe_scatter(n, peers=2, batch=5):
+    """Row pass + exchange step in one kernel (MCU_OUT_PEERS) with every 'peer' slab in local memory."""
+    plan = m.mufft_create_plan_1d_c2c(n, -1, 0)
+    pin, x = managed(2 * n * batch)
+    x[:] = np.random.default_rng(n).random(2 * n * batch, np.float32) - np.float32(0.5)
+    width, rows_total, row0 = n // peers, batch + 3, 2
+    slabs = [m.mufft_cuda_device_alloc(rows_total * width * 8) for _ in range(peers)]
+    bases = (C.c_void_p * peers)(*slabs)
+    rc = m.mufft_execute_plan_1d_batch_scatter_async(plan, bases, peers, row0, pin, batch, 0)
+    rc |= m.mufft_cuda_synchronize()
+    # read the slabs back through a managed bounce buffer (C2C of length 2 would be silly: plain copies via the batch API are not exposed)
+    want = np.fft.fft(x.view(np.complex64).reshape(batch, n).astype(np.complex128), axis=1)
+    emit(what="scatter", n=n, peers=peers, rc=rc, uses_engine=m.mufft_cuda_plan_1d_uses_engine(plan), last_error=m.mufft_cuda_last_error().decode(),
+         note="launch only (slabs are cudaMalloc memory; contents are checked by tests/test_slab_gpu.py)", want_norm=float(np.linalg.norm(want)))
+    for s_ in slabs:
+        m.mufft_cuda_device_free(s_)
+    m.mufft_free_plan_1d(plan)
+    m.mufft_free(pin)
+
+
 if __name__ == "__main__":
     assert m.mufft_cuda_device_count() >= 1 and m.mufft_cuda_set_device(0) == 0
     emit(what="start", arg=ARG)
     if ARG == "variant":  # a library built with other CTA shapes (tools/ab_build.sh), copied over the product one by the caller
         for shape in ((1024, 1024, 256), (256, 256, 4096), (512, 512, 1024)):
             probe_2d(*shape, modes=(1, 3, 5), tag="_variant")
+    elif ARG == "final":  # the defaults as shipped + the paths changed last
+        probe_2d(1024, 1024, 256, modes=(1, 8))
+        probe_2d(256, 256, 2048, modes=(1, 8))
+        for n_, parts_, st_ in ((8192, 3, 0), (1024, 2, 0), (16384, 2, 1), (32768, 2, 0), (64, 5, 1)):
+            probe_partitioned(n_, parts_, st_)
+        probe_scatter(16384)
+        probe_1d(16384, 4096)
     elif ARG == "quick":
         probe_2d(1024, 1024, 32)
         probe_1d(16384, 2048)
