@@ -106,6 +106,8 @@ struct engine_shape_t {
     int min_blocks;  // row kernels: __launch_bounds__ minimum CTAs per SM
     int pad_shift;   // one padding element per 2^pad_shift elements of the exchange area (0 = derive from radix[0])
     int packed;      // 1 = complex adds as packed FP32x2 instructions (FADD2), see caddp
+    int tw;          // twiddle mode of the kernels that do not choose one themselves: 0 = every twiddle from the
+                     // table, MUFFT_TW_DERIVE = power-of-two entries loaded, the rest derived (see engine_butterflies)
 };
 
 // Shape variants.  Variant 0 is the general one.  Variants 1 and 2 exist for the real transforms:
@@ -129,6 +131,10 @@ struct engine_shape_t {
 #ifndef MUFFT_SHAPE_PACKED
 #define MUFFT_SHAPE_PACKED 1
 #endif
+#ifndef MUFFT_SHAPE_TW
+#define MUFFT_SHAPE_TW 0
+#endif
+// -DMUFFT_TW_ALL=<mode> forces the twiddle mode of every shape (A/B measurements)
 // -DMUFFT_PACKED=<0|1> forces the packed flag of every shape (A/B measurements)
 
 // Widest radix first in variant 0: the first pass (p == 1) needs no twiddles.  Every radix divides R.
@@ -144,7 +150,7 @@ __host__ __device__ constexpr engine_shape_t engine_shape(int n, int variant = 0
         constexpr int r[] = { MUFFT_SHAPE_R0, MUFFT_SHAPE_R1, MUFFT_SHAPE_R2, MUFFT_SHAPE_R3 };
         int passes = 0, prod = 1;
         while (prod < MUFFT_SHAPE_N) prod *= r[passes++];
-        return { MUFFT_SHAPE_R, passes, { r[0], r[1], r[2], r[3] }, MUFFT_ROWS_CTA_THREADS, MUFFT_ROWS_MIN_BLOCKS, MUFFT_SHAPE_PAD, MUFFT_SHAPE_PACKED };
+        return { MUFFT_SHAPE_R, passes, { r[0], r[1], r[2], r[3] }, MUFFT_ROWS_CTA_THREADS, MUFFT_ROWS_MIN_BLOCKS, MUFFT_SHAPE_PAD, MUFFT_SHAPE_PACKED, MUFFT_SHAPE_TW };
     }
 #endif
     if (variant == MUFFT_VARIANT_MIRROR_LAST) {
@@ -195,6 +201,14 @@ __host__ __device__ constexpr bool engine_packed(int n, int v = 0)
     return MUFFT_PACKED != 0;
 #else
     return engine_shape(n, v).packed != 0;
+#endif
+}
+__host__ __device__ constexpr int engine_tw_mode(int n, int v = 0)
+{
+#ifdef MUFFT_TW_ALL
+    return MUFFT_TW_ALL;
+#else
+    return engine_shape(n, v).tw;
 #endif
 }
 __host__ __device__ constexpr int engine_num_passes(int n, int v = 0) { return engine_shape(n, v).passes; }
@@ -429,13 +443,14 @@ struct TwTree {
     }
 };
 
-template <int N, int DIR, int PASS, int V = 0, int PK = -1, int TWM = 0>
+template <int N, int DIR, int PASS, int V = 0, int PK = -1, int TWM_ = -1>
 __device__ __forceinline__ void engine_butterflies(cpx (&v)[engine_regs(N, V)], const cpx *__restrict__ tw, int t)
 {
     constexpr int R = engine_regs(N, V);
     constexpr int r = engine_radix(N, PASS, V);
     constexpr int p = engine_span(N, PASS, V);
     constexpr int NB = R / r;
+    constexpr int TWM = TWM_ < 0 ? engine_tw_mode(N, V) : TWM_; // -1 = the shape's own choice
     static_assert(NB * r == R, "every pass radix must divide the values per thread");
 #pragma unroll
     for (int u = 0; u < NB; u++) {
@@ -528,7 +543,7 @@ __device__ __forceinline__ void engine_scatter_natural(const cpx (&v)[engine_reg
 // All passes of an N-point transform.  Every thread of the transform must call this (it
 // synchronises them); SYNC_T / SLOTS say how (see engine_sync): the row kernel passes the
 // threads of one transform, the column kernel passes the whole CTA.
-template <int N, int DIR, int CS, int SYNC_T, int SLOTS, int PASS = 0, int V = 0, int PK = -1, int TWM = 0>
+template <int N, int DIR, int CS, int SYNC_T, int SLOTS, int PASS = 0, int V = 0, int PK = -1, int TWM = -1>
 __device__ __forceinline__ void engine_run(cpx (&v)[engine_regs(N, V)], cpx *sm, const cpx *__restrict__ tw, int t, int slot)
 {
     engine_butterflies<N, DIR, PASS, V, PK, TWM>(v, tw, t);
@@ -579,7 +594,7 @@ __device__ __forceinline__ void engine_gather_plane(cpx (&v)[engine_regs(N, 0)],
     }
 }
 // As engine_run, with the split exchange; `sm` holds engine_smem_elems(N) * CS floats.
-template <int N, int DIR, int CS, int SYNC_T, int SLOTS, int PASS = 0, int PK = -1, int TWM = 0>
+template <int N, int DIR, int CS, int SYNC_T, int SLOTS, int PASS = 0, int PK = -1, int TWM = -1>
 __device__ __forceinline__ void engine_run_split(cpx (&v)[engine_regs(N, 0)], float *sm, const cpx *__restrict__ tw, int t, int slot)
 {
     engine_butterflies<N, DIR, PASS, 0, PK, TWM>(v, tw, t);

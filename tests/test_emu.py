@@ -29,6 +29,16 @@ def emu():
     return C.CDLL(os.path.join(EMU_DIR, "_build", "libmufft_emu.so"), mode=os.RTLD_LOCAL)
 
 
+@pytest.fixture(scope="module", params=["table", "derived"])
+def emu_rows(request, emu):
+    """The row kernels twice: twiddles from the table (product default) and with -DMUFFT_TW_ALL=2, every
+    kernel deriving all but the power-of-two twiddles (the A/B build of tools/ab_r2.txt)."""
+    if request.param == "table":
+        return emu
+    subprocess.run(["make", "-s", "-C", EMU_DIR, "-j", str(min(8, os.cpu_count() or 1)), "BUILD=_build_derived", "EXTRA=-DMUFFT_TW_ALL=2"], check=True)
+    return C.CDLL(os.path.join(EMU_DIR, "_build_derived", "libmufft_emu.so"), mode=os.RTLD_LOCAL)
+
+
 @pytest.fixture(scope="module")
 def host():
     """Host-side helpers of the real library (pure CPU code): engine twiddle tables and the variant choice."""
@@ -91,7 +101,8 @@ ROWS_SIZES = [64, 512, 2048, 4096, 16384]
 
 @pytest.mark.parametrize("n", ROWS_SIZES)
 @pytest.mark.parametrize("direction", [-1, 1])
-def test_rows_c2c(emu, host, oracle, n, direction):
+def test_rows_c2c(emu_rows, host, oracle, n, direction):
+    emu = emu_rows
     rng = np.random.default_rng(n + direction)
     batch = 3 if n <= 4096 else 2  # 3 leaves a partly filled CTA at n = 64
     x = crnd(rng, batch, n)
@@ -101,7 +112,8 @@ def test_rows_c2c(emu, host, oracle, n, direction):
 
 
 @pytest.mark.parametrize("n", ROWS_SIZES)
-def test_rows_zero_padded(emu, host, oracle, n):
+def test_rows_zero_padded(emu_rows, host, oracle, n):
+    emu = emu_rows
     rng = np.random.default_rng(n)
     x = crnd(rng, 2, n // 2)
     got = rows(emu, host, n, -1, IN_HALF, OUT_COMPLEX, x, n)
@@ -111,8 +123,9 @@ def test_rows_zero_padded(emu, host, oracle, n):
 
 @pytest.mark.parametrize("n", ROWS_SIZES)
 @pytest.mark.parametrize("full", [False, True])
-def test_rows_r2c(emu, host, oracle, n, full):
+def test_rows_r2c(emu_rows, host, oracle, n, full):
     """Real transform of 2n points on the complex engine of length n (mirrored last pass where the shape has one)."""
+    emu = emu_rows
     rng = np.random.default_rng(2 * n + full)
     r = rnd(rng, 2, 2 * n)
     elems = 2 * n if full else n + 1
@@ -124,8 +137,9 @@ def test_rows_r2c(emu, host, oracle, n, full):
 
 @pytest.mark.parametrize("n", [512, 16384])
 @pytest.mark.parametrize("full", [False, True])
-def test_rows_zero_padded_r2c(emu, host, oracle, n, full):
+def test_rows_zero_padded_r2c(emu_rows, host, oracle, n, full):
     """Zero-padded load stage and R2C epilogue in the same kernel (2n-point real transform of n reals)."""
+    emu = emu_rows
     rng = np.random.default_rng(7 * n + full)
     r = rnd(rng, 2, n)
     elems = 2 * n if full else n + 1
@@ -160,9 +174,10 @@ def test_rows_scatter_to_peer_slabs(emu, host, n, direction):
 
 @pytest.mark.parametrize("n", [512, 16384])
 @pytest.mark.parametrize("mono", [False, True])
-def test_rows_partitioned_multiply(emu, host, oracle, n, mono):
+def test_rows_partitioned_multiply(emu_rows, host, oracle, n, mono):
     """MCU_IN_MULACC / MCU_IN_MULACC_C2R: output block b = IFFT(sum_p S[b - p] .* F[p]) / N, the load stage of
     mufft_execute_conv_output_partitioned_batch (stereo: n-point complex; mono: C2R resolve of n + 1 bins)."""
+    emu = emu_rows
     parts, batch = 3, 2
     rng = np.random.default_rng(n + 5 + mono)
     bins = n + 1 if mono else n
@@ -191,7 +206,8 @@ def test_rows_partitioned_multiply(emu, host, oracle, n, mono):
 
 
 @pytest.mark.parametrize("n", ROWS_SIZES)
-def test_rows_c2r(emu, host, oracle, n):
+def test_rows_c2r(emu_rows, host, oracle, n):
+    emu = emu_rows
     rng = np.random.default_rng(3 * n)
     spec = np.stack([oracle.r2c(rnd(rng, 2 * n)) for _ in range(2)])  # [2][n+1]
     got = rows(emu, host, n, 1, IN_C2R, OUT_COMPLEX, spec, n, rtw=resolve_twiddles(1, n))
@@ -200,8 +216,9 @@ def test_rows_c2r(emu, host, oracle, n):
 
 
 @pytest.mark.parametrize("n", [512, 16384])
-def test_rows_spectral_multiply(emu, host, n):
+def test_rows_spectral_multiply(emu_rows, host, n):
     """Load stage of mufft_execute_conv_output: norm * a .* b, then the inverse transform (ref kernel.c:22-34)."""
+    emu = emu_rows
     rng = np.random.default_rng(5 * n)
     a, f = crnd(rng, 2, n), crnd(rng, n)
     got = rows(emu, host, n, 1, IN_MUL, OUT_COMPLEX, a, n, in2=f, norm=1.0 / n)
