@@ -228,7 +228,7 @@ def test_rows_spectral_multiply(emu_rows, host, n):
 
 
 @pytest.mark.parametrize("lite", [0, 1, 2, 3])
-@pytest.mark.parametrize("nx,ny,ctas", [(256, 256, 1), (256, 256, 3), (512, 256, 2)])
+@pytest.mark.parametrize("nx,ny,ctas", [(256, 256, 1), (256, 256, 3), (512, 256, 2), (2048, 256, 2)])  # 2048: rows on named barriers
 @pytest.mark.parametrize("direction", [-1, 1])
 def test_fused_2d(emu, host, oracle, nx, ny, ctas, direction, lite):
     """The persistent fused 2D kernel with CTAs really running side by side: row tickets, lagged column
@@ -254,7 +254,8 @@ def test_fused_2d(emu, host, oracle, nx, ny, ctas, direction, lite):
     (256, 256, 3, 1, 1),    # one CTA walks every ticket alone
     (256, 256, 4, 3, 1),    # CTAs side by side, column tiles right behind their rows (deferred-copy path gets exercised)
     (256, 256, 2, 5, 2),    # lag >= batch: all rows first
-    (512, 256, 2, 2, 1),    # rectangular: different row / column tile shapes, named barriers for the rows
+    (512, 256, 2, 2, 1),    # rectangular: different row / column tile shapes
+    (2048, 256, 2, 2, 1),   # two warps per row: the plane-by-plane exchange on named barriers; 128-byte tensor boxes
     (1024, 1024, 2, 2, 1),  # the BASELINE configs[3] image shape: 64 KiB tiles, four tensor boxes per column tile
 ])
 @pytest.mark.parametrize("direction", [-1, 1])
