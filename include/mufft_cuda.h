@@ -149,6 +149,12 @@ void mufft_cuda_set_fused_2d(int mode);
  * the two.  Same results either way.  MUFFT_CUDA_ONCHIP_LIMIT in the environment sets the initial value. */
 void mufft_cuda_set_onchip_limit(unsigned n);
 unsigned mufft_cuda_get_onchip_limit(void);
+/* Row transforms of 32768 and 65536 points, for plans created afterwards: 1 = ONE kernel on a
+ * thread-block cluster of 2 / 4 CTAs (512 threads each, the transform in registers, exchange through
+ * distributed shared memory), 0 (default until measured on the GPU) = the two-kernel split.  Plain and
+ * zero-padded C2C and the scatter epilogue of the slab exchange; real transforms of these lengths keep
+ * the two-kernel path.  Same results either way.  MUFFT_CUDA_CLUSTER_ROWS sets the initial value. */
+void mufft_cuda_set_cluster_rows(int enable);
 /* Transform lengths beyond the single-kernel limit, up to 2097152: 1 (default) = two kernels (N = N1*N2: column transforms, then
  * twiddle + row transforms with a transposed store), 0 = one generic radix pass per kernel. */
 void mufft_cuda_set_two_kernel(int enable);

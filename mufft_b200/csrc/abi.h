@@ -206,6 +206,10 @@ int mcu_prefetch(const void *ptr, size_t bytes, int to_device, void *stream);
 
 /* ---- kernels ------------------------------------------------------------------------------ */
 int mcu_launch_rows(const mcu_rows_args *args, void *stream);
+/* Row transforms of 32768 / 65536 points on a thread-block cluster (rowsc_kernel.cuh): in_mode COMPLEX or
+ * HALF, out_mode COMPLEX or PEERS, args->tw = the engine table of n (variant 0). */
+int mcu_rows_cluster_supported(unsigned n);
+int mcu_launch_rows_cluster(const mcu_rows_args *args, void *stream);
 int mcu_launch_cols(const mcu_cols_args *args, void *stream);
 int mcu_launch_pass(const mcu_pass_args *args, void *stream);
 /* n2 of the two-kernel split of n for a row (columns = 0) or column (columns = 1) transform

@@ -37,6 +37,8 @@ MUFFT_F2D_SHAPES(MUFFT_DECLARE_F2D)
 cudaError_t rowst_launch_256(const mcu_rowst_args &, cudaStream_t);
 cudaError_t rowst_launch_512(const mcu_rowst_args &, cudaStream_t);
 cudaError_t rowst_launch_1024(const mcu_rowst_args &, cudaStream_t);
+cudaError_t rowsc_launch_32768(const mcu_rows_args &, cudaStream_t);
+cudaError_t rowsc_launch_65536(const mcu_rows_args &, cudaStream_t);
 
 static std::atomic<unsigned long long> g_launches{0};
 
@@ -153,6 +155,8 @@ static void fill_table_variant(float *table, int direction, int variant)
     X(2) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192)
 // row kernels also exist for MCU_ENGINE_BIG_N
 #define MUFFT_FOR_ENGINE_SIZES(X) MUFFT_FOR_CONV_SIZES(X) X(16384)
+// lengths with an engine twiddle table: the above and the cluster shapes (rowsc_kernel.cuh)
+#define MUFFT_FOR_TABLE_SIZES(X) MUFFT_FOR_ENGINE_SIZES(X) X(32768) X(65536)
 
 } // namespace mufft
 
@@ -268,7 +272,7 @@ size_t mcu_engine_table_size(unsigned n, int variant)
 {
     switch (n) {
 #define X(v) case v: return (size_t)(variant == 1 ? engine_tw_total(v, 1) : variant == 2 ? engine_tw_total(v, 2) : engine_tw_total(v, 0)) + 1;
-        MUFFT_FOR_ENGINE_SIZES(X)
+        MUFFT_FOR_TABLE_SIZES(X)
 #undef X
     default: return 0;
     }
@@ -278,7 +282,7 @@ void mcu_engine_table_fill(float *table, unsigned n, int direction, int variant)
 {
     switch (n) {
 #define X(v) case v: fill_table_variant<v>(table, direction, variant); break;
-        MUFFT_FOR_ENGINE_SIZES(X)
+        MUFFT_FOR_TABLE_SIZES(X)
 #undef X
     default: break;
     }
@@ -293,6 +297,18 @@ int mcu_launch_rows(const mcu_rows_args *a, void *stream)
 #define X(v) case v: return (int)(a->direction < 0 ? rows_launch_##v##_fwd(*a, s) : rows_launch_##v##_inv(*a, s));
         MUFFT_FOR_ENGINE_SIZES(X)
 #undef X
+    default: return (int)cudaErrorInvalidValue;
+    }
+}
+
+int mcu_rows_cluster_supported(unsigned n) { return n == 32768 || n == 65536; }
+
+int mcu_launch_rows_cluster(const mcu_rows_args *a, void *stream)
+{
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    switch (a->n) {
+    case 32768: return (int)rowsc_launch_32768(*a, (cudaStream_t)stream);
+    case 65536: return (int)rowsc_launch_65536(*a, (cudaStream_t)stream);
     default: return (int)cudaErrorInvalidValue;
     }
 }

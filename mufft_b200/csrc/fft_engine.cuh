@@ -191,6 +191,10 @@ __host__ __device__ constexpr engine_shape_t engine_shape(int n, int variant = 0
     // thread) and 132 KiB of exchange area: one CTA per SM.  Opt-in until measured (abi.h:
     // MCU_ENGINE_BIG_N); the default for this length is the two-kernel split.
     case 16384: return { 32, 3, { 32, 32, 16, 1 }, 512, 1, 0, 0 };
+    // Thread-block cluster shapes (rowsc_kernel.cuh): 2 / 4 CTAs of 512 threads per transform, exchange
+    // through distributed shared memory.  Not usable by the single-CTA kernels.
+    case 32768: return { 32, 3, { 32, 32, 32, 1 }, 512, 1, 5, 0 };
+    case 65536: return { 32, 4, { 32, 32, 32, 2 }, 512, 1, 5, 0 };
     default: return { 0, 0, { 1, 1, 1, 1 }, 256, 1, 0, 1 };
     }
 }

@@ -76,6 +76,8 @@ __attribute__((constructor)) static void read_env(void)
     if (e != NULL) g_prefetch = e[0] == '1';
     e = getenv("MUFFT_CUDA_ONCHIP_LIMIT");
     if (e != NULL) g_onchip_limit = atoi(e) >= MCU_ENGINE_BIG_N ? MCU_ENGINE_BIG_N : MCU_ENGINE_MAX_N;
+    e = getenv("MUFFT_CUDA_CLUSTER_ROWS");
+    if (e != NULL) mufft_cuda_set_cluster_rows(atoi(e));
     e = getenv("MUFFT_CUDA_FUSED_2D");
     if (e != NULL) mufft_cuda_set_fused_2d(atoi(e));
     e = getenv("MUFFT_CUDA_L2_CHUNK_MB");
@@ -88,6 +90,11 @@ __attribute__((constructor)) static void read_env(void)
     if (e != NULL && atoi(e) >= 1 && atoi(e) <= 1024) g_stage_chunk_bytes = (size_t)atoi(e) << 20;
 }
 void mufft_cuda_set_prefetch(int enable) { g_prefetch = enable != 0; }
+/* Row transforms of 32768 / 65536 points: 1 = one kernel on a thread-block cluster of 2 / 4 CTAs with the
+ * exchange through distributed shared memory (rowsc_kernel.cuh; plans created afterwards, plain and
+ * zero-padded C2C and the scatter epilogue), 0 (default until measured on the GPU) = the two-kernel split. */
+static int g_cluster_rows = 0;
+void mufft_cuda_set_cluster_rows(int enable) { g_cluster_rows = enable != 0; }
 /* Lengths above MCU_ENGINE_MAX_N: 1 (default) = two kernels (column transforms of length N1, then
  * twiddle + row transforms of length N2 with a transposed store), 0 = one generic pass per radix. */
 static int g_two_kernel = 1;
@@ -190,6 +197,7 @@ typedef struct axis {
     unsigned n;
     int direction;
     void *d_engine_tw; /* engine table: non-NULL = row transforms of this axis run in one kernel */
+    void *d_cluster_tw; /* engine table of the cluster shape (32768 / 65536 points), or NULL: rowsc_kernel.cuh */
     void *d_engine_tw_real; /* table of the mirrored-pass shape the R2C (forward) / C2R (inverse) row kernel uses, or NULL */
     void *d_roots;     /* exp(dir*2*pi*i*j/n), j < n: generic multi-pass kernels, two-kernel split */
     unsigned n1, n2;   /* two-kernel split n = n1 * n2 (0 = not used) */
@@ -202,6 +210,7 @@ static void axis_free(axis *ax)
 {
     mcu_free(ax->d_engine_tw);
     mcu_free(ax->d_engine_tw_real);
+    mcu_free(ax->d_cluster_tw);
     mcu_free(ax->d_roots);
     mcu_free(ax->d_tw_n1);
     mcu_free(ax->d_tw_n2);
@@ -237,6 +246,10 @@ static int axis_init(axis *ax, unsigned n, int direction, int want_generic)
             ax->d_engine_tw_real = make_engine_table(n, direction, variant);
             if (!ax->d_engine_tw_real) return -1;
         }
+    }
+    if (want_generic == AXIS_ROWS && g_cluster_rows && mcu_rows_cluster_supported(n)) {
+        ax->d_cluster_tw = make_engine_table(n, direction, 0);
+        if (!ax->d_cluster_tw) return -1;
     }
     if (want_generic && mcu_split_n2(n, columns) != 0) { /* rows use it above MCU_ENGINE_MAX_N, columns above MCU_COLS_MAX_N */
         ax->n2 = mcu_split_n2(n, columns);
@@ -581,6 +594,19 @@ static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode
         if (out_mode == MCU_OUT_PEERS) a.peers = *tls_peers;
         if (pd != NULL) { a.parts = pd->parts; a.in_part_stride = pd->in_step; a.in2_part_stride = pd->in2_step; }
         return mcu_launch_rows(&a, stream);
+    }
+    if (ax->d_cluster_tw != NULL && ((out_mode == MCU_OUT_COMPLEX && (in_mode == MCU_IN_COMPLEX || in_mode == MCU_IN_HALF)) ||
+                                     (out_mode == MCU_OUT_PEERS && in_mode == MCU_IN_COMPLEX))) {
+        /* one kernel on a thread-block cluster; the real transforms and the spectral multiply of these
+         * lengths keep the resolve kernels + two-kernel path below */
+        mcu_rows_args a;
+        memset(&a, 0, sizeof(a));
+        a.out = out; a.in = in; a.tw = ax->d_cluster_tw;
+        a.out_stride = out_stride; a.in_stride = in_stride;
+        a.batch = batch; a.n = n; a.direction = ax->direction;
+        a.in_mode = in_mode; a.out_mode = out_mode; a.norm = norm;
+        if (out_mode == MCU_OUT_PEERS) a.peers = *tls_peers;
+        return mcu_launch_rows_cluster(&a, stream);
     }
     if (out_mode == MCU_OUT_PEERS && !(ax->n2 != 0 && g_two_kernel)) {
         snprintf(tls_error, sizeof(tls_error), "scatter: this length has no two-kernel path");

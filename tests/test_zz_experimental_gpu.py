@@ -1,0 +1,69 @@
+"""GPU tests of paths that are validated on the CPU emulation (tests/test_emu.py) but have not run
+on hardware yet.  They are skipped unless MUFFT_TEST_EXPERIMENTAL=1, so that the suite the driver
+runs only contains paths with hardware evidence; tools/probe_optin.py runs the same checks without
+torch in a few seconds under gpurun.  Move a test into the regular files once its path has passed here.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("MUFFT_TEST_EXPERIMENTAL") != "1", reason="set MUFFT_TEST_EXPERIMENTAL=1 to run")]
+
+
+def tol(n):
+    return 1e-6 * math.log2(n)
+
+
+@pytest.fixture(scope="module")
+def m():
+    import mufft_b200
+    assert mufft_b200.mufft_cuda_device_count() >= 1
+    return mufft_b200
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    return torch
+
+
+@pytest.mark.parametrize("n", [32768, 65536])
+def test_cluster_rows(m, torch, oracle, n):
+    """mufft_cuda_set_cluster_rows(1): 32768 / 65536-point rows in one kernel on a cluster of 2 / 4 CTAs."""
+    batch = 301
+    g = torch.Generator(device="cuda")
+    g.manual_seed(n)
+    x = torch.rand((batch, 2 * n), dtype=torch.float32, device="cuda", generator=g) - 0.5
+    xc = torch.view_as_complex(x.view(batch, n, 2))
+    m.mufft_cuda_set_cluster_rows(1)
+    try:
+        for direction in (-1, 1):
+            plan = m.mufft_create_plan_1d_c2c(n, direction, 0)
+            y = torch.zeros_like(x)
+            m.mufft_cuda_launch_count(1)
+            assert m.mufft_execute_plan_1d_batch(plan, y.data_ptr(), x.data_ptr(), batch, 0, 0) == 0, m.mufft_cuda_last_error()
+            assert m.mufft_cuda_launch_count(1) == 1
+            m.mufft_free_plan_1d(plan)
+            ref = torch.fft.fft(xc, dim=1) if direction < 0 else torch.fft.ifft(xc, dim=1, norm="forward")
+            yc = torch.view_as_complex(y.view(batch, n, 2))
+            err = (torch.linalg.vector_norm(yc - ref, dim=1) / torch.linalg.vector_norm(ref, dim=1)).max().item()
+            assert err <= tol(n)
+            got = yc[batch - 1].cpu().numpy()
+            want = oracle.c2c(xc[batch - 1].cpu().numpy(), direction)
+            assert float(np.linalg.norm(got - want) / np.linalg.norm(want)) <= tol(n)
+        # zero-padded forward transform
+        plan = m.mufft_create_plan_1d_c2c(n, -1, m.MUFFT_FLAG_ZERO_PAD_UPPER_HALF)
+        xh = x[:, :n].contiguous()
+        y = torch.zeros_like(x)
+        assert m.mufft_execute_plan_1d_batch(plan, y.data_ptr(), xh.data_ptr(), batch, 0, 0) == 0
+        m.mufft_free_plan_1d(plan)
+        xp = torch.zeros((batch, n), dtype=torch.complex64, device="cuda")
+        xp[:, : n // 2] = torch.view_as_complex(xh.view(batch, n // 2, 2))
+        ref = torch.fft.fft(xp, dim=1)
+        yc = torch.view_as_complex(y.view(batch, n, 2))
+        assert (torch.linalg.vector_norm(yc - ref) / torch.linalg.vector_norm(ref)).item() <= tol(n)
+    finally:
+        m.mufft_cuda_set_cluster_rows(0)

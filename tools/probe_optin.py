@@ -233,6 +233,28 @@ if __name__ == "__main__":
             probe_partitioned(n_, parts_, st_)
         probe_scatter(16384)
         probe_1d(16384, 4096)
+    elif ARG == "cluster":  # 32768 / 65536-point rows: two-kernel split vs one kernel on a thread-block cluster
+        for n_ in (32768, 65536):
+            batch_ = (1 << 31) // (8 * n_)
+            pin, x = managed(2 * n_ * batch_)
+            pout, y = managed(2 * n_ * batch_)
+            fill(x, n_, 2 * n_)
+            xc, yc = x.view(np.complex64).reshape(batch_, n_), y.view(np.complex64).reshape(batch_, n_)
+            for cluster in (0, 1, 0, 1):
+                m.mufft_cuda_set_cluster_rows(cluster)
+                for direction in (-1, 1):
+                    plan = m.mufft_create_plan_1d_c2c(n_, direction, 0)
+                    m.mufft_cuda_launch_count(1)
+                    ms = timed(lambda: m.mufft_execute_plan_1d_batch(plan, pout, pin, batch_, 0, 0), 5)
+                    launches = m.mufft_cuda_launch_count(1) / 7
+                    f1 = (lambda z: np.fft.fft(z)) if direction < 0 else (lambda z: np.fft.ifft(z, norm="forward"))
+                    err = max(rel_l2(yc[b], f1(xc[b].astype(np.complex128))) for b in (0, batch_ - 1))
+                    emit(what="c2c1d_cluster", n=n_, batch=batch_, direction=direction, cluster_rows=cluster, launches_per_call=launches, ms=round(ms, 4),
+                         gbs=round(16 * n_ * batch_ / ms / 1e6, 1), rel_l2=err, ok=bool(err <= 1e-6 * math.log2(n_)), last_error=m.mufft_cuda_last_error().decode())
+                    m.mufft_free_plan_1d(plan)
+            m.mufft_cuda_set_cluster_rows(0)
+            m.mufft_free(pin)
+            m.mufft_free(pout)
     elif ARG == "quick":
         probe_2d(1024, 1024, 32)
         probe_1d(16384, 2048)
