@@ -151,10 +151,12 @@ void mufft_cuda_set_onchip_limit(unsigned n);
 unsigned mufft_cuda_get_onchip_limit(void);
 /* Row transforms of 32768 and 65536 points, for plans created afterwards: 1 = ONE kernel on a
  * thread-block cluster of 2 / 4 CTAs (512 threads each, the transform in registers, exchange through
- * distributed shared memory), 0 (default until measured on the GPU) = the two-kernel split.  Plain and
+ * distributed shared memory: 1 = remote stores + release / acquire cluster barriers, 2 = st.async
+ * remote stores counted on an mbarrier of the receiving CTA), 0 (default until measured on the GPU) =
+ * the two-kernel split.  Plain and
  * zero-padded C2C and the scatter epilogue of the slab exchange; real transforms of these lengths keep
  * the two-kernel path.  Same results either way.  MUFFT_CUDA_CLUSTER_ROWS sets the initial value. */
-void mufft_cuda_set_cluster_rows(int enable);
+void mufft_cuda_set_cluster_rows(int mode);
 /* Transform lengths beyond the single-kernel limit, up to 2097152: 1 (default) = two kernels (N = N1*N2: column transforms, then
  * twiddle + row transforms with a transposed store), 0 = one generic radix pass per kernel. */
 void mufft_cuda_set_two_kernel(int enable);

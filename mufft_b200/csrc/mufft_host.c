@@ -94,7 +94,7 @@ void mufft_cuda_set_prefetch(int enable) { g_prefetch = enable != 0; }
  * exchange through distributed shared memory (rowsc_kernel.cuh; plans created afterwards, plain and
  * zero-padded C2C and the scatter epilogue), 0 (default until measured on the GPU) = the two-kernel split. */
 static int g_cluster_rows = 0;
-void mufft_cuda_set_cluster_rows(int enable) { g_cluster_rows = enable != 0; }
+void mufft_cuda_set_cluster_rows(int mode) { g_cluster_rows = mode <= 0 ? 0 : (mode >= 2 ? 2 : 1); }
 /* Lengths above MCU_ENGINE_MAX_N: 1 (default) = two kernels (column transforms of length N1, then
  * twiddle + row transforms of length N2 with a transposed store), 0 = one generic pass per radix. */
 static int g_two_kernel = 1;
@@ -605,6 +605,7 @@ static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode
         a.out_stride = out_stride; a.in_stride = in_stride;
         a.batch = batch; a.n = n; a.direction = ax->direction;
         a.in_mode = in_mode; a.out_mode = out_mode; a.norm = norm;
+        a.prefetch = g_cluster_rows == 2; /* flavour: st.async + mbarrier exchange */
         if (out_mode == MCU_OUT_PEERS) a.peers = *tls_peers;
         return mcu_launch_rows_cluster(&a, stream);
     }

@@ -9,14 +9,14 @@
 
 namespace mufft {
 
-template <int DIR, int IN_MODE, int OUT_MODE>
+template <int DIR, int IN_MODE, int OUT_MODE, bool ASYNC>
 static cudaError_t launch(const mcu_rows_args &a, cudaStream_t stream)
 {
     constexpr int N = ROWSC_N;
     constexpr int CL = rowsc_cluster(N);
     static_assert(rowsc_supported(N), "no cluster shape for this length");
     static int clusters = 0; // per instantiation
-    auto kernel = fft_rows_cluster_kernel<N, DIR, IN_MODE, OUT_MODE>;
+    auto kernel = fft_rows_cluster_kernel<N, DIR, IN_MODE, OUT_MODE, ASYNC>;
     if (clusters == 0) {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rowsc_smem_bytes());
         if (err != cudaSuccess) return err;
@@ -46,9 +46,12 @@ template <int DIR>
 static cudaError_t launch_dir(const mcu_rows_args &a, cudaStream_t stream)
 {
     switch (a.in_mode * 8 + a.out_mode) {
-    case MCU_IN_COMPLEX * 8 + MCU_OUT_COMPLEX: return launch<DIR, MCU_IN_COMPLEX, MCU_OUT_COMPLEX>(a, stream);
-    case MCU_IN_COMPLEX * 8 + MCU_OUT_PEERS: return launch<DIR, MCU_IN_COMPLEX, MCU_OUT_PEERS>(a, stream);
-    case MCU_IN_HALF * 8 + MCU_OUT_COMPLEX: return launch<DIR, MCU_IN_HALF, MCU_OUT_COMPLEX>(a, stream);
+    // args.prefetch doubles as the flavour switch here: 1 = st.async + mbarrier exchange
+#define MUFFT_ROWSC_CASE(im, om) case im * 8 + om: return a.prefetch ? launch<DIR, im, om, true>(a, stream) : launch<DIR, im, om, false>(a, stream);
+        MUFFT_ROWSC_CASE(MCU_IN_COMPLEX, MCU_OUT_COMPLEX)
+        MUFFT_ROWSC_CASE(MCU_IN_COMPLEX, MCU_OUT_PEERS)
+        MUFFT_ROWSC_CASE(MCU_IN_HALF, MCU_OUT_COMPLEX)
+#undef MUFFT_ROWSC_CASE
     default: return cudaErrorInvalidValue;
     }
 }

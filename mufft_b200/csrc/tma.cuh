@@ -28,7 +28,13 @@ struct alignas(64) tensor_map_t {
 // Only the issuing thread touches the high half; copies are synchronous, so a phase completes
 // inside the last tma_load_* of its expect_tx.
 __device__ __forceinline__ void tma_mbar_init(uint64_t *bar, uint32_t) { __atomic_store_n(bar, 0ull, __ATOMIC_SEQ_CST); }
-__device__ __forceinline__ void tma_mbar_expect_tx(uint64_t *bar, uint32_t bytes) { __atomic_fetch_add(bar, (uint64_t)bytes << 32, __ATOMIC_SEQ_CST); }
+// (bytes may be completed by other threads BEFORE the expectation is posted - remote st.async
+// senders of rowsc_kernel.cuh -: whichever operation brings the pending count to zero ends the phase)
+__device__ __forceinline__ void tma_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    const uint64_t now = __atomic_add_fetch(bar, (uint64_t)bytes << 32, __ATOMIC_SEQ_CST);
+    if ((now >> 32) == 0) __atomic_fetch_add(bar, 1ull, __ATOMIC_SEQ_CST);
+}
 __device__ __forceinline__ void emu_tx_done(uint64_t *bar, uint32_t bytes)
 {
     const uint64_t left = __atomic_sub_fetch(bar, (uint64_t)bytes << 32, __ATOMIC_SEQ_CST);

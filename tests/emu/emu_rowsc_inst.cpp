@@ -13,21 +13,25 @@ template <int DIR, int IN_MODE, int OUT_MODE>
 int run(const mcu_rows_args &a, unsigned clusters)
 {
     constexpr int CL = rowsc_cluster(EMU_N);
-    emu::launch(emu::idx3{ clusters * CL, 1, 1 }, MUFFT_ROWSC_THREADS, rowsc_smem_bytes(), CL, CL,
-                [&] { fft_rows_cluster_kernel<EMU_N, DIR, IN_MODE, OUT_MODE>(a); });
+    if (a.prefetch) // st.async + mbarrier flavour
+        emu::launch(emu::idx3{ clusters * CL, 1, 1 }, MUFFT_ROWSC_THREADS, rowsc_smem_bytes(), CL, CL,
+                    [&] { fft_rows_cluster_kernel<EMU_N, DIR, IN_MODE, OUT_MODE, true>(a); });
+    else
+        emu::launch(emu::idx3{ clusters * CL, 1, 1 }, MUFFT_ROWSC_THREADS, rowsc_smem_bytes(), CL, CL,
+                    [&] { fft_rows_cluster_kernel<EMU_N, DIR, IN_MODE, OUT_MODE, false>(a); });
     return 0;
 }
 } // namespace
 
 // out_mode: 0 = complex rows, 3 = scatter over `peers` slabs (bases/shift/row0/pitch as mcu_peer_dest)
 extern "C" int EMU_CAT(emu_rows_cluster_, EMU_N)(int direction, int in_mode, int out_mode, void *out, const void *in, const void *tw,
-                                                 size_t out_stride, size_t in_stride, size_t batch, unsigned clusters,
+                                                 size_t out_stride, size_t in_stride, size_t batch, unsigned clusters, int async_flavour,
                                                  void *const *bases, unsigned peers, unsigned shift, size_t row0, size_t pitch)
 {
     mcu_rows_args a;
     memset(&a, 0, sizeof(a));
     a.out = out; a.in = in; a.tw = tw; a.out_stride = out_stride; a.in_stride = in_stride; a.batch = batch;
-    a.n = EMU_N; a.direction = direction; a.in_mode = in_mode; a.out_mode = out_mode; a.norm = 1.0f;
+    a.n = EMU_N; a.direction = direction; a.in_mode = in_mode; a.out_mode = out_mode; a.norm = 1.0f; a.prefetch = async_flavour;
     for (unsigned p = 0; p < peers && p < MCU_MAX_PEERS; p++) a.peers.base[p] = bases[p];
     a.peers.shift = shift; a.peers.row0 = row0; a.peers.pitch = pitch;
     if (in_mode == MCU_IN_COMPLEX && out_mode == MCU_OUT_COMPLEX)

@@ -283,13 +283,15 @@ def test_fused_2d_tma(emu, host, oracle, nx, ny, batch, ctas, lag, direction, li
 
 @pytest.mark.parametrize("n", [32768, 65536])
 @pytest.mark.parametrize("case", ["fwd", "inv", "zero_pad", "peers"])
-def test_rows_on_a_cluster(emu, host, oracle, n, case):
+@pytest.mark.parametrize("flavour", [0, 1])
+def test_rows_on_a_cluster(emu, host, oracle, n, case, flavour):
     """rowsc_kernel.cuh: one transform per cluster of 2 (32768) or 4 (65536) CTAs, exchange through
     distributed shared memory; three transforms over two clusters, so that the per-cluster loop and its
-    barriers between consecutive transforms are exercised too."""
+    barriers between consecutive transforms are exercised too.  flavour 1 = st.async remote stores counted on
+    an mbarrier of the receiving CTA instead of release / acquire cluster barriers."""
     fn = getattr(emu, f"emu_rows_cluster_{n}")
     fn.restype = C.c_int
-    fn.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, vp, sz, sz, sz, C.c_uint, C.POINTER(C.c_void_p), C.c_uint, C.c_uint, sz, sz]
+    fn.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, vp, sz, sz, sz, C.c_uint, C.c_int, C.POINTER(C.c_void_p), C.c_uint, C.c_uint, sz, sz]
     direction = 1 if case == "inv" else -1
     batch, clusters = 3, 2
     rng = np.random.default_rng(n + len(case))
@@ -298,7 +300,7 @@ def test_rows_on_a_cluster(emu, host, oracle, n, case):
     if case == "zero_pad":
         x = crnd(rng, batch, n // 2)
         out = np.full((batch, n), np.nan, np.complex64)
-        assert fn(direction, IN_HALF, OUT_COMPLEX, out.ctypes.data, x.ctypes.data, tw.ctypes.data, n, n // 2, batch, clusters, no_peers, 0, 0, 0, 0) == 0
+        assert fn(direction, IN_HALF, OUT_COMPLEX, out.ctypes.data, x.ctypes.data, tw.ctypes.data, n, n // 2, batch, clusters, flavour, no_peers, 0, 0, 0, 0) == 0
         xp = np.zeros((batch, n), np.complex128)
         xp[:, : n // 2] = x
         want = np.fft.fft(xp, axis=1)
@@ -310,12 +312,12 @@ def test_rows_on_a_cluster(emu, host, oracle, n, case):
             width = n // peers
             slabs = [np.full((rows_total, width), np.nan, np.complex64) for _ in range(peers)]
             bases = (C.c_void_p * peers)(*[s_.ctypes.data for s_ in slabs])
-            assert fn(direction, IN_COMPLEX, 3, None, x.ctypes.data, tw.ctypes.data, 0, n, batch, clusters, bases, peers, int(math.log2(width)), row0, width) == 0
+            assert fn(direction, IN_COMPLEX, 3, None, x.ctypes.data, tw.ctypes.data, 0, n, batch, clusters, flavour, bases, peers, int(math.log2(width)), row0, width) == 0
             out = np.concatenate([s_[row0:row0 + batch] for s_ in slabs], axis=1)
             assert all(np.all(np.isnan(s_[:row0].real)) and np.all(np.isnan(s_[row0 + batch:].real)) for s_ in slabs)
         else:
             out = np.full((batch, n), np.nan, np.complex64)
-            assert fn(direction, IN_COMPLEX, OUT_COMPLEX, out.ctypes.data, x.ctypes.data, tw.ctypes.data, n, n, batch, clusters, no_peers, 0, 0, 0, 0) == 0
+            assert fn(direction, IN_COMPLEX, OUT_COMPLEX, out.ctypes.data, x.ctypes.data, tw.ctypes.data, n, n, batch, clusters, flavour, no_peers, 0, 0, 0, 0) == 0
     for b in range(batch):
         assert cpu_libs.rel_l2(out[b], want[b]) <= tol(n)
     if case in ("fwd", "inv"):
