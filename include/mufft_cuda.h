@@ -149,6 +149,10 @@ void mufft_cuda_set_fused_2d(int mode);
  * the two.  Same results either way.  MUFFT_CUDA_ONCHIP_LIMIT in the environment sets the initial value. */
 void mufft_cuda_set_onchip_limit(unsigned n);
 unsigned mufft_cuda_get_onchip_limit(void);
+/* Latency of synchronous calls on small transforms (one launch + one synchronise per
+ * mufft_execute_plan_1d call): 1 = the library busy-polls the stream instead of blocking in the driver
+ * when a call touches at most 1 MiB; 0 (default until measured).  MUFFT_CUDA_SPIN_SYNC sets the initial value. */
+void mufft_cuda_set_spin_sync(int enable);
 /* Row transforms of 32768 and 65536 points, for plans created afterwards: 1 = ONE kernel on a
  * thread-block cluster of 2 / 4 CTAs (512 threads each, the transform in registers, exchange through
  * distributed shared memory: 1 = remote stores + release / acquire cluster barriers, 2 = st.async

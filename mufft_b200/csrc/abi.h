@@ -195,6 +195,7 @@ int mcu_pointer_kind(const void *ptr);
 int mcu_stream_create(void **stream);
 int mcu_stream_destroy(void *stream);
 int mcu_stream_sync(void *stream);
+int mcu_stream_sync_spin(void *stream); /* same, busy-polling cudaStreamQuery */
 int mcu_event_create(void **event);
 int mcu_event_destroy(void *event);
 int mcu_event_record(void *event, void *stream);

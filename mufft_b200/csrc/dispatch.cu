@@ -224,6 +224,15 @@ int mcu_stream_create(void **stream)
 }
 int mcu_stream_destroy(void *stream) { return stream ? (int)cudaStreamDestroy((cudaStream_t)stream) : 0; }
 int mcu_stream_sync(void *stream) { return (int)cudaStreamSynchronize((cudaStream_t)stream); }
+// Busy-polls the stream instead of blocking in the driver: for work of a few microseconds the
+// wake-up of a blocking synchronise costs more than the work.
+int mcu_stream_sync_spin(void *stream)
+{
+    cudaError_t err;
+    while ((err = cudaStreamQuery((cudaStream_t)stream)) == cudaErrorNotReady) {
+    }
+    return (int)err;
+}
 int mcu_event_create(void **event)
 {
     cudaEvent_t e;

@@ -76,6 +76,8 @@ __attribute__((constructor)) static void read_env(void)
     if (e != NULL) g_prefetch = e[0] == '1';
     e = getenv("MUFFT_CUDA_ONCHIP_LIMIT");
     if (e != NULL) g_onchip_limit = atoi(e) >= MCU_ENGINE_BIG_N ? MCU_ENGINE_BIG_N : MCU_ENGINE_MAX_N;
+    e = getenv("MUFFT_CUDA_SPIN_SYNC");
+    if (e != NULL) mufft_cuda_set_spin_sync(atoi(e));
     e = getenv("MUFFT_CUDA_CLUSTER_ROWS");
     if (e != NULL) mufft_cuda_set_cluster_rows(atoi(e));
     e = getenv("MUFFT_CUDA_FUSED_2D");
@@ -90,6 +92,12 @@ __attribute__((constructor)) static void read_env(void)
     if (e != NULL && atoi(e) >= 1 && atoi(e) <= 1024) g_stage_chunk_bytes = (size_t)atoi(e) << 20;
 }
 void mufft_cuda_set_prefetch(int enable) { g_prefetch = enable != 0; }
+/* Synchronous executes that touch at most SPIN_SYNC_BYTES of device-visible memory (the fft.h calls on
+ * single small transforms, BASELINE configs[0]): 1 = busy-poll the stream instead of blocking in
+ * cudaStreamSynchronize (latency path; off until measured). */
+static int g_spin_sync = 0;
+#define SPIN_SYNC_BYTES ((size_t)1 << 20)
+void mufft_cuda_set_spin_sync(int enable) { g_spin_sync = enable != 0; }
 /* Row transforms of 32768 / 65536 points: 1 = one kernel on a thread-block cluster of 2 / 4 CTAs with the
  * exchange through distributed shared memory (rowsc_kernel.cuh; plans created afterwards, plain and
  * zero-padded C2C and the scatter epilogue), 0 (default until measured on the GPU) = the two-kernel split. */
@@ -413,7 +421,10 @@ static int run_any(stage *st, unit_launch fn, void *ctx, const io_desc *io, int 
 
     if (vis_in && vis_out && vis_in2) {
         TRY(fn(ctx, io->out, io->out_stride, io->in, io->in_stride, io->in2, io->in2_stride, io->count, tls_stream));
-        if (!async) TRY(mcu_stream_sync(tls_stream));
+        if (!async) {
+            if (g_spin_sync && span_in + span_out <= SPIN_SYNC_BYTES) TRY(mcu_stream_sync_spin(tls_stream));
+            else TRY(mcu_stream_sync(tls_stream));
+        }
         return 0;
     }
     if (async) {

@@ -233,6 +233,22 @@ if __name__ == "__main__":
             probe_partitioned(n_, parts_, st_)
         probe_scatter(16384)
         probe_1d(16384, 4096)
+    elif ARG == "latency":  # BASELINE configs[0] as the reference runs it: one 64-point transform per fft.h call
+        plan = m.mufft_create_plan_1d_c2c(64, -1, 0)
+        pin, x = managed(128)
+        pout, y = managed(128)
+        x[:] = np.random.default_rng(0).random(128, np.float32) - np.float32(0.5)
+        for spin in (0, 1, 0, 1):
+            m.mufft_cuda_set_spin_sync(spin)
+            for _ in range(500):
+                m.mufft_execute_plan_1d(plan, pout, pin)
+            t0 = time.perf_counter()
+            for _ in range(20000):
+                m.mufft_execute_plan_1d(plan, pout, pin)
+            us = (time.perf_counter() - t0) / 20000 * 1e6
+            err = rel_l2(y.view(np.complex64), np.fft.fft(x.view(np.complex64).astype(np.complex128)))
+            emit(what="single_call_latency", n=64, spin_sync=spin, us_per_call=round(us, 3), rel_l2=err, ok=bool(err < 6e-6))
+        m.mufft_cuda_set_spin_sync(0)
     elif ARG == "cluster":  # 32768 / 65536-point rows: two-kernel split vs one kernel on a thread-block cluster
         for n_ in (32768, 65536):
             batch_ = (1 << 31) // (8 * n_)
