@@ -149,6 +149,12 @@ void mufft_cuda_set_fused_2d(int mode);
  * the two.  Same results either way.  MUFFT_CUDA_ONCHIP_LIMIT in the environment sets the initial value. */
 void mufft_cuda_set_onchip_limit(unsigned n);
 unsigned mufft_cuda_get_onchip_limit(void);
+/* 2D R2C plans whose row transforms have 256..2048 complex points (Nx = 512..4096 reals) and 256..2048
+ * rows: 1 = the fused persistent kernel (real row transforms with the resolve epilogue straight into
+ * the output, column transforms in place, intermediate kept in L2), 0 (default until measured on the
+ * GPU) = row kernel + column kernel through plan scratch.  Same results either way.
+ * MUFFT_CUDA_FUSED_2D_REAL sets the initial value. */
+void mufft_cuda_set_fused_2d_real(int enable);
 /* Latency of synchronous calls on small transforms (one launch + one synchronise per
  * mufft_execute_plan_1d call): 1 = the library busy-polls the stream instead of blocking in the driver
  * when a call touches at most 1 MiB; 0 (default until measured).  MUFFT_CUDA_SPIN_SYNC sets the initial value. */

@@ -83,6 +83,7 @@ SIGNATURES = {
     "mufft_execute_conv_output_partitioned_batch_async": (_i, [_vp, _vp, _vp, _vp, _u, _sz]),
     "mufft_cuda_set_prefetch": (None, [_i]),
     "mufft_cuda_set_fused_2d": (None, [_i]),
+    "mufft_cuda_set_fused_2d_real": (None, [_i]),
     "mufft_cuda_set_two_kernel": (None, [_i]),
     "mufft_cuda_set_cluster_rows": (None, [_i]),
     "mufft_cuda_set_spin_sync": (None, [_i]),

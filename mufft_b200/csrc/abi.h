@@ -126,6 +126,9 @@ typedef struct mcu_2d_args {
     void *out;             /* [batch][ny][nx] complex; also holds the row-transformed intermediate */
     const void *in;
     const void *tw_x, *tw_y; /* engine twiddle tables of nx and ny */
+    const void *rtw;       /* out_mode R2C / R2C_FULL: resolve twiddles of the rows, nx entries */
+    int out_mode;          /* MCU_OUT_COMPLEX: complex images; MCU_OUT_R2C / MCU_OUT_R2C_FULL: real images of 2 nx floats per row
+                            * in, rows of pitch 2 nx bins out (tw_x = the table of mcu_rows_variant(nx, MCU_IN_COMPLEX, out_mode)) */
     unsigned *counters;    /* 1 + batch zero-initialised words: ticket counter, rows-done per image */
     size_t out_image, in_image; /* complex elements between consecutive images */
     size_t batch;
@@ -217,8 +220,10 @@ int mcu_launch_pass(const mcu_pass_args *args, void *stream);
  * (0 = n is outside its range and takes the generic passes) */
 unsigned mcu_split_n2(unsigned n, int columns);
 int mcu_launch_rowst(const mcu_rowst_args *args, void *stream);
-/* 1 if the fused 2D kernel exists for this image shape */
+/* 1 if the fused 2D kernel exists for this image shape (nx = complex length of a row transform) and
+ * kind of output (MCU_OUT_COMPLEX, or MCU_OUT_R2C / MCU_OUT_R2C_FULL for real images) */
 int mcu_2d_fused_supported(unsigned nx, unsigned ny);
+int mcu_2d_fused_real_supported(unsigned nx, unsigned ny, int out_mode);
 int mcu_launch_2d_fused(const mcu_2d_args *args, void *stream);
 int mcu_launch_resolve(const mcu_resolve_args *args, void *stream);
 int mcu_launch_conv(const mcu_conv_args *args, void *stream);

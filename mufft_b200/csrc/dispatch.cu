@@ -31,7 +31,7 @@ MUFFT_DECLARE_COLS(512) MUFFT_DECLARE_COLS(1024) MUFFT_DECLARE_COLS(2048)
 
 #define MUFFT_F2D_SIZES(X, nx) X(nx, 256) X(nx, 512) X(nx, 1024) X(nx, 2048)
 #define MUFFT_F2D_SHAPES(X) MUFFT_F2D_SIZES(X, 256) MUFFT_F2D_SIZES(X, 512) MUFFT_F2D_SIZES(X, 1024) MUFFT_F2D_SIZES(X, 2048)
-#define MUFFT_DECLARE_F2D(pw, ph) cudaError_t f2d_launch_##pw##x##ph(const mcu_2d_args &, cudaStream_t); bool f2d_supported_##pw##x##ph();
+#define MUFFT_DECLARE_F2D(pw, ph) cudaError_t f2d_launch_##pw##x##ph(const mcu_2d_args &, cudaStream_t); bool f2d_supported_##pw##x##ph(); bool f2d_real_supported_##pw##x##ph(int);
 MUFFT_F2D_SHAPES(MUFFT_DECLARE_F2D)
 
 cudaError_t rowst_launch_256(const mcu_rowst_args &, cudaStream_t);
@@ -349,6 +349,14 @@ int mcu_launch_cols(const mcu_cols_args *a, void *stream)
 int mcu_2d_fused_supported(unsigned nx, unsigned ny)
 {
 #define X(pw, ph) if (nx == pw && ny == ph) return f2d_supported_##pw##x##ph() ? 1 : 0;
+    MUFFT_F2D_SHAPES(X)
+#undef X
+    return 0;
+}
+
+int mcu_2d_fused_real_supported(unsigned nx, unsigned ny, int out_mode)
+{
+#define X(pw, ph) if (nx == pw && ny == ph) return f2d_real_supported_##pw##x##ph(out_mode) ? 1 : 0;
     MUFFT_F2D_SHAPES(X)
 #undef X
     return 0;

@@ -125,10 +125,53 @@ static cudaError_t launch_dir(const mcu_2d_args &a, cudaStream_t stream)
   }
 }
 
+// Real images (forward R2C): one flavour, the one measured best for most complex shapes.
+template <int OM>
+static cudaError_t launch_real(const mcu_2d_args &a, cudaStream_t stream)
+{
+  if constexpr (!f2d_real_supported(F2D_NX, F2D_NY, OM)) {
+    (void)a; (void)stream;
+    return cudaErrorInvalidValue;
+  } else {
+    constexpr int FLAGS = F2D_ONE_SIDED | F2D_DERIVE;
+    constexpr int VX = f2d_rows_variant(F2D_NX, OM);
+    constexpr unsigned width = OM == MCU_OUT_R2C ? F2D_NX + 1 : 2 * F2D_NX;
+    constexpr unsigned per_image = F2D_NY / f2d_rows_per_tile(F2D_NX) + (width + f2d_cols_per_tile(F2D_NY) - 1) / f2d_cols_per_tile(F2D_NY);
+    static int ctas = 0; // per instantiation
+    auto kernel = fft2d_fused_kernel<F2D_NX, F2D_NY, -1, FLAGS, OM>;
+    constexpr size_t smem = f2d_smem_bytes(F2D_NX, F2D_NY, false, VX);
+    if (ctas == 0) {
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        int dev = 0, sms = 0, per_sm = 0;
+        if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
+        if ((err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return err;
+        if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, MUFFT_F2D_THREADS, smem)) != cudaSuccess) return err;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        ctas = sms * per_sm;
+    }
+    if (a.batch == 0) return cudaSuccess;
+    const unsigned long long tickets = (unsigned long long)a.batch * per_image;
+    if (tickets + (unsigned long long)ctas >= 0xffffffffull) return cudaErrorInvalidConfiguration;
+    const unsigned grid = tickets < (unsigned long long)ctas ? (unsigned)tickets : (unsigned)ctas;
+    mcu_2d_args b = a;
+    if (b.lag == 0) b.lag = 1 + (3 * grid / 2 + per_image - 1) / per_image;
+    kernel<<<grid, MUFFT_F2D_THREADS, smem, stream>>>(b);
+    return cudaGetLastError();
+  }
+}
+
 bool MUFFT_CAT4(f2d_supported_, F2D_NX, x, F2D_NY)() { return f2d_supported(F2D_NX, F2D_NY); }
+bool MUFFT_CAT4(f2d_real_supported_, F2D_NX, x, F2D_NY)(int out_mode)
+{
+    return out_mode == MCU_OUT_R2C ? f2d_real_supported(F2D_NX, F2D_NY, MCU_OUT_R2C)
+                                   : (out_mode == MCU_OUT_R2C_FULL ? f2d_real_supported(F2D_NX, F2D_NY, MCU_OUT_R2C_FULL) : false);
+}
 
 cudaError_t MUFFT_CAT4(f2d_launch_, F2D_NX, x, F2D_NY)(const mcu_2d_args &a, cudaStream_t stream)
 {
+    if (a.out_mode == MCU_OUT_R2C) return a.direction < 0 ? launch_real<MCU_OUT_R2C>(a, stream) : cudaErrorInvalidValue;
+    if (a.out_mode == MCU_OUT_R2C_FULL) return a.direction < 0 ? launch_real<MCU_OUT_R2C_FULL>(a, stream) : cudaErrorInvalidValue;
     // Measured on B200 over all 16 shapes (profiles/README.md, round-1 flavour table): one-sided fences
     // + derived twiddles is the best or within 1.5 % of the best flavour everywhere except 1024 x 1024
     // (BASELINE configs[3]), where the twiddle tables in shared memory win: 1.279 ms plain, 1.194 / 1.209.

@@ -17,6 +17,7 @@
 
 #include "abi.h"
 #include "fft_engine.cuh"
+#include "rows_kernel.cuh"
 
 namespace mufft {
 
@@ -48,15 +49,25 @@ __host__ __device__ constexpr bool f2d_supported(int nx, int ny)
            engine_threads(ny) * 4 <= MUFFT_F2D_THREADS && (engine_threads(nx) <= 32 || f2d_rows_per_tile(nx) <= 15) &&
            ny % (f2d_rows_per_tile(nx) * f2d_row_repeat(nx, ny)) == 0 && nx % f2d_cols_per_tile(ny) == 0;
 }
-__host__ __device__ constexpr size_t f2d_xch_elems(int nx, int ny)
+__host__ __device__ constexpr size_t f2d_xch_elems(int nx, int ny, int vx = 0)
 {
-    size_t r = (size_t)f2d_rows_per_tile(nx) * engine_smem_elems(nx);
+    size_t r = (size_t)f2d_rows_per_tile(nx) * engine_smem_elems(nx, vx);
     size_t c = (size_t)f2d_cols_per_tile(ny) * engine_smem_elems(ny);
     return r > c ? r : c;
 }
-__host__ __device__ constexpr size_t f2d_smem_bytes(int nx, int ny, bool lite = false)
+__host__ __device__ constexpr size_t f2d_smem_bytes(int nx, int ny, bool lite = false, int vx = 0)
 {
-    return f2d_xch_elems(nx, ny) * sizeof(float2) + 16 + (lite ? (size_t)(engine_tw_total(nx) + (nx != ny ? engine_tw_total(ny) : 0)) * sizeof(float2) : 0);
+    return f2d_xch_elems(nx, ny, vx) * sizeof(float2) + 16 +
+           (lite ? (size_t)(engine_tw_total(nx, vx) + ((nx != ny || vx != 0) ? engine_tw_total(ny) : 0)) * sizeof(float2) : 0);
+}
+// Real-to-complex images (OM = MCU_OUT_R2C / MCU_OUT_R2C_FULL): NX is the complex length of a row
+// transform (half the real row), the output rows have a pitch of 2 NX bins (ref fft.h:238-257) of which
+// NX + 1 (all 2 NX with FULL) carry data and get column transforms.
+__host__ __device__ constexpr int f2d_rows_variant(int nx, int om) { return rows_variant(nx, MCU_IN_COMPLEX, om); }
+__host__ __device__ constexpr bool f2d_real_supported(int nx, int ny, int om)
+{
+    return f2d_supported(nx, ny) && f2d_row_repeat(nx, ny) == 1 &&
+           engine_threads(nx, f2d_rows_variant(nx, om)) == engine_threads(nx); // same tile shape as the complex kernel
 }
 
 // Polling load (no L1 invalidation per iteration; the acquire fence follows once, after success).
@@ -128,15 +139,16 @@ __device__ __forceinline__ void f2d_fence_acquire()
     if constexpr (LITE) fence_acquire_gpu();
     else fence_acq_rel_gpu();
 }
-// Twiddle tables of both axes in shared memory (one table when the sides are equal), in cpx.
-__host__ __device__ constexpr int f2d_tw_elems(int nx, int ny) { return engine_tw_total(nx) + (nx != ny ? engine_tw_total(ny) : 0); }
+// Twiddle tables of both axes in shared memory (one table when the sides are equal and the rows use
+// the general engine shape, vx == 0), in cpx.
+__host__ __device__ constexpr int f2d_tw_elems(int nx, int ny, int vx = 0) { return engine_tw_total(nx, vx) + ((nx != ny || vx != 0) ? engine_tw_total(ny) : 0); }
 // Copies them behind `dst`; the caller's next CTA barrier publishes them.
-template <int NX, int NY>
+template <int NX, int NY, int VX = 0>
 __device__ __forceinline__ void f2d_stage_twiddles(cpx *dst, const cpx *__restrict__ twx, const cpx *__restrict__ twy, int tid, int threads)
 {
-    for (int i = tid; i < engine_tw_total(NX); i += threads) dst[i] = __ldg(twx + i);
-    if constexpr (NX != NY)
-        for (int i = tid; i < engine_tw_total(NY); i += threads) dst[engine_tw_total(NX) + i] = __ldg(twy + i);
+    for (int i = tid; i < engine_tw_total(NX, VX); i += threads) dst[i] = __ldg(twx + i);
+    if constexpr (NX != NY || VX != 0)
+        for (int i = tid; i < engine_tw_total(NY); i += threads) dst[engine_tw_total(NX, VX) + i] = __ldg(twy + i);
 }
 // Pull `bytes` (a multiple of 16, 16-byte aligned) into L2 ahead of use.
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
@@ -160,14 +172,22 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
 #define F2D_DERIVE 4
 #define F2D_LITE (F2D_SMEM_TW | F2D_ONE_SIDED)
 __host__ __device__ constexpr int f2d_twm(int flags) { return ((flags & F2D_SMEM_TW) ? MUFFT_TW_SMEM : 0) | ((flags & F2D_DERIVE) ? MUFFT_TW_DERIVE : 0); }
-template <int NX, int NY, int DIR, int FLAGS = 0>
+// OM: MCU_OUT_COMPLEX = complex images; MCU_OUT_R2C / MCU_OUT_R2C_FULL = real images (forward only): the row
+// tiles run the real-to-complex row transform (engine of NX points + the resolve epilogue of
+// rows_kernel.cuh, ref kernel.c:47-82) into rows of pitch 2 NX, the column tiles transform the NX + 1
+// (2 NX) columns that carry data; the last column tile is partly masked.
+template <int NX, int NY, int DIR, int FLAGS = 0, int OM = MCU_OUT_COMPLEX>
 __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d_fused_kernel(const mcu_2d_args a)
 {
-    constexpr int RX = engine_regs(NX), TX = NX / RX, ROWS = f2d_rows_per_tile(NX);
+    constexpr int VX = f2d_rows_variant(NX, OM);
+    constexpr int RX = engine_regs(NX, VX), TX = NX / RX, ROWS = f2d_rows_per_tile(NX);
     constexpr int RY = engine_regs(NY), TY = NY / RY, COLS = f2d_cols_per_tile(NY);
     constexpr int REP = f2d_row_repeat(NX, NY);
+    constexpr int PITCH = OM == MCU_OUT_COMPLEX ? NX : 2 * NX;                               // output row pitch
+    constexpr int WIDTH = OM == MCU_OUT_COMPLEX ? NX : (OM == MCU_OUT_R2C ? NX + 1 : 2 * NX); // columns to transform
+    static_assert(OM == MCU_OUT_COMPLEX || (REP == 1 && DIR < 0 && MUFFT_F2D_THREADS / TX == ROWS), "real images: forward, one row group per ticket");
     constexpr unsigned NR = NY / (ROWS * REP); // row tickets per image
-    constexpr unsigned NC = NX / COLS; // column tickets per image
+    constexpr unsigned NC = (WIDTH + COLS - 1) / COLS; // column tickets per image
     MUFFT_DYNAMIC_SMEM(smem_raw);
     MUFFT_STATIC_SMEM_U32(s_ticket, 2);
     MUFFT_STATIC_SMEM_U32(s_wait, 2);
@@ -178,10 +198,10 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d
     const cpx *__restrict__ twy = static_cast<const cpx *>(a.tw_y);
     constexpr bool LITE = (FLAGS & F2D_ONE_SIDED) != 0; // fences
     if constexpr ((FLAGS & F2D_SMEM_TW) != 0) {
-        cpx *tws = smem + f2d_xch_elems(NX, NY) + 2; // behind the exchange area (+16 bytes)
-        f2d_stage_twiddles<NX, NY>(tws, twx, twy, tid, MUFFT_F2D_THREADS);
+        cpx *tws = smem + f2d_xch_elems(NX, NY, VX) + 2; // behind the exchange area (+16 bytes)
+        f2d_stage_twiddles<NX, NY, VX>(tws, twx, twy, tid, MUFFT_F2D_THREADS);
         twx = tws;
-        twy = NX != NY ? tws + engine_tw_total(NX) : tws;
+        twy = (NX != NY || VX != 0) ? tws + engine_tw_total(NX, VX) : tws;
     }
     unsigned *ticket_counter = a.counters;
     unsigned *rows_done = a.counters + 1;
@@ -282,6 +302,37 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d
             continue;
         }
 #endif
+        if constexpr (OM != MCU_OUT_COMPLEX) {
+          if (is_rows) {
+            // real rows: NX complex = 2 NX floats in, NX + 1 (2 NX) bins out at pitch 2 NX
+            const int slot = tid / TX, t = tid - slot * TX;
+            const size_t row = (size_t)tile * ROWS + slot;
+            const cpx *__restrict__ in = static_cast<const cpx *>(a.in) + (size_t)image * a.in_image + row * NX;
+            if (tid == 0 && image + 1 < a.batch && (reinterpret_cast<uintptr_t>(in + a.in_image) & 15) == 0)
+                prefetch_l2_bulk(in + a.in_image, (unsigned)(ROWS * NX * sizeof(cpx)));
+            cpx v[RX];
+#pragma unroll
+            for (int e = 0; e < RX; e++) v[e] = __ldcs(in + t + e * TX);
+            if (tid == 0) release_pending();
+            cpx *sm = smem + slot * engine_smem_elems(NX, VX);
+            engine_run<NX, DIR, 1, TX, ROWS, 0, VX, -1, f2d_twm(FLAGS)>(v, sm, twx, t, slot);
+            rows_store<NX, OM, TX, ROWS, VX>(v, out + row * PITCH, sm, static_cast<const cpx *>(a.rtw), t, slot, true);
+            if (tid == 0) pending = image;
+          } else {
+            const int c = tid % COLS, t = tid / COLS;
+            const bool active = tile * COLS + c < (unsigned)WIDTH;
+            cpx *__restrict__ col = out + (size_t)tile * COLS + c;
+            cpx v[RY];
+#pragma unroll
+            for (int e = 0; e < RY; e++) v[e] = active ? __ldcg(col + (size_t)(t + e * TY) * PITCH) : make_float2(0.0f, 0.0f);
+            if (tid == 0) release_pending();
+            engine_run<NY, DIR, COLS, MUFFT_F2D_THREADS, 1, 0, 0, -1, f2d_twm(FLAGS)>(v, smem + c, twy, t, 0);
+            if (active) {
+#pragma unroll
+                for (int e = 0; e < RY; e++) __stcs(col + (size_t)(t + e * TY) * PITCH, v[e]);
+            }
+          }
+        } else
         if (is_rows) {
             const int slot = tid / TX, t = tid - slot * TX;
             // pull the same rows of the next image into L2 (one bulk prefetch of the ticket's

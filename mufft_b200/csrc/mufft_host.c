@@ -80,6 +80,8 @@ __attribute__((constructor)) static void read_env(void)
     if (e != NULL) mufft_cuda_set_spin_sync(atoi(e));
     e = getenv("MUFFT_CUDA_CLUSTER_ROWS");
     if (e != NULL) mufft_cuda_set_cluster_rows(atoi(e));
+    e = getenv("MUFFT_CUDA_FUSED_2D_REAL");
+    if (e != NULL) mufft_cuda_set_fused_2d_real(atoi(e));
     e = getenv("MUFFT_CUDA_FUSED_2D");
     if (e != NULL) mufft_cuda_set_fused_2d(atoi(e));
     e = getenv("MUFFT_CUDA_L2_CHUNK_MB");
@@ -110,6 +112,11 @@ void mufft_cuda_set_two_kernel(int enable) { g_two_kernel = enable != 0; }
 /* 2D C2C: 1 (default) = the fused persistent kernel when the shape has one, 0 = row kernel +
  * column kernel per group of images (the path every other shape and R2C/C2R take). */
 static int g_fused_2d = 1;
+/* Real-to-complex images of 256..2048 complex points per row transform: 1 = the fused kernel as well
+ * (rows with the resolve epilogue into the output, columns in place), 0 (default until measured on the
+ * GPU) = row kernel + column kernel through plan scratch. */
+static int g_fused_2d_real = 0;
+void mufft_cuda_set_fused_2d_real(int enable) { g_fused_2d_real = enable != 0; }
 void mufft_cuda_set_fused_2d(int mode) { g_fused_2d = mode <= 0 ? 0 : (mode > 8 ? 1 : mode); }
 
 /* ---- per-thread state --------------------------------------------------------------------- */
@@ -1310,6 +1317,21 @@ static int run_2d_device(mufft_plan_2d *plan, void *out, const void *in, size_t 
             f.tma = tma_of[g_fused_2d];
             f.flags = flags_of[g_fused_2d];
         }
+        return mcu_launch_2d_fused(&f, stream);
+    }
+    if ((plan->kind == KIND_R2C || plan->kind == KIND_R2C_FULL) && g_fused_2d && g_fused_2d_real &&
+        mcu_2d_fused_real_supported(nx, ny, plan->kind == KIND_R2C ? MCU_OUT_R2C : MCU_OUT_R2C_FULL)) {
+        /* real images in one persistent launch: rows + resolve into `out` (pitch 2 nx), columns in place */
+        const int out_mode = plan->kind == KIND_R2C ? MCU_OUT_R2C : MCU_OUT_R2C_FULL;
+        mcu_2d_args f;
+        memset(&f, 0, sizeof(f));
+        TRY(grow(&plan->d_counters, &plan->counters_bytes, (images + 1) * sizeof(unsigned)));
+        TRY(mcu_memset(plan->d_counters, 0, (images + 1) * sizeof(unsigned), stream));
+        f.out = out; f.in = in; f.tw_y = plan->ax_y.d_engine_tw; f.rtw = plan->d_rtw;
+        f.tw_x = mcu_rows_variant(nx, MCU_IN_COMPLEX, out_mode) != 0 ? plan->ax_x.d_engine_tw_real : plan->ax_x.d_engine_tw;
+        f.counters = plan->d_counters; f.out_image = 2 * (size_t)nx * ny; f.in_image = (size_t)nx * ny;
+        f.batch = images; f.nx = nx; f.ny = ny; f.direction = plan->ax_x.direction;
+        f.out_mode = out_mode; f.flags = -1;
         return mcu_launch_2d_fused(&f, stream);
     }
     const int real_rows = plan->kind != KIND_C2C;

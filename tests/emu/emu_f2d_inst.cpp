@@ -34,3 +34,32 @@ extern "C" int EMU_CAT(emu_2d_fused_, EMU_NX, x, EMU_NY)(int direction, void *ou
     }
     return 0;
 }
+
+// Real images (forward R2C, half or full spectrum): EMU_NX = complex points per row transform (the rows
+// have 2 EMU_NX reals), output rows of pitch 2 EMU_NX bins.
+extern "C" int EMU_CAT(emu_2d_fused_real_, EMU_NX, x, EMU_NY)(int full, void *out, const void *in, const void *tw_x, const void *tw_y, const void *rtw,
+                                                             unsigned *counters, size_t batch, unsigned lag, unsigned ctas)
+{
+    constexpr int NX = EMU_NX, NY = EMU_NY;
+    mcu_2d_args a;
+    memset(&a, 0, sizeof(a));
+    a.out = out; a.in = in; a.tw_x = tw_x; a.tw_y = tw_y; a.rtw = rtw; a.counters = counters;
+    a.out_image = 2 * (size_t)NX * NY; a.in_image = (size_t)NX * NY; a.batch = batch; a.nx = NX; a.ny = NY;
+    a.direction = -1; a.lag = lag; a.out_mode = full ? MCU_OUT_R2C_FULL : MCU_OUT_R2C;
+    const emu::idx3 grid{ ctas, 1, 1 };
+    constexpr int FLAGS = F2D_ONE_SIDED | F2D_DERIVE;
+    if (full) {
+        if constexpr (f2d_real_supported(NX, NY, MCU_OUT_R2C_FULL)) {
+            emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY, false, f2d_rows_variant(NX, MCU_OUT_R2C_FULL)), ctas, 1,
+                        [&] { fft2d_fused_kernel<NX, NY, -1, FLAGS, MCU_OUT_R2C_FULL>(a); });
+            return 0;
+        }
+    } else {
+        if constexpr (f2d_real_supported(NX, NY, MCU_OUT_R2C)) {
+            emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY, false, f2d_rows_variant(NX, MCU_OUT_R2C)), ctas, 1,
+                        [&] { fft2d_fused_kernel<NX, NY, -1, FLAGS, MCU_OUT_R2C>(a); });
+            return 0;
+        }
+    }
+    return -3;
+}

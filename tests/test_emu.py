@@ -322,3 +322,32 @@ def test_rows_on_a_cluster(emu, host, oracle, n, case, flavour):
         assert cpu_libs.rel_l2(out[b], want[b]) <= tol(n)
     if case in ("fwd", "inv"):
         assert cpu_libs.rel_l2(out[0], oracle.c2c(x[0], direction)) <= tol(n)
+
+
+@pytest.mark.parametrize("nx,ny,ctas", [(256, 256, 1), (512, 256, 3), (2048, 256, 2)])
+@pytest.mark.parametrize("full", [0, 1])
+def test_fused_2d_real(emu, host, oracle, nx, ny, ctas, full):
+    """Real images in the fused kernel: row tiles run the R2C row transform (engine of nx complex points + the
+    resolve epilogue; 512 and 2048 use the mirrored-last-pass shape) into rows of pitch 2 nx bins, column
+    tiles transform the nx + 1 (2 nx with FULL_R2C) columns that carry data, the last one partly masked."""
+    fn = getattr(emu, f"emu_2d_fused_real_{nx}x{ny}")
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, sz, C.c_uint, C.c_uint]
+    batch = 3
+    rng = np.random.default_rng(nx + ny + full)
+    x = rnd(rng, batch, ny, 2 * nx)
+    out = np.full((batch, ny, 2 * nx), np.nan + 1j * np.nan, np.complex64)
+    counters = np.zeros(1 + batch, np.uint32)
+    mode = OUT_R2C_FULL if full else OUT_R2C
+    variant = host.mcu_rows_variant(nx, IN_COMPLEX, mode)
+    twx, twy, rtw = engine_table(host, nx, -1, variant), engine_table(host, ny, -1), resolve_twiddles(-1, nx)
+    assert fn(full, out.ctypes.data, x.ctypes.data, twx.ctypes.data, twy.ctypes.data, rtw.ctypes.data, counters.ctypes.data, batch, 1, ctas) == 0
+    width = 2 * nx if full else nx + 1
+    for b in range(batch):
+        want = np.fft.fft2(x[b].astype(np.float64))[:, :width]
+        assert cpu_libs.rel_l2(out[b][:, :width], want) <= tol(2 * nx * ny)
+    want = oracle.r2c_2d(x[0], cpu_libs.FLAG_FULL_R2C if full else 0)
+    assert cpu_libs.rel_l2(out[0][:, :width], want[:, :width]) <= tol(2 * nx * ny)
+    if not full:
+        assert np.all(np.isnan(out[:, :, width:].real)), "columns beyond Nx/2 + 1 must stay untouched"
+    assert list(counters[1:]) == [ny] * batch

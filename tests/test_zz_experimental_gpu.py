@@ -67,3 +67,31 @@ def test_cluster_rows(m, torch, oracle, n):
         assert (torch.linalg.vector_norm(yc - ref) / torch.linalg.vector_norm(ref)).item() <= tol(n)
     finally:
         m.mufft_cuda_set_cluster_rows(0)
+
+
+@pytest.mark.parametrize("nx,ny", [(512, 256), (1024, 1024), (2048, 512), (4096, 256)])
+@pytest.mark.parametrize("flags", [0, 1 << 16])
+def test_fused_2d_real(m, torch, oracle, nx, ny, flags):
+    """mufft_cuda_set_fused_2d_real(1): 2D R2C images (nx reals per row) in the fused persistent kernel."""
+    batch = max(3, min(24, (64 << 20) // (8 * nx * ny)))
+    g = torch.Generator(device="cuda")
+    g.manual_seed(nx + ny)
+    x = torch.rand((batch, ny, nx), dtype=torch.float32, device="cuda", generator=g) - 0.5
+    out = torch.zeros((batch, ny, nx, 2), dtype=torch.float32, device="cuda")
+    m.mufft_cuda_set_fused_2d_real(1)
+    try:
+        plan = m.mufft_create_plan_2d_r2c(nx, ny, flags)
+        m.mufft_cuda_launch_count(1)
+        assert m.mufft_execute_plan_2d_batch(plan, out.data_ptr(), x.data_ptr(), batch) == 0, m.mufft_cuda_last_error()
+        assert m.mufft_cuda_launch_count(1) == 1
+        m.mufft_free_plan_2d(plan)
+    finally:
+        m.mufft_cuda_set_fused_2d_real(0)
+    width = nx if flags else nx // 2 + 1
+    got = torch.view_as_complex(out)[:, :, :width]
+    ref = torch.fft.fft2(x)[:, :, :width]
+    err = (torch.linalg.vector_norm((got - ref).reshape(batch, -1), dim=1) / torch.linalg.vector_norm(ref.reshape(batch, -1), dim=1)).max().item()
+    assert err <= tol(nx * ny)
+    want = oracle.r2c_2d(x[batch - 1].cpu().numpy(), flags)[:, :width]
+    g1 = got[batch - 1].cpu().numpy()
+    assert float(np.linalg.norm(g1 - want) / np.linalg.norm(want)) <= tol(nx * ny)

@@ -233,6 +233,28 @@ if __name__ == "__main__":
             probe_partitioned(n_, parts_, st_)
         probe_scatter(16384)
         probe_1d(16384, 4096)
+    elif ARG == "real2d":  # 2D R2C images: row kernel + column kernel through scratch vs the fused persistent kernel
+        for nx_, ny_ in ((1024, 1024), (512, 512), (2048, 2048), (4096, 1024)):
+            batch_ = max(2, (1 << 30) // (nx_ * ny_ * 8))
+            pin, x = managed(nx_ * ny_ * batch_)
+            pout, y = managed(2 * nx_ * ny_ * batch_)
+            fill(x, nx_ + ny_, nx_ * ny_)
+            xr, yc = x.reshape(batch_, ny_, nx_), y.view(np.complex64).reshape(batch_, ny_, nx_)
+            for fused in (0, 1, 0, 1):
+                m.mufft_cuda_set_fused_2d_real(fused)
+                plan = m.mufft_create_plan_2d_r2c(nx_, ny_, 0)
+                m.mufft_cuda_launch_count(1)
+                ms = timed(lambda: m.mufft_execute_plan_2d_batch(plan, pout, pin, batch_), 5)
+                launches = m.mufft_cuda_launch_count(1) / 7
+                w_ = nx_ // 2 + 1
+                err = max(rel_l2(yc[b][:, :w_], np.fft.fft2(xr[b].astype(np.float64))[:, :w_]) for b in (0, batch_ - 1))
+                emit(what="r2c2d", nx=nx_, ny=ny_, batch=batch_, fused_real=fused, launches_per_call=launches, ms=round(ms, 4),
+                     gbs=round((4 * nx_ * ny_ + 8 * w_ * ny_) * batch_ / ms / 1e6, 1), rel_l2=err, ok=bool(err <= 1e-6 * math.log2(nx_ * ny_)),
+                     last_error=m.mufft_cuda_last_error().decode())
+                m.mufft_free_plan_2d(plan)
+            m.mufft_cuda_set_fused_2d_real(0)
+            m.mufft_free(pin)
+            m.mufft_free(pout)
     elif ARG == "latency":  # BASELINE configs[0] as the reference runs it: one 64-point transform per fft.h call
         plan = m.mufft_create_plan_1d_c2c(64, -1, 0)
         pin, x = managed(128)
