@@ -351,3 +351,59 @@ def test_fused_2d_real(emu, host, oracle, nx, ny, ctas, full):
     if not full:
         assert np.all(np.isnan(out[:, :, width:].real)), "columns beyond Nx/2 + 1 must stay untouched"
     assert list(counters[1:]) == [ny] * batch
+
+
+@pytest.mark.parametrize("n1,n2", [(64, 256), (32, 1024), (128, 512)])
+@pytest.mark.parametrize("case", ["fwd", "inv", "zero_pad"])
+def test_two_kernel_long_transform(emu, host, oracle, n1, n2, case):
+    """N = N1 * N2 beyond the single-kernel limit: column kernel on the [N1][N2] view, then rowst_kernel.cuh
+    (inter-stage twiddle, N2-point rows, transposed store), chained through scratch as mufft_host.c does."""
+    n = n1 * n2
+    direction = 1 if case == "inv" else -1
+    fn = getattr(emu, f"emu_two_kernel_{n1}x{n2}")
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, sz, C.c_int]
+    rng = np.random.default_rng(n + len(case))
+    batch, half = 2, case == "zero_pad"
+    x = crnd(rng, batch, n // 2 if half else n)
+    out = np.full((batch, n), np.nan, np.complex64)
+    scratch = np.zeros((batch, n), np.complex64)
+    j = np.arange(n, dtype=np.float64)
+    roots = (np.cos(2 * np.pi * direction * j / n).astype(np.float32) + 1j * np.sin(2 * np.pi * direction * j / n).astype(np.float32)).astype(np.complex64)
+    assert fn(direction, out.ctypes.data, scratch.ctypes.data, x.ctypes.data, engine_table(host, n1, direction).ctypes.data,
+              engine_table(host, n2, direction).ctypes.data, roots.ctypes.data, batch, int(half)) == 0
+    for b in range(batch):
+        want = oracle.c2c(x[b], direction, cpu_libs.FLAG_ZERO_PAD if half else 0, n=n)
+        assert cpu_libs.rel_l2(out[b], want) <= tol(n)
+
+
+@pytest.mark.parametrize("n", [64, 1024, 4096])
+@pytest.mark.parametrize("mono", [0, 1])
+@pytest.mark.parametrize("half", [0, 1])
+def test_fused_convolution_kernel(emu, host, oracle, n, mono, half):
+    """conv_kernel.cuh: load, forward transform, multiply by the filter spectrum (stereo) or resolve /
+    multiply / fold back (mono), inverse transform, store - one kernel per batch of blocks."""
+    fn = getattr(emu, f"emu_conv_{n}")
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, sz, sz, sz, C.c_float]
+    big = 2 * n if mono else n                         # the convolution's FFT length in fft.h terms
+    method = (0 if mono else 1) | (4 if half else 0) | 8
+    rng = np.random.default_rng(n + 2 * mono + half)
+    batch = 3
+    in_len = big // 2 if half else big                 # samples per block (complex for stereo, real for mono)
+    taps = rnd(rng, big // 2)
+    if mono:
+        blocks = rnd(rng, batch, in_len)
+        x_arg = blocks.view(np.complex64)
+    else:
+        blocks = crnd(rng, batch, in_len)
+        x_arg = blocks
+    _, _, fspec = oracle.conv(blocks[0], taps, big, method)  # the filter spectrum exactly as conv_input(SECOND) leaves it
+    out = np.full((batch, n), np.nan + 1j * np.nan, np.complex64)
+    assert fn(mono, half, out.ctypes.data, x_arg.ctypes.data, fspec.ctypes.data, engine_table(host, n, -1).ctypes.data,
+              engine_table(host, n, 1).ctypes.data, resolve_twiddles(-1, n).ctypes.data, resolve_twiddles(1, n).ctypes.data,
+              n, x_arg.shape[1], batch, 1.0 / big) == 0
+    for b in range(batch):
+        want, _, _ = oracle.conv(blocks[b], taps, big, method)
+        got = out[b].view(np.float32) if mono else out[b]
+        assert cpu_libs.rel_l2(got, want) <= 2 * tol(big)
