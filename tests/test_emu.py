@@ -135,6 +135,20 @@ def test_rows_r2c(emu_rows, host, oracle, n, full):
         assert cpu_libs.rel_l2(got[b], want) <= tol(2 * n)
 
 
+@pytest.mark.parametrize("n", [512, 1024, 16384])
+def test_rows_spectral_multiply_c2r(emu_rows, host, oracle, n):
+    """Load stage of the mono mufft_execute_conv_output: product of two half spectra, C2R resolve, inverse
+    transform (MCU_IN_MUL_C2R; 512 and 16384 feed the mirrored first pass, 1024 the general shape)."""
+    emu = emu_rows
+    rng = np.random.default_rng(9 * n)
+    a = np.stack([np.fft.rfft(rnd(rng, 2 * n).astype(np.float64)) for _ in range(2)]).astype(np.complex64)  # [2][n+1]
+    f = np.fft.rfft(rnd(rng, 2 * n).astype(np.float64)).astype(np.complex64)
+    got = rows(emu, host, n, 1, IN_MUL_C2R, OUT_COMPLEX, a, n, in2=f, norm=1.0 / (2 * n), rtw=resolve_twiddles(1, n))
+    for b in range(2):
+        want = np.fft.irfft(a[b].astype(np.complex128) * f.astype(np.complex128), 2 * n)
+        assert cpu_libs.rel_l2(got[b].view(np.float32), want) <= 2 * tol(2 * n)
+
+
 @pytest.mark.parametrize("n", [512, 16384])
 @pytest.mark.parametrize("full", [False, True])
 def test_rows_zero_padded_r2c(emu_rows, host, oracle, n, full):
