@@ -113,7 +113,7 @@ static cudaError_t launch_dir(const mcu_2d_args &a, cudaStream_t stream)
     if (a.batch == 0) return cudaSuccess;
     const unsigned long long tickets = (unsigned long long)a.batch *
         (F2D_NY / (f2d_rows_per_tile(F2D_NX) * f2d_row_repeat(F2D_NX, F2D_NY)) + F2D_NX / f2d_cols_per_tile(F2D_NY));
-    if (tickets + (unsigned long long)ctas >= 0xffffffffull) return cudaErrorInvalidConfiguration;
+    if (tickets + 2ull * (unsigned long long)ctas >= 0xffffffffull) return cudaErrorInvalidConfiguration; // F2D_EARLY draws two ahead
     const unsigned grid = tickets < (unsigned long long)ctas ? (unsigned)tickets : (unsigned)ctas;
     // lag L: the last row ticket of image i and its first column ticket are L*(NR+NC)-NR tickets
     // apart; keep that above ~1.5x the tickets in flight (one per CTA)
@@ -183,6 +183,8 @@ cudaError_t MUFFT_CAT4(f2d_launch_, F2D_NX, x, F2D_NY)(const mcu_2d_args &a, cud
         MUFFT_F2D_FLAVOUR(F2D_LITE)
         MUFFT_F2D_FLAVOUR(F2D_ONE_SIDED | F2D_DERIVE)
         MUFFT_F2D_FLAVOUR(F2D_LITE | F2D_DERIVE)
+        MUFFT_F2D_FLAVOUR(F2D_LITE | F2D_EARLY)
+        MUFFT_F2D_FLAVOUR(F2D_ONE_SIDED | F2D_DERIVE | F2D_EARLY)
 #undef MUFFT_F2D_FLAVOUR
     default: return cudaErrorInvalidValue;
     }

@@ -166,10 +166,15 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
 //                  than not - every fence.acq_rel.gpu of the ticket protocol invalidates it - so that
 //                  they pull as many sectors from L2 as a whole pass over the data;
 //   F2D_ONE_SIDED  release / acquire fences instead of fence.acq_rel.gpu in the ticket protocol;
-//   F2D_DERIVE     only the power-of-two twiddles are loaded, the rest derived (MUFFT_TW_DERIVE).
+//   F2D_DERIVE     only the power-of-two twiddles are loaded, the rest derived (MUFFT_TW_DERIVE);
+//   F2D_EARLY      tickets are drawn TWO tiles ahead, so that the rows-done counter a column ticket
+//                  depends on is read at the START of the tile before it and the answer is in a
+//                  register when the ticket is handed to the CTA: the L2 round trip of that read leaves
+//                  the critical path between two tiles (not measured yet).
 #define F2D_SMEM_TW 1
 #define F2D_ONE_SIDED 2
 #define F2D_DERIVE 4
+#define F2D_EARLY 8
 #define F2D_LITE (F2D_SMEM_TW | F2D_ONE_SIDED)
 __host__ __device__ constexpr int f2d_twm(int flags) { return ((flags & F2D_SMEM_TW) ? MUFFT_TW_SMEM : 0) | ((flags & F2D_DERIVE) ? MUFFT_TW_DERIVE : 0); }
 // OM: MCU_OUT_COMPLEX = complex images; MCU_OUT_R2C / MCU_OUT_R2C_FULL = real images (forward only): the row
@@ -256,10 +261,11 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d
     // stored (they may be the very rows it would wait for, and they cannot be released before the
     // next CTA barrier has covered every thread's stores).  Then the ticket is published with the
     // wait flag set and the wait happens after that barrier.
-    auto publish = [&](unsigned k, int slot) {
+    // `seen`: a value of the image's rows-done counter read earlier (0 = none)
+    auto publish = [&](unsigned k, int slot, unsigned seen = 0) {
         unsigned image, tile, wait = 0;
         if (k < total && !decode(k, image, tile)) {
-            if (ld_relaxed(rows_done + image) < (unsigned)NY) {
+            if (seen < (unsigned)NY && ld_relaxed(rows_done + image) < (unsigned)NY) {
                 if (pending != ~0u) wait = 1;
                 else wait_rows(image);
             }
@@ -270,7 +276,11 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d
     };
 
     unsigned next_ticket = 0;
-    if (tid == 0) publish(atomicAdd(ticket_counter, 1u), 0);
+    unsigned ahead = 0, ahead_seen = 0; // F2D_EARLY, thread 0: the ticket after the current one and what is known of its dependency
+    if (tid == 0) {
+        publish(atomicAdd(ticket_counter, 1u), 0);
+        if constexpr ((FLAGS & F2D_EARLY) != 0) ahead = atomicAdd(ticket_counter, 1u);
+    }
     for (int it = 0;; it++) {
         __syncthreads(); // ticket visible; the previous ticket's users of the exchange area are done
         const unsigned k = s_ticket[it & 1];
@@ -289,7 +299,17 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d
             __syncthreads();
         }
         // draw the next ticket now; its round trip to L2 overlaps this tile
-        if (tid == 0) next_ticket = atomicAdd(ticket_counter, 1u);
+        if constexpr ((FLAGS & F2D_EARLY) != 0) {
+            if (tid == 0) {
+                // `ahead` was drawn a tile ago: look at its dependency now, use the answer after this tile
+                unsigned im, tl;
+                ahead_seen = (unsigned)NY;
+                if (ahead < total && !decode(ahead, im, tl)) ahead_seen = ld_relaxed(rows_done + im);
+                next_ticket = atomicAdd(ticket_counter, 1u);
+            }
+        } else {
+            if (tid == 0) next_ticket = atomicAdd(ticket_counter, 1u);
+        }
         unsigned image, tile;
         const bool is_rows = decode(k, image, tile);
 
@@ -368,7 +388,14 @@ __global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d
 #pragma unroll
             for (int e = 0; e < RY; e++) __stcs(col + (size_t)(t + e * TY) * NX, v[e]);
         }
-        if (tid == 0) publish(next_ticket, (it + 1) & 1);
+        if constexpr ((FLAGS & F2D_EARLY) != 0) {
+            if (tid == 0) {
+                publish(ahead, (it + 1) & 1, ahead_seen);
+                ahead = next_ticket;
+            }
+        } else {
+            if (tid == 0) publish(next_ticket, (it + 1) & 1);
+        }
     }
 }
 
