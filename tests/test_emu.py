@@ -97,6 +97,7 @@ def tol(n):
 # 2048 / 4096: CTA-wide exchanges, mirrored shapes; 16384: the 512-thread one-CTA-per-SM shape
 # (MCU_ENGINE_BIG_N) that has not run on a GPU yet.
 ROWS_SIZES = [64, 512, 2048, 4096, 16384]
+ALL_ROWS_SIZES = [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384]  # every engine shape
 
 
 @pytest.mark.parametrize("n", ROWS_SIZES)
@@ -421,3 +422,47 @@ def test_fused_convolution_kernel(emu, host, oracle, n, mono, half):
         want, _, _ = oracle.conv(blocks[b], taps, big, method)
         got = out[b].view(np.float32) if mono else out[b]
         assert cpu_libs.rel_l2(got, want) <= 2 * tol(big)
+
+
+@pytest.mark.parametrize("n", ALL_ROWS_SIZES)
+def test_every_engine_shape(emu, host, oracle, n):
+    """Forward and inverse C2C plus the real transforms of 2n points on every length of engine_shape(), in a
+    batch that leaves the last CTA partly filled."""
+    rng = np.random.default_rng(1000 + n)
+    per_cta = max(1, 256 // max(1, n // 32))
+    batch = min(5, per_cta + 1) if n <= 2048 else 2
+    x = crnd(rng, batch, n)
+    for direction in (-1, 1):
+        got = rows(emu, host, n, direction, IN_COMPLEX, OUT_COMPLEX, x, n)
+        for b in range(batch):
+            assert cpu_libs.rel_l2(got[b], oracle.c2c(x[b], direction)) <= max(tol(n), 2e-7)
+    r = rnd(rng, batch, 2 * n)
+    spec = rows(emu, host, n, -1, IN_COMPLEX, OUT_R2C, r.view(np.complex64), n + 1, rtw=resolve_twiddles(-1, n))
+    back = rows(emu, host, n, 1, IN_C2R, OUT_COMPLEX, spec, n, rtw=resolve_twiddles(1, n))
+    for b in range(batch):
+        assert cpu_libs.rel_l2(spec[b], oracle.r2c(r[b])) <= max(tol(2 * n), 2e-7)
+        assert cpu_libs.rel_l2(back[b].view(np.float32), oracle.c2r(spec[b], 2 * n)) <= max(tol(2 * n), 2e-7)
+
+
+@pytest.mark.parametrize("n", [2, 8, 32, 128, 512, 2048])
+@pytest.mark.parametrize("direction", [-1, 1])
+def test_column_kernel(emu, host, oracle, n, direction):
+    """cols_kernel.cuh: transforms down the columns of [n][width] images without a transpose; a width that is
+    not a multiple of the tile, different input / output pitches, two images, and the zero-padded lower half
+    (rows_valid) the two-kernel path uses."""
+    fn = getattr(emu, f"emu_cols_{n}")
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, vp, vp, vp, sz, sz, sz, sz, sz, C.c_uint, C.c_uint]
+    rng = np.random.default_rng(n + direction)
+    width, in_pitch, out_pitch, images = 21, 24, 29, 2
+    x = crnd(rng, images, n, in_pitch)
+    tw = engine_table(host, n, direction)
+    for rows_valid in (0, n // 2):
+        out = np.full((images, n, out_pitch), np.nan + 1j * np.nan, np.complex64)
+        assert fn(direction, out.ctypes.data, x.ctypes.data, tw.ctypes.data, out_pitch, in_pitch, n * out_pitch, n * in_pitch, images, width, rows_valid) == 0
+        xin = x[:, :, :width].astype(np.complex128)
+        if rows_valid:
+            xin[:, rows_valid:, :] = 0
+        want = np.fft.fft(xin, axis=1) if direction < 0 else np.fft.ifft(xin, axis=1, norm="forward")
+        assert cpu_libs.rel_l2(out[:, :, :width], want) <= max(tol(n), 2e-7)
+        assert np.all(np.isnan(out[:, :, width:].real)), "wrote beyond the requested columns"
