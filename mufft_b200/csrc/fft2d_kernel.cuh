@@ -28,6 +28,17 @@ namespace mufft {
 #define MUFFT_F2D_MIN_BLOCKS 2
 #endif
 
+// Shapes whose sides both run with 16 values per thread (256 and 512 points) need far fewer registers:
+// at 3 CTAs per SM (80 registers) they compile without spills, at 4 (64 registers) with 36 bytes.  The
+// default keeps them at MUFFT_F2D_MIN_BLOCKS until the extra occupancy has been measured
+// (tools/ab_r2.txt: f2d_small3 / f2d_small4).
+#ifndef MUFFT_F2D_MIN_BLOCKS_R16
+#define MUFFT_F2D_MIN_BLOCKS_R16 MUFFT_F2D_MIN_BLOCKS
+#endif
+__host__ __device__ constexpr int f2d_min_blocks(int nx, int ny)
+{
+    return engine_regs(nx) <= 16 && engine_regs(ny) <= 16 ? MUFFT_F2D_MIN_BLOCKS_R16 : MUFFT_F2D_MIN_BLOCKS;
+}
 __host__ __device__ constexpr int f2d_rows_per_tile(int nx) { return MUFFT_F2D_THREADS / engine_threads(nx); }
 __host__ __device__ constexpr int f2d_cols_per_tile(int ny) { return MUFFT_F2D_THREADS / engine_threads(ny); }
 // A row ticket covers f2d_row_repeat() consecutive groups of f2d_rows_per_tile() rows, each warp
@@ -182,7 +193,7 @@ __host__ __device__ constexpr int f2d_twm(int flags) { return ((flags & F2D_SMEM
 // rows_kernel.cuh, ref kernel.c:47-82) into rows of pitch 2 NX, the column tiles transform the NX + 1
 // (2 NX) columns that carry data; the last column tile is partly masked.
 template <int NX, int NY, int DIR, int FLAGS = 0, int OM = MCU_OUT_COMPLEX>
-__global__ void __launch_bounds__(MUFFT_F2D_THREADS, MUFFT_F2D_MIN_BLOCKS) fft2d_fused_kernel(const mcu_2d_args a)
+__global__ void __launch_bounds__(MUFFT_F2D_THREADS, f2d_min_blocks(NX, NY)) fft2d_fused_kernel(const mcu_2d_args a)
 {
     constexpr int VX = f2d_rows_variant(NX, OM);
     constexpr int RX = engine_regs(NX, VX), TX = NX / RX, ROWS = f2d_rows_per_tile(NX);
