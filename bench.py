@@ -481,7 +481,9 @@ class Job:
                 os.environ.setdefault("MASTER_PORT", "29577")
                 dist_mod.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
             world = dist_mod.get_world_size()
-            self.slab = SlabRFFT2D(n, ny, device=dev, chunks=int(os.environ.get("MUFFT_SLAB_CHUNKS", "8")))
+            # MUFFT_SLAB_R2C_EXCHANGE=p2p: the R2C row kernel scatters the half spectrum into the peers' slabs (opt-in)
+            self.slab = SlabRFFT2D(n, ny, device=dev, chunks=int(os.environ.get("MUFFT_SLAB_CHUNKS", "8")),
+                                   exchange=os.environ.get("MUFFT_SLAB_R2C_EXCHANGE") or None)
             self.inp = rnd(ny // world, n)
             self.out = torch.empty((ny, self.slab.cols_local), dtype=torch.complex64, device=dev)
             self.buf = self.slab.buffers()

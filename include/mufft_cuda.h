@@ -63,7 +63,11 @@ int mufft_execute_plan_1d_columns(mufft_plan_1d *plan, void *output, const void 
  * mufft_cuda_ipc_import for the others, so the kernel's stores are the all-to-all transpose and
  * travel over NVLink; no pack pass, no separate collective.  `peers` must be a power of two that
  * divides N.  Enqueued on the current stream; the caller synchronises the devices (any barrier
- * ordered after this call on every device) before reading the slabs. */
+ * ordered after this call on every device) before reading the slabs.
+ * With an R2C plan (N reals per row, no FULL_R2C / zero padding, N/2 <= the single-kernel limit) the
+ * N/2 + 1 bins of row b are scattered the same way: bin k to device min(k / (N/2 / peers), peers - 1);
+ * the slabs are [rows][N/2 / peers] complex, except the last device's, which is one column wider and
+ * takes the Nyquist bin N/2 as its last column (the layout of mufft_b200/slab.py: SlabRFFT2D). */
 int mufft_execute_plan_1d_batch_scatter_async(mufft_plan_1d *plan, void *const *peer_outputs, unsigned peers,
                                               size_t dest_row0, const void *input, size_t batch, size_t input_stride_bytes);
 

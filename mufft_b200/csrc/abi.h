@@ -38,7 +38,8 @@ enum {
     MCU_OUT_COMPLEX = 0,  /* out[i] = y[i] */
     MCU_OUT_R2C = 1,      /* N+1 bins from the N-point half-length spectrum  (ref kernel.c:47-63) */
     MCU_OUT_R2C_FULL = 2, /* all 2N bins                                      (ref kernel.c:65-82) */
-    MCU_OUT_PEERS = 3     /* out[i] = y[i], scattered over the column slabs of several devices (mcu_peer_dest) */
+    MCU_OUT_PEERS = 3,    /* out[i] = y[i], scattered over the column slabs of several devices (mcu_peer_dest) */
+    MCU_OUT_R2C_PEERS = 4 /* the N+1 bins of MCU_OUT_R2C scattered the same way; bin N rides with the last device */
 };
 
 /* Destination of a row transform whose output is the exchange step of a slab-decomposed 2D
@@ -51,6 +52,8 @@ typedef struct mcu_peer_dest {
     void *base[MCU_MAX_PEERS];
     size_t row0, pitch;
     unsigned shift;       /* log2(columns per device) */
+    unsigned last;        /* MCU_OUT_R2C_PEERS: index of the last device, which also takes bin N (column 2^shift of its slab) */
+    size_t pitch_last;    /* MCU_OUT_R2C_PEERS: row pitch of the last device's slab (pitch + 1 when tight) */
 } mcu_peer_dest;
 
 typedef struct mcu_rows_args {

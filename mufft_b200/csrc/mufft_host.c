@@ -609,7 +609,7 @@ static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode
         a.batch = batch; a.n = n; a.direction = ax->direction;
         a.in_mode = in_mode; a.out_mode = out_mode; a.norm = norm;
         a.prefetch = g_prefetch;
-        if (out_mode == MCU_OUT_PEERS) a.peers = *tls_peers;
+        if (out_mode == MCU_OUT_PEERS || out_mode == MCU_OUT_R2C_PEERS) a.peers = *tls_peers;
         if (pd != NULL) { a.parts = pd->parts; a.in_part_stride = pd->in_step; a.in2_part_stride = pd->in2_step; }
         return mcu_launch_rows(&a, stream);
     }
@@ -797,11 +797,17 @@ int mufft_execute_plan_1d_batch_async(mufft_plan_1d *plan, void *output, const v
 int mufft_execute_plan_1d_batch_scatter_async(mufft_plan_1d *plan, void *const *peer_outputs, unsigned peers,
                                               size_t dest_row0, const void *input, size_t batch, size_t input_stride_bytes)
 {
-    if (plan == NULL || plan->kind != KIND_C2C || plan->zero_pad || peers == 0 || peers > MCU_MAX_PEERS ||
+    const int real = plan != NULL && plan->kind == KIND_R2C;
+    if (plan == NULL || (plan->kind != KIND_C2C && !real) || plan->zero_pad || peers == 0 || peers > MCU_MAX_PEERS ||
         (peers & (peers - 1)) != 0 || plan->n % peers != 0 || input_stride_bytes % CPX != 0) {
-        snprintf(tls_error, sizeof(tls_error), "scatter: needs a plain C2C plan and a power-of-two number of devices dividing N");
+        snprintf(tls_error, sizeof(tls_error), "scatter: needs a plain C2C or R2C plan and a power-of-two number of devices dividing its complex length");
         return -1;
     }
+    if (real && plan->ax.d_engine_tw == NULL) {
+        snprintf(tls_error, sizeof(tls_error), "scatter: R2C rows must fit the single-kernel engine (N <= %u reals)", 2 * g_onchip_limit);
+        return -1;
+    }
+    /* plan->n complex points per row either way (an R2C row of N reals is N/2 complex) */
     const size_t in_stride = input_stride_bytes ? input_stride_bytes : (size_t)plan->n * CPX;
     if (batch == 0) return 0;
     if (!device_visible(mcu_pointer_kind(input), in_stride * (batch - 1) + (size_t)plan->n * CPX)) {
@@ -814,10 +820,12 @@ int mufft_execute_plan_1d_batch_scatter_async(mufft_plan_1d *plan, void *const *
     for (unsigned p = 0; p < peers; p++) d.base[p] = peer_outputs[p];
     d.row0 = dest_row0;
     d.pitch = cols;
+    d.pitch_last = real ? cols + 1 : cols; /* the Nyquist bin is one more column of the last slab */
+    d.last = peers - 1;
     while ((1u << d.shift) < cols) d.shift++;
     tls_peers = &d;
-    int err = run_rows(&plan->ax, &plan->scr, NULL, MCU_IN_COMPLEX, MCU_OUT_PEERS, 1.0f, NULL, 0, input, in_stride / CPX,
-                       NULL, 0, batch, tls_stream, NULL);
+    int err = run_rows(&plan->ax, &plan->scr, plan->d_rtw, MCU_IN_COMPLEX, real ? MCU_OUT_R2C_PEERS : MCU_OUT_PEERS, 1.0f, NULL, 0,
+                       input, in_stride / CPX, NULL, 0, batch, tls_stream, NULL);
     tls_peers = NULL;
     return err;
 }

@@ -27,7 +27,7 @@ static cudaError_t launch_mode(const mcu_rows_args &a, cudaStream_t stream)
     const size_t groups = (a.batch + TPC - 1) / TPC;
     if (groups == 0) return cudaSuccess;
 
-    if constexpr (OUT_MODE != MCU_OUT_PEERS && rows_tma_supported(N, IN_MODE, V)) {
+    if constexpr (OUT_MODE != MCU_OUT_PEERS && OUT_MODE != MCU_OUT_R2C_PEERS && rows_tma_supported(N, IN_MODE, V)) {
         // whole 16-byte chunks from 16-byte aligned rows; C2R rows are read 2 elements beyond bin N/2
         const bool aligned = ((uintptr_t)a.in % 16 == 0) && ((a.in_stride * sizeof(float2)) % 16 == 0) &&
                              a.in_stride * sizeof(float2) >= (size_t)rows_land_bytes(N, IN_MODE);
@@ -71,6 +71,7 @@ cudaError_t MUFFT_CAT(rows_launch_, ROWS_N, _fwd)(const mcu_rows_args &a, cudaSt
     case MCU_IN_COMPLEX * 8 + MCU_OUT_PEERS: return launch_mode<MCU_IN_COMPLEX, MCU_OUT_PEERS>(a, s);
     case MCU_IN_COMPLEX * 8 + MCU_OUT_R2C: return launch_mode<MCU_IN_COMPLEX, MCU_OUT_R2C>(a, s);
     case MCU_IN_COMPLEX * 8 + MCU_OUT_R2C_FULL: return launch_mode<MCU_IN_COMPLEX, MCU_OUT_R2C_FULL>(a, s);
+    case MCU_IN_COMPLEX * 8 + MCU_OUT_R2C_PEERS: return launch_mode<MCU_IN_COMPLEX, MCU_OUT_R2C_PEERS>(a, s);
     case MCU_IN_HALF * 8 + MCU_OUT_COMPLEX: return launch_mode<MCU_IN_HALF, MCU_OUT_COMPLEX>(a, s);
     case MCU_IN_HALF * 8 + MCU_OUT_R2C: return launch_mode<MCU_IN_HALF, MCU_OUT_R2C>(a, s);
     case MCU_IN_HALF * 8 + MCU_OUT_R2C_FULL: return launch_mode<MCU_IN_HALF, MCU_OUT_R2C_FULL>(a, s);

@@ -25,7 +25,7 @@ namespace mufft {
 // transforms take the mirrored-pass variants where the shape table has them (fft_engine.cuh).
 __host__ __device__ constexpr int rows_variant(int n, int in_mode, int out_mode)
 {
-    if ((out_mode == MCU_OUT_R2C || out_mode == MCU_OUT_R2C_FULL) && engine_variant_exists(n, MUFFT_VARIANT_MIRROR_LAST))
+    if ((out_mode == MCU_OUT_R2C || out_mode == MCU_OUT_R2C_FULL || out_mode == MCU_OUT_R2C_PEERS) && engine_variant_exists(n, MUFFT_VARIANT_MIRROR_LAST))
         return MUFFT_VARIANT_MIRROR_LAST;
     if ((in_mode == MCU_IN_C2R || in_mode == MCU_IN_MUL_C2R || in_mode == MCU_IN_MULACC_C2R) && engine_variant_exists(n, MUFFT_VARIANT_MIRROR_FIRST))
         return MUFFT_VARIANT_MIRROR_FIRST;
@@ -216,19 +216,37 @@ __device__ __forceinline__ void rows_load(cpx (&v)[engine_regs(N, V)], Ptr in, c
 
 // R2C resolve of one bin pair (ref kernel.c:47-82): from Z[k], Z[N-k] and rtw[k], X[k] and X[N-k]
 // (rtw[N-k] = conj rtw[k]); with FULL also X[k+N] and X[2N-k].
-template <bool FULL>
-__device__ __forceinline__ void r2c_pair_store(cpx *__restrict__ out, int k, int n, cpx za, cpx zb, cpx w)
+// Where a row transform's spectrum goes: a plain row, or (exchange step of a slab R2C transform)
+// the column slabs of several devices, bin k to device min(k >> shift, last).
+struct spectrum_row {
+    cpx *__restrict__ out;
+    __device__ __forceinline__ void operator()(int k, cpx v) const { out[k] = v; }
+};
+struct spectrum_peers {
+    const mcu_peer_dest &d;
+    size_t b; // row of this transform inside the slabs
+    __device__ __forceinline__ void operator()(int k, cpx v) const
+    {
+        unsigned p = (unsigned)k >> d.shift;
+        p = p > d.last ? d.last : p;
+        const size_t pitch = p == d.last ? d.pitch_last : d.pitch;
+        static_cast<cpx *>(d.base[p])[(d.row0 + b) * pitch + ((unsigned)k - (p << d.shift))] = v;
+    }
+};
+
+template <bool FULL, typename Store>
+__device__ __forceinline__ void r2c_pair_store(const Store &store, int k, int n, cpx za, cpx zb, cpx w)
 {
     const cpx cb = cconj(zb);
     const cpx fe = cadd(za, cb);
     const cpx fo = cmul(w, csub(za, cb));
     const cpx xk = cscale(0.5f, cadd(fe, fo));
     const cpx xn = cscale(0.5f, csub(fe, fo)); // = conj X[N-k] = X[k+N]
-    out[k] = xk;
-    if (k != n - k) out[n - k] = cconj(xn);
+    store(k, xk);
+    if (k != n - k) store(n - k, cconj(xn));
     if constexpr (FULL) {
-        out[k + n] = xn;
-        if (k != n - k) out[2 * n - k] = cconj(xk);
+        store(k + n, xn);
+        if (k != n - k) store(2 * n - k, cconj(xk));
     }
 }
 
@@ -251,19 +269,16 @@ __device__ __forceinline__ void rows_store_peers(const cpx (&v)[engine_regs(N, V
 }
 
 // ---- epilogue: output <- registers -----------------------------------------------------------------
-template <int N, int OUT_MODE, int T_SYNC, int SLOTS, int V>
-__device__ __forceinline__ void rows_store(cpx (&v)[engine_regs(N, V)], cpx *__restrict__ out, cpx *sm,
-                                           const cpx *__restrict__ rtw, int t, int slot, bool active)
+// R2C epilogues (half or full spectrum) writing through `store(k, value)`: spectrum_row for a plain
+// output row, spectrum_peers for the exchange step of a slab transform.
+template <int N, int OUT_MODE, int T_SYNC, int SLOTS, int V, typename Store>
+__device__ __forceinline__ void rows_store_spectrum(cpx (&v)[engine_regs(N, V)], const Store &store, cpx *sm,
+                                                    const cpx *__restrict__ rtw, int t, int slot, bool active)
 {
     constexpr int R = engine_regs(N, V);
     constexpr int T = N / R;
     constexpr int SH = engine_pad_shift(N, V);
-    if constexpr (OUT_MODE == MCU_OUT_COMPLEX) {
-        if (active) {
-#pragma unroll
-            for (int e = 0; e < R; e++) out[t + e * T] = v[e];
-        }
-    } else if constexpr (V == MUFFT_VARIANT_MIRROR_LAST) {
+    if constexpr (V == MUFFT_VARIANT_MIRROR_LAST) {
         // The mirrored last pass left Z[i0 + q*Q0] in slot u + q*NB and Z[Q0 - i0 + q*Q0] in slot
         // u + H + q*NB; the partner of bin i0 + q*Q0 is output r-1-q of the image butterfly.
         constexpr bool full = OUT_MODE == MCU_OUT_R2C_FULL;
@@ -277,21 +292,21 @@ __device__ __forceinline__ void rows_store(cpx (&v)[engine_regs(N, V)], cpx *__r
             const int i0 = t + u * T;
             if (u == 0 && i0 == 0) {
                 // butterflies 0 and Q0/2 are their own images
-                out[0] = make_float2(v[0].x + v[0].y, 0.0f);
-                out[N] = make_float2(v[0].x - v[0].y, 0.0f);
+                store(0, make_float2(v[0].x + v[0].y, 0.0f));
+                store(N, make_float2(v[0].x - v[0].y, 0.0f));
                 if constexpr (full) {
                     // bin 2N - 0 does not exist; X[N] is written above
                 }
 #pragma unroll
                 for (int q = 1; q <= r / 2; q++)
-                    r2c_pair_store<full>(out, q * Q0, N, v[q * NB], v[(r - q) * NB], __ldg(rtw + q * Q0));
+                    r2c_pair_store<full>(store, q * Q0, N, v[q * NB], v[(r - q) * NB], __ldg(rtw + q * Q0));
 #pragma unroll
                 for (int q = 0; q < r / 2; q++)
-                    r2c_pair_store<full>(out, Q0 / 2 + q * Q0, N, v[H + q * NB], v[H + (r - 1 - q) * NB], __ldg(rtw + Q0 / 2 + q * Q0));
+                    r2c_pair_store<full>(store, Q0 / 2 + q * Q0, N, v[H + q * NB], v[H + (r - 1 - q) * NB], __ldg(rtw + Q0 / 2 + q * Q0));
             } else {
 #pragma unroll
                 for (int q = 0; q < r; q++)
-                    r2c_pair_store<full>(out, i0 + q * Q0, N, v[u + q * NB], v[u + H + (r - 1 - q) * NB], __ldg(rtw + i0 + q * Q0));
+                    r2c_pair_store<full>(store, i0 + q * Q0, N, v[u + q * NB], v[u + H + (r - 1 - q) * NB], __ldg(rtw + i0 + q * Q0));
             }
         }
     } else {
@@ -306,18 +321,34 @@ __device__ __forceinline__ void rows_store(cpx (&v)[engine_regs(N, V)], cpx *__r
             for (int e = 0; e < R; e++) {
                 const int k = t + e * T;
                 if (k == 0) {
-                    out[0] = make_float2(v[e].x + v[e].y, 0.0f);
-                    out[N] = make_float2(v[e].x - v[e].y, 0.0f);
+                    store(0, make_float2(v[e].x + v[e].y, 0.0f));
+                    store(N, make_float2(v[e].x - v[e].y, 0.0f));
                 } else {
                     const cpx za = v[e];
                     const cpx zb = cconj(sm[pad_pos<SH>(N - k)]);
                     const cpx fe = cadd(za, zb);
                     const cpx fo = cmul(__ldg(rtw + k), csub(za, zb));
-                    out[k] = cscale(0.5f, cadd(fe, fo));
-                    if constexpr (full) out[k + N] = cscale(0.5f, csub(fe, fo));
+                    store(k, cscale(0.5f, cadd(fe, fo)));
+                    if constexpr (full) store(k + N, cscale(0.5f, csub(fe, fo)));
                 }
             }
         }
+    }
+}
+
+template <int N, int OUT_MODE, int T_SYNC, int SLOTS, int V>
+__device__ __forceinline__ void rows_store(cpx (&v)[engine_regs(N, V)], cpx *__restrict__ out, cpx *sm,
+                                           const cpx *__restrict__ rtw, int t, int slot, bool active)
+{
+    if constexpr (OUT_MODE == MCU_OUT_COMPLEX) {
+        constexpr int R = engine_regs(N, V);
+        constexpr int T = N / R;
+        if (active) {
+#pragma unroll
+            for (int e = 0; e < R; e++) out[t + e * T] = v[e];
+        }
+    } else {
+        rows_store_spectrum<N, OUT_MODE, T_SYNC, SLOTS, V>(v, spectrum_row{ out }, sm, rtw, t, slot, active);
     }
 }
 
@@ -353,6 +384,8 @@ fft_rows_kernel(const mcu_rows_args a)
     engine_run<N, DIR, 1, T, TPC, 0, V, rows_packed(N, IN_MODE, OUT_MODE)>(v, sm, tw, t, slot);
     if constexpr (OUT_MODE == MCU_OUT_PEERS) {
         if (active) rows_store_peers<N, V>(v, a.peers, b, t);
+    } else if constexpr (OUT_MODE == MCU_OUT_R2C_PEERS) {
+        rows_store_spectrum<N, MCU_OUT_R2C, T, TPC, V>(v, spectrum_peers{ a.peers, b }, sm, rtw, t, slot, active);
     } else {
         cpx *__restrict__ out = static_cast<cpx *>(a.out) + b * a.out_stride;
         rows_store<N, OUT_MODE, T, TPC, V>(v, out, sm, rtw, t, slot, active);

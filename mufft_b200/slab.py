@@ -261,9 +261,16 @@ class SlabRFFT2D:
     The exchange is NCCL all-to-all with per-peer tiles (uneven for the last rank), block c in
     flight on a side stream while block c+1 of rows is transformed; the local passes go through
     the C ABI.  `local_*` hooks let the exchange logic run on CPU under gloo.
+
+    ``exchange="p2p"`` (forward only, opt-in until it has run on hardware; needs Nx/2 within the
+    library's single-kernel row limit and a power-of-two number of ranks): the column slabs are device
+    allocations mapped into every rank through CUDA IPC and the R2C row kernel's epilogue stores bin k
+    of every row straight into the slab of rank min(k // (H/G), G-1)
+    (`mufft_execute_plan_1d_batch_scatter_async` on the R2C plan): no row buffer, no pack and unpack
+    copies, no NCCL call on the data path.  The inverse keeps the NCCL exchange.
     """
 
-    def __init__(self, nx, ny, group=None, device=None, chunks=4, local_r2c_rows=None, local_c2r_rows=None, local_cols=None):
+    def __init__(self, nx, ny, group=None, device=None, chunks=4, local_r2c_rows=None, local_c2r_rows=None, local_cols=None, exchange=None):
         self.group = group
         self.world = g = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -291,12 +298,49 @@ class SlabRFFT2D:
             local_r2c_rows, local_c2r_rows, local_cols = self._cuda_r2c_rows, self._cuda_c2r_rows, self._cuda_cols
         self.local_r2c_rows, self.local_c2r_rows, self.local_cols = local_r2c_rows, local_c2r_rows, local_cols
         self._side = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        exchange = exchange or "nccl"
+        if exchange == "p2p" and (self._plans is None or g & (g - 1)):
+            raise ValueError("the p2p exchange needs the CUDA library and a power-of-two number of ranks")
+        self.exchange = exchange
+        self._ipc = None  # (own slab allocation, [peer pointers], flag tensor)
 
     def close(self):
+        if self._ipc is not None:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)  # nobody may still be writing into a slab that is about to go away
+            own, peers, _ = self._ipc
+            for r, p in enumerate(peers):
+                if r != self.rank:
+                    self._m.mufft_cuda_ipc_close(p)
+            self._m.mufft_cuda_device_free(own)
+            self._ipc = None
         if self._plans:
             for p in self._plans:
                 self._m.mufft_free_plan_1d(p)
             self._plans = None
+
+    def _p2p_setup(self):
+        """This rank's column slab [Ny][cols_local] as a shareable device allocation; maps everybody else's."""
+        m = self._m
+        own = m.mufft_cuda_device_alloc(self.ny * self.cols_local * 8)
+        if not own:
+            raise RuntimeError("cudaMalloc failed: " + m.mufft_cuda_last_error().decode())
+        handle = ctypes.create_string_buffer(64)
+        if m.mufft_cuda_ipc_export(handle, own):
+            raise RuntimeError(m.mufft_cuda_last_error().decode())
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=self.group)
+        peers = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                peers.append(own)
+            else:
+                p = m.mufft_cuda_ipc_import(ctypes.create_string_buffer(h, 64))
+                if not p:
+                    raise RuntimeError("cudaIpcOpenMemHandle failed: " + m.mufft_cuda_last_error().decode())
+                peers.append(p)
+        self._ipc = (own, peers, torch.zeros(1, dtype=torch.float32, device=self.device))
+        self._peer_array = (ctypes.c_void_p * self.world)(*peers)
 
     def _use_current_stream(self):
         self._m.mufft_cuda_set_stream(torch.cuda.current_stream(self.device).cuda_stream or None)
@@ -325,11 +369,17 @@ class SlabRFFT2D:
     def buffers(self):
         c64 = dict(dtype=torch.complex64, device=self.device)
         g, rl = self.world, self.rows_local
+        if self.exchange == "p2p":
+            if self._ipc is None:
+                self._p2p_setup()
+            slab = torch.as_tensor(_DeviceArray(self._ipc[0], (self.ny, self.cols_local)), device=self.device)
+        else:
+            slab = torch.empty((self.ny, self.cols_local), **c64)
         return {
             "rows": torch.empty((rl, self.h + 1), **c64),                              # half spectra of the local rows
             "send": [torch.empty((rl, w), **c64) for w in self.widths],                # tile for peer p: its columns of my rows
             "recv": [torch.empty((rl, self.cols_local), **c64) for _ in range(g)],     # tile from peer s: my columns of its rows
-            "slab": torch.empty((self.ny, self.cols_local), **c64),
+            "slab": slab,
         }
 
     def _col_range(self, p):
@@ -358,6 +408,15 @@ class SlabRFFT2D:
         """inp float32 [Ny/G][Nx] -> out complex64 [Ny][cols_local] (this rank's columns of the half spectrum)."""
         g, rl = self.world, self.rows_local
         buf = buf or self.buffers()
+        if self.exchange == "p2p":
+            flag = self._ipc[2]
+            dist.all_reduce(flag, group=self.group)  # nobody still reads its slab from the previous call
+            self._use_current_stream()
+            self._check(self._m.mufft_execute_plan_1d_batch_scatter_async(self._plans[0], self._peer_array, g, self.rank * rl,
+                                                                          inp.data_ptr(), rl, inp.stride(0) * 4))
+            dist.all_reduce(flag, group=self.group)  # every rank's row kernel, and with it its remote stores, has completed
+            self.local_cols(out, buf["slab"], -1)
+            return out
         rows, send, recv = buf["rows"], buf["send"], buf["recv"]
         rc = rl // self.chunks
         works = []

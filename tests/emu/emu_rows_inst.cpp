@@ -30,6 +30,7 @@ static int dispatch(const mcu_rows_args &a)
         case MCU_IN_COMPLEX * 8 + MCU_OUT_PEERS: return run<-1, MCU_IN_COMPLEX, MCU_OUT_PEERS>(a);
         case MCU_IN_COMPLEX * 8 + MCU_OUT_R2C: return run<-1, MCU_IN_COMPLEX, MCU_OUT_R2C>(a);
         case MCU_IN_COMPLEX * 8 + MCU_OUT_R2C_FULL: return run<-1, MCU_IN_COMPLEX, MCU_OUT_R2C_FULL>(a);
+        case MCU_IN_COMPLEX * 8 + MCU_OUT_R2C_PEERS: return run<-1, MCU_IN_COMPLEX, MCU_OUT_R2C_PEERS>(a);
         case MCU_IN_HALF * 8 + MCU_OUT_COMPLEX: return run<-1, MCU_IN_HALF, MCU_OUT_COMPLEX>(a);
         case MCU_IN_HALF * 8 + MCU_OUT_R2C: return run<-1, MCU_IN_HALF, MCU_OUT_R2C>(a);
         case MCU_IN_HALF * 8 + MCU_OUT_R2C_FULL: return run<-1, MCU_IN_HALF, MCU_OUT_R2C_FULL>(a);
@@ -76,6 +77,19 @@ extern "C" int EMU_CAT(emu_rows_parts_, EMU_N)(int in_mode, void *out, const voi
 }
 
 // Exchange-step epilogue (MCU_OUT_PEERS): element x of row b goes to slab x >> shift.
+// Same for the R2C epilogue (MCU_OUT_R2C_PEERS): EMU_N + 1 bins per row, bin EMU_N in the last slab.
+extern "C" int EMU_CAT(emu_rows_r2c_peers_, EMU_N)(void *const *bases, unsigned peers, unsigned shift, size_t row0, size_t pitch,
+                                                   const void *in, const void *tw, const void *rtw, size_t in_stride, size_t batch)
+{
+    mcu_rows_args a;
+    memset(&a, 0, sizeof(a));
+    a.in = in; a.tw = tw; a.rtw = rtw; a.in_stride = in_stride; a.batch = batch; a.n = EMU_N; a.direction = -1;
+    a.in_mode = MCU_IN_COMPLEX; a.out_mode = MCU_OUT_R2C_PEERS; a.norm = 1.0f;
+    for (unsigned p = 0; p < peers && p < MCU_MAX_PEERS; p++) a.peers.base[p] = bases[p];
+    a.peers.row0 = row0; a.peers.pitch = pitch; a.peers.pitch_last = pitch + 1; a.peers.shift = shift; a.peers.last = peers - 1;
+    return dispatch(a);
+}
+
 extern "C" int EMU_CAT(emu_rows_peers_, EMU_N)(int direction, void *const *bases, unsigned peers, unsigned shift, size_t row0, size_t pitch,
                                                const void *in, const void *tw, size_t in_stride, size_t batch)
 {

@@ -187,6 +187,33 @@ def test_rows_scatter_to_peer_slabs(emu, host, n, direction):
             assert cpu_libs.rel_l2(slabs[p_][row0 + b], want[b, p_ * width:(p_ + 1) * width]) <= 2 * tol(n)
 
 
+@pytest.mark.parametrize("n", [64, 512, 1024, 16384])
+def test_rows_r2c_scatter_to_peer_slabs(emu, host, oracle, n):
+    """MCU_OUT_R2C_PEERS: the exchange step of a slab R2C transform in the epilogue of the real row transform -
+    bin k of row b lands in the slab of device min(k / (n / peers), peers - 1); the last slab is one column
+    wider and takes the Nyquist bin (512 / 16384: mirrored last pass, 64 / 1024: general shape)."""
+    peers, batch, row0, rows_total = 4, 3, 1, 5
+    width = n // peers
+    rng = np.random.default_rng(n + 123)
+    r = rnd(rng, batch, 2 * n)
+    slabs = [np.full((rows_total, width + (1 if p_ == peers - 1 else 0)), np.nan + 1j * np.nan, np.complex64) for p_ in range(peers)]
+    bases = (C.c_void_p * peers)(*[s_.ctypes.data for s_ in slabs])
+    fn = getattr(emu, f"emu_rows_r2c_peers_{n}")
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(C.c_void_p), C.c_uint, C.c_uint, sz, sz, vp, vp, vp, sz, sz]
+    variant = host.mcu_rows_variant(n, IN_COMPLEX, 4)
+    assert variant == host.mcu_rows_variant(n, IN_COMPLEX, OUT_R2C)
+    tw = engine_table(host, n, -1, variant)
+    assert fn(bases, peers, int(math.log2(width)), row0, width, r.ctypes.data, tw.ctypes.data, resolve_twiddles(-1, n).ctypes.data, n, batch) == 0
+    for b in range(batch):
+        want = oracle.r2c(r[b])
+        got = np.concatenate([s_[row0 + b] for s_ in slabs])
+        assert got.shape == want.shape
+        assert cpu_libs.rel_l2(got, want) <= max(tol(2 * n), 2e-7)
+    for s_ in slabs:
+        assert np.all(np.isnan(s_[:row0].real)) and np.all(np.isnan(s_[row0 + batch:].real)), "wrote outside its rows"
+
+
 @pytest.mark.parametrize("n", [512, 16384])
 @pytest.mark.parametrize("mono", [False, True])
 def test_rows_partitioned_multiply(emu_rows, host, oracle, n, mono):

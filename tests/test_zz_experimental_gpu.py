@@ -95,3 +95,61 @@ def test_fused_2d_real(m, torch, oracle, nx, ny, flags):
     want = oracle.r2c_2d(x[batch - 1].cpu().numpy(), flags)[:, :width]
     g1 = got[batch - 1].cpu().numpy()
     assert float(np.linalg.norm(g1 - want) / np.linalg.norm(want)) <= tol(nx * ny)
+
+
+def _rworker_p2p(rank, world, port, nx, ny, result):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import mufft_b200
+        from mufft_b200.slab import SlabRFFT2D
+        assert mufft_b200.mufft_cuda_set_device(rank) == 0
+        g = torch.Generator(device="cpu").manual_seed(13)
+        full = torch.rand(ny, nx, generator=g) - 0.5
+        rl = ny // world
+        plan = SlabRFFT2D(nx, ny, device=dev, exchange="p2p")
+        mine = full[rank * rl:(rank + 1) * rl].contiguous().to(dev)
+        spec = torch.empty((ny, plan.cols_local), dtype=torch.complex64, device=dev)
+        back = torch.empty((rl, nx), dtype=torch.float32, device=dev)
+        buf = plan.buffers()
+        for _ in range(2):
+            plan.forward(spec, mine, buf=buf)
+            plan.inverse(back, spec, buf=buf)
+        torch.cuda.synchronize()
+        ref = torch.fft.rfft2(full.to(dev).to(torch.float64))
+        lo = rank * plan.cols_even
+        want = ref[:, lo:lo + plan.cols_local]
+        e1 = (torch.linalg.vector_norm(spec.to(torch.complex128) - want) / torch.linalg.vector_norm(want)).item()
+        e2 = (torch.linalg.vector_norm(back.double() / (nx * ny) - mine.double()) / torch.linalg.vector_norm(mine.double())).item()
+        result[rank] = max(e1, e2)
+        plan.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nx,ny", [(256, 128), (4096, 2048), (32768, 512)])
+def test_slab_2d_real_p2p(nx, ny):
+    """SlabRFFT2D(exchange="p2p"): the R2C row kernel's epilogue scatters the half spectrum into the column slabs
+    (one rank with one GPU - the scatter still runs, every bin to the own slab -, one process per GPU otherwise)."""
+    import socket
+
+    import torch
+    import torch.multiprocessing as mp
+    world = min(4, torch.cuda.device_count())
+    while world & (world - 1):
+        world -= 1
+    with socket.socket() as s_:
+        s_.bind(("127.0.0.1", 0))
+        port = s_.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    result = ctx.Manager().dict()
+    procs = [ctx.Process(target=_rworker_p2p, args=(r, world, port, nx, ny, result)) for r in range(world)]
+    [p_.start() for p_ in procs]
+    [p_.join(300) for p_ in procs]
+    assert all(p_.exitcode == 0 for p_ in procs), [p_.exitcode for p_ in procs]
+    assert len(result) == world and max(result.values()) <= tol(nx * ny), dict(result)
