@@ -7,6 +7,8 @@
 #include "abi.h"
 #include "fft_engine.cuh"
 #include "rows_kernel.cuh"
+#include "generic_kernels.cuh"
+#include "engine_tables.h"
 
 #include <atomic>
 #include <math.h>
@@ -42,38 +44,6 @@ cudaError_t rowsc_launch_65536(const mcu_rows_args &, cudaStream_t);
 
 static std::atomic<unsigned long long> g_launches{0};
 
-// ---- generic Stockham pass ----------------------------------------------------------------
-template <int RADIX, int DIR>
-__global__ void __launch_bounds__(256) stockham_pass_kernel(const mcu_pass_args a)
-{
-    const size_t q = a.n / RADIX;
-    const size_t total = q * a.width;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const size_t x = idx % a.width;
-    const size_t i = idx / a.width;
-    const size_t k = i & (size_t)(a.p - 1);
-    const size_t base = (i - k) * RADIX + k;
-    const size_t step = a.n / ((size_t)RADIX * a.p);
-    const cpx *__restrict__ roots = static_cast<const cpx *>(a.roots);
-
-    for (size_t b = blockIdx.y; b < a.batch; b += gridDim.y) {
-        const cpx *__restrict__ in = static_cast<const cpx *>(a.in) + b * a.in_batch + x;
-        cpx *__restrict__ out = static_cast<cpx *>(a.out) + b * a.out_batch + x;
-        cpx v[RADIX];
-#pragma unroll
-        for (int m = 0; m < RADIX; m++)
-            v[m] = (a.half && m >= RADIX / 2) ? make_float2(0.0f, 0.0f) : in[(i + m * q) * a.in_stride];
-        if (a.p > 1) {
-#pragma unroll
-            for (int m = 1; m < RADIX; m++) v[m] = cmul(v[m], __ldg(roots + k * m * step));
-        }
-        dft_regs<RADIX, DIR>(v);
-#pragma unroll
-        for (int r = 0; r < RADIX; r++) out[(base + (size_t)r * a.p) * a.out_stride] = v[r];
-    }
-}
-
 template <int RADIX>
 static cudaError_t launch_pass_radix(const mcu_pass_args &a, cudaStream_t stream)
 {
@@ -86,77 +56,6 @@ static cudaError_t launch_pass_radix(const mcu_pass_args &a, cudaStream_t stream
     else stockham_pass_kernel<RADIX, 1><<<grid, 256, 0, stream>>>(a);
     return cudaGetLastError();
 }
-
-// ---- stand-alone resolve / multiply -----------------------------------------------------
-__global__ void __launch_bounds__(256) resolve_kernel(const mcu_resolve_args a)
-{
-    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= a.n) return;
-    const unsigned n = a.n;
-    const cpx *__restrict__ rtw = static_cast<const cpx *>(a.rtw);
-    for (size_t b = blockIdx.y; b < a.batch; b += gridDim.y) {
-        const cpx *__restrict__ in = static_cast<const cpx *>(a.in) + b * a.in_stride;
-        const cpx *__restrict__ in2 = a.in2 ? static_cast<const cpx *>(a.in2) + b * a.in2_stride : in;
-        cpx *__restrict__ out = static_cast<cpx *>(a.out) + b * a.out_stride;
-        if (a.mode == MCU_RES_MUL) {
-            out[k] = cscale(a.norm, cmul(in[k], in2[k]));
-        } else if (a.mode == MCU_RES_C2R || a.mode == MCU_RES_MUL_C2R) {
-            cpx xa = in[k], xb = in[n - k];
-            if (a.mode == MCU_RES_MUL_C2R) {
-                xa = cscale(a.norm, cmul(xa, in2[k]));
-                xb = cscale(a.norm, cmul(xb, in2[n - k]));
-            }
-            xb = cconj(xb);
-            out[k] = cadd(cadd(xa, xb), cmul(csub(xa, xb), __ldg(rtw + k)));
-        } else {
-            const cpx za = in[k];
-            if (k == 0) {
-                out[0] = make_float2(za.x + za.y, 0.0f);
-                out[n] = make_float2(za.x - za.y, 0.0f);
-            } else {
-                const cpx zb = cconj(in[n - k]);
-                const cpx fe = cadd(za, zb);
-                const cpx fo = cmul(__ldg(rtw + k), csub(za, zb));
-                out[k] = cscale(0.5f, cadd(fe, fo));
-                if (a.mode == MCU_RES_R2C_FULL) out[k + n] = cscale(0.5f, csub(fe, fo));
-            }
-        }
-    }
-}
-
-// ---- engine twiddle tables -----------------------------------------------------------------
-template <int N, int V>
-static void fill_table(float *table, int direction)
-{
-    constexpr int passes = engine_num_passes(N, V);
-    for (int j = 1; j < passes; j++) {
-        const int r = engine_radix(N, j, V), p = engine_span(N, j, V);
-        float *block = table + 2 * (size_t)engine_tw_offset(N, j, V);
-        for (int m = 1; m < r; m++)
-            for (int k = 0; k < p; k++) {
-                // exp(dir * 2*pi*i * k*m / (r*p)), evaluated in double and rounded once, the way
-                // the reference builds its tables (ref fft.c:102-106).
-                const double phase = (M_PI * direction * 2.0 * (double)(k * m)) / (double)(r * p);
-                block[2 * ((size_t)(m - 1) * p + k) + 0] = (float)cos(phase);
-                block[2 * ((size_t)(m - 1) * p + k) + 1] = (float)sin(phase);
-            }
-    }
-}
-
-template <int N>
-static void fill_table_variant(float *table, int direction, int variant)
-{
-    if (variant == 1) { if constexpr (engine_variant_exists(N, 1)) fill_table<N, 1>(table, direction); }
-    else if (variant == 2) { if constexpr (engine_variant_exists(N, 2)) fill_table<N, 2>(table, direction); }
-    else fill_table<N, 0>(table, direction);
-}
-
-#define MUFFT_FOR_CONV_SIZES(X) \
-    X(2) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192)
-// row kernels also exist for MCU_ENGINE_BIG_N
-#define MUFFT_FOR_ENGINE_SIZES(X) MUFFT_FOR_CONV_SIZES(X) X(16384)
-// lengths with an engine twiddle table: the above and the cluster shapes (rowsc_kernel.cuh)
-#define MUFFT_FOR_TABLE_SIZES(X) MUFFT_FOR_ENGINE_SIZES(X) X(32768) X(65536)
 
 } // namespace mufft
 
@@ -265,37 +164,10 @@ int mcu_prefetch(const void *ptr, size_t bytes, int to_device, void *stream)
 }
 
 // ---- engine twiddle tables (see fill_table above) --------------------------------------------
-int mcu_rows_variant(unsigned n, int in_mode, int out_mode)
-{
-    // the kernels' own choice (rows_kernel.cuh), so that the table handed to a kernel is always the
-    // one of the shape it was compiled for
-    switch (n) {
-#define X(v) case v: return rows_variant(v, in_mode, out_mode);
-        MUFFT_FOR_ENGINE_SIZES(X)
-#undef X
-    default: return 0;
-    }
-}
-
-size_t mcu_engine_table_size(unsigned n, int variant)
-{
-    switch (n) {
-#define X(v) case v: return (size_t)(variant == 1 ? engine_tw_total(v, 1) : variant == 2 ? engine_tw_total(v, 2) : engine_tw_total(v, 0)) + 1;
-        MUFFT_FOR_TABLE_SIZES(X)
-#undef X
-    default: return 0;
-    }
-}
-
-void mcu_engine_table_fill(float *table, unsigned n, int direction, int variant)
-{
-    switch (n) {
-#define X(v) case v: fill_table_variant<v>(table, direction, variant); break;
-        MUFFT_FOR_TABLE_SIZES(X)
-#undef X
-    default: break;
-    }
-}
+int mcu_rows_variant(unsigned n, int in_mode, int out_mode) { return tables_rows_variant(n, in_mode, out_mode); }
+size_t mcu_engine_table_size(unsigned n, int variant) { return tables_size(n, variant); }
+void mcu_engine_table_fill(float *table, unsigned n, int direction, int variant) { tables_fill(table, n, direction, variant); }
+unsigned mcu_split_n2(unsigned n, int columns) { return tables_split_n2(n, columns); }
 
 // ---- launches -------------------------------------------------------------------------------
 int mcu_launch_rows(const mcu_rows_args *a, void *stream)
@@ -369,23 +241,6 @@ int mcu_launch_2d_fused(const mcu_2d_args *a, void *stream)
     MUFFT_F2D_SHAPES(X)
 #undef X
     return (int)cudaErrorInvalidValue;
-}
-
-// n = n1 * n2 with n1 <= 2048 (column kernel) and n2 in {256, 512, 1024} (row kernel B)
-unsigned mcu_split_n2(unsigned n, int columns)
-{
-    if (n <= MCU_COLS_MAX_N || (n & (n - 1)) != 0) return 0;
-    // MUFFT_CUDA_SPLIT_N2=<256|512|1024>: measurement knob, overrides the choice where it is legal
-    static const unsigned forced = [] { const char *e = getenv("MUFFT_CUDA_SPLIT_N2"); return e ? (unsigned)atoi(e) : 0u; }();
-    if ((forced == 256 || forced == 512 || forced == 1024) && n / forced >= 2 && n / forced <= MCU_COLS_MAX_N) return forced;
-    // Row transforms: the widest second factor wins from 32768 points on (measured on B200,
-    // profiles/README.md section 3: N = 32768 4.06 -> 3.52 ms, N = 2^20 6.00 -> 4.27 ms with 1024 instead
-    // of 256 / 512).  Column transforms keep the narrow split they were measured with.
-    if (!columns && n >= 32768u && n <= 2048u * 1024u) return 1024;
-    if (n <= 2048u * 256u) return 256;
-    if (n <= 2048u * 512u) return 512;
-    if (n <= 2048u * 1024u) return 1024;
-    return 0;
 }
 
 int mcu_launch_rowst(const mcu_rowst_args *a, void *stream)
