@@ -19,3 +19,21 @@ extern "C" int EMU_CAT(emu_cols_, EMU_N)(int direction, void *out, const void *i
     else emu::launch(grid, cols_cta_threads(N), cols_smem_bytes(N), 1, 1, [&] { fft_cols_kernel<N, 1, false>(a); });
     return 0;
 }
+
+extern "C" int EMU_CAT(emu_launch_cols_, EMU_N)(const mcu_cols_args *a)
+{
+    constexpr int N = EMU_N;
+    const emu::idx3 grid{ (unsigned)((a->width + cols_tile(N) - 1) / cols_tile(N)), (unsigned)(a->batch > 65535 ? 65535 : a->batch), 1 };
+    if (grid.x == 0 || grid.y == 0) return 0;
+    if (a->roots != nullptr) {
+        if constexpr (N == 256 || N == 512 || N == 1024) {
+            if (a->direction < 0) emu::launch(grid, cols_cta_threads(N), cols_smem_bytes(N), 1, 1, [&] { fft_cols_kernel<N, -1, true>(*a); });
+            else emu::launch(grid, cols_cta_threads(N), cols_smem_bytes(N), 1, 1, [&] { fft_cols_kernel<N, 1, true>(*a); });
+            return 0;
+        }
+        return 1;
+    }
+    if (a->direction < 0) emu::launch(grid, cols_cta_threads(N), cols_smem_bytes(N), 1, 1, [&] { fft_cols_kernel<N, -1, false>(*a); });
+    else emu::launch(grid, cols_cta_threads(N), cols_smem_bytes(N), 1, 1, [&] { fft_cols_kernel<N, 1, false>(*a); });
+    return 0;
+}

@@ -66,3 +66,18 @@ extern "C" int EMU_CAT(emu_2d_fused_real_, EMU_NX, x, EMU_NY)(int full, void *ou
     }
     return -3;
 }
+
+// struct-taking entry point for the emulated CUDA side (emu_abi.cpp): the flavour the product launcher would pick
+extern "C" int EMU_CAT(emu_launch_2d_, EMU_NX, x, EMU_NY)(const mcu_2d_args *a, unsigned ctas)
+{
+    constexpr int NX = EMU_NX, NY = EMU_NY;
+    mcu_2d_args b = *a;
+    if (b.lag == 0) b.lag = 1;
+    const emu::idx3 grid{ ctas, 1, 1 };
+    if (b.out_mode == MCU_OUT_R2C || b.out_mode == MCU_OUT_R2C_FULL)
+        return EMU_CAT(emu_2d_fused_real_, EMU_NX, x, EMU_NY)(b.out_mode == MCU_OUT_R2C_FULL, b.out, b.in, b.tw_x, b.tw_y, b.rtw, b.counters, b.batch, b.lag, ctas);
+    constexpr int FLAGS = F2D_ONE_SIDED | F2D_DERIVE;
+    if (b.direction < 0) emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, -1, FLAGS>(b); });
+    else emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, 1, FLAGS>(b); });
+    return 0;
+}

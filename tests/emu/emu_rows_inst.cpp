@@ -41,6 +41,7 @@ static int dispatch(const mcu_rows_args &a)
     if (a.out_mode != MCU_OUT_COMPLEX) return -1;
     switch (a.in_mode) {
     case MCU_IN_COMPLEX: return run<1, MCU_IN_COMPLEX, MCU_OUT_COMPLEX>(a);
+    case MCU_IN_HALF: return run<1, MCU_IN_HALF, MCU_OUT_COMPLEX>(a);
     case MCU_IN_C2R: return run<1, MCU_IN_C2R, MCU_OUT_COMPLEX>(a);
     case MCU_IN_MUL: return run<1, MCU_IN_MUL, MCU_OUT_COMPLEX>(a);
     case MCU_IN_MUL_C2R: return run<1, MCU_IN_MUL_C2R, MCU_OUT_COMPLEX>(a);
@@ -49,6 +50,9 @@ static int dispatch(const mcu_rows_args &a)
     default: return -1;
     }
 }
+
+// struct-taking entry point for the emulated CUDA side (emu_abi.cpp)
+extern "C" int EMU_CAT(emu_launch_rows_, EMU_N)(const mcu_rows_args *a) { return dispatch(*a); }
 
 extern "C" int EMU_CAT(emu_rows_, EMU_N)(int direction, int in_mode, int out_mode, void *out, const void *in, const void *in2,
                                          const void *tw, const void *rtw, size_t out_stride, size_t in_stride, size_t in2_stride,

@@ -42,3 +42,16 @@ extern "C" int EMU_CAT(emu_rows_cluster_, EMU_N)(int direction, int in_mode, int
         return direction < 0 ? run<-1, MCU_IN_COMPLEX, MCU_OUT_PEERS>(a, clusters) : run<1, MCU_IN_COMPLEX, MCU_OUT_PEERS>(a, clusters);
     return -1;
 }
+
+extern "C" int EMU_CAT(emu_launch_rows_cluster_, EMU_N)(const mcu_rows_args *a)
+{
+    const unsigned clusters = a->batch < 2 ? (unsigned)a->batch : 2u;
+    if (clusters == 0) return 0;
+    if (a->in_mode == MCU_IN_COMPLEX && a->out_mode == MCU_OUT_COMPLEX)
+        return a->direction < 0 ? run<-1, MCU_IN_COMPLEX, MCU_OUT_COMPLEX>(*a, clusters) : run<1, MCU_IN_COMPLEX, MCU_OUT_COMPLEX>(*a, clusters);
+    if (a->in_mode == MCU_IN_HALF && a->out_mode == MCU_OUT_COMPLEX)
+        return a->direction < 0 ? run<-1, MCU_IN_HALF, MCU_OUT_COMPLEX>(*a, clusters) : run<1, MCU_IN_HALF, MCU_OUT_COMPLEX>(*a, clusters);
+    if (a->in_mode == MCU_IN_COMPLEX && a->out_mode == MCU_OUT_PEERS)
+        return a->direction < 0 ? run<-1, MCU_IN_COMPLEX, MCU_OUT_PEERS>(*a, clusters) : run<1, MCU_IN_COMPLEX, MCU_OUT_PEERS>(*a, clusters);
+    return 1;
+}

@@ -1,0 +1,270 @@
+"""The C host layer (mufft_b200/csrc/mufft_host.c, unchanged) on top of an emulated CUDA side
+(tests/emu/emu_abi.cpp + the kernel templates on the CPU emulation): the whole fft.h /
+mufft_cuda.h surface runs on the CPU and is checked against the oracle.
+
+What this covers that the kernel-level emulation tests do not: plan construction and validation,
+which path and which twiddle table a plan takes, chunking, the staged path for ordinary host
+memory, the 2D and convolution orchestration, the path switches.  It is test infrastructure:
+libmufft_hostemu.so lives under tests/emu/_build and nothing in the package or the bench loads it.
+"""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cpu_libs
+
+EMU_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+vp, sz, u, i32 = C.c_void_p, C.c_size_t, C.c_uint, C.c_int
+
+
+def tol(n):
+    return max(1e-6 * math.log2(n), 2e-7)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    subprocess.run(["make", "-s", "-C", EMU_DIR, "-j", str(min(8, os.cpu_count() or 1))], check=True)
+    path = os.path.join(EMU_DIR, "_build", "libmufft_hostemu.so")
+    wrapped = cpu_libs._CpuLib(path, "mufft_")  # the numpy-level wrapper the GPU parity tests use
+    raw = wrapped.lib
+    for name, res, args in [
+        ("mufft_cuda_set_onchip_limit", None, [u]), ("mufft_cuda_set_fused_2d", None, [i32]), ("mufft_cuda_set_fused_2d_real", None, [i32]),
+        ("mufft_cuda_set_cluster_rows", None, [i32]), ("mufft_cuda_set_two_kernel", None, [i32]), ("mufft_cuda_launch_count", C.c_ulonglong, [i32]),
+        ("mufft_cuda_last_error", C.c_char_p, []), ("mufft_alloc", vp, [sz]), ("mufft_free", None, [vp]),
+        ("mufft_execute_plan_1d_batch", i32, [vp, vp, vp, sz, sz, sz]), ("mufft_execute_plan_2d_batch", i32, [vp, vp, vp, sz]),
+        ("mufft_execute_conv_batch", i32, [vp, vp, vp, vp, sz, sz]), ("mufft_execute_conv_input_batch", i32, [vp, u, vp, vp, sz]),
+        ("mufft_execute_conv_output_partitioned_batch", i32, [vp, vp, vp, vp, u, sz]),
+        ("mufft_execute_plan_1d_batch_scatter_async", i32, [vp, C.POINTER(vp), u, sz, vp, sz, sz]), ("mufft_cuda_synchronize", i32, []),
+        ("mufft_cuda_device_alloc", vp, [sz]), ("mufft_cuda_device_free", None, [vp]), ("mufft_cuda_plan_1d_uses_engine", i32, [vp]),
+    ]:
+        fn = getattr(raw, name)
+        fn.restype, fn.argtypes = res, args
+    return wrapped
+
+
+def rnd(rng, *shape):
+    return rng.random(shape, np.float32) - np.float32(0.5)
+
+
+def crnd(rng, *shape):
+    return (rnd(rng, *shape) + 1j * rnd(rng, *shape)).astype(np.complex64)
+
+
+def managed(lib, arr):
+    """A copy of arr in 'managed' memory of the emulated device (used in place by the host layer)."""
+    arr = np.ascontiguousarray(arr)
+    ptr = lib.lib.mufft_alloc(max(arr.nbytes, 8))
+    view = np.ctypeslib.as_array((C.c_uint8 * arr.nbytes).from_address(ptr)).view(arr.dtype).reshape(arr.shape)
+    view[...] = arr
+    return ptr, view
+
+
+@pytest.mark.parametrize("n", [2, 4, 8, 64, 512, 4096, 16384])
+def test_fft_h_1d(lib, oracle, n):
+    """mufft_execute_plan_1d on ordinary host memory (the staged path): C2C both directions, zero pad,
+    R2C half / full, C2R - the reference's own call sequence (ref test.c:33-62)."""
+    rng = np.random.default_rng(n)
+    x = crnd(rng, n)
+    for d in (-1, 1):
+        assert cpu_libs.rel_l2(lib.c2c(x, d), oracle.c2c(x, d)) <= tol(n)
+    if n >= 4:
+        assert cpu_libs.rel_l2(lib.c2c(x[: n // 2], -1, cpu_libs.FLAG_ZERO_PAD, n=n), oracle.c2c(x[: n // 2], -1, cpu_libs.FLAG_ZERO_PAD, n=n)) <= tol(n)
+        r = rnd(rng, n)
+        for flags in (0, cpu_libs.FLAG_FULL_R2C):
+            assert cpu_libs.rel_l2(lib.r2c(r, flags), oracle.r2c(r, flags)) <= tol(n)
+        spec = oracle.r2c(r)
+        assert cpu_libs.rel_l2(lib.c2r(spec, n), oracle.c2r(spec, n)) <= tol(n)
+
+
+def test_constructor_validation_matches_the_reference(lib, oracle):
+    """NULL for non powers of two, N == 1, real transforms of 2 points (ref fft.c:478-481, 517-520, 628-631)."""
+    for kind in ("c2c", "r2c", "c2r"):
+        for n in (0, 1, 2, 3, 6, 12, 100, 4, 64):
+            want = oracle.plan_1d_is_null(kind, n) if n else True  # the reference returns a degenerate plan for 0; we refuse it
+            assert lib.plan_1d_is_null(kind, n) == want, (kind, n)
+
+
+@pytest.mark.parametrize("n,limit,two_kernel", [(16384, 16384, 1), (16384, 8192, 1), (32768, 16384, 1), (65536, 16384, 1), (32768, 16384, 0)])
+def test_long_transforms_pick_their_path(lib, n, limit, two_kernel):
+    """16384 points: one kernel or, with the limit lowered, the two-kernel split; 32768 / 65536: two kernels;
+    with the two-kernel path switched off (as beyond 2^21 points): one generic radix-8/4/2 pass per launch.
+    Launch counts tell which path ran; results against numpy float64."""
+    raw = lib.lib
+    raw.mufft_cuda_set_onchip_limit(limit)
+    raw.mufft_cuda_set_two_kernel(two_kernel)
+    try:
+        rng = np.random.default_rng(n)
+        x = crnd(rng, n)
+        pin, xv = managed(lib, x)
+        pout, yv = managed(lib, np.zeros(n, np.complex64))
+        plan = lib._create_plan_1d_c2c(n, -1, 0)
+        assert plan
+        raw.mufft_cuda_launch_count(1)
+        assert raw.mufft_execute_plan_1d_batch(plan, pout, pin, 1, 0, 0) == 0, raw.mufft_cuda_last_error()
+        launches = raw.mufft_cuda_launch_count(1)
+        expect = 1 if n <= limit else (2 if two_kernel else math.ceil(math.log2(n) / 3))
+        assert launches == expect
+        assert raw.mufft_cuda_plan_1d_uses_engine(plan) == (1 if n <= limit else 0)
+        lib._free_plan_1d(plan)
+        assert cpu_libs.rel_l2(yv, np.fft.fft(x.astype(np.complex128))) <= tol(n)
+        raw.mufft_free(pin)
+        raw.mufft_free(pout)
+    finally:
+        raw.mufft_cuda_set_onchip_limit(16384)
+        raw.mufft_cuda_set_two_kernel(1)
+
+
+@pytest.mark.parametrize("n", [32768, 65536])
+@pytest.mark.parametrize("mode", [1, 2])
+def test_cluster_rows_switch(lib, n, mode):
+    """mufft_cuda_set_cluster_rows: plans created afterwards run 32768 / 65536-point rows in ONE launch (the
+    cluster kernel, both exchange flavours); zero-padded too; a real transform of that complex length keeps
+    the two-kernel path."""
+    raw = lib.lib
+    raw.mufft_cuda_set_cluster_rows(mode)
+    try:
+        rng = np.random.default_rng(n + mode)
+        x = crnd(rng, 2, n)
+        pin, _ = managed(lib, x)
+        pout, yv = managed(lib, np.zeros((2, n), np.complex64))
+        for flags, cols in ((0, n), (cpu_libs.FLAG_ZERO_PAD, n // 2)):
+            plan = lib._create_plan_1d_c2c(n, 1, flags)
+            raw.mufft_cuda_launch_count(1)
+            assert raw.mufft_execute_plan_1d_batch(plan, pout, pin, 2, 0, n * 8) == 0, raw.mufft_cuda_last_error()
+            assert raw.mufft_cuda_launch_count(1) == 1
+            lib._free_plan_1d(plan)
+            xp = np.zeros((2, n), np.complex128)
+            xp[:, :cols] = x[:, :cols]
+            want = np.fft.ifft(xp, axis=1, norm="forward")
+            assert cpu_libs.rel_l2(yv, want) <= tol(n)
+        raw.mufft_free(pin)
+        raw.mufft_free(pout)
+    finally:
+        raw.mufft_cuda_set_cluster_rows(0)
+
+
+@pytest.mark.parametrize("nx,ny", [(16, 8), (64, 64), (256, 256), (512, 256), (32, 2048), (4096, 4)])
+def test_fft_h_2d(lib, oracle, nx, ny):
+    """mufft_execute_plan_2d: C2C both directions (fused kernel for 256 x 256 and 512 x 256 here, row + column
+    kernels otherwise), R2C half / full with the reference's pitch, C2R with its scratch-sized output."""
+    rng = np.random.default_rng(nx + ny)
+    x = crnd(rng, ny, nx)
+    for d in (-1, 1):
+        assert cpu_libs.rel_l2(lib.c2c_2d(x, d), oracle.c2c_2d(x, d)) <= tol(nx * ny)
+    if nx >= 4:
+        r = rnd(rng, ny, nx)
+        for flags in (0, cpu_libs.FLAG_FULL_R2C):
+            w = nx if flags else nx // 2 + 1
+            assert cpu_libs.rel_l2(lib.r2c_2d(r, flags)[:, :w], oracle.r2c_2d(r, flags)[:, :w]) <= tol(nx * ny)
+        spec = oracle.r2c_2d(r)
+        assert cpu_libs.rel_l2(lib.c2r_2d(spec), oracle.c2r_2d(spec)) <= tol(nx * ny)
+
+
+@pytest.mark.parametrize("fused_real", [0, 1])
+def test_fused_2d_real_switch(lib, oracle, fused_real):
+    """2D R2C of 512 x 256 reals (row transforms of 256 complex points): with the switch on the whole batch is
+    ONE launch of the fused kernel, otherwise a row launch and a column launch through plan scratch."""
+    raw = lib.lib
+    nx, ny, batch = 512, 256, 3
+    raw.mufft_cuda_set_fused_2d_real(fused_real)
+    try:
+        rng = np.random.default_rng(5)
+        r = rnd(rng, batch, ny, nx)
+        pin, _ = managed(lib, r)
+        pout, yv = managed(lib, np.zeros((batch, ny, nx), np.complex64))
+        plan = lib._create_plan_2d_r2c(nx, ny, 0)
+        raw.mufft_cuda_launch_count(1)
+        assert raw.mufft_execute_plan_2d_batch(plan, pout, pin, batch) == 0, raw.mufft_cuda_last_error()
+        assert raw.mufft_cuda_launch_count(1) == (1 if fused_real else 2)
+        lib._free_plan_2d(plan)
+        for b in range(batch):
+            want = oracle.r2c_2d(r[b])[:, : nx // 2 + 1]
+            assert cpu_libs.rel_l2(yv[b][:, : nx // 2 + 1], want) <= tol(nx * ny)
+        raw.mufft_free(pin)
+        raw.mufft_free(pout)
+    finally:
+        raw.mufft_cuda_set_fused_2d_real(0)
+
+
+@pytest.mark.parametrize("n", [8, 256, 2048, 16384, 32768])
+@pytest.mark.parametrize("method", [0, 1, 1 | 4 | 8, 0 | 4 | 8])
+def test_fft_h_convolution(lib, oracle, n, method):
+    """conv_input x 2 + conv_output as the reference's callers do (ref test.c:375-431), mono and stereo, with
+    and without zero padding; block sizes as the reference reports them."""
+    rng = np.random.default_rng(n + method)
+    stereo = method & 1
+    la = n // 2 if method & 4 else n
+    lb = n // 2 if method & 8 else n
+    a = crnd(rng, la) if stereo else rnd(rng, la)
+    b = rnd(rng, lb)
+    got, s0, s1 = lib.conv(a, b, n, method)
+    want, w0, w1 = oracle.conv(a, b, n, method)
+    assert s0.size == w0.size
+    assert cpu_libs.rel_l2(got, want) <= 2 * tol(n)
+
+
+@pytest.mark.parametrize("n,parts,stereo", [(64, 3, 1), (1024, 2, 0), (8192, 3, 0), (16384, 2, 1)])
+def test_partitioned_convolution(lib, oracle, n, parts, stereo):
+    """mufft_execute_conv_output_partitioned_batch through the host layer (the mono case needs the table of the
+    mirrored-first-pass shape where one exists: 8192 reals = 4096 complex points)."""
+    raw = lib.lib
+    method = stereo | 4 | 8
+    batch, half = 3, n // 2
+    total = batch + parts - 1
+    rng = np.random.default_rng(n + parts)
+    x = crnd(rng, total, half) if stereo else rnd(rng, total, half)
+    taps = rnd(rng, parts, half)
+    plan = lib._create_plan_conv(n, 0, method)
+    blk = lib._conv_get_transformed_block_size(plan)
+    px, _ = managed(lib, x)
+    pt, _ = managed(lib, taps)
+    ps, _ = managed(lib, np.zeros(total * blk, np.uint8))
+    pf, _ = managed(lib, np.zeros(parts * blk, np.uint8))
+    po, out = managed(lib, np.zeros((batch, n), np.complex64 if stereo else np.float32))
+    assert raw.mufft_execute_conv_input_batch(plan, 0, ps, px, total) == 0
+    assert raw.mufft_execute_conv_input_batch(plan, 1, pf, pt, parts) == 0
+    assert raw.mufft_execute_conv_output_partitioned_batch(plan, po, ps + (parts - 1) * blk, pf, parts, batch) == 0, raw.mufft_cuda_last_error()
+    lib._free_plan_conv(plan)
+    for b in range(batch):
+        want = sum(oracle.conv(x[b + parts - 1 - p], taps[p], n, method)[0].astype(np.complex128 if stereo else np.float64) for p in range(parts))
+        assert cpu_libs.rel_l2(out[b], want) <= 2 * tol(n)
+    for p in (px, pt, ps, pf, po):
+        raw.mufft_free(p)
+
+
+@pytest.mark.parametrize("kind,n", [("c2c", 1024), ("c2c", 16384), ("r2c", 2048), ("r2c", 32768)])
+def test_scatter_to_column_slabs(lib, oracle, kind, n):
+    """mufft_execute_plan_1d_batch_scatter_async (exchange step of the slab transforms) with every 'peer' slab in
+    local memory: C2C rows, and R2C rows whose Nyquist bin rides with the last slab."""
+    raw = lib.lib
+    peers, batch, row0 = 4, 3, 2
+    rng = np.random.default_rng(n)
+    if kind == "c2c":
+        x = crnd(rng, batch, n)
+        plan, bins, want = lib._create_plan_1d_c2c(n, -1, 0), n, [oracle.c2c(x[b], -1) for b in range(batch)]
+    else:
+        x = rnd(rng, batch, n)
+        plan, bins, want = lib._create_plan_1d_r2c(n, 0), n // 2, [oracle.r2c(x[b]) for b in range(batch)]
+    width = bins // peers
+    widths = [width] * (peers - 1) + [width + (1 if kind == "r2c" else 0)]
+    rows_total = batch + row0 + 1
+    slabs = [raw.mufft_cuda_device_alloc(rows_total * w * 8) for w in widths]
+    views = [np.ctypeslib.as_array((C.c_float * (2 * rows_total * w)).from_address(s)).view(np.complex64).reshape(rows_total, w) for s, w in zip(slabs, widths)]
+    for v in views:
+        v[...] = np.nan
+    pin, _ = managed(lib, x)
+    arr = (vp * peers)(*slabs)
+    assert raw.mufft_execute_plan_1d_batch_scatter_async(plan, arr, peers, row0, pin, batch, 0) == 0, raw.mufft_cuda_last_error()
+    assert raw.mufft_cuda_synchronize() == 0
+    for b in range(batch):
+        got = np.concatenate([v[row0 + b] for v in views])
+        assert cpu_libs.rel_l2(got, want[b]) <= tol(n)
+    assert all(np.all(np.isnan(v[:row0].real)) and np.all(np.isnan(v[row0 + batch:].real)) for v in views)
+    lib._free_plan_1d(plan)
+    raw.mufft_free(pin)
+    for s in slabs:
+        raw.mufft_cuda_device_free(s)
