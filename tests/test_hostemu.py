@@ -268,3 +268,17 @@ def test_scatter_to_column_slabs(lib, oracle, kind, n):
     raw.mufft_free(pin)
     for s in slabs:
         raw.mufft_cuda_device_free(s)
+
+
+@pytest.mark.skipif(os.environ.get("MUFFT_TEST_SLOW") != "1", reason="about 8 minutes of CPU: set MUFFT_TEST_SLOW=1")
+def test_reference_test_suite_passes_on_the_emulation(lib):
+    """The reference's OWN test.c (compiled unchanged, FFTW replaced by oracle/fftw3_shim) against the host layer
+    on the emulated CUDA side: all 3144 cases of its sweep (ref test.c:493-579) with the reference's thresholds.
+    The same binary built against libmufft_b200.so runs on the GPU in tests/test_consumers.py."""
+    if not os.path.isdir("/root/reference") or not os.path.exists(os.path.join(EMU_DIR, "..", "..", "oracle", "_ref", "fftw3_shim.o")):
+        pytest.skip("needs /root/reference and `make -C oracle consumers`")
+    subprocess.run(["make", "-s", "-C", EMU_DIR, "consumer"], check=True)
+    res = subprocess.run([os.path.join(EMU_DIR, "_build", "muFFT-test-hostemu")], capture_output=True, text=True, timeout=3000)
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
+    assert res.stdout.rstrip().endswith("All tests passed!")
+    assert res.stdout.count("... Passed") > 2500
