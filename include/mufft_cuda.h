@@ -13,7 +13,9 @@
  *   C2C      in N*8 (N/2*8 with ZERO_PAD_UPPER_HALF)   out N*8
  *   R2C      in N*4 (N/2*4 zero padded)                out (N/2+1)*8, or N*8 with FULL_R2C
  *   C2R      in (N/2+1)*8                              out N*4
- * Strides must be multiples of 8 bytes and buffers 8-byte aligned.
+ * Strides must be multiples of 8 bytes.  Buffers should be 8-byte aligned (mufft_alloc gives 256): a
+ * buffer that is not - a float array with 4-byte alignment on the real side of R2C / C2R - is never
+ * used in place but staged like host memory (synchronous calls only; the async calls refuse it).
  */
 #ifndef MUFFT_CUDA_H__
 #define MUFFT_CUDA_H__

@@ -404,6 +404,8 @@ typedef struct io_desc {
     size_t count;
 } io_desc;
 
+#define ALIGNED(ptr) (((uintptr_t)(ptr) % CPX) == 0)
+
 static int copy_units(void *dst, size_t dpitch, const void *src, size_t spitch, size_t unit, size_t count, void *stream)
 {
     if (dpitch == unit && spitch == unit) return mcu_copy_async(dst, src, unit * count, stream);
@@ -418,12 +420,16 @@ static int run_any(stage *st, unit_launch fn, void *ctx, const io_desc *io, int 
     if (io->count == 0) return 0;
     const size_t span_in = io->in_stride * (io->count - 1) + io->in_unit;
     const size_t span_out = io->out_stride * (io->count - 1) + io->out_unit;
-    const int vis_in = device_visible(mcu_pointer_kind(io->in), span_in);
-    const int vis_out = device_visible(mcu_pointer_kind(io->out), span_out);
+    /* The kernels move 8-byte complex values: a buffer that is not 8-byte aligned (legal for the real
+     * side of R2C / C2R, e.g. a float array on the caller's stack; the reference's scalar path accepts
+     * it) cannot be used in place, whatever memory it is.  It takes the staged path below, whose
+     * copies have no alignment rule. */
+    const int vis_in = ALIGNED(io->in) && device_visible(mcu_pointer_kind(io->in), span_in);
+    const int vis_out = ALIGNED(io->out) && device_visible(mcu_pointer_kind(io->out), span_out);
     int vis_in2 = 1;
     if (io->in2) {
         size_t span2 = io->in2_stride ? io->in2_stride * (io->count - 1) + io->in2_unit : io->in2_unit;
-        vis_in2 = device_visible(mcu_pointer_kind(io->in2), span2);
+        vis_in2 = ALIGNED(io->in2) && device_visible(mcu_pointer_kind(io->in2), span2);
     }
 
     if (vis_in && vis_out && vis_in2) {
@@ -435,7 +441,7 @@ static int run_any(stage *st, unit_launch fn, void *ctx, const io_desc *io, int 
         return 0;
     }
     if (async) {
-        snprintf(tls_error, sizeof(tls_error), "asynchronous execute needs device-accessible (device or managed) pointers");
+        snprintf(tls_error, sizeof(tls_error), "asynchronous execute needs device-accessible (device or managed), 8-byte aligned pointers");
         return -1;
     }
 
@@ -762,9 +768,8 @@ static int exec_1d(mufft_plan_1d *plan, int in_mode, int out_mode, float norm,
     io.out_stride = out_stride ? out_stride : io.out_unit;
     io.in2_stride = in2_stride;
     io.count = batch;
-    if ((io.in_stride | io.out_stride | io.in2_stride) % CPX != 0 ||
-        (((uintptr_t)output | (uintptr_t)input | (uintptr_t)input2) % CPX) != 0) {
-        snprintf(tls_error, sizeof(tls_error), "buffers and strides must be multiples of 8 bytes");
+    if ((io.in_stride | io.out_stride | io.in2_stride) % CPX != 0) {
+        snprintf(tls_error, sizeof(tls_error), "strides must be multiples of 8 bytes");
         return -1;
     }
     return run_any(&plan->st, rows_unit_launch, &ctx, &io, async);
@@ -1033,8 +1038,8 @@ static int conv_fused(mufft_plan_conv *plan, void *output, const void *input, co
     io.out_stride = io.out_unit;
     io.in2_stride = filter_stride;
     io.count = batch;
-    if (filter_stride % CPX != 0 || (((uintptr_t)output | (uintptr_t)input | (uintptr_t)filter) % CPX) != 0) {
-        snprintf(tls_error, sizeof(tls_error), "buffers and strides must be multiples of 8 bytes");
+    if (filter_stride % CPX != 0) {
+        snprintf(tls_error, sizeof(tls_error), "strides must be multiples of 8 bytes");
         return -1;
     }
     return run_any(&plan->plans[0]->st, conv_unit_launch, &ctx, &io, async);
@@ -1395,10 +1400,6 @@ static int exec_2d(mufft_plan_2d *plan, void *output, const void *input, size_t 
     io.in_stride = io.in_unit;
     io.out_stride = io.out_unit;
     io.count = batch;
-    if ((((uintptr_t)output | (uintptr_t)input) % CPX) != 0) {
-        snprintf(tls_error, sizeof(tls_error), "buffers must be 8-byte aligned");
-        return -1;
-    }
     return run_any(&plan->st, image_unit_launch, plan, &io, async);
 }
 

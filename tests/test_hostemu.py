@@ -63,6 +63,49 @@ def managed(lib, arr):
     return ptr, view
 
 
+@pytest.mark.parametrize("where", ["host", "managed"])
+@pytest.mark.parametrize("n", [16, 4096])
+def test_buffers_with_4_byte_alignment_are_staged(lib, oracle, where, n):
+    """A float array need not be 8-byte aligned in C; the reference's scalar path takes it.  The
+    kernels move 8-byte values, so the host layer must stage such a buffer (whatever memory it is in)
+    instead of using it in place - and must not skip the transform."""
+    rng = np.random.default_rng(n)
+    r = rnd(rng, n)
+    if where == "host":
+        raw_in = np.zeros(n * 4 + 64, np.uint8)
+        raw_out = np.zeros((n // 2 + 1) * 8 + 64, np.uint8)
+        base_in, base_out = raw_in.ctypes.data, raw_out.ctypes.data
+    else:
+        base_in, raw_in = managed(lib, np.zeros(n * 4 + 64, np.uint8))
+        base_out, raw_out = managed(lib, np.zeros((n // 2 + 1) * 8 + 64, np.uint8))
+    off_in = (-base_in) % 8 + 4    # 4 mod 8
+    off_out = (-base_out) % 8 + 4
+    raw_in[off_in:off_in + n * 4] = r.view(np.uint8)
+    plan = lib._create_plan_1d_r2c(n, 0)
+    lib.lib.mufft_cuda_launch_count(1)
+    lib._execute_plan_1d(plan, base_out + off_out, base_in + off_in)
+    assert lib.lib.mufft_cuda_launch_count(1) == 1, lib.lib.mufft_cuda_last_error()
+    got = raw_out[off_out:off_out + (n // 2 + 1) * 8].copy().view(np.complex64)
+    assert cpu_libs.rel_l2(got, oracle.r2c(r)) <= tol(n)
+    # and back: complex input aligned, real output misaligned
+    plan_inv = lib._create_plan_1d_c2r(n, 0)
+    spec = cpu_libs.aligned_copy(got, np.complex64)
+    raw_in[:] = 0
+    lib._execute_plan_1d(plan_inv, base_in + off_in, spec.ctypes.data)
+    back = raw_in[off_in:off_in + n * 4].copy().view(np.float32)
+    assert cpu_libs.rel_l2(back, oracle.c2r(spec, n)) <= tol(n)
+    # the asynchronous calls cannot stage: they refuse
+    if where == "managed":
+        fn = lib.lib.mufft_execute_plan_1d_batch_async
+        fn.restype, fn.argtypes = i32, [vp, vp, vp, sz, sz, sz]
+        assert fn(plan, base_out + off_out, base_in + off_in, 1, 0, 0) != 0
+        assert b"aligned" in lib.lib.mufft_cuda_last_error()
+        lib.lib.mufft_free(base_in)
+        lib.lib.mufft_free(base_out)
+    lib._free_plan_1d(plan)
+    lib._free_plan_1d(plan_inv)
+
+
 @pytest.mark.parametrize("n", [2, 4, 8, 64, 512, 4096, 16384])
 def test_fft_h_1d(lib, oracle, n):
     """mufft_execute_plan_1d on ordinary host memory (the staged path): C2C both directions, zero pad,
