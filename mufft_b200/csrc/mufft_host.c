@@ -355,7 +355,17 @@ typedef struct stage {
     void *ev_begin;
     void *ev_kernels;   /* recorded after the kernels of each chunk: the next chunk's kernels wait for it */
     int ready;
+    int device_plus_1;  /* device the owning plan's tables and scratch live on (0 = not bound to a plan) */
 } stage;
+
+/* A plan belongs to the device that was current when it was created: its twiddle tables, scratch and
+ * staging buffers live there.  With one host thread per GPU, executing it while another device is
+ * current would fault inside the kernel; say so instead. */
+static void stage_bind_device(stage *st)
+{
+    int dev = 0;
+    if (mcu_get_device(&dev) == 0) st->device_plus_1 = dev + 1;
+}
 
 static int grow(void **ptr, size_t *have, size_t need)
 {
@@ -392,6 +402,17 @@ static void stage_free(stage *st)
     memset(st, 0, sizeof(*st));
 }
 
+static int stage_check_device(const stage *st)
+{
+    int dev = -1;
+    if (st->device_plus_1 != 0 && mcu_get_device(&dev) == 0 && dev != st->device_plus_1 - 1) {
+        snprintf(tls_error, sizeof(tls_error), "plan was created on CUDA device %d but device %d is current "
+                 "(mufft_cuda_set_device)", st->device_plus_1 - 1, dev);
+        return -1;
+    }
+    return 0;
+}
+
 /* Runs `count` units on device-visible pointers; strides in bytes. */
 typedef int (*unit_launch)(void *ctx, void *out, size_t out_stride, const void *in, size_t in_stride,
                            const void *in2, size_t in2_stride, size_t count, void *stream);
@@ -418,6 +439,7 @@ static int copy_units(void *dst, size_t dpitch, const void *src, size_t spitch, 
 static int run_any(stage *st, unit_launch fn, void *ctx, const io_desc *io, int async)
 {
     if (io->count == 0) return 0;
+    if (stage_check_device(st) != 0) return -1;
     const size_t span_in = io->in_stride * (io->count - 1) + io->in_unit;
     const size_t span_out = io->out_stride * (io->count - 1) + io->out_unit;
     /* The kernels move 8-byte complex values: a buffer that is not 8-byte aligned (legal for the real
@@ -549,6 +571,7 @@ mufft_plan_1d *mufft_create_plan_1d_c2c(unsigned N, int direction, unsigned flag
     plan->direction = direction;
     plan->zero_pad = (flags & MUFFT_FLAG_ZERO_PAD_UPPER_HALF) != 0;
     plan->use_engine = N <= g_onchip_limit;
+    stage_bind_device(&plan->st);
     if (axis_init(&plan->ax, N, direction, plan->use_engine ? 0 : AXIS_ROWS) != 0) {
         mufft_free_plan_1d(plan);
         return NULL;
@@ -808,6 +831,7 @@ int mufft_execute_plan_1d_batch_scatter_async(mufft_plan_1d *plan, void *const *
         snprintf(tls_error, sizeof(tls_error), "scatter: needs a plain C2C or R2C plan and a power-of-two number of devices dividing its complex length");
         return -1;
     }
+    if (stage_check_device(&plan->st) != 0) return -1;
     if (real && plan->ax.d_engine_tw == NULL) {
         snprintf(tls_error, sizeof(tls_error), "scatter: R2C rows must fit the single-kernel engine (N <= %u reals)", 2 * g_onchip_limit);
         return -1;
@@ -866,6 +890,7 @@ int mufft_execute_plan_1d_columns(mufft_plan_1d *plan, void *output, const void 
         snprintf(tls_error, sizeof(tls_error), "columns: needs a plain C2C plan and pitches that are multiples of 8 bytes");
         return -1;
     }
+    if (stage_check_device(&plan->st) != 0) return -1;
     const size_t span_in = input_pitch_bytes * ((size_t)plan->n - 1) + width * CPX;
     const size_t span_out = output_pitch_bytes * ((size_t)plan->n - 1) + width * CPX;
     if (!device_visible(mcu_pointer_kind(input), span_in) || !device_visible(mcu_pointer_kind(output), span_out)) {
@@ -1068,6 +1093,7 @@ static int conv_partitioned(mufft_plan_conv *plan, void *output, const void *spe
         return -1;
     }
     if (batch == 0) return 0;
+    if (stage_check_device(&plan->output_plan->st) != 0) return -1;
     const size_t blk = plan->block_size;
     const size_t out_unit = (size_t)plan->output_plan->n * CPX;
     if ((((uintptr_t)output | (uintptr_t)spectra | (uintptr_t)filter_spectra) % CPX) != 0) {
@@ -1183,6 +1209,7 @@ static mufft_plan_2d *plan_2d_common(unsigned nx, unsigned ny, int direction, in
     plan->kind = kind;
     plan->vertical_nx = nx;
     plan->cols_engine = ny <= MCU_COLS_MAX_N;
+    stage_bind_device(&plan->st);
     if (axis_init(&plan->ax_x, nx, direction, nx > g_onchip_limit ? AXIS_ROWS : 0) != 0 ||
         axis_init(&plan->ax_y, ny, direction, plan->cols_engine ? 0 : AXIS_COLS) != 0) {
         mufft_free_plan_2d(plan);

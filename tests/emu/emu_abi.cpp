@@ -78,9 +78,11 @@ int free_kind(void *p)
 extern "C" {
 
 // ---- runtime ---------------------------------------------------------------------------------------
-int mcu_device_count(int *count) { *count = 1; return 0; }
-int mcu_set_device(int device) { return device == 0 ? 0 : 101; }
-int mcu_get_device(int *device) { *device = 0; return 0; }
+// two "devices" (memory is not tied to either): enough to test the plan / current-device check of the host layer
+static thread_local int t_device = 0;
+int mcu_device_count(int *count) { *count = 2; return 0; }
+int mcu_set_device(int device) { if (device < 0 || device > 1) return 101; t_device = device; return 0; }
+int mcu_get_device(int *device) { *device = t_device; return 0; }
 int mcu_sm_count(int *count) { *count = 4; return 0; }
 const char *mcu_error_string(int err) { return err == 0 ? "no error" : "emulated CUDA side: error"; }
 

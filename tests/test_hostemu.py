@@ -63,6 +63,33 @@ def managed(lib, arr):
     return ptr, view
 
 
+def test_a_plan_belongs_to_the_device_it_was_created_on(lib, oracle):
+    """One host thread per GPU: a plan's tables and scratch live on the device that was current at
+    creation.  Executing it with another device current is refused with a message instead of
+    faulting inside a kernel (the emulation has two devices for this)."""
+    raw = lib.lib
+    raw.mufft_cuda_set_device.restype, raw.mufft_cuda_set_device.argtypes = i32, [i32]
+    n = 64
+    x = cpu_libs.aligned_copy(crnd(np.random.default_rng(1), n), np.complex64)
+    y = cpu_libs.aligned_zeros(n, np.complex64)
+    plan = lib._create_plan_1d_c2c(n, -1, 0)
+    plan2 = lib._create_plan_2d_c2c(16, 16, -1, 0)
+    try:
+        assert raw.mufft_cuda_set_device(1) == 0
+        raw.mufft_cuda_launch_count(1)
+        assert raw.mufft_execute_plan_1d_batch(plan, y.ctypes.data, x.ctypes.data, 1, 0, 0) != 0
+        assert b"device 0 but device 1" in raw.mufft_cuda_last_error()
+        img = cpu_libs.aligned_zeros(256, np.complex64)
+        assert raw.mufft_execute_plan_2d_batch(plan2, img.ctypes.data, img.ctypes.data, 1) != 0
+        assert raw.mufft_cuda_launch_count(1) == 0
+    finally:
+        assert raw.mufft_cuda_set_device(0) == 0
+    assert raw.mufft_execute_plan_1d_batch(plan, y.ctypes.data, x.ctypes.data, 1, 0, 0) == 0
+    assert cpu_libs.rel_l2(y, oracle.c2c(x, -1)) <= tol(n)
+    lib._free_plan_1d(plan)
+    lib._free_plan_2d(plan2)
+
+
 @pytest.mark.parametrize("where", ["host", "managed"])
 @pytest.mark.parametrize("n", [16, 4096])
 def test_buffers_with_4_byte_alignment_are_staged(lib, oracle, where, n):
