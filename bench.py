@@ -359,6 +359,44 @@ def run_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
+# ---- opt-in paths: seconds-long probes appended to the default run -----------------------------------
+def run_optin_probes(seconds_each=60):
+    """The paths that are NOT defaults yet (profiles/README.md section 6) measured next to the run of
+    record: tools/probe_optin.py (ctypes + numpy, parity against numpy float64 on every line), one
+    child process per probe so that a path that misbehaves cannot take the bench line with it; after
+    the first probe that fails or times out the rest is skipped.  Reported under also.optin_probes;
+    nothing here feeds `value`, `roofline` or `e2e`.  MUFFT_BENCH_PROBES=0 switches it off."""
+    keep = ("what", "n", "nx", "ny", "batch", "direction", "fused_mode", "fused_real", "cluster_rows", "spin_sync", "ms", "ms_r2c", "ms_c2r",
+            "gbs", "us_per_call", "launches_per_call", "rel_l2", "ok")
+    out = []
+    t_start = time.time()
+    for what in ("latency", "real2d", "early", "cluster"):
+        if time.time() - t_start > 2.5 * seconds_each:  # keep the default run within minutes
+            out.append({"what": what, "error": "skipped: probe time budget used up"})
+            break
+        try:
+            res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "probe_optin.py"), what], capture_output=True, text=True,
+                                 timeout=seconds_each, cwd=ROOT)
+        except subprocess.TimeoutExpired:
+            out.append({"what": what, "error": f"no result within {seconds_each} s (child killed); remaining probes skipped"})
+            break
+        lines = []
+        for ln in res.stdout.splitlines():
+            if ln.startswith("{"):
+                try:
+                    d = json.loads(ln)
+                except ValueError:
+                    continue
+                if d.get("what") not in ("start", "done"):
+                    lines.append({k: d[k] for k in keep if k in d})
+        if res.returncode != 0:
+            out.append({"what": what, "error": "exit %d: %s" % (res.returncode, res.stderr.strip().splitlines()[-1][:200] if res.stderr.strip() else ""),
+                        "lines": lines})
+            break
+        out.extend(lines)
+    return out
+
+
 # ---- GPU arm ---------------------------------------------------------------------------------------
 class Job:
     """Device-resident buffers + the batched async C-ABI call for one workload."""
@@ -700,6 +738,14 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_reference_sample(kind, n, ny, seconds_of_cpu_work=20.0)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    # last, when every number of the line is in hand: the opt-in paths, each in a child process
+    if world == 1 and args.also and not args.units and args.workload == "c2c4096" and os.environ.get("MUFFT_BENCH_PROBES", "1") != "0":
+        torch.cuda.synchronize()
+        try:
+            also["optin_probes"] = run_optin_probes()
+        except Exception as exc:  # never lose the line over a probe
+            also["optin_probes"] = [{"error": repr(exc)[:200]}]
 
     if rank == 0:
         line = {
