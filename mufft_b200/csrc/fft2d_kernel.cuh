@@ -182,10 +182,16 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
 //                  depends on is read at the START of the tile before it and the answer is in a
 //                  register when the ticket is handed to the CTA: the L2 round trip of that read leaves
 //                  the critical path between two tiles (not measured yet).
+//   F2D_OCC3       compiled for THREE CTAs per SM (80 registers per thread, the excess spilled; 24 warps per
+//                  SM instead of 16).  ncu on the plain kernel: 25 % warp occupancy, issue slots 43 % busy,
+//                  barrier + scoreboard stalls on top - more warps to hide them against the cost of the
+//                  spills (not measured yet).  Not combinable with F2D_SMEM_TW (three exchange areas plus
+//                  three table copies exceed the shared memory of an SM).
 #define F2D_SMEM_TW 1
 #define F2D_ONE_SIDED 2
 #define F2D_DERIVE 4
 #define F2D_EARLY 8
+#define F2D_OCC3 16
 #define F2D_LITE (F2D_SMEM_TW | F2D_ONE_SIDED)
 __host__ __device__ constexpr int f2d_twm(int flags) { return ((flags & F2D_SMEM_TW) ? MUFFT_TW_SMEM : 0) | ((flags & F2D_DERIVE) ? MUFFT_TW_DERIVE : 0); }
 // OM: MCU_OUT_COMPLEX = complex images; MCU_OUT_R2C / MCU_OUT_R2C_FULL = real images (forward only): the row
@@ -193,7 +199,8 @@ __host__ __device__ constexpr int f2d_twm(int flags) { return ((flags & F2D_SMEM
 // rows_kernel.cuh, ref kernel.c:47-82) into rows of pitch 2 NX, the column tiles transform the NX + 1
 // (2 NX) columns that carry data; the last column tile is partly masked.
 template <int NX, int NY, int DIR, int FLAGS = 0, int OM = MCU_OUT_COMPLEX>
-__global__ void __launch_bounds__(MUFFT_F2D_THREADS, f2d_min_blocks(NX, NY)) fft2d_fused_kernel(const mcu_2d_args a)
+__global__ void __launch_bounds__(MUFFT_F2D_THREADS, (FLAGS & F2D_OCC3) != 0 && f2d_min_blocks(NX, NY) < 3 ? 3 : f2d_min_blocks(NX, NY))
+fft2d_fused_kernel(const mcu_2d_args a)
 {
     constexpr int VX = f2d_rows_variant(NX, OM);
     constexpr int RX = engine_regs(NX, VX), TX = NX / RX, ROWS = f2d_rows_per_tile(NX);

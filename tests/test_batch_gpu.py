@@ -155,50 +155,6 @@ def test_c2c_batch_host_memory(m, torch, oracle, n, kind):
         assert rel_l2(got[i], oracle.c2c(x[i].view(np.complex64), -1)) <= tol(n)
 
 
-@pytest.mark.parametrize("where", ["pageable", "managed", "device"])
-def test_buffers_with_4_byte_alignment_are_staged(m, torch, oracle, where):
-    """The real side of R2C / C2R is a float array, which C aligns to 4 bytes only (the reference's
-    scalar path takes it).  The kernels move 8-byte values, so such a buffer is never used in place:
-    it takes the staged path whatever memory it lives in (same check on the emulated host layer:
-    tests/test_hostemu.py)."""
-    n, batch = 4096, 37
-    r = np.random.default_rng(11).random((batch, n), np.float32) - np.float32(0.5)
-    out_floats = batch * (n // 2 + 1) * 2
-    if where == "pageable":
-        raw_in = np.zeros(batch * n + 16, np.float32)
-        raw_out = np.zeros(out_floats + 16, np.float32)
-        base_in, base_out = raw_in.ctypes.data, raw_out.ctypes.data
-    elif where == "managed":
-        base_in, base_out = m.mufft_alloc((batch * n + 16) * 4), m.mufft_alloc((out_floats + 16) * 4)
-        raw_in = np.ctypeslib.as_array((ctypes.c_float * (batch * n + 16)).from_address(base_in))
-        raw_out = np.ctypeslib.as_array((ctypes.c_float * (out_floats + 16)).from_address(base_out))
-    else:
-        t_in = torch.zeros(batch * n + 16, dtype=torch.float32, device="cuda")
-        t_out = torch.zeros(out_floats + 16, dtype=torch.float32, device="cuda")
-        base_in, base_out = t_in.data_ptr(), t_out.data_ptr()
-    o_in = ((-base_in) % 8) // 4 + 1   # in floats: the address is 4 mod 8
-    o_out = ((-base_out) % 8) // 4 + 1
-    if where == "device":
-        t_in[o_in:o_in + batch * n] = torch.from_numpy(r.ravel()).cuda()
-        torch.cuda.synchronize()
-    else:
-        raw_in[o_in:o_in + batch * n] = r.ravel()
-    plan = m.mufft_create_plan_1d_r2c(n, 0)
-    assert m.mufft_execute_plan_1d_batch(plan, base_out + 4 * o_out, base_in + 4 * o_in, batch, 0, 0) == 0, m.mufft_cuda_last_error()
-    assert m.mufft_execute_plan_1d_batch_async(plan, base_out + 4 * o_out, base_in + 4 * o_in, batch, 0, 0) != 0  # cannot stage
-    m.mufft_free_plan_1d(plan)
-    if where == "device":
-        got = t_out[o_out:o_out + out_floats].cpu().numpy()
-    else:
-        got = raw_out[o_out:o_out + out_floats].copy()
-    got = got.view(np.complex64).reshape(batch, n // 2 + 1)
-    for i in sample_indices(batch, 6):
-        assert rel_l2(got[i], oracle.r2c(r[i])) <= tol(n)
-    if where == "managed":
-        m.mufft_free(base_in)
-        m.mufft_free(base_out)
-
-
 @pytest.mark.parametrize("n", [64, 2048, 8192, 32768])
 @pytest.mark.parametrize("stereo", [0, 1])
 def test_conv_batch_device(m, torch, oracle, n, stereo):

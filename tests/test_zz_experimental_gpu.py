@@ -132,6 +132,83 @@ def _rworker_p2p(rank, world, port, nx, ny, result):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("nx,ny", [(256, 256), (512, 2048), (1024, 1024), (2048, 256)])
+@pytest.mark.parametrize("mode", [9, 10, 11])
+def test_c2c_2d_fused_flavours_not_measured_yet(m, torch, oracle, nx, ny, mode):
+    """mufft_cuda_set_fused_2d 9 / 10 (tickets drawn two tiles ahead) and 11 (three CTAs per SM): same checks as
+    tests/test_batch_gpu.py::test_c2c_2d_fused_flavours runs on the measured flavours."""
+    from cpu_libs import rel_l2
+    m.mufft_cuda_set_fused_2d(mode)
+    try:
+        batch = max(5, min(40, (96 << 20) // (8 * nx * ny)))
+        g = torch.Generator(device="cuda")
+        g.manual_seed(nx + ny + mode)
+        x = torch.rand((batch, ny, nx, 2), dtype=torch.float32, device="cuda", generator=g) - 0.5
+        y = torch.zeros_like(x)
+        xc = torch.view_as_complex(x)
+        for direction in (-1, 1):
+            plan = m.mufft_create_plan_2d_c2c(nx, ny, direction, 0)
+            assert plan
+            m.mufft_cuda_launch_count(1)
+            assert m.mufft_execute_plan_2d_batch(plan, y.data_ptr(), x.data_ptr(), batch) == 0, m.mufft_cuda_last_error()
+            assert m.mufft_cuda_launch_count(1) == 1
+            m.mufft_free_plan_2d(plan)
+            ref = torch.fft.fft2(xc) if direction < 0 else torch.fft.ifft2(xc, norm="forward")
+            yc = torch.view_as_complex(y)
+            err = (torch.linalg.vector_norm((yc - ref).reshape(batch, -1), dim=1) /
+                   torch.linalg.vector_norm(ref.reshape(batch, -1), dim=1)).max().item()
+            assert err <= tol(nx * ny)
+            assert rel_l2(yc[batch - 1].cpu().numpy(), oracle.c2c_2d(xc[batch - 1].cpu().numpy(), direction)) <= tol(nx * ny)
+    finally:
+        m.mufft_cuda_set_fused_2d(1)
+
+
+@pytest.mark.parametrize("where", ["pageable", "managed", "device"])
+def test_buffers_with_4_byte_alignment_are_staged(m, torch, oracle, where):
+    """The real side of R2C / C2R is a float array, which C aligns to 4 bytes only (the reference's
+    scalar path takes it).  The kernels move 8-byte values, so such a buffer is never used in place:
+    it takes the staged path whatever memory it lives in (same check on the emulated host layer:
+    tests/test_hostemu.py)."""
+    import ctypes
+    from cpu_libs import rel_l2
+    n, batch = 4096, 37
+    r = np.random.default_rng(11).random((batch, n), np.float32) - np.float32(0.5)
+    out_floats = batch * (n // 2 + 1) * 2
+    if where == "pageable":
+        raw_in = np.zeros(batch * n + 16, np.float32)
+        raw_out = np.zeros(out_floats + 16, np.float32)
+        base_in, base_out = raw_in.ctypes.data, raw_out.ctypes.data
+    elif where == "managed":
+        base_in, base_out = m.mufft_alloc((batch * n + 16) * 4), m.mufft_alloc((out_floats + 16) * 4)
+        raw_in = np.ctypeslib.as_array((ctypes.c_float * (batch * n + 16)).from_address(base_in))
+        raw_out = np.ctypeslib.as_array((ctypes.c_float * (out_floats + 16)).from_address(base_out))
+    else:
+        t_in = torch.zeros(batch * n + 16, dtype=torch.float32, device="cuda")
+        t_out = torch.zeros(out_floats + 16, dtype=torch.float32, device="cuda")
+        base_in, base_out = t_in.data_ptr(), t_out.data_ptr()
+    o_in = ((-base_in) % 8) // 4 + 1   # in floats: the address is 4 mod 8
+    o_out = ((-base_out) % 8) // 4 + 1
+    if where == "device":
+        t_in[o_in:o_in + batch * n] = torch.from_numpy(r.ravel()).cuda()
+        torch.cuda.synchronize()
+    else:
+        raw_in[o_in:o_in + batch * n] = r.ravel()
+    plan = m.mufft_create_plan_1d_r2c(n, 0)
+    assert m.mufft_execute_plan_1d_batch(plan, base_out + 4 * o_out, base_in + 4 * o_in, batch, 0, 0) == 0, m.mufft_cuda_last_error()
+    assert m.mufft_execute_plan_1d_batch_async(plan, base_out + 4 * o_out, base_in + 4 * o_in, batch, 0, 0) != 0  # cannot stage
+    m.mufft_free_plan_1d(plan)
+    if where == "device":
+        got = t_out[o_out:o_out + out_floats].cpu().numpy()
+    else:
+        got = raw_out[o_out:o_out + out_floats].copy()
+    got = got.view(np.complex64).reshape(batch, n // 2 + 1)
+    for i in (0, 1, batch // 2, batch - 1):
+        assert rel_l2(got[i], oracle.r2c(r[i])) <= tol(n)
+    if where == "managed":
+        m.mufft_free(base_in)
+        m.mufft_free(base_out)
+
+
 @pytest.mark.parametrize("nx,ny", [(256, 128), (4096, 2048), (32768, 512)])
 def test_slab_2d_real_p2p(nx, ny):
     """SlabRFFT2D(exchange="p2p"): the R2C row kernel's epilogue scatters the half spectrum into the column slabs

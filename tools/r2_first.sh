@@ -11,7 +11,7 @@ mkdir -p gpurun_out
     timeout 120 python tools/probe_optin.py $what 2>&1 | cut -c1-400
   done
   echo "=== experimental GPU tests that need no torch-free probe: slab R2C p2p (1 GPU)"
-  MUFFT_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_zz_experimental_gpu.py -m gpu -q -x 2>&1 | tail -5
+  MUFFT_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_zz_experimental_gpu.py -m gpu -q 2>&1 | tail -15
   echo "=== A/B builds"
   bash tools/ab_fast.sh tools/ab_r2.txt
   echo "=== fused 2D at three CTAs per SM needs a flavour without shared-memory tables"
