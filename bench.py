@@ -374,14 +374,24 @@ def run_optin_probes(seconds_each=60):
         if time.time() - t_start > 2.5 * seconds_each:  # keep the default run within minutes
             out.append({"what": what, "error": "skipped: probe time budget used up"})
             break
-        try:
-            res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "probe_optin.py"), what], capture_output=True, text=True,
-                                 timeout=seconds_each, cwd=ROOT)
-        except subprocess.TimeoutExpired:
-            out.append({"what": what, "error": f"no result within {seconds_each} s (child killed); remaining probes skipped"})
-            break
+        # output through files, not pipes, and no unbounded wait: a child that cannot be reaped must
+        # not hold up the bench line
+        with tempfile.TemporaryFile("w+") as f_out, tempfile.TemporaryFile("w+") as f_err:
+            child = subprocess.Popen([sys.executable, os.path.join(ROOT, "tools", "probe_optin.py"), what], stdout=f_out, stderr=f_err, cwd=ROOT)
+            try:
+                rc = child.wait(timeout=seconds_each)
+            except subprocess.TimeoutExpired:
+                child.kill()
+                try:
+                    child.wait(timeout=20)
+                except subprocess.TimeoutExpired:
+                    pass
+                rc = None
+            f_out.seek(0)
+            f_err.seek(0)
+            stdout, stderr = f_out.read(), f_err.read()
         lines = []
-        for ln in res.stdout.splitlines():
+        for ln in stdout.splitlines():
             if ln.startswith("{"):
                 try:
                     d = json.loads(ln)
@@ -389,9 +399,11 @@ def run_optin_probes(seconds_each=60):
                     continue
                 if d.get("what") not in ("start", "done"):
                     lines.append({k: d[k] for k in keep if k in d})
-        if res.returncode != 0:
-            out.append({"what": what, "error": "exit %d: %s" % (res.returncode, res.stderr.strip().splitlines()[-1][:200] if res.stderr.strip() else ""),
-                        "lines": lines})
+        if rc is None:
+            out.append({"what": what, "error": f"no end within {seconds_each} s (child killed); remaining probes skipped", "lines": lines})
+            break
+        if rc != 0:
+            out.append({"what": what, "error": "exit %d: %s" % (rc, stderr.strip().splitlines()[-1][:200] if stderr.strip() else ""), "lines": lines})
             break
         out.extend(lines)
     return out
