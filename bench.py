@@ -364,20 +364,38 @@ def run_optin_probes(seconds_each=60):
     """The paths that are NOT defaults yet (profiles/README.md section 6) measured next to the run of
     record: tools/probe_optin.py (ctypes + numpy, parity against numpy float64 on every line), one
     child process per probe so that a path that misbehaves cannot take the bench line with it; after
-    the first probe that fails or times out the rest is skipped.  Reported under also.optin_probes;
+    the first probe that has to be killed (time limit) the rest is skipped.  Reported under also.optin_probes;
     nothing here feeds `value`, `roofline` or `e2e`.  MUFFT_BENCH_PROBES=0 switches it off."""
     keep = ("what", "n", "nx", "ny", "batch", "direction", "fused_mode", "fused_real", "cluster_rows", "spin_sync", "ms", "ms_r2c", "ms_c2r",
-            "gbs", "us_per_call", "launches_per_call", "rel_l2", "ok")
+            "gbs", "us_per_call", "launches_per_call", "rel_l2", "ok", "workload", "units", "frac", "label")
+    jobs = [(what, [sys.executable, os.path.join(ROOT, "tools", "probe_optin.py"), what], None) for what in ("latency", "real2d", "early", "cluster")]
+    # prebuilt A/B variants of the library (tools/ab_build.sh, same sources with other compile-time choices), when
+    # they travelled with the tree: tools/fastbench.py on the workloads tools/ab_r2.txt lists for each, the product
+    # library first ("base")
+    try:
+        variants = []
+        for ln in open(os.path.join(ROOT, "tools", "ab_r2.txt")):
+            f = [x.strip() for x in ln.split("|")]
+            if len(f) >= 3 and f[0] and not f[0].startswith("#"):
+                lib = os.path.join(ROOT, "ab_variants", f[0], "libmufft_b200.so")
+                if f[0] == "base" or os.path.exists(lib):
+                    variants.append((f[0], f[2].split(), None if f[0] == "base" else lib))
+        if len(variants) > 1:
+            for label, wls, lib in variants:
+                env = dict(os.environ, MUFFT_B200_LIB=lib) if lib else None
+                jobs.append(("variant " + label, [sys.executable, os.path.join(ROOT, "tools", "fastbench.py"), "--label", label, *wls], env))
+    except OSError:
+        pass
     out = []
     t_start = time.time()
-    for what in ("latency", "real2d", "early", "cluster"):
+    for what, cmd, env in jobs:
         if time.time() - t_start > 2.5 * seconds_each:  # keep the default run within minutes
             out.append({"what": what, "error": "skipped: probe time budget used up"})
             break
         # output through files, not pipes, and no unbounded wait: a child that cannot be reaped must
         # not hold up the bench line
         with tempfile.TemporaryFile("w+") as f_out, tempfile.TemporaryFile("w+") as f_err:
-            child = subprocess.Popen([sys.executable, os.path.join(ROOT, "tools", "probe_optin.py"), what], stdout=f_out, stderr=f_err, cwd=ROOT)
+            child = subprocess.Popen(cmd, stdout=f_out, stderr=f_err, cwd=ROOT, env=env)
             try:
                 rc = child.wait(timeout=seconds_each)
             except subprocess.TimeoutExpired:
@@ -398,13 +416,14 @@ def run_optin_probes(seconds_each=60):
                 except ValueError:
                     continue
                 if d.get("what") not in ("start", "done"):
-                    lines.append({k: d[k] for k in keep if k in d})
+                    lines.append({k: (round(d[k], 10) if isinstance(d[k], float) else d[k]) for k in keep if k in d})
         if rc is None:
             out.append({"what": what, "error": f"no end within {seconds_each} s (child killed); remaining probes skipped", "lines": lines})
             break
         if rc != 0:
+            # a probe that failed cleanly took only its own process (and CUDA context) with it: carry on
             out.append({"what": what, "error": "exit %d: %s" % (rc, stderr.strip().splitlines()[-1][:200] if stderr.strip() else ""), "lines": lines})
-            break
+            continue
         out.extend(lines)
     return out
 

@@ -6,6 +6,10 @@ import ctypes as C
 import os
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmufft_b200.so")
+# A/B measurements only (tools/ab_build.sh builds the same sources with other compile-time choices into
+# ab_variants/<label>/libmufft_b200.so): MUFFT_B200_LIB selects such a build of THIS library instead.
+if os.environ.get("MUFFT_B200_LIB"):
+    LIB_PATH = os.path.abspath(os.environ["MUFFT_B200_LIB"])
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} is missing: build it with `make -C mufft_b200/csrc -j` or "
