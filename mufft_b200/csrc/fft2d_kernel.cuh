@@ -187,11 +187,17 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
 //                  barrier + scoreboard stalls on top - more warps to hide them against the cost of the
 //                  spills (not measured yet).  Not combinable with F2D_SMEM_TW (three exchange areas plus
 //                  three table copies exceed the shared memory of an SM).
+//   F2D_INTERLEAVE inside a round of tickets (the NR row tickets of image s and the NC column tickets of image
+//                  s - lag) row and column tickets alternate (evenly spread when NR != NC) instead of all rows
+//                  first: the two CTAs of an SM then tend to hold one tile of each kind - row tiles read HBM
+//                  and write L2, column tiles read L2 and write HBM - instead of two of the same kind, and
+//                  the HBM reads and writes are spread evenly over time (not measured yet).
 #define F2D_SMEM_TW 1
 #define F2D_ONE_SIDED 2
 #define F2D_DERIVE 4
 #define F2D_EARLY 8
 #define F2D_OCC3 16
+#define F2D_INTERLEAVE 32
 #define F2D_LITE (F2D_SMEM_TW | F2D_ONE_SIDED)
 __host__ __device__ constexpr int f2d_twm(int flags) { return ((flags & F2D_SMEM_TW) ? MUFFT_TW_SMEM : 0) | ((flags & F2D_DERIVE) ? MUFFT_TW_DERIVE : 0); }
 // OM: MCU_OUT_COMPLEX = complex images; MCU_OUT_R2C / MCU_OUT_R2C_FULL = real images (forward only): the row
@@ -244,6 +250,13 @@ fft2d_fused_kernel(const mcu_2d_args a)
         } else if (k - head < body) {
             const unsigned long long kk = k - head;
             const unsigned s = lag + (unsigned)(kk / (NR + NC)), j = (unsigned)(kk % (NR + NC));
+            if constexpr ((FLAGS & F2D_INTERLEAVE) != 0) {
+                // r(j) = floor(j NR / (NR + NC)) row tickets precede position j; position j is a row ticket iff r(j + 1) > r(j)
+                const unsigned r0 = (unsigned)((unsigned long long)j * NR / (NR + NC)), r1 = (unsigned)((unsigned long long)(j + 1) * NR / (NR + NC));
+                if (r1 > r0) { image = s; tile = r0; return true; }
+                image = s - lag; tile = j - r0;
+                return false;
+            }
             if (j < NR) { image = s; tile = j; return true; }
             image = s - lag; tile = j - NR;
             return false;

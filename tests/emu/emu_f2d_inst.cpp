@@ -28,6 +28,12 @@ extern "C" int EMU_CAT(emu_2d_fused_, EMU_NX, x, EMU_NY)(int direction, void *ou
     } else if (lite == 4) { // smem tables + one-sided fences + tickets two ahead
         if (direction < 0) emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY, true), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, -1, F2D_LITE | F2D_EARLY>(a); });
         else emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY, true), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, 1, F2D_LITE | F2D_EARLY>(a); });
+    } else if (lite == 5) { // smem tables + one-sided fences, row and column tickets alternating
+        if (direction < 0) emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY, true), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, -1, F2D_LITE | F2D_INTERLEAVE>(a); });
+        else emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY, true), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, 1, F2D_LITE | F2D_INTERLEAVE>(a); });
+    } else if (lite == 6) { // derived twiddles from the global table, tickets alternating
+        if (direction < 0) emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, -1, F2D_ONE_SIDED | F2D_DERIVE | F2D_INTERLEAVE>(a); });
+        else emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, 1, F2D_ONE_SIDED | F2D_DERIVE | F2D_INTERLEAVE>(a); });
     } else if (lite == 3) { // derived twiddles from the global table
         if (direction < 0) emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, -1, F2D_ONE_SIDED | F2D_DERIVE>(a); });
         else emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, 1, F2D_ONE_SIDED | F2D_DERIVE>(a); });

@@ -269,14 +269,15 @@ def test_rows_spectral_multiply(emu_rows, host, n):
         assert cpu_libs.rel_l2(got[b], want[b]) <= tol(n)
 
 
-@pytest.mark.parametrize("lite", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("lite", [0, 1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("nx,ny,ctas", [(256, 256, 1), (256, 256, 3), (512, 256, 2), (2048, 256, 2)])  # 2048: rows on named barriers
 @pytest.mark.parametrize("direction", [-1, 1])
 def test_fused_2d(emu, host, oracle, nx, ny, ctas, direction, lite):
     """The persistent fused 2D kernel with CTAs really running side by side: row tickets, lagged column
     tickets, the rows-done counters and the deferred release (fft2d_kernel.cuh); lite 1 = twiddle tables
     in shared memory (two tables when the sides differ) and one-sided fences, 2 = that with derived
-    twiddles, 3 = derived twiddles from the global table, 4 = 1 with tickets drawn two tiles ahead."""
+    twiddles, 3 = derived twiddles from the global table, 4 = 1 with tickets drawn two tiles ahead, 5 / 6 = 1 / 3
+    with row and column tickets alternating inside a round."""
     batch = 3
     fn = getattr(emu, f"emu_2d_fused_{nx}x{ny}")
     fn.restype = C.c_int

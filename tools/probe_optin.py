@@ -24,7 +24,7 @@ LOG = open(os.path.join(OUT, "probe_optin.jsonl"), "a")
 QUICK = len(sys.argv) > 1 and sys.argv[1] == "quick"
 # mufft_cuda_set_fused_2d: 1 direct loads, 2 TMA-fed, 3 / 4 the same with smem twiddles + one-sided fences,
 # 5 = 3 + derived twiddles, 6 = one-sided fences + derived twiddles (global table), 7 = one-sided fences only,
-# 8 = plain, 9 / 10 = 3 / 6 with tickets drawn two tiles ahead (early dependency read), 11 = 6 at three CTAs per SM
+# 8 = plain, 9 / 10 = 3 / 6 with tickets drawn two tiles ahead (early dependency read), 11 = 6 at three CTAs per SM, 12 / 13 = 3 / 6 with row and column tickets alternating
 MODES = (8, 3, 6, 9, 10, 1)
 ARG = sys.argv[1] if len(sys.argv) > 1 else ""
 
@@ -236,7 +236,7 @@ if __name__ == "__main__":
         probe_1d(16384, 4096)
     elif ARG == "early":  # fused 2D: tickets two ahead (modes 9 / 10) and three CTAs per SM (11) against the flavours they extend (3 / 6)
         for shape in ((1024, 1024, 256), (512, 512, 1024), (256, 256, 4096), (2048, 2048, 64), (1024, 256, 1024)):
-            probe_2d(*shape, modes=(3, 9, 6, 10, 11, 3, 9, 6, 10, 11))
+            probe_2d(*shape, modes=(3, 9, 12, 6, 10, 11, 13, 3, 9, 12, 6, 10, 11, 13))
     elif ARG == "real2d":  # 2D R2C images: row kernel + column kernel through scratch vs the fused persistent kernel
         for nx_, ny_ in ((1024, 1024), (512, 512), (2048, 2048), (4096, 1024)):
             batch_ = max(2, (1 << 30) // (nx_ * ny_ * 8))
