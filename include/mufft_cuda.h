@@ -152,6 +152,10 @@ void mufft_cuda_set_prefetch(int enable);
  * Same results (within rounding of the derived twiddles) in all modes.  MUFFT_CUDA_FUSED_2D in the
  * environment sets the initial value. */
 void mufft_cuda_set_fused_2d(int mode);
+/* Fused 2D kernel, measurement knob: the column pass of an image starts this many images behind its row
+ * pass (0 = default: chosen from the number of resident CTAs, 3 for 1024 x 1024 on a B200).  Same results
+ * for every value.  MUFFT_CUDA_FUSED_2D_LAG sets the initial value. */
+void mufft_cuda_set_fused_2d_lag(unsigned images);
 /* Longest row transform done by ONE kernel, for plans created afterwards: 16384 (default: one
  * 512-thread CTA per 16384-point transform, read once and written once) or 8192 (16384 points take
  * the two-kernel split; measured 1.8x slower, kept for comparison).  Affects 1D plans of 16384

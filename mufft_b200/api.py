@@ -88,6 +88,7 @@ SIGNATURES = {
     "mufft_cuda_set_prefetch": (None, [_i]),
     "mufft_cuda_set_fused_2d": (None, [_i]),
     "mufft_cuda_set_fused_2d_real": (None, [_i]),
+    "mufft_cuda_set_fused_2d_lag": (None, [_u]),
     "mufft_cuda_set_two_kernel": (None, [_i]),
     "mufft_cuda_set_cluster_rows": (None, [_i]),
     "mufft_cuda_set_spin_sync": (None, [_i]),

@@ -84,6 +84,8 @@ __attribute__((constructor)) static void read_env(void)
     if (e != NULL) mufft_cuda_set_fused_2d_real(atoi(e));
     e = getenv("MUFFT_CUDA_FUSED_2D");
     if (e != NULL) mufft_cuda_set_fused_2d(atoi(e));
+    e = getenv("MUFFT_CUDA_FUSED_2D_LAG");
+    if (e != NULL && atoi(e) >= 0) mufft_cuda_set_fused_2d_lag((unsigned)atoi(e));
     e = getenv("MUFFT_CUDA_L2_CHUNK_MB");
     if (e != NULL && atoi(e) >= 1 && atoi(e) <= 4096) g_l2_chunk_bytes = (size_t)atoi(e) << 20;
     e = getenv("MUFFT_CUDA_MID_GROUP_MB");
@@ -117,6 +119,12 @@ static int g_fused_2d = 1;
  * GPU) = row kernel + column kernel through plan scratch. */
 static int g_fused_2d_real = 0;
 void mufft_cuda_set_fused_2d_real(int enable) { g_fused_2d_real = enable != 0; }
+/* Fused 2D kernel: the column tickets of an image are issued this many images after its row tickets
+ * (0 = the launcher's choice: far enough that ~1.5 x the tickets in flight lie in between; 3 for
+ * 1024 x 1024 on 148 SMs).  Smaller = the intermediate is younger in L2 when it is read back but column
+ * tiles wait more often; a measurement knob. */
+static unsigned g_fused_2d_lag = 0;
+void mufft_cuda_set_fused_2d_lag(unsigned images) { g_fused_2d_lag = images; }
 void mufft_cuda_set_fused_2d(int mode) { g_fused_2d = mode <= 0 ? 0 : (mode > 13 ? 1 : mode); }
 
 /* ---- per-thread state --------------------------------------------------------------------- */
@@ -1352,6 +1360,7 @@ static int run_2d_device(mufft_plan_2d *plan, void *out, const void *in, size_t 
         f.out = out; f.in = in; f.tw_x = plan->ax_x.d_engine_tw; f.tw_y = plan->ax_y.d_engine_tw;
         f.counters = plan->d_counters; f.out_image = (size_t)nx * ny; f.in_image = (size_t)nx * ny;
         f.batch = images; f.nx = nx; f.ny = ny; f.direction = plan->ax_x.direction;
+        f.lag = g_fused_2d_lag;
         {   /* mode -> (TMA-fed kernel?, F2D_* flavour bits): see mufft_cuda_set_fused_2d in mufft_cuda.h */
             static const int tma_of[14] = { 0, 0, 1, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0 },
                              flags_of[14] = { 0, -1, 0, 3, 3, 7, 6, 2, 0, 3 | 8, 6 | 8, 6 | 16, 3 | 32, 6 | 32 };
@@ -1373,6 +1382,7 @@ static int run_2d_device(mufft_plan_2d *plan, void *out, const void *in, size_t 
         f.counters = plan->d_counters; f.out_image = 2 * (size_t)nx * ny; f.in_image = (size_t)nx * ny;
         f.batch = images; f.nx = nx; f.ny = ny; f.direction = plan->ax_x.direction;
         f.out_mode = out_mode; f.flags = -1;
+        f.lag = g_fused_2d_lag;
         return mcu_launch_2d_fused(&f, stream);
     }
     const int real_rows = plan->kind != KIND_C2C;

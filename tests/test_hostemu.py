@@ -234,6 +234,33 @@ def test_fft_h_2d(lib, oracle, nx, ny):
         assert cpu_libs.rel_l2(lib.c2r_2d(spec), oracle.c2r_2d(spec)) <= tol(nx * ny)
 
 
+@pytest.mark.parametrize("lag", [1, 2, 7])
+def test_fused_2d_lag_knob(lib, oracle, lag):
+    """mufft_cuda_set_fused_2d_lag: the column pass runs `lag` images behind the row pass (7 > batch: all rows
+    first); same results for every value, one launch for the batch."""
+    raw = lib.lib
+    raw.mufft_cuda_set_fused_2d_lag.restype, raw.mufft_cuda_set_fused_2d_lag.argtypes = None, [u]
+    nx = ny = 256
+    batch = 4
+    x = cpu_libs.aligned_copy(crnd(np.random.default_rng(lag), batch, ny, nx), np.complex64)
+    y = cpu_libs.aligned_zeros(batch * ny * nx, np.complex64).reshape(batch, ny, nx)
+    plan = lib._create_plan_2d_c2c(nx, ny, -1, 0)
+    raw.mufft_cuda_set_fused_2d_lag(lag)
+    try:
+        px, vx = managed(lib, x)
+        py, vy = managed(lib, y)
+        raw.mufft_cuda_launch_count(1)
+        assert raw.mufft_execute_plan_2d_batch(plan, py, px, batch) == 0, raw.mufft_cuda_last_error()
+        assert raw.mufft_cuda_launch_count(1) == 1
+        for b in range(batch):
+            assert cpu_libs.rel_l2(vy[b], oracle.c2c_2d(x[b], -1)) <= tol(nx * ny)
+        raw.mufft_free(px)
+        raw.mufft_free(py)
+    finally:
+        raw.mufft_cuda_set_fused_2d_lag(0)
+        lib._free_plan_2d(plan)
+
+
 @pytest.mark.parametrize("fused_real", [0, 1])
 def test_fused_2d_real_switch(lib, oracle, fused_real):
     """2D R2C of 512 x 256 reals (row transforms of 256 complex points): with the switch on the whole batch is
