@@ -139,7 +139,7 @@ void mufft_cuda_set_prefetch(int enable);
  *   1 (default)  one persistent kernel does rows and columns of the whole batch with the intermediate
  *                kept in L2, in the flavour measured fastest for the shape;
  *   0            separate row and column kernels per group of images (what every other 2D shape uses);
- *   2..15        that kernel in one fixed flavour, for measurements and tests: 8 plain; 7 one-sided
+ *   2..16        that kernel in one fixed flavour, for measurements and tests: 8 plain; 7 one-sided
  *                (release / acquire) fences in the ticket protocol; 3 = 7 + twiddle tables staged in
  *                shared memory; 6 = 7 + only the power-of-two twiddles loaded, the rest derived;
  *                5 = 3 + 6; 2 / 4 = tiles brought into shared memory by the TMA unit one tile ahead
@@ -149,7 +149,9 @@ void mufft_cuda_set_prefetch(int enable);
  *                (not measured yet); 11 = 6 compiled for three CTAs per SM instead of two (80 registers,
  *                the excess spilled; not measured yet); 12 / 13 = 3 / 6 with row and column tickets
  *                alternating inside a round instead of all row tickets first (not measured yet);
- *                14 = 7 at three CTAs per SM, 15 = 11 + 13 (not measured yet).
+ *                14 = 7 at three CTAs per SM, 15 = 11 + 13, 16 = 3 at three CTAs per SM (three exchange areas
+ *                and three table copies fit the shared memory of an SM for 1024 x 1024 and the 256 / 512-point
+ *                shapes only) (not measured yet).
  * Same results (within rounding of the derived twiddles) in all modes.  MUFFT_CUDA_FUSED_2D in the
  * environment sets the initial value. */
 void mufft_cuda_set_fused_2d(int mode);

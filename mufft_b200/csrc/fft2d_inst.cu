@@ -187,6 +187,7 @@ cudaError_t MUFFT_CAT4(f2d_launch_, F2D_NX, x, F2D_NY)(const mcu_2d_args &a, cud
         MUFFT_F2D_FLAVOUR(F2D_ONE_SIDED | F2D_DERIVE | F2D_EARLY)
         MUFFT_F2D_FLAVOUR(F2D_ONE_SIDED | F2D_DERIVE | F2D_OCC3)
         MUFFT_F2D_FLAVOUR(F2D_ONE_SIDED | F2D_OCC3)
+        MUFFT_F2D_FLAVOUR(F2D_LITE | F2D_OCC3)
         MUFFT_F2D_FLAVOUR(F2D_ONE_SIDED | F2D_DERIVE | F2D_OCC3 | F2D_INTERLEAVE)
         MUFFT_F2D_FLAVOUR(F2D_LITE | F2D_INTERLEAVE)
         MUFFT_F2D_FLAVOUR(F2D_ONE_SIDED | F2D_DERIVE | F2D_INTERLEAVE)

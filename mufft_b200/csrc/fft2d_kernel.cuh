@@ -185,8 +185,8 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
 //   F2D_OCC3       compiled for THREE CTAs per SM (80 registers per thread, the excess spilled; 24 warps per
 //                  SM instead of 16).  ncu on the plain kernel: 25 % warp occupancy, issue slots 43 % busy,
 //                  barrier + scoreboard stalls on top - more warps to hide them against the cost of the
-//                  spills (not measured yet).  Not combinable with F2D_SMEM_TW (three exchange areas plus
-//                  three table copies exceed the shared memory of an SM).
+//                  spills (not measured yet).  With F2D_SMEM_TW three exchange areas plus three table copies fit
+//                  the shared memory of an SM only for 1024 x 1024 (3 x 75 600 bytes) and the 256 / 512-point shapes.
 //   F2D_INTERLEAVE inside a round of tickets (the NR row tickets of image s and the NC column tickets of image
 //                  s - lag) row and column tickets alternate (evenly spread when NR != NC) instead of all rows
 //                  first: the two CTAs of an SM then tend to hold one tile of each kind - row tiles read HBM

@@ -125,7 +125,7 @@ void mufft_cuda_set_fused_2d_real(int enable) { g_fused_2d_real = enable != 0; }
  * tiles wait more often; a measurement knob. */
 static unsigned g_fused_2d_lag = 0;
 void mufft_cuda_set_fused_2d_lag(unsigned images) { g_fused_2d_lag = images; }
-void mufft_cuda_set_fused_2d(int mode) { g_fused_2d = mode <= 0 ? 0 : (mode > 15 ? 1 : mode); }
+void mufft_cuda_set_fused_2d(int mode) { g_fused_2d = mode <= 0 ? 0 : (mode > 16 ? 1 : mode); }
 
 /* ---- per-thread state --------------------------------------------------------------------- */
 static __thread void *tls_stream = NULL;
@@ -1362,8 +1362,8 @@ static int run_2d_device(mufft_plan_2d *plan, void *out, const void *in, size_t 
         f.batch = images; f.nx = nx; f.ny = ny; f.direction = plan->ax_x.direction;
         f.lag = g_fused_2d_lag;
         {   /* mode -> (TMA-fed kernel?, F2D_* flavour bits): see mufft_cuda_set_fused_2d in mufft_cuda.h */
-            static const int tma_of[16] = { 0, 0, 1, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 },
-                             flags_of[16] = { 0, -1, 0, 3, 3, 7, 6, 2, 0, 3 | 8, 6 | 8, 6 | 16, 3 | 32, 6 | 32, 2 | 16, 6 | 16 | 32 };
+            static const int tma_of[17] = { 0, 0, 1, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 },
+                             flags_of[17] = { 0, -1, 0, 3, 3, 7, 6, 2, 0, 3 | 8, 6 | 8, 6 | 16, 3 | 32, 6 | 32, 2 | 16, 6 | 16 | 32, 3 | 16 };
             f.tma = tma_of[g_fused_2d];
             f.flags = flags_of[g_fused_2d];
         }

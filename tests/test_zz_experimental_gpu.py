@@ -133,7 +133,7 @@ def _rworker_p2p(rank, world, port, nx, ny, result):
 
 
 @pytest.mark.parametrize("nx,ny", [(256, 256), (512, 2048), (1024, 1024), (2048, 256)])
-@pytest.mark.parametrize("mode", [9, 10, 11, 12, 13, 14, 15])
+@pytest.mark.parametrize("mode", [9, 10, 11, 12, 13, 14, 15, 16])
 def test_c2c_2d_fused_flavours_not_measured_yet(m, torch, oracle, nx, ny, mode):
     """mufft_cuda_set_fused_2d 9 / 10 (tickets drawn two tiles ahead), 11 (three CTAs per SM), 12 / 13 (alternating tickets): same checks as
     tests/test_batch_gpu.py::test_c2c_2d_fused_flavours runs on the measured flavours."""

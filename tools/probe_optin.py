@@ -236,7 +236,7 @@ if __name__ == "__main__":
         probe_1d(16384, 4096)
     elif ARG == "early":  # fused 2D: tickets two ahead (modes 9 / 10) and three CTAs per SM (11) against the flavours they extend (3 / 6)
         for shape in ((1024, 1024, 256), (512, 512, 1024), (256, 256, 4096), (2048, 2048, 64), (1024, 256, 1024)):
-            probe_2d(*shape, modes=(1, 3, 9, 12, 6, 10, 11, 13, 14, 15))
+            probe_2d(*shape, modes=(1, 3, 16, 9, 12, 6, 11, 10, 13, 14, 15))
         for lag in (1, 2, 4, 6):  # default for this shape on 148 SMs: 3
             m.mufft_cuda_set_fused_2d_lag(lag)
             probe_2d(1024, 1024, 256, modes=(1,), tag=f"_lag{lag}")
