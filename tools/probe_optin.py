@@ -286,7 +286,7 @@ if __name__ == "__main__":
             pout, y = managed(2 * n_ * batch_)
             fill(x, n_, 2 * n_)
             xc, yc = x.view(np.complex64).reshape(batch_, n_), y.view(np.complex64).reshape(batch_, n_)
-            for cluster in (0, 1, 0, 1):
+            for cluster in (0, 1, 2, 0, 1, 2):  # 1 = cluster barriers, 2 = st.async + mbarrier exchange
                 m.mufft_cuda_set_cluster_rows(cluster)
                 for direction in (-1, 1):
                     plan = m.mufft_create_plan_1d_c2c(n_, direction, 0)
