@@ -46,3 +46,22 @@ def test_probe_2d_and_the_knobs_it_turns(env):
     lines = json_lines(res.stdout)
     assert len(lines) == 7 and all(d["ok"] for d in lines), lines
     assert [d.get("fused_mode") for d in lines[:5]] == [1, 9, 11, 12, 16]
+
+
+def test_probe_real2d_latency_cluster(env):
+    """The probes bench.py starts first at round end: 2D R2C with and without the fused kernel (512 reals x 256
+    rows = a 256 x 256 complex shape the emulation has), single-call latency with both synchronise flavours,
+    32768-point rows on the two-kernel split and on both cluster flavours."""
+    code = (
+        "import sys; sys.argv = ['probe_optin.py', 'dry']; sys.path.insert(0, 'tools')\n"
+        "import probe_optin as p\n"
+        "p.probe_real2d(shapes=((512, 256),), bytes_in=1)\n"
+        "p.probe_latency(iters=20, warm=2)\n"
+        "p.probe_cluster(sizes=(32768,), bytes_in=1, flavours=(0, 1, 2))\n")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=1500, cwd=ROOT, env=env)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = json_lines(res.stdout)
+    assert [d["what"] for d in lines] == ["r2c2d"] * 4 + ["single_call_latency"] * 4 + ["c2c1d_cluster"] * 6
+    assert all(d["ok"] for d in lines), lines
+    assert [d["launches_per_call"] for d in lines[:4]] == [2.0, 1.0, 2.0, 1.0]          # fused real 2D is one launch
+    assert [d["launches_per_call"] for d in lines[8:]] == [2.0, 2.0, 1.0, 1.0, 1.0, 1.0]  # the cluster kernel replaces two

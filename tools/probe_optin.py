@@ -221,6 +221,79 @@ def probe_scatter(n, peers=2, batch=5):
     m.mufft_free(pin)
 
 
+def probe_real2d(shapes=((1024, 1024), (512, 512), (2048, 2048), (4096, 1024)), bytes_in=1 << 30):
+    """2D R2C images (nx reals per row): row kernel + column kernel through scratch vs the fused persistent kernel."""
+    for nx_, ny_ in shapes:
+        batch_ = max(2, bytes_in // (nx_ * ny_ * 8))
+        pin, x = managed(nx_ * ny_ * batch_)
+        pout, y = managed(2 * nx_ * ny_ * batch_)
+        fill(x, nx_ + ny_, nx_ * ny_)
+        xr, yc = x.reshape(batch_, ny_, nx_), y.view(np.complex64).reshape(batch_, ny_, nx_)
+        for fused in (0, 1, 0, 1):
+            m.mufft_cuda_set_fused_2d_real(fused)
+            plan = m.mufft_create_plan_2d_r2c(nx_, ny_, 0)
+            m.mufft_cuda_launch_count(1)
+            ms = timed(lambda: m.mufft_execute_plan_2d_batch(plan, pout, pin, batch_), 5)
+            launches = m.mufft_cuda_launch_count(1) / 7
+            w_ = nx_ // 2 + 1
+            err = max(rel_l2(yc[b][:, :w_], np.fft.fft2(xr[b].astype(np.float64))[:, :w_]) for b in (0, batch_ - 1))
+            emit(what="r2c2d", nx=nx_, ny=ny_, batch=batch_, fused_real=fused, launches_per_call=launches, ms=round(ms, 4),
+                 gbs=round((4 * nx_ * ny_ + 8 * w_ * ny_) * batch_ / ms / 1e6, 1), rel_l2=err, ok=bool(err <= 1e-6 * math.log2(nx_ * ny_)),
+                 last_error=m.mufft_cuda_last_error().decode())
+            m.mufft_free_plan_2d(plan)
+        m.mufft_cuda_set_fused_2d_real(0)
+        m.mufft_free(pin)
+        m.mufft_free(pout)
+
+
+def probe_latency(iters=20000, warm=500):
+    """One 64-point transform per fft.h call on mufft_alloc memory, blocking vs busy-poll synchronise."""
+    plan = m.mufft_create_plan_1d_c2c(64, -1, 0)
+    pin, x = managed(128)
+    pout, y = managed(128)
+    x[:] = np.random.default_rng(0).random(128, np.float32) - np.float32(0.5)
+    for spin in (0, 1, 0, 1):
+        m.mufft_cuda_set_spin_sync(spin)
+        for _ in range(warm):
+            m.mufft_execute_plan_1d(plan, pout, pin)
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            m.mufft_execute_plan_1d(plan, pout, pin)
+        us = (time.perf_counter() - t0) / iters * 1e6
+        err = rel_l2(y.view(np.complex64), np.fft.fft(x.view(np.complex64).astype(np.complex128)))
+        emit(what="single_call_latency", n=64, spin_sync=spin, us_per_call=round(us, 3), rel_l2=err, ok=bool(err < 6e-6))
+    m.mufft_cuda_set_spin_sync(0)
+    m.mufft_free_plan_1d(plan)
+    m.mufft_free(pin)
+    m.mufft_free(pout)
+
+
+def probe_cluster(sizes=(32768, 65536), bytes_in=1 << 31, flavours=(0, 1, 2, 0, 1, 2)):
+    """Rows of 32768 / 65536 points: two-kernel split (0) vs one kernel on a thread-block cluster
+    (1 = cluster barriers, 2 = st.async + mbarrier exchange)."""
+    for n_ in sizes:
+        batch_ = max(2, bytes_in // (8 * n_))
+        pin, x = managed(2 * n_ * batch_)
+        pout, y = managed(2 * n_ * batch_)
+        fill(x, n_, 2 * n_)
+        xc, yc = x.view(np.complex64).reshape(batch_, n_), y.view(np.complex64).reshape(batch_, n_)
+        for cluster in flavours:
+            m.mufft_cuda_set_cluster_rows(cluster)
+            for direction in (-1, 1):
+                plan = m.mufft_create_plan_1d_c2c(n_, direction, 0)
+                m.mufft_cuda_launch_count(1)
+                ms = timed(lambda: m.mufft_execute_plan_1d_batch(plan, pout, pin, batch_, 0, 0), 5)
+                launches = m.mufft_cuda_launch_count(1) / 7
+                f1 = (lambda z: np.fft.fft(z)) if direction < 0 else (lambda z: np.fft.ifft(z, norm="forward"))
+                err = max(rel_l2(yc[b], f1(xc[b].astype(np.complex128))) for b in (0, batch_ - 1))
+                emit(what="c2c1d_cluster", n=n_, batch=batch_, direction=direction, cluster_rows=cluster, launches_per_call=launches, ms=round(ms, 4),
+                     gbs=round(16 * n_ * batch_ / ms / 1e6, 1), rel_l2=err, ok=bool(err <= 1e-6 * math.log2(n_)), last_error=m.mufft_cuda_last_error().decode())
+                m.mufft_free_plan_1d(plan)
+        m.mufft_cuda_set_cluster_rows(0)
+        m.mufft_free(pin)
+        m.mufft_free(pout)
+
+
 if __name__ == "__main__":
     assert m.mufft_cuda_device_count() >= 1 and m.mufft_cuda_set_device(0) == 0
     emit(what="start", arg=ARG)
@@ -242,65 +315,11 @@ if __name__ == "__main__":
             probe_2d(1024, 1024, 256, modes=(1,), tag=f"_lag{lag}")
         m.mufft_cuda_set_fused_2d_lag(0)
     elif ARG == "real2d":  # 2D R2C images: row kernel + column kernel through scratch vs the fused persistent kernel
-        for nx_, ny_ in ((1024, 1024), (512, 512), (2048, 2048), (4096, 1024)):
-            batch_ = max(2, (1 << 30) // (nx_ * ny_ * 8))
-            pin, x = managed(nx_ * ny_ * batch_)
-            pout, y = managed(2 * nx_ * ny_ * batch_)
-            fill(x, nx_ + ny_, nx_ * ny_)
-            xr, yc = x.reshape(batch_, ny_, nx_), y.view(np.complex64).reshape(batch_, ny_, nx_)
-            for fused in (0, 1, 0, 1):
-                m.mufft_cuda_set_fused_2d_real(fused)
-                plan = m.mufft_create_plan_2d_r2c(nx_, ny_, 0)
-                m.mufft_cuda_launch_count(1)
-                ms = timed(lambda: m.mufft_execute_plan_2d_batch(plan, pout, pin, batch_), 5)
-                launches = m.mufft_cuda_launch_count(1) / 7
-                w_ = nx_ // 2 + 1
-                err = max(rel_l2(yc[b][:, :w_], np.fft.fft2(xr[b].astype(np.float64))[:, :w_]) for b in (0, batch_ - 1))
-                emit(what="r2c2d", nx=nx_, ny=ny_, batch=batch_, fused_real=fused, launches_per_call=launches, ms=round(ms, 4),
-                     gbs=round((4 * nx_ * ny_ + 8 * w_ * ny_) * batch_ / ms / 1e6, 1), rel_l2=err, ok=bool(err <= 1e-6 * math.log2(nx_ * ny_)),
-                     last_error=m.mufft_cuda_last_error().decode())
-                m.mufft_free_plan_2d(plan)
-            m.mufft_cuda_set_fused_2d_real(0)
-            m.mufft_free(pin)
-            m.mufft_free(pout)
+        probe_real2d()
     elif ARG == "latency":  # BASELINE configs[0] as the reference runs it: one 64-point transform per fft.h call
-        plan = m.mufft_create_plan_1d_c2c(64, -1, 0)
-        pin, x = managed(128)
-        pout, y = managed(128)
-        x[:] = np.random.default_rng(0).random(128, np.float32) - np.float32(0.5)
-        for spin in (0, 1, 0, 1):
-            m.mufft_cuda_set_spin_sync(spin)
-            for _ in range(500):
-                m.mufft_execute_plan_1d(plan, pout, pin)
-            t0 = time.perf_counter()
-            for _ in range(20000):
-                m.mufft_execute_plan_1d(plan, pout, pin)
-            us = (time.perf_counter() - t0) / 20000 * 1e6
-            err = rel_l2(y.view(np.complex64), np.fft.fft(x.view(np.complex64).astype(np.complex128)))
-            emit(what="single_call_latency", n=64, spin_sync=spin, us_per_call=round(us, 3), rel_l2=err, ok=bool(err < 6e-6))
-        m.mufft_cuda_set_spin_sync(0)
+        probe_latency()
     elif ARG == "cluster":  # 32768 / 65536-point rows: two-kernel split vs one kernel on a thread-block cluster
-        for n_ in (32768, 65536):
-            batch_ = (1 << 31) // (8 * n_)
-            pin, x = managed(2 * n_ * batch_)
-            pout, y = managed(2 * n_ * batch_)
-            fill(x, n_, 2 * n_)
-            xc, yc = x.view(np.complex64).reshape(batch_, n_), y.view(np.complex64).reshape(batch_, n_)
-            for cluster in (0, 1, 2, 0, 1, 2):  # 1 = cluster barriers, 2 = st.async + mbarrier exchange
-                m.mufft_cuda_set_cluster_rows(cluster)
-                for direction in (-1, 1):
-                    plan = m.mufft_create_plan_1d_c2c(n_, direction, 0)
-                    m.mufft_cuda_launch_count(1)
-                    ms = timed(lambda: m.mufft_execute_plan_1d_batch(plan, pout, pin, batch_, 0, 0), 5)
-                    launches = m.mufft_cuda_launch_count(1) / 7
-                    f1 = (lambda z: np.fft.fft(z)) if direction < 0 else (lambda z: np.fft.ifft(z, norm="forward"))
-                    err = max(rel_l2(yc[b], f1(xc[b].astype(np.complex128))) for b in (0, batch_ - 1))
-                    emit(what="c2c1d_cluster", n=n_, batch=batch_, direction=direction, cluster_rows=cluster, launches_per_call=launches, ms=round(ms, 4),
-                         gbs=round(16 * n_ * batch_ / ms / 1e6, 1), rel_l2=err, ok=bool(err <= 1e-6 * math.log2(n_)), last_error=m.mufft_cuda_last_error().decode())
-                    m.mufft_free_plan_1d(plan)
-            m.mufft_cuda_set_cluster_rows(0)
-            m.mufft_free(pin)
-            m.mufft_free(pout)
+        probe_cluster()
     elif ARG == "quick":
         probe_2d(1024, 1024, 32)
         probe_1d(16384, 2048)
