@@ -55,6 +55,7 @@ def test_probe_real2d_latency_cluster(env):
     code = (
         "import sys; sys.argv = ['probe_optin.py', 'dry']; sys.path.insert(0, 'tools')\n"
         "import probe_optin as p\n"
+        "p.REPS = 1\n"
         "p.probe_real2d(shapes=((512, 256),), bytes_in=1)\n"
         "p.probe_latency(iters=20, warm=2)\n"
         "p.probe_cluster(sizes=(32768,), bytes_in=1, flavours=(0, 1, 2))\n")

@@ -27,6 +27,7 @@ QUICK = len(sys.argv) > 1 and sys.argv[1] == "quick"
 # 8 = plain, 9 / 10 = 3 / 6 with tickets drawn two tiles ahead (early dependency read), 11 = 6 at three CTAs per SM, 12 / 13 = 3 / 6 with row and column tickets alternating
 MODES = (8, 3, 6, 9, 10, 1)
 ARG = sys.argv[1] if len(sys.argv) > 1 else ""
+REPS = 5  # timed calls per measurement (after 2 warm-up calls) in the real2d / cluster probes
 
 
 def emit(**kw):
@@ -233,8 +234,8 @@ def probe_real2d(shapes=((1024, 1024), (512, 512), (2048, 2048), (4096, 1024)), 
             m.mufft_cuda_set_fused_2d_real(fused)
             plan = m.mufft_create_plan_2d_r2c(nx_, ny_, 0)
             m.mufft_cuda_launch_count(1)
-            ms = timed(lambda: m.mufft_execute_plan_2d_batch(plan, pout, pin, batch_), 5)
-            launches = m.mufft_cuda_launch_count(1) / 7
+            ms = timed(lambda: m.mufft_execute_plan_2d_batch(plan, pout, pin, batch_), REPS)
+            launches = m.mufft_cuda_launch_count(1) / (2 + REPS)
             w_ = nx_ // 2 + 1
             err = max(rel_l2(yc[b][:, :w_], np.fft.fft2(xr[b].astype(np.float64))[:, :w_]) for b in (0, batch_ - 1))
             emit(what="r2c2d", nx=nx_, ny=ny_, batch=batch_, fused_real=fused, launches_per_call=launches, ms=round(ms, 4),
@@ -282,8 +283,8 @@ def probe_cluster(sizes=(32768, 65536), bytes_in=1 << 31, flavours=(0, 1, 2, 0, 
             for direction in (-1, 1):
                 plan = m.mufft_create_plan_1d_c2c(n_, direction, 0)
                 m.mufft_cuda_launch_count(1)
-                ms = timed(lambda: m.mufft_execute_plan_1d_batch(plan, pout, pin, batch_, 0, 0), 5)
-                launches = m.mufft_cuda_launch_count(1) / 7
+                ms = timed(lambda: m.mufft_execute_plan_1d_batch(plan, pout, pin, batch_, 0, 0), REPS)
+                launches = m.mufft_cuda_launch_count(1) / (2 + REPS)
                 f1 = (lambda z: np.fft.fft(z)) if direction < 0 else (lambda z: np.fft.ifft(z, norm="forward"))
                 err = max(rel_l2(yc[b], f1(xc[b].astype(np.complex128))) for b in (0, batch_ - 1))
                 emit(what="c2c1d_cluster", n=n_, batch=batch_, direction=direction, cluster_rows=cluster, launches_per_call=launches, ms=round(ms, 4),
