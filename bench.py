@@ -386,20 +386,29 @@ def run_optin_probes(seconds_each=60):
                 jobs.append(("variant " + label, [sys.executable, os.path.join(ROOT, "tools", "fastbench.py"), "--label", label, *wls], env))
     except OSError:
         pass
+    # MUFFT_BENCH_PROBES=2 adds the GPU tests of the same paths (tests/test_zz_experimental_gpu.py, skipped in the regular
+    # suite until a path has hardware evidence): their pytest summary says which paths may move into the regular files
+    if os.environ.get("MUFFT_BENCH_PROBES") == "2":  # off by default: two more minutes
+      jobs.append(("experimental gpu tests", [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_zz_experimental_gpu.py"), "-m", "gpu",
+                                              "-q", "--no-header", "-p", "no:cacheprovider", "-rf"], dict(os.environ, MUFFT_TEST_EXPERIMENTAL="1")))
     out = []
     t_start = time.time()
     for what, cmd, env in jobs:
-        if time.time() - t_start > 2.5 * seconds_each:  # keep the default run within minutes
+        if time.time() - t_start > 3 * seconds_each:  # keep the default run within minutes
             out.append({"what": what, "error": "skipped: probe time budget used up"})
             break
+        limit = 2 * seconds_each if what == "experimental gpu tests" else seconds_each
         # output through files, not pipes, and no unbounded wait: a child that cannot be reaped must
-        # not hold up the bench line
+        # not hold up the bench line; its own session, so that a kill takes its children along
         with tempfile.TemporaryFile("w+") as f_out, tempfile.TemporaryFile("w+") as f_err:
-            child = subprocess.Popen(cmd, stdout=f_out, stderr=f_err, cwd=ROOT, env=env)
+            child = subprocess.Popen(cmd, stdout=f_out, stderr=f_err, cwd=ROOT, env=env, start_new_session=True)
             try:
-                rc = child.wait(timeout=seconds_each)
+                rc = child.wait(timeout=limit)
             except subprocess.TimeoutExpired:
-                child.kill()
+                try:
+                    os.killpg(child.pid, 9)
+                except OSError:
+                    child.kill()
                 try:
                     child.wait(timeout=20)
                 except subprocess.TimeoutExpired:
@@ -417,8 +426,12 @@ def run_optin_probes(seconds_each=60):
                     continue
                 if d.get("what") not in ("start", "done"):
                     lines.append({k: (round(d[k], 10) if isinstance(d[k], float) else d[k]) for k in keep if k in d})
+        if what == "experimental gpu tests":  # pytest prints text: keep the failures (-rf) and the summary line
+            tail = [ln.strip()[:300] for ln in stdout.splitlines() if ln.startswith("FAILED") or " passed" in ln or " failed" in ln or " error" in ln]
+            out.append({"what": what, "exit": rc, "summary": tail[-12:]})
+            continue
         if rc is None:
-            out.append({"what": what, "error": f"no end within {seconds_each} s (child killed); remaining probes skipped", "lines": lines})
+            out.append({"what": what, "error": f"no end within {limit} s (child killed); remaining probes skipped", "lines": lines})
             break
         if rc != 0:
             # a probe that failed cleanly took only its own process (and CUDA context) with it: carry on
