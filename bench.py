@@ -368,7 +368,11 @@ def run_optin_probes(seconds_each=60):
     nothing here feeds `value`, `roofline` or `e2e`.  MUFFT_BENCH_PROBES=0 switches it off."""
     keep = ("what", "n", "nx", "ny", "batch", "direction", "fused_mode", "fused_real", "cluster_rows", "spin_sync", "ms", "ms_r2c", "ms_c2r",
             "gbs", "us_per_call", "launches_per_call", "rel_l2", "ok", "workload", "units", "frac", "label")
-    jobs = [(what, [sys.executable, os.path.join(ROOT, "tools", "probe_optin.py"), what], None) for what in ("latency", "real2d", "early", "cluster")]
+    def probe(what):
+        return (what, [sys.executable, os.path.join(ROOT, "tools", "probe_optin.py"), what], None)
+    # order: what matters most for the next round first (fused 2D flavours = BASELINE configs[3], derived twiddles =
+    # configs[2]); the kernels that use hardware features no default kernel uses (clusters, DSMEM, st.async) last
+    jobs = [probe("latency"), probe("early")]
     # prebuilt A/B variants of the library (tools/ab_build.sh, same sources with other compile-time choices), when
     # they travelled with the tree: tools/fastbench.py on the workloads tools/ab_r2.txt lists for each, the product
     # library first ("base")
@@ -386,6 +390,7 @@ def run_optin_probes(seconds_each=60):
                 jobs.append(("variant " + label, [sys.executable, os.path.join(ROOT, "tools", "fastbench.py"), "--label", label, *wls], env))
     except OSError:
         pass
+    jobs += [probe("real2d"), probe("cluster")]
     # MUFFT_BENCH_PROBES=2 adds the GPU tests of the same paths (tests/test_zz_experimental_gpu.py, skipped in the regular
     # suite until a path has hardware evidence): their pytest summary says which paths may move into the regular files
     if os.environ.get("MUFFT_BENCH_PROBES") == "2":  # off by default: two more minutes
@@ -394,7 +399,7 @@ def run_optin_probes(seconds_each=60):
     out = []
     t_start = time.time()
     for what, cmd, env in jobs:
-        if time.time() - t_start > 3 * seconds_each:  # keep the default run within minutes
+        if time.time() - t_start > 2 * seconds_each:  # keep the default run within minutes
             out.append({"what": what, "error": "skipped: probe time budget used up"})
             break
         limit = 2 * seconds_each if what == "experimental gpu tests" else seconds_each

@@ -37,14 +37,19 @@ def test_probe_runner_survives_failing_and_hanging_children(monkeypatch):
 
     def fake(cmd, **kw):
         what = cmd[-1]
+        if "fastbench.py" in cmd[1]:
+            what = "variant"
         code = {"latency": "import json; print(json.dumps({'what': 'single_call_latency', 'us_per_call': 7.5, 'ok': True, 'junk': 1}))",
-                "real2d": "raise SystemExit(3)",
-                "early": "import time; print('{\"what\": \"c2c2d\", \"ms\": 1.0, \"ok\": true}', flush=True); time.sleep(60)"}.get(what, "print('{}')")
+                "early": "raise SystemExit(3)",
+                "variant": "print('{\"workload\": \"c2c4096\", \"ms\": 2.7, \"ok\": true, \"label\": \"x\"}')",
+                "real2d": "import time; print('{\"what\": \"r2c2d\", \"ms\": 1.0, \"ok\": true}', flush=True); time.sleep(60)"}.get(what, "print('{}')")
         return real([sys.executable, "-c", code], **{k: v for k, v in kw.items() if k != "env"})
 
     monkeypatch.setattr(bench.subprocess, "Popen", fake)
     out = bench.run_optin_probes(seconds_each=2)
     assert out[0] == {"what": "single_call_latency", "us_per_call": 7.5, "ok": True}   # unknown keys dropped
-    assert out[1]["what"] == "real2d" and out[1]["error"].startswith("exit 3")          # a clean failure: carry on
-    assert out[2]["what"] == "early" and "killed" in out[2]["error"] and out[2]["lines"] == [{"what": "c2c2d", "ms": 1.0, "ok": True}]
-    assert len(out) == 3                                                                # nothing is started after a kill
+    assert out[1]["what"] == "early" and out[1]["error"].startswith("exit 3")           # a clean failure: carry on
+    variants = [d for d in out if d.get("workload") == "c2c4096"]                       # base + every prebuilt variant (if any travelled)
+    assert len(variants) in (0, 2, 3, 4, 5) and all(d["label"] == "x" for d in variants)
+    assert out[-1]["what"] == "real2d" and "killed" in out[-1]["error"] and out[-1]["lines"] == [{"what": "r2c2d", "ms": 1.0, "ok": True}]
+    assert not any(d.get("what") == "cluster" for d in out)                             # nothing is started after a kill
