@@ -761,8 +761,8 @@ def main():
             k2, n2, ny2, u2 = WORKLOADS[name]
             j2 = Job(m, torch, k2, n2, ny2, u2, dev)
             m.mufft_cuda_launch_count(1)
-            t_ms, per2 = time_steps(torch, None, j2, 3, 10)
-            l2 = m.mufft_cuda_launch_count(1) * 10 // 13
+            t_ms, per2 = time_steps(torch, None, j2, 10, 10)
+            l2 = m.mufft_cuda_launch_count(1) * 10 // 20
             ms2 = t_ms / 10
             also[name] = {"workload": DESCRIPTION[name], "gflops": u2 * flops_per_unit(k2, n2, ny2) / (ms2 * 1e-3) * 1e-9,
                           "units_per_s": u2 / (ms2 * 1e-3), "ms_per_step": ms2,
