@@ -750,6 +750,39 @@ def main():
                "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
                "api": "mufft_execute_plan_1d_batch(host pinned in/out)" if kind in ("c2c", "r2c", "c2r") else "host-pointer batch API",
                "matches_device_path": same}
+        if world == 1:
+            # what the bus itself does on this box with the same pinned buffers (plain cudaMemcpyAsync through torch,
+            # 1 GiB each way): the ceiling of any host-buffer path, reported next to the e2e number it bounds
+            try:
+                rows = max(1, min(host_in.shape[0], host_out.shape[0], (1 << 30) // max(1, 4 * max(host_in.shape[1], host_out.shape[1]))))
+                s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+                def copy_in():
+                    with torch.cuda.stream(s_in):
+                        job.inp[:rows].copy_(host_in[:rows], non_blocking=True)
+
+                def copy_out():
+                    with torch.cuda.stream(s_out):
+                        host_out[:rows].copy_(job.out[:rows], non_blocking=True)
+
+                def rate(fns, nbytes):
+                    best = 0.0
+                    for _ in range(3):
+                        torch.cuda.synchronize()
+                        t1 = time.perf_counter()
+                        for fn in fns:
+                            fn()
+                        torch.cuda.synchronize()
+                        best = max(best, nbytes / (time.perf_counter() - t1) * 1e-9)
+                    return best
+                b_in, b_out = rows * host_in.shape[1] * 4, rows * host_out.shape[1] * 4
+                copy_in(); copy_out(); torch.cuda.synchronize()
+                e2e["pcie"] = {"h2d_alone_gbs": rate([copy_in], b_in), "d2h_alone_gbs": rate([copy_out], b_out),
+                               "both_ways_gbs": rate([copy_in, copy_out], b_in + b_out),
+                               "e2e_gbs": (host_in.numel() + host_out.numel()) * 4 / (dt / e2e_steps) * 1e-9,
+                               "how": "torch pinned<->device copies of %.2f GiB each way on two streams, best of 3" % (b_in / 2**30)}
+            except Exception as exc:
+                e2e["pcie"] = {"error": repr(exc)[:200]}
         del host_in, host_out
 
     also = {}
