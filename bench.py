@@ -366,7 +366,7 @@ def run_optin_probes(seconds_each=60):
     child process per probe so that a path that misbehaves cannot take the bench line with it; after
     the first probe that has to be killed (time limit) the rest is skipped.  Reported under also.optin_probes;
     nothing here feeds `value`, `roofline` or `e2e`.  MUFFT_BENCH_PROBES=0 switches it off."""
-    keep = ("what", "n", "nx", "ny", "batch", "direction", "fused_mode", "fused_real", "cluster_rows", "spin_sync", "ms", "ms_r2c", "ms_c2r",
+    keep = ("what", "n", "nx", "ny", "batch", "direction", "fused_mode", "fused_real", "cluster_rows", "spin_sync", "prefetch", "kind", "ms", "ms_host_fill_alone", "ms_r2c", "ms_c2r",
             "gbs", "us_per_call", "launches_per_call", "rel_l2", "ok", "workload", "units", "frac", "label")
     def probe(what):
         return (what, [sys.executable, os.path.join(ROOT, "tools", "probe_optin.py"), what], None)
@@ -390,7 +390,7 @@ def run_optin_probes(seconds_each=60):
                 jobs.append(("variant " + label, [sys.executable, os.path.join(ROOT, "tools", "fastbench.py"), "--label", label, *wls], env))
     except OSError:
         pass
-    jobs += [probe("real2d"), probe("cluster")]
+    jobs += [probe("real2d"), probe("managed"), probe("cluster")]
     # MUFFT_BENCH_PROBES=2 adds the GPU tests of the same paths (tests/test_zz_experimental_gpu.py, skipped in the regular
     # suite until a path has hardware evidence): their pytest summary says which paths may move into the regular files
     if os.environ.get("MUFFT_BENCH_PROBES") == "2":  # off by default: two more minutes

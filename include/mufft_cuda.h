@@ -176,6 +176,11 @@ void mufft_cuda_set_fused_2d_real(int enable);
  * mufft_execute_plan_1d call): 1 = the library busy-polls the stream instead of blocking in the driver
  * when a call touches at most 1 MiB; 0 (default until measured).  MUFFT_CUDA_SPIN_SYNC sets the initial value. */
 void mufft_cuda_set_spin_sync(int enable);
+/* Synchronous calls on CUDA managed memory (mufft_alloc) that the caller fills and reads on the host between
+ * calls: 0 (default until measured) = the kernel's page faults migrate the pages, 1 = buffers of 256 KiB or more
+ * are prefetched to the device in front of the kernel, 2 = and the output back to the host behind it (only
+ * right when the host reads it next).  MUFFT_CUDA_MANAGED_PREFETCH sets the initial value. */
+void mufft_cuda_set_managed_prefetch(int level);
 /* Row transforms of 32768 and 65536 points, for plans created afterwards: 1 = ONE kernel on a
  * thread-block cluster of 2 / 4 CTAs (512 threads each, the transform in registers, exchange through
  * distributed shared memory: 1 = remote stores + release / acquire cluster barriers, 2 = st.async

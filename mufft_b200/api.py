@@ -92,6 +92,7 @@ SIGNATURES = {
     "mufft_cuda_set_two_kernel": (None, [_i]),
     "mufft_cuda_set_cluster_rows": (None, [_i]),
     "mufft_cuda_set_spin_sync": (None, [_i]),
+    "mufft_cuda_set_managed_prefetch": (None, [_i]),
     "mufft_cuda_set_onchip_limit": (None, [_u]),
     "mufft_cuda_get_onchip_limit": (_u, []),
     "mufft_cuda_plan_1d_uses_engine": (_i, [_vp]),

@@ -78,6 +78,8 @@ __attribute__((constructor)) static void read_env(void)
     if (e != NULL) g_onchip_limit = atoi(e) >= MCU_ENGINE_BIG_N ? MCU_ENGINE_BIG_N : MCU_ENGINE_MAX_N;
     e = getenv("MUFFT_CUDA_SPIN_SYNC");
     if (e != NULL) mufft_cuda_set_spin_sync(atoi(e));
+    e = getenv("MUFFT_CUDA_MANAGED_PREFETCH");
+    if (e != NULL) mufft_cuda_set_managed_prefetch(atoi(e));
     e = getenv("MUFFT_CUDA_CLUSTER_ROWS");
     if (e != NULL) mufft_cuda_set_cluster_rows(atoi(e));
     e = getenv("MUFFT_CUDA_FUSED_2D_REAL");
@@ -102,6 +104,15 @@ void mufft_cuda_set_prefetch(int enable) { g_prefetch = enable != 0; }
 static int g_spin_sync = 0;
 #define SPIN_SYNC_BYTES ((size_t)1 << 20)
 void mufft_cuda_set_spin_sync(int enable) { g_spin_sync = enable != 0; }
+/* Synchronous executes on CUDA managed memory (what mufft_alloc returns and the reference's callers fill and
+ * read from the host between calls): 0 (default until measured) = the kernel's page faults bring the pages
+ * over, 1 = buffers of MANAGED_PREFETCH_MIN bytes or more are prefetched to the device on the stream in
+ * front of the kernel (bulk migration instead of fault-driven), 2 = and the output is prefetched back to the
+ * host behind it, so that the caller's reads do not fault either (wrong choice when the next call consumes
+ * the output on the device, hence a separate level). */
+static int g_managed_prefetch = 0;
+#define MANAGED_PREFETCH_MIN ((size_t)256 << 10)
+void mufft_cuda_set_managed_prefetch(int level) { g_managed_prefetch = level <= 0 ? 0 : (level >= 2 ? 2 : 1); }
 /* Row transforms of 32768 / 65536 points: 1 = one kernel on a thread-block cluster of 2 / 4 CTAs with the
  * exchange through distributed shared memory (rowsc_kernel.cuh; plans created afterwards, plain and
  * zero-padded C2C and the scatter epilogue), 0 (default until measured on the GPU) = the two-kernel split. */
@@ -454,8 +465,9 @@ static int run_any(stage *st, unit_launch fn, void *ctx, const io_desc *io, int 
      * side of R2C / C2R, e.g. a float array on the caller's stack; the reference's scalar path accepts
      * it) cannot be used in place, whatever memory it is.  It takes the staged path below, whose
      * copies have no alignment rule. */
-    const int vis_in = ALIGNED(io->in) && device_visible(mcu_pointer_kind(io->in), span_in);
-    const int vis_out = ALIGNED(io->out) && device_visible(mcu_pointer_kind(io->out), span_out);
+    const int kind_in = mcu_pointer_kind(io->in), kind_out = mcu_pointer_kind(io->out);
+    const int vis_in = ALIGNED(io->in) && device_visible(kind_in, span_in);
+    const int vis_out = ALIGNED(io->out) && device_visible(kind_out, span_out);
     int vis_in2 = 1;
     if (io->in2) {
         size_t span2 = io->in2_stride ? io->in2_stride * (io->count - 1) + io->in2_unit : io->in2_unit;
@@ -463,7 +475,12 @@ static int run_any(stage *st, unit_launch fn, void *ctx, const io_desc *io, int 
     }
 
     if (vis_in && vis_out && vis_in2) {
+        const int pf_in = !async && g_managed_prefetch >= 1 && kind_in == MCU_MEM_MANAGED && span_in >= MANAGED_PREFETCH_MIN;
+        const int pf_out = !async && g_managed_prefetch >= 1 && kind_out == MCU_MEM_MANAGED && span_out >= MANAGED_PREFETCH_MIN;
+        if (pf_in) (void)mcu_prefetch(io->in, span_in, 1, tls_stream);   /* advisory: errors are ignored */
+        if (pf_out) (void)mcu_prefetch(io->out, span_out, 1, tls_stream);
         TRY(fn(ctx, io->out, io->out_stride, io->in, io->in_stride, io->in2, io->in2_stride, io->count, tls_stream));
+        if (pf_out && g_managed_prefetch >= 2) (void)mcu_prefetch(io->out, span_out, 0, tls_stream);
         if (!async) {
             if (g_spin_sync && span_in + span_out <= SPIN_SYNC_BYTES) TRY(mcu_stream_sync_spin(tls_stream));
             else TRY(mcu_stream_sync(tls_stream));

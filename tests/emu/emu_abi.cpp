@@ -120,7 +120,13 @@ int mcu_copy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, s
     for (size_t r = 0; r < rows; r++) memmove((char *)dst + r * dpitch, (const char *)src + r * spitch, width_bytes);
     return 0;
 }
-int mcu_prefetch(const void *, size_t, int, void *) { return 0; }
+// counted, so that the host layer's managed-memory prefetch policy can be tested: calls to the device / to the host
+static std::atomic<unsigned> g_prefetch_calls[2];
+int mcu_prefetch(const void *, size_t, int to_device, void *) { g_prefetch_calls[to_device ? 1 : 0]++; return 0; }
+unsigned emu_prefetch_calls(int to_device, int reset)
+{
+    return reset ? g_prefetch_calls[to_device ? 1 : 0].exchange(0) : g_prefetch_calls[to_device ? 1 : 0].load();
+}
 
 // ---- tables ------------------------------------------------------------------------------------------
 int mcu_rows_variant(unsigned n, int in_mode, int out_mode) { return tables_rows_variant(n, in_mode, out_mode); }

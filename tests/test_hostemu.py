@@ -63,6 +63,34 @@ def managed(lib, arr):
     return ptr, view
 
 
+@pytest.mark.parametrize("level,n,want", [(0, 65536, (0, 0)), (1, 65536, (2, 0)), (2, 65536, (2, 1)), (2, 1024, (0, 0))])
+def test_managed_memory_prefetch_policy(lib, oracle, level, n, want):
+    """mufft_cuda_set_managed_prefetch: synchronous calls on mufft_alloc memory prefetch buffers of 256 KiB or more to
+    the device in front of the kernel (level 1: input and output) and the output back to the host behind it
+    (level 2); small buffers and level 0 leave it to the page faults.  The emulated CUDA side counts the calls."""
+    raw = lib.lib
+    raw.mufft_cuda_set_managed_prefetch.restype, raw.mufft_cuda_set_managed_prefetch.argtypes = None, [i32]
+    raw.emu_prefetch_calls.restype, raw.emu_prefetch_calls.argtypes = u, [i32, i32]
+    x = crnd(np.random.default_rng(n), n)
+    px, vx = managed(lib, x)
+    py, vy = managed(lib, np.zeros(n, np.complex64))
+    plan = lib._create_plan_1d_c2c(n, -1, 0)
+    raw.mufft_cuda_set_managed_prefetch(level)
+    try:
+        raw.emu_prefetch_calls(0, 1), raw.emu_prefetch_calls(1, 1)
+        lib._execute_plan_1d(plan, py, px)
+        assert (raw.emu_prefetch_calls(1, 1), raw.emu_prefetch_calls(0, 1)) == want
+        assert cpu_libs.rel_l2(vy, oracle.c2c(x, -1)) <= tol(n)
+        # host memory is staged, never prefetched
+        assert cpu_libs.rel_l2(lib.c2c(x, -1), oracle.c2c(x, -1)) <= tol(n)
+        assert (raw.emu_prefetch_calls(1, 1), raw.emu_prefetch_calls(0, 1)) == (0, 0)
+    finally:
+        raw.mufft_cuda_set_managed_prefetch(0)
+        lib._free_plan_1d(plan)
+        raw.mufft_free(px)
+        raw.mufft_free(py)
+
+
 def test_a_plan_belongs_to_the_device_it_was_created_on(lib, oracle):
     """One host thread per GPU: a plan's tables and scratch live on the device that was current at
     creation.  Executing it with another device current is refused with a message instead of

@@ -45,9 +45,10 @@ def _worker(rank, world, port, nx, ny, chunks, natural, direction, result):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("natural", [False, True])
-@pytest.mark.parametrize("nx,ny,chunks", [(16, 8, 1), (32, 64, 4), (64, 16, 3)])
+# every shape and both output layouts on 2 ranks; 4 ranks on the shapes with several chunks (each case spawns its ranks:
+# ~7 s of process start-up, which is what bounds the list)
+@pytest.mark.parametrize("world,natural,nx,ny,chunks", [(2, False, 16, 8, 1), (2, True, 16, 8, 1), (2, False, 32, 64, 4), (2, True, 32, 64, 4),
+                                                        (2, False, 64, 16, 3), (2, True, 64, 16, 3), (4, False, 32, 64, 4), (4, True, 64, 16, 3)])
 def test_slab_exchange_gloo(world, natural, nx, ny, chunks):
     port = _free_port()
     ctx = mp.get_context("spawn")
@@ -109,8 +110,7 @@ def _rworker(rank, world, port, nx, ny, chunks, result):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [1, 2, 4])
-@pytest.mark.parametrize("nx,ny,chunks", [(16, 8, 1), (32, 64, 4), (64, 16, 3)])
+@pytest.mark.parametrize("world,nx,ny,chunks", [(1, 32, 64, 4), (2, 16, 8, 1), (2, 32, 64, 4), (2, 64, 16, 3), (4, 64, 16, 3)])
 def test_slab_real_exchange_gloo(world, nx, ny, chunks):
     """R2C forward (row slabs -> column slabs of the half spectrum, Nyquist column on the last rank)
     and the C2R inverse from that layout, against torch.fft.rfft2 / a round trip."""

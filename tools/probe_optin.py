@@ -269,6 +269,41 @@ def probe_latency(iters=20000, warm=500):
     m.mufft_free(pout)
 
 
+def probe_managed(cases=(("c2c1d", 65536, 1), ("c2c2d", 1024, 1024), ("c2c2d", 4096, 4096)), rounds=6):
+    """The reference's calling pattern on mufft_alloc memory: the host WRITES the whole input, one synchronous fft.h
+    call, the host READS the whole output - per round, with the managed-memory prefetch off / to the device / and
+    back (mufft_cuda_set_managed_prefetch 0 / 1 / 2).  Time per round includes the host's own passes over the data."""
+    for what, nx, ny in cases:
+        count = nx * ny
+        pin, x = managed(2 * count)
+        pout, y = managed(2 * count)
+        src = np.random.default_rng(count).random(2 * count, np.float32) - np.float32(0.5)
+        plan = m.mufft_create_plan_1d_c2c(nx, -1, 0) if what == "c2c1d" else m.mufft_create_plan_2d_c2c(nx, ny, -1, 0)
+        run = (lambda: m.mufft_execute_plan_1d(plan, pout, pin)) if what == "c2c1d" else (lambda: m.mufft_execute_plan_2d(plan, pout, pin))
+        sc = src.view(np.complex64)
+        want = np.fft.fft(sc.astype(np.complex128)) if what == "c2c1d" else np.fft.fft2(sc.reshape(ny, nx).astype(np.complex128))
+        for level in (0, 1, 2, 0, 1, 2):
+            m.mufft_cuda_set_managed_prefetch(level)
+            best, acc = 1e9, 0.0
+            for r in range(rounds):
+                t0 = time.perf_counter()
+                x[:] = src                      # the host produces the input
+                run()
+                acc += float(y[::1024].sum())   # ... and consumes the output (every page is touched)
+                if r > 0:
+                    best = min(best, time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            x[:] = src
+            t_fill = time.perf_counter() - t0
+            err = rel_l2(y.view(np.complex64), want)
+            emit(what="managed_round_trip", kind=what, nx=nx, ny=ny, prefetch=level, ms=round(best * 1e3, 4), ms_host_fill_alone=round(t_fill * 1e3, 4),
+                 rel_l2=err, ok=bool(err <= 1e-6 * math.log2(count)))
+        m.mufft_cuda_set_managed_prefetch(0)
+        (m.mufft_free_plan_1d if what == "c2c1d" else m.mufft_free_plan_2d)(plan)
+        m.mufft_free(pin)
+        m.mufft_free(pout)
+
+
 def probe_cluster(sizes=(32768, 65536), bytes_in=1 << 31, flavours=(0, 1, 2, 0, 1, 2)):
     """Rows of 32768 / 65536 points: two-kernel split (0) vs one kernel on a thread-block cluster
     (1 = cluster barriers, 2 = st.async + mbarrier exchange)."""
@@ -319,6 +354,8 @@ if __name__ == "__main__":
         probe_real2d()
     elif ARG == "latency":  # BASELINE configs[0] as the reference runs it: one 64-point transform per fft.h call
         probe_latency()
+    elif ARG == "managed":  # fft.h calls on mufft_alloc memory the host fills and reads between calls
+        probe_managed()
     elif ARG == "cluster":  # 32768 / 65536-point rows: two-kernel split vs one kernel on a thread-block cluster
         probe_cluster()
     elif ARG == "quick":
