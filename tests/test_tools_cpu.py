@@ -40,11 +40,13 @@ def test_probe_2d_and_the_knobs_it_turns(env):
         "import probe_optin as p\n"
         "p.probe_2d(256, 256, 2, modes=(1, 9, 11, 12, 16), tag='_dry')\n"
         "p.m.mufft_cuda_set_fused_2d_lag(2); p.probe_2d(256, 256, 3, modes=(1,), tag='_lag2'); p.m.mufft_cuda_set_fused_2d_lag(0)\n"
-        "p.probe_partitioned(64, 3, 1)\n")
+        "p.probe_partitioned(64, 3, 1)\n"
+        "p.probe_managed(cases=(('c2c1d', 1024, 1), ('c2c2d', 256, 256)), rounds=2)\n")
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = json_lines(res.stdout)
-    assert len(lines) == 7 and all(d["ok"] for d in lines), lines
+    assert len(lines) == 7 + 12 and all(d["ok"] for d in lines), lines
+    assert [d["prefetch"] for d in lines[7:]] == [0, 1, 2, 0, 1, 2] * 2
     assert [d.get("fused_mode") for d in lines[:5]] == [1, 9, 11, 12, 16]
 
 
