@@ -102,7 +102,12 @@ SIGNATURES = {
 __all__ = [n for n in dir() if n.startswith("MUFFT_")] + list(SIGNATURES) + ["mufft_convolve_func", "SIGNATURES", "ptr"]
 
 for _name, (_res, _args) in SIGNATURES.items():
-    _fn = getattr(lib, _name)  # AttributeError here = the library does not export a declared symbol
+    try:
+        _fn = getattr(lib, _name)  # AttributeError here = the library does not export a declared symbol
+    except AttributeError:
+        if not os.environ.get("MUFFT_B200_LIB"):
+            raise
+        continue  # an A/B build made before the symbol existed: the measurement tools do not need it
     _fn.restype, _fn.argtypes = _res, _args
     globals()[_name] = _fn
 
