@@ -107,7 +107,8 @@ for _name, (_res, _args) in SIGNATURES.items():
     except AttributeError:
         if not os.environ.get("MUFFT_B200_LIB"):
             raise
-        continue  # an A/B build made before the symbol existed: the measurement tools do not need it
+        __all__.remove(_name)  # an A/B build made before the symbol existed: the measurement tools do not need it
+        continue
     _fn.restype, _fn.argtypes = _res, _args
     globals()[_name] = _fn
 
