@@ -6,7 +6,7 @@
 # Results: gpurun_out/probe_optin.jsonl, gpurun_out/fastbench.jsonl, gpurun_out/r2_first.log
 mkdir -p gpurun_out
 {
-  for what in early cluster real2d latency; do
+  for what in early real2d managed latency cluster; do
     echo "=== probe $what"
     timeout 120 python tools/probe_optin.py $what 2>&1 | cut -c1-400
   done
