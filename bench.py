@@ -399,7 +399,7 @@ def run_optin_probes(seconds_each=60):
     out = []
     t_start = time.time()
     for what, cmd, env in jobs:
-        if time.time() - t_start > 2 * seconds_each:  # keep the default run within minutes
+        if time.time() - t_start > 2.5 * seconds_each:  # keep the default run within minutes
             out.append({"what": what, "error": "skipped: probe time budget used up"})
             break
         limit = 2 * seconds_each if what == "experimental gpu tests" else seconds_each
