@@ -167,7 +167,8 @@ if __name__ == "__main__":
     args = ap.parse_args()
     assert m.mufft_cuda_device_count() >= 1 and m.mufft_cuda_set_device(0) == 0
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "fastbench.jsonl"), "a") as log:
+    dry = os.environ.get("MUFFT_B200_LIB", "").endswith("libmufft_hostemu.so")  # the emulated host layer: not a measurement
+    with open(os.devnull if dry else os.path.join(ROOT, "gpurun_out", "fastbench.jsonl"), "a") as log:
         for w in args.workloads:
             name, _, u = w.partition(":")
             res = run(name, int(u) if u else 0, args.reps)
