@@ -36,7 +36,10 @@ def emit(**kw):
     print(line, flush=True)
     LOG.write(line + "\n")
     LOG.flush()
-    os.fsync(LOG.fileno())
+    try:
+        os.fsync(LOG.fileno())
+    except OSError:  # /dev/null (dry runs)
+        pass
 
 
 def managed(count_floats):
