@@ -10,8 +10,34 @@ import json
 import sys
 
 
+def probes_in(obj, out):
+    """Every `optin_probes` list anywhere inside a parsed JSON document (the driver may wrap the bench line)."""
+    if isinstance(obj, dict):
+        for k, v in obj.items():
+            if k == "optin_probes" and isinstance(v, list):
+                for p in v:
+                    if isinstance(p, dict):
+                        out.extend(p["lines"]) if "lines" in p else out.append(p)
+            else:
+                probes_in(v, out)
+    elif isinstance(obj, list):
+        for v in obj:
+            probes_in(v, out)
+    elif isinstance(obj, str) and obj.lstrip().startswith("{") and "optin_probes" in obj:
+        try:
+            probes_in(json.loads(obj), out)  # a bench line kept as a string
+        except ValueError:
+            pass
+
+
 def lines_of(path):
     out = []
+    try:
+        probes_in(json.load(open(path)), out)  # one JSON document, possibly pretty-printed
+        if out:
+            return out
+    except ValueError:
+        pass
     for ln in open(path):
         ln = ln.strip()
         if not ln.startswith("{"):
@@ -20,10 +46,10 @@ def lines_of(path):
             d = json.loads(ln)
         except ValueError:
             continue
-        probes = (d.get("also") or {}).get("optin_probes") if isinstance(d.get("also"), dict) else None
-        if probes is not None:
-            for p in probes:
-                out.extend(p.get("lines", [])) if "lines" in p else out.append(p)
+        found = []
+        probes_in(d, found)
+        if found:
+            out.extend(found)
         elif "what" in d or "workload" in d:
             out.append(d)
     return out
