@@ -359,91 +359,32 @@ def run_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
-# ---- opt-in paths: seconds-long probes appended to the default run -----------------------------------
-def run_optin_probes(seconds_each=60):
-    """The paths that are NOT defaults yet (profiles/README.md section 6) measured next to the run of
-    record: tools/probe_optin.py (ctypes + numpy, parity against numpy float64 on every line), one
-    child process per probe so that a path that misbehaves cannot take the bench line with it; after
-    the first probe that has to be killed (time limit) the rest is skipped.  Reported under also.optin_probes;
-    nothing here feeds `value`, `roofline` or `e2e`.  MUFFT_BENCH_PROBES=0 switches it off."""
-    keep = ("what", "n", "nx", "ny", "batch", "direction", "fused_mode", "fused_real", "cluster_rows", "spin_sync", "prefetch", "kind", "ms", "ms_host_fill_alone", "ms_r2c", "ms_c2r",
-            "gbs", "us_per_call", "launches_per_call", "rel_l2", "ok", "workload", "units", "frac", "label")
-    def probe(what):
-        return (what, [sys.executable, os.path.join(ROOT, "tools", "probe_optin.py"), what], None)
-    # order: what matters most for the next round first (fused 2D flavours = BASELINE configs[3], derived twiddles =
-    # configs[2]); the kernels that use hardware features no default kernel uses (clusters, DSMEM, st.async) last
-    jobs = [probe("latency"), probe("early")]
-    # prebuilt A/B variants of the library (tools/ab_build.sh, same sources with other compile-time choices), when
-    # they travelled with the tree: tools/fastbench.py on the workloads tools/ab_r2.txt lists for each, the product
-    # library first ("base")
-    try:
-        variants = []
-        for ln in open(os.path.join(ROOT, "tools", "ab_r2.txt")):
-            f = [x.strip() for x in ln.split("|")]
-            if len(f) >= 3 and f[0] and not f[0].startswith("#"):
-                lib = os.path.join(ROOT, "ab_variants", f[0], "libmufft_b200.so")
-                if f[0] == "base" or os.path.exists(lib):
-                    variants.append((f[0], f[2].split(), None if f[0] == "base" else lib))
-        if len(variants) > 1:
-            for label, wls, lib in variants:
-                env = dict(os.environ, MUFFT_B200_LIB=lib) if lib else None
-                jobs.append(("variant " + label, [sys.executable, os.path.join(ROOT, "tools", "fastbench.py"), "--label", label, *wls], env))
-    except OSError:
-        pass
-    jobs += [probe("real2d"), probe("managed"), probe("cluster")]
-    # MUFFT_BENCH_PROBES=2 adds the GPU tests of the same paths (tests/test_zz_experimental_gpu.py, skipped in the regular
-    # suite until a path has hardware evidence): their pytest summary says which paths may move into the regular files
-    if os.environ.get("MUFFT_BENCH_PROBES") == "2":  # off by default: two more minutes
-      jobs.append(("experimental gpu tests", [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_zz_experimental_gpu.py"), "-m", "gpu",
-                                              "-q", "--no-header", "-p", "no:cacheprovider", "-rf"], dict(os.environ, MUFFT_TEST_EXPERIMENTAL="1")))
-    out = []
-    t_start = time.time()
-    for what, cmd, env in jobs:
-        if time.time() - t_start > 2.5 * seconds_each:  # keep the default run within minutes
-            out.append({"what": what, "error": "skipped: probe time budget used up"})
-            break
-        limit = 2 * seconds_each if what == "experimental gpu tests" else seconds_each
-        # output through files, not pipes, and no unbounded wait: a child that cannot be reaped must
-        # not hold up the bench line; its own session, so that a kill takes its children along
-        with tempfile.TemporaryFile("w+") as f_out, tempfile.TemporaryFile("w+") as f_err:
-            child = subprocess.Popen(cmd, stdout=f_out, stderr=f_err, cwd=ROOT, env=env, start_new_session=True)
-            try:
-                rc = child.wait(timeout=limit)
-            except subprocess.TimeoutExpired:
-                try:
-                    os.killpg(child.pid, 9)
-                except OSError:
-                    child.kill()
-                try:
-                    child.wait(timeout=20)
-                except subprocess.TimeoutExpired:
-                    pass
-                rc = None
-            f_out.seek(0)
-            f_err.seek(0)
-            stdout, stderr = f_out.read(), f_err.read()
-        lines = []
-        for ln in stdout.splitlines():
-            if ln.startswith("{"):
-                try:
-                    d = json.loads(ln)
-                except ValueError:
-                    continue
-                if d.get("what") not in ("start", "done"):
-                    lines.append({k: (round(d[k], 10) if isinstance(d[k], float) else d[k]) for k in keep if k in d})
-        if what == "experimental gpu tests":  # pytest prints text: keep the failures (-rf) and the summary line
-            tail = [ln.strip()[:300] for ln in stdout.splitlines() if ln.startswith("FAILED") or " passed" in ln or " failed" in ln or " error" in ln]
-            out.append({"what": what, "exit": rc, "summary": tail[-12:]})
-            continue
-        if rc is None:
-            out.append({"what": what, "error": f"no end within {limit} s (child killed); remaining probes skipped", "lines": lines})
-            break
-        if rc != 0:
-            # a probe that failed cleanly took only its own process (and CUDA context) with it: carry on
-            out.append({"what": what, "error": "exit %d: %s" % (rc, stderr.strip().splitlines()[-1][:200] if stderr.strip() else ""), "lines": lines})
-            continue
-        out.extend(lines)
-    return out
+# ---- the one JSON line ---------------------------------------------------------------------------------
+MAX_LINE_BYTES = 4000  # the driver keeps only the tail of stdout: the line of record must stay far below that
+
+
+def format_line(line):
+    """JSON text of the line of record, guaranteed compact: floats rounded to 6 significant digits, and if it
+    still exceeds MAX_LINE_BYTES the optional parts go first (`also` entries, longest first, then `also` itself)."""
+    def rnd(o):
+        if isinstance(o, float):
+            return float(f"{o:.6g}")
+        if isinstance(o, dict):
+            return {k: rnd(v) for k, v in o.items()}
+        if isinstance(o, (list, tuple)):
+            return [rnd(v) for v in o]
+        return o
+    line = rnd(line)
+    text = json.dumps(line, separators=(",", ":"))
+    also = line.get("also")
+    while len(text) > MAX_LINE_BYTES and isinstance(also, dict) and also:
+        also.pop(max(also, key=lambda k: len(json.dumps(also[k]))))
+        line["also_truncated"] = True
+        text = json.dumps(line, separators=(",", ":"))
+    if len(text) > MAX_LINE_BYTES:
+        line.pop("also", None)
+        text = json.dumps(line, separators=(",", ":"))
+    return text
 
 
 # ---- GPU arm ---------------------------------------------------------------------------------------
@@ -716,7 +657,9 @@ def main():
     # kernel's mean duration is the step's event time divided by the launches it contains
     achieved = units * by / (ms_per_step * 1e-3) * 1e-9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
+                "traffic": ncu_traffic(args.workload),
+                "traffic_source": "profiles/traffic.json: ncu --set full capture of this kernel at this size, not re-measured in this run",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": units * by, "kernel_ms": ms_per_step,
                 "median_step_ms": sorted(per)[len(per) // 2], "min_step_ms": min(per)}
 
@@ -750,39 +693,48 @@ def main():
                "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
                "api": "mufft_execute_plan_1d_batch(host pinned in/out)" if kind in ("c2c", "r2c", "c2r") else "host-pointer batch API",
                "matches_device_path": same}
-        if world == 1:
-            # what the bus itself does on this box with the same pinned buffers (plain cudaMemcpyAsync through torch,
-            # 1 GiB each way): the ceiling of any host-buffer path, reported next to the e2e number it bounds
-            try:
-                rows = max(1, min(host_in.shape[0], host_out.shape[0], (1 << 30) // max(1, 4 * max(host_in.shape[1], host_out.shape[1]))))
-                s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        # What the bus itself does on this box with the same pinned buffers (plain cudaMemcpyAsync through torch,
+        # up to 1 GiB each way per GPU): the ceiling of any host-buffer path, reported next to the e2e number it
+        # bounds.  At N > 1 every rank copies at the same time (barrier-aligned) and the aggregate is reported.
+        try:
+            rows = max(1, min(host_in.shape[0], host_out.shape[0], (1 << 30) // max(1, 4 * max(host_in.shape[1], host_out.shape[1]))))
+            s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
 
-                def copy_in():
-                    with torch.cuda.stream(s_in):
-                        job.inp[:rows].copy_(host_in[:rows], non_blocking=True)
+            def copy_in():
+                with torch.cuda.stream(s_in):
+                    job.inp[:rows].copy_(host_in[:rows], non_blocking=True)
 
-                def copy_out():
-                    with torch.cuda.stream(s_out):
-                        host_out[:rows].copy_(job.out[:rows], non_blocking=True)
+            def copy_out():
+                with torch.cuda.stream(s_out):
+                    host_out[:rows].copy_(job.out[:rows], non_blocking=True)
 
-                def rate(fns, nbytes):
-                    best = 0.0
-                    for _ in range(3):
+            def rate(fns, nbytes):
+                best = 0.0
+                for _ in range(3):
+                    torch.cuda.synchronize()
+                    if dist is not None:
+                        dist.barrier()
                         torch.cuda.synchronize()
-                        t1 = time.perf_counter()
-                        for fn in fns:
-                            fn()
-                        torch.cuda.synchronize()
-                        best = max(best, nbytes / (time.perf_counter() - t1) * 1e-9)
-                    return best
-                b_in, b_out = rows * host_in.shape[1] * 4, rows * host_out.shape[1] * 4
-                copy_in(); copy_out(); torch.cuda.synchronize()
-                e2e["pcie"] = {"h2d_alone_gbs": rate([copy_in], b_in), "d2h_alone_gbs": rate([copy_out], b_out),
-                               "both_ways_gbs": rate([copy_in, copy_out], b_in + b_out),
-                               "e2e_gbs": (host_in.numel() + host_out.numel()) * 4 / (dt / e2e_steps) * 1e-9,
-                               "how": "torch pinned<->device copies of %.2f GiB each way on two streams, best of 3" % (b_in / 2**30)}
-            except Exception as exc:
-                e2e["pcie"] = {"error": repr(exc)[:200]}
+                    t1 = time.perf_counter()
+                    for fn in fns:
+                        fn()
+                    torch.cuda.synchronize()
+                    el = time.perf_counter() - t1
+                    if dist is not None:
+                        tt = torch.tensor([el], dtype=torch.float64, device="cuda")
+                        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                        el = float(tt.item())
+                    best = max(best, n_gpus * nbytes / el * 1e-9)
+                return best
+            b_in, b_out = rows * host_in.shape[1] * 4, rows * host_out.shape[1] * 4
+            copy_in(); copy_out(); torch.cuda.synchronize()
+            both = rate([copy_in, copy_out], b_in + b_out)
+            e2e_gbs = n_gpus * (host_in.numel() + host_out.numel()) * 4 / (dt / e2e_steps) * 1e-9
+            e2e["pcie"] = {"h2d_alone_gbs": round(rate([copy_in], b_in), 1), "d2h_alone_gbs": round(rate([copy_out], b_out), 1),
+                           "both_ways_gbs": round(both, 1), "e2e_gbs": round(e2e_gbs, 1), "e2e_over_bus": round(e2e_gbs / both, 3),
+                           "how": "aggregate over %d GPU(s): plain pinned<->device copies of %.2f GiB each way per GPU on two streams, all ranks at once, best of 3" % (n_gpus, b_in / 2**30)}
+        except Exception as exc:
+            e2e["pcie"] = {"error": repr(exc)[:200]}
         del host_in, host_out
 
     also = {}
@@ -797,11 +749,9 @@ def main():
             t_ms, per2 = time_steps(torch, None, j2, 10, 10)
             l2 = m.mufft_cuda_launch_count(1) * 10 // 20
             ms2 = t_ms / 10
-            also[name] = {"workload": DESCRIPTION[name], "gflops": u2 * flops_per_unit(k2, n2, ny2) / (ms2 * 1e-3) * 1e-9,
-                          "units_per_s": u2 / (ms2 * 1e-3), "ms_per_step": ms2,
-                          "hbm_gbs_algorithmic": u2 * bytes_per_unit(k2, n2, ny2) / (ms2 * 1e-3) * 1e-9,
-                          "roofline_frac": u2 * bytes_per_unit(k2, n2, ny2) / (ms2 * 1e-3) * 1e-9 / peak,
-                          "gpu_launches": l2}
+            gbs2 = u2 * bytes_per_unit(k2, n2, ny2) / (ms2 * 1e-3) * 1e-9
+            also[name] = {"ms": round(ms2, 4), "gflops": round(u2 * flops_per_unit(k2, n2, ny2) / (ms2 * 1e-3) * 1e-9, 1),
+                          "gbs": round(gbs2, 1), "frac": round(gbs2 / peak, 3), "launches": l2}
             j2.free()
             del j2
             torch.cuda.empty_cache()
@@ -818,23 +768,15 @@ def main():
         for _ in range(iters):
             m.mufft_execute_plan_1d(plan, a_out, a_in)
         us = (time.perf_counter() - t0) / iters * 1e6
-        also["c2c64_single_call"] = {"workload": "1D C2C forward N=64, one transform per mufft_execute_plan_1d call (BASELINE configs[0])",
-                                     "us_per_call": us, "gflops": 5 * 64 * 6 / us * 1e-3,
-                                     "note": "launch + synchronise per call; the batched form of the same transform is 'c2c64'"}
+        # launch + synchronise per call; the batched form of the same transform is 'c2c64'
+        also["c2c64_single_call"] = {"us_per_call": round(us, 3), "gflops": round(5 * 64 * 6 / us * 1e-3, 4)}
         m.mufft_free(a_in); m.mufft_free(a_out); m.mufft_free_plan_1d(plan)
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and not args.no_cpu:
+        # the other ranks wait in the barrier below; a bounded sample (~20 s of CPU work over all cores)
         cpu = cpu_reference_sample(kind, n, ny, seconds_of_cpu_work=20.0)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-
-    # last, when every number of the line is in hand: the opt-in paths, each in a child process
-    if world == 1 and args.also and not args.units and args.workload == "c2c4096" and os.environ.get("MUFFT_BENCH_PROBES", "1") != "0":
-        torch.cuda.synchronize()
-        try:
-            also["optin_probes"] = run_optin_probes()
-        except Exception as exc:  # never lose the line over a probe
-            also["optin_probes"] = [{"error": repr(exc)[:200]}]
 
     if rank == 0:
         line = {
@@ -850,7 +792,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": clock_info, "also": also,
         }
-        print(json.dumps(line), flush=True)
+        print(format_line(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

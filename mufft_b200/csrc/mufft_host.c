@@ -18,6 +18,7 @@
 #include "abi.h"
 
 #include <math.h>
+#include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -142,17 +143,38 @@ void mufft_cuda_set_fused_2d(int mode) { g_fused_2d = mode <= 0 ? 0 : (mode > 16
 static __thread void *tls_stream = NULL;
 static __thread char tls_error[256] = "";
 
+/* Error convention of this file: 0 = success; MCU_ERR_REPORTED = failure whose message is already in
+ * tls_error (set by the innermost layer that knew what went wrong); any other value = a raw CUDA error
+ * code from abi.h that nobody has described yet.  fail() turns the latter into the former exactly once, so
+ * that enclosing TRY() layers pass an inner message through instead of overwriting it. */
+#define MCU_ERR_REPORTED (-1)
+static __thread unsigned tls_warned = 0;
+static void warn_stderr(void)
+{
+    /* the fft.h execute calls return void: stderr is the only signal a caller that does not poll
+     * mufft_cuda_last_error() gets.  Rate-limited per thread, not once per process. */
+    if (tls_warned < 8) {
+        tls_warned++;
+        fprintf(stderr, "mufft_b200: %s%s\n", tls_error, tls_warned == 8 ? " (further messages on this thread suppressed)" : "");
+    }
+}
+#if defined(__GNUC__)
+__attribute__((format(printf, 1, 2)))
+#endif
+static int set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tls_error, sizeof(tls_error), fmt, ap);
+    va_end(ap);
+    warn_stderr();
+    return MCU_ERR_REPORTED;
+}
 static int fail(int err, const char *what)
 {
-    if (err != 0) {
-        snprintf(tls_error, sizeof(tls_error), "%s: %s", what, mcu_error_string(err));
-        static int warned = 0;
-        if (!warned) {
-            warned = 1;
-            fprintf(stderr, "mufft_b200: %s\n", tls_error);
-        }
-    }
-    return err;
+    if (err == 0) return 0;
+    if (err != MCU_ERR_REPORTED) return set_error("%s: %s", what, mcu_error_string(err));
+    return MCU_ERR_REPORTED;
 }
 #define TRY(expr) do { int e_ = (expr); if (e_ != 0) return fail(e_, #expr); } while (0)
 
@@ -160,12 +182,7 @@ static int have_device(void)
 {
     int count = 0;
     if (mcu_device_count(&count) != 0 || count <= 0) {
-        snprintf(tls_error, sizeof(tls_error), "no usable CUDA device (this library has no CPU path)");
-        static int warned = 0;
-        if (!warned) {
-            warned = 1;
-            fprintf(stderr, "mufft_b200: %s\n", tls_error);
-        }
+        (void)set_error("no usable CUDA device (this library has no CPU path)");
         return 0;
     }
     return 1;
@@ -425,9 +442,8 @@ static int stage_check_device(const stage *st)
 {
     int dev = -1;
     if (st->device_plus_1 != 0 && mcu_get_device(&dev) == 0 && dev != st->device_plus_1 - 1) {
-        snprintf(tls_error, sizeof(tls_error), "plan was created on CUDA device %d but device %d is current "
-                 "(mufft_cuda_set_device)", st->device_plus_1 - 1, dev);
-        return -1;
+        return set_error("plan was created on CUDA device %d but device %d is current "
+                         "(mufft_cuda_set_device)", st->device_plus_1 - 1, dev);
     }
     return 0;
 }
@@ -488,8 +504,7 @@ static int run_any(stage *st, unit_launch fn, void *ctx, const io_desc *io, int 
         return 0;
     }
     if (async) {
-        snprintf(tls_error, sizeof(tls_error), "asynchronous execute needs device-accessible (device or managed), 8-byte aligned pointers");
-        return -1;
+        return set_error("asynchronous execute needs device-accessible (device or managed), 8-byte aligned pointers");
     }
 
     TRY(stage_init(st));
@@ -650,9 +665,8 @@ static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode
 {
     const unsigned n = ax->n;
     if ((in_mode == MCU_IN_MULACC || in_mode == MCU_IN_MULACC_C2R) && (pd == NULL || ax->d_engine_tw == NULL)) {
-        snprintf(tls_error, sizeof(tls_error), "partitioned convolution needs a transform that fits the on-chip engine "
+        return set_error("partitioned convolution needs a transform that fits the on-chip engine "
                  "(stereo N <= %u, mono N <= %u)", g_onchip_limit, 2 * g_onchip_limit);
-        return -1;
     }
     if (ax->d_engine_tw != NULL) {
         mcu_rows_args a;
@@ -682,8 +696,7 @@ static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode
         return mcu_launch_rows_cluster(&a, stream);
     }
     if (out_mode == MCU_OUT_PEERS && !(ax->n2 != 0 && g_two_kernel)) {
-        snprintf(tls_error, sizeof(tls_error), "scatter: this length has no two-kernel path");
-        return -1;
+        return set_error("scatter: this length has no two-kernel path");
     }
 
     /* Generic path: bounded scratch, so walk the batch in chunks (L2-sized for the two-kernel path). */
@@ -817,8 +830,7 @@ static int exec_1d(mufft_plan_1d *plan, int in_mode, int out_mode, float norm,
     io.in2_stride = in2_stride;
     io.count = batch;
     if ((io.in_stride | io.out_stride | io.in2_stride) % CPX != 0) {
-        snprintf(tls_error, sizeof(tls_error), "strides must be multiples of 8 bytes");
-        return -1;
+        return set_error("strides must be multiples of 8 bytes");
     }
     return run_any(&plan->st, rows_unit_launch, &ctx, &io, async);
 }
@@ -853,20 +865,17 @@ int mufft_execute_plan_1d_batch_scatter_async(mufft_plan_1d *plan, void *const *
     const int real = plan != NULL && plan->kind == KIND_R2C;
     if (plan == NULL || (plan->kind != KIND_C2C && !real) || plan->zero_pad || peers == 0 || peers > MCU_MAX_PEERS ||
         (peers & (peers - 1)) != 0 || plan->n % peers != 0 || input_stride_bytes % CPX != 0) {
-        snprintf(tls_error, sizeof(tls_error), "scatter: needs a plain C2C or R2C plan and a power-of-two number of devices dividing its complex length");
-        return -1;
+        return set_error("scatter: needs a plain C2C or R2C plan and a power-of-two number of devices dividing its complex length");
     }
     if (stage_check_device(&plan->st) != 0) return -1;
     if (real && plan->ax.d_engine_tw == NULL) {
-        snprintf(tls_error, sizeof(tls_error), "scatter: R2C rows must fit the single-kernel engine (N <= %u reals)", 2 * g_onchip_limit);
-        return -1;
+        return set_error("scatter: R2C rows must fit the single-kernel engine (N <= %u reals)", 2 * g_onchip_limit);
     }
     /* plan->n complex points per row either way (an R2C row of N reals is N/2 complex) */
     const size_t in_stride = input_stride_bytes ? input_stride_bytes : (size_t)plan->n * CPX;
     if (batch == 0) return 0;
     if (!device_visible(mcu_pointer_kind(input), in_stride * (batch - 1) + (size_t)plan->n * CPX)) {
-        snprintf(tls_error, sizeof(tls_error), "scatter: needs device-accessible (device or managed) pointers");
-        return -1;
+        return set_error("scatter: needs device-accessible (device or managed) pointers");
     }
     mcu_peer_dest d;
     memset(&d, 0, sizeof(d));
@@ -912,15 +921,13 @@ int mufft_execute_plan_1d_columns(mufft_plan_1d *plan, void *output, const void 
 {
     if (plan == NULL || plan->kind != KIND_C2C || plan->zero_pad || width == 0 || width > 0xffffffffu ||
         (output_pitch_bytes | input_pitch_bytes) % CPX != 0) {
-        snprintf(tls_error, sizeof(tls_error), "columns: needs a plain C2C plan and pitches that are multiples of 8 bytes");
-        return -1;
+        return set_error("columns: needs a plain C2C plan and pitches that are multiples of 8 bytes");
     }
     if (stage_check_device(&plan->st) != 0) return -1;
     const size_t span_in = input_pitch_bytes * ((size_t)plan->n - 1) + width * CPX;
     const size_t span_out = output_pitch_bytes * ((size_t)plan->n - 1) + width * CPX;
     if (!device_visible(mcu_pointer_kind(input), span_in) || !device_visible(mcu_pointer_kind(output), span_out)) {
-        snprintf(tls_error, sizeof(tls_error), "columns: needs device-accessible (device or managed) pointers");
-        return -1;
+        return set_error("columns: needs device-accessible (device or managed) pointers");
     }
     if (plan->ax_cols.n == 0 && axis_init(&plan->ax_cols, plan->n, plan->direction, plan->n > MCU_COLS_MAX_N ? AXIS_COLS : 0) != 0) return -1;
     return run_cols_axis(&plan->ax_cols, &plan->scr_cols, output, output_pitch_bytes / CPX, 0, input, input_pitch_bytes / CPX, 0,
@@ -1089,8 +1096,7 @@ static int conv_fused(mufft_plan_conv *plan, void *output, const void *input, co
     io.in2_stride = filter_stride;
     io.count = batch;
     if (filter_stride % CPX != 0) {
-        snprintf(tls_error, sizeof(tls_error), "strides must be multiples of 8 bytes");
-        return -1;
+        return set_error("strides must be multiples of 8 bytes");
     }
     return run_any(&plan->plans[0]->st, conv_unit_launch, &ctx, &io, async);
 }
@@ -1114,16 +1120,14 @@ static int conv_partitioned(mufft_plan_conv *plan, void *output, const void *spe
                             unsigned parts, size_t batch, int async)
 {
     if (plan == NULL || parts == 0) {
-        snprintf(tls_error, sizeof(tls_error), "partitioned convolution: needs a plan and at least one partition");
-        return -1;
+        return set_error("partitioned convolution: needs a plan and at least one partition");
     }
     if (batch == 0) return 0;
     if (stage_check_device(&plan->output_plan->st) != 0) return -1;
     const size_t blk = plan->block_size;
     const size_t out_unit = (size_t)plan->output_plan->n * CPX;
     if ((((uintptr_t)output | (uintptr_t)spectra | (uintptr_t)filter_spectra) % CPX) != 0) {
-        snprintf(tls_error, sizeof(tls_error), "buffers must be 8-byte aligned");
-        return -1;
+        return set_error("buffers must be 8-byte aligned");
     }
     /* the history blocks in front of `spectra` are read too: classify the whole range */
     const char *first = (const char *)spectra - (size_t)(parts - 1) * blk;
@@ -1131,8 +1135,7 @@ static int conv_partitioned(mufft_plan_conv *plan, void *output, const void *spe
         !device_visible(mcu_pointer_kind(spectra), batch * blk) ||
         !device_visible(mcu_pointer_kind(filter_spectra), (size_t)parts * blk) ||
         !device_visible(mcu_pointer_kind(output), batch * out_unit)) {
-        snprintf(tls_error, sizeof(tls_error), "partitioned convolution needs device-accessible (device or managed) pointers");
-        return -1;
+        return set_error("partitioned convolution needs device-accessible (device or managed) pointers");
     }
     part_desc pd = { parts, -(long long)(blk / CPX), (long long)(blk / CPX) };
     mufft_plan_1d *inv = plan->output_plan;

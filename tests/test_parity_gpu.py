@@ -167,3 +167,51 @@ def test_flags_cpu_bits_ignored(gpu, oracle):
     base = gpu.c2c(x, FORWARD, 0)
     for flags in range(8):  # test.c sweeps all NO_AVX|NO_SSE3|NO_SSE subsets
         assert np.array_equal(gpu.c2c(x, FORWARD, flags), base)
+
+
+@pytest.mark.parametrize("samples", [5, 2049, 8192])
+@pytest.mark.parametrize("where", ["pageable", "managed", "device"])
+def test_get_convolve_func(oracle, samples, where):
+    """mufft_get_convolve_func (ref fft.h:201-207): the returned function computes out = norm * a .* b
+    (ref kernel.c:22-34) on whatever memory it is handed and is complete on return."""
+    import ctypes as C
+
+    import mufft_b200 as m
+
+    if m.mufft_cuda_device_count() < 1:
+        pytest.fail("no CUDA device visible")
+    fn = m.mufft_get_convolve_func(0)
+    assert fn
+    a, b = cplx(samples, seed=10), cplx(samples, seed=11)
+    norm = 1.0 / 4096.0
+    want = np.zeros(samples, np.complex64)
+    oracle.lib.oracle_convolve.argtypes = [C.c_void_p] * 3 + [C.c_float, C.c_uint]
+    oracle.lib.oracle_convolve.restype = None
+    oracle.lib.oracle_convolve(want.ctypes.data, a.ctypes.data, b.ctypes.data, norm, samples)
+    nbytes = samples * 8
+    if where == "pageable":
+        got = np.zeros(samples, np.complex64)
+        fn(got.ctypes.data, a.ctypes.data, b.ctypes.data, norm, samples)
+    elif where == "managed":
+        ptrs = [m.mufft_alloc(nbytes) for _ in range(3)]
+        assert all(ptrs)
+        views = [np.frombuffer((C.c_char * nbytes).from_address(p), np.complex64) for p in ptrs]
+        views[1][:] = a
+        views[2][:] = b
+        fn(ptrs[0], ptrs[1], ptrs[2], norm, samples)
+        got = views[0].copy()
+        del views
+        for p in ptrs:
+            m.mufft_free(p)
+    else:
+        import torch
+        da = torch.from_numpy(a.view(np.float32)).cuda()
+        db = torch.from_numpy(b.view(np.float32)).cuda()
+        do = torch.zeros_like(da)
+        torch.cuda.synchronize()
+        fn(do.data_ptr(), da.data_ptr(), db.data_ptr(), norm, samples)
+        got = do.cpu().numpy().view(np.complex64)
+    assert rel_l2(got, want) <= 1e-6
+    assert np.max(np.abs(got - want)) <= 1e-7
+    truth = norm * a.astype(np.complex128) * b.astype(np.complex128)
+    assert rel_l2(got, truth) <= 1e-6
