@@ -77,7 +77,7 @@ DESCRIPTION = {
     "c2c2d1024": "batched 2D C2C 1024x1024, batch 256 per GPU (BASELINE configs[3])",
     "c2c64": "batched 1D C2C forward N=64, batch 2^24 per GPU (batched form of BASELINE configs[0])",
     "c2c16384": "batched 1D C2C forward N=16384, batch 32768 per GPU (longest single-kernel length: one 512-thread CTA per transform)",
-    "c2c32768": "batched 1D C2C forward N=32768, batch 16384 per GPU (first length on the two-kernel split; row length of BASELINE configs[4])",
+    "c2c32768": "batched 1D C2C forward N=32768, batch 16384 per GPU (single-launch four-step kernel, intermediate in L2; row length of BASELINE configs[4])",
     "c2c256": "batched 1D C2C forward N=256, batch 2^22 per GPU",
     "c2c1024": "batched 1D C2C forward N=1024, batch 2^20 per GPU",
     "c2c2048": "batched 1D C2C forward N=2048, batch 2^19 per GPU",
@@ -614,8 +614,6 @@ def main():
     dev = torch.device("cuda", local)
     assert m.mufft_cuda_set_device(local) == 0
     m.mufft_cuda_set_stream(torch.cuda.current_stream().cuda_stream or None)
-    if os.environ.get("MUFFT_BENCH_FUSED_2D"):
-        m.mufft_cuda_set_fused_2d(int(os.environ["MUFFT_BENCH_FUSED_2D"]))
     dist = None
     if world > 1:
         import torch.distributed as dist_mod

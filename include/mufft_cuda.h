@@ -78,6 +78,11 @@ int mufft_execute_plan_1d_batch_scatter_async(mufft_plan_1d *plan, void *const *
  * into this one (peer access over NVLink is enabled on demand). */
 void *mufft_cuda_device_alloc(size_t size);
 void mufft_cuda_device_free(void *ptr);
+/* Synchronous helpers for callers that keep their data in device memory: copy `bytes` between any two kinds of
+ * memory (host, pinned, managed, device), fill device-accessible memory with a byte value.  Both are ordered after the
+ * work already queued on the current stream and complete on return.  0 on success. */
+int mufft_cuda_copy(void *dst, const void *src, size_t bytes);
+int mufft_cuda_memset(void *ptr, int value, size_t bytes);
 int mufft_cuda_ipc_export(void *handle64, void *device_ptr);
 void *mufft_cuda_ipc_import(const void *handle64);
 int mufft_cuda_ipc_close(void *ptr);
@@ -126,76 +131,37 @@ int mufft_execute_conv_batch_async(mufft_plan_conv *plan, void *output, const vo
  * distance apart.  Outputs as mufft_execute_conv_output writes them, tightly packed; the caller
  * overlap-adds consecutive output blocks exactly as with a one-block filter.  Device-accessible
  * (device or managed) memory only; the transform must fit the on-chip engine (stereo N <= 16384,
- * mono N <= 32768 with the default mufft_cuda_set_onchip_limit), otherwise nonzero is returned. */
+ * mono N <= 32768), otherwise nonzero is returned. */
 int mufft_execute_conv_output_partitioned_batch(mufft_plan_conv *plan, void *output, const void *spectra,
                                                 const void *filter_spectra, unsigned parts, size_t batch);
 int mufft_execute_conv_output_partitioned_batch_async(mufft_plan_conv *plan, void *output, const void *spectra,
                                                       const void *filter_spectra, unsigned parts, size_t batch);
 
-/* Row-transform kernel flavour: 0 = direct loads (default), 1 = persistent CTAs with bulk-copy
- * prefetch into shared memory when the input rows are 16-byte aligned.  Same results either way. */
-void mufft_cuda_set_prefetch(int enable);
-/* 2D C2C transforms of 256..2048 points per side.
- *   1 (default)  one persistent kernel does rows and columns of the whole batch with the intermediate
- *                kept in L2, in the flavour measured fastest for the shape;
- *   0            separate row and column kernels per group of images (what every other 2D shape uses);
- *   2..16        that kernel in one fixed flavour, for measurements and tests: 8 plain; 7 one-sided
- *                (release / acquire) fences in the ticket protocol; 3 = 7 + twiddle tables staged in
- *                shared memory; 6 = 7 + only the power-of-two twiddles loaded, the rest derived;
- *                5 = 3 + 6; 2 / 4 = tiles brought into shared memory by the TMA unit one tile ahead
- *                (bulk copy for row tiles, 2D tensor-map boxes for column tiles), plain / as 3 -
- *                measured slower than direct loads on B200, kept as an experiment; 9 / 10 = 3 / 6 with
- *                tickets drawn two tiles ahead and the dependency of a column ticket read early
- *                (not measured yet); 11 = 6 compiled for three CTAs per SM instead of two (80 registers,
- *                the excess spilled; not measured yet); 12 / 13 = 3 / 6 with row and column tickets
- *                alternating inside a round instead of all row tickets first (not measured yet);
- *                14 = 7 at three CTAs per SM, 15 = 11 + 13, 16 = 3 at three CTAs per SM (three exchange areas
- *                and three table copies fit the shared memory of an SM for 1024 x 1024 and the 256 / 512-point
- *                shapes only) (not measured yet).
- * Same results (within rounding of the derived twiddles) in all modes.  MUFFT_CUDA_FUSED_2D in the
- * environment sets the initial value. */
-void mufft_cuda_set_fused_2d(int mode);
-/* Fused 2D kernel, measurement knob: the column pass of an image starts this many images behind its row
- * pass (0 = default: chosen from the number of resident CTAs, 3 for 1024 x 1024 on a B200).  Same results
- * for every value.  MUFFT_CUDA_FUSED_2D_LAG sets the initial value. */
-void mufft_cuda_set_fused_2d_lag(unsigned images);
-/* Longest row transform done by ONE kernel, for plans created afterwards: 16384 (default: one
- * 512-thread CTA per 16384-point transform, read once and written once) or 8192 (16384 points take
- * the two-kernel split; measured 1.8x slower, kept for comparison).  Affects 1D plans of 16384
- * complex / 32768 real points and 2D plans with such rows.  Other values are rounded down to one of
- * the two.  Same results either way.  MUFFT_CUDA_ONCHIP_LIMIT in the environment sets the initial value. */
-void mufft_cuda_set_onchip_limit(unsigned n);
-unsigned mufft_cuda_get_onchip_limit(void);
-/* 2D R2C plans whose row transforms have 256..2048 complex points (Nx = 512..4096 reals) and 256..2048
- * rows: 1 = the fused persistent kernel (real row transforms with the resolve epilogue straight into
- * the output, column transforms in place, intermediate kept in L2), 0 (default until measured on the
- * GPU) = row kernel + column kernel through plan scratch.  Same results either way.
- * MUFFT_CUDA_FUSED_2D_REAL sets the initial value. */
-void mufft_cuda_set_fused_2d_real(int enable);
-/* Latency of synchronous calls on small transforms (one launch + one synchronise per
- * mufft_execute_plan_1d call): 1 = the library busy-polls the stream instead of blocking in the driver
- * when a call touches at most 1 MiB; 0 (default until measured).  MUFFT_CUDA_SPIN_SYNC sets the initial value. */
-void mufft_cuda_set_spin_sync(int enable);
-/* Synchronous calls on CUDA managed memory (mufft_alloc) that the caller fills and reads on the host between
- * calls: 0 (default until measured) = the kernel's page faults migrate the pages, 1 = buffers of 256 KiB or more
- * are prefetched to the device in front of the kernel, 2 = and the output back to the host behind it (only
- * right when the host reads it next).  MUFFT_CUDA_MANAGED_PREFETCH sets the initial value. */
-void mufft_cuda_set_managed_prefetch(int level);
-/* Row transforms of 32768 and 65536 points, for plans created afterwards: 1 = ONE kernel on a
- * thread-block cluster of 2 / 4 CTAs (512 threads each, the transform in registers, exchange through
- * distributed shared memory: 1 = remote stores + release / acquire cluster barriers, 2 = st.async
- * remote stores counted on an mbarrier of the receiving CTA), 0 (default until measured on the GPU) =
- * the two-kernel split.  Plain and
- * zero-padded C2C and the scatter epilogue of the slab exchange; real transforms of these lengths keep
- * the two-kernel path.  Same results either way.  MUFFT_CUDA_CLUSTER_ROWS sets the initial value. */
-void mufft_cuda_set_cluster_rows(int mode);
-/* Transform lengths beyond the single-kernel limit, up to 2097152: 1 (default) = two kernels (N = N1*N2: column transforms, then
- * twiddle + row transforms with a transposed store), 0 = one generic radix pass per kernel. */
-void mufft_cuda_set_two_kernel(int enable);
+/* Plan-creation flags of this implementation, OR-ed into the `flags` argument of the fft.h constructors
+ * (the reference's own flags use bits 0-2, 16 and 17, its internal ones bits 24-28; ref fft.h:52-65,
+ * fft_internal.h:180-192).  They select the slower fallback paths, which are kept for measurement and
+ * for tests; results are the same (within rounding) on every path.  There is no process-global switch:
+ * what a plan does is fixed when it is created, and two plans with different flags can run side by side.
+ *   MUFFT_CUDA_FLAG_SEPARATE_2D     2D plans: row kernel + column kernel through plan scratch instead of the
+ *                                   fused persistent kernel (which exists for 256..2048 complex points per side).
+ *   MUFFT_CUDA_FLAG_TWO_KERNEL      rows longer than 8192 points: the two-kernel four-step split through
+ *                                   scratch in HBM instead of the single-launch kernels (16384 points on one
+ *                                   CTA, 32768..1048576 points on the four-step kernel that keeps its
+ *                                   intermediate in L2).
+ *   MUFFT_CUDA_FLAG_GENERIC_PASSES  lengths beyond 8192 points: one generic radix-8/4/2 Stockham pass per
+ *                                   kernel launch (the reference's own structure, fft.c:811-850).
+ *   MUFFT_CUDA_FLAG_FOUR_STEP_16K   16384-point rows: the single-launch four-step kernel (16 x 1024) instead
+ *                                   of the one-CTA engine kernel. */
+#define MUFFT_CUDA_FLAG_SEPARATE_2D (1u << 20)
+#define MUFFT_CUDA_FLAG_TWO_KERNEL (1u << 21)
+#define MUFFT_CUDA_FLAG_GENERIC_PASSES (1u << 22)
+#define MUFFT_CUDA_FLAG_FOUR_STEP_16K (1u << 23)
 
 /* Introspection used by tests and the bench: which path a plan takes.
- * 1D: 1 = single-kernel shared-memory engine, 0 = multi-pass generic kernels.
- * 2D: bit 0 = rows on the engine, bit 1 = columns on the shared-memory column kernel. */
+ * 1D: 1 = one kernel launch per batch (on-chip engine up to 16384 points, L2-resident four-step beyond),
+ *     0 = several launches through scratch.
+ * 2D: bit 0 = rows in one launch, bit 1 = columns on the shared-memory column kernel, bit 2 = the fused
+ *     persistent kernel does the whole transform. */
 int mufft_cuda_plan_1d_uses_engine(const mufft_plan_1d *plan);
 int mufft_cuda_plan_2d_paths(const mufft_plan_2d *plan);
 

@@ -32,6 +32,11 @@ MUFFT_CONV_METHOD_FLAG_ZERO_PAD_UPPER_HALF_FIRST = 1 << 2
 MUFFT_CONV_METHOD_FLAG_ZERO_PAD_UPPER_HALF_SECOND = 1 << 3
 MUFFT_CONV_BLOCK_FIRST = 0
 MUFFT_CONV_BLOCK_SECOND = 1
+# plan-creation flags of include/mufft_cuda.h (slower fallback paths, for measurement and tests)
+MUFFT_CUDA_FLAG_SEPARATE_2D = 1 << 20
+MUFFT_CUDA_FLAG_TWO_KERNEL = 1 << 21
+MUFFT_CUDA_FLAG_GENERIC_PASSES = 1 << 22
+MUFFT_CUDA_FLAG_FOUR_STEP_16K = 1 << 23
 
 _vp, _u, _i, _sz = C.c_void_p, C.c_uint, C.c_int, C.c_size_t
 mufft_convolve_func = C.CFUNCTYPE(None, _vp, _vp, _vp, C.c_float, _u)
@@ -72,6 +77,8 @@ SIGNATURES = {
     "mufft_execute_plan_1d_batch_scatter_async": (_i, [_vp, C.POINTER(C.c_void_p), _u, _sz, _vp, _sz, _sz]),
     "mufft_cuda_device_alloc": (_vp, [_sz]),
     "mufft_cuda_device_free": (None, [_vp]),
+    "mufft_cuda_copy": (_i, [_vp, _vp, _sz]),
+    "mufft_cuda_memset": (_i, [_vp, _i, _sz]),
     "mufft_cuda_ipc_export": (_i, [_vp, _vp]),
     "mufft_cuda_ipc_import": (_vp, [_vp]),
     "mufft_cuda_ipc_close": (_i, [_vp]),
@@ -85,16 +92,6 @@ SIGNATURES = {
     "mufft_execute_conv_batch_async": (_i, [_vp, _vp, _vp, _vp, _sz, _sz]),
     "mufft_execute_conv_output_partitioned_batch": (_i, [_vp, _vp, _vp, _vp, _u, _sz]),
     "mufft_execute_conv_output_partitioned_batch_async": (_i, [_vp, _vp, _vp, _vp, _u, _sz]),
-    "mufft_cuda_set_prefetch": (None, [_i]),
-    "mufft_cuda_set_fused_2d": (None, [_i]),
-    "mufft_cuda_set_fused_2d_real": (None, [_i]),
-    "mufft_cuda_set_fused_2d_lag": (None, [_u]),
-    "mufft_cuda_set_two_kernel": (None, [_i]),
-    "mufft_cuda_set_cluster_rows": (None, [_i]),
-    "mufft_cuda_set_spin_sync": (None, [_i]),
-    "mufft_cuda_set_managed_prefetch": (None, [_i]),
-    "mufft_cuda_set_onchip_limit": (None, [_u]),
-    "mufft_cuda_get_onchip_limit": (_u, []),
     "mufft_cuda_plan_1d_uses_engine": (_i, [_vp]),
     "mufft_cuda_plan_2d_paths": (_i, [_vp]),
 }

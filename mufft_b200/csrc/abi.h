@@ -70,7 +70,6 @@ typedef struct mcu_rows_args {
     int direction;         /* -1 forward, +1 inverse */
     int in_mode, out_mode;
     float norm;
-    int prefetch;          /* 1 = use the persistent bulk-copy prefetch kernel when the input allows it */
     unsigned parts;        /* MCU_IN_MULACC*: number of (spectrum, filter partition) pairs summed per transform */
     long long in_part_stride;  /* complex elements from the spectrum of pair p to that of pair p+1 (may be negative) */
     long long in2_part_stride; /* same for the filter partitions */
@@ -124,26 +123,42 @@ typedef struct mcu_rowst_args {
     mcu_peer_dest peers;
 } mcu_rowst_args;
 
-/* Fused 2D C2C kernel (fft2d_kernel.cuh): whole batch in one persistent launch. */
+/* Fused 2D kernel (fft2d_kernel.cuh): whole batch in one persistent launch. */
+enum { MCU_2D_C2C = 0, MCU_2D_R2C = 1, MCU_2D_R2C_FULL = 2, MCU_2D_C2R = 3 };
 typedef struct mcu_2d_args {
-    void *out;             /* [batch][ny][nx] complex; also holds the row-transformed intermediate */
-    const void *in;
-    const void *tw_x, *tw_y; /* engine twiddle tables of nx and ny */
-    const void *rtw;       /* out_mode R2C / R2C_FULL: resolve twiddles of the rows, nx entries */
-    int out_mode;          /* MCU_OUT_COMPLEX: complex images; MCU_OUT_R2C / MCU_OUT_R2C_FULL: real images of 2 nx floats per row
-                            * in, rows of pitch 2 nx bins out (tw_x = the table of mcu_rows_variant(nx, MCU_IN_COMPLEX, out_mode)) */
-    unsigned *counters;    /* 1 + batch zero-initialised words: ticket counter, rows-done per image */
+    void *out;             /* C2C: [batch][ny][nx] complex, also holds the row-transformed intermediate; R2C: rows of pitch
+                            * 2 nx bins; C2R: [batch][ny][nx] complex = 2 nx floats per row */
+    const void *in;        /* C2C: as out; R2C: 2 nx floats per row; C2R: spectrum rows of pitch 2 nx bins, nx + 1 carry data */
+    const void *tw_x, *tw_y; /* engine twiddle tables of nx (the variant of mcu_2d_rows_variant) and ny (variant 0) */
+    const void *rtw;       /* R2C / C2R: resolve twiddles of the rows, nx entries */
+    int kind;              /* MCU_2D_*; nx = complex points per row transform (half the real row length) */
+    unsigned *counters;    /* 1 + 2 * batch zero-initialised words: ticket counter, producer / consumer tiles done per image */
+    void *mid;             /* C2R: ring of `ring` intermediate images of mcu_2d_mid_elems(nx, ny) complex each */
+    unsigned ring;
     size_t out_image, in_image; /* complex elements between consecutive images */
     size_t batch;
     unsigned nx, ny;
     int direction;
-    unsigned lag;          /* column tickets run this many images behind the row tickets (set by the launcher) */
-    int tma;               /* 1 = tiles are brought into shared memory by bulk async copies one tile ahead
-                            * (fft2d_tma_kernel.cuh) when shape and alignment allow, 0 = direct loads */
-    int flags;             /* kernel flavour, F2D_* bits of fft2d_kernel.cuh: 1 twiddle tables in shared memory,
-                            * 2 one-sided fences, 4 derived twiddles (the TMA kernel knows 0 and 3 only);
-                            * -1 = the launcher's measured choice for the shape */
+    unsigned lag;          /* consumer tickets run this many images behind the producer tickets (0 = the launcher's choice) */
 } mcu_2d_args;
+
+/* Single-launch four-step kernel for rows of n = n1 * n2 points (long_kernel.cuh): both steps in one
+ * persistent CTA, the intermediate in a scratch slot of n complex per CTA that stays in L2. */
+typedef struct mcu_long_args {
+    void *out;             /* X[k], natural order */
+    const void *in;
+    const void *tw;        /* engine twiddle table of n2 (variant 0) */
+    const void *roots;     /* exp(dir*2*pi*i*j/n), j < n */
+    void *scratch;         /* scratch_slots slots of n complex each */
+    size_t scratch_slots;  /* at most this many CTAs are launched */
+    size_t out_batch, in_batch; /* complex elements between consecutive transforms */
+    size_t batch;
+    unsigned n, n1, n2;
+    int direction;
+    int in_mode;           /* MCU_IN_COMPLEX or MCU_IN_HALF */
+    int to_peers;          /* 1 = scatter X over the devices of `peers` instead of writing `out` */
+    mcu_peer_dest peers;
+} mcu_long_args;
 
 /* Generic one-pass Stockham kernel (any length; used beyond the engine limits). */
 typedef struct mcu_pass_args {
@@ -201,7 +216,6 @@ int mcu_pointer_kind(const void *ptr);
 int mcu_stream_create(void **stream);
 int mcu_stream_destroy(void *stream);
 int mcu_stream_sync(void *stream);
-int mcu_stream_sync_spin(void *stream); /* same, busy-polling cudaStreamQuery */
 int mcu_event_create(void **event);
 int mcu_event_destroy(void *event);
 int mcu_event_record(void *event, void *stream);
@@ -213,20 +227,24 @@ int mcu_prefetch(const void *ptr, size_t bytes, int to_device, void *stream);
 
 /* ---- kernels ------------------------------------------------------------------------------ */
 int mcu_launch_rows(const mcu_rows_args *args, void *stream);
-/* Row transforms of 32768 / 65536 points on a thread-block cluster (rowsc_kernel.cuh): in_mode COMPLEX or
- * HALF, out_mode COMPLEX or PEERS, args->tw = the engine table of n (variant 0). */
-int mcu_rows_cluster_supported(unsigned n);
-int mcu_launch_rows_cluster(const mcu_rows_args *args, void *stream);
+/* Single-launch four-step rows: n2 of the split the kernel uses for n (0 = no such kernel for n), the
+ * number of CTAs it keeps resident on the current device (= scratch slots worth allocating), the launch. */
+unsigned mcu_long_n2(unsigned n);
+unsigned mcu_long_ctas(unsigned n);
+int mcu_launch_long(const mcu_long_args *args, void *stream);
 int mcu_launch_cols(const mcu_cols_args *args, void *stream);
 int mcu_launch_pass(const mcu_pass_args *args, void *stream);
 /* n2 of the two-kernel split of n for a row (columns = 0) or column (columns = 1) transform
  * (0 = n is outside its range and takes the generic passes) */
 unsigned mcu_split_n2(unsigned n, int columns);
 int mcu_launch_rowst(const mcu_rowst_args *args, void *stream);
-/* 1 if the fused 2D kernel exists for this image shape (nx = complex length of a row transform) and
- * kind of output (MCU_OUT_COMPLEX, or MCU_OUT_R2C / MCU_OUT_R2C_FULL for real images) */
+/* 1 if the fused 2D kernel exists for this image shape (nx = complex length of a row transform); the engine
+ * shape variant its row transforms use for a kind (selects the table passed as tw_x); the lag the launcher
+ * would pick on the current device (C2R: the ring must hold more than lag images); elements of a C2R ring slot */
 int mcu_2d_fused_supported(unsigned nx, unsigned ny);
-int mcu_2d_fused_real_supported(unsigned nx, unsigned ny, int out_mode);
+int mcu_2d_rows_variant(unsigned nx, int kind);
+unsigned mcu_2d_default_lag(unsigned nx, unsigned ny, int kind);
+size_t mcu_2d_mid_elems(unsigned nx, unsigned ny);
 int mcu_launch_2d_fused(const mcu_2d_args *args, void *stream);
 int mcu_launch_resolve(const mcu_resolve_args *args, void *stream);
 int mcu_launch_conv(const mcu_conv_args *args, void *stream);

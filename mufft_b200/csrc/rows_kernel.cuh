@@ -8,12 +8,10 @@
 // Fused into the last pass (epilogue):
 //   * R2C resolve, half or full spectrum (ref kernel.c:47-82, called at fft.c:846-849)
 //
-// Two kernels share the prologue / engine / epilogue code:
-//   fft_rows_kernel      one group of transforms per CTA, inputs loaded straight into registers;
-//   fft_rows_tma_kernel  persistent CTAs: the inputs of the NEXT groups are already on their way
-//                        into shared-memory landing buffers (cp.async.bulk + mbarrier, issued by
-//                        one thread) while the current group is being transformed, so enough
-//                        bytes are in flight per SM even when one transform fills the CTA.
+// fft_rows_kernel: one group of transforms per CTA, inputs loaded straight into registers.  (A persistent
+// variant fed by bulk async copies into shared-memory landing buffers was measured in round 1 and was
+// 2-12 % slower at every length - the landing-buffer read is one more shared-memory access per element on
+// the busiest pipe - so it is gone; profiles/README.md keeps the numbers.)
 #pragma once
 
 #include "abi.h"
@@ -90,7 +88,6 @@ __device__ __forceinline__ cpx mulacc_at(Ptr in, const cpx *__restrict__ in2, in
 
 // ---- prologue: registers <- input ------------------------------------------------------------------
 // Variant 0 / 1: element k = t + e*T in slot e.  Variant 2: the slots of the mirrored first pass.
-// `in` may point to global memory or to a shared-memory landing buffer.
 template <int N, int IN_MODE, int V, typename Ptr>
 __device__ __forceinline__ void rows_load(cpx (&v)[engine_regs(N, V)], Ptr in, const cpx *__restrict__ in2,
                                           const cpx *__restrict__ rtw, float norm, int t, const rows_parts pp = { 1, 0, 0 })
@@ -352,7 +349,7 @@ __device__ __forceinline__ void rows_store(cpx (&v)[engine_regs(N, V)], cpx *__r
     }
 }
 
-// ---- kernel 1: one group per CTA, direct loads ---------------------------------------------------
+// ---- the kernel: one group per CTA, direct loads ---------------------------------------------------
 template <int N, int DIR, int IN_MODE, int OUT_MODE>
 __global__ void __launch_bounds__(rows_cta_threads(N, rows_variant(N, IN_MODE, OUT_MODE)), engine_min_blocks(N, rows_variant(N, IN_MODE, OUT_MODE)))
 fft_rows_kernel(const mcu_rows_args a)
@@ -391,128 +388,5 @@ fft_rows_kernel(const mcu_rows_args a)
         rows_store<N, OUT_MODE, T, TPC, V>(v, out, sm, rtw, t, slot, active);
     }
 }
-
-// ---- kernel 2: persistent, inputs prefetched into shared memory by bulk async copies ------------
-#ifndef MUFFT_EMU // bulk async copies and mbarriers are not emulated (tests/emu)
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// global -> shared bulk copy (16-byte aligned addresses, size a multiple of 16), completion
-// counted in bytes on `bar`.
-__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-#endif // MUFFT_EMU
-
-#define MUFFT_TMA_STAGES 2
-// Bytes a landing buffer receives per transform (a multiple of 16).
-__host__ __device__ constexpr int rows_land_bytes(int n, int in_mode)
-{
-    return in_mode == MCU_IN_HALF ? n * 4 : (in_mode == MCU_IN_C2R || in_mode == MCU_IN_MUL_C2R) ? (n + 2) * 8 : n * 8;
-}
-__host__ __device__ constexpr size_t rows_tma_smem_bytes(int n, int in_mode, int v = 0)
-{
-    return 128 + (size_t)rows_per_cta(n, v) * (MUFFT_TMA_STAGES * (size_t)rows_land_bytes(n, in_mode) + rows_smem_elems(n, v) * sizeof(float2));
-}
-// The bulk-copy path needs whole 16-byte chunks.
-__host__ __device__ constexpr bool rows_tma_supported(int n, int in_mode, int v = 0)
-{
-    return n >= 64 && in_mode <= MCU_IN_MUL_C2R && rows_land_bytes(n, in_mode) % 16 == 0 && rows_tma_smem_bytes(n, in_mode, v) <= 227 * 1024 &&
-           MUFFT_TMA_STAGES * rows_per_cta(n, v) * 8 <= 128;
-}
-
-#ifndef MUFFT_EMU
-template <int N, int DIR, int IN_MODE, int OUT_MODE>
-__global__ void __launch_bounds__(rows_cta_threads(N, rows_variant(N, IN_MODE, OUT_MODE)), engine_min_blocks(N, rows_variant(N, IN_MODE, OUT_MODE)))
-fft_rows_tma_kernel(const mcu_rows_args a)
-{
-    constexpr int V = rows_variant(N, IN_MODE, OUT_MODE);
-    constexpr int R = engine_regs(N, V);
-    constexpr int T = N / R;
-    constexpr int TPC = rows_per_cta(N, V);
-    constexpr int STAGES = MUFFT_TMA_STAGES;
-    constexpr int LAND = rows_land_bytes(N, IN_MODE);
-    MUFFT_DYNAMIC_SMEM(smem_raw);
-
-    const int tid = threadIdx.x;
-    const int slot = tid / T;
-    const int t = tid - slot * T;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw) + slot * STAGES;
-    unsigned char *land = smem_raw + 128 + (size_t)slot * STAGES * LAND;
-    cpx *sm = reinterpret_cast<cpx *>(smem_raw + 128 + (size_t)TPC * STAGES * LAND) + slot * rows_smem_elems(N, V);
-    const cpx *__restrict__ tw = static_cast<const cpx *>(a.tw);
-    const cpx *__restrict__ rtw = static_cast<const cpx *>(a.rtw);
-    const size_t groups = (a.batch + TPC - 1) / TPC;
-
-    if (t == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES; s++) mbar_init(bars + s, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    engine_sync<T, TPC>(slot);
-
-    auto issue = [&](int stage, size_t g) {
-        const size_t b = g * TPC + slot;
-        if (g < groups && b < a.batch) {
-            mbar_expect_tx(bars + stage, LAND);
-            bulk_load(land + stage * LAND, static_cast<const cpx *>(a.in) + b * a.in_stride, LAND, bars + stage);
-        }
-    };
-    if (t == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES; s++) issue(s, (size_t)blockIdx.x + (size_t)s * gridDim.x);
-    }
-
-    int stage = 0;
-    uint32_t parity = 0;
-    for (size_t g = blockIdx.x; g < groups; g += gridDim.x) {
-        size_t b = g * TPC + slot;
-        const bool active = b < a.batch;
-        if (!active) b = a.batch - 1;
-        const cpx *__restrict__ in2 = static_cast<const cpx *>(a.in2) + b * a.in2_stride;
-
-        cpx v[R];
-        if (active) mbar_wait(bars + stage, parity);
-        rows_load<N, IN_MODE, V>(v, reinterpret_cast<const cpx *>(land + stage * LAND), in2, rtw, a.norm, t);
-        // Order this thread's generic-proxy reads of the landing buffer before the async-proxy
-        // (bulk copy) write that refills it: without the fence a queued LDS can still be reading
-        // when the next copy lands (seen as rare wrong transforms in long persistent loops).
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        // every thread of the transform has its inputs in registers: the landing buffer can be
-        // refilled, and the exchange area is free of the previous group's readers
-        engine_sync<T, TPC>(slot);
-        if (t == 0) issue(stage, g + (size_t)STAGES * gridDim.x);
-
-        engine_run<N, DIR, 1, T, TPC, 0, V, rows_packed(N, IN_MODE, OUT_MODE)>(v, sm, tw, t, slot);
-        cpx *__restrict__ out = static_cast<cpx *>(a.out) + b * a.out_stride;
-        rows_store<N, OUT_MODE, T, TPC, V>(v, out, sm, rtw, t, slot, active);
-
-        if (++stage == STAGES) {
-            stage = 0;
-            parity ^= 1;
-        }
-    }
-}
-
-#endif // MUFFT_EMU
 
 } // namespace mufft

@@ -1,5 +1,6 @@
 // Compiled with -DROWST_N=<n2>; exposes rowst_launch_<n2>(args, stream) to dispatch.cu.
 #include "rowst_kernel.cuh"
+#include "launch_util.cuh"
 
 #ifndef ROWST_N
 #error "compile with -DROWST_N=<256|512|1024>"
@@ -12,12 +13,11 @@ namespace mufft {
 template <int DIR>
 static cudaError_t launch_dir(const mcu_rowst_args &a, cudaStream_t stream)
 {
-    static bool configured = false;
+    static launch_cfg cfg; // per instantiation, per device inside
     auto kernel = fft_rowst_kernel<ROWST_N, DIR>;
-    if (!configured) {
-        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rowst_smem_bytes(ROWST_N));
+    {
+        const cudaError_t err = launch_prepare(cfg, kernel, rowst_smem_bytes(ROWST_N), 0, nullptr);
         if (err != cudaSuccess) return err;
-        configured = true;
     }
     if (a.batch == 0) return cudaSuccess;
     dim3 grid(a.n1 / MUFFT_ROWST_TILE, (unsigned)(a.batch > 65535 ? 65535 : a.batch));

@@ -36,11 +36,13 @@ EMU_FOR_COLS_SIZES(X)
 int emu_launch_rowst_256(const mcu_rowst_args *);
 int emu_launch_rowst_512(const mcu_rowst_args *);
 int emu_launch_rowst_1024(const mcu_rowst_args *);
-int emu_launch_rows_cluster_32768(const mcu_rows_args *);
-int emu_launch_rows_cluster_65536(const mcu_rows_args *);
+#define EMU_FOR_FOURSTEP_SHAPES(X) X(16, 1024) X(32, 1024) X(32, 2048)
+#define X(n1, n2) int emu_launch_long_##n1##x##n2(const mcu_long_args *, unsigned);
+EMU_FOR_FOURSTEP_SHAPES(X)
+#undef X
 // fused 2D shapes compiled for the emulation (tests/emu/Makefile: F2D_SHAPES)
 #define EMU_FOR_F2D_SHAPES(X) X(256, 256) X(512, 256) X(2048, 256)
-#define X(nx, ny) int emu_launch_2d_##nx##x##ny(const mcu_2d_args *, unsigned);
+#define X(nx, ny) int emu_launch_2d_##nx##x##ny(const mcu_2d_args *, unsigned); int emu_2d_rows_variant_##nx##x##ny(int);
 EMU_FOR_F2D_SHAPES(X)
 #undef X
 }
@@ -108,7 +110,6 @@ int mcu_pointer_kind(const void *ptr)
 int mcu_stream_create(void **stream) { *stream = malloc(1); return 0; }
 int mcu_stream_destroy(void *stream) { free(stream); return 0; }
 int mcu_stream_sync(void *) { return 0; }
-int mcu_stream_sync_spin(void *) { return 0; }
 int mcu_event_create(void **event) { *event = malloc(1); return 0; }
 int mcu_event_destroy(void *event) { free(event); return 0; }
 int mcu_event_record(void *, void *) { return 0; }
@@ -146,11 +147,17 @@ int mcu_launch_rows(const mcu_rows_args *a, void *)
     default: return 1;
     }
 }
-int mcu_rows_cluster_supported(unsigned n) { return n == 32768 || n == 65536; }
-int mcu_launch_rows_cluster(const mcu_rows_args *a, void *)
+// single-launch four-step rows: 3 "resident" CTAs walk the batch
+static unsigned long_n1_of(unsigned n) { return n == 16384 ? 16 : (n == 32768 || n == 65536 ? 32 : 0); }
+unsigned mcu_long_n2(unsigned n) { return long_n1_of(n) ? n / long_n1_of(n) : 0; }
+unsigned mcu_long_ctas(unsigned n) { return long_n1_of(n) ? 3 : 0; }
+int mcu_launch_long(const mcu_long_args *a, void *)
 {
     g_launches++;
-    return a->n == 32768 ? emu_launch_rows_cluster_32768(a) : (a->n == 65536 ? emu_launch_rows_cluster_65536(a) : 1);
+#define X(a1, a2) if (a->n1 == a1 && a->n2 == a2) return emu_launch_long_##a1##x##a2(a, 3);
+    EMU_FOR_FOURSTEP_SHAPES(X)
+#undef X
+    return 1;
 }
 int mcu_launch_conv(const mcu_conv_args *a, void *)
 {
@@ -189,10 +196,15 @@ int mcu_2d_fused_supported(unsigned nx, unsigned ny)
 #undef X
     return 0;
 }
-int mcu_2d_fused_real_supported(unsigned nx, unsigned ny, int out_mode)
+int mcu_2d_rows_variant(unsigned nx, int kind)
 {
-    return (out_mode == MCU_OUT_R2C || out_mode == MCU_OUT_R2C_FULL) && mcu_2d_fused_supported(nx, ny);
+#define X(px, py) if (nx == px) return emu_2d_rows_variant_##px##x##py(kind);
+    EMU_FOR_F2D_SHAPES(X)
+#undef X
+    return 0;
 }
+unsigned mcu_2d_default_lag(unsigned, unsigned, int) { return 1; }
+size_t mcu_2d_mid_elems(unsigned nx, unsigned ny) { return ((size_t)nx + 2) * ny; }
 int mcu_launch_2d_fused(const mcu_2d_args *a, void *)
 {
     g_launches++;

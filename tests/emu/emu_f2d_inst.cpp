@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE ONLY: the fused 2D kernel of mufft_b200/csrc/fft2d_kernel.cuh compiled for the
 // CPU emulation at one image shape (-DEMU_NX=<nx> -DEMU_NY=<ny>).  `ctas` CTAs run concurrently
-// (all resident, as the persistent launch on the GPU), so the ticket / rows-done protocol between
+// (all resident, as the persistent launch on the GPU), so the ticket / tiles-done protocol between
 // CTAs is exercised for real.
 #include "fft2d_kernel.cuh"
 
@@ -8,82 +8,33 @@ using namespace mufft;
 #define EMU_CAT_(a, b, c, d) a##b##c##d
 #define EMU_CAT(a, b, c, d) EMU_CAT_(a, b, c, d)
 
-extern "C" int EMU_CAT(emu_2d_fused_, EMU_NX, x, EMU_NY)(int direction, void *out, const void *in, const void *tw_x, const void *tw_y,
-                                                        unsigned *counters, size_t batch, unsigned lag, unsigned ctas, int lite)
+template <int DIR, int KIND>
+static int run_kind(const mcu_2d_args &a, unsigned ctas)
 {
     constexpr int NX = EMU_NX, NY = EMU_NY;
-    if (!f2d_supported(NX, NY)) return -3;
-    mcu_2d_args a;
-    memset(&a, 0, sizeof(a));
-    a.out = out; a.in = in; a.tw_x = tw_x; a.tw_y = tw_y; a.counters = counters;
-    a.out_image = (size_t)NX * NY; a.in_image = (size_t)NX * NY; a.batch = batch; a.nx = NX; a.ny = NY;
-    a.direction = direction; a.lag = lag;
     const emu::idx3 grid{ ctas, 1, 1 };
-    if (lite == 1) { // twiddle tables in shared memory + one-sided fences
-        if (direction < 0) emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY, true), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, -1, F2D_LITE>(a); });
-        else emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY, true), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, 1, F2D_LITE>(a); });
-    } else if (lite == 2) { // ... + derived twiddles
-        if (direction < 0) emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY, true), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, -1, F2D_LITE | F2D_DERIVE>(a); });
-        else emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY, true), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, 1, F2D_LITE | F2D_DERIVE>(a); });
-    } else if (lite == 4) { // smem tables + one-sided fences + tickets two ahead
-        if (direction < 0) emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY, true), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, -1, F2D_LITE | F2D_EARLY>(a); });
-        else emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY, true), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, 1, F2D_LITE | F2D_EARLY>(a); });
-    } else if (lite == 5) { // smem tables + one-sided fences, row and column tickets alternating
-        if (direction < 0) emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY, true), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, -1, F2D_LITE | F2D_INTERLEAVE>(a); });
-        else emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY, true), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, 1, F2D_LITE | F2D_INTERLEAVE>(a); });
-    } else if (lite == 6) { // derived twiddles from the global table, tickets alternating
-        if (direction < 0) emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, -1, F2D_ONE_SIDED | F2D_DERIVE | F2D_INTERLEAVE>(a); });
-        else emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, 1, F2D_ONE_SIDED | F2D_DERIVE | F2D_INTERLEAVE>(a); });
-    } else if (lite == 3) { // derived twiddles from the global table
-        if (direction < 0) emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, -1, F2D_ONE_SIDED | F2D_DERIVE>(a); });
-        else emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, 1, F2D_ONE_SIDED | F2D_DERIVE>(a); });
-    } else {
-        if (direction < 0) emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, -1>(a); });
-        else emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, 1>(a); });
-    }
+    emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY, KIND), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, DIR, KIND>(a); });
     return 0;
 }
 
-// Real images (forward R2C, half or full spectrum): EMU_NX = complex points per row transform (the rows
-// have 2 EMU_NX reals), output rows of pitch 2 EMU_NX bins.
-extern "C" int EMU_CAT(emu_2d_fused_real_, EMU_NX, x, EMU_NY)(int full, void *out, const void *in, const void *tw_x, const void *tw_y, const void *rtw,
-                                                             unsigned *counters, size_t batch, unsigned lag, unsigned ctas)
-{
-    constexpr int NX = EMU_NX, NY = EMU_NY;
-    mcu_2d_args a;
-    memset(&a, 0, sizeof(a));
-    a.out = out; a.in = in; a.tw_x = tw_x; a.tw_y = tw_y; a.rtw = rtw; a.counters = counters;
-    a.out_image = 2 * (size_t)NX * NY; a.in_image = (size_t)NX * NY; a.batch = batch; a.nx = NX; a.ny = NY;
-    a.direction = -1; a.lag = lag; a.out_mode = full ? MCU_OUT_R2C_FULL : MCU_OUT_R2C;
-    const emu::idx3 grid{ ctas, 1, 1 };
-    constexpr int FLAGS = F2D_ONE_SIDED | F2D_DERIVE;
-    if (full) {
-        if constexpr (f2d_real_supported(NX, NY, MCU_OUT_R2C_FULL)) {
-            emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY, false, f2d_rows_variant(NX, MCU_OUT_R2C_FULL)), ctas, 1,
-                        [&] { fft2d_fused_kernel<NX, NY, -1, FLAGS, MCU_OUT_R2C_FULL>(a); });
-            return 0;
-        }
-    } else {
-        if constexpr (f2d_real_supported(NX, NY, MCU_OUT_R2C)) {
-            emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY, false, f2d_rows_variant(NX, MCU_OUT_R2C)), ctas, 1,
-                        [&] { fft2d_fused_kernel<NX, NY, -1, FLAGS, MCU_OUT_R2C>(a); });
-            return 0;
-        }
-    }
-    return -3;
-}
-
-// struct-taking entry point for the emulated CUDA side (emu_abi.cpp): the flavour the product launcher would pick
+// struct-taking entry point (emu_abi.cpp and tests/test_emu.py): lag 0 = 1
 extern "C" int EMU_CAT(emu_launch_2d_, EMU_NX, x, EMU_NY)(const mcu_2d_args *a, unsigned ctas)
 {
     constexpr int NX = EMU_NX, NY = EMU_NY;
+    if (!f2d_supported(NX, NY)) return -3;
+    if (a->batch == 0) return 0;
     mcu_2d_args b = *a;
     if (b.lag == 0) b.lag = 1;
-    const emu::idx3 grid{ ctas, 1, 1 };
-    if (b.out_mode == MCU_OUT_R2C || b.out_mode == MCU_OUT_R2C_FULL)
-        return EMU_CAT(emu_2d_fused_real_, EMU_NX, x, EMU_NY)(b.out_mode == MCU_OUT_R2C_FULL, b.out, b.in, b.tw_x, b.tw_y, b.rtw, b.counters, b.batch, b.lag, ctas);
-    constexpr int FLAGS = F2D_ONE_SIDED | F2D_DERIVE;
-    if (b.direction < 0) emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, -1, FLAGS>(b); });
-    else emu::launch(grid, MUFFT_F2D_THREADS, f2d_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_fused_kernel<NX, NY, 1, FLAGS>(b); });
-    return 0;
+    switch (b.kind) {
+    case MCU_2D_C2C: return b.direction < 0 ? run_kind<-1, F2D_C2C>(b, ctas) : run_kind<1, F2D_C2C>(b, ctas);
+    case MCU_2D_R2C: return run_kind<-1, F2D_R2C>(b, ctas);
+    case MCU_2D_R2C_FULL: return run_kind<-1, F2D_R2C_FULL>(b, ctas);
+    case MCU_2D_C2R: {
+        const size_t lag_eff = b.lag < b.batch ? b.lag : b.batch;
+        if (b.mid == nullptr || b.ring == 0 || !(b.ring > lag_eff || b.ring >= b.batch)) return 1;
+        return run_kind<1, F2D_C2R>(b, ctas);
+    }
+    default: return 1;
+    }
 }
+extern "C" int EMU_CAT(emu_2d_rows_variant_, EMU_NX, x, EMU_NY)(int kind) { return f2d_rows_variant(EMU_NX, kind); }

@@ -1,7 +1,6 @@
 """Batched entry points of include/mufft_cuda.h against the oracle: device-resident, strided,
-pinned-host and pageable-host buffers.  Batches are large enough that the persistent prefetch
-kernel (rows_kernel.cuh: fft_rows_tma_kernel) runs several groups per CTA, and ragged enough that
-the last group has idle transform slots."""
+pinned-host and pageable-host buffers.  Batches are large enough that the persistent kernels run
+several tiles per CTA, and ragged enough that the last group of a row kernel has idle transform slots."""
 import ctypes
 import math
 
@@ -13,15 +12,12 @@ from cpu_libs import FLAG_FULL_R2C, FLAG_ZERO_PAD, rel_l2
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["direct", "prefetch"])
-def m(request):
-    """The library with the row kernels in direct-load or bulk-copy prefetch flavour."""
+@pytest.fixture(scope="module")
+def m():
     import mufft_b200
     if mufft_b200.mufft_cuda_device_count() < 1:
         pytest.fail("no CUDA device visible")
-    mufft_b200.mufft_cuda_set_prefetch(request.param == "prefetch")
-    yield mufft_b200
-    mufft_b200.mufft_cuda_set_prefetch(0)
+    return mufft_b200
 
 
 @pytest.fixture(scope="module")
@@ -290,20 +286,27 @@ def test_conv_fused_batch_host_memory(m, torch, oracle):
         assert rel_l2(out[i].view(np.complex64), want) <= 2 * tol(n)
 
 
-@pytest.mark.parametrize("nx,ny", [(64, 64), (256, 128), (256, 256), (512, 2048), (2048, 256), (1024, 1024), (128, 2048),
+SEPARATE_2D, TWO_KERNEL, GENERIC_PASSES, FOUR_STEP_16K = 1 << 20, 1 << 21, 1 << 22, 1 << 23  # mufft_cuda.h plan flags
+
+
+@pytest.mark.parametrize("nx,ny", [(64, 64), (256, 128), (256, 256), (512, 512), (512, 2048), (2048, 256), (1024, 1024), (128, 2048),
                                    (8192, 8), (16, 4096), (32, 16384), (16384, 32), (64, 8192)])
-@pytest.mark.parametrize("fused", [1, 0])
-def test_c2c_2d_batch_device(m, torch, oracle, nx, ny, fused):
-    """fused=1: one persistent kernel for the whole batch where the shape has one (256..2048 per
-    side); fused=0: row kernel + column kernel per group of images."""
-    m.mufft_cuda_set_fused_2d(fused)
+@pytest.mark.parametrize("separate", [0, 1])
+def test_c2c_2d_batch_device(m, torch, oracle, nx, ny, separate):
+    """Default: one persistent kernel for the whole batch where the shape has one (256..2048 per
+    side); MUFFT_CUDA_FLAG_SEPARATE_2D: row kernel + column kernel per group of images."""
     batch = max(3, min(40, (64 << 20) // (8 * nx * ny)))
     x = dev_random(torch, (batch, ny, nx, 2), nx + ny)
     y = torch.zeros_like(x)
+    fusable = all(256 <= v <= 2048 for v in (nx, ny))
     for direction in (-1, 1):
-        plan = m.mufft_create_plan_2d_c2c(nx, ny, direction, 0)
+        plan = m.mufft_create_plan_2d_c2c(nx, ny, direction, SEPARATE_2D if separate else 0)
         assert plan
+        assert bool(m.mufft_cuda_plan_2d_paths(plan) & 4) == (fusable and not separate)
+        m.mufft_cuda_launch_count(1)
         assert m.mufft_execute_plan_2d_batch(plan, y.data_ptr(), x.data_ptr(), batch) == 0, m.mufft_cuda_last_error()
+        if fusable and not separate:
+            assert m.mufft_cuda_launch_count(1) == 1, "the fused path is one launch for the whole batch"
         m.mufft_free_plan_2d(plan)
         xc = torch.view_as_complex(x)
         ref = torch.fft.fft2(xc) if direction < 0 else torch.fft.ifft2(xc, norm="forward")
@@ -314,36 +317,59 @@ def test_c2c_2d_batch_device(m, torch, oracle, nx, ny, fused):
         for i in (0, batch - 1):
             want = oracle.c2c_2d(xc[i].cpu().numpy(), direction)
             assert rel_l2(yc[i].cpu().numpy(), want) <= tol(nx * ny)
-    m.mufft_cuda_set_fused_2d(1)
 
 
-@pytest.mark.parametrize("nx,ny", [(256, 256), (512, 2048), (1024, 1024), (2048, 256)])
-@pytest.mark.parametrize("mode", [2, 3, 4, 5, 6, 7, 8])
-def test_c2c_2d_fused_flavours(m, torch, oracle, nx, ny, mode):
-    """Every fixed flavour of the fused 2D kernel (mufft_cuda_set_fused_2d 2..8: TMA-fed tiles, twiddle
-    tables in shared memory, one-sided fences, derived twiddles, plain); mode 1, the per-shape default,
-    is what test_c2c_2d_batch_device runs."""
-    m.mufft_cuda_set_fused_2d(mode)
-    try:
-        batch = max(5, min(40, (96 << 20) // (8 * nx * ny)))
-        x = dev_random(torch, (batch, ny, nx, 2), nx + ny + mode)
-        y = torch.zeros_like(x)
-        xc = torch.view_as_complex(x)
-        for direction in (-1, 1):
-            plan = m.mufft_create_plan_2d_c2c(nx, ny, direction, 0)
-            assert plan
-            m.mufft_cuda_launch_count(1)
-            assert m.mufft_execute_plan_2d_batch(plan, y.data_ptr(), x.data_ptr(), batch) == 0, m.mufft_cuda_last_error()
-            assert m.mufft_cuda_launch_count(1) == 1, "the fused path is one launch for the whole batch"
-            m.mufft_free_plan_2d(plan)
-            ref = torch.fft.fft2(xc) if direction < 0 else torch.fft.ifft2(xc, norm="forward")
-            yc = torch.view_as_complex(y)
-            err = (torch.linalg.vector_norm((yc - ref).reshape(batch, -1), dim=1) /
-                   torch.linalg.vector_norm(ref.reshape(batch, -1), dim=1)).max().item()
-            assert err <= tol(nx * ny)
-            assert rel_l2(yc[batch - 1].cpu().numpy(), oracle.c2c_2d(xc[batch - 1].cpu().numpy(), direction)) <= tol(nx * ny)
-    finally:
-        m.mufft_cuda_set_fused_2d(1)
+@pytest.mark.parametrize("nx,ny", [(512, 256), (1024, 1024), (2048, 512), (4096, 256), (64, 128), (8192, 64)])
+@pytest.mark.parametrize("flags", [0, FLAG_FULL_R2C, SEPARATE_2D])
+def test_r2c_2d_batch_device(m, torch, oracle, nx, ny, flags):
+    """2D R2C images of nx reals per row: the fused persistent kernel where the shape has one (rows with the resolve
+    epilogue straight into the output, columns in place: one launch), else / with SEPARATE_2D row kernel + column kernel."""
+    batch = max(3, min(24, (64 << 20) // (8 * nx * ny)))
+    g = torch.Generator(device="cuda")
+    g.manual_seed(nx + ny)
+    x = torch.rand((batch, ny, nx), dtype=torch.float32, device="cuda", generator=g) - 0.5
+    out = torch.zeros((batch, ny, nx, 2), dtype=torch.float32, device="cuda")
+    fused = all(256 <= v <= 2048 for v in (nx // 2, ny)) and not flags & SEPARATE_2D
+    plan = m.mufft_create_plan_2d_r2c(nx, ny, flags)
+    assert plan
+    m.mufft_cuda_launch_count(1)
+    assert m.mufft_execute_plan_2d_batch(plan, out.data_ptr(), x.data_ptr(), batch) == 0, m.mufft_cuda_last_error()
+    assert m.mufft_cuda_launch_count(1) == (1 if fused else 2)
+    m.mufft_free_plan_2d(plan)
+    width = nx if flags & FLAG_FULL_R2C else nx // 2 + 1
+    got = torch.view_as_complex(out)[:, :, :width]
+    ref = torch.fft.fft2(x)[:, :, :width]
+    err = (torch.linalg.vector_norm((got - ref).reshape(batch, -1), dim=1) / torch.linalg.vector_norm(ref.reshape(batch, -1), dim=1)).max().item()
+    assert err <= tol(nx * ny)
+    want = oracle.r2c_2d(x[batch - 1].cpu().numpy(), flags & FLAG_FULL_R2C)[:, :width]
+    assert rel_l2(got[batch - 1].cpu().numpy(), want) <= tol(nx * ny)
+
+
+@pytest.mark.parametrize("nx,ny,batch", [(512, 256, 41), (1024, 1024, 19), (2048, 512, 7), (4096, 256, 9), (1024, 1024, 1), (64, 128, 5), (8192, 64, 3)])
+@pytest.mark.parametrize("flags", [0, SEPARATE_2D])
+def test_c2r_2d_batch_device(m, torch, oracle, nx, ny, batch, flags):
+    """2D C2R images (spectrum rows of pitch nx complex, nx/2 + 1 carry data; dense real output): the fused kernel does
+    the columns first into the plan's ring of intermediates and the C2R rows out of it (ref fft.c:861-916) - batches
+    longer than the ring exercise the slot hand-over - else / with SEPARATE_2D column kernel + row kernel."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(nx + ny + batch)
+    real = torch.rand((batch, ny, nx), dtype=torch.float32, device="cuda", generator=g) - 0.5
+    spec = torch.full((batch, ny, nx), float("nan"), dtype=torch.complex64, device="cuda")  # the padding columns are never read
+    spec[:, :, : nx // 2 + 1] = torch.fft.rfft2(real.double()).to(torch.complex64)
+    out = torch.zeros((batch, ny, nx), dtype=torch.float32, device="cuda")
+    fused = all(256 <= v <= 2048 for v in (nx // 2, ny)) and not flags & SEPARATE_2D
+    plan = m.mufft_create_plan_2d_c2r(nx, ny, flags)
+    assert plan
+    for _ in range(2):  # twice: the ring and the counters are reused
+        m.mufft_cuda_launch_count(1)
+        assert m.mufft_execute_plan_2d_batch(plan, out.data_ptr(), torch.view_as_real(spec).data_ptr(), batch) == 0, m.mufft_cuda_last_error()
+        assert m.mufft_cuda_launch_count(1) == (1 if fused else 2)
+    m.mufft_free_plan_2d(plan)
+    want = real.double() * (nx * ny)
+    err = (torch.linalg.vector_norm((out.double() - want).reshape(batch, -1), dim=1) / torch.linalg.vector_norm(want.reshape(batch, -1), dim=1)).max().item()
+    assert err <= tol(nx * ny)
+    clean = torch.nan_to_num(torch.view_as_real(spec[batch - 1]), nan=0.0).cpu().numpy().view(np.complex64).reshape(ny, nx)
+    assert rel_l2(out[batch - 1].cpu().numpy(), oracle.c2r_2d(clean)) <= tol(nx * ny)
 
 
 @pytest.mark.parametrize("case", ["c2c2d-fused", "c2c2d-separate", "r2c2d", "c2r2d", "c2c-long"])
@@ -370,8 +396,7 @@ def test_staged_host_batches_that_share_plan_scratch(m, torch, oracle, case):
     nx = ny = 256
     batch = 500
     if case.startswith("c2c2d"):
-        m.mufft_cuda_set_fused_2d(1 if case == "c2c2d-fused" else 0)
-        plan = m.mufft_create_plan_2d_c2c(nx, ny, -1, 0)
+        plan = m.mufft_create_plan_2d_c2c(nx, ny, -1, 0 if case == "c2c2d-fused" else SEPARATE_2D)
         x = rng.random((batch, ny * nx * 2), np.float32) - np.float32(0.5)
         out = np.zeros_like(x)
     elif case == "r2c2d":
@@ -391,7 +416,6 @@ def test_staged_host_batches_that_share_plan_scratch(m, torch, oracle, case):
         od = torch.zeros(out.shape, dtype=torch.float32, device="cuda")
         assert m.mufft_execute_plan_2d_batch(plan, od.data_ptr(), xd.data_ptr(), batch) == 0
     finally:
-        m.mufft_cuda_set_fused_2d(1)
         m.mufft_free_plan_2d(plan)
     got, dev = out.reshape(batch, ny, -1), od.cpu().numpy().reshape(batch, ny, -1)
     if case == "r2c2d":  # only columns 0..Nx/2 of the pitch-Nx complex rows are defined
@@ -399,85 +423,158 @@ def test_staged_host_batches_that_share_plan_scratch(m, torch, oracle, case):
     assert np.array_equal(got, dev)
 
 
-@pytest.mark.parametrize("n", [16384, 65536, 1 << 18, 1 << 19, 1 << 20, 1 << 21, 1 << 22])
-@pytest.mark.parametrize("two_kernel", [1, 0])
-def test_large_n(m, torch, oracle, n, two_kernel):
-    """N above the single-kernel limit: two-kernel split (N = N1*N2) up to 2^21, generic radix
-    passes beyond and when the split is switched off; C2C both directions, zero pad, R2C and C2R."""
-    if two_kernel == 0 and n > (1 << 19):
+@pytest.mark.parametrize("n", [16384, 32768, 65536, 1 << 17, 1 << 18, 1 << 19, 1 << 20, 1 << 21, 1 << 22])
+@pytest.mark.parametrize("path", ["default", "two_kernel", "generic", "four_step_16k"])
+def test_large_n(m, torch, oracle, n, path):
+    """N above one CTA's reach.  Default: the single-launch four-step kernel (32768 / 65536 points, intermediate in L2),
+    the two-kernel split (N = N1*N2) up to 2^21, generic radix passes beyond; the plan flags force the fallbacks.
+    C2C both directions, zero pad, R2C and C2R of twice the length."""
+    if path == "generic" and n > (1 << 19):
         pytest.skip("generic passes are covered at the smaller lengths")
-    m.mufft_cuda_set_two_kernel(two_kernel)
-    # 16384 points fit ONE kernel by default (tests above); here they take the paths of the longer lengths
-    m.mufft_cuda_set_onchip_limit(8192)
-    try:
-        batch = 3
-        x = dev_random(torch, (batch, 2 * n), n)
-        y = torch.zeros_like(x)
-        xc = torch.view_as_complex(x.view(batch, n, 2))
-        for direction in (-1, 1):
-            plan = m.mufft_create_plan_1d_c2c(n, direction, 0)
-            assert plan
-            assert m.mufft_execute_plan_1d_batch(plan, y.data_ptr(), x.data_ptr(), batch, 0, 0) == 0
-            m.mufft_free_plan_1d(plan)
-            ref = torch.fft.fft(xc, dim=1) if direction < 0 else torch.fft.ifft(xc, dim=1, norm="forward")
-            yc = torch.view_as_complex(y.view(batch, n, 2))
-            err = (torch.linalg.vector_norm(yc - ref, dim=1) / torch.linalg.vector_norm(ref, dim=1)).max().item()
-            assert err <= tol(n)
-            if n <= (1 << 20):
-                got = yc[batch - 1].cpu().numpy()
-                assert rel_l2(got, oracle.c2c(xc[batch - 1].cpu().numpy(), direction)) <= tol(n)
-        # zero-padded forward: the input rows really are N/2 long
-        xh = dev_random(torch, (batch, n), 7)
-        plan = m.mufft_create_plan_1d_c2c(n, -1, FLAG_ZERO_PAD)
-        assert m.mufft_execute_plan_1d_batch(plan, y.data_ptr(), xh.data_ptr(), batch, 0, 0) == 0
+    if path == "two_kernel" and n > (1 << 21):
+        pytest.skip("no two-kernel split beyond 2^21")
+    if path == "four_step_16k" and n != 16384:
+        pytest.skip("the flag only concerns 16384 points")
+    flags = {"default": 0, "two_kernel": TWO_KERNEL, "generic": GENERIC_PASSES, "four_step_16k": FOUR_STEP_16K}[path]
+    one_launch = (path == "default" and n <= 65536) or path == "four_step_16k"
+    batch = 3 if n > 65536 else 301  # more transforms than resident CTAs: the four-step kernel reuses its scratch slots
+    x = dev_random(torch, (batch, 2 * n), n)
+    y = torch.zeros_like(x)
+    xc = torch.view_as_complex(x.view(batch, n, 2))
+    for direction in (-1, 1):
+        plan = m.mufft_create_plan_1d_c2c(n, direction, flags)
+        assert plan
+        assert m.mufft_cuda_plan_1d_uses_engine(plan) == (1 if one_launch else 0)
+        m.mufft_cuda_launch_count(1)
+        assert m.mufft_execute_plan_1d_batch(plan, y.data_ptr(), x.data_ptr(), batch, 0, 0) == 0, m.mufft_cuda_last_error()
+        if one_launch:
+            assert m.mufft_cuda_launch_count(1) == 1
         m.mufft_free_plan_1d(plan)
-        xp = torch.zeros((batch, n), dtype=torch.complex64, device="cuda")
-        xp[:, : n // 2] = torch.view_as_complex(xh.view(batch, n // 2, 2))
-        ref = torch.fft.fft(xp, dim=1)
+        ref = torch.fft.fft(xc, dim=1) if direction < 0 else torch.fft.ifft(xc, dim=1, norm="forward")
         yc = torch.view_as_complex(y.view(batch, n, 2))
-        assert (torch.linalg.vector_norm(yc - ref) / torch.linalg.vector_norm(ref)).item() <= tol(n)
-        # R2C + C2R of real length 2N (complex engine length N)
-        r = dev_random(torch, (batch, 2 * n), 9)
-        spec = torch.zeros((batch, 2 * (n + 1)), dtype=torch.float32, device="cuda")
-        fwd = m.mufft_create_plan_1d_r2c(2 * n, 0)
-        assert m.mufft_execute_plan_1d_batch(fwd, spec.data_ptr(), r.data_ptr(), batch, 0, 0) == 0
-        m.mufft_free_plan_1d(fwd)
-        ref = torch.fft.rfft(r, dim=1)
-        sc = torch.view_as_complex(spec.view(batch, n + 1, 2))
-        assert (torch.linalg.vector_norm(sc - ref) / torch.linalg.vector_norm(ref)).item() <= tol(2 * n)
-        back = torch.zeros_like(r)
-        inv = m.mufft_create_plan_1d_c2r(2 * n, 0)
-        assert m.mufft_execute_plan_1d_batch(inv, back.data_ptr(), spec.data_ptr(), batch, 0, 0) == 0
-        m.mufft_free_plan_1d(inv)
-        assert (torch.linalg.vector_norm(back / (2 * n) - r) / torch.linalg.vector_norm(r)).item() <= 2 * tol(2 * n)
-    finally:
-        m.mufft_cuda_set_two_kernel(1)
-        m.mufft_cuda_set_onchip_limit(16384)
+        err = (torch.linalg.vector_norm(yc - ref, dim=1) / torch.linalg.vector_norm(ref, dim=1)).max().item()
+        assert err <= tol(n)
+        if n <= (1 << 20):
+            got = yc[batch - 1].cpu().numpy()
+            assert rel_l2(got, oracle.c2c(xc[batch - 1].cpu().numpy(), direction)) <= tol(n)
+    # zero-padded forward: the input rows really are N/2 long
+    xh = dev_random(torch, (batch, n), 7)
+    plan = m.mufft_create_plan_1d_c2c(n, -1, FLAG_ZERO_PAD | flags)
+    assert m.mufft_execute_plan_1d_batch(plan, y.data_ptr(), xh.data_ptr(), batch, 0, 0) == 0
+    m.mufft_free_plan_1d(plan)
+    xp = torch.zeros((batch, n), dtype=torch.complex64, device="cuda")
+    xp[:, : n // 2] = torch.view_as_complex(xh.view(batch, n // 2, 2))
+    ref = torch.fft.fft(xp, dim=1)
+    yc = torch.view_as_complex(y.view(batch, n, 2))
+    assert (torch.linalg.vector_norm(yc - ref) / torch.linalg.vector_norm(ref)).item() <= tol(n)
+    # R2C + C2R of real length 2N (complex engine length N)
+    batch = min(batch, 37)
+    r = dev_random(torch, (batch, 2 * n), 9)
+    spec = torch.zeros((batch, 2 * (n + 1)), dtype=torch.float32, device="cuda")
+    fwd = m.mufft_create_plan_1d_r2c(2 * n, flags)
+    assert m.mufft_execute_plan_1d_batch(fwd, spec.data_ptr(), r.data_ptr(), batch, 0, 0) == 0
+    m.mufft_free_plan_1d(fwd)
+    ref = torch.fft.rfft(r, dim=1)
+    sc = torch.view_as_complex(spec.view(batch, n + 1, 2))
+    assert (torch.linalg.vector_norm(sc - ref) / torch.linalg.vector_norm(ref)).item() <= tol(2 * n)
+    back = torch.zeros_like(r)
+    inv = m.mufft_create_plan_1d_c2r(2 * n, flags)
+    assert m.mufft_execute_plan_1d_batch(inv, back.data_ptr(), spec.data_ptr(), batch, 0, 0) == 0
+    m.mufft_free_plan_1d(inv)
+    assert (torch.linalg.vector_norm(back / (2 * n) - r) / torch.linalg.vector_norm(r)).item() <= 2 * tol(2 * n)
 
 
-def test_onchip_limit_knob(m, torch):
-    """mufft_cuda_set_onchip_limit: 16384-point plans run in one kernel by default and on the two-kernel
-    split when the limit is lowered; both give the same transform."""
+def test_plans_with_different_path_flags_run_side_by_side(m, torch):
+    """There is no process-global switch: a 16384-point plan on the engine, one on the four-step kernel and one on the
+    two-kernel split coexist and give the same transform."""
     n, batch = 16384, 37
     x = dev_random(torch, (batch, 2 * n), 3)
+    plans = [(m.mufft_create_plan_1d_c2c(n, -1, f), launches) for f, launches in ((0, 1), (FOUR_STEP_16K, 1), (TWO_KERNEL, 2))]
     outs = []
-    try:
-        for limit, engine in ((16384, 1), (8192, 0), (12345, 0), (1 << 20, 1)):
-            m.mufft_cuda_set_onchip_limit(limit)
-            assert m.mufft_cuda_get_onchip_limit() == (16384 if engine else 8192)
-            plan = m.mufft_create_plan_1d_c2c(n, -1, 0)
-            assert m.mufft_cuda_plan_1d_uses_engine(plan) == engine
-            y = torch.zeros_like(x)
-            m.mufft_cuda_launch_count(1)
-            assert m.mufft_execute_plan_1d_batch(plan, y.data_ptr(), x.data_ptr(), batch, 0, 0) == 0
-            assert m.mufft_cuda_launch_count(1) == (1 if engine else 2)
-            m.mufft_free_plan_1d(plan)
-            outs.append(torch.view_as_complex(y.view(batch, n, 2)))
-    finally:
-        m.mufft_cuda_set_onchip_limit(16384)
+    for plan, launches in plans + plans[::-1]:
+        y = torch.zeros_like(x)
+        m.mufft_cuda_launch_count(1)
+        assert m.mufft_execute_plan_1d_batch(plan, y.data_ptr(), x.data_ptr(), batch, 0, 0) == 0
+        assert m.mufft_cuda_launch_count(1) == launches
+        outs.append(torch.view_as_complex(y.view(batch, n, 2)))
+    for plan, _ in plans:
+        m.mufft_free_plan_1d(plan)
     ref = torch.fft.fft(torch.view_as_complex(x.view(batch, n, 2)), dim=1)
     for y in outs:
         assert (torch.linalg.vector_norm(y - ref) / torch.linalg.vector_norm(ref)).item() <= tol(n)
+
+
+@pytest.mark.parametrize("where", ["pageable", "managed", "device"])
+def test_buffers_with_4_byte_alignment_are_staged(m, torch, oracle, where):
+    """The real side of R2C / C2R is a float array, which C aligns to 4 bytes only (the reference's
+    scalar path takes it).  The kernels move 8-byte values, so such a buffer is never used in place:
+    it takes the staged path whatever memory it lives in (same check on the emulated host layer:
+    tests/test_hostemu.py)."""
+    n, batch = 4096, 37
+    r = np.random.default_rng(11).random((batch, n), np.float32) - np.float32(0.5)
+    out_floats = batch * (n // 2 + 1) * 2
+    if where == "pageable":
+        raw_in = np.zeros(batch * n + 16, np.float32)
+        raw_out = np.zeros(out_floats + 16, np.float32)
+        base_in, base_out = raw_in.ctypes.data, raw_out.ctypes.data
+    elif where == "managed":
+        base_in, base_out = m.mufft_alloc((batch * n + 16) * 4), m.mufft_alloc((out_floats + 16) * 4)
+        raw_in = np.ctypeslib.as_array((ctypes.c_float * (batch * n + 16)).from_address(base_in))
+        raw_out = np.ctypeslib.as_array((ctypes.c_float * (out_floats + 16)).from_address(base_out))
+    else:
+        t_in = torch.zeros(batch * n + 16, dtype=torch.float32, device="cuda")
+        t_out = torch.zeros(out_floats + 16, dtype=torch.float32, device="cuda")
+        base_in, base_out = t_in.data_ptr(), t_out.data_ptr()
+    o_in = ((-base_in) % 8) // 4 + 1   # in floats: the address is 4 mod 8
+    o_out = ((-base_out) % 8) // 4 + 1
+    if where == "device":
+        t_in[o_in:o_in + batch * n] = torch.from_numpy(r.ravel()).cuda()
+        torch.cuda.synchronize()
+    else:
+        raw_in[o_in:o_in + batch * n] = r.ravel()
+    plan = m.mufft_create_plan_1d_r2c(n, 0)
+    assert m.mufft_execute_plan_1d_batch(plan, base_out + 4 * o_out, base_in + 4 * o_in, batch, 0, 0) == 0, m.mufft_cuda_last_error()
+    assert m.mufft_execute_plan_1d_batch_async(plan, base_out + 4 * o_out, base_in + 4 * o_in, batch, 0, 0) != 0  # cannot stage
+    m.mufft_free_plan_1d(plan)
+    if where == "device":
+        got = t_out[o_out:o_out + out_floats].cpu().numpy()
+    else:
+        got = raw_out[o_out:o_out + out_floats].copy()
+    got = got.view(np.complex64).reshape(batch, n // 2 + 1)
+    for i in (0, 1, batch // 2, batch - 1):
+        assert rel_l2(got[i], oracle.r2c(r[i])) <= tol(n)
+    if where == "managed":
+        m.mufft_free(base_in)
+        m.mufft_free(base_out)
+
+
+def test_second_device_after_the_first(m, torch):
+    """Function attributes (the opt-in to more than 48 KB of shared memory) are per device: kernels that were first
+    launched on device 0 must also run on device 1 of the same process (skipped with one GPU)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    results = []
+    try:
+        for dev in (0, 1):
+            assert m.mufft_cuda_set_device(dev) == 0
+            with torch.cuda.device(dev):
+                x = torch.rand((5, 2 * 8192), dtype=torch.float32, device=f"cuda:{dev}") - 0.5
+                y = torch.zeros_like(x)
+                plan = m.mufft_create_plan_1d_c2c(8192, -1, 0)
+                assert m.mufft_execute_plan_1d_batch(plan, y.data_ptr(), x.data_ptr(), 5, 0, 0) == 0, m.mufft_cuda_last_error()
+                m.mufft_free_plan_1d(plan)
+                ref = torch.fft.fft(torch.view_as_complex(x.view(5, 8192, 2)), dim=1)
+                results.append((torch.linalg.vector_norm(torch.view_as_complex(y.view(5, 8192, 2)) - ref) / torch.linalg.vector_norm(ref)).item())
+                img = torch.rand((3, 1024, 1024, 2), dtype=torch.float32, device=f"cuda:{dev}") - 0.5
+                o2 = torch.zeros_like(img)
+                p2 = m.mufft_create_plan_2d_c2c(1024, 1024, -1, 0)
+                assert m.mufft_execute_plan_2d_batch(p2, o2.data_ptr(), img.data_ptr(), 3) == 0, m.mufft_cuda_last_error()
+                m.mufft_free_plan_2d(p2)
+                ref2 = torch.fft.fft2(torch.view_as_complex(img))
+                results.append((torch.linalg.vector_norm(torch.view_as_complex(o2) - ref2) / torch.linalg.vector_norm(ref2)).item())
+    finally:
+        m.mufft_cuda_set_device(0)
+    assert max(results) <= tol(1024 * 1024)
 
 
 def test_linearity_and_parseval_at_full_size(m, torch):

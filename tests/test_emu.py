@@ -32,7 +32,7 @@ def emu():
 @pytest.fixture(scope="module", params=["table", "derived"])
 def emu_rows(request, emu):
     """The row kernels twice: twiddles from the table (product default) and with -DMUFFT_TW_ALL=2, every
-    kernel deriving all but the power-of-two twiddles (the A/B build of tools/ab_r2.txt)."""
+    kernel deriving all but the power-of-two twiddles (an A/B build of tools/ab_build.sh)."""
     if request.param == "table":
         return emu
     subprocess.run(["make", "-s", "-C", EMU_DIR, "-j", str(min(8, os.cpu_count() or 1)), "BUILD=_build_derived", "EXTRA=-DMUFFT_TW_ALL=2"], check=True)
@@ -269,122 +269,74 @@ def test_rows_spectral_multiply(emu_rows, host, n):
         assert cpu_libs.rel_l2(got[b], want[b]) <= tol(n)
 
 
-@pytest.mark.parametrize("lite", [0, 1, 2, 3, 4, 5, 6])
-@pytest.mark.parametrize("nx,ny,ctas", [(256, 256, 1), (256, 256, 3), (512, 256, 2), (2048, 256, 2)])  # 2048: rows on named barriers
-@pytest.mark.parametrize("direction", [-1, 1])
-def test_fused_2d(emu, host, oracle, nx, ny, ctas, direction, lite):
-    """The persistent fused 2D kernel with CTAs really running side by side: row tickets, lagged column
-    tickets, the rows-done counters and the deferred release (fft2d_kernel.cuh); lite 1 = twiddle tables
-    in shared memory (two tables when the sides differ) and one-sided fences, 2 = that with derived
-    twiddles, 3 = derived twiddles from the global table, 4 = 1 with tickets drawn two tiles ahead, 5 / 6 = 1 / 3
-    with row and column tickets alternating inside a round."""
-    batch = 3
-    fn = getattr(emu, f"emu_2d_fused_{nx}x{ny}")
-    fn.restype = C.c_int
-    fn.argtypes = [C.c_int, vp, vp, vp, vp, vp, sz, C.c_uint, C.c_uint, C.c_int]
-    rng = np.random.default_rng(11 + ctas)
-    x = crnd(rng, batch, ny, nx)
-    out = np.full((batch, ny, nx), np.nan, np.complex64)
-    counters = np.zeros(1 + batch, np.uint32)
-    assert fn(direction, out.ctypes.data, x.ctypes.data, engine_table(host, nx, direction).ctypes.data,
-              engine_table(host, ny, direction).ctypes.data, counters.ctypes.data, batch, 1, ctas, lite) == 0
-    for b in range(batch):
-        assert cpu_libs.rel_l2(out[b], oracle.c2c_2d(x[b], direction)) <= tol(nx * ny)
-    assert list(counters[1:]) == [ny] * batch
+class PeerDest(C.Structure):  # abi.h: mcu_peer_dest
+    _fields_ = [("base", vp * 16), ("row0", sz), ("pitch", sz), ("shift", C.c_uint), ("last", C.c_uint), ("pitch_last", sz)]
+
+
+class Args2D(C.Structure):  # abi.h: mcu_2d_args
+    _fields_ = [("out", vp), ("in_", vp), ("tw_x", vp), ("tw_y", vp), ("rtw", vp), ("kind", C.c_int), ("counters", vp), ("mid", vp),
+                ("ring", C.c_uint), ("out_image", sz), ("in_image", sz), ("batch", sz), ("nx", C.c_uint), ("ny", C.c_uint),
+                ("direction", C.c_int), ("lag", C.c_uint)]
+
+
+class ArgsLong(C.Structure):  # abi.h: mcu_long_args
+    _fields_ = [("out", vp), ("in_", vp), ("tw", vp), ("roots", vp), ("scratch", vp), ("scratch_slots", sz), ("out_batch", sz),
+                ("in_batch", sz), ("batch", sz), ("n", C.c_uint), ("n1", C.c_uint), ("n2", C.c_uint), ("direction", C.c_int),
+                ("in_mode", C.c_int), ("to_peers", C.c_int), ("peers", PeerDest)]
+
+
+KIND_C2C, KIND_R2C, KIND_R2C_FULL, KIND_C2R = 0, 1, 2, 3
+
+
+def fused_2d(emu, nx, ny, ctas, **kw):
+    fn = getattr(emu, f"emu_launch_2d_{nx}x{ny}")
+    fn.restype, fn.argtypes = C.c_int, [C.POINTER(Args2D), C.c_uint]
+    a = Args2D(nx=nx, ny=ny, **kw)
+    return fn(C.byref(a), ctas)
 
 
 @pytest.mark.parametrize("nx,ny,batch,ctas,lag", [
     (256, 256, 3, 1, 1),    # one CTA walks every ticket alone
-    (256, 256, 4, 3, 1),    # CTAs side by side, column tiles right behind their rows (deferred-copy path gets exercised)
+    (256, 256, 4, 3, 1),    # CTAs side by side, column tiles right behind their rows (the deferred release gets exercised)
     (256, 256, 2, 5, 2),    # lag >= batch: all rows first
-    (512, 256, 2, 2, 1),    # rectangular: different row / column tile shapes
-    (2048, 256, 2, 2, 1),   # two warps per row: the plane-by-plane exchange on named barriers; 128-byte tensor boxes
-    (1024, 1024, 2, 2, 1),  # the BASELINE configs[3] image shape: 64 KiB tiles, four tensor boxes per column tile
+    (512, 256, 3, 2, 1),    # rectangular: different row / column tile shapes, two twiddle tables
+    (2048, 256, 3, 2, 1),   # two warps per row: rows on named barriers
 ])
 @pytest.mark.parametrize("direction", [-1, 1])
-@pytest.mark.parametrize("lite", [0, 1])
-def test_fused_2d_tma(emu, host, oracle, nx, ny, batch, ctas, lag, direction, lite):
-    """fft2d_tma_kernel.cuh: tiles land in shared memory through (emulated) bulk copies one tile ahead
-    of the butterflies, exchanges run plane by plane in a half-size area."""
-    if nx == 1024 and direction == 1:
-        pytest.skip("one direction is enough at the large shape")
-    fn = getattr(emu, f"emu_2d_tma_{nx}x{ny}")
-    fn.restype = C.c_int
-    fn.argtypes = [C.c_int, vp, vp, vp, vp, vp, sz, C.c_uint, C.c_uint, C.c_int]
-    rng = np.random.default_rng(nx + ny + batch + ctas)
+def test_fused_2d(emu, host, oracle, nx, ny, batch, ctas, lag, direction):
+    """The persistent fused 2D kernel with CTAs really running side by side: producer (row) tickets, lagged
+    consumer (column) tickets, the tiles-done counters and the deferred release (fft2d_kernel.cuh), in the
+    flavour the product build uses for the shape."""
+    rng = np.random.default_rng(11 + ctas)
     x = crnd(rng, batch, ny, nx)
     out = np.full((batch, ny, nx), np.nan, np.complex64)
-    counters = np.zeros(1 + batch, np.uint32)
-    assert fn(direction, out.ctypes.data, x.ctypes.data, engine_table(host, nx, direction).ctypes.data,
-              engine_table(host, ny, direction).ctypes.data, counters.ctypes.data, batch, lag, ctas, lite) == 0
-    want = np.fft.fft2(x.astype(np.complex128)) if direction < 0 else np.fft.ifft2(x.astype(np.complex128), norm="forward")
+    counters = np.zeros(1 + 2 * batch, np.uint32)
+    twx, twy = engine_table(host, nx, direction), engine_table(host, ny, direction)
+    assert fused_2d(emu, nx, ny, ctas, out=out.ctypes.data, in_=x.ctypes.data, tw_x=twx.ctypes.data, tw_y=twy.ctypes.data,
+                    kind=KIND_C2C, counters=counters.ctypes.data, out_image=nx * ny, in_image=nx * ny, batch=batch,
+                    direction=direction, lag=lag) == 0
     for b in range(batch):
-        assert cpu_libs.rel_l2(out[b], want[b]) <= tol(nx * ny)
-    assert cpu_libs.rel_l2(out[0], oracle.c2c_2d(x[0], direction)) <= tol(nx * ny)
-    assert list(counters[1:]) == [ny] * batch
-
-
-@pytest.mark.parametrize("n", [32768, 65536])
-@pytest.mark.parametrize("case", ["fwd", "inv", "zero_pad", "peers"])
-@pytest.mark.parametrize("flavour", [0, 1])
-def test_rows_on_a_cluster(emu, host, oracle, n, case, flavour):
-    """rowsc_kernel.cuh: one transform per cluster of 2 (32768) or 4 (65536) CTAs, exchange through
-    distributed shared memory; three transforms over two clusters, so that the per-cluster loop and its
-    barriers between consecutive transforms are exercised too.  flavour 1 = st.async remote stores counted on
-    an mbarrier of the receiving CTA instead of release / acquire cluster barriers."""
-    fn = getattr(emu, f"emu_rows_cluster_{n}")
-    fn.restype = C.c_int
-    fn.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, vp, sz, sz, sz, C.c_uint, C.c_int, C.POINTER(C.c_void_p), C.c_uint, C.c_uint, sz, sz]
-    direction = 1 if case == "inv" else -1
-    batch, clusters = 3, 2
-    rng = np.random.default_rng(n + len(case))
-    tw = engine_table(host, n, direction)
-    no_peers = (C.c_void_p * 1)(None)
-    if case == "zero_pad":
-        x = crnd(rng, batch, n // 2)
-        out = np.full((batch, n), np.nan, np.complex64)
-        assert fn(direction, IN_HALF, OUT_COMPLEX, out.ctypes.data, x.ctypes.data, tw.ctypes.data, n, n // 2, batch, clusters, flavour, no_peers, 0, 0, 0, 0) == 0
-        xp = np.zeros((batch, n), np.complex128)
-        xp[:, : n // 2] = x
-        want = np.fft.fft(xp, axis=1)
-    else:
-        x = crnd(rng, batch, n)
-        want = np.fft.fft(x.astype(np.complex128), axis=1) if direction < 0 else np.fft.ifft(x.astype(np.complex128), axis=1, norm="forward")
-        if case == "peers":
-            peers, row0, rows_total = 8, 1, 5
-            width = n // peers
-            slabs = [np.full((rows_total, width), np.nan, np.complex64) for _ in range(peers)]
-            bases = (C.c_void_p * peers)(*[s_.ctypes.data for s_ in slabs])
-            assert fn(direction, IN_COMPLEX, 3, None, x.ctypes.data, tw.ctypes.data, 0, n, batch, clusters, flavour, bases, peers, int(math.log2(width)), row0, width) == 0
-            out = np.concatenate([s_[row0:row0 + batch] for s_ in slabs], axis=1)
-            assert all(np.all(np.isnan(s_[:row0].real)) and np.all(np.isnan(s_[row0 + batch:].real)) for s_ in slabs)
-        else:
-            out = np.full((batch, n), np.nan, np.complex64)
-            assert fn(direction, IN_COMPLEX, OUT_COMPLEX, out.ctypes.data, x.ctypes.data, tw.ctypes.data, n, n, batch, clusters, flavour, no_peers, 0, 0, 0, 0) == 0
-    for b in range(batch):
-        assert cpu_libs.rel_l2(out[b], want[b]) <= tol(n)
-    if case in ("fwd", "inv"):
-        assert cpu_libs.rel_l2(out[0], oracle.c2c(x[0], direction)) <= tol(n)
+        assert cpu_libs.rel_l2(out[b], oracle.c2c_2d(x[b], direction)) <= tol(nx * ny)
+    assert list(counters[1:1 + batch]) == [ny // (256 // (nx // (32 if nx >= 1024 else 16)))] * batch  # producer tiles per image
 
 
 @pytest.mark.parametrize("nx,ny,ctas", [(256, 256, 1), (512, 256, 3), (2048, 256, 2)])
 @pytest.mark.parametrize("full", [0, 1])
 def test_fused_2d_real(emu, host, oracle, nx, ny, ctas, full):
     """Real images in the fused kernel: row tiles run the R2C row transform (engine of nx complex points + the
-    resolve epilogue; 512 and 2048 use the mirrored-last-pass shape) into rows of pitch 2 nx bins, column
+    resolve epilogue; 512 uses the mirrored-last-pass shape) into rows of pitch 2 nx bins, column
     tiles transform the nx + 1 (2 nx with FULL_R2C) columns that carry data, the last one partly masked."""
-    fn = getattr(emu, f"emu_2d_fused_real_{nx}x{ny}")
-    fn.restype = C.c_int
-    fn.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, sz, C.c_uint, C.c_uint]
     batch = 3
     rng = np.random.default_rng(nx + ny + full)
     x = rnd(rng, batch, ny, 2 * nx)
     out = np.full((batch, ny, 2 * nx), np.nan + 1j * np.nan, np.complex64)
-    counters = np.zeros(1 + batch, np.uint32)
-    mode = OUT_R2C_FULL if full else OUT_R2C
-    variant = host.mcu_rows_variant(nx, IN_COMPLEX, mode)
-    twx, twy, rtw = engine_table(host, nx, -1, variant), engine_table(host, ny, -1), resolve_twiddles(-1, nx)
-    assert fn(full, out.ctypes.data, x.ctypes.data, twx.ctypes.data, twy.ctypes.data, rtw.ctypes.data, counters.ctypes.data, batch, 1, ctas) == 0
+    counters = np.zeros(1 + 2 * batch, np.uint32)
+    kind = KIND_R2C_FULL if full else KIND_R2C
+    vfn = getattr(emu, f"emu_2d_rows_variant_{nx}x{ny}")
+    vfn.restype, vfn.argtypes = C.c_int, [C.c_int]
+    twx, twy, rtw = engine_table(host, nx, -1, vfn(kind)), engine_table(host, ny, -1), resolve_twiddles(-1, nx)
+    assert fused_2d(emu, nx, ny, ctas, out=out.ctypes.data, in_=x.ctypes.data, tw_x=twx.ctypes.data, tw_y=twy.ctypes.data, rtw=rtw.ctypes.data,
+                    kind=kind, counters=counters.ctypes.data, out_image=2 * nx * ny, in_image=nx * ny, batch=batch, direction=-1, lag=1) == 0
     width = 2 * nx if full else nx + 1
     for b in range(batch):
         want = np.fft.fft2(x[b].astype(np.float64))[:, :width]
@@ -393,7 +345,85 @@ def test_fused_2d_real(emu, host, oracle, nx, ny, ctas, full):
     assert cpu_libs.rel_l2(out[0][:, :width], want[:, :width]) <= tol(2 * nx * ny)
     if not full:
         assert np.all(np.isnan(out[:, :, width:].real)), "columns beyond Nx/2 + 1 must stay untouched"
-    assert list(counters[1:]) == [ny] * batch
+
+
+@pytest.mark.parametrize("nx,ny,batch,ctas,lag,ring", [
+    (256, 256, 1, 2, 1, 1),   # one image: the fft.h call
+    (256, 256, 5, 3, 1, 2),   # ring shorter than the batch: producers wait for the slot's previous consumers
+    (512, 256, 4, 2, 2, 3),   # mirrored-first-pass rows; two images of lag
+    (2048, 256, 3, 2, 1, 3),  # general row shape (the mirrored one would change the tile shape), ring = batch
+])
+def test_fused_2d_c2r(emu, host, oracle, nx, ny, batch, ctas, lag, ring):
+    """Complex-to-real images in the fused kernel (ref fft.c:861-916: columns first): column tiles transform the
+    nx + 1 columns of the input spectrum into a ring slot, row tiles run the C2R resolve + inverse row transform
+    from the slot into the dense real output; the slot is only reused once its consumers are done."""
+    rng = np.random.default_rng(nx + ny + batch)
+    real = rnd(rng, batch, ny, 2 * nx)
+    spec = np.zeros((batch, ny, 2 * nx), np.complex64)
+    spec[:, :, :nx + 1] = np.fft.rfft2(real.astype(np.float64)).astype(np.complex64)
+    spec[:, :, nx + 1:] = np.nan  # padding columns: never read
+    out = np.full((batch, ny, 2 * nx), np.nan, np.float32)
+    counters = np.zeros(1 + 2 * batch, np.uint32)
+    mid = np.full((ring, ny, nx + 2), np.nan, np.complex64)
+    vfn = getattr(emu, f"emu_2d_rows_variant_{nx}x{ny}")
+    vfn.restype, vfn.argtypes = C.c_int, [C.c_int]
+    twx, twy, rtw = engine_table(host, nx, 1, vfn(KIND_C2R)), engine_table(host, ny, 1), resolve_twiddles(1, nx)
+    assert fused_2d(emu, nx, ny, ctas, out=out.ctypes.data, in_=spec.ctypes.data, tw_x=twx.ctypes.data, tw_y=twy.ctypes.data, rtw=rtw.ctypes.data,
+                    kind=KIND_C2R, counters=counters.ctypes.data, mid=mid.ctypes.data, ring=ring, out_image=nx * ny, in_image=2 * nx * ny,
+                    batch=batch, direction=1, lag=lag) == 0
+    for b in range(batch):
+        assert cpu_libs.rel_l2(out[b], real[b].astype(np.float64) * (2 * nx * ny)) <= tol(2 * nx * ny)
+    clean = np.where(np.isnan(spec[0].real), 0, spec[0]).astype(np.complex64)
+    assert cpu_libs.rel_l2(out[0], oracle.c2r_2d(clean)) <= tol(2 * nx * ny)
+
+
+@pytest.mark.parametrize("n1,n2", [(16, 1024), (32, 1024), (32, 2048)])
+@pytest.mark.parametrize("case", ["fwd", "inv", "zero_pad", "peers"])
+def test_four_step_rows(emu, host, oracle, n1, n2, case):
+    """long_kernel.cuh: n1 x n2 points per transform in one launch - register column transforms with derived
+    inter-stage twiddles into the CTA's scratch slot, row transforms with the mapping switch of the last pass.
+    Five transforms over two CTAs (strided in and out), so that slot reuse and the barriers between consecutive
+    transforms are exercised."""
+    fn = getattr(emu, f"emu_launch_long_{n1}x{n2}")
+    fn.restype, fn.argtypes = C.c_int, [C.POINTER(ArgsLong), C.c_uint]
+    n = n1 * n2
+    direction = 1 if case == "inv" else -1
+    batch, ctas = 5, 2
+    rng = np.random.default_rng(n + len(case))
+    tw = engine_table(host, n2, direction)
+    j = np.arange(n, dtype=np.float64)
+    roots = (np.cos(2 * np.pi * direction * j / n).astype(np.float32) + 1j * np.sin(2 * np.pi * direction * j / n).astype(np.float32)).astype(np.complex64)
+    scratch = np.full((ctas, n), np.nan, np.complex64)
+    in_len = n // 2 if case == "zero_pad" else n
+    in_stride, out_stride = in_len + 8, n + 4
+    xbuf = np.full((batch, in_stride), np.nan, np.complex64)
+    xbuf[:, :in_len] = crnd(rng, batch, in_len)
+    x = np.zeros((batch, n), np.complex128)
+    x[:, :in_len] = xbuf[:, :in_len]
+    want = np.fft.fft(x, axis=1) if direction < 0 else np.fft.ifft(x, axis=1, norm="forward")
+    a = ArgsLong(in_=xbuf.ctypes.data, tw=tw.ctypes.data, roots=roots.ctypes.data, scratch=scratch.ctypes.data, scratch_slots=ctas,
+                 in_batch=in_stride, batch=batch, n=n, n1=n1, n2=n2, direction=direction, in_mode=IN_HALF if case == "zero_pad" else IN_COMPLEX)
+    if case == "peers":
+        peers, row0, rows_total = 8, 1, 7
+        width = n // peers
+        slabs = [np.full((rows_total, width), np.nan, np.complex64) for _ in range(peers)]
+        a.to_peers = 1
+        for p_, s_ in enumerate(slabs):
+            a.peers.base[p_] = s_.ctypes.data
+        a.peers.row0, a.peers.pitch, a.peers.shift = row0, width, int(math.log2(width))
+        assert fn(C.byref(a), ctas) == 0
+        out = np.concatenate([s_[row0:row0 + batch] for s_ in slabs], axis=1)
+        assert all(np.all(np.isnan(s_[:row0].real)) and np.all(np.isnan(s_[row0 + batch:].real)) for s_ in slabs)
+    else:
+        obuf = np.full((batch, out_stride), np.nan, np.complex64)
+        a.out, a.out_batch = obuf.ctypes.data, out_stride
+        assert fn(C.byref(a), ctas) == 0
+        out = obuf[:, :n]
+        assert np.all(np.isnan(obuf[:, n:].real)), "nothing is written between the transforms"
+    for b in range(batch):
+        assert cpu_libs.rel_l2(out[b], want[b]) <= tol(n)
+    if case in ("fwd", "inv"):
+        assert cpu_libs.rel_l2(out[0], oracle.c2c(xbuf[0, :n].copy(), direction)) <= tol(n)
 
 
 @pytest.mark.parametrize("n1,n2", [(64, 256), (32, 1024), (128, 512)])

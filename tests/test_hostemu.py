@@ -32,8 +32,7 @@ def lib():
     wrapped = cpu_libs._CpuLib(path, "mufft_")  # the numpy-level wrapper the GPU parity tests use
     raw = wrapped.lib
     for name, res, args in [
-        ("mufft_cuda_set_onchip_limit", None, [u]), ("mufft_cuda_set_fused_2d", None, [i32]), ("mufft_cuda_set_fused_2d_real", None, [i32]),
-        ("mufft_cuda_set_cluster_rows", None, [i32]), ("mufft_cuda_set_two_kernel", None, [i32]), ("mufft_cuda_launch_count", C.c_ulonglong, [i32]),
+        ("mufft_cuda_launch_count", C.c_ulonglong, [i32]), ("mufft_cuda_plan_2d_paths", i32, [vp]),
         ("mufft_cuda_last_error", C.c_char_p, []), ("mufft_alloc", vp, [sz]), ("mufft_free", None, [vp]),
         ("mufft_execute_plan_1d_batch", i32, [vp, vp, vp, sz, sz, sz]), ("mufft_execute_plan_2d_batch", i32, [vp, vp, vp, sz]),
         ("mufft_execute_conv_batch", i32, [vp, vp, vp, vp, sz, sz]), ("mufft_execute_conv_input_batch", i32, [vp, u, vp, vp, sz]),
@@ -63,19 +62,18 @@ def managed(lib, arr):
     return ptr, view
 
 
-@pytest.mark.parametrize("level,n,want", [(0, 65536, (0, 0)), (1, 65536, (2, 0)), (2, 65536, (2, 1)), (2, 1024, (0, 0))])
-def test_managed_memory_prefetch_policy(lib, oracle, level, n, want):
-    """mufft_cuda_set_managed_prefetch: synchronous calls on mufft_alloc memory prefetch buffers of 256 KiB or more to
-    the device in front of the kernel (level 1: input and output) and the output back to the host behind it
-    (level 2); small buffers and level 0 leave it to the page faults.  The emulated CUDA side counts the calls."""
+@pytest.mark.parametrize("n,want", [(65536, (2, 0)), (1024, (0, 0))])
+def test_managed_memory_prefetch_policy(lib, oracle, n, want):
+    """Synchronous calls on mufft_alloc memory prefetch buffers of 256 KiB or more to the device in front of the
+    kernel (input and output; measured 1.3x faster than fault-driven migration); small buffers are left to the page
+    faults, and nothing is prefetched back (the next call may consume the output on the device).  The emulated
+    CUDA side counts the calls."""
     raw = lib.lib
-    raw.mufft_cuda_set_managed_prefetch.restype, raw.mufft_cuda_set_managed_prefetch.argtypes = None, [i32]
     raw.emu_prefetch_calls.restype, raw.emu_prefetch_calls.argtypes = u, [i32, i32]
     x = crnd(np.random.default_rng(n), n)
     px, vx = managed(lib, x)
     py, vy = managed(lib, np.zeros(n, np.complex64))
     plan = lib._create_plan_1d_c2c(n, -1, 0)
-    raw.mufft_cuda_set_managed_prefetch(level)
     try:
         raw.emu_prefetch_calls(0, 1), raw.emu_prefetch_calls(1, 1)
         lib._execute_plan_1d(plan, py, px)
@@ -85,7 +83,6 @@ def test_managed_memory_prefetch_policy(lib, oracle, level, n, want):
         assert cpu_libs.rel_l2(lib.c2c(x, -1), oracle.c2c(x, -1)) <= tol(n)
         assert (raw.emu_prefetch_calls(1, 1), raw.emu_prefetch_calls(0, 1)) == (0, 0)
     finally:
-        raw.mufft_cuda_set_managed_prefetch(0)
         lib._free_plan_1d(plan)
         raw.mufft_free(px)
         raw.mufft_free(py)
@@ -186,63 +183,53 @@ def test_constructor_validation_matches_the_reference(lib, oracle):
             assert lib.plan_1d_is_null(kind, n) == want, (kind, n)
 
 
-@pytest.mark.parametrize("n,limit,two_kernel", [(16384, 16384, 1), (16384, 8192, 1), (32768, 16384, 1), (65536, 16384, 1), (32768, 16384, 0)])
-def test_long_transforms_pick_their_path(lib, n, limit, two_kernel):
-    """16384 points: one kernel or, with the limit lowered, the two-kernel split; 32768 / 65536: two kernels;
-    with the two-kernel path switched off (as beyond 2^21 points): one generic radix-8/4/2 pass per launch.
-    Launch counts tell which path ran; results against numpy float64."""
-    raw = lib.lib
-    raw.mufft_cuda_set_onchip_limit(limit)
-    raw.mufft_cuda_set_two_kernel(two_kernel)
-    try:
-        rng = np.random.default_rng(n)
-        x = crnd(rng, n)
-        pin, xv = managed(lib, x)
-        pout, yv = managed(lib, np.zeros(n, np.complex64))
-        plan = lib._create_plan_1d_c2c(n, -1, 0)
-        assert plan
-        raw.mufft_cuda_launch_count(1)
-        assert raw.mufft_execute_plan_1d_batch(plan, pout, pin, 1, 0, 0) == 0, raw.mufft_cuda_last_error()
-        launches = raw.mufft_cuda_launch_count(1)
-        expect = 1 if n <= limit else (2 if two_kernel else math.ceil(math.log2(n) / 3))
-        assert launches == expect
-        assert raw.mufft_cuda_plan_1d_uses_engine(plan) == (1 if n <= limit else 0)
-        lib._free_plan_1d(plan)
-        assert cpu_libs.rel_l2(yv, np.fft.fft(x.astype(np.complex128))) <= tol(n)
-        raw.mufft_free(pin)
-        raw.mufft_free(pout)
-    finally:
-        raw.mufft_cuda_set_onchip_limit(16384)
-        raw.mufft_cuda_set_two_kernel(1)
+SEPARATE_2D, TWO_KERNEL, GENERIC_PASSES, FOUR_STEP_16K = 1 << 20, 1 << 21, 1 << 22, 1 << 23  # mufft_cuda.h plan flags
 
 
-@pytest.mark.parametrize("n", [32768, 65536])
-@pytest.mark.parametrize("mode", [1, 2])
-def test_cluster_rows_switch(lib, n, mode):
-    """mufft_cuda_set_cluster_rows: plans created afterwards run 32768 / 65536-point rows in ONE launch (the
-    cluster kernel, both exchange flavours); zero-padded too; a real transform of that complex length keeps
-    the two-kernel path."""
+@pytest.mark.parametrize("n,flags,launches,one_launch", [
+    (16384, 0, 1, 1),                 # one CTA per transform on the engine
+    (16384, FOUR_STEP_16K, 1, 1),     # 16 x 1024 on the four-step kernel
+    (16384, TWO_KERNEL, 2, 0),        # column kernel + transposing row kernel through scratch
+    (32768, 0, 1, 1),                 # 32 x 1024 four-step kernel, intermediate in the CTA's L2 slot
+    (65536, 0, 1, 1),                 # 32 x 2048
+    (65536, TWO_KERNEL, 2, 0),
+    (131072, 0, 2, 0),                # beyond the four-step shapes: two kernels
+    (32768, GENERIC_PASSES, 5, 0),    # one radix-8/4/2 pass per launch, as the reference (fft.c:811-850)
+])
+@pytest.mark.parametrize("zero_pad", [0, 1])
+def test_long_transforms_pick_their_path(lib, n, flags, launches, one_launch, zero_pad):
+    """Which path a plan takes is fixed by its creation flags (no process-global switch); launch counts tell which
+    one ran; results against numpy float64, plain and with the zero-padded upper half."""
     raw = lib.lib
-    raw.mufft_cuda_set_cluster_rows(mode)
-    try:
-        rng = np.random.default_rng(n + mode)
-        x = crnd(rng, 2, n)
-        pin, _ = managed(lib, x)
-        pout, yv = managed(lib, np.zeros((2, n), np.complex64))
-        for flags, cols in ((0, n), (cpu_libs.FLAG_ZERO_PAD, n // 2)):
-            plan = lib._create_plan_1d_c2c(n, 1, flags)
-            raw.mufft_cuda_launch_count(1)
-            assert raw.mufft_execute_plan_1d_batch(plan, pout, pin, 2, 0, n * 8) == 0, raw.mufft_cuda_last_error()
-            assert raw.mufft_cuda_launch_count(1) == 1
-            lib._free_plan_1d(plan)
-            xp = np.zeros((2, n), np.complex128)
-            xp[:, :cols] = x[:, :cols]
-            want = np.fft.ifft(xp, axis=1, norm="forward")
-            assert cpu_libs.rel_l2(yv, want) <= tol(n)
-        raw.mufft_free(pin)
-        raw.mufft_free(pout)
-    finally:
-        raw.mufft_cuda_set_cluster_rows(0)
+    rng = np.random.default_rng(n)
+    cols = n // 2 if zero_pad else n
+    x = crnd(rng, 2, cols)
+    pin, _ = managed(lib, x)
+    pout, yv = managed(lib, np.zeros((2, n), np.complex64))
+    plan = lib._create_plan_1d_c2c(n, -1, flags | (cpu_libs.FLAG_ZERO_PAD if zero_pad else 0))
+    assert plan
+    raw.mufft_cuda_launch_count(1)
+    assert raw.mufft_execute_plan_1d_batch(plan, pout, pin, 2, 0, 0) == 0, raw.mufft_cuda_last_error()
+    assert raw.mufft_cuda_launch_count(1) == launches
+    assert raw.mufft_cuda_plan_1d_uses_engine(plan) == one_launch
+    lib._free_plan_1d(plan)
+    xp = np.zeros((2, n), np.complex128)
+    xp[:, :cols] = x
+    assert cpu_libs.rel_l2(yv, np.fft.fft(xp, axis=1)) <= tol(n)
+    raw.mufft_free(pin)
+    raw.mufft_free(pout)
+
+
+@pytest.mark.parametrize("n", [65536, 131072])
+def test_long_real_transforms(lib, oracle, n):
+    """R2C / C2R of n reals with n/2 complex points beyond the on-chip engine: resolve sweep + four-step kernel
+    (32768 points) or two kernels (65536 points) through plan scratch."""
+    rng = np.random.default_rng(n)
+    r = rnd(rng, n)
+    spec = lib.r2c(r)
+    assert cpu_libs.rel_l2(spec, np.fft.rfft(r.astype(np.float64))) <= tol(n)
+    back = lib.c2r(spec, n)
+    assert cpu_libs.rel_l2(back, r.astype(np.float64) * n) <= tol(n)
 
 
 @pytest.mark.parametrize("nx,ny", [(16, 8), (64, 64), (256, 256), (512, 256), (32, 2048), (4096, 4)])
@@ -262,57 +249,63 @@ def test_fft_h_2d(lib, oracle, nx, ny):
         assert cpu_libs.rel_l2(lib.c2r_2d(spec), oracle.c2r_2d(spec)) <= tol(nx * ny)
 
 
-@pytest.mark.parametrize("lag", [1, 2, 7])
-def test_fused_2d_lag_knob(lib, oracle, lag):
-    """mufft_cuda_set_fused_2d_lag: the column pass runs `lag` images behind the row pass (7 > batch: all rows
-    first); same results for every value, one launch for the batch."""
+@pytest.mark.parametrize("kind", ["c2c", "r2c", "r2c_full", "c2r"])
+@pytest.mark.parametrize("separate", [0, 1])
+def test_fused_2d_is_the_default_and_a_plan_flag_turns_it_off(lib, oracle, kind, separate):
+    """2D plans of 512 x 256 points (256-point row transforms for the real kinds): the whole batch is ONE launch of
+    the fused kernel for every kind - C2R through the plan's ring of intermediates - unless the plan was created
+    with MUFFT_CUDA_FLAG_SEPARATE_2D: then a row launch and a column launch through plan scratch."""
     raw = lib.lib
-    raw.mufft_cuda_set_fused_2d_lag.restype, raw.mufft_cuda_set_fused_2d_lag.argtypes = None, [u]
-    nx = ny = 256
-    batch = 4
-    x = cpu_libs.aligned_copy(crnd(np.random.default_rng(lag), batch, ny, nx), np.complex64)
-    y = cpu_libs.aligned_zeros(batch * ny * nx, np.complex64).reshape(batch, ny, nx)
-    plan = lib._create_plan_2d_c2c(nx, ny, -1, 0)
-    raw.mufft_cuda_set_fused_2d_lag(lag)
-    try:
-        px, vx = managed(lib, x)
-        py, vy = managed(lib, y)
-        raw.mufft_cuda_launch_count(1)
-        assert raw.mufft_execute_plan_2d_batch(plan, py, px, batch) == 0, raw.mufft_cuda_last_error()
-        assert raw.mufft_cuda_launch_count(1) == 1
-        for b in range(batch):
-            assert cpu_libs.rel_l2(vy[b], oracle.c2c_2d(x[b], -1)) <= tol(nx * ny)
-        raw.mufft_free(px)
-        raw.mufft_free(py)
-    finally:
-        raw.mufft_cuda_set_fused_2d_lag(0)
-        lib._free_plan_2d(plan)
-
-
-@pytest.mark.parametrize("fused_real", [0, 1])
-def test_fused_2d_real_switch(lib, oracle, fused_real):
-    """2D R2C of 512 x 256 reals (row transforms of 256 complex points): with the switch on the whole batch is
-    ONE launch of the fused kernel, otherwise a row launch and a column launch through plan scratch."""
-    raw = lib.lib
-    nx, ny, batch = 512, 256, 3
-    raw.mufft_cuda_set_fused_2d_real(fused_real)
-    try:
-        rng = np.random.default_rng(5)
-        r = rnd(rng, batch, ny, nx)
-        pin, _ = managed(lib, r)
+    nx, ny, batch = 512, 256, 5
+    flags = SEPARATE_2D if separate else 0
+    rng = np.random.default_rng(5)
+    if kind == "c2c":
+        x = crnd(rng, batch, ny, nx)
+        plan = lib._create_plan_2d_c2c(nx, ny, -1, flags)
         pout, yv = managed(lib, np.zeros((batch, ny, nx), np.complex64))
-        plan = lib._create_plan_2d_r2c(nx, ny, 0)
-        raw.mufft_cuda_launch_count(1)
-        assert raw.mufft_execute_plan_2d_batch(plan, pout, pin, batch) == 0, raw.mufft_cuda_last_error()
-        assert raw.mufft_cuda_launch_count(1) == (1 if fused_real else 2)
-        lib._free_plan_2d(plan)
-        for b in range(batch):
-            want = oracle.r2c_2d(r[b])[:, : nx // 2 + 1]
-            assert cpu_libs.rel_l2(yv[b][:, : nx // 2 + 1], want) <= tol(nx * ny)
-        raw.mufft_free(pin)
-        raw.mufft_free(pout)
-    finally:
-        raw.mufft_cuda_set_fused_2d_real(0)
+    elif kind == "c2r":
+        real = rnd(rng, batch, ny, nx)
+        x = np.zeros((batch, ny, nx), np.complex64)
+        x[:, :, : nx // 2 + 1] = np.fft.rfft2(real.astype(np.float64)).astype(np.complex64)
+        plan = lib._create_plan_2d_c2r(nx, ny, flags)
+        pout, yv = managed(lib, np.zeros((batch, ny, nx), np.float32))
+    else:
+        x = rnd(rng, batch, ny, nx)
+        plan = lib._create_plan_2d_r2c(nx, ny, flags | (cpu_libs.FLAG_FULL_R2C if kind == "r2c_full" else 0))
+        pout, yv = managed(lib, np.zeros((batch, ny, nx), np.complex64))
+    assert plan
+    assert bool(raw.mufft_cuda_plan_2d_paths(plan) & 4) == (not separate)
+    pin, _ = managed(lib, x)
+    raw.mufft_cuda_launch_count(1)
+    assert raw.mufft_execute_plan_2d_batch(plan, pout, pin, batch) == 0, raw.mufft_cuda_last_error()
+    assert raw.mufft_cuda_launch_count(1) == (2 if separate else 1)
+    lib._free_plan_2d(plan)
+    for b in range(batch):
+        if kind == "c2c":
+            assert cpu_libs.rel_l2(yv[b], oracle.c2c_2d(x[b], -1)) <= tol(nx * ny)
+        elif kind == "c2r":
+            assert cpu_libs.rel_l2(yv[b], oracle.c2r_2d(x[b])) <= tol(nx * ny)
+        else:
+            w = nx if kind == "r2c_full" else nx // 2 + 1
+            want = oracle.r2c_2d(x[b], cpu_libs.FLAG_FULL_R2C if kind == "r2c_full" else 0)[:, :w]
+            assert cpu_libs.rel_l2(yv[b][:, :w], want) <= tol(nx * ny)
+    raw.mufft_free(pin)
+    raw.mufft_free(pout)
+
+
+def test_error_messages_survive_the_layers_above(lib):
+    """An inner layer's message is what mufft_cuda_last_error() returns: a stereo partitioned convolution beyond the
+    on-chip engine is refused by run_rows, two TRY() layers below the entry point (GPUTEST_r01 was red on this)."""
+    raw = lib.lib
+    plan = lib._create_plan_conv(32768, 0, 1 | 4 | 8)
+    assert plan
+    blk = 32768 * 8
+    bufs = [raw.mufft_alloc(4 * blk) for _ in range(3)]
+    assert raw.mufft_execute_conv_output_partitioned_batch(plan, bufs[0], bufs[1] + blk, bufs[2], 2, 1) != 0
+    assert b"fits the on-chip engine" in raw.mufft_cuda_last_error()
+    for b_ in bufs:
+        raw.mufft_free(b_)
+    lib._free_plan_conv(plan)
 
 
 @pytest.mark.parametrize("n", [8, 256, 2048, 16384, 32768])
