@@ -557,6 +557,32 @@ class Job:
             raise RuntimeError("execute failed: " + self.m.mufft_cuda_last_error().decode())
 
 
+def slab_also(m, ndev, nx=32768, ny=32768, reps=5):
+    """One nx x ny C2C transform over ndev devices of this process (include/mufft_cuda.h slab plan), data resident in
+    the plan's device slabs; device-event time (max over devices), best of `reps` after 2 warm-up runs."""
+    plan = m.mufft_cuda_create_plan_2d_slab_c2c(nx, ny, m.MUFFT_FORWARD, ndev, None, 0)
+    if not plan:
+        raise RuntimeError(m.mufft_cuda_last_error().decode())
+    try:
+        for g in range(ndev):  # any finite data: timing does not depend on values (zeros would do, but keep it honest)
+            assert m.mufft_cuda_memset(m.mufft_cuda_slab_input(plan, g), 0x3c, m.mufft_cuda_slab_input_bytes(plan, g)) == 0
+        times = []
+        for i in range(2 + reps):
+            if m.mufft_cuda_execute_plan_2d_slab(plan) != 0:
+                raise RuntimeError(m.mufft_cuda_last_error().decode())
+            if i >= 2:
+                times.append(m.mufft_cuda_slab_last_ms(plan))
+        ms = sorted(times)[len(times) // 2]
+    finally:
+        m.mufft_cuda_free_plan_2d_slab(plan)
+        m.mufft_cuda_set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    flops = 5.0 * nx * ny * (math.log2(nx) + math.log2(ny))
+    per_gpu_out = 8.0 * nx * ny * (ndev - 1) / ndev / ndev  # bytes leaving each GPU over NVLink
+    return {"workload": "single 2D C2C %dx%d over %d GPUs, C-ABI slab plan, peer-store exchange, transposed-out" % (nx, ny, ndev),
+            "ms": round(ms, 4), "gflops": round(flops / ms * 1e-6, 1), "nvlink_gbs_per_gpu_per_dir": round(per_gpu_out / ms * 1e-6, 1),
+            "hbm_gbs_per_gpu_algorithmic": round(16.0 * nx * ny / ndev / ms * 1e-6, 1)}
+
+
 def time_steps(torch, dist, job, warmup, steps):
     """CUDA-event timing on the launching stream; returns (total ms max over ranks, per-step ms list)."""
     for _ in range(warmup):
@@ -769,6 +795,28 @@ def main():
         # launch + synchronise per call; the batched form of the same transform is 'c2c64'
         also["c2c64_single_call"] = {"us_per_call": round(us, 3), "gflops": round(5 * 64 * 6 / us * 1e-3, 4)}
         m.mufft_free(a_in); m.mufft_free(a_out); m.mufft_free_plan_1d(plan)
+
+    # BASELINE configs[4] next to the scaling curve: ONE 32768 x 32768 C2C over all N GPUs through the C-ABI slab plan
+    # (mufft_cuda_create_plan_2d_slab_c2c: one process - rank 0 - drives every device; the row kernels' peer stores
+    # over NVLink are the all-to-all).  The other ranks stay off their GPUs meanwhile (no NCCL kernel spinning there).
+    if world > 1 and args.also and not args.units and args.workload == "c2c4096":
+        flag = os.path.join(tempfile.gettempdir(), "mufft_slab_done_%s" % os.environ.get("MASTER_PORT", "0"))
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        if rank == 0:
+            try:
+                also["slab2d"] = slab_also(m, world)
+            except Exception as exc:
+                also["slab2d"] = {"error": repr(exc)[:200]}
+            open(flag, "w").close()
+        else:
+            t_end = time.time() + 300
+            while not os.path.exists(flag) and time.time() < t_end:
+                time.sleep(0.05)
+        dist.barrier()
+        if rank == 0:
+            os.unlink(flag)
 
     cpu = None
     if rank == 0 and not args.no_cpu:

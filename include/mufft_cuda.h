@@ -137,6 +137,36 @@ int mufft_execute_conv_output_partitioned_batch(mufft_plan_conv *plan, void *out
 int mufft_execute_conv_output_partitioned_batch_async(mufft_plan_conv *plan, void *output, const void *spectra,
                                                       const void *filter_spectra, unsigned parts, size_t batch);
 
+/* ---- one large 2D transform over several devices of this process (slab decomposition) ----------------------
+ * BASELINE-style: device g owns rows [g Ny/G, (g+1) Ny/G) of the [Ny][Nx] array.  Row pass local, with the
+ * exchange fused into it: the row kernel stores element x of every row straight into the column slab of device
+ * x / (Nx/G) over NVLink (peer access; no pack pass, no collective library).  Events order the devices, then each
+ * transforms the columns of its slab in place.  Result: device g holds columns [g Nx/G, (g+1) Nx/G) of the
+ * spectrum as a row-major [Ny][Nx/G] array ("transposed-out"); the _host call gathers the natural [Ny][Nx]
+ * order.  R2C (forward, Nx reals per row): real row transforms first (half the exchanged volume); the Nx/2 lower
+ * columns are split evenly and the Nyquist column Nx/2 rides with the last device.
+ * ndev: a power of two (<= 16) dividing Ny and Nx (R2C: Nx/2); devices: CUDA ordinals, NULL = 0 .. ndev-1.  The
+ * reference's function this distributes is mufft_execute_plan_2d (fft.c:852-989). */
+typedef struct mufft_plan_2d_slab mufft_plan_2d_slab;
+mufft_plan_2d_slab *mufft_cuda_create_plan_2d_slab_c2c(unsigned Nx, unsigned Ny, int direction, unsigned ndev, const int *devices, unsigned flags);
+mufft_plan_2d_slab *mufft_cuda_create_plan_2d_slab_r2c(unsigned Nx, unsigned Ny, unsigned ndev, const int *devices, unsigned flags);
+void mufft_cuda_free_plan_2d_slab(mufft_plan_2d_slab *plan);
+unsigned mufft_cuda_slab_devices(const mufft_plan_2d_slab *plan);
+/* Plan-owned device buffers of device index g: the input row slab ([Ny/G][Nx] complex, R2C: floats) and the
+ * output column slab ([Ny][columns] complex; columns and the first column's index in the spectrum below). */
+void *mufft_cuda_slab_input(mufft_plan_2d_slab *plan, unsigned g);
+void *mufft_cuda_slab_output(mufft_plan_2d_slab *plan, unsigned g);
+size_t mufft_cuda_slab_input_bytes(const mufft_plan_2d_slab *plan, unsigned g);
+size_t mufft_cuda_slab_output_bytes(const mufft_plan_2d_slab *plan, unsigned g);
+unsigned mufft_cuda_slab_output_columns(const mufft_plan_2d_slab *plan, unsigned g, unsigned *first_column);
+/* Transforms the input slabs into the output slabs on all devices; returns when every device is done. */
+int mufft_cuda_execute_plan_2d_slab(mufft_plan_2d_slab *plan);
+/* Device time of the last execute in milliseconds: max over the devices, row pass start to column pass end. */
+float mufft_cuda_slab_last_ms(const mufft_plan_2d_slab *plan);
+/* Whole arrays in host memory: input [Ny][Nx] (complex, R2C: floats), output [Ny][Nx] complex in natural order
+ * (R2C: [Ny][Nx/2 + 1]), i.e. what mufft_execute_plan_2d computes, on ndev devices. */
+int mufft_cuda_execute_plan_2d_slab_host(mufft_plan_2d_slab *plan, void *output, const void *input);
+
 /* Plan-creation flags of this implementation, OR-ed into the `flags` argument of the fft.h constructors
  * (the reference's own flags use bits 0-2, 16 and 17, its internal ones bits 24-28; ref fft.h:52-65,
  * fft_internal.h:180-192).  They select the slower fallback paths, which are kept for measurement and

@@ -92,6 +92,18 @@ SIGNATURES = {
     "mufft_execute_conv_batch_async": (_i, [_vp, _vp, _vp, _vp, _sz, _sz]),
     "mufft_execute_conv_output_partitioned_batch": (_i, [_vp, _vp, _vp, _vp, _u, _sz]),
     "mufft_execute_conv_output_partitioned_batch_async": (_i, [_vp, _vp, _vp, _vp, _u, _sz]),
+    "mufft_cuda_create_plan_2d_slab_c2c": (_vp, [_u, _u, _i, _u, C.POINTER(_i), _u]),
+    "mufft_cuda_create_plan_2d_slab_r2c": (_vp, [_u, _u, _u, C.POINTER(_i), _u]),
+    "mufft_cuda_free_plan_2d_slab": (None, [_vp]),
+    "mufft_cuda_slab_devices": (_u, [_vp]),
+    "mufft_cuda_slab_input": (_vp, [_vp, _u]),
+    "mufft_cuda_slab_output": (_vp, [_vp, _u]),
+    "mufft_cuda_slab_input_bytes": (_sz, [_vp, _u]),
+    "mufft_cuda_slab_output_bytes": (_sz, [_vp, _u]),
+    "mufft_cuda_slab_output_columns": (_u, [_vp, _u, C.POINTER(_u)]),
+    "mufft_cuda_execute_plan_2d_slab": (_i, [_vp]),
+    "mufft_cuda_slab_last_ms": (C.c_float, [_vp]),
+    "mufft_cuda_execute_plan_2d_slab_host": (_i, [_vp, _vp, _vp]),
     "mufft_cuda_plan_1d_uses_engine": (_i, [_vp]),
     "mufft_cuda_plan_2d_paths": (_i, [_vp]),
 }

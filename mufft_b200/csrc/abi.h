@@ -221,6 +221,11 @@ int mcu_event_destroy(void *event);
 int mcu_event_record(void *event, void *stream);
 int mcu_stream_wait_event(void *stream, void *event);
 int mcu_event_sync(void *event);
+int mcu_event_create_timing(void **event);                 /* an event that records time stamps */
+int mcu_event_elapsed_ms(float *ms, void *start, void *end); /* both recorded on streams of the same device */
+/* lets kernels and copies of the current device address memory of `peer_device` (NVLink / PCIe peer to peer);
+ * already enabled = success */
+int mcu_enable_peer_access(int peer_device);
 int mcu_copy_async(void *dst, const void *src, size_t bytes, void *stream);
 int mcu_copy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t rows, void *stream);
 int mcu_prefetch(const void *ptr, size_t bytes, int to_device, void *stream);

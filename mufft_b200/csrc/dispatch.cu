@@ -137,6 +137,29 @@ int mcu_event_destroy(void *event) { return event ? (int)cudaEventDestroy((cudaE
 int mcu_event_record(void *event, void *stream) { return (int)cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream); }
 int mcu_stream_wait_event(void *stream, void *event) { return (int)cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0); }
 int mcu_event_sync(void *event) { return (int)cudaEventSynchronize((cudaEvent_t)event); }
+int mcu_event_create_timing(void **event)
+{
+    cudaEvent_t e;
+    cudaError_t err = cudaEventCreate(&e);
+    *event = (void *)e;
+    return (int)err;
+}
+int mcu_event_elapsed_ms(float *ms, void *start, void *end) { return (int)cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)end); }
+int mcu_enable_peer_access(int peer_device)
+{
+    int dev = 0, can = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return (int)err;
+    if (dev == peer_device) return 0;
+    if ((err = cudaDeviceCanAccessPeer(&can, dev, peer_device)) != cudaSuccess) return (int)err;
+    if (!can) return (int)cudaErrorPeerAccessUnsupported;
+    err = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (err == cudaErrorPeerAccessAlreadyEnabled) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return (int)err;
+}
 int mcu_copy_async(void *dst, const void *src, size_t bytes, void *stream)
 {
     if (bytes == 0) return 0;

@@ -233,9 +233,13 @@ fft2d_fused_kernel(const mcu_2d_args a)
     };
     // What ticket k has to wait for: a consumer for the producers of its image; a C2R producer for the
     // consumers of the image that used its ring slot before.  nullptr = nothing.
-    auto dependency = [&](unsigned k, unsigned &need) -> const unsigned * {
+    // `reads` = the ticket will read what the counter announces (acquire needed); a producer waiting for its
+    // ring slot only overwrites it (write-after-read: the wait alone orders it, and the acquire fence would
+    // throw away the SM's L1 - twiddle tables included - for nothing).
+    auto dependency = [&](unsigned k, unsigned &need, bool &reads) -> const unsigned * {
         unsigned image, tile;
-        if (!decode(k, image, tile)) { need = NP; return produced + image; }
+        if (!decode(k, image, tile)) { need = NP; reads = true; return produced + image; }
+        reads = false;
         if (COLS_FIRST && image >= a.ring) { need = NQ; return consumed + (image - a.ring); }
         return nullptr;
     };
@@ -255,13 +259,14 @@ fft2d_fused_kernel(const mcu_2d_args a)
         unsigned wait = 0;
         if (k < total) {
             unsigned need = 0;
-            const unsigned *dep = dependency(k, need);
+            bool reads = false;
+            const unsigned *dep = dependency(k, need, reads);
             if (dep != nullptr) {
                 if (ld_relaxed(dep) < need) {
                     if (pending != nullptr) wait = 1;
                     else wait_for(dep, need);
                 }
-                fence_acquire_gpu();
+                if (reads) fence_acquire_gpu();
             }
         }
         s_ticket[slot] = k;
@@ -280,10 +285,11 @@ fft2d_fused_kernel(const mcu_2d_args a)
         if (s_wait[it & 1]) { // rare: see publish
             if (tid == 0) {
                 unsigned need = 0;
-                const unsigned *dep = dependency(k, need);
+                bool reads = false;
+                const unsigned *dep = dependency(k, need, reads);
                 release_pending();
                 wait_for(dep, need);
-                fence_acquire_gpu();
+                if (reads) fence_acquire_gpu();
             }
             __syncthreads();
         }

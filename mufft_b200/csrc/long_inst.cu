@@ -12,9 +12,15 @@
 
 namespace mufft {
 
+// A shape the configured tile (MUFFT_LONG_TR) cannot take reports "unsupported": the host layer then uses the
+// two-kernel split for that length instead of failing the build.
 template <int DIR, int IN_MODE, bool TO_PEERS>
 static cudaError_t launch_long(const mcu_long_args &a, cudaStream_t stream, int *ctas_only)
 {
+  if constexpr (!long_supported(LONG_N1, LONG_N2)) {
+    (void)a; (void)stream; (void)ctas_only;
+    return cudaErrorInvalidValue;
+  } else {
     static launch_cfg cfg;
     auto kernel = fft_long_kernel<LONG_N1, LONG_N2, DIR, IN_MODE, TO_PEERS>;
     constexpr size_t smem = long_smem_bytes(LONG_N2);
@@ -31,6 +37,7 @@ static cudaError_t launch_long(const mcu_long_args &a, cudaStream_t stream, int 
     if (grid == 0) return cudaErrorInvalidValue;
     kernel<<<(unsigned)grid, long_cta_threads(LONG_N2), smem, stream>>>(a);
     return cudaGetLastError();
+  }
 }
 
 // All instantiations of a shape have the same launch bounds and shared memory, hence the same occupancy.

@@ -16,11 +16,17 @@
 //           anyway): a warp then stores runs of TR consecutive k1 (64 or 128 bytes) per k2.
 //
 // The scratch slot (N complex per resident CTA, 38 MB for 32768 points on 148 SMs x 1 CTA, 76 MB x 2)
-// is written and read back by the same CTA a few microseconds apart and overwritten by the CTA's next
-// transform, so it lives in the 126 MB L2: HBM sees each transform's input once and its output once
-// (16 N bytes), where the two-kernel split (cols_kernel.cuh + rowst_kernel.cuh) moves 32 N bytes and
-// the reference's log8(N) = 5 passes move 80 N (ref fft.c:811-850 over kernel.c:395-453).  Input loads
-// and output stores carry streaming hints so that they do not push the scratch out of L2.
+// is written and read back by the same CTA a few microseconds apart, so it lives in the 126 MB L2: HBM
+// sees each transform's input once and its output once (16 N bytes), where the two-kernel split
+// (cols_kernel.cuh + rowst_kernel.cuh) moves 32 N bytes and the reference's log8(N) = 5 passes move 80 N
+// (ref fft.c:811-850 over kernel.c:395-453).  Two things keep it that way (ncu on the first version,
+// profiles/r02b_long32768.txt: 2.03 GB written for 1.07 GB of output - every scratch line was eventually
+// written back, dead):
+//   * once a group of rows has been read back, its scratch lines are DISCARDED (discard.global.L2 = drop the
+//     dirty lines from L2 without a write-back): the intermediate never reaches HBM and the live footprint
+//     is half a slot per CTA;
+//   * input loads and output stores carry streaming hints, and the next transform's input is pulled into
+//     L2 by a bulk prefetch while the current one is in step B, so step A's loads find it there.
 #pragma once
 
 #include "abi.h"
@@ -32,6 +38,29 @@ namespace mufft {
 #ifndef MUFFT_LONG_TR
 #define MUFFT_LONG_TR 8 // rows per group of step B (8: 64-byte output runs; 16: 128-byte runs, twice the CTA)
 #endif
+#ifndef MUFFT_LONG_DISCARD
+#define MUFFT_LONG_DISCARD 1
+#endif
+#ifndef MUFFT_LONG_PREFETCH
+#define MUFFT_LONG_PREFETCH 1
+#endif
+// Drop 128 bytes (aligned) from L2 without writing them back: the data is dead.
+__device__ __forceinline__ void discard_l2_128(const void *p)
+{
+#ifdef MUFFT_EMU
+    (void)p;
+#else
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+#endif
+}
+__device__ __forceinline__ void prefetch_l2_bytes(const void *p, unsigned bytes) // 16-byte aligned, a multiple of 16
+{
+#ifdef MUFFT_EMU
+    (void)p; (void)bytes;
+#else
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#endif
+}
 __host__ __device__ constexpr int long_tile_rows(int n2) { (void)n2; return MUFFT_LONG_TR; }
 __host__ __device__ constexpr int long_cta_threads(int n2) { return long_tile_rows(n2) * engine_threads(n2); }
 // Row pitch of the exchange area, in cpx: after the mapping switch a half-warp reads TR rows x 16/TR
@@ -96,6 +125,15 @@ fft_long_kernel(const mcu_long_args a)
         }
         __syncthreads(); // Y is complete and visible to the whole CTA (reads below bypass L1)
 
+        if constexpr (MUFFT_LONG_PREFETCH != 0) {
+            // the next transform of this CTA: into L2 now, in 16 pieces, so that step A finds it there
+            constexpr unsigned in_bytes = (IN_MODE == MCU_IN_HALF ? N / 2 : N) * sizeof(cpx);
+            const size_t nb = b + gridDim.x;
+            if (tid < 16 && nb < a.batch) {
+                const char *nxt = reinterpret_cast<const char *>(static_cast<const cpx *>(a.in) + nb * a.in_batch) + (size_t)tid * (in_bytes / 16);
+                if ((reinterpret_cast<uintptr_t>(nxt) & 15) == 0) prefetch_l2_bytes(nxt, in_bytes / 16);
+            }
+        }
         // ---- step B: N2-point transforms along the rows of Y, TR rows at a time ---------------------
 #pragma unroll 1
         for (int g = 0; g < N1 / TR; g++) {
@@ -117,6 +155,11 @@ fft_long_kernel(const mcu_long_args a)
                 }
             });
             __syncthreads();
+            if constexpr (MUFFT_LONG_DISCARD != 0) {
+                // every thread has its part of this group's rows in registers / shared memory: the scratch lines are dead
+                const char *dead = reinterpret_cast<const char *>(scratch + (size_t)g * TR * N2);
+                for (int l = tid; l < TR * N2 * (int)sizeof(cpx) / 128; l += THREADS) discard_l2_128(dead + (size_t)l * 128);
+            }
             const cpx *sm2 = smem + slot2 * SE;
 #pragma unroll
             for (int e = 0; e < R; e++) v[e] = sm2[pad_pos<SH>(t2 + e * T)];

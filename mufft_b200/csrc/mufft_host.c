@@ -1459,3 +1459,5 @@ int mufft_execute_plan_2d_batch_async(mufft_plan_2d *plan, void *output, const v
 {
     return exec_2d(plan, output, input, batch, 1);
 }
+
+#include "mufft_slab.inc"

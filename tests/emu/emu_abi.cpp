@@ -115,6 +115,9 @@ int mcu_event_destroy(void *event) { free(event); return 0; }
 int mcu_event_record(void *, void *) { return 0; }
 int mcu_stream_wait_event(void *, void *) { return 0; }
 int mcu_event_sync(void *) { return 0; }
+int mcu_event_create_timing(void **event) { *event = malloc(1); return 0; }
+int mcu_event_elapsed_ms(float *ms, void *, void *) { *ms = 1.0f; return 0; }
+int mcu_enable_peer_access(int peer) { return peer < 0 || peer > 1 ? 101 : 0; }
 int mcu_copy_async(void *dst, const void *src, size_t bytes, void *) { if (bytes) memmove(dst, src, bytes); return 0; }
 int mcu_copy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t rows, void *)
 {

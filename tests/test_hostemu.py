@@ -400,3 +400,40 @@ def test_reference_test_suite_passes_on_the_emulation(lib):
     assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
     assert res.stdout.rstrip().endswith("All tests passed!")
     assert res.stdout.count("... Passed") > 2500
+
+
+@pytest.mark.parametrize("kind,nx,ny,ndev", [("c2c", 256, 128, 2), ("c2c", 64, 64, 1), ("c2c", 32768, 8, 2), ("r2c", 512, 64, 2), ("r2c", 64, 32, 1)])
+def test_slab_plan_over_the_devices_of_one_process(lib, oracle, kind, nx, ny, ndev):
+    """mufft_cuda_create_plan_2d_slab_*: one 2D transform over `ndev` devices of this process (the emulated CUDA side
+    has two): row pass with the exchange fused in (stores into every device's column slab), events, column pass in
+    place; the _host call gathers the natural [Ny][Nx] order, i.e. what mufft_execute_plan_2d computes.  32768-point
+    rows take the four-step kernel with the scatter epilogue."""
+    raw = lib.lib
+    raw.mufft_cuda_create_plan_2d_slab_c2c.restype, raw.mufft_cuda_create_plan_2d_slab_c2c.argtypes = vp, [u, u, i32, u, C.POINTER(i32), u]
+    raw.mufft_cuda_create_plan_2d_slab_r2c.restype, raw.mufft_cuda_create_plan_2d_slab_r2c.argtypes = vp, [u, u, u, C.POINTER(i32), u]
+    raw.mufft_cuda_free_plan_2d_slab.restype, raw.mufft_cuda_free_plan_2d_slab.argtypes = None, [vp]
+    raw.mufft_cuda_execute_plan_2d_slab_host.restype, raw.mufft_cuda_execute_plan_2d_slab_host.argtypes = i32, [vp, vp, vp]
+    raw.mufft_cuda_slab_output_columns.restype, raw.mufft_cuda_slab_output_columns.argtypes = u, [vp, u, C.POINTER(u)]
+    rng = np.random.default_rng(nx + ny)
+    if kind == "c2c":
+        x = crnd(rng, ny, nx)
+        plan = raw.mufft_cuda_create_plan_2d_slab_c2c(nx, ny, -1, ndev, None, 0)
+        out = np.full((ny, nx), np.nan, np.complex64)
+        want = oracle.c2c_2d(x, -1) if nx * ny <= 1 << 16 else np.fft.fft2(x.astype(np.complex128))
+    else:
+        x = rnd(rng, ny, nx)
+        plan = raw.mufft_cuda_create_plan_2d_slab_r2c(nx, ny, ndev, None, 0)
+        out = np.full((ny, nx // 2 + 1), np.nan, np.complex64)
+        want = oracle.r2c_2d(x)[:, : nx // 2 + 1]
+    assert plan, raw.mufft_cuda_last_error()
+    first = u(0)
+    widths = [raw.mufft_cuda_slab_output_columns(plan, g, C.byref(first)) for g in range(ndev)]
+    assert sum(widths) == out.shape[1]
+    for _ in range(2):
+        assert raw.mufft_cuda_execute_plan_2d_slab_host(plan, out.ctypes.data, x.ctypes.data) == 0, raw.mufft_cuda_last_error()
+    raw.mufft_cuda_free_plan_2d_slab(plan)
+    assert cpu_libs.rel_l2(out, want) <= tol(nx * ny)
+    # argument checks: the devices must divide the array, and exist
+    assert not raw.mufft_cuda_create_plan_2d_slab_c2c(64, 64, -1, 3, None, 0)
+    assert not raw.mufft_cuda_create_plan_2d_slab_c2c(64, 64, -1, 4, None, 0)  # the emulated side has two devices
+    assert b"visible" in raw.mufft_cuda_last_error()

@@ -9,7 +9,13 @@ import socket
 import numpy as np
 import pytest
 
+from cpu_libs import rel_l2
+
 pytestmark = pytest.mark.gpu
+
+
+def tol(n):
+    return 1e-6 * math.log2(n)
 
 
 def _free_port():
@@ -125,3 +131,45 @@ def test_slab_2d_real(nx, ny):
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     tol = 1e-6 * math.log2(nx * ny)
     assert len(result) == world and max(result.values()) <= tol, dict(result)
+
+
+def _pow2_devices(torch, cap=8):
+    world = min(cap, torch.cuda.device_count())
+    while world & (world - 1):
+        world -= 1
+    return world
+
+
+@pytest.mark.parametrize("kind,nx,ny", [("c2c", 4096, 4096), ("c2c", 32768, 256), ("c2c", 256, 128), ("r2c", 4096, 2048), ("r2c", 32768, 64)])
+def test_slab_plan_in_c_against_the_oracle(oracle, kind, nx, ny):
+    """include/mufft_cuda.h: mufft_cuda_create_plan_2d_slab_* - the slab transform behind the C ABI, one process
+    driving every visible GPU (a power of two of them; a single GPU still runs the scatter row kernel, the
+    events and the in-place column pass).  Compared with the ORACLE's mufft_execute_plan_2d on the whole array
+    (4096 x 4096: SURVEY.md section 8c), not with a GPU library."""
+    import ctypes as C
+
+    import torch
+
+    import mufft_b200 as m
+    ndev = _pow2_devices(torch)
+    rng = np.random.default_rng(nx + ny)
+    if kind == "c2c":
+        x = (rng.random((ny, nx, 2), np.float32) - np.float32(0.5)).view(np.complex64).reshape(ny, nx)
+        plan = m.mufft_cuda_create_plan_2d_slab_c2c(nx, ny, -1, ndev, None, 0)
+        out = np.full((ny, nx), np.nan, np.complex64)
+        want = oracle.c2c_2d(x, -1)
+    else:
+        x = rng.random((ny, nx), np.float32) - np.float32(0.5)
+        plan = m.mufft_cuda_create_plan_2d_slab_r2c(nx, ny, ndev, None, 0)
+        out = np.full((ny, nx // 2 + 1), np.nan, np.complex64)
+        want = oracle.r2c_2d(x)[:, : nx // 2 + 1]
+    assert plan, m.mufft_cuda_last_error()
+    assert m.mufft_cuda_slab_devices(plan) == ndev
+    first = C.c_uint(0)
+    assert sum(m.mufft_cuda_slab_output_columns(plan, g, C.byref(first)) for g in range(ndev)) == out.shape[1]
+    for _ in range(2):  # the plan is reusable
+        out[...] = np.nan
+        assert m.mufft_cuda_execute_plan_2d_slab_host(plan, out.ctypes.data, x.ctypes.data) == 0, m.mufft_cuda_last_error()
+    assert m.mufft_cuda_slab_last_ms(plan) > 0.0
+    m.mufft_cuda_free_plan_2d_slab(plan)
+    assert rel_l2(out, want) <= tol(nx * ny)
