@@ -1,6 +1,6 @@
 // One translation unit per shape of the single-launch four-step kernel (long_kernel.cuh): compiled with
 // -DLONG_N1=<16|32> -DLONG_N2=<1024|2048>.  Exposes long_launch_<n1>x<n2>(args, stream) and
-// long_ctas_<n1>x<n2>() (scratch slots the launch needs on the current device) to dispatch.cu.
+// long_ctas_<n1>x<n2>() (scratch slots worth allocating on the current device) to dispatch.cu.
 #include "long_kernel.cuh"
 #include "launch_util.cuh"
 
@@ -22,20 +22,25 @@ static cudaError_t launch_long(const mcu_long_args &a, cudaStream_t stream, int 
     return cudaErrorInvalidValue;
   } else {
     static launch_cfg cfg;
-    auto kernel = fft_long_kernel<LONG_N1, LONG_N2, DIR, IN_MODE, TO_PEERS>;
+    constexpr bool SPLIT = long_split(LONG_N1, LONG_N2);
+    constexpr int SLOTS = long_slots_per_cta(LONG_N1, LONG_N2), THREADS = long_launch_threads(LONG_N1, LONG_N2);
+    auto kernel = [] {
+        if constexpr (SPLIT) return fft_long_split_kernel<LONG_N1, LONG_N2, DIR, IN_MODE, TO_PEERS>;
+        else return fft_long_kernel<LONG_N1, LONG_N2, DIR, IN_MODE, TO_PEERS>;
+    }();
     constexpr size_t smem = long_smem_bytes(LONG_N2);
     int resident = 0;
-    cudaError_t err = launch_prepare(cfg, kernel, smem, long_cta_threads(LONG_N2), &resident);
+    cudaError_t err = launch_prepare(cfg, kernel, smem, THREADS, &resident);
     if (err != cudaSuccess) return err;
     if (ctas_only != nullptr) {
-        *ctas_only = resident;
+        *ctas_only = resident * SLOTS; // scratch slots worth allocating
         return cudaSuccess;
     }
     if (a.batch == 0) return cudaSuccess;
     size_t grid = a.batch < (size_t)resident ? a.batch : (size_t)resident;
-    if (a.scratch_slots < grid) grid = a.scratch_slots;
+    if (a.scratch_slots / SLOTS < grid) grid = a.scratch_slots / SLOTS;
     if (grid == 0) return cudaErrorInvalidValue;
-    kernel<<<(unsigned)grid, long_cta_threads(LONG_N2), smem, stream>>>(a);
+    kernel<<<(unsigned)grid, THREADS, smem, stream>>>(a);
     return cudaGetLastError();
   }
 }

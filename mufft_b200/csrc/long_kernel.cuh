@@ -25,8 +25,8 @@
 //   * once a group of rows has been read back, its scratch lines are DISCARDED (discard.global.L2 = drop the
 //     dirty lines from L2 without a write-back): the intermediate never reaches HBM and the live footprint
 //     is half a slot per CTA;
-//   * input loads and output stores carry streaming hints, and the next transform's input is pulled into
-//     L2 by a bulk prefetch while the current one is in step B, so step A's loads find it there.
+//   * input loads and output stores carry streaming hints.  (Pulling the next transform's input into L2 by a
+//     bulk prefetch during step B was measured too and is a loss: it pushes the scratch out.)
 #pragma once
 
 #include "abi.h"
@@ -42,7 +42,7 @@ namespace mufft {
 #define MUFFT_LONG_DISCARD 1
 #endif
 #ifndef MUFFT_LONG_PREFETCH
-#define MUFFT_LONG_PREFETCH 1
+#define MUFFT_LONG_PREFETCH 0
 #endif
 // Drop 128 bytes (aligned) from L2 without writing them back: the data is dead.
 __device__ __forceinline__ void discard_l2_128(const void *p)
@@ -61,7 +61,8 @@ __device__ __forceinline__ void prefetch_l2_bytes(const void *p, unsigned bytes)
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 #endif
 }
-__host__ __device__ constexpr int long_tile_rows(int n2) { (void)n2; return MUFFT_LONG_TR; }
+// 16 rows per group need a 1024-thread CTA and 270 KB of exchange area at n2 = 2048: 8 there
+__host__ __device__ constexpr int long_tile_rows(int n2) { return n2 <= 1024 ? MUFFT_LONG_TR : 8; }
 __host__ __device__ constexpr int long_cta_threads(int n2) { return long_tile_rows(n2) * engine_threads(n2); }
 // Row pitch of the exchange area, in cpx: after the mapping switch a half-warp reads TR rows x 16/TR
 // consecutive elements; pitch = 2 (mod 16) for TR = 8, odd for TR = 16 puts them in 16 different banks.
@@ -79,12 +80,41 @@ __host__ __device__ constexpr bool long_supported(int n1, int n2)
            n2 % long_cta_threads(n2) == 0 && n1 % long_tile_rows(n2) == 0 && long_smem_bytes(n2) <= 227 * 1024 &&
            long_tile_rows(n2) <= 15 + (engine_threads(n2) <= 32 ? 64 : 0); // named barriers 1..15 when a row spans several warps
 }
+// The split kernel (below) runs step A and step B of consecutive transforms side by side on two halves of a CTA;
+// rows that fit one warp only (their exchanges need no named barrier: those are taken by the hand-over).
+#ifndef MUFFT_LONG_SPLIT
+#define MUFFT_LONG_SPLIT 1
+#endif
+__host__ __device__ constexpr bool long_split(int n1, int n2) { return MUFFT_LONG_SPLIT != 0 && long_supported(n1, n2) && engine_threads(n2) <= 32 && 2 * long_cta_threads(n2) <= 1024; }
+// scratch slots a CTA needs, threads it runs with
+__host__ __device__ constexpr int long_slots_per_cta(int n1, int n2) { return long_split(n1, n2) ? 2 : 1; }
+__host__ __device__ constexpr int long_launch_threads(int n1, int n2) { return long_split(n1, n2) ? 2 * long_cta_threads(n2) : long_cta_threads(n2); }
 
-template <int N1, int N2, int DIR, int IN_MODE, bool TO_PEERS>
-__global__ void __launch_bounds__(long_cta_threads(N2), long_cta_threads(N2) <= 256 ? 2 : 1)
-fft_long_kernel(const mcu_long_args a)
+// ---- step A: N1-point transforms down the columns of the [N1][N2] view, `THREADS` threads -------------------
+template <int N1, int N2, int DIR, int IN_MODE, int THREADS>
+__device__ __forceinline__ void long_step_a(const cpx *__restrict__ in, cpx *__restrict__ scratch, const cpx *__restrict__ roots, int tid)
 {
-    constexpr int N = N1 * N2;
+    constexpr int LG = ilog2(N1);
+#pragma unroll 1
+    for (int c = tid; c < N2; c += THREADS) {
+        cpx x[N1];
+#pragma unroll
+        for (int m = 0; m < N1; m++)
+            x[m] = (IN_MODE == MCU_IN_HALF && m >= N1 / 2) ? make_float2(0.0f, 0.0f) : __ldcs(in + c + m * N2); // rows >= N1/2 are the zero half: never read
+        dft_regs<N1, DIR, false>(x);
+        cpx base[LG];
+#pragma unroll
+        for (int j = 0; j < LG; j++) base[j] = __ldg(roots + ((unsigned)c << j));
+        TwTree<N1, LG, LG - 1, 0, true>::run(x, base, make_float2(1.0f, 0.0f));
+#pragma unroll
+        for (int k1 = 0; k1 < N1; k1++) scratch[k1 * N2 + c] = x[k1];
+    }
+}
+
+// ---- step B: N2-point transforms along the rows of Y, TR rows at a time; `sync` = barrier of the THREADS threads
+template <int N1, int N2, int DIR, bool TO_PEERS, typename Sync>
+__device__ __forceinline__ void long_step_b(const mcu_long_args &a, size_t b, cpx *__restrict__ scratch, cpx *smem, const cpx *__restrict__ tw, int tid, Sync sync)
+{
     constexpr int THREADS = long_cta_threads(N2);
     constexpr int R = engine_regs(N2);
     constexpr int T = N2 / R;
@@ -92,41 +122,78 @@ fft_long_kernel(const mcu_long_args a)
     constexpr int NP = engine_num_passes(N2);
     constexpr int SH = engine_pad_shift(N2);
     constexpr int SE = long_row_pitch(N2);
-    constexpr int LG = ilog2(N1);
+    const int slot = tid / T, t = tid - slot * T;   // passes 0 .. NP-2: lanes walk along a row
+    const int slot2 = tid % TR, t2 = tid / TR;      // last pass: lanes walk across the TR rows
+#pragma unroll 1
+    for (int g = 0; g < N1 / TR; g++) {
+        cpx v[R];
+        {
+            const cpx *__restrict__ y = scratch + (size_t)(g * TR + slot) * N2;
+#pragma unroll
+            for (int e = 0; e < R; e++) v[e] = __ldcg(y + t + e * T);
+        }
+        cpx *sm = smem + slot * SE;
+        static_for<NP - 1>([&](auto pc) {
+            constexpr int PASS = decltype(pc)::value;
+            engine_butterflies<N2, DIR, PASS>(v, tw, t);
+            if constexpr (PASS > 0) engine_sync<T, TR>(slot);
+            engine_scatter<N2, PASS, 1>(v, sm, t);
+            if constexpr (PASS + 1 < NP - 1) {
+                engine_sync<T, TR>(slot);
+                engine_gather<N2, 1>(v, sm, t);
+            }
+        });
+        sync();
+        if constexpr (MUFFT_LONG_DISCARD != 0) {
+            // every thread has its part of this group's rows in registers / shared memory: the scratch lines are dead
+            const char *dead = reinterpret_cast<const char *>(scratch + (size_t)g * TR * N2);
+            for (int l = tid; l < TR * N2 * (int)sizeof(cpx) / 128; l += THREADS) discard_l2_128(dead + (size_t)l * 128);
+        }
+        const cpx *sm2 = smem + slot2 * SE;
+#pragma unroll
+        for (int e = 0; e < R; e++) v[e] = sm2[pad_pos<SH>(t2 + e * T)];
+        engine_butterflies<N2, DIR, NP - 1>(v, tw, t2);
+        if constexpr (TO_PEERS) {
+            // exchange step of a slab 2D transform: X[x] goes to the column slab of device x >> shift
+            const size_t row = (a.peers.row0 + b) * a.peers.pitch;
+            const unsigned cmask = (1u << a.peers.shift) - 1u;
+#pragma unroll
+            for (int e = 0; e < R; e++) {
+                const unsigned x = (unsigned)(t2 + e * T) * N1 + g * TR + slot2;
+                static_cast<cpx *>(a.peers.base[x >> a.peers.shift])[row + (x & cmask)] = v[e];
+            }
+        } else {
+            cpx *__restrict__ out = static_cast<cpx *>(a.out) + b * a.out_batch + g * TR + slot2;
+#pragma unroll
+            for (int e = 0; e < R; e++) __stcs(out + (size_t)(t2 + e * T) * N1, v[e]);
+        }
+        sync(); // the exchange area is reused by the next group, the scratch slot by the next transform
+    }
+}
+
+// One CTA = one transform at a time: step A, barrier, step B.
+template <int N1, int N2, int DIR, int IN_MODE, bool TO_PEERS>
+__global__ void __launch_bounds__(long_cta_threads(N2), long_cta_threads(N2) <= 256 ? 2 : 1)
+fft_long_kernel(const mcu_long_args a)
+{
+    constexpr int N = N1 * N2;
+    constexpr int THREADS = long_cta_threads(N2);
     static_assert(long_supported(N1, N2), "shape");
     static_assert(IN_MODE == MCU_IN_COMPLEX || IN_MODE == MCU_IN_HALF, "input modes: complex, zero-padded upper half");
     MUFFT_DYNAMIC_SMEM(smem_raw);
     cpx *smem = reinterpret_cast<cpx *>(smem_raw);
-
     const int tid = threadIdx.x;
-    const int slot = tid / T, t = tid - slot * T;   // step B, passes 0 .. NP-2: lanes walk along a row
-    const int slot2 = tid % TR, t2 = tid / TR;      // step B, last pass: lanes walk across the TR rows
     const cpx *__restrict__ tw = static_cast<const cpx *>(a.tw);
     const cpx *__restrict__ roots = static_cast<const cpx *>(a.roots);
     cpx *__restrict__ scratch = static_cast<cpx *>(a.scratch) + (size_t)blockIdx.x * N;
 
     for (size_t b = blockIdx.x; b < a.batch; b += gridDim.x) {
         const cpx *__restrict__ in = static_cast<const cpx *>(a.in) + b * a.in_batch;
-
-        // ---- step A: N1-point transforms down the columns of the [N1][N2] view ----------------------
-#pragma unroll 1
-        for (int c = tid; c < N2; c += THREADS) {
-            cpx x[N1];
-#pragma unroll
-            for (int m = 0; m < N1; m++)
-                x[m] = (IN_MODE == MCU_IN_HALF && m >= N1 / 2) ? make_float2(0.0f, 0.0f) : __ldcs(in + c + m * N2); // rows >= N1/2 are the zero half: never read
-            dft_regs<N1, DIR, false>(x);
-            cpx base[LG];
-#pragma unroll
-            for (int j = 0; j < LG; j++) base[j] = __ldg(roots + ((unsigned)c << j));
-            TwTree<N1, LG, LG - 1, 0, true>::run(x, base, make_float2(1.0f, 0.0f));
-#pragma unroll
-            for (int k1 = 0; k1 < N1; k1++) scratch[k1 * N2 + c] = x[k1];
-        }
-        __syncthreads(); // Y is complete and visible to the whole CTA (reads below bypass L1)
-
+        long_step_a<N1, N2, DIR, IN_MODE, THREADS>(in, scratch, roots, tid);
+        __syncthreads(); // Y is complete and visible to the whole CTA (the reads of step B bypass L1)
         if constexpr (MUFFT_LONG_PREFETCH != 0) {
-            // the next transform of this CTA: into L2 now, in 16 pieces, so that step A finds it there
+            // the next transform of this CTA: into L2 now, in 16 pieces (measured: a LOSS - 0.54 -> 0.45 of the roofline at
+            // 32768 points, the prefetched lines push scratch and each other out of L2 - hence off by default)
             constexpr unsigned in_bytes = (IN_MODE == MCU_IN_HALF ? N / 2 : N) * sizeof(cpx);
             const size_t nb = b + gridDim.x;
             if (tid < 16 && nb < a.batch) {
@@ -134,51 +201,62 @@ fft_long_kernel(const mcu_long_args a)
                 if ((reinterpret_cast<uintptr_t>(nxt) & 15) == 0) prefetch_l2_bytes(nxt, in_bytes / 16);
             }
         }
-        // ---- step B: N2-point transforms along the rows of Y, TR rows at a time ---------------------
-#pragma unroll 1
-        for (int g = 0; g < N1 / TR; g++) {
-            cpx v[R];
-            {
-                const cpx *__restrict__ y = scratch + (size_t)(g * TR + slot) * N2;
-#pragma unroll
-                for (int e = 0; e < R; e++) v[e] = __ldcg(y + t + e * T);
-            }
-            cpx *sm = smem + slot * SE;
-            static_for<NP - 1>([&](auto pc) {
-                constexpr int PASS = decltype(pc)::value;
-                engine_butterflies<N2, DIR, PASS>(v, tw, t);
-                if constexpr (PASS > 0) engine_sync<T, TR>(slot);
-                engine_scatter<N2, PASS, 1>(v, sm, t);
-                if constexpr (PASS + 1 < NP - 1) {
-                    engine_sync<T, TR>(slot);
-                    engine_gather<N2, 1>(v, sm, t);
-                }
-            });
-            __syncthreads();
-            if constexpr (MUFFT_LONG_DISCARD != 0) {
-                // every thread has its part of this group's rows in registers / shared memory: the scratch lines are dead
-                const char *dead = reinterpret_cast<const char *>(scratch + (size_t)g * TR * N2);
-                for (int l = tid; l < TR * N2 * (int)sizeof(cpx) / 128; l += THREADS) discard_l2_128(dead + (size_t)l * 128);
-            }
-            const cpx *sm2 = smem + slot2 * SE;
-#pragma unroll
-            for (int e = 0; e < R; e++) v[e] = sm2[pad_pos<SH>(t2 + e * T)];
-            engine_butterflies<N2, DIR, NP - 1>(v, tw, t2);
-            if constexpr (TO_PEERS) {
-                // exchange step of a slab 2D transform: X[x] goes to the column slab of device x >> shift
-                const size_t row = (a.peers.row0 + b) * a.peers.pitch;
-                const unsigned cmask = (1u << a.peers.shift) - 1u;
-#pragma unroll
-                for (int e = 0; e < R; e++) {
-                    const unsigned x = (unsigned)(t2 + e * T) * N1 + g * TR + slot2;
-                    static_cast<cpx *>(a.peers.base[x >> a.peers.shift])[row + (x & cmask)] = v[e];
-                }
-            } else {
-                cpx *__restrict__ out = static_cast<cpx *>(a.out) + b * a.out_batch + g * TR + slot2;
-#pragma unroll
-                for (int e = 0; e < R; e++) __stcs(out + (size_t)(t2 + e * T) * N1, v[e]);
-            }
-            __syncthreads(); // the exchange area is reused by the next group, the scratch slot by the next transform
+        long_step_b<N1, N2, DIR, TO_PEERS>(a, b, scratch, smem, tw, tid, [] { __syncthreads(); });
+    }
+}
+
+// Named barriers between / inside the two halves of a split CTA.
+#define LONG_BAR_FULL 1  // +0 / +1: slot filled by the producer half
+#define LONG_BAR_FREE 3  // +0 / +1: slot read out by the consumer half
+#define LONG_BAR_GROUP 5 // the consumer half's own barrier
+__device__ __forceinline__ void named_bar_sync(int id, int count)
+{
+#ifdef MUFFT_EMU
+    emu::bar_sync(id, count);
+#else
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count)
+{
+#ifdef MUFFT_EMU
+    emu::bar_arrive(id, count);
+#else
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+}
+
+// One CTA = two transforms in flight: the lower half of the threads (producers) runs step A of transform j + 1 -
+// pure streaming: coalesced HBM loads, a register butterfly, coalesced stores into one of the CTA's TWO scratch
+// slots - while the upper half (consumers) runs step B of transform j out of the other slot.  The HBM read stream
+// never pauses for the shared-memory phases and the other way round; ncu on the one-transform-at-a-time kernel
+// (profiles/r02c_long32768.txt) had shown half of all stall samples waiting for loads with the issue slots 31 % busy.
+// Hand-over by named barriers: FULL[s] (producers arrive, consumers wait), FREE[s] (consumers arrive, producers wait).
+template <int N1, int N2, int DIR, int IN_MODE, bool TO_PEERS>
+__global__ void __launch_bounds__(2 * long_cta_threads(N2), 1)
+fft_long_split_kernel(const mcu_long_args a)
+{
+    constexpr int N = N1 * N2;
+    constexpr int GT = long_cta_threads(N2); // threads per half (the launcher only picks this kernel when long_split(N1, N2))
+    MUFFT_DYNAMIC_SMEM(smem_raw);
+    cpx *smem = reinterpret_cast<cpx *>(smem_raw);
+    const bool producer = threadIdx.x < GT;
+    const int tid = producer ? threadIdx.x : threadIdx.x - GT;
+    const cpx *__restrict__ tw = static_cast<const cpx *>(a.tw);
+    const cpx *__restrict__ roots = static_cast<const cpx *>(a.roots);
+    cpx *__restrict__ slots = static_cast<cpx *>(a.scratch) + (size_t)blockIdx.x * 2 * N;
+
+    unsigned j = 0;
+    for (size_t b = blockIdx.x; b < a.batch; b += gridDim.x, j++) {
+        cpx *__restrict__ scratch = slots + (size_t)(j & 1) * N;
+        if (producer) {
+            if (j >= 2) named_bar_sync(LONG_BAR_FREE + (j & 1), 2 * GT); // transform j - 2 has been read out of this slot
+            long_step_a<N1, N2, DIR, IN_MODE, GT>(static_cast<const cpx *>(a.in) + b * a.in_batch, scratch, roots, tid);
+            named_bar_arrive(LONG_BAR_FULL + (j & 1), 2 * GT);
+        } else {
+            named_bar_sync(LONG_BAR_FULL + (j & 1), 2 * GT); // Y is complete and visible (the reads of step B bypass L1)
+            long_step_b<N1, N2, DIR, TO_PEERS>(a, b, scratch, smem, tw, tid, [] { named_bar_sync(LONG_BAR_GROUP, GT); });
+            if (b + 2 * (size_t)gridDim.x < a.batch) named_bar_arrive(LONG_BAR_FREE + (j & 1), 2 * GT); // only if a producer will wait for it
         }
     }
 }

@@ -18,6 +18,7 @@
 #include "abi.h"
 
 #include <math.h>
+#include <pthread.h>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -134,11 +135,58 @@ const char *mufft_cuda_last_error(void) { return tls_error; }
 unsigned long long mufft_cuda_launch_count(int reset) { return mcu_launch_count(reset); }
 
 /* ---- memory (ref fft.c:1032-1084) ----------------------------------------------------------- */
+/* Live allocations made through this library (mufft_alloc / mufft_calloc / mufft_cuda_device_alloc): the kind of
+ * memory of a pointer inside one of them is known without asking the driver.  cudaPointerGetAttributes costs
+ * about a microsecond per pointer, a fifth of a small synchronous call (tools/latency_probe.cu); the reference's
+ * callers hand in mufft_alloc memory (test.c:33-62, bench.c:203-219), so the common case never pays it.
+ * Foreign pointers (cudaMalloc, torch, plain host memory) are not in the table and are classified by the driver. */
+#define REGISTRY_MAX 512
+static struct { uintptr_t base; size_t size; int kind; } g_registry[REGISTRY_MAX];
+static int g_registry_count = 0;
+static pthread_rwlock_t g_registry_lock = PTHREAD_RWLOCK_INITIALIZER;
+
+static void registry_add(void *ptr, size_t size, int kind)
+{
+    pthread_rwlock_wrlock(&g_registry_lock);
+    if (g_registry_count < REGISTRY_MAX) {
+        g_registry[g_registry_count].base = (uintptr_t)ptr;
+        g_registry[g_registry_count].size = size ? size : 1;
+        g_registry[g_registry_count].kind = kind;
+        g_registry_count++;
+    }
+    pthread_rwlock_unlock(&g_registry_lock);
+}
+
+static void registry_remove(void *ptr)
+{
+    pthread_rwlock_wrlock(&g_registry_lock);
+    for (int i = 0; i < g_registry_count; i++)
+        if (g_registry[i].base == (uintptr_t)ptr) {
+            g_registry[i] = g_registry[--g_registry_count];
+            break;
+        }
+    pthread_rwlock_unlock(&g_registry_lock);
+}
+
+static int pointer_kind(const void *ptr)
+{
+    int kind = -1;
+    pthread_rwlock_rdlock(&g_registry_lock);
+    for (int i = 0; i < g_registry_count; i++)
+        if ((uintptr_t)ptr - g_registry[i].base < g_registry[i].size) {
+            kind = g_registry[i].kind;
+            break;
+        }
+    pthread_rwlock_unlock(&g_registry_lock);
+    return kind >= 0 ? kind : mcu_pointer_kind(ptr);
+}
+
 void *mufft_alloc(size_t size)
 {
     void *ptr = NULL;
     if (!have_device()) return NULL;
     if (fail(mcu_malloc_managed(&ptr, size), "cudaMallocManaged") != 0) return NULL;
+    registry_add(ptr, size, MCU_MEM_MANAGED);
     return ptr;
 }
 
@@ -151,7 +199,9 @@ void *mufft_calloc(size_t size)
 
 void mufft_free(void *ptr)
 {
-    if (ptr != NULL) (void)mcu_free(ptr);
+    if (ptr == NULL) return;
+    registry_remove(ptr);
+    (void)mcu_free(ptr);
 }
 
 static int is_pow2_ge2(unsigned n) { return n >= 2 && (n & (n - 1)) == 0; }
@@ -427,13 +477,13 @@ static int run_any(stage *st, unit_launch fn, void *ctx, const io_desc *io, int 
      * side of R2C / C2R, e.g. a float array on the caller's stack; the reference's scalar path accepts
      * it) cannot be used in place, whatever memory it is.  It takes the staged path below, whose
      * copies have no alignment rule. */
-    const int kind_in = mcu_pointer_kind(io->in), kind_out = mcu_pointer_kind(io->out);
+    const int kind_in = pointer_kind(io->in), kind_out = pointer_kind(io->out);
     const int vis_in = ALIGNED(io->in) && device_visible(kind_in, span_in);
     const int vis_out = ALIGNED(io->out) && device_visible(kind_out, span_out);
     int vis_in2 = 1;
     if (io->in2) {
         size_t span2 = io->in2_stride ? io->in2_stride * (io->count - 1) + io->in2_unit : io->in2_unit;
-        vis_in2 = ALIGNED(io->in2) && device_visible(mcu_pointer_kind(io->in2), span2);
+        vis_in2 = ALIGNED(io->in2) && device_visible(pointer_kind(io->in2), span2);
     }
 
     if (vis_in && vis_out && vis_in2) {
@@ -694,8 +744,8 @@ static int run_long_core(const axis *ax, scratch *scr, void *dst, size_t dst_str
         *where = dst;
     }
     if (ax->long_n2 != 0) {
-        size_t slots = mcu_long_ctas(n);
-        if (slots > cnt) slots = cnt;
+        size_t slots = mcu_long_ctas(n); /* resident CTAs x slots per CTA (two when the CTA runs two transforms side by side) */
+        if (slots > 2 * cnt) slots = 2 * cnt;
         if (slots == 0) return set_error("four-step kernel: no resident CTA on this device");
         TRY(grow(&scr->slots, &scr->slots_bytes, slots * n * CPX));
         mcu_long_args la;
@@ -846,7 +896,7 @@ int mufft_execute_plan_1d_batch_scatter_async(mufft_plan_1d *plan, void *const *
     /* plan->n complex points per row either way (an R2C row of N reals is N/2 complex) */
     const size_t in_stride = input_stride_bytes ? input_stride_bytes : (size_t)plan->n * CPX;
     if (batch == 0) return 0;
-    if (!device_visible(mcu_pointer_kind(input), in_stride * (batch - 1) + (size_t)plan->n * CPX)) {
+    if (!device_visible(pointer_kind(input), in_stride * (batch - 1) + (size_t)plan->n * CPX)) {
         return set_error("scatter: needs device-accessible (device or managed) pointers");
     }
     mcu_peer_dest d;
@@ -870,9 +920,15 @@ void *mufft_cuda_device_alloc(size_t size)
     void *ptr = NULL;
     if (!have_device()) return NULL;
     if (fail(mcu_malloc(&ptr, size), "cudaMalloc") != 0) return NULL;
+    registry_add(ptr, size, MCU_MEM_DEVICE);
     return ptr;
 }
-void mufft_cuda_device_free(void *ptr) { (void)mcu_free(ptr); }
+void mufft_cuda_device_free(void *ptr)
+{
+    if (ptr == NULL) return;
+    registry_remove(ptr);
+    (void)mcu_free(ptr);
+}
 int mufft_cuda_copy(void *dst, const void *src, size_t bytes)
 {
     TRY(mcu_copy_async(dst, src, bytes, tls_stream));
@@ -910,7 +966,7 @@ int mufft_execute_plan_1d_columns(mufft_plan_1d *plan, void *output, const void 
     if (stage_check_device(&plan->st) != 0) return -1;
     const size_t span_in = input_pitch_bytes * ((size_t)plan->n - 1) + width * CPX;
     const size_t span_out = output_pitch_bytes * ((size_t)plan->n - 1) + width * CPX;
-    if (!device_visible(mcu_pointer_kind(input), span_in) || !device_visible(mcu_pointer_kind(output), span_out)) {
+    if (!device_visible(pointer_kind(input), span_in) || !device_visible(pointer_kind(output), span_out)) {
         return set_error("columns: needs device-accessible (device or managed) pointers");
     }
     if (plan->ax_cols.n == 0 && axis_init(&plan->ax_cols, plan->n, plan->direction, plan->n > MCU_COLS_MAX_N ? AXIS_COLS : 0, plan->flags) != 0)
@@ -1116,10 +1172,10 @@ static int conv_partitioned(mufft_plan_conv *plan, void *output, const void *spe
     }
     /* the history blocks in front of `spectra` are read too: classify the whole range */
     const char *first = (const char *)spectra - (size_t)(parts - 1) * blk;
-    if (!device_visible(mcu_pointer_kind(first), (batch + parts - 1) * blk) ||
-        !device_visible(mcu_pointer_kind(spectra), batch * blk) ||
-        !device_visible(mcu_pointer_kind(filter_spectra), (size_t)parts * blk) ||
-        !device_visible(mcu_pointer_kind(output), batch * out_unit)) {
+    if (!device_visible(pointer_kind(first), (batch + parts - 1) * blk) ||
+        !device_visible(pointer_kind(spectra), batch * blk) ||
+        !device_visible(pointer_kind(filter_spectra), (size_t)parts * blk) ||
+        !device_visible(pointer_kind(output), batch * out_unit)) {
         return set_error("partitioned convolution needs device-accessible (device or managed) pointers");
     }
     part_desc pd = { parts, -(long long)(blk / CPX), (long long)(blk / CPX) };

@@ -47,6 +47,16 @@ struct Barrier {
     std::mutex m;
     std::condition_variable cv;
     unsigned waiting = 0, generation = 0;
+    // bar.arrive: counts as a participant of the current phase but does not wait for it to complete
+    void arrive(unsigned count)
+    {
+        std::unique_lock<std::mutex> lock(m);
+        if (++waiting == count) {
+            waiting = 0;
+            generation++;
+            cv.notify_all();
+        }
+    }
     void sync(unsigned count)
     {
         std::unique_lock<std::mutex> lock(m);
@@ -96,6 +106,7 @@ inline T *static_smem(unsigned count)
 }
 
 inline void bar_sync(unsigned id, unsigned count) { t_cta->named[id].sync(count); }
+inline void bar_arrive(unsigned id, unsigned count) { t_cta->named[id].arrive(count); }
 inline void sync_threads() { t_cta->named[0].sync(t_cta->threads); }
 inline void sync_warp()
 {

@@ -153,7 +153,7 @@ int mcu_launch_rows(const mcu_rows_args *a, void *)
 // single-launch four-step rows: 3 "resident" CTAs walk the batch
 static unsigned long_n1_of(unsigned n) { return n == 16384 ? 16 : (n == 32768 || n == 65536 ? 32 : 0); }
 unsigned mcu_long_n2(unsigned n) { return long_n1_of(n) ? n / long_n1_of(n) : 0; }
-unsigned mcu_long_ctas(unsigned n) { return long_n1_of(n) ? 3 : 0; }
+unsigned mcu_long_ctas(unsigned n) { return long_n1_of(n) ? 3 * 2 : 0; } // 3 CTAs, up to two slots each
 int mcu_launch_long(const mcu_long_args *a, void *)
 {
     g_launches++;

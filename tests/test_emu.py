@@ -393,7 +393,8 @@ def test_four_step_rows(emu, host, oracle, n1, n2, case):
     tw = engine_table(host, n2, direction)
     j = np.arange(n, dtype=np.float64)
     roots = (np.cos(2 * np.pi * direction * j / n).astype(np.float32) + 1j * np.sin(2 * np.pi * direction * j / n).astype(np.float32)).astype(np.complex64)
-    scratch = np.full((ctas, n), np.nan, np.complex64)
+    spc = getattr(emu, f"emu_long_slots_per_cta_{n1}x{n2}")()  # 2: the split kernel (two transforms in flight per CTA)
+    scratch = np.full((ctas * spc, n), np.nan, np.complex64)
     in_len = n // 2 if case == "zero_pad" else n
     in_stride, out_stride = in_len + 8, n + 4
     xbuf = np.full((batch, in_stride), np.nan, np.complex64)
@@ -401,7 +402,7 @@ def test_four_step_rows(emu, host, oracle, n1, n2, case):
     x = np.zeros((batch, n), np.complex128)
     x[:, :in_len] = xbuf[:, :in_len]
     want = np.fft.fft(x, axis=1) if direction < 0 else np.fft.ifft(x, axis=1, norm="forward")
-    a = ArgsLong(in_=xbuf.ctypes.data, tw=tw.ctypes.data, roots=roots.ctypes.data, scratch=scratch.ctypes.data, scratch_slots=ctas,
+    a = ArgsLong(in_=xbuf.ctypes.data, tw=tw.ctypes.data, roots=roots.ctypes.data, scratch=scratch.ctypes.data, scratch_slots=ctas * spc,
                  in_batch=in_stride, batch=batch, n=n, n1=n1, n2=n2, direction=direction, in_mode=IN_HALF if case == "zero_pad" else IN_COMPLEX)
     if case == "peers":
         peers, row0, rows_total = 8, 1, 7
