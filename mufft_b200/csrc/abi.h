@@ -226,6 +226,12 @@ int mcu_event_elapsed_ms(float *ms, void *start, void *end); /* both recorded on
 /* lets kernels and copies of the current device address memory of `peer_device` (NVLink / PCIe peer to peer);
  * already enabled = success */
 int mcu_enable_peer_access(int peer_device);
+/* CUDA graphs for the latency path: everything enqueued on `stream` between begin and end becomes an executable
+ * graph (*exec); replaying it costs one driver call however many nodes it has. */
+int mcu_capture_begin(void *stream);
+int mcu_capture_end(void *stream, void **exec); /* also ends a capture that failed; *exec = NULL then */
+int mcu_graph_launch(void *exec, void *stream);
+int mcu_graph_destroy(void *exec);
 int mcu_copy_async(void *dst, const void *src, size_t bytes, void *stream);
 int mcu_copy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t rows, void *stream);
 int mcu_prefetch(const void *ptr, size_t bytes, int to_device, void *stream);
@@ -262,6 +268,7 @@ size_t mcu_engine_table_size(unsigned n, int variant);
 void mcu_engine_table_fill(float *table, unsigned n, int direction, int variant);
 /* number of kernel launches issued through mcu_launch_* since the last reset (for bench.py) */
 unsigned long long mcu_launch_count(int reset);
+void mcu_launch_count_add(unsigned long long n); /* launches replayed from a graph */
 
 #ifdef __cplusplus
 }

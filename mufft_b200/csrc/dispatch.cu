@@ -160,6 +160,28 @@ int mcu_enable_peer_access(int peer_device)
     }
     return (int)err;
 }
+int mcu_capture_begin(void *stream) { return (int)cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal); }
+int mcu_capture_end(void *stream, void **exec)
+{
+    cudaGraph_t graph = nullptr;
+    *exec = nullptr;
+    cudaError_t err = cudaStreamEndCapture((cudaStream_t)stream, &graph);
+    if (err != cudaSuccess || graph == nullptr) {
+        (void)cudaGetLastError();
+        return err != cudaSuccess ? (int)err : (int)cudaErrorStreamCaptureInvalidated;
+    }
+    cudaGraphExec_t ge = nullptr;
+    err = cudaGraphInstantiate(&ge, graph, 0);
+    (void)cudaGraphDestroy(graph);
+    if (err != cudaSuccess) {
+        (void)cudaGetLastError();
+        return (int)err;
+    }
+    *exec = (void *)ge;
+    return 0;
+}
+int mcu_graph_launch(void *exec, void *stream) { return (int)cudaGraphLaunch((cudaGraphExec_t)exec, (cudaStream_t)stream); }
+int mcu_graph_destroy(void *exec) { return exec ? (int)cudaGraphExecDestroy((cudaGraphExec_t)exec) : 0; }
 int mcu_copy_async(void *dst, const void *src, size_t bytes, void *stream)
 {
     if (bytes == 0) return 0;
@@ -327,6 +349,7 @@ int mcu_launch_resolve(const mcu_resolve_args *a, void *stream)
     return (int)cudaGetLastError();
 }
 
+void mcu_launch_count_add(unsigned long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 unsigned long long mcu_launch_count(int reset)
 {
     return reset ? g_launches.exchange(0) : g_launches.load();

@@ -22,12 +22,8 @@ static cudaError_t launch_long(const mcu_long_args &a, cudaStream_t stream, int 
     return cudaErrorInvalidValue;
   } else {
     static launch_cfg cfg;
-    constexpr bool SPLIT = long_split(LONG_N1, LONG_N2);
-    constexpr int SLOTS = long_slots_per_cta(LONG_N1, LONG_N2), THREADS = long_launch_threads(LONG_N1, LONG_N2);
-    auto kernel = [] {
-        if constexpr (SPLIT) return fft_long_split_kernel<LONG_N1, LONG_N2, DIR, IN_MODE, TO_PEERS>;
-        else return fft_long_kernel<LONG_N1, LONG_N2, DIR, IN_MODE, TO_PEERS>;
-    }();
+    constexpr int SLOTS = 1, THREADS = long_cta_threads(LONG_N2);
+    auto kernel = fft_long_kernel<LONG_N1, LONG_N2, DIR, IN_MODE, TO_PEERS>;
     constexpr size_t smem = long_smem_bytes(LONG_N2);
     int resident = 0;
     cudaError_t err = launch_prepare(cfg, kernel, smem, THREADS, &resident);

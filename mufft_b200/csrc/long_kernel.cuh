@@ -26,7 +26,7 @@
 //     dirty lines from L2 without a write-back): the intermediate never reaches HBM and the live footprint
 //     is half a slot per CTA;
 //   * input loads and output stores carry streaming hints.  (Pulling the next transform's input into L2 by a
-//     bulk prefetch during step B was measured too and is a loss: it pushes the scratch out.)
+//     bulk prefetch during step B was measured too and is a loss, 0.54 -> 0.45: it pushes the scratch out.)
 #pragma once
 
 #include "abi.h"
@@ -38,12 +38,6 @@ namespace mufft {
 #ifndef MUFFT_LONG_TR
 #define MUFFT_LONG_TR 8 // rows per group of step B (8: 64-byte output runs; 16: 128-byte runs, twice the CTA)
 #endif
-#ifndef MUFFT_LONG_DISCARD
-#define MUFFT_LONG_DISCARD 1
-#endif
-#ifndef MUFFT_LONG_PREFETCH
-#define MUFFT_LONG_PREFETCH 0
-#endif
 // Drop 128 bytes (aligned) from L2 without writing them back: the data is dead.
 __device__ __forceinline__ void discard_l2_128(const void *p)
 {
@@ -51,14 +45,6 @@ __device__ __forceinline__ void discard_l2_128(const void *p)
     (void)p;
 #else
     asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
-#endif
-}
-__device__ __forceinline__ void prefetch_l2_bytes(const void *p, unsigned bytes) // 16-byte aligned, a multiple of 16
-{
-#ifdef MUFFT_EMU
-    (void)p; (void)bytes;
-#else
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 #endif
 }
 // 16 rows per group need a 1024-thread CTA and 270 KB of exchange area at n2 = 2048: 8 there
@@ -80,16 +66,6 @@ __host__ __device__ constexpr bool long_supported(int n1, int n2)
            n2 % long_cta_threads(n2) == 0 && n1 % long_tile_rows(n2) == 0 && long_smem_bytes(n2) <= 227 * 1024 &&
            long_tile_rows(n2) <= 15 + (engine_threads(n2) <= 32 ? 64 : 0); // named barriers 1..15 when a row spans several warps
 }
-// The split kernel (below) runs step A and step B of consecutive transforms side by side on two halves of a CTA;
-// rows that fit one warp only (their exchanges need no named barrier: those are taken by the hand-over).
-#ifndef MUFFT_LONG_SPLIT
-#define MUFFT_LONG_SPLIT 1
-#endif
-__host__ __device__ constexpr bool long_split(int n1, int n2) { return MUFFT_LONG_SPLIT != 0 && long_supported(n1, n2) && engine_threads(n2) <= 32 && 2 * long_cta_threads(n2) <= 1024; }
-// scratch slots a CTA needs, threads it runs with
-__host__ __device__ constexpr int long_slots_per_cta(int n1, int n2) { return long_split(n1, n2) ? 2 : 1; }
-__host__ __device__ constexpr int long_launch_threads(int n1, int n2) { return long_split(n1, n2) ? 2 * long_cta_threads(n2) : long_cta_threads(n2); }
-
 // ---- step A: N1-point transforms down the columns of the [N1][N2] view, `THREADS` threads -------------------
 template <int N1, int N2, int DIR, int IN_MODE, int THREADS>
 __device__ __forceinline__ void long_step_a(const cpx *__restrict__ in, cpx *__restrict__ scratch, const cpx *__restrict__ roots, int tid)
@@ -144,8 +120,9 @@ __device__ __forceinline__ void long_step_b(const mcu_long_args &a, size_t b, cp
             }
         });
         sync();
-        if constexpr (MUFFT_LONG_DISCARD != 0) {
+        {
             // every thread has its part of this group's rows in registers / shared memory: the scratch lines are dead
+            // (measured at 32768 points: 0.375 -> 0.54 of the HBM roofline with the discard)
             const char *dead = reinterpret_cast<const char *>(scratch + (size_t)g * TR * N2);
             for (int l = tid; l < TR * N2 * (int)sizeof(cpx) / 128; l += THREADS) discard_l2_128(dead + (size_t)l * 128);
         }
@@ -171,7 +148,11 @@ __device__ __forceinline__ void long_step_b(const mcu_long_args &a, size_t b, cp
     }
 }
 
-// One CTA = one transform at a time: step A, barrier, step B.
+// One CTA = one transform at a time: step A, barrier, step B; two CTAs of 256 threads per SM drift against each other.
+// (A variant with step A of transform j + 1 and step B of transform j on two halves of a 512-thread CTA - producer /
+// consumer hand-over by named barriers, two scratch slots per CTA - measured the same 0.54 of the roofline at 32768
+// points as this kernel with 8 or 16 rows per group: with ~110 registers per thread an SM holds 16 warps whichever way
+// they are arranged, and ncu shows them waiting for loads a third of the time.  profiles/README.md keeps the numbers.)
 template <int N1, int N2, int DIR, int IN_MODE, bool TO_PEERS>
 __global__ void __launch_bounds__(long_cta_threads(N2), long_cta_threads(N2) <= 256 ? 2 : 1)
 fft_long_kernel(const mcu_long_args a)
@@ -191,73 +172,7 @@ fft_long_kernel(const mcu_long_args a)
         const cpx *__restrict__ in = static_cast<const cpx *>(a.in) + b * a.in_batch;
         long_step_a<N1, N2, DIR, IN_MODE, THREADS>(in, scratch, roots, tid);
         __syncthreads(); // Y is complete and visible to the whole CTA (the reads of step B bypass L1)
-        if constexpr (MUFFT_LONG_PREFETCH != 0) {
-            // the next transform of this CTA: into L2 now, in 16 pieces (measured: a LOSS - 0.54 -> 0.45 of the roofline at
-            // 32768 points, the prefetched lines push scratch and each other out of L2 - hence off by default)
-            constexpr unsigned in_bytes = (IN_MODE == MCU_IN_HALF ? N / 2 : N) * sizeof(cpx);
-            const size_t nb = b + gridDim.x;
-            if (tid < 16 && nb < a.batch) {
-                const char *nxt = reinterpret_cast<const char *>(static_cast<const cpx *>(a.in) + nb * a.in_batch) + (size_t)tid * (in_bytes / 16);
-                if ((reinterpret_cast<uintptr_t>(nxt) & 15) == 0) prefetch_l2_bytes(nxt, in_bytes / 16);
-            }
-        }
         long_step_b<N1, N2, DIR, TO_PEERS>(a, b, scratch, smem, tw, tid, [] { __syncthreads(); });
-    }
-}
-
-// Named barriers between / inside the two halves of a split CTA.
-#define LONG_BAR_FULL 1  // +0 / +1: slot filled by the producer half
-#define LONG_BAR_FREE 3  // +0 / +1: slot read out by the consumer half
-#define LONG_BAR_GROUP 5 // the consumer half's own barrier
-__device__ __forceinline__ void named_bar_sync(int id, int count)
-{
-#ifdef MUFFT_EMU
-    emu::bar_sync(id, count);
-#else
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-#endif
-}
-__device__ __forceinline__ void named_bar_arrive(int id, int count)
-{
-#ifdef MUFFT_EMU
-    emu::bar_arrive(id, count);
-#else
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-#endif
-}
-
-// One CTA = two transforms in flight: the lower half of the threads (producers) runs step A of transform j + 1 -
-// pure streaming: coalesced HBM loads, a register butterfly, coalesced stores into one of the CTA's TWO scratch
-// slots - while the upper half (consumers) runs step B of transform j out of the other slot.  The HBM read stream
-// never pauses for the shared-memory phases and the other way round; ncu on the one-transform-at-a-time kernel
-// (profiles/r02c_long32768.txt) had shown half of all stall samples waiting for loads with the issue slots 31 % busy.
-// Hand-over by named barriers: FULL[s] (producers arrive, consumers wait), FREE[s] (consumers arrive, producers wait).
-template <int N1, int N2, int DIR, int IN_MODE, bool TO_PEERS>
-__global__ void __launch_bounds__(2 * long_cta_threads(N2), 1)
-fft_long_split_kernel(const mcu_long_args a)
-{
-    constexpr int N = N1 * N2;
-    constexpr int GT = long_cta_threads(N2); // threads per half (the launcher only picks this kernel when long_split(N1, N2))
-    MUFFT_DYNAMIC_SMEM(smem_raw);
-    cpx *smem = reinterpret_cast<cpx *>(smem_raw);
-    const bool producer = threadIdx.x < GT;
-    const int tid = producer ? threadIdx.x : threadIdx.x - GT;
-    const cpx *__restrict__ tw = static_cast<const cpx *>(a.tw);
-    const cpx *__restrict__ roots = static_cast<const cpx *>(a.roots);
-    cpx *__restrict__ slots = static_cast<cpx *>(a.scratch) + (size_t)blockIdx.x * 2 * N;
-
-    unsigned j = 0;
-    for (size_t b = blockIdx.x; b < a.batch; b += gridDim.x, j++) {
-        cpx *__restrict__ scratch = slots + (size_t)(j & 1) * N;
-        if (producer) {
-            if (j >= 2) named_bar_sync(LONG_BAR_FREE + (j & 1), 2 * GT); // transform j - 2 has been read out of this slot
-            long_step_a<N1, N2, DIR, IN_MODE, GT>(static_cast<const cpx *>(a.in) + b * a.in_batch, scratch, roots, tid);
-            named_bar_arrive(LONG_BAR_FULL + (j & 1), 2 * GT);
-        } else {
-            named_bar_sync(LONG_BAR_FULL + (j & 1), 2 * GT); // Y is complete and visible (the reads of step B bypass L1)
-            long_step_b<N1, N2, DIR, TO_PEERS>(a, b, scratch, smem, tw, tid, [] { named_bar_sync(LONG_BAR_GROUP, GT); });
-            if (b + 2 * (size_t)gridDim.x < a.batch) named_bar_arrive(LONG_BAR_FREE + (j & 1), 2 * GT); // only if a producer will wait for it
-        }
     }
 }
 

@@ -69,6 +69,8 @@ __attribute__((constructor)) static void read_env(void)
  * stream in front of the kernel - bulk migration instead of page fault by page fault (measured: 1.00 -> 0.77 ms
  * for one 65536-point transform, 165 -> 145 ms for a 4096 x 4096 image, profiles/r02a_probes.jsonl). */
 #define MANAGED_PREFETCH_MIN ((size_t)256 << 10)
+/* Synchronous calls that touch at most this many bytes of device-visible memory may be replayed from a CUDA graph */
+#define GRAPH_MAX_BYTES ((size_t)1 << 20)
 /* Path flags of mufft_cuda.h that a plan keeps */
 #define PATH_FLAGS (MUFFT_CUDA_FLAG_SEPARATE_2D | MUFFT_CUDA_FLAG_TWO_KERNEL | MUFFT_CUDA_FLAG_GENERIC_PASSES | MUFFT_CUDA_FLAG_FOUR_STEP_16K)
 
@@ -388,6 +390,15 @@ typedef struct stage {
     void *ev_kernels;   /* recorded after the kernels of each chunk: the next chunk's kernels wait for it */
     int ready;
     int device_plus_1;  /* device the owning plan's tables and scratch live on (0 = not bound to a plan) */
+    /* latency path: the last small synchronous call on device-visible memory, as an executable CUDA graph */
+    struct {
+        void *exec, *capture_stream;
+        const void *in, *in2;
+        void *out;
+        size_t count, in_stride, out_stride, in2_stride;
+        unsigned long long launches; /* kernel launches inside the graph (mufft_cuda_launch_count counts them per replay) */
+        int key, seen, disabled;
+    } graph;
 } stage;
 
 /* A plan belongs to the device that was current when it was created: its twiddle tables, scratch and
@@ -429,6 +440,8 @@ static void stage_free(stage *st)
         mcu_free(st->slot[i].d_out);
     }
     mcu_free(st->d_shared);
+    mcu_graph_destroy(st->graph.exec);
+    mcu_stream_destroy(st->graph.capture_stream);
     mcu_event_destroy(st->ev_begin);
     mcu_event_destroy(st->ev_kernels);
     memset(st, 0, sizeof(*st));
@@ -467,7 +480,7 @@ static int copy_units(void *dst, size_t dpitch, const void *src, size_t spitch, 
 /* Chunked, pipelined host<->device staging: slot s handles chunks s, s+SLOTS, ... on its own
  * stream (copy in, kernels, copy out), so the copies of one chunk overlap the kernels and the
  * opposite-direction copies of its neighbours. */
-static int run_any(stage *st, unit_launch fn, void *ctx, const io_desc *io, int async)
+static int run_any(stage *st, unit_launch fn, void *ctx, const io_desc *io, int async, int graph_key)
 {
     if (io->count == 0) return 0;
     if (stage_check_device(st) != 0) return -1;
@@ -491,6 +504,53 @@ static int run_any(stage *st, unit_launch fn, void *ctx, const io_desc *io, int 
         const int pf_out = !async && kind_out == MCU_MEM_MANAGED && span_out >= MANAGED_PREFETCH_MIN;
         if (pf_in) (void)mcu_prefetch(io->in, span_in, 1, tls_stream);   /* advisory: errors are ignored */
         if (pf_out) (void)mcu_prefetch(io->out, span_out, 1, tls_stream);
+        /* Latency path (BASELINE configs[0]: one small transform per fft.h call).  Such a call is
+         * launch-bound: on the measured box a bare kernel launch + cudaStreamSynchronize is 8.7 us, the same launch
+         * replayed from a CUDA graph 6.8 us (tools/latency_probe.cu, profiles/r02d_latency.jsonl).  The second time a
+         * small synchronous call comes with the same pointers it is captured into a graph, from then on replayed. */
+        if (!async && graph_key != 0 && !st->graph.disabled && span_in + span_out <= GRAPH_MAX_BYTES) {
+            const int same = st->graph.key == graph_key && st->graph.in == io->in && st->graph.in2 == io->in2 &&
+                             st->graph.out == io->out && st->graph.count == io->count && st->graph.in_stride == io->in_stride &&
+                             st->graph.out_stride == io->out_stride && st->graph.in2_stride == io->in2_stride;
+            if (same && st->graph.exec != NULL) {
+                mcu_launch_count_add(st->graph.launches);
+                TRY(mcu_graph_launch(st->graph.exec, tls_stream));
+                TRY(mcu_stream_sync(tls_stream));
+                return 0;
+            }
+            if (same && st->graph.seen >= 1) {
+                /* second identical call (the first ran uncaptured and did every allocation / attribute call): capture */
+                int ok = st->graph.capture_stream != NULL || mcu_stream_create(&st->graph.capture_stream) == 0;
+                if (ok && mcu_capture_begin(st->graph.capture_stream) == 0) {
+                    const unsigned long long before = mcu_launch_count(0);
+                    const int err = fn(ctx, io->out, io->out_stride, io->in, io->in_stride, io->in2, io->in2_stride, io->count, st->graph.capture_stream);
+                    void *exec = NULL;
+                    ok = mcu_capture_end(st->graph.capture_stream, &exec) == 0 && err == 0 && exec != NULL;
+                    if (ok) {
+                        mcu_graph_destroy(st->graph.exec);
+                        st->graph.exec = exec;
+                        st->graph.launches = mcu_launch_count(0) - before;
+                        TRY(mcu_graph_launch(st->graph.exec, tls_stream));
+                        TRY(mcu_stream_sync(tls_stream));
+                        return 0;
+                    }
+                    mcu_graph_destroy(exec);
+                } else {
+                    ok = 0;
+                }
+                if (!ok) {
+                    st->graph.disabled = 1; /* this path cannot be captured: never try again, run it the ordinary way */
+                    tls_error[0] = 0;
+                }
+            } else if (!same) {
+                mcu_graph_destroy(st->graph.exec);
+                st->graph.exec = NULL;
+                st->graph.key = graph_key; st->graph.in = io->in; st->graph.in2 = io->in2; st->graph.out = io->out; st->graph.count = io->count;
+                st->graph.in_stride = io->in_stride; st->graph.out_stride = io->out_stride; st->graph.in2_stride = io->in2_stride;
+                st->graph.seen = 0;
+            }
+            st->graph.seen++;
+        }
         TRY(fn(ctx, io->out, io->out_stride, io->in, io->in_stride, io->in2, io->in2_stride, io->count, tls_stream));
         if (!async) TRY(mcu_stream_sync(tls_stream));
         return 0;
@@ -744,8 +804,8 @@ static int run_long_core(const axis *ax, scratch *scr, void *dst, size_t dst_str
         *where = dst;
     }
     if (ax->long_n2 != 0) {
-        size_t slots = mcu_long_ctas(n); /* resident CTAs x slots per CTA (two when the CTA runs two transforms side by side) */
-        if (slots > 2 * cnt) slots = 2 * cnt;
+        size_t slots = mcu_long_ctas(n); /* one per resident CTA */
+        if (slots > cnt) slots = cnt;
         if (slots == 0) return set_error("four-step kernel: no resident CTA on this device");
         TRY(grow(&scr->slots, &scr->slots_bytes, slots * n * CPX));
         mcu_long_args la;
@@ -854,7 +914,7 @@ static int exec_1d(mufft_plan_1d *plan, int in_mode, int out_mode, float norm,
     if ((io.in_stride | io.out_stride | io.in2_stride) % CPX != 0) {
         return set_error("strides must be multiples of 8 bytes");
     }
-    return run_any(&plan->st, rows_unit_launch, &ctx, &io, async);
+    return run_any(&plan->st, rows_unit_launch, &ctx, &io, async, 1 + in_mode * 16 + out_mode);
 }
 
 void mufft_execute_plan_1d(mufft_plan_1d *plan, void *MUFFT_RESTRICT output, const void *MUFFT_RESTRICT input)
@@ -1139,7 +1199,7 @@ static int conv_fused(mufft_plan_conv *plan, void *output, const void *input, co
     if (filter_stride % CPX != 0) {
         return set_error("strides must be multiples of 8 bytes");
     }
-    return run_any(&plan->plans[0]->st, conv_unit_launch, &ctx, &io, async);
+    return run_any(&plan->plans[0]->st, conv_unit_launch, &ctx, &io, async, 0);
 }
 
 int mufft_execute_conv_batch(mufft_plan_conv *plan, void *output, const void *input_first,
@@ -1232,7 +1292,7 @@ static void mufft_convolve_cuda(void *output, const void *a, const void *b, floa
         if (tls_mul_stage.device_plus_1 != 0) stage_free(&tls_mul_stage); /* streams and buffers of the other device */
         tls_mul_stage.device_plus_1 = dev + 1;
     }
-    (void)run_any(&tls_mul_stage, mul_unit_launch, ctx, &io, 0);
+    (void)run_any(&tls_mul_stage, mul_unit_launch, ctx, &io, 0, 0);
 }
 
 mufft_convolve_func mufft_get_convolve_func(unsigned flags)
@@ -1498,7 +1558,7 @@ static int exec_2d(mufft_plan_2d *plan, void *output, const void *input, size_t 
     io.in_stride = io.in_unit;
     io.out_stride = io.out_unit;
     io.count = batch;
-    return run_any(&plan->st, image_unit_launch, plan, &io, async);
+    return run_any(&plan->st, image_unit_launch, plan, &io, async, 0);
 }
 
 void mufft_execute_plan_2d(mufft_plan_2d *plan, void *MUFFT_RESTRICT output, const void *MUFFT_RESTRICT input)

@@ -118,6 +118,14 @@ int mcu_event_sync(void *) { return 0; }
 int mcu_event_create_timing(void **event) { *event = malloc(1); return 0; }
 int mcu_event_elapsed_ms(float *ms, void *, void *) { *ms = 1.0f; return 0; }
 int mcu_enable_peer_access(int peer) { return peer < 0 || peer > 1 ? 101 : 0; }
+// graphs: the emulated side executes everything at once, so a "capture" has already run its work; report captures as
+// unsupported and let the host layer take its ordinary path (counted, so that the fallback is tested)
+static std::atomic<unsigned> g_capture_attempts;
+int mcu_capture_begin(void *) { g_capture_attempts++; return 801; }
+int mcu_capture_end(void *, void **exec) { *exec = nullptr; return 801; }
+int mcu_graph_launch(void *, void *) { return 801; }
+int mcu_graph_destroy(void *) { return 0; }
+unsigned emu_capture_attempts(int reset) { return reset ? g_capture_attempts.exchange(0) : g_capture_attempts.load(); }
 int mcu_copy_async(void *dst, const void *src, size_t bytes, void *) { if (bytes) memmove(dst, src, bytes); return 0; }
 int mcu_copy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t rows, void *)
 {
@@ -153,7 +161,7 @@ int mcu_launch_rows(const mcu_rows_args *a, void *)
 // single-launch four-step rows: 3 "resident" CTAs walk the batch
 static unsigned long_n1_of(unsigned n) { return n == 16384 ? 16 : (n == 32768 || n == 65536 ? 32 : 0); }
 unsigned mcu_long_n2(unsigned n) { return long_n1_of(n) ? n / long_n1_of(n) : 0; }
-unsigned mcu_long_ctas(unsigned n) { return long_n1_of(n) ? 3 * 2 : 0; } // 3 CTAs, up to two slots each
+unsigned mcu_long_ctas(unsigned n) { return long_n1_of(n) ? 3 : 0; }
 int mcu_launch_long(const mcu_long_args *a, void *)
 {
     g_launches++;
@@ -241,6 +249,7 @@ int mcu_launch_resolve(const mcu_resolve_args *a, void *)
     return 0;
 }
 
+void mcu_launch_count_add(unsigned long long n) { g_launches += n; }
 unsigned long long mcu_launch_count(int reset) { return reset ? g_launches.exchange(0) : g_launches.load(); }
 
 } // extern "C"

@@ -7,22 +7,21 @@ using namespace mufft;
 #define EMU_CAT_(a, b, c, d) a##b##c##d
 #define EMU_CAT(a, b, c, d) EMU_CAT_(a, b, c, d)
 
-extern "C" int EMU_CAT(emu_long_slots_per_cta_, EMU_N1, x, EMU_N2)() { return long_slots_per_cta(EMU_N1, EMU_N2); }
+extern "C" int EMU_CAT(emu_long_slots_per_cta_, EMU_N1, x, EMU_N2)() { return 1; }
 extern "C" int EMU_CAT(emu_launch_long_, EMU_N1, x, EMU_N2)(const mcu_long_args *a, unsigned ctas)
 {
     constexpr int N1 = EMU_N1, N2 = EMU_N2;
     if (a->batch == 0) return 0;
     if (a->n1 != N1 || a->n2 != N2 || a->n != (unsigned)(N1 * N2)) return 1;
-    constexpr bool SPLIT = long_split(N1, N2);
-    constexpr int SLOTS = long_slots_per_cta(N1, N2);
+    constexpr int SLOTS = 1;
     size_t grid = a->batch < ctas ? a->batch : ctas;
     if (a->scratch_slots / SLOTS < grid) grid = a->scratch_slots / SLOTS;
     if (grid == 0) return 1;
     const emu::idx3 g{ (unsigned)grid, 1, 1 };
-    const unsigned threads = long_launch_threads(N1, N2);
+    const unsigned threads = long_cta_threads(N2);
     const size_t smem = long_smem_bytes(N2);
     const bool fwd = a->direction < 0;
-#define fft_long_kernel_for(...) [&] { if constexpr (SPLIT) fft_long_split_kernel<__VA_ARGS__>(*a); else fft_long_kernel<__VA_ARGS__>(*a); }()
+#define fft_long_kernel_for(...) fft_long_kernel<__VA_ARGS__>(*a)
     // CTAs are independent of each other: run them one after another
     if (a->to_peers) {
         if (a->in_mode != MCU_IN_COMPLEX) return 1;

@@ -592,3 +592,62 @@ def test_linearity_and_parseval_at_full_size(m, torch):
     e_in = (x.double() ** 2).sum(dim=1)
     e_out = (fx.double() ** 2).sum(dim=1)
     assert torch.max(torch.abs(e_out / (n * e_in) - 1)).item() < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["c2c64", "r2c4096", "conv1024", "c2c65536"])
+def test_repeated_small_calls_are_replayed_from_a_graph(m, torch, oracle, kind):
+    """The latency path (BASELINE configs[0] as `muFFT-bench 1000000 64` runs it): a small synchronous fft.h call that
+    comes again with the same pointers is captured into a CUDA graph and replayed.  The data changes between the
+    calls, the pointers change in the middle of the run: results must follow, launch counts stay those of the path."""
+    rng = np.random.default_rng(5)
+    if kind == "conv1024":
+        n = 1024
+        method = 1 | 4 | 8
+        plan = m.mufft_create_plan_conv(n, 0, method)
+        blk = m.mufft_conv_get_transformed_block_size(plan)
+        taps = (rng.random(n // 2, np.float32) - np.float32(0.5))
+        bufs = [m.mufft_alloc(blk) for _ in range(3)] + [m.mufft_alloc(n * 8), m.mufft_alloc(n * 8)]
+        fspec, spec, inp = bufs[0], bufs[1], bufs[3]
+        view_in = np.ctypeslib.as_array((ctypes.c_float * n).from_address(inp))
+        t_dev = m.mufft_alloc(n * 2)
+        np.ctypeslib.as_array((ctypes.c_float * (n // 2)).from_address(t_dev))[:] = taps
+        m.mufft_execute_conv_input(plan, 1, fspec, t_dev)
+        for k in range(6):
+            out = bufs[4] if k < 3 else bufs[2]  # blk = n * 8 bytes for the stereo method: both can hold an output
+            a = (rng.random(n, np.float32) - np.float32(0.5))
+            view_in[:] = a
+            m.mufft_execute_conv_input(plan, 0, spec, inp)
+            m.mufft_execute_conv_output(plan, out, spec, fspec)
+            got = np.ctypeslib.as_array((ctypes.c_float * (2 * n)).from_address(out)).view(np.complex64).copy()
+            want = oracle.conv(a.view(np.complex64), taps, n, method)[0]
+            assert rel_l2(got, want) <= 2 * tol(n), k
+        m.mufft_free_plan_conv(plan)
+        for b in bufs + [t_dev]:
+            m.mufft_free(b)
+        return
+    n = int(kind[3:])
+    real = kind.startswith("r2c")
+    plan = m.mufft_create_plan_1d_r2c(n, 0) if real else m.mufft_create_plan_1d_c2c(n, -1, 0)
+    in_floats, out_floats = (n, 2 * (n // 2 + 1)) if real else (2 * n, 2 * n)
+    ins = [m.mufft_alloc(in_floats * 4) for _ in range(2)]
+    outs = [m.mufft_alloc(out_floats * 4) for _ in range(2)]
+    dev_in = torch.zeros(in_floats, dtype=torch.float32, device="cuda")
+    dev_out = torch.zeros(out_floats, dtype=torch.float32, device="cuda")
+    for k in range(9):
+        x = rng.random(in_floats, np.float32) - np.float32(0.5)
+        want = oracle.r2c(x) if real else oracle.c2c(x.view(np.complex64), -1)
+        if k < 6:
+            pi, po = ins[k // 3], outs[k // 3]  # three calls per pointer pair: ordinary, captured, replayed
+            np.ctypeslib.as_array((ctypes.c_float * in_floats).from_address(pi))[:] = x
+        else:
+            dev_in.copy_(torch.from_numpy(x))
+            torch.cuda.synchronize()
+            pi, po = dev_in.data_ptr(), dev_out.data_ptr()
+        m.mufft_cuda_launch_count(1)
+        m.mufft_execute_plan_1d(plan, po, pi)
+        assert m.mufft_cuda_launch_count(1) == (1 if n <= 65536 and not (real and n > 32768) else 2), k
+        got = dev_out.cpu().numpy() if k >= 6 else np.ctypeslib.as_array((ctypes.c_float * out_floats).from_address(po)).copy()
+        assert rel_l2(got.view(np.complex64), want) <= tol(n), k
+    m.mufft_free_plan_1d(plan)
+    for b in ins + outs:
+        m.mufft_free(b)

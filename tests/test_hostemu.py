@@ -437,3 +437,26 @@ def test_slab_plan_over_the_devices_of_one_process(lib, oracle, kind, nx, ny, nd
     assert not raw.mufft_cuda_create_plan_2d_slab_c2c(64, 64, -1, 3, None, 0)
     assert not raw.mufft_cuda_create_plan_2d_slab_c2c(64, 64, -1, 4, None, 0)  # the emulated side has two devices
     assert b"visible" in raw.mufft_cuda_last_error()
+
+
+def test_small_repeated_calls_try_the_graph_path_and_fall_back(lib, oracle):
+    """The latency path: the second identical small synchronous call on device-visible memory is captured into a CUDA
+    graph.  The emulated CUDA side refuses captures, so here the host layer must try exactly once, switch the path off
+    for the plan and keep giving right answers the ordinary way."""
+    raw = lib.lib
+    raw.emu_capture_attempts.restype, raw.emu_capture_attempts.argtypes = u, [i32]
+    x = crnd(np.random.default_rng(3), 64)
+    px, vx = managed(lib, x)
+    py, vy = managed(lib, np.zeros(64, np.complex64))
+    plan = lib._create_plan_1d_c2c(64, -1, 0)
+    raw.emu_capture_attempts(1)
+    for k in range(5):
+        vx[:] = x * (k + 1)
+        raw.mufft_cuda_launch_count(1)
+        lib._execute_plan_1d(plan, py, px)
+        assert raw.mufft_cuda_launch_count(1) == 1
+        assert cpu_libs.rel_l2(vy, oracle.c2c((x * (k + 1)).astype(np.complex64), -1)) <= tol(64)
+    assert raw.emu_capture_attempts(1) == 1
+    lib._free_plan_1d(plan)
+    raw.mufft_free(px)
+    raw.mufft_free(py)
