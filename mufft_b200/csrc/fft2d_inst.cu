@@ -26,27 +26,6 @@ static cudaError_t launch_kind(const mcu_2d_args &a, cudaStream_t stream, unsign
     (void)a; (void)stream; (void)lag_only;
     return cudaErrorInvalidValue;
   } else {
-    if constexpr (KIND == F2D_C2C && f2d_split_preferred(F2D_NX, F2D_NY)) {
-        // rows and columns on different halves of a 512-thread CTA, static work assignment (fft2d_split_kernel)
-        static launch_cfg scfg;
-        auto skernel = fft2d_split_kernel<F2D_NX, F2D_NY, DIR>;
-        constexpr size_t ssmem = f2d_split_smem_bytes(F2D_NX, F2D_NY);
-        int resident = 0;
-        cudaError_t serr = launch_prepare(scfg, skernel, ssmem, 2 * MUFFT_F2D_THREADS, &resident);
-        if (serr != cudaSuccess) return serr;
-        if (lag_only != nullptr) {
-            *lag_only = 4;
-            return cudaSuccess;
-        }
-        if (a.batch == 0) return cudaSuccess;
-        mcu_2d_args b = a;
-        if (b.lag == 0) b.lag = 4;
-        // every CTA must be resident (the halves wait for each other across CTAs): never more than fit
-        const unsigned long long col_tiles = (unsigned long long)a.batch * (F2D_NX / f2d_cols_per_tile(F2D_NY));
-        const unsigned grid = col_tiles < (unsigned long long)resident ? (unsigned)col_tiles : (unsigned)resident;
-        skernel<<<grid, 2 * MUFFT_F2D_THREADS, ssmem, stream>>>(b);
-        return cudaGetLastError();
-    }
     static launch_cfg cfg;
     auto kernel = fft2d_fused_kernel<F2D_NX, F2D_NY, DIR, KIND>;
     constexpr size_t smem = f2d_smem_bytes(F2D_NX, F2D_NY, KIND);

@@ -363,151 +363,9 @@ fft2d_fused_kernel(const mcu_2d_args a)
     }
 }
 
-// ---- split variant: rows and columns on different halves of the CTA, no tickets ---------------------------------
-// ncu on the ticket kernel (profiles/r02b_c2c2d1024.txt): 25 % warp occupancy with every warp of a CTA in the same
-// phase of the same tile - load, butterflies, exchange, store - so that the issue slots are contended for a while
-// (not_selected + selected 30 % of the samples) and idle the rest (barrier 17 %, long scoreboard 16 %).  Here a CTA
-// of 512 threads has two halves with different jobs that drift against each other:
-//   * the upper half is ROWS independent row groups (a warp or part of a warp per row; only __syncwarp inside a
-//     transform): each walks its own static sequence of rows of all images - no ticket, no CTA barrier, ever;
-//   * the lower half transforms column tiles (static sequence as well), synchronising on a named barrier of its own.
-// Rows announce themselves per image (rows_done, release); a column tile waits for its image's NY rows (acquire).
-// Rows run at most `lag` images ahead of the columns that are finished (cols_done), which bounds the intermediate
-// that must stay in L2.  Every wait is on work that is assigned to a resident CTA and does not itself wait for
-// anything newer: no deadlock as long as the whole grid is resident (the launcher sees to that).
-// C2C only; row transforms that fit one warp (NX <= 1024).
-#ifndef MUFFT_F2D_SPLIT
-#define MUFFT_F2D_SPLIT 0
-#endif
-#define F2D_BAR_COLS 15 // named barrier of the column half
-__host__ __device__ constexpr bool f2d_split_supported(int nx, int ny) { return f2d_supported(nx, ny) && engine_threads(nx) <= 32; }
-// ... and where the launcher prefers it: shapes that only fit two ticket CTAs per SM (32 values per thread on both axes)
-__host__ __device__ constexpr bool f2d_split_preferred(int nx, int ny)
-{
-    return MUFFT_F2D_SPLIT != 0 && f2d_split_supported(nx, ny) && engine_regs(nx) >= 32 && engine_regs(ny) >= 32;
-}
-__host__ __device__ constexpr size_t f2d_split_smem_bytes(int nx, int ny)
-{
-    return ((size_t)f2d_rows_per_tile(nx) * engine_smem_elems(nx) + (size_t)f2d_cols_per_tile(ny) * engine_smem_elems(ny)) * sizeof(float2) + 16 +
-           ((f2d_flavour(nx, ny) & F2D_SMEM_TW) ? (size_t)f2d_tw_elems(nx, ny, 0) * sizeof(float2) : 0);
-}
-__device__ __forceinline__ void f2d_bar_sync(int id, int count)
-{
-#ifdef MUFFT_EMU
-    emu::bar_sync(id, count);
-#else
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-#endif
-}
-
-template <int NX, int NY, int DIR>
-__global__ void __launch_bounds__(2 * MUFFT_F2D_THREADS, 1)
-fft2d_split_kernel(const mcu_2d_args a)
-{
-    constexpr int FLAGS = f2d_flavour(NX, NY);
-    constexpr int TWM = f2d_twm(FLAGS);
-    constexpr int HALF = MUFFT_F2D_THREADS;
-    constexpr int RX = engine_regs(NX), TX = NX / RX, ROWS = f2d_rows_per_tile(NX);
-    constexpr int RY = engine_regs(NY), TY = NY / RY, COLS = f2d_cols_per_tile(NY);
-    constexpr unsigned NC = NX / COLS; // column tiles per image
-    MUFFT_DYNAMIC_SMEM(smem_raw);
-    MUFFT_STATIC_SMEM_U32(s_ready, 1);
-    cpx *smem = reinterpret_cast<cpx *>(smem_raw);
-    cpx *smem_rows = smem;                                                  // ROWS exchange areas of the row half
-    cpx *smem_cols = smem + (size_t)ROWS * engine_smem_elems(NX);           // the column half's exchange area
-    const cpx *__restrict__ twx = static_cast<const cpx *>(a.tw_x);
-    const cpx *__restrict__ twy = static_cast<const cpx *>(a.tw_y);
-    if constexpr ((FLAGS & F2D_SMEM_TW) != 0) {
-        cpx *tws = smem_cols + (size_t)COLS * engine_smem_elems(NY) + 2;
-        for (int i = threadIdx.x; i < engine_tw_total(NX); i += 2 * HALF) tws[i] = __ldg(twx + i);
-        if constexpr (NX != NY)
-            for (int i = threadIdx.x; i < engine_tw_total(NY); i += 2 * HALF) tws[engine_tw_total(NX) + i] = __ldg(twy + i);
-        twx = tws;
-        twy = NX != NY ? tws + engine_tw_total(NX) : tws;
-        __syncthreads(); // the only CTA-wide barrier of the kernel
-    }
-    unsigned *rows_done = a.counters + 1;            // [batch] rows finished per image
-    unsigned *cols_done = a.counters + 1 + a.batch;  // [batch] column tiles finished per image
-    const unsigned lag = a.lag ? a.lag : 1;
-    auto wait_for = [&](const unsigned *counter, unsigned need) {
-        unsigned ns = 32;
-        while (ld_relaxed(counter) < need) {
-            __nanosleep(ns);
-            if (ns < 1024) ns *= 2;
-        }
-    };
-
-    if (threadIdx.x >= HALF) {
-        // ---- row half: ROWS independent row groups ---------------------------------------------------------------
-        const int tid = threadIdx.x - HALF;
-        const int slot = tid / TX, t = tid - slot * TX;
-        cpx *sm = smem_rows + slot * engine_smem_elems(NX);
-        const unsigned long long total = (unsigned long long)a.batch * NY;
-        unsigned *pending = nullptr; // t == 0 of the group: a finished row whose announcement is still held back
-        unsigned checked = 0;        // images < checked + lag may be written without asking
-        for (unsigned long long u = (unsigned long long)blockIdx.x * ROWS + slot; u < total; u += (unsigned long long)gridDim.x * ROWS) {
-            const unsigned image = (unsigned)(u / NY), row = (unsigned)(u % NY);
-            if (image >= checked + lag) {
-                // do not run further ahead of the finished columns than `lag` images: the intermediate must stay in L2
-                if (t == 0) {
-                    if (pending != nullptr) { fence_release_gpu(); red_relaxed_add(pending, 1u); pending = nullptr; }
-                    wait_for(cols_done + (image - lag), NC);
-                }
-                checked = image - lag + 1;
-                engine_sync<TX, ROWS>(slot);
-            }
-            const cpx *__restrict__ in = static_cast<const cpx *>(a.in) + (size_t)image * a.in_image + (size_t)row * NX;
-            cpx v[RX];
-#pragma unroll
-            for (int e = 0; e < RX; e++) v[e] = __ldcs(in + t + e * TX);
-            // the previous row's stores have long landed: announce it while this row's loads fly
-            if (t == 0 && pending != nullptr) { fence_release_gpu(); red_relaxed_add(pending, 1u); pending = nullptr; }
-            engine_run<NX, DIR, 1, TX, ROWS, 0, 0, -1, TWM>(v, sm, twx, t, slot);
-            cpx *__restrict__ o = static_cast<cpx *>(a.out) + (size_t)image * a.out_image + (size_t)row * NX;
-#pragma unroll
-            for (int e = 0; e < RX; e++) o[t + e * TX] = v[e];
-            engine_sync<TX, ROWS>(slot); // every lane's stores precede the group leader's release (and the exchange area is free again)
-            if (t == 0) pending = rows_done + image;
-        }
-        if (t == 0 && pending != nullptr) { fence_release_gpu(); red_relaxed_add(pending, 1u); }
-    } else {
-        // ---- column half: one tile of COLS columns at a time -------------------------------------------------------
-        const int tid = threadIdx.x;
-        const int c = tid % COLS, t = tid / COLS;
-        const unsigned long long total = (unsigned long long)a.batch * NC;
-        unsigned *pending = nullptr; // thread 0
-        for (unsigned long long v0 = blockIdx.x; v0 < total; v0 += gridDim.x) {
-            const unsigned image = (unsigned)(v0 / NC), tile = (unsigned)(v0 % NC);
-            if (tid == 0) {
-                const bool ready = ld_relaxed(rows_done + image) >= (unsigned)NY;
-                if (ready) fence_acquire_gpu();
-                s_ready[0] = ready ? 1u : 0u;
-            }
-            f2d_bar_sync(F2D_BAR_COLS, HALF); // the verdict is visible; the previous tile's stores are issued, its exchange area is free
-            if (s_ready[0] == 0) {
-                // rare: the rows are not there yet.  The held-back announcement may go out now (the barrier above covered every
-                // thread's stores of the previous tile), then wait.
-                if (tid == 0) {
-                    if (pending != nullptr) { fence_release_gpu(); red_relaxed_add(pending, 1u); pending = nullptr; }
-                    wait_for(rows_done + image, (unsigned)NY);
-                    fence_acquire_gpu();
-                }
-                f2d_bar_sync(F2D_BAR_COLS, HALF);
-            }
-            cpx *__restrict__ col = static_cast<cpx *>(a.out) + (size_t)image * a.out_image + (size_t)tile * COLS + c;
-            cpx v[RY];
-#pragma unroll
-            for (int e = 0; e < RY; e++) v[e] = __ldcg(col + (size_t)(t + e * TY) * NX); // written by other SMs: L2 only
-            if (tid == 0 && pending != nullptr) { fence_release_gpu(); red_relaxed_add(pending, 1u); pending = nullptr; }
-            // the engine's "CTA" barrier is the column half's named barrier: slot F2D_BAR_COLS - 1 of a two-slot layout
-            engine_run<NY, DIR, COLS, HALF, 2, 0, 0, -1, TWM>(v, smem_cols + c, twy, t, F2D_BAR_COLS - 1);
-#pragma unroll
-            for (int e = 0; e < RY; e++) __stcs(col + (size_t)(t + e * TY) * NX, v[e]);
-            if (tid == 0) pending = cols_done + image;
-        }
-        f2d_bar_sync(F2D_BAR_COLS, HALF); // every thread's stores precede the last release
-        if (tid == 0 && pending != nullptr) { fence_release_gpu(); red_relaxed_add(pending, 1u); }
-    }
-}
+// (A split variant - row groups and a column half on the two halves of a 512-thread CTA, static work sequences, no
+// tickets and no CTA-wide barrier - was built and measured in round 2: 1.402 ms against 1.210 ms for 1024 x 1024 x 256,
+// profiles/r02e_ab.txt and r02e_c2c2d1024_split_rejected.txt.  Desynchronising the two passes does not help when the
+// SM still holds 16 warps: it is gone.)
 
 } // namespace mufft

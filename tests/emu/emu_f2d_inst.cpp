@@ -37,21 +37,4 @@ extern "C" int EMU_CAT(emu_launch_2d_, EMU_NX, x, EMU_NY)(const mcu_2d_args *a, 
     default: return 1;
     }
 }
-// The split variant (rows and columns on different halves of a 512-thread CTA, static assignment): C2C, `ctas` resident CTAs.
-extern "C" int EMU_CAT(emu_launch_2d_split_, EMU_NX, x, EMU_NY)(const mcu_2d_args *a, unsigned ctas)
-{
-    constexpr int NX = EMU_NX, NY = EMU_NY;
-    if constexpr (!f2d_split_supported(NX, NY)) {
-        (void)a; (void)ctas;
-        return -3;
-    } else {
-        if (a->batch == 0) return 0;
-        mcu_2d_args b = *a;
-        if (b.lag == 0) b.lag = 1;
-        const emu::idx3 grid{ ctas, 1, 1 };
-        if (b.direction < 0) emu::launch(grid, 2 * MUFFT_F2D_THREADS, f2d_split_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_split_kernel<NX, NY, -1>(b); });
-        else emu::launch(grid, 2 * MUFFT_F2D_THREADS, f2d_split_smem_bytes(NX, NY), ctas, 1, [&] { fft2d_split_kernel<NX, NY, 1>(b); });
-        return 0;
-    }
-}
 extern "C" int EMU_CAT(emu_2d_rows_variant_, EMU_NX, x, EMU_NY)(int kind) { return f2d_rows_variant(EMU_NX, kind); }

@@ -320,32 +320,6 @@ def test_fused_2d(emu, host, oracle, nx, ny, batch, ctas, lag, direction):
     assert list(counters[1:1 + batch]) == [ny // (256 // (nx // (32 if nx >= 1024 else 16)))] * batch  # producer tiles per image
 
 
-@pytest.mark.parametrize("nx,ny,batch,ctas,lag", [
-    (256, 256, 3, 1, 1),    # one CTA: its two halves hand images to each other
-    (256, 256, 5, 3, 1),    # rows at most one image ahead of the finished columns
-    (256, 256, 4, 2, 3),    # rows run far ahead
-    (512, 256, 3, 2, 2),    # rectangular: different row / column tile shapes, two twiddle tables
-])
-@pytest.mark.parametrize("direction", [-1, 1])
-def test_fused_2d_split(emu, host, oracle, nx, ny, batch, ctas, lag, direction):
-    """fft2d_split_kernel: row groups and the column half of every CTA walk static work sequences and meet only through
-    the rows-done / columns-done counters (no tickets, no CTA-wide barrier)."""
-    fn = getattr(emu, f"emu_launch_2d_split_{nx}x{ny}")
-    fn.restype, fn.argtypes = C.c_int, [C.POINTER(Args2D), C.c_uint]
-    rng = np.random.default_rng(7 + ctas + lag)
-    x = crnd(rng, batch, ny, nx)
-    out = np.full((batch, ny, nx), np.nan, np.complex64)
-    counters = np.zeros(1 + 2 * batch, np.uint32)
-    twx, twy = engine_table(host, nx, direction), engine_table(host, ny, direction)
-    a = Args2D(out=out.ctypes.data, in_=x.ctypes.data, tw_x=twx.ctypes.data, tw_y=twy.ctypes.data, kind=KIND_C2C, counters=counters.ctypes.data,
-               out_image=nx * ny, in_image=nx * ny, batch=batch, nx=nx, ny=ny, direction=direction, lag=lag)
-    assert fn(C.byref(a), ctas) == 0
-    for b in range(batch):
-        assert cpu_libs.rel_l2(out[b], oracle.c2c_2d(x[b], direction)) <= tol(nx * ny)
-    assert list(counters[1:1 + batch]) == [ny] * batch
-    assert list(counters[1 + batch:]) == [nx // (256 // (ny // 16))] * batch
-
-
 @pytest.mark.parametrize("nx,ny,ctas", [(256, 256, 1), (512, 256, 3), (2048, 256, 2)])
 @pytest.mark.parametrize("full", [0, 1])
 def test_fused_2d_real(emu, host, oracle, nx, ny, ctas, full):
