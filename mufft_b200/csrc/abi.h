@@ -91,6 +91,8 @@ typedef struct mcu_cols_args {
     unsigned rows_valid;   /* rows >= rows_valid are taken as zero and never read (0 = all n rows valid) */
     const void *roots;     /* NULL, or exp(dir*2*pi*i*j/n_total): element (image, row) is multiplied by */
     unsigned root_mask;    /* roots[(image*row) & root_mask] before the transform (n = 256, 512, 1024 only) */
+    int discard_input;     /* 1 = the input is scratch that nobody reads again: its lines are dropped from L2 once they
+                            * have been read, without a write-back (needs 16-column tiles of 128-byte aligned row segments) */
 } mcu_cols_args;
 
 /* Fused convolution kernel (conv_kernel.cuh): forward transform, spectral multiply, inverse

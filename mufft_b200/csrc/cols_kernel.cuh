@@ -64,6 +64,18 @@ __global__ void __launch_bounds__(cols_cta_threads(N)) fft_cols_kernel(const mcu
 
         engine_run<N, DIR, TC, cols_cta_threads(N), 1>(v, sm, tw, t, 0);
 
+        if constexpr (TC == 16) {
+            // dead scratch (the intermediate of a two-sweep column transform): one lane per 128-byte row segment drops it
+            // from L2, so that it is never written back to HBM.  Every lane's loads completed before the engine's exchanges.
+            if (a.discard_input && c == 0) {
+#ifndef MUFFT_EMU
+#pragma unroll
+                for (int e = 0; e < R; e++)
+                    if ((unsigned)(t + e * T) < rows_valid) asm volatile("discard.global.L2 [%0], 128;" ::"l"(in + (size_t)(t + e * T) * a.in_pitch) : "memory");
+#endif
+            }
+        }
+
         if (active) {
 #pragma unroll
             for (int e = 0; e < R; e++) out[(size_t)(t + e * T) * a.out_pitch] = v[e];

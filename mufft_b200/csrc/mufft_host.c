@@ -61,6 +61,12 @@ __attribute__((constructor)) static void read_env(void)
  * intermediate.  L2-sized groups measured SLOWER than whole-batch launches (profiles/README.md section 3:
  * 2D R2C 1024^2 x 256 1.40 ms with 86 launches against 0.92 ms with 2), so the cap only bounds the scratch. */
 #define MID_GROUP_BYTES ((size_t)2048 << 20)
+/* Long columns (two sweeps of the column kernel): columns per block, as bytes of the block's intermediate.  With the
+ * second sweep DISCARDING the intermediate from L2 as it reads it, an L2-sized block never touches HBM. */
+#ifndef MUFFT_COLS_BLOCK_MB
+#define MUFFT_COLS_BLOCK_MB 32
+#endif
+#define COLS_BLOCK_BYTES ((size_t)MUFFT_COLS_BLOCK_MB << 20)
 #define SCRATCH_CAP_BYTES ((size_t)1 << 30)
 #define ZERO_COPY_BYTES ((size_t)64 << 10)   /* pinned buffers up to this size are used in place */
 #define MAX_STEPS 32
@@ -1418,7 +1424,7 @@ static int run_cols_axis(const axis *ax, scratch *scr_cols, void *out, size_t ou
          *      w_n^(k1*y2) fused into the load -> out rows k1 + n1*k2 */
         const unsigned n1 = ax->n1, n2 = ax->n2;
         /* blocks of columns whose scratch ([k1][y2][block]) stays in L2 between the two sweeps */
-        size_t wb = SPLIT_CHUNK_BYTES / ((size_t)ax->n * CPX);
+        size_t wb = COLS_BLOCK_BYTES / ((size_t)ax->n * CPX);
         wb = wb < 16 ? 16 : wb - wb % 16;
         if (wb > width) wb = width;
         TRY(scratch_reserve(scr_cols, wb * ax->n * CPX));
@@ -1437,6 +1443,7 @@ static int run_cols_axis(const axis *ax, scratch *scr_cols, void *out, size_t ou
                 cb.out = (char *)out + (img * out_image + c0) * CPX; cb.out_pitch = (size_t)n1 * out_pitch; cb.out_image = out_pitch;
                 cb.tw = ax->d_tw_n2; cb.batch = n1; cb.n = n2; cb.width = w; cb.direction = ax->direction;
                 cb.roots = ax->d_roots; cb.root_mask = ax->n - 1;
+                cb.discard_input = w % 16 == 0; /* whole 128-byte segments of plan-owned scratch */
                 TRY(mcu_launch_cols(&cb, stream));
             }
         }

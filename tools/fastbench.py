@@ -161,6 +161,28 @@ def run(name, units, reps, flags):
             nbytes, flops = 4.0 * nx * ny + 8.0 * w * ny, 2.5 * nx * ny * math.log2(nx * ny)
         m.mufft_free_plan_2d(plan)
         tol = 1e-6 * math.log2(nx * ny)
+    elif name.startswith("cols"):
+        # column pass of a slab transform: the plan's N-point C2C transform down the columns of ONE [N][W] matrix, in place
+        n, w = (int(v) for v in name[4:].split("x"))
+        units = 1
+        x = dev(2 * n * w)
+        probe = sorted({0, w // 2 + 1, w - 1})
+        host = {c: rnd(rng, 2 * n) for c in probe}
+        # a full host copy is small enough at these sizes (n * w * 8 bytes <= 1 GiB): fill on the host, copy once
+        full = np.zeros((n, w, 2), np.float32)
+        for c, h in host.items():
+            full[:, c, :] = h.reshape(n, 2)
+        x.put(0, full.ravel())
+        del full
+        plan = m.mufft_create_plan_1d_c2c(n, -1, flags)
+        # in place and repeated: only the first run transforms the probe columns; time on a second buffer
+        y = dev(2 * n * w)
+        best, med = timed(lambda: m.mufft_execute_plan_1d_columns(plan, y.ptr, x.ptr, w, w * 8, w * 8), reps)
+        got = y.get(0, 2 * n * w).reshape(n, w, 2)
+        err = max(rel_l2(got[:, c, :].copy().view(np.complex64), np.fft.fft(h.view(np.complex64).astype(np.complex128))) for c, h in host.items())
+        del got
+        m.mufft_free_plan_1d(plan)
+        nbytes, flops, tol = 16.0 * n * w, 5.0 * n * w * math.log2(n), 1e-6 * math.log2(n)
     elif name.startswith(("c2c", "r2c", "c2r")):
         kind, n = name[:3], int(name[3:])
         if kind == "c2c":
