@@ -162,6 +162,23 @@ typedef struct mcu_long_args {
     mcu_peer_dest peers;
 } mcu_long_args;
 
+/* Single-launch four-step COLUMN transforms of n = n1 x 1024 points down a row-major [n][width] matrix
+ * (longcols_kernel.cuh): blocks of 32 columns, intermediate in a ring of L2-resident scratch slots. */
+typedef struct mcu_longcols_args {
+    void *out;             /* may equal `in` */
+    const void *in;
+    const void *tw;        /* engine twiddle table of 1024 points (variant 0) */
+    const void *roots;     /* exp(dir*2*pi*i*j/n), j < n */
+    void *scratch;         /* `ring` slots of mcu_longcols_slot_elems(n) complex each */
+    unsigned *counters;    /* 1 + 2 * ceil(width / 32) zero-initialised words */
+    unsigned ring;         /* > lag, or >= the number of column blocks */
+    unsigned lag;          /* B tiles run this many blocks behind the A tiles (0 = the launcher's choice) */
+    size_t out_pitch, in_pitch; /* complex elements between consecutive rows */
+    unsigned width;        /* columns */
+    unsigned n, n1;
+    int direction;
+} mcu_longcols_args;
+
 /* Generic one-pass Stockham kernel (any length; used beyond the engine limits). */
 typedef struct mcu_pass_args {
     void *out;
@@ -245,6 +262,12 @@ int mcu_launch_rows(const mcu_rows_args *args, void *stream);
 unsigned mcu_long_n2(unsigned n);
 unsigned mcu_long_ctas(unsigned n);
 int mcu_launch_long(const mcu_long_args *args, void *stream);
+/* Single-launch four-step columns: 1 if the kernel exists for n rows; complex elements of one ring slot; the lag the
+ * launcher would pick on the current device (the ring must hold more slots); the launch. */
+int mcu_longcols_supported(unsigned n);
+size_t mcu_longcols_slot_elems(unsigned n);
+unsigned mcu_longcols_default_lag(unsigned n);
+int mcu_launch_longcols(const mcu_longcols_args *args, void *stream);
 int mcu_launch_cols(const mcu_cols_args *args, void *stream);
 int mcu_launch_pass(const mcu_pass_args *args, void *stream);
 /* n2 of the two-kernel split of n for a row (columns = 0) or column (columns = 1) transform

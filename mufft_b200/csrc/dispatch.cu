@@ -45,6 +45,8 @@ cudaError_t rowst_launch_1024(const mcu_rowst_args &, cudaStream_t);
 #define MUFFT_DECLARE_LONG(n1, n2) cudaError_t long_launch_##n1##x##n2(const mcu_long_args &, cudaStream_t); int long_ctas_##n1##x##n2();
 MUFFT_LONG_SHAPES(MUFFT_DECLARE_LONG)
 
+cudaError_t longcols_launch(const mcu_longcols_args &, cudaStream_t, unsigned *lag_only);
+
 static std::atomic<unsigned long long> g_launches{0};
 
 template <int RADIX>
@@ -253,6 +255,27 @@ int mcu_launch_long(const mcu_long_args *a, void *stream)
     MUFFT_LONG_SHAPES(X)
 #undef X
     return (int)cudaErrorInvalidValue;
+}
+
+int mcu_longcols_supported(unsigned n) { return n == 4096 || n == 8192 || n == 16384 || n == 32768; }
+size_t mcu_longcols_slot_elems(unsigned n) { return (size_t)n * 32; } // a block of 32 columns (longcols_kernel.cuh: LONGCOLS_CB)
+unsigned mcu_longcols_default_lag(unsigned n)
+{
+    if (!mcu_longcols_supported(n)) return 0;
+    mcu_longcols_args a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.n1 = n / 1024; a.direction = -1;
+    unsigned lag = 0;
+    if (longcols_launch(a, nullptr, &lag) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return lag;
+}
+int mcu_launch_longcols(const mcu_longcols_args *a, void *stream)
+{
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)longcols_launch(*a, (cudaStream_t)stream, nullptr);
 }
 
 int mcu_launch_conv(const mcu_conv_args *a, void *stream)

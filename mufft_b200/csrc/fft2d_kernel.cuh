@@ -84,7 +84,18 @@ __host__ __device__ constexpr bool f2d_supported(int nx, int ny)
 // Row pitch (complex elements) of the intermediate / output image a kind works on, columns that carry data.
 __host__ __device__ constexpr int f2d_pitch(int nx, int kind) { return kind == F2D_C2C ? nx : (kind == F2D_C2R ? nx + 2 : 2 * nx); }
 __host__ __device__ constexpr int f2d_width(int nx, int kind) { return kind == F2D_C2C ? nx : (kind == F2D_R2C_FULL ? 2 * nx : nx + 1); }
-__host__ __device__ constexpr unsigned f2d_row_tiles(int nx, int ny) { return ny / f2d_rows_per_tile(nx); }
+// Row groups per row ticket.  Short rows (16 values per thread: 256 / 512 points) are little work per ticket - 8 rows of
+// 256 points against 8 columns of up to 2048 - so a ticket takes several groups back to back; the rows of a group belong
+// to one warp each, no CTA barrier in between.
+#ifndef MUFFT_F2D_ROW_REPEAT
+#define MUFFT_F2D_ROW_REPEAT 1
+#endif
+__host__ __device__ constexpr int f2d_row_repeat(int nx, int ny)
+{
+    const int want = engine_regs(nx) <= 16 && engine_threads(nx) <= 32 ? MUFFT_F2D_ROW_REPEAT : 1;
+    return ny % (f2d_rows_per_tile(nx) * want) == 0 && ny / (f2d_rows_per_tile(nx) * want) >= 8 ? want : 1;
+}
+__host__ __device__ constexpr unsigned f2d_row_tiles(int nx, int ny) { return ny / (f2d_rows_per_tile(nx) * f2d_row_repeat(nx, ny)); }
 __host__ __device__ constexpr unsigned f2d_col_tiles(int nx, int ny, int kind) { return (f2d_width(nx, kind) + f2d_cols_per_tile(ny) - 1) / f2d_cols_per_tile(ny); }
 __host__ __device__ constexpr unsigned f2d_tickets_per_image(int nx, int ny, int kind) { return f2d_row_tiles(nx, ny) + f2d_col_tiles(nx, ny, kind); }
 __host__ __device__ constexpr size_t f2d_xch_elems(int nx, int ny, int vx)
@@ -173,6 +184,7 @@ fft2d_fused_kernel(const mcu_2d_args a)
     constexpr int PITCH = f2d_pitch(NX, KIND);   // rows of the image the column tiles work on
     constexpr int WIDTH = f2d_width(NX, KIND);   // columns to transform
     constexpr bool COLS_FIRST = KIND == F2D_C2R;
+    constexpr int REP = f2d_row_repeat(NX, NY);
     constexpr unsigned NR = f2d_row_tiles(NX, NY), NC = f2d_col_tiles(NX, NY, KIND);
     constexpr unsigned NP = COLS_FIRST ? NC : NR; // producer / consumer tiles per image
     constexpr unsigned NQ = COLS_FIRST ? NR : NC;
@@ -300,35 +312,40 @@ fft2d_fused_kernel(const mcu_2d_args a)
 
         if (is_rows) {
             const int slot = tid / TX, t = tid - slot * TX;
-            const size_t row = (size_t)tile * ROWS + slot;
             cpx *sm = smem + slot * engine_smem_elems(NX, VX);
-            cpx v[RX];
-            if constexpr (KIND == F2D_C2R) {
-                // consumer: ring slot (written by other SMs: L2 reads) -> dense real rows of NX complex = 2 NX floats
-                const cpx *mid = static_cast<const cpx *>(a.mid) + (size_t)(image % a.ring) * f2d_mid_elems(NX, NY) + row * PITCH;
-                rows_load<NX, MCU_IN_C2R, VX>(v, cg_ptr{ mid }, static_cast<const cpx *>(nullptr), static_cast<const cpx *>(a.rtw), 1.0f, t);
-                if (tid == 0) release_pending();
-                engine_run<NX, DIR, 1, TX, ROWS, 0, VX, -1, TWM>(v, sm, twx, t, slot);
-                cpx *__restrict__ o = static_cast<cpx *>(a.out) + (size_t)image * a.out_image + row * NX;
-#pragma unroll
-                for (int e = 0; e < RX; e++) __stcs(o + t + e * TX, v[e]);
-                if (tid == 0) pending = consumed + image;
-            } else {
-                // producer: input rows (streamed, read once) -> rows of the output buffer
-                const cpx *__restrict__ in = static_cast<const cpx *>(a.in) + (size_t)image * a.in_image + row * NX;
+            if constexpr (KIND != F2D_C2R) {
                 // pull the same rows of the next image into L2: that ticket is about one wave of tickets ahead
                 if (tid == 0 && image + 1 < a.batch) {
-                    const cpx *nxt = static_cast<const cpx *>(a.in) + (size_t)(image + 1) * a.in_image + (size_t)tile * ROWS * NX;
-                    if ((reinterpret_cast<uintptr_t>(nxt) & 15) == 0) prefetch_l2_bulk(nxt, (unsigned)(ROWS * NX * sizeof(cpx)));
+                    const cpx *nxt = static_cast<const cpx *>(a.in) + (size_t)(image + 1) * a.in_image + (size_t)tile * (REP * ROWS) * NX;
+                    if ((reinterpret_cast<uintptr_t>(nxt) & 15) == 0) prefetch_l2_bulk(nxt, (unsigned)(REP * ROWS * NX * sizeof(cpx)));
                 }
-#pragma unroll
-                for (int e = 0; e < RX; e++) v[e] = __ldcs(in + t + e * TX);
-                if (tid == 0) release_pending(); // the previous tile, while this one's loads fly
-                engine_run<NX, DIR, 1, TX, ROWS, 0, VX, -1, TWM>(v, sm, twx, t, slot);
-                cpx *__restrict__ o = static_cast<cpx *>(a.out) + (size_t)image * a.out_image + row * PITCH;
-                rows_store<NX, f2d_out_mode(KIND), TX, ROWS, VX>(v, o, sm, static_cast<const cpx *>(a.rtw), t, slot, true);
-                if (tid == 0) pending = produced + image;
             }
+#pragma unroll 1
+            for (int rep = 0; rep < REP; rep++) {
+                const size_t row = ((size_t)tile * REP + rep) * ROWS + slot;
+                cpx v[RX];
+                if constexpr (KIND == F2D_C2R) {
+                    // consumer: ring slot (written by other SMs: L2 reads) -> dense real rows of NX complex = 2 NX floats
+                    const cpx *mid = static_cast<const cpx *>(a.mid) + (size_t)(image % a.ring) * f2d_mid_elems(NX, NY) + row * PITCH;
+                    rows_load<NX, MCU_IN_C2R, VX>(v, cg_ptr{ mid }, static_cast<const cpx *>(nullptr), static_cast<const cpx *>(a.rtw), 1.0f, t);
+                    if (rep == 0 && tid == 0) release_pending();
+                    engine_run<NX, DIR, 1, TX, ROWS, 0, VX, -1, TWM>(v, sm, twx, t, slot);
+                    cpx *__restrict__ o = static_cast<cpx *>(a.out) + (size_t)image * a.out_image + row * NX;
+#pragma unroll
+                    for (int e = 0; e < RX; e++) __stcs(o + t + e * TX, v[e]);
+                } else {
+                    // producer: input rows (streamed, read once) -> rows of the output buffer
+                    const cpx *__restrict__ in = static_cast<const cpx *>(a.in) + (size_t)image * a.in_image + row * NX;
+#pragma unroll
+                    for (int e = 0; e < RX; e++) v[e] = __ldcs(in + t + e * TX);
+                    if (rep == 0 && tid == 0) release_pending(); // the previous tile, while this one's loads fly
+                    engine_run<NX, DIR, 1, TX, ROWS, 0, VX, -1, TWM>(v, sm, twx, t, slot);
+                    cpx *__restrict__ o = static_cast<cpx *>(a.out) + (size_t)image * a.out_image + row * PITCH;
+                    rows_store<NX, f2d_out_mode(KIND), TX, ROWS, VX>(v, o, sm, static_cast<const cpx *>(a.rtw), t, slot, true);
+                }
+                if constexpr (REP > 1) engine_sync<TX, ROWS>(slot); // the exchange area is reused by the next row of this group
+            }
+            if (tid == 0) pending = (KIND == F2D_C2R ? consumed : produced) + image;
         } else {
             const int c = tid % COLS, t = tid / COLS;
             const bool active = WIDTH % COLS == 0 || tile * COLS + c < (unsigned)WIDTH;

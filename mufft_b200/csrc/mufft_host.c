@@ -240,6 +240,7 @@ typedef struct axis {
     void *d_engine_tw; /* engine table: non-NULL = row transforms of this axis run in one kernel */
     unsigned long_n2;  /* != 0: rows run on the single-launch four-step kernel, n = (n / long_n2) x long_n2 (long_kernel.cuh) */
     int generic_only;  /* MUFFT_CUDA_FLAG_GENERIC_PASSES: no two-kernel split either */
+    int long_cols;     /* columns run on the single-launch four-step column kernel, n = (n / 1024) x 1024 (longcols_kernel.cuh) */
     void *d_engine_tw_real; /* table of the mirrored-pass shape the R2C (forward) / C2R (inverse) row kernel uses, or NULL */
     void *d_roots;     /* exp(dir*2*pi*i*j/n), j < n: generic multi-pass kernels, two-kernel split */
     unsigned n1, n2;   /* two-kernel split n = n1 * n2 (0 = not used) */
@@ -303,6 +304,13 @@ static int axis_init(axis *ax, unsigned n, int direction, int want_generic, unsi
         ax->n1 = n / ax->n2;
         ax->d_tw_n2 = make_engine_table(ax->n2, direction, 0);
         if (!ax->d_tw_n2) return -1;
+    } else if (columns && !(flags & (MUFFT_CUDA_FLAG_TWO_KERNEL | MUFFT_CUDA_FLAG_GENERIC_PASSES)) && mcu_longcols_supported(n)) {
+        /* one launch, one pass over HBM: blocks of 32 columns, intermediate in L2 */
+        ax->long_cols = 1;
+        ax->n2 = 1024;
+        ax->n1 = n / 1024;
+        ax->d_tw_n2 = make_engine_table(1024, direction, 0);
+        if (!ax->d_tw_n2) return -1;
     } else if (want_generic && !ax->generic_only && mcu_split_n2(n, columns) != 0) { /* rows use it above the on-chip limit, columns above MCU_COLS_MAX_N */
         ax->n2 = mcu_split_n2(n, columns);
         ax->n1 = n / ax->n2;
@@ -357,8 +365,10 @@ static void *make_resolve_twiddles(int direction, unsigned n)
 typedef struct scratch {
     void *buf[2];
     size_t bytes;
-    void *slots;       /* scratch slots of the four-step kernel: one transform per resident CTA, lives in L2 */
+    void *slots;       /* scratch slots of the four-step kernels: one transform per resident CTA / a ring of column blocks; lives in L2 */
     size_t slots_bytes;
+    void *counters;    /* ticket and tiles-done counters of the four-step column kernel */
+    size_t counters_bytes;
 } scratch;
 
 static int scratch_reserve(scratch *s, size_t bytes)
@@ -379,6 +389,7 @@ static void scratch_free(scratch *s)
     mcu_free(s->buf[0]);
     mcu_free(s->buf[1]);
     mcu_free(s->slots);
+    mcu_free(s->counters);
     memset(s, 0, sizeof(*s));
 }
 
@@ -1415,6 +1426,26 @@ static int run_cols_axis(const axis *ax, scratch *scr_cols, void *out, size_t ou
         a.out_pitch = out_pitch; a.in_pitch = in_pitch; a.out_image = out_image; a.in_image = in_image;
         a.batch = images; a.n = ax->n; a.width = width; a.direction = ax->direction;
         return mcu_launch_cols(&a, stream);
+    }
+    if (ax->long_cols) {
+        const unsigned blocks = (width + 31) / 32;
+        const unsigned lag = mcu_longcols_default_lag(ax->n);
+        size_t ring = (size_t)lag + 3;
+        if (ring > blocks) ring = blocks;
+        if (lag == 0 || ring == 0) return set_error("four-step column kernel: no resident CTA on this device");
+        TRY(grow(&scr_cols->slots, &scr_cols->slots_bytes, ring * mcu_longcols_slot_elems(ax->n) * CPX));
+        TRY(grow(&scr_cols->counters, &scr_cols->counters_bytes, (2 * (size_t)blocks + 1) * sizeof(unsigned)));
+        for (size_t img = 0; img < images; img++) {
+            mcu_longcols_args la;
+            memset(&la, 0, sizeof(la));
+            TRY(mcu_memset(scr_cols->counters, 0, (2 * (size_t)blocks + 1) * sizeof(unsigned), stream));
+            la.out = (char *)out + img * out_image * CPX; la.in = (const char *)in + img * in_image * CPX;
+            la.tw = ax->d_tw_n2; la.roots = ax->d_roots; la.scratch = scr_cols->slots; la.counters = scr_cols->counters;
+            la.ring = (unsigned)ring; la.lag = lag; la.out_pitch = out_pitch; la.in_pitch = in_pitch; la.width = width;
+            la.n = ax->n; la.n1 = ax->n1; la.direction = ax->direction;
+            TRY(mcu_launch_longcols(&la, stream));
+        }
+        return 0;
     }
     if (ax->n2 != 0) {
         /* Long columns, n = n1 * n2 (row y = y1*n2 + y2, output row k = k1 + n1*k2), two sweeps of

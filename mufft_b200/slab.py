@@ -61,6 +61,10 @@ class SlabFFT2D:
             if self.device.type != "cuda":
                 raise RuntimeError("SlabFFT2D runs its transforms on a CUDA device (there is no CPU path)")
             self._m = m
+            # plans (twiddle tables, scratch) live on the device that is current when they are created: make it ours
+            torch.cuda.set_device(self.device)
+            if m.mufft_cuda_set_device(self.device.index if self.device.index is not None else torch.cuda.current_device()):
+                raise RuntimeError(m.mufft_cuda_last_error().decode())
             px = m.mufft_create_plan_1d_c2c(nx, direction, 0)
             py = m.mufft_create_plan_1d_c2c(ny, direction, 0)
             if not px or not py:
@@ -136,7 +140,8 @@ class SlabFFT2D:
         self._peer_array = (ctypes.c_void_p * self.world)(*peers)
 
     def buffers(self):
-        """Work buffers (allocate once, reuse across executes)."""
+        """Work buffers (allocate once, reuse across executes).  With the p2p exchange `recv` aliases the plan-owned,
+        IPC-shared column slab: it must not be used after close()."""
         c64 = dict(dtype=torch.complex64, device=self.device)
         g, rl, cl = self.world, self.rows_local, self.cols_local
         if self.exchange == "p2p":
@@ -290,6 +295,9 @@ class SlabRFFT2D:
             if self.device.type != "cuda":
                 raise RuntimeError("SlabRFFT2D runs its transforms on a CUDA device (there is no CPU path)")
             self._m = m
+            torch.cuda.set_device(self.device)  # plans live on the device that is current when they are created
+            if m.mufft_cuda_set_device(self.device.index if self.device.index is not None else torch.cuda.current_device()):
+                raise RuntimeError(m.mufft_cuda_last_error().decode())
             plans = (m.mufft_create_plan_1d_r2c(nx, 0), m.mufft_create_plan_1d_c2r(nx, 0),
                      m.mufft_create_plan_1d_c2c(ny, m.MUFFT_FORWARD, 0), m.mufft_create_plan_1d_c2c(ny, m.MUFFT_INVERSE, 0))
             if not all(plans):

@@ -40,6 +40,7 @@ int emu_launch_rowst_1024(const mcu_rowst_args *);
 #define X(n1, n2) int emu_launch_long_##n1##x##n2(const mcu_long_args *, unsigned);
 EMU_FOR_FOURSTEP_SHAPES(X)
 #undef X
+int emu_launch_longcols(const mcu_longcols_args *, unsigned);
 // fused 2D shapes compiled for the emulation (tests/emu/Makefile: F2D_SHAPES)
 #define EMU_FOR_F2D_SHAPES(X) X(256, 256) X(512, 256) X(2048, 256)
 #define X(nx, ny) int emu_launch_2d_##nx##x##ny(const mcu_2d_args *, unsigned); int emu_2d_rows_variant_##nx##x##ny(int);
@@ -169,6 +170,14 @@ int mcu_launch_long(const mcu_long_args *a, void *)
     EMU_FOR_FOURSTEP_SHAPES(X)
 #undef X
     return 1;
+}
+int mcu_longcols_supported(unsigned n) { return n == 4096 || n == 8192 || n == 16384 || n == 32768; }
+size_t mcu_longcols_slot_elems(unsigned n) { return (size_t)n * 32; }
+unsigned mcu_longcols_default_lag(unsigned n) { return mcu_longcols_supported(n) ? 1 : 0; }
+int mcu_launch_longcols(const mcu_longcols_args *a, void *)
+{
+    g_launches++;
+    return emu_launch_longcols(a, 3);
 }
 int mcu_launch_conv(const mcu_conv_args *a, void *)
 {

@@ -37,4 +37,5 @@ extern "C" int EMU_CAT(emu_launch_2d_, EMU_NX, x, EMU_NY)(const mcu_2d_args *a, 
     default: return 1;
     }
 }
+extern "C" unsigned EMU_CAT(emu_2d_row_tiles_, EMU_NX, x, EMU_NY)() { return f2d_row_tiles(EMU_NX, EMU_NY); }
 extern "C" int EMU_CAT(emu_2d_rows_variant_, EMU_NX, x, EMU_NY)(int kind) { return f2d_rows_variant(EMU_NX, kind); }

@@ -651,3 +651,37 @@ def test_repeated_small_calls_are_replayed_from_a_graph(m, torch, oracle, kind):
     m.mufft_free_plan_1d(plan)
     for b in ins + outs:
         m.mufft_free(b)
+
+
+@pytest.mark.parametrize("n,width", [(4096, 37), (8192, 256), (32768, 1000), (32768, 4096), (65536, 64)])
+@pytest.mark.parametrize("path", ["default", "two_kernel"])
+def test_long_columns(m, torch, oracle, n, width, path):
+    """mufft_execute_plan_1d_columns beyond 2048 rows (the column pass of a slab transform): one persistent launch of
+    the four-step column kernel for 4096..32768 rows - blocks of 32 columns, the last one partly masked, intermediate in
+    L2 - or (plan flag, and beyond 32768 rows) two sweeps of the column kernel through scratch; in place and out of place."""
+    if path == "two_kernel" and width > 1000:
+        pytest.skip("the fallback is covered at the smaller widths")
+    flags = TWO_KERNEL if path == "two_kernel" else 0
+    pitch = width + 5
+    x = dev_random(torch, (n, pitch, 2), n + width)
+    xc = torch.view_as_complex(x)[:, :width]
+    ref = torch.fft.fft(xc.to(torch.complex128), dim=0)
+    plan = m.mufft_create_plan_1d_c2c(n, -1, flags)
+    assert plan
+    y = torch.full_like(x, float("nan"))
+    m.mufft_cuda_launch_count(1)
+    assert m.mufft_execute_plan_1d_columns(plan, y.data_ptr(), x.data_ptr(), width, pitch * 8, pitch * 8) == 0, m.mufft_cuda_last_error()
+    torch.cuda.synchronize()
+    one_launch = path == "default" and n <= 32768
+    assert (m.mufft_cuda_launch_count(1) == 1) == one_launch
+    yc = torch.view_as_complex(y)
+    assert (torch.linalg.vector_norm(yc[:, :width] - ref) / torch.linalg.vector_norm(ref)).item() <= tol(n)
+    assert torch.isnan(yc[:, width:].real).all(), "nothing is written beyond the last column"
+    col = xc[:, width - 1].contiguous().cpu().numpy()
+    assert rel_l2(yc[:, width - 1].cpu().numpy(), oracle.c2c(col, -1)) <= tol(n)
+    # in place, twice on the same plan (ring and counters are reused): FFT of the FFT = the reversed input times n
+    assert m.mufft_execute_plan_1d_columns(plan, y.data_ptr(), y.data_ptr(), width, pitch * 8, pitch * 8) == 0
+    torch.cuda.synchronize()
+    m.mufft_free_plan_1d(plan)
+    back = torch.roll(torch.flip(yc[:, :width], dims=[0]), 1, dims=0) / n
+    assert (torch.linalg.vector_norm(back - xc) / torch.linalg.vector_norm(xc)).item() <= 2 * tol(n)

@@ -25,8 +25,12 @@ vp, sz = C.c_void_p, C.c_size_t
 
 @pytest.fixture(scope="module")
 def emu():
-    subprocess.run(["make", "-s", "-C", EMU_DIR, "-j", str(min(8, os.cpu_count() or 1))], check=True)
-    return C.CDLL(os.path.join(EMU_DIR, "_build", "libmufft_emu.so"), mode=os.RTLD_LOCAL)
+    """The kernels as the product builds them; MUFFT_EMU_EXTRA="-D..." runs the same tests on an A/B variant of the kernels
+    (built into tests/emu/_build_variant) before GPU time is spent on it."""
+    extra = os.environ.get("MUFFT_EMU_EXTRA", "")
+    build = "_build_variant" if extra else "_build"
+    subprocess.run(["make", "-s", "-C", EMU_DIR, "-j", str(min(8, os.cpu_count() or 1)), f"BUILD={build}", f"EXTRA={extra}"], check=True)
+    return C.CDLL(os.path.join(EMU_DIR, build, "libmufft_emu.so"), mode=os.RTLD_LOCAL)
 
 
 @pytest.fixture(scope="module", params=["table", "derived"])
@@ -317,7 +321,7 @@ def test_fused_2d(emu, host, oracle, nx, ny, batch, ctas, lag, direction):
                     direction=direction, lag=lag) == 0
     for b in range(batch):
         assert cpu_libs.rel_l2(out[b], oracle.c2c_2d(x[b], direction)) <= tol(nx * ny)
-    assert list(counters[1:1 + batch]) == [ny // (256 // (nx // (32 if nx >= 1024 else 16)))] * batch  # producer tiles per image
+    assert list(counters[1:1 + batch]) == [getattr(emu, f"emu_2d_row_tiles_{nx}x{ny}")()] * batch  # producer (row) tiles per image
 
 
 @pytest.mark.parametrize("nx,ny,ctas", [(256, 256, 1), (512, 256, 3), (2048, 256, 2)])
@@ -524,3 +528,46 @@ def test_column_kernel(emu, host, oracle, n, direction):
         want = np.fft.fft(xin, axis=1) if direction < 0 else np.fft.ifft(xin, axis=1, norm="forward")
         assert cpu_libs.rel_l2(out[:, :, :width], want) <= max(tol(n), 2e-7)
         assert np.all(np.isnan(out[:, :, width:].real)), "wrote beyond the requested columns"
+
+
+class ArgsLongCols(C.Structure):  # abi.h: mcu_longcols_args
+    _fields_ = [("out", vp), ("in_", vp), ("tw", vp), ("roots", vp), ("scratch", vp), ("counters", vp), ("ring", C.c_uint), ("lag", C.c_uint),
+                ("out_pitch", sz), ("in_pitch", sz), ("width", C.c_uint), ("n", C.c_uint), ("n1", C.c_uint), ("direction", C.c_int)]
+
+
+@pytest.mark.parametrize("n1,width,ctas,lag,ring,inplace", [
+    (4, 32, 1, 1, 1, False),     # one block, one CTA
+    (4, 100, 3, 1, 2, True),     # four blocks (the last one partly masked), ring shorter than the blocks, in place
+    (8, 64, 2, 2, 3, False),
+    (32, 40, 3, 1, 2, True),     # the BASELINE configs[4] column length
+])
+@pytest.mark.parametrize("direction", [-1, 1])
+def test_four_step_columns(emu, host, oracle, n1, width, ctas, lag, ring, inplace, direction):
+    """longcols_kernel.cuh: n1 x 1024-point transforms down the columns of a [n][width] matrix in one persistent launch -
+    A tiles (register transforms + derived twiddles) into a ring of scratch slots, lagged B tiles (engine column
+    transforms) out of it; slot reuse waits for the consumers."""
+    if n1 == 32 and direction == 1:
+        pytest.skip("one direction is enough at the large shape")
+    fn = emu.emu_launch_longcols
+    fn.restype, fn.argtypes = C.c_int, [C.POINTER(ArgsLongCols), C.c_uint]
+    n = n1 * 1024
+    pitch = width + 3
+    rng = np.random.default_rng(n1 + width)
+    buf = np.full((n, pitch), np.nan, np.complex64)
+    buf[:, :width] = crnd(rng, n, width)
+    x = buf[:, :width].astype(np.complex128)
+    want = np.fft.fft(x, axis=0) if direction < 0 else np.fft.ifft(x, axis=0, norm="forward")
+    out = buf if inplace else np.full((n, pitch), np.nan, np.complex64)
+    first_col = buf[:, 0].copy()
+    tw = engine_table(host, 1024, direction)
+    j = np.arange(n, dtype=np.float64)
+    roots = (np.cos(2 * np.pi * direction * j / n).astype(np.float32) + 1j * np.sin(2 * np.pi * direction * j / n).astype(np.float32)).astype(np.complex64)
+    blocks = (width + 31) // 32
+    scratch = np.full((ring, n * 32), np.nan, np.complex64)
+    counters = np.zeros(1 + 2 * blocks, np.uint32)
+    a = ArgsLongCols(out=out.ctypes.data, in_=buf.ctypes.data, tw=tw.ctypes.data, roots=roots.ctypes.data, scratch=scratch.ctypes.data,
+                     counters=counters.ctypes.data, ring=ring, lag=lag, out_pitch=pitch, in_pitch=pitch, width=width, n=n, n1=n1, direction=direction)
+    assert fn(C.byref(a), ctas) == 0
+    assert cpu_libs.rel_l2(out[:, :width], want) <= tol(n)
+    assert np.all(np.isnan(out[:, width:].real)), "nothing is written beyond the last column"
+    assert cpu_libs.rel_l2(out[:, 0], oracle.c2c(first_col, direction)) <= tol(n)

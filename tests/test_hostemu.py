@@ -460,3 +460,24 @@ def test_small_repeated_calls_try_the_graph_path_and_fall_back(lib, oracle):
     lib._free_plan_1d(plan)
     raw.mufft_free(px)
     raw.mufft_free(py)
+
+
+@pytest.mark.parametrize("ny,flags,launches", [(4096, 0, 2), (4096, TWO_KERNEL, 3), (2048, 0, 2)])
+def test_long_columns_of_a_2d_plan(lib, oracle, ny, flags, launches):
+    """2D plans with more than 2048 rows: the column pass is ONE launch of the four-step column kernel (4096..32768
+    rows), or two sweeps of the column kernel with MUFFT_CUDA_FLAG_TWO_KERNEL; up to 2048 rows one column kernel.
+    (+ 1 launch for the rows.)"""
+    raw = lib.lib
+    nx = 40 if False else 32
+    x = crnd(np.random.default_rng(ny), ny, nx)
+    pin, _ = managed(lib, x)
+    pout, yv = managed(lib, np.zeros((ny, nx), np.complex64))
+    plan = lib._create_plan_2d_c2c(nx, ny, 1, flags)
+    assert plan
+    raw.mufft_cuda_launch_count(1)
+    assert raw.mufft_execute_plan_2d_batch(plan, pout, pin, 1) == 0, raw.mufft_cuda_last_error()
+    assert raw.mufft_cuda_launch_count(1) == launches
+    lib._free_plan_2d(plan)
+    assert cpu_libs.rel_l2(yv, oracle.c2c_2d(x, 1)) <= tol(nx * ny)
+    raw.mufft_free(pin)
+    raw.mufft_free(pout)
