@@ -78,6 +78,10 @@ int mufft_execute_plan_1d_batch_scatter_async(mufft_plan_1d *plan, void *const *
  * into this one (peer access over NVLink is enabled on demand). */
 void *mufft_cuda_device_alloc(size_t size);
 void mufft_cuda_device_free(void *ptr);
+/* Page-locked (pinned) host memory: the synchronous batch calls stage ordinary host memory through the same pipeline, but
+ * the copies of pinned buffers run at the full rate of the bus and overlap in both directions. */
+void *mufft_cuda_host_alloc(size_t size);
+void mufft_cuda_host_free(void *ptr);
 /* Synchronous helpers for callers that keep their data in device memory: copy `bytes` between any two kinds of
  * memory (host, pinned, managed, device), fill device-accessible memory with a byte value.  Both are ordered after the
  * work already queued on the current stream and complete on return.  0 on success. */

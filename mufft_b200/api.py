@@ -77,6 +77,8 @@ SIGNATURES = {
     "mufft_execute_plan_1d_batch_scatter_async": (_i, [_vp, C.POINTER(C.c_void_p), _u, _sz, _vp, _sz, _sz]),
     "mufft_cuda_device_alloc": (_vp, [_sz]),
     "mufft_cuda_device_free": (None, [_vp]),
+    "mufft_cuda_host_alloc": (_vp, [_sz]),
+    "mufft_cuda_host_free": (None, [_vp]),
     "mufft_cuda_copy": (_i, [_vp, _vp, _sz]),
     "mufft_cuda_memset": (_i, [_vp, _i, _sz]),
     "mufft_cuda_ipc_export": (_i, [_vp, _vp]),

@@ -84,18 +84,9 @@ __host__ __device__ constexpr bool f2d_supported(int nx, int ny)
 // Row pitch (complex elements) of the intermediate / output image a kind works on, columns that carry data.
 __host__ __device__ constexpr int f2d_pitch(int nx, int kind) { return kind == F2D_C2C ? nx : (kind == F2D_C2R ? nx + 2 : 2 * nx); }
 __host__ __device__ constexpr int f2d_width(int nx, int kind) { return kind == F2D_C2C ? nx : (kind == F2D_R2C_FULL ? 2 * nx : nx + 1); }
-// Row groups per row ticket.  Short rows (16 values per thread: 256 / 512 points) are little work per ticket - 8 rows of
-// 256 points against 8 columns of up to 2048 - so a ticket takes several groups back to back; the rows of a group belong
-// to one warp each, no CTA barrier in between.
-#ifndef MUFFT_F2D_ROW_REPEAT
-#define MUFFT_F2D_ROW_REPEAT 1
-#endif
-__host__ __device__ constexpr int f2d_row_repeat(int nx, int ny)
-{
-    const int want = engine_regs(nx) <= 16 && engine_threads(nx) <= 32 ? MUFFT_F2D_ROW_REPEAT : 1;
-    return ny % (f2d_rows_per_tile(nx) * want) == 0 && ny / (f2d_rows_per_tile(nx) * want) >= 8 ? want : 1;
-}
-__host__ __device__ constexpr unsigned f2d_row_tiles(int nx, int ny) { return ny / (f2d_rows_per_tile(nx) * f2d_row_repeat(nx, ny)); }
+// (Several row groups per row ticket for short rows - 8 rows of 256 points are little work per ticket - were measured in
+// round 2: 2 groups -4..+2 %, 4 groups -20 %: profiles/r02h_ab.txt.  One group per ticket it stays.)
+__host__ __device__ constexpr unsigned f2d_row_tiles(int nx, int ny) { return ny / f2d_rows_per_tile(nx); }
 __host__ __device__ constexpr unsigned f2d_col_tiles(int nx, int ny, int kind) { return (f2d_width(nx, kind) + f2d_cols_per_tile(ny) - 1) / f2d_cols_per_tile(ny); }
 __host__ __device__ constexpr unsigned f2d_tickets_per_image(int nx, int ny, int kind) { return f2d_row_tiles(nx, ny) + f2d_col_tiles(nx, ny, kind); }
 __host__ __device__ constexpr size_t f2d_xch_elems(int nx, int ny, int vx)
@@ -184,7 +175,7 @@ fft2d_fused_kernel(const mcu_2d_args a)
     constexpr int PITCH = f2d_pitch(NX, KIND);   // rows of the image the column tiles work on
     constexpr int WIDTH = f2d_width(NX, KIND);   // columns to transform
     constexpr bool COLS_FIRST = KIND == F2D_C2R;
-    constexpr int REP = f2d_row_repeat(NX, NY);
+    constexpr int REP = 1; // row groups per row ticket
     constexpr unsigned NR = f2d_row_tiles(NX, NY), NC = f2d_col_tiles(NX, NY, KIND);
     constexpr unsigned NP = COLS_FIRST ? NC : NR; // producer / consumer tiles per image
     constexpr unsigned NQ = COLS_FIRST ? NR : NC;

@@ -43,8 +43,6 @@ static cudaError_t launch_n1(const mcu_longcols_args &a, cudaStream_t stream, un
 cudaError_t longcols_launch(const mcu_longcols_args &a, cudaStream_t stream, unsigned *lag_only)
 {
     switch (a.n1) {
-    case 4: return launch_n1<4>(a, stream, lag_only);
-    case 8: return launch_n1<8>(a, stream, lag_only);
     case 16: return launch_n1<16>(a, stream, lag_only);
     case 32: return launch_n1<32>(a, stream, lag_only);
     default: return cudaErrorInvalidValue;

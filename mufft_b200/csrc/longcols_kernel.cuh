@@ -1,4 +1,4 @@
-// Column transforms of 4096 .. 32768 points (the column pass of a slab-decomposed 2D transform, BASELINE configs[4])
+// Column transforms of 16384 and 32768 points (the column pass of a slab-decomposed 2D transform, BASELINE configs[4])
 // in ONE persistent launch and ONE pass over HBM: the four-step split n = N1 x 1024 down the columns of a row-major
 // [n][width] matrix, with the intermediate of a block of 32 columns kept in L2.
 //
@@ -31,7 +31,7 @@ namespace mufft {
 #define LONGCOLS_N2 1024
 #define LONGCOLS_CB 32       // columns per block
 #define LONGCOLS_THREADS 256
-__host__ __device__ constexpr bool longcols_supported(int n1) { return n1 == 4 || n1 == 8 || n1 == 16 || n1 == 32; }
+__host__ __device__ constexpr bool longcols_supported(int n1) { return n1 == 16 || n1 == 32; } // 4 / 8 work too but lose to two sweeps
 __host__ __device__ constexpr unsigned longcols_a_tiles() { return (LONGCOLS_N2 / 16) * (LONGCOLS_CB / 16); }
 __host__ __device__ constexpr unsigned longcols_b_tiles(int n1) { return (unsigned)n1 * (LONGCOLS_CB / 8); }
 __host__ __device__ constexpr size_t longcols_slot_elems(int n1) { return (size_t)n1 * LONGCOLS_N2 * LONGCOLS_CB; }

@@ -1006,6 +1006,20 @@ void mufft_cuda_device_free(void *ptr)
     registry_remove(ptr);
     (void)mcu_free(ptr);
 }
+void *mufft_cuda_host_alloc(size_t size)
+{
+    void *ptr = NULL;
+    if (!have_device()) return NULL;
+    if (fail(mcu_malloc_pinned(&ptr, size), "cudaHostAlloc") != 0) return NULL;
+    registry_add(ptr, size, MCU_MEM_PINNED);
+    return ptr;
+}
+void mufft_cuda_host_free(void *ptr)
+{
+    if (ptr == NULL) return;
+    registry_remove(ptr);
+    (void)mcu_free_pinned(ptr);
+}
 int mufft_cuda_copy(void *dst, const void *src, size_t bytes)
 {
     TRY(mcu_copy_async(dst, src, bytes, tls_stream));

@@ -171,7 +171,7 @@ int mcu_launch_long(const mcu_long_args *a, void *)
 #undef X
     return 1;
 }
-int mcu_longcols_supported(unsigned n) { return n == 4096 || n == 8192 || n == 16384 || n == 32768; }
+int mcu_longcols_supported(unsigned n) { return n == 16384 || n == 32768; }
 size_t mcu_longcols_slot_elems(unsigned n) { return (size_t)n * 32; }
 unsigned mcu_longcols_default_lag(unsigned n) { return mcu_longcols_supported(n) ? 1 : 0; }
 int mcu_launch_longcols(const mcu_longcols_args *a, void *)

@@ -462,10 +462,10 @@ def test_small_repeated_calls_try_the_graph_path_and_fall_back(lib, oracle):
     raw.mufft_free(py)
 
 
-@pytest.mark.parametrize("ny,flags,launches", [(4096, 0, 2), (4096, TWO_KERNEL, 3), (2048, 0, 2)])
+@pytest.mark.parametrize("ny,flags,launches", [(16384, 0, 2), (16384, TWO_KERNEL, 3), (4096, 0, 3), (2048, 0, 2)])
 def test_long_columns_of_a_2d_plan(lib, oracle, ny, flags, launches):
-    """2D plans with more than 2048 rows: the column pass is ONE launch of the four-step column kernel (4096..32768
-    rows), or two sweeps of the column kernel with MUFFT_CUDA_FLAG_TWO_KERNEL; up to 2048 rows one column kernel.
+    """2D plans with more than 2048 rows: the column pass is ONE launch of the four-step column kernel (16384 / 32768
+    rows), else or with MUFFT_CUDA_FLAG_TWO_KERNEL two sweeps of the column kernel; up to 2048 rows one column kernel.
     (+ 1 launch for the rows.)"""
     raw = lib.lib
     nx = 40 if False else 32

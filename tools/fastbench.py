@@ -161,6 +161,58 @@ def run(name, units, reps, flags):
             nbytes, flops = 4.0 * nx * ny + 8.0 * w * ny, 2.5 * nx * ny * math.log2(nx * ny)
         m.mufft_free_plan_2d(plan)
         tol = 1e-6 * math.log2(nx * ny)
+    elif name.startswith("e2e"):
+        # the host-pointer path: pinned host buffers through the synchronous batch call (H2D, kernels, D2H pipelined by the
+        # library), wall clock; next to it what plain pinned copies of the same buffers reach both ways at once
+        n = int(name[3:])
+        units = units or max(1, (1 << 31) // (8 * n))
+        nbytes_buf = 8 * n * units
+        hin, hout = m.mufft_cuda_host_alloc(nbytes_buf), m.mufft_cuda_host_alloc(nbytes_buf)
+        assert hin and hout, m.mufft_cuda_last_error()
+        vin = np.ctypeslib.as_array((C.c_float * (2 * n * units)).from_address(hin))
+        vout = np.ctypeslib.as_array((C.c_float * (2 * n * units)).from_address(hout))
+        vin[:] = 0
+        host = {b: rnd(rng, 2 * n) for b in ends(units)}
+        for b, h in host.items():
+            vin[b * 2 * n:(b + 1) * 2 * n] = h
+        plan = m.mufft_create_plan_1d_c2c(n, -1, flags)
+        times = []
+        for i in range(1 + reps):
+            t0 = time.perf_counter()
+            assert m.mufft_execute_plan_1d_batch(plan, hout, hin, units, 0, 0) == 0, m.mufft_cuda_last_error()
+            if i:
+                times.append((time.perf_counter() - t0) * 1e3)
+        times.sort()
+        best, med = times[0], times[len(times) // 2]
+        err = max(rel_l2(vout[b * 2 * n:(b + 1) * 2 * n].view(np.complex64), np.fft.fft(h.view(np.complex64).astype(np.complex128))) for b, h in host.items())
+        m.mufft_free_plan_1d(plan)
+        bus = None
+        if EV.rt is not None:  # raw bus rate: the same buffers, plain copies both ways at once on two streams
+            d1, d2 = dev(min(2 * n * units, 1 << 28)), dev(min(2 * n * units, 1 << 28))
+            cb = min(nbytes_buf, 1 << 30)
+            s1, s2 = C.c_void_p(), C.c_void_p()
+            EV.rt.cudaStreamCreateWithFlags(C.byref(s1), 1)
+            EV.rt.cudaStreamCreateWithFlags(C.byref(s2), 1)
+            EV.rt.cudaMemcpyAsync.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+            rates = []
+            for _ in range(3):
+                EV.rt.cudaDeviceSynchronize()
+                t0 = time.perf_counter()
+                EV.rt.cudaMemcpyAsync(d1.ptr, hin, cb, 4, s1)
+                EV.rt.cudaMemcpyAsync(hout, d2.ptr, cb, 4, s2)
+                EV.rt.cudaDeviceSynchronize()
+                rates.append(2 * cb / (time.perf_counter() - t0) * 1e-9)
+            bus = max(rates)
+            # the timed output was overwritten by the probe copy: fine, parity was taken before
+        m.mufft_cuda_host_free(hin)
+        m.mufft_cuda_host_free(hout)
+        for d in bufs:
+            d.free()
+        gbs = 2.0 * nbytes_buf / med / 1e6
+        return {"workload": name, "units": units, "ms": round(med, 3), "ms_best": round(best, 3), "bus_gbs": round(gbs, 1),
+                "raw_both_ways_gbs": round(bus, 1) if bus else None, "over_bus": round(gbs / bus, 3) if bus else None,
+                "gflops": round(5.0 * n * math.log2(n) * units / med / 1e6, 1), "rel_l2": err, "ok": bool(err <= 2e-6 * math.log2(n)),
+                "gbs": round(gbs, 1), "frac": 0.0}
     elif name.startswith("cols"):
         # column pass of a slab transform: the plan's N-point C2C transform down the columns of ONE [N][W] matrix, in place
         n, w = (int(v) for v in name[4:].split("x"))
