@@ -1378,6 +1378,10 @@ static mufft_plan_2d *plan_2d_common(unsigned nx, unsigned ny, int direction, in
     plan->cols_engine = ny <= MCU_COLS_MAX_N;
     plan->flags = flags & PATH_FLAGS;
     plan->fused = !(flags & MUFFT_CUDA_FLAG_SEPARATE_2D) && mcu_2d_fused_supported(nx, ny);
+    /* C2R images whose rows have fewer than 512 complex points: 8 such rows are too little work per ticket of the fused
+     * kernel, the column kernel + row kernel through scratch are faster (512 x 512: 1.03 against 1.42 ms per 1024 images;
+     * from 512 complex points on the fused kernel wins or ties: profiles/README.md R2.5) */
+    if (kind == KIND_C2R && nx < 512) plan->fused = 0;
     stage_bind_device(&plan->st);
     if (axis_init(&plan->ax_x, nx, direction, nx > onchip_limit(flags) ? AXIS_ROWS : 0, flags) != 0 ||
         axis_init(&plan->ax_y, ny, direction, plan->cols_engine ? 0 : AXIS_COLS, flags) != 0) {

@@ -253,8 +253,8 @@ def test_fft_h_2d(lib, oracle, nx, ny):
 @pytest.mark.parametrize("separate", [0, 1])
 def test_fused_2d_is_the_default_and_a_plan_flag_turns_it_off(lib, oracle, kind, separate):
     """2D plans of 512 x 256 points (256-point row transforms for the real kinds): the whole batch is ONE launch of
-    the fused kernel for every kind - C2R through the plan's ring of intermediates - unless the plan was created
-    with MUFFT_CUDA_FLAG_SEPARATE_2D: then a row launch and a column launch through plan scratch."""
+    the fused kernel (C2R: only from 512 complex points per row on, through the plan's ring of intermediates) unless
+    the plan was created with MUFFT_CUDA_FLAG_SEPARATE_2D: then a row launch and a column launch through plan scratch."""
     raw = lib.lib
     nx, ny, batch = 512, 256, 5
     flags = SEPARATE_2D if separate else 0
@@ -274,11 +274,12 @@ def test_fused_2d_is_the_default_and_a_plan_flag_turns_it_off(lib, oracle, kind,
         plan = lib._create_plan_2d_r2c(nx, ny, flags | (cpu_libs.FLAG_FULL_R2C if kind == "r2c_full" else 0))
         pout, yv = managed(lib, np.zeros((batch, ny, nx), np.complex64))
     assert plan
-    assert bool(raw.mufft_cuda_plan_2d_paths(plan) & 4) == (not separate)
+    fused = not separate and kind != "c2r"  # C2R rows of 256 complex points are too short for the fused kernel to pay
+    assert bool(raw.mufft_cuda_plan_2d_paths(plan) & 4) == fused
     pin, _ = managed(lib, x)
     raw.mufft_cuda_launch_count(1)
     assert raw.mufft_execute_plan_2d_batch(plan, pout, pin, batch) == 0, raw.mufft_cuda_last_error()
-    assert raw.mufft_cuda_launch_count(1) == (2 if separate else 1)
+    assert raw.mufft_cuda_launch_count(1) == (1 if fused else 2)
     lib._free_plan_2d(plan)
     for b in range(batch):
         if kind == "c2c":
@@ -479,5 +480,28 @@ def test_long_columns_of_a_2d_plan(lib, oracle, ny, flags, launches):
     assert raw.mufft_cuda_launch_count(1) == launches
     lib._free_plan_2d(plan)
     assert cpu_libs.rel_l2(yv, oracle.c2c_2d(x, 1)) <= tol(nx * ny)
+    raw.mufft_free(pin)
+    raw.mufft_free(pout)
+
+
+def test_fused_2d_c2r_through_the_host_layer(lib, oracle):
+    """C2R images with rows of 2048 complex points (4096 reals) x 256 rows: ONE launch of the fused kernel - columns into
+    the plan's ring of intermediates, C2R rows out of it - for a batch longer than the ring."""
+    raw = lib.lib
+    nx, ny, batch = 4096, 256, 6
+    rng = np.random.default_rng(9)
+    real = rnd(rng, batch, ny, nx)
+    x = np.zeros((batch, ny, nx), np.complex64)
+    x[:, :, : nx // 2 + 1] = np.fft.rfft2(real.astype(np.float64)).astype(np.complex64)
+    plan = lib._create_plan_2d_c2r(nx, ny, 0)
+    assert plan and raw.mufft_cuda_plan_2d_paths(plan) & 4
+    pin, _ = managed(lib, x)
+    pout, yv = managed(lib, np.zeros((batch, ny, nx), np.float32))
+    raw.mufft_cuda_launch_count(1)
+    assert raw.mufft_execute_plan_2d_batch(plan, pout, pin, batch) == 0, raw.mufft_cuda_last_error()
+    assert raw.mufft_cuda_launch_count(1) == 1
+    lib._free_plan_2d(plan)
+    for b in (0, batch - 1):
+        assert cpu_libs.rel_l2(yv[b], oracle.c2r_2d(x[b])) <= tol(nx * ny)
     raw.mufft_free(pin)
     raw.mufft_free(pout)
