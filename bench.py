@@ -557,10 +557,13 @@ class Job:
             raise RuntimeError("execute failed: " + self.m.mufft_cuda_last_error().decode())
 
 
-def slab_also(m, ndev, nx=32768, ny=32768, reps=5):
-    """One nx x ny C2C transform over ndev devices of this process (include/mufft_cuda.h slab plan), data resident in
-    the plan's device slabs; device-event time (max over devices), best of `reps` after 2 warm-up runs."""
-    plan = m.mufft_cuda_create_plan_2d_slab_c2c(nx, ny, m.MUFFT_FORWARD, ndev, None, 0)
+def slab_also(m, ndev, nx=32768, ny=32768, reps=5, real=False):
+    """One nx x ny C2C (real: R2C) transform over ndev devices of this process (include/mufft_cuda.h slab plan), data
+    resident in the plan's device slabs; device-event time (max over devices), median of `reps` after 2 warm-up runs."""
+    if real:
+        plan = m.mufft_cuda_create_plan_2d_slab_r2c(nx, ny, ndev, None, 0)
+    else:
+        plan = m.mufft_cuda_create_plan_2d_slab_c2c(nx, ny, m.MUFFT_FORWARD, ndev, None, 0)
     if not plan:
         raise RuntimeError(m.mufft_cuda_last_error().decode())
     try:
@@ -571,16 +574,17 @@ def slab_also(m, ndev, nx=32768, ny=32768, reps=5):
             if m.mufft_cuda_execute_plan_2d_slab(plan) != 0:
                 raise RuntimeError(m.mufft_cuda_last_error().decode())
             if i >= 2:
-                times.append(m.mufft_cuda_slab_last_ms(plan))
-        ms = sorted(times)[len(times) // 2]
+                times.append((m.mufft_cuda_slab_last_ms(plan), m.mufft_cuda_slab_last_rows_ms(plan)))
+        ms, rows_ms = sorted(times)[len(times) // 2]
     finally:
         m.mufft_cuda_free_plan_2d_slab(plan)
         m.mufft_cuda_set_device(int(os.environ.get("LOCAL_RANK", "0")))
-    flops = 5.0 * nx * ny * (math.log2(nx) + math.log2(ny))
-    per_gpu_out = 8.0 * nx * ny * (ndev - 1) / ndev / ndev  # bytes leaving each GPU over NVLink
-    return {"workload": "single 2D C2C %dx%d over %d GPUs, C-ABI slab plan, peer-store exchange, transposed-out" % (nx, ny, ndev),
-            "ms": round(ms, 4), "gflops": round(flops / ms * 1e-6, 1), "nvlink_gbs_per_gpu_per_dir": round(per_gpu_out / ms * 1e-6, 1),
-            "hbm_gbs_per_gpu_algorithmic": round(16.0 * nx * ny / ndev / ms * 1e-6, 1)}
+    flops = (2.5 if real else 5.0) * nx * ny * (math.log2(nx) + math.log2(ny))
+    per_gpu_out = (4.0 if real else 8.0) * nx * ny * (ndev - 1) / ndev / ndev  # bytes leaving each GPU over NVLink
+    return {"workload": "single 2D %s %dx%d over %d GPUs, C-ABI slab plan, peer-store exchange, transposed-out" % ("R2C" if real else "C2C", nx, ny, ndev),
+            "ms": round(ms, 4), "rows_and_exchange_ms": round(rows_ms, 4), "gflops": round(flops / ms * 1e-6, 1),
+            "nvlink_gbs_per_gpu_per_dir_in_row_pass": round(per_gpu_out / rows_ms * 1e-6, 1) if rows_ms > 0 else None,
+            "hbm_gbs_per_gpu_algorithmic": round((8.0 if real else 16.0) * nx * ny / ndev / ms * 1e-6, 1)}
 
 
 def time_steps(torch, dist, job, warmup, steps):
@@ -805,10 +809,11 @@ def main():
         dist.barrier()
         torch.cuda.synchronize()
         if rank == 0:
-            try:
-                also["slab2d"] = slab_also(m, world)
-            except Exception as exc:
-                also["slab2d"] = {"error": repr(exc)[:200]}
+            for key, real in (("slab2d", False), ("slab2d_r2c", True)):
+                try:
+                    also[key] = slab_also(m, world, real=real)
+                except Exception as exc:
+                    also[key] = {"error": repr(exc)[:200]}
             open(flag, "w").close()
         else:
             t_end = time.time() + 300

@@ -167,6 +167,8 @@ unsigned mufft_cuda_slab_output_columns(const mufft_plan_2d_slab *plan, unsigned
 int mufft_cuda_execute_plan_2d_slab(mufft_plan_2d_slab *plan);
 /* Device time of the last execute in milliseconds: max over the devices, row pass start to column pass end. */
 float mufft_cuda_slab_last_ms(const mufft_plan_2d_slab *plan);
+/* ... and of its row pass + exchange alone (the column pass is the rest, less the wait for the slowest device). */
+float mufft_cuda_slab_last_rows_ms(const mufft_plan_2d_slab *plan);
 /* Whole arrays in host memory: input [Ny][Nx] (complex, R2C: floats), output [Ny][Nx] complex in natural order
  * (R2C: [Ny][Nx/2 + 1]), i.e. what mufft_execute_plan_2d computes, on ndev devices. */
 int mufft_cuda_execute_plan_2d_slab_host(mufft_plan_2d_slab *plan, void *output, const void *input);

@@ -105,6 +105,7 @@ SIGNATURES = {
     "mufft_cuda_slab_output_columns": (_u, [_vp, _u, C.POINTER(_u)]),
     "mufft_cuda_execute_plan_2d_slab": (_i, [_vp]),
     "mufft_cuda_slab_last_ms": (C.c_float, [_vp]),
+    "mufft_cuda_slab_last_rows_ms": (C.c_float, [_vp]),
     "mufft_cuda_execute_plan_2d_slab_host": (_i, [_vp, _vp, _vp]),
     "mufft_cuda_plan_1d_uses_engine": (_i, [_vp]),
     "mufft_cuda_plan_2d_paths": (_i, [_vp]),

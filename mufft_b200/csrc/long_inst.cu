@@ -17,14 +17,14 @@ namespace mufft {
 template <int DIR, int IN_MODE, bool TO_PEERS>
 static cudaError_t launch_long(const mcu_long_args &a, cudaStream_t stream, int *ctas_only)
 {
-  if constexpr (!long_supported(LONG_N1, LONG_N2)) {
+  if constexpr (!long_supported(LONG_N1, LONG_N2, TO_PEERS)) {
     (void)a; (void)stream; (void)ctas_only;
     return cudaErrorInvalidValue;
   } else {
     static launch_cfg cfg;
-    constexpr int SLOTS = 1, THREADS = long_cta_threads(LONG_N2);
+    constexpr int SLOTS = 1, THREADS = long_cta_threads(LONG_N2, TO_PEERS);
     auto kernel = fft_long_kernel<LONG_N1, LONG_N2, DIR, IN_MODE, TO_PEERS>;
-    constexpr size_t smem = long_smem_bytes(LONG_N2);
+    constexpr size_t smem = long_smem_bytes(LONG_N2, TO_PEERS);
     int resident = 0;
     cudaError_t err = launch_prepare(cfg, kernel, smem, THREADS, &resident);
     if (err != cudaSuccess) return err;

@@ -47,24 +47,26 @@ __device__ __forceinline__ void discard_l2_128(const void *p)
     asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
 #endif
 }
-// 16 rows per group need a 1024-thread CTA and 270 KB of exchange area at n2 = 2048: 8 there
-__host__ __device__ constexpr int long_tile_rows(int n2) { return n2 <= 1024 ? MUFFT_LONG_TR : 8; }
-__host__ __device__ constexpr int long_cta_threads(int n2) { return long_tile_rows(n2) * engine_threads(n2); }
+// Rows per group of step B.  Local output: 8 (64-byte runs; 16 measured the same).  Scatter to peer slabs over NVLink:
+// 16, so that every store run is a whole 128-byte line.  16 rows need a 1024-thread CTA and 270 KB of exchange area at
+// n2 = 2048: 8 there either way.
+__host__ __device__ constexpr int long_tile_rows(int n2, bool peers = false) { return n2 <= 1024 ? (peers ? 16 : MUFFT_LONG_TR) : 8; }
+__host__ __device__ constexpr int long_cta_threads(int n2, bool peers = false) { return long_tile_rows(n2, peers) * engine_threads(n2); }
 // Row pitch of the exchange area, in cpx: after the mapping switch a half-warp reads TR rows x 16/TR
 // consecutive elements; pitch = 2 (mod 16) for TR = 8, odd for TR = 16 puts them in 16 different banks.
-__host__ __device__ constexpr int long_row_pitch(int n2)
+__host__ __device__ constexpr int long_row_pitch(int n2, bool peers = false)
 {
     int se = engine_smem_elems(n2);
-    if (long_tile_rows(n2) >= 16) return se | 1;
+    if (long_tile_rows(n2, peers) >= 16) return se | 1;
     while (se % 16 != 2) se++;
     return se;
 }
-__host__ __device__ constexpr size_t long_smem_bytes(int n2) { return (size_t)long_tile_rows(n2) * long_row_pitch(n2) * sizeof(float2); }
-__host__ __device__ constexpr bool long_supported(int n1, int n2)
+__host__ __device__ constexpr size_t long_smem_bytes(int n2, bool peers = false) { return (size_t)long_tile_rows(n2, peers) * long_row_pitch(n2, peers) * sizeof(float2); }
+__host__ __device__ constexpr bool long_supported(int n1, int n2, bool peers = false)
 {
-    return (n1 == 16 || n1 == 32) && engine_regs(n2) > 0 && engine_num_passes(n2) >= 2 && long_cta_threads(n2) <= 1024 &&
-           n2 % long_cta_threads(n2) == 0 && n1 % long_tile_rows(n2) == 0 && long_smem_bytes(n2) <= 227 * 1024 &&
-           long_tile_rows(n2) <= 15 + (engine_threads(n2) <= 32 ? 64 : 0); // named barriers 1..15 when a row spans several warps
+    return (n1 == 16 || n1 == 32) && engine_regs(n2) > 0 && engine_num_passes(n2) >= 2 && long_cta_threads(n2, peers) <= 1024 &&
+           n2 % long_cta_threads(n2, peers) == 0 && n1 % long_tile_rows(n2, peers) == 0 && long_smem_bytes(n2, peers) <= 227 * 1024 &&
+           long_tile_rows(n2, peers) <= 15 + (engine_threads(n2) <= 32 ? 64 : 0); // named barriers 1..15 when a row spans several warps
 }
 // ---- step A: N1-point transforms down the columns of the [N1][N2] view, `THREADS` threads -------------------
 template <int N1, int N2, int DIR, int IN_MODE, int THREADS>
@@ -91,13 +93,13 @@ __device__ __forceinline__ void long_step_a(const cpx *__restrict__ in, cpx *__r
 template <int N1, int N2, int DIR, bool TO_PEERS, typename Sync>
 __device__ __forceinline__ void long_step_b(const mcu_long_args &a, size_t b, cpx *__restrict__ scratch, cpx *smem, const cpx *__restrict__ tw, int tid, Sync sync)
 {
-    constexpr int THREADS = long_cta_threads(N2);
+    constexpr int THREADS = long_cta_threads(N2, TO_PEERS);
     constexpr int R = engine_regs(N2);
     constexpr int T = N2 / R;
-    constexpr int TR = long_tile_rows(N2);
+    constexpr int TR = long_tile_rows(N2, TO_PEERS);
     constexpr int NP = engine_num_passes(N2);
     constexpr int SH = engine_pad_shift(N2);
-    constexpr int SE = long_row_pitch(N2);
+    constexpr int SE = long_row_pitch(N2, TO_PEERS);
     const int slot = tid / T, t = tid - slot * T;   // passes 0 .. NP-2: lanes walk along a row
     const int slot2 = tid % TR, t2 = tid / TR;      // last pass: lanes walk across the TR rows
 #pragma unroll 1
@@ -154,12 +156,12 @@ __device__ __forceinline__ void long_step_b(const mcu_long_args &a, size_t b, cp
 // points as this kernel with 8 or 16 rows per group: with ~110 registers per thread an SM holds 16 warps whichever way
 // they are arranged, and ncu shows them waiting for loads a third of the time.  profiles/README.md keeps the numbers.)
 template <int N1, int N2, int DIR, int IN_MODE, bool TO_PEERS>
-__global__ void __launch_bounds__(long_cta_threads(N2), long_cta_threads(N2) <= 256 ? 2 : 1)
+__global__ void __launch_bounds__(long_cta_threads(N2, TO_PEERS), long_cta_threads(N2, TO_PEERS) <= 256 ? 2 : 1)
 fft_long_kernel(const mcu_long_args a)
 {
     constexpr int N = N1 * N2;
-    constexpr int THREADS = long_cta_threads(N2);
-    static_assert(long_supported(N1, N2), "shape");
+    constexpr int THREADS = long_cta_threads(N2, TO_PEERS);
+    static_assert(long_supported(N1, N2, TO_PEERS), "shape");
     static_assert(IN_MODE == MCU_IN_COMPLEX || IN_MODE == MCU_IN_HALF, "input modes: complex, zero-padded upper half");
     MUFFT_DYNAMIC_SMEM(smem_raw);
     cpx *smem = reinterpret_cast<cpx *>(smem_raw);

@@ -18,8 +18,9 @@ extern "C" int EMU_CAT(emu_launch_long_, EMU_N1, x, EMU_N2)(const mcu_long_args 
     if (a->scratch_slots / SLOTS < grid) grid = a->scratch_slots / SLOTS;
     if (grid == 0) return 1;
     const emu::idx3 g{ (unsigned)grid, 1, 1 };
-    const unsigned threads = long_cta_threads(N2);
-    const size_t smem = long_smem_bytes(N2);
+    const bool peers = a->to_peers != 0;
+    const unsigned threads = long_cta_threads(N2, peers);
+    const size_t smem = long_smem_bytes(N2, peers);
     const bool fwd = a->direction < 0;
 #define fft_long_kernel_for(...) fft_long_kernel<__VA_ARGS__>(*a)
     // CTAs are independent of each other: run them one after another
