@@ -3,7 +3,7 @@
 #   <label> | <EXTRA nvcc flags> | <workload[:units] ...> | <lengths for tools/quick_check.py>
 # -> ab_variants/<label>/libmufft_b200.so.  tools/ab_run.sh then measures them on the GPU box
 # without spending GPU time on compiling.
-cfg=${1:-tools/ab.txt}
+cfg=${1:-tools/ab_example.txt}
 mkdir -p ab_variants
 while IFS='|' read -r LABEL EXTRA WLS CHECKS; do
   LABEL=$(echo $LABEL); [ -z "$LABEL" ] && continue

@@ -3,7 +3,7 @@
 # tools/fastbench.py - no torch import, a few seconds per variant.  Config lines:
 #   <label> | <EXTRA nvcc flags> | <fastbench workloads> | <ignored>
 # The product library is put back at the end.  Results: gpurun_out/fastbench.jsonl (label = variant).
-cfg=${1:-tools/ab_r2.txt}
+cfg=${1:-tools/ab_example.txt}
 mkdir -p gpurun_out
 cp mufft_b200/libmufft_b200.so /tmp/libmufft_b200.product.so
 while IFS='|' read -r LABEL EXTRA WLS CHECKS; do

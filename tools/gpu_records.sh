@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU call L: the records as the driver takes them, on the final tree - full suite with -x, smoke, bench of record,
+# The records as the driver takes them (run under gpurun on one B200; outputs under gpurun_out/r02l_*, copied to profiles/) - full suite with -x, smoke, bench of record,
 # reference arm, ncu launch list of the bench command, ncu --set full of the headline kernel
 mkdir -p gpurun_out
 python -m pytest tests/ -x -q -m gpu -p no:cacheprovider > gpurun_out/r02l_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/r02l_pytest.log
