@@ -13,10 +13,9 @@ extern "C" {
 
 /* Largest transform length handled by the single-kernel shared-memory engine. */
 #define MCU_ENGINE_MAX_N 8192
-/* Row kernels are also built for this length (one 512-thread CTA per transform, one CTA per SM);
- * the host layer prefers them to the two-kernel split unless told otherwise
- * (mufft_cuda_set_onchip_limit / MUFFT_CUDA_ONCHIP_LIMIT).  Convolution in one kernel and the column
- * kernels stop at MCU_ENGINE_MAX_N / MCU_COLS_MAX_N. */
+/* Row kernels are also built for this length (one 512-thread CTA per transform, one CTA per SM); plans use them
+ * unless created with MUFFT_CUDA_FLAG_TWO_KERNEL / _GENERIC_PASSES / _FOUR_STEP_16K.  Convolution in one kernel and the
+ * column kernels stop at MCU_ENGINE_MAX_N / MCU_COLS_MAX_N. */
 #define MCU_ENGINE_BIG_N 16384
 /* Largest column length handled by the shared-memory column kernel. */
 #define MCU_COLS_MAX_N 2048

@@ -71,6 +71,12 @@ def test_no_cpu_fallback_without_a_device():
     assert not m.mufft_create_plan_2d_c2c(8, 8, m.MUFFT_FORWARD, 0)
     assert not m.mufft_create_plan_conv(64, 0, 0)
     assert not m.mufft_alloc(1024)
+    assert not m.mufft_cuda_device_alloc(1024) and not m.mufft_cuda_host_alloc(1024)
+    assert not m.mufft_cuda_create_plan_2d_slab_c2c(64, 64, m.MUFFT_FORWARD, 1, None, 0)
+    assert not m.mufft_cuda_create_plan_2d_slab_r2c(64, 64, 1, None, 0)
+    m.mufft_cuda_free_plan_2d_slab(None)
+    m.mufft_cuda_device_free(None)
+    m.mufft_cuda_host_free(None)
     m.mufft_free(None)
     m.mufft_free_plan_1d(None)
     m.mufft_free_plan_2d(None)
