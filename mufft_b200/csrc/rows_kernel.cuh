@@ -102,13 +102,12 @@ __device__ __forceinline__ void rows_load(cpx (&v)[engine_regs(N, V)], Ptr in, c
 #pragma unroll
         for (int e = 0; e < R; e++) v[e] = e < R / 2 ? in[t + e * T] : make_float2(0.0f, 0.0f);
     } else if constexpr (IN_MODE == MCU_IN_MUL) {
-        cpx w[R];
-#pragma unroll
-        for (int e = 0; e < R; e++) w[e] = __ldg(in2 + t + e * T);
+        // the block spectrum (HBM) first, all loads in flight; the filter bins (L1 / L2 hits: one filter for the whole
+        // batch) are then fetched as they are used - holding all R of them as well would need 2 R register pairs
 #pragma unroll
         for (int e = 0; e < R; e++) v[e] = in[t + e * T];
 #pragma unroll
-        for (int e = 0; e < R; e++) v[e] = cscale(norm, cmul(v[e], w[e]));
+        for (int e = 0; e < R; e++) v[e] = cscale(norm, cmul(v[e], __ldg(in2 + t + e * T)));
     } else if constexpr (IN_MODE == MCU_IN_MULACC) {
         // partition loop outermost: every partition is one coalesced sweep over the block spectrum
 #pragma unroll
