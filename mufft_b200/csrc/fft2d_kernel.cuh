@@ -371,6 +371,10 @@ fft2d_fused_kernel(const mcu_2d_args a)
     }
 }
 
+// (A pipelined variant - tickets drawn two ahead and published a barrier early, so that every warp issues the next tile's
+// loads before it goes to the ticket barrier - was built and measured in round 2 as well: 1.303 ms against 1.213 ms for
+// 1024 x 1024 x 256; ncu shows the load stalls (16 % -> 9 % of the samples) simply turning into barrier stalls (17 % -> 26 %):
+// profiles/r02n_ab.txt, r02n_c2c2d1024_pipe_rejected.txt.  Gone too.)
 // (A split variant - row groups and a column half on the two halves of a 512-thread CTA, static work sequences, no
 // tickets and no CTA-wide barrier - was built and measured in round 2: 1.402 ms against 1.210 ms for 1024 x 1024 x 256,
 // profiles/r02e_ab.txt and r02e_c2c2d1024_split_rejected.txt.  Desynchronising the two passes does not help when the
