@@ -61,10 +61,12 @@ __attribute__((constructor)) static void read_env(void)
  * intermediate.  L2-sized groups measured SLOWER than whole-batch launches (profiles/README.md section 3:
  * 2D R2C 1024^2 x 256 1.40 ms with 86 launches against 0.92 ms with 2), so the cap only bounds the scratch. */
 #define MID_GROUP_BYTES ((size_t)2048 << 20)
-/* Long columns (two sweeps of the column kernel): columns per block, as bytes of the block's intermediate.  With the
- * second sweep DISCARDING the intermediate from L2 as it reads it, an L2-sized block never touches HBM. */
+/* Long columns on two sweeps of the column kernel (lengths the one-launch kernel of longcols_kernel.cuh does not take):
+ * columns per block, as bytes of the block's intermediate.  L2-sized blocks (16 / 32 / 64 MiB, second sweep discarding the
+ * intermediate as it reads it) were measured and LOSE to whole-slab sweeps - 1.47 / 1.23 / 1.09 ms against 1.04 ms at
+ * 32768 x 4096 (profiles/r02g_ab_cols_blocks.txt): launch gaps and wave tails again.  The cap only bounds the scratch. */
 #ifndef MUFFT_COLS_BLOCK_MB
-#define MUFFT_COLS_BLOCK_MB 32
+#define MUFFT_COLS_BLOCK_MB 1024
 #endif
 #define COLS_BLOCK_BYTES ((size_t)MUFFT_COLS_BLOCK_MB << 20)
 #define SCRATCH_CAP_BYTES ((size_t)1 << 30)
