@@ -50,7 +50,7 @@ __host__ __device__ constexpr int f2d_flavour(int nx, int ny)
 #ifdef MUFFT_F2D_FLAVOUR
     return MUFFT_F2D_FLAVOUR;
 #else
-    return (nx == ny && (nx == 1024 || nx == 512)) ? F2D_SMEM_TW : F2D_DERIVE;
+    return (nx == ny && nx == 1024) ? (F2D_SMEM_TW | F2D_DERIVE) : (nx == ny && nx == 512) ? F2D_SMEM_TW : F2D_DERIVE; // profiles/r02q_ab.txt
 #endif
 }
 __host__ __device__ constexpr int f2d_min_blocks(int nx, int ny)

@@ -183,7 +183,7 @@ __host__ __device__ constexpr engine_shape_t engine_shape(int n, int variant = 0
     case 128: return { 8, 3, { 8, 8, 2, 1 } , 256, 1, 0, 1 };
     case 256: return { 16, 2, { 16, 16, 1, 1 } , 256, 1, 0, 1 };
     case 512: return { 16, 3, { 16, 16, 2, 1 } , 256, 1, 0, 1 };
-    case 1024: return { 32, 2, { 32, 32, 1, 1 }, 128, 1, 0, 0 };
+    case 1024: return { 32, 2, { 32, 32, 1, 1 }, 128, 1, 0, 1 }; // packed: 1D 1.03 -> 1.05, fused 2D 1.210 -> 1.191 ms (profiles/r02p_ab.txt)
     case 2048: return { 32, 3, { 32, 32, 2, 1 }, 64, 1, 0, 1 };
     case 4096: return { 16, 3, { 16, 16, 16, 1 }, 256, 3, 0, 1 };
     case 8192: return { 32, 3, { 32, 16, 16, 1 }, 256, 2, 0, 0 };

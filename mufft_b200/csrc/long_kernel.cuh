@@ -38,6 +38,38 @@ namespace mufft {
 #ifndef MUFFT_LONG_TR
 #define MUFFT_LONG_TR 8 // rows per group of step B (8: 64-byte output runs; 16: 128-byte runs, twice the CTA)
 #endif
+#ifndef MUFFT_LONG_PACKED_A
+#define MUFFT_LONG_PACKED_A 1 // packed complex adds (FADD2) in the register transforms of step A (measured: 65536 points 0.450 -> 0.460)
+#endif
+#ifndef MUFFT_LONG_MIN_BLOCKS
+#define MUFFT_LONG_MIN_BLOCKS 2 // CTAs of 256 threads per SM
+#endif
+// Store of an intermediate that is read back from L2 a few microseconds later: the line is marked evict_last, so that the
+// streaming input / output lines passing through L2 push it out less easily (measured, profiles/r02o_ab.txt: 32768 points
+// 0.544 -> 0.564 of the roofline, 65536 points 0.437 -> 0.450, long columns 0.442 -> 0.446; -DMUFFT_SCRATCH_EVICT_LAST=0
+// gives plain stores).
+#ifndef MUFFT_SCRATCH_EVICT_LAST
+#define MUFFT_SCRATCH_EVICT_LAST 1
+#endif
+__device__ __forceinline__ unsigned long long scratch_policy()
+{
+#if MUFFT_SCRATCH_EVICT_LAST && !defined(MUFFT_EMU)
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+#else
+    return 0;
+#endif
+}
+__device__ __forceinline__ void st_scratch(cpx *p, cpx v, unsigned long long policy)
+{
+#if MUFFT_SCRATCH_EVICT_LAST && !defined(MUFFT_EMU)
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(policy) : "memory");
+#else
+    (void)policy;
+    *p = v;
+#endif
+}
 // Drop 128 bytes (aligned) from L2 without writing them back: the data is dead.
 __device__ __forceinline__ void discard_l2_128(const void *p)
 {
@@ -50,15 +82,19 @@ __device__ __forceinline__ void discard_l2_128(const void *p)
 // Rows per group of step B.  Local output: 8 (64-byte runs; 16 measured the same).  Scatter to peer slabs over NVLink:
 // 16, so that every store run is a whole 128-byte line.  16 rows need a 1024-thread CTA and 270 KB of exchange area at
 // n2 = 2048: 8 there either way.
-__host__ __device__ constexpr int long_tile_rows(int n2, bool peers = false) { return n2 <= 1024 ? (peers ? 16 : MUFFT_LONG_TR) : 8; }
+#ifndef MUFFT_LONG_TR2
+#define MUFFT_LONG_TR2 8 // rows per group at n2 = 2048 (4: two CTAs of 256 threads per SM instead of one of 512, 32-byte runs)
+#endif
+__host__ __device__ constexpr int long_tile_rows(int n2, bool peers = false) { return n2 <= 1024 ? (peers ? 16 : MUFFT_LONG_TR) : MUFFT_LONG_TR2; }
 __host__ __device__ constexpr int long_cta_threads(int n2, bool peers = false) { return long_tile_rows(n2, peers) * engine_threads(n2); }
 // Row pitch of the exchange area, in cpx: after the mapping switch a half-warp reads TR rows x 16/TR
-// consecutive elements; pitch = 2 (mod 16) for TR = 8, odd for TR = 16 puts them in 16 different banks.
+// consecutive elements; pitch = 16/TR (mod 16) for TR <= 8, odd for TR = 16 puts them in 16 different bank pairs.
 __host__ __device__ constexpr int long_row_pitch(int n2, bool peers = false)
 {
     int se = engine_smem_elems(n2);
-    if (long_tile_rows(n2, peers) >= 16) return se | 1;
-    while (se % 16 != 2) se++;
+    const int tr = long_tile_rows(n2, peers);
+    if (tr >= 16) return se | 1;
+    while (se % 16 != 16 / tr) se++;
     return se;
 }
 __host__ __device__ constexpr size_t long_smem_bytes(int n2, bool peers = false) { return (size_t)long_tile_rows(n2, peers) * long_row_pitch(n2, peers) * sizeof(float2); }
@@ -73,19 +109,20 @@ template <int N1, int N2, int DIR, int IN_MODE, int THREADS>
 __device__ __forceinline__ void long_step_a(const cpx *__restrict__ in, cpx *__restrict__ scratch, const cpx *__restrict__ roots, int tid)
 {
     constexpr int LG = ilog2(N1);
+    const unsigned long long policy = scratch_policy();
 #pragma unroll 1
     for (int c = tid; c < N2; c += THREADS) {
         cpx x[N1];
 #pragma unroll
         for (int m = 0; m < N1; m++)
             x[m] = (IN_MODE == MCU_IN_HALF && m >= N1 / 2) ? make_float2(0.0f, 0.0f) : __ldcs(in + c + m * N2); // rows >= N1/2 are the zero half: never read
-        dft_regs<N1, DIR, false>(x);
+        dft_regs<N1, DIR, MUFFT_LONG_PACKED_A != 0>(x);
         cpx base[LG];
 #pragma unroll
         for (int j = 0; j < LG; j++) base[j] = __ldg(roots + ((unsigned)c << j));
         TwTree<N1, LG, LG - 1, 0, true>::run(x, base, make_float2(1.0f, 0.0f));
 #pragma unroll
-        for (int k1 = 0; k1 < N1; k1++) scratch[k1 * N2 + c] = x[k1];
+        for (int k1 = 0; k1 < N1; k1++) st_scratch(scratch + k1 * N2 + c, x[k1], policy);
     }
 }
 
@@ -156,7 +193,7 @@ __device__ __forceinline__ void long_step_b(const mcu_long_args &a, size_t b, cp
 // points as this kernel with 8 or 16 rows per group: with ~110 registers per thread an SM holds 16 warps whichever way
 // they are arranged, and ncu shows them waiting for loads a third of the time.  profiles/README.md keeps the numbers.)
 template <int N1, int N2, int DIR, int IN_MODE, bool TO_PEERS>
-__global__ void __launch_bounds__(long_cta_threads(N2, TO_PEERS), long_cta_threads(N2, TO_PEERS) <= 256 ? 2 : 1)
+__global__ void __launch_bounds__(long_cta_threads(N2, TO_PEERS), long_cta_threads(N2, TO_PEERS) <= 256 ? MUFFT_LONG_MIN_BLOCKS : 1)
 fft_long_kernel(const mcu_long_args a)
 {
     constexpr int N = N1 * N2;

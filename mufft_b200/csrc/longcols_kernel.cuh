@@ -25,6 +25,7 @@
 #include "abi.h"
 #include "fft_engine.cuh"
 #include "fft2d_kernel.cuh" // ticket protocol helpers: ld_relaxed, red_relaxed_add, one-sided fences
+#include "long_kernel.cuh"  // st_scratch
 
 namespace mufft {
 
@@ -118,6 +119,7 @@ fft_longcols_kernel(const mcu_longcols_args a)
         s_wait[slot] = wait;
     };
 
+    const unsigned long long policy = scratch_policy();
     unsigned next_ticket = 0;
     if (tid == 0) publish(atomicAdd(ticket_counter, 1u), 0);
     for (int it = 0;; it++) {
@@ -157,14 +159,14 @@ fft_longcols_kernel(const mcu_longcols_args a)
 #pragma unroll
             for (int m = 0; m < N1; m++) x[m] = active ? __ldcs(in + (size_t)m * N2 * a.in_pitch) : make_float2(0.0f, 0.0f);
             if (tid == 0) release_pending();
-            dft_regs<N1, DIR, false>(x);
+            dft_regs<N1, DIR, MUFFT_LONG_PACKED_A != 0>(x);
             cpx base[LG];
 #pragma unroll
             for (int j = 0; j < LG; j++) base[j] = __ldg(roots + (y2 << j));
             TwTree<N1, LG, LG - 1, 0, true>::run(x, base, make_float2(1.0f, 0.0f));
             cpx *__restrict__ s = slot_base + ((size_t)(cb / 8) * N2 + y2) * 8 + (cb % 8);
 #pragma unroll
-            for (int k1 = 0; k1 < N1; k1++) s[(size_t)k1 * (CB / 8) * N2 * 8] = x[k1];
+            for (int k1 = 0; k1 < N1; k1++) st_scratch(s + (size_t)k1 * (CB / 8) * N2 * 8, x[k1], policy);
             if (tid == 0) pending = produced + block;
         } else {
             // ---- B tile: row group k1, 8 columns: 1024-point column transforms on the engine ---------------------
