@@ -2,6 +2,12 @@
 // f2d_launch_<nx>x<ny>(args, stream) (every kind, both directions of C2C) to dispatch.cu.
 #include "fft2d_kernel.cuh"
 #include "launch_util.cuh"
+#ifndef MUFFT_F2D_TMA
+#define MUFFT_F2D_TMA 1 // C2C images of the shapes the warp-specialised TMA kernel takes (1024 x 1024) go to it (fft2d_tma_kernel.cuh): 1.056 vs 1.176 ms
+#endif
+#if MUFFT_F2D_TMA
+#include "fft2d_tma_kernel.cuh"
+#endif
 
 #if !defined(F2D_NX) || !defined(F2D_NY)
 #error "compile with -DF2D_NX=<nx> -DF2D_NY=<ny>"
@@ -19,6 +25,70 @@ static unsigned default_lag(unsigned grid, unsigned per_image) { return 1 + (3 *
 
 // Shapes the fused kernel cannot take with the configured CTA size report "unsupported" to the
 // host layer (which then uses the row kernel + column kernel path) instead of failing the build.
+#if MUFFT_F2D_TMA
+#ifndef MUFFT_F2D_TMA_TWM
+#define MUFFT_F2D_TMA_TWM (MUFFT_TW_SMEM | MUFFT_TW_DERIVE)
+#endif
+// cuTensorMapEncodeTiled through the runtime's driver entry point query: no link against libcuda.
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                    const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn encode_tiled()
+{
+    static encode_tiled_fn fn = nullptr;
+    if (fn == nullptr) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult res;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &res) == cudaSuccess && res == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<encode_tiled_fn>(ptr);
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+// true = launched (or failed: *err); false = this call is not for the TMA kernel (alignment, pitch), use the ticket kernel
+template <int DIR>
+static bool launch_tma(const mcu_2d_args &a, cudaStream_t stream, cudaError_t *err)
+{
+  if constexpr (!f2d_tma_supported(F2D_NX, F2D_NY)) {
+    (void)a; (void)stream; (void)err;
+    return false;
+  } else {
+    if (a.out_image != (size_t)F2D_NX * F2D_NY || (a.in_image & 1) != 0 || (reinterpret_cast<uintptr_t>(a.out) & 127) != 0 ||
+        (reinterpret_cast<uintptr_t>(a.in) & 15) != 0 || a.batch * (size_t)F2D_NY >= 0x7fffffffull || a.batch < 8)
+        return false; // (up to 4 images the ticket kernel is the faster one, 34 vs 38 us: profiles/r02y_ab.txt)
+    encode_tiled_fn encode = encode_tiled();
+    if (encode == nullptr) return false;
+    static launch_cfg cfg;
+    auto kernel = fft2d_tma_kernel<F2D_NX, F2D_NY, DIR, MUFFT_F2D_TMA_TWM>;
+    constexpr size_t smem = f2d_tma_smem_bytes(F2D_NX, F2D_NY);
+    int ctas = 0;
+    if ((*err = launch_prepare(cfg, kernel, smem, F2D_TMA_THREADS, &ctas)) != cudaSuccess) return true;
+    f2d_tma_params p;
+    p.a = a;
+    const cuuint64_t dims[2] = { 2ull * F2D_NX, (cuuint64_t)a.batch * F2D_NY };
+    const cuuint64_t strides[1] = { (cuuint64_t)F2D_NX * sizeof(float2) };
+    const cuuint32_t box[2] = { 16, F2D_TMA_BOX_ROWS };
+    const cuuint32_t estr[2] = { 1, 1 };
+    if (encode(&p.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+        *err = cudaErrorInvalidValue;
+        return true;
+    }
+    constexpr unsigned per_image = f2d_tickets_per_image(F2D_NX, F2D_NY, F2D_C2C);
+    const unsigned long long tickets = (unsigned long long)a.batch * per_image;
+    if (tickets + (unsigned long long)ctas >= 0xffffffffull) { *err = cudaErrorInvalidConfiguration; return true; }
+    const unsigned grid = (unsigned)ctas;
+#ifdef MUFFT_F2D_TMA_LAG
+    if (p.a.lag == 0) p.a.lag = MUFFT_F2D_TMA_LAG;
+#endif
+    if (p.a.lag == 0) p.a.lag = default_lag(F2D_TMA_STAGES * grid, per_image); // three tiles in flight per CTA
+    kernel<<<grid, F2D_TMA_THREADS, smem, stream>>>(p);
+    *err = cudaGetLastError();
+    return true;
+  }
+}
+#endif
+
 template <int DIR, int KIND>
 static cudaError_t launch_kind(const mcu_2d_args &a, cudaStream_t stream, unsigned *lag_only)
 {
@@ -38,6 +108,12 @@ static cudaError_t launch_kind(const mcu_2d_args &a, cudaStream_t stream, unsign
         return cudaSuccess;
     }
     if (a.batch == 0) return cudaSuccess;
+#if MUFFT_F2D_TMA
+    if constexpr (KIND == F2D_C2C) {
+        cudaError_t terr = cudaSuccess;
+        if (launch_tma<DIR>(a, stream, &terr)) return terr;
+    }
+#endif
     const unsigned long long tickets = (unsigned long long)a.batch * per_image;
     if (tickets + (unsigned long long)ctas >= 0xffffffffull) return cudaErrorInvalidConfiguration; // every CTA draws one ticket past the end
     const unsigned grid = tickets < (unsigned long long)ctas ? (unsigned)tickets : (unsigned)ctas;

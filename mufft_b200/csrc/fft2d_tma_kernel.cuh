@@ -1,0 +1,430 @@
+// Batched 2D C2C transforms, warp-specialised: ONE persistent CTA per SM, tiles moved by the TMA unit.
+//
+// The ticket kernel of fft2d_kernel.cuh keeps a tile in REGISTERS from its loads to its stores: with 100 registers per
+// thread an SM holds two CTAs, and ncu shows each of them computing a quarter of the time and waiting for its own loads,
+// stores and barriers the rest (profiles/README.md R2.4).  Here the tile lives in SHARED memory from the moment the TMA
+// unit is asked for it until the TMA unit has written it back, so loads, stores and butterflies of different tiles
+// overlap inside one CTA:
+//
+//   loader   (1 thread)   draws tickets (same order as the ticket kernel: rows of image i, columns of image i - lag),
+//                         waits for a column ticket's rows to be announced, waits for a free buffer, asks the TMA unit
+//                         for the tile: 8 rows = 8 bulk copies of NX complex, 8 columns = boxes of 256 rows x 64 bytes
+//                         through a tensor map of the output buffer; completion arrives on the buffer's `full` barrier
+//   groups   (2 x 256)    wait for `full`, pull the tile into registers (natural order: element t + e*T in slot e),
+//                         run the engine with the buffer itself as exchange area, put the result back in natural
+//                         order, fence.proxy.async, arrive on `staged`
+//   storers  (3 threads)  one per buffer, each in a warp of its own: wait for `staged`, hand the buffer to the TMA unit
+//                         (bulk stores), wait until it has been READ (-> `freed`, the loader may refill it) and until
+//                         the writes are COMPLETE (-> release + add on the image's counter: a finished row tile)
+//
+// Buffer of sequence number s (per CTA) is s % 3, its group s % 2: while two tiles are being computed the third buffer
+// is in flight from or to memory.  Every wait is on work with a smaller ticket number, as in the ticket kernel: no
+// deadlock.  End of work: six EXIT entries (lcm of groups and buffers), so that every group sees three and every storer two.
+//
+// L2 policies: the input is read once (evict_first), the row-transformed intermediate must survive in L2 until its
+// columns are read `lag` images later (evict_last), the final store is streaming again (evict_first).  Without them
+// ncu shows 6.3 GB of DRAM traffic for 4.29 GB of images (profiles/r02r_tma_nohints.txt); with them 4.31 GB.
+//
+// Measured (profiles/README.md R2.12): 1024 x 1024 x 256 in 1.056 ms against 1.176 ms for the ticket kernel.  With the
+// groups doing NOTHING (MUFFT_TMA_DIAG=3: tiles are only moved in and out) the same launch takes 0.985 ms: that is the
+// L2's own limit - every byte crosses it four times on the SM side (in, intermediate out, intermediate in, out) and twice
+// on the DRAM side, 12.9 GB at the 13.1 TB/s the L2 sustains for a plain copy (6.55 TB/s read + written, both sides) - so a
+// single-pass 2D transform with the intermediate in L2 cannot exceed 0.67 of the HBM roofline on this chip.
+#pragma once
+
+#include <cuda.h>
+#include <cstdio>
+
+#include "fft2d_kernel.cuh"
+
+namespace mufft {
+
+#define F2D_TMA_GROUPS 2
+#define F2D_TMA_STAGES 3
+#define F2D_TMA_GROUP_THREADS 256
+// + a warp for the loader and one per storer
+#define F2D_TMA_THREADS (F2D_TMA_GROUPS * F2D_TMA_GROUP_THREADS + 32 * (1 + F2D_TMA_STAGES))
+#define F2D_TMA_BOX_ROWS 256
+enum { F2D_TMA_ROWS = 0, F2D_TMA_COLS = 1, F2D_TMA_EXIT = 2 };
+
+struct f2d_tma_params {
+    mcu_2d_args a;
+    alignas(64) CUtensorMap map; // output buffer as [batch * NY][2 * NX] floats, boxes of 16 floats x F2D_TMA_BOX_ROWS rows
+};
+
+__host__ __device__ constexpr bool f2d_tma_supported(int nx, int ny)
+{
+    return engine_regs(nx) == 32 && engine_regs(ny) == 32 && nx / 32 == 32 && ny / 32 == 32 && engine_num_passes(nx) == 2 && engine_num_passes(ny) == 2 &&
+           ny % F2D_TMA_BOX_ROWS == 0;
+}
+// A row's exchange area inside a buffer; its first nx elements hold the row in natural order (16-byte aligned for the bulk copies).
+__host__ __device__ constexpr int f2d_tma_row_pitch(int nx) { return (engine_smem_elems(nx, 0) + 1) & ~1; }
+__host__ __device__ constexpr size_t f2d_tma_buf_bytes(int nx, int ny)
+{
+    size_t r = (size_t)(F2D_TMA_GROUP_THREADS / (nx / 32)) * f2d_tma_row_pitch(nx), c = (size_t)(F2D_TMA_GROUP_THREADS / (ny / 32)) * engine_smem_elems(ny);
+    return ((r > c ? r : c) * sizeof(float2) + 127) / 128 * 128;
+}
+__host__ __device__ constexpr size_t f2d_tma_smem_bytes(int nx, int ny)
+{
+    return F2D_TMA_STAGES * f2d_tma_buf_bytes(nx, ny) + (size_t)f2d_tw_elems(nx, ny, 0) * sizeof(float2) + (F2D_TMA_GROUPS + 2) * F2D_TMA_STAGES * 8 + F2D_TMA_STAGES * 16;
+}
+
+#ifndef MUFFT_EMU
+// Timing experiments with WRONG results (never in the product build): 3 = the groups only pass the buffers on,
+// 4 = that, and every tile is moved as 8 rows, 5 = every tile as 8 columns.
+#ifndef MUFFT_TMA_DIAG
+#define MUFFT_TMA_DIAG 0
+#endif
+// Tickets drawn this many tiles ahead of the load, the input rows of a row ticket pulled into L2 at once (0 / 1 / 2:
+// 1.069 / 1.056 / 1.057 ms).
+#ifndef MUFFT_TMA_AHEAD
+#define MUFFT_TMA_AHEAD 2
+#endif
+// Nanoseconds between polls of the loader and the storers: their polling must not take issue slots from the compute
+// warps on their scheduler (0 / 20 / 100 / 400: the same within 0.3 %).
+#ifndef MUFFT_TMA_POLL_NS
+#define MUFFT_TMA_POLL_NS 100
+#endif
+// L2 policies of the four streams of tiles: 0 = none, 1 = evict_first, 2 = evict_last.
+#ifndef MUFFT_TMA_POLICY_IN
+#define MUFFT_TMA_POLICY_IN 1
+#endif
+#ifndef MUFFT_TMA_POLICY_MID_ST
+#define MUFFT_TMA_POLICY_MID_ST 2
+#endif
+#ifndef MUFFT_TMA_POLICY_MID_LD
+#define MUFFT_TMA_POLICY_MID_LD 0
+#endif
+#ifndef MUFFT_TMA_POLICY_OUT
+#define MUFFT_TMA_POLICY_OUT 1
+#endif
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(void *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(void *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(void *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// A protocol error must not hang the device: two seconds without progress end the wait (false).
+// SLEEP: nanoseconds between polls (0 for the compute warps).
+template <int SLEEP>
+__device__ __forceinline__ bool mbar_wait(void *bar, unsigned parity)
+{
+    if (mbar_try_wait(bar, parity)) return true;
+    const unsigned long long t0 = global_ns();
+    unsigned spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if constexpr (SLEEP > 0) __nanosleep(SLEEP);
+        if ((++spins & (SLEEP > 0 ? 1023u : 65535u)) == 0 && global_ns() - t0 > 2000000000ull) return false;
+    }
+    return true;
+}
+#ifdef MUFFT_TMA_DEBUG
+#define F2D_TMA_WAIT(SLEEP, bar, parity, what, p0_, p1_) do { if (!mbar_wait<SLEEP>(bar, parity)) { if ((threadIdx.x & 31) == 0) printf("cta %d tid %d: timeout %s b=%u use=%u\n", (int)blockIdx.x, (int)threadIdx.x, what, (unsigned)(p0_), (unsigned)(p1_)); return; } } while (0)
+#else
+#define F2D_TMA_WAIT(SLEEP, bar, parity, what, p0_, p1_) do { if (!mbar_wait<SLEEP>(bar, parity)) __trap(); } while (0)
+#endif
+
+template <int KIND>
+__device__ __forceinline__ unsigned long long l2_policy()
+{
+    unsigned long long pol = 0;
+    if constexpr (KIND == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    if constexpr (KIND == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+template <int KIND>
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, unsigned bytes, void *bar, unsigned long long pol)
+{
+    if constexpr (KIND == 0)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+    else
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                     ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void bulk_store_1d(void *dst, const void *src, unsigned bytes, unsigned long long pol)
+{
+    if constexpr (KIND == 0)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+    else
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes), "l"(pol) : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void tensor_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, void *bar, unsigned long long pol)
+{
+    if constexpr (KIND == 0)
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+                     ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void tensor_store_2d(const CUtensorMap *map, int c0, int c1, const void *src, unsigned long long pol)
+{
+    if constexpr (KIND == 0)
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                     ::"l"(map), "r"(c0), "r"(c1), "r"(smem_u32(src)) : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;"
+                     ::"l"(map), "r"(c0), "r"(c1), "r"(smem_u32(src)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void group_barrier(int group)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(F2D_TMA_GROUP_THREADS) : "memory");
+}
+
+// (A version whose groups stored their results from registers, handing the buffer back to the loader right after the
+// gather of the exchange, was measured too: 1.184 ms against 1.056 ms - the stores stall the compute warps and a finished
+// row can only be announced a tile late.  profiles/r02u_ab.txt.)
+template <int NX, int NY, int DIR, int TWM>
+__global__ void __launch_bounds__(F2D_TMA_THREADS, 1)
+fft2d_tma_kernel(const __grid_constant__ f2d_tma_params p)
+{
+    static_assert(f2d_tma_supported(NX, NY), "shape");
+    constexpr int RX = 32, TX = NX / RX, ROWS = F2D_TMA_GROUP_THREADS / TX; // 8 rows per tile, one warp each
+    constexpr int RY = 32, TY = NY / RY, COLS = F2D_TMA_GROUP_THREADS / TY; // 8 columns per tile: 64-byte segments
+    constexpr unsigned NR = NY / ROWS, NC = NX / COLS;
+    constexpr int ROW_PITCH = f2d_tma_row_pitch(NX);
+    constexpr size_t BUF = f2d_tma_buf_bytes(NX, NY);
+    constexpr unsigned TILE_BYTES = ROWS * NX * sizeof(cpx);
+    constexpr int UTIL0 = F2D_TMA_GROUPS * F2D_TMA_GROUP_THREADS; // first thread of the loader's warp
+    static_assert(TILE_BYTES == COLS * NY * sizeof(cpx), "square tiles");
+    static_assert((size_t)ROWS * ROW_PITCH * sizeof(cpx) <= BUF && (ROW_PITCH * sizeof(cpx)) % 16 == 0, "row tile layout");
+    static_assert((f2d_tw_elems(NX, NY, 0) * sizeof(cpx)) % 16 == 0, "meta alignment");
+    // Used as it is: pointer arithmetic through integers would turn every LDS / STS below into a generic LD / ST (seen
+    // in the first ncu capture).  The kernel has no static shared memory: offset 0, aligned for the tensor copies.
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char *base = smem_raw;
+    cpx *tws = reinterpret_cast<cpx *>(base + F2D_TMA_STAGES * BUF);
+    uint4 *meta = reinterpret_cast<uint4 *>(tws + f2d_tw_elems(NX, NY, 0)); // x = type, y = image, z = tile
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(meta + F2D_TMA_STAGES);
+    // full[b * GROUPS + g]: one barrier per (buffer, group) - a parity wait only works for a waiter that sees EVERY phase
+    // of its barrier, and a group meets a given buffer every second time the buffer is used
+    unsigned long long *full = bars, *staged = bars + F2D_TMA_GROUPS * F2D_TMA_STAGES, *freed = staged + F2D_TMA_STAGES;
+
+    const mcu_2d_args &a = p.a;
+    const int tid = threadIdx.x;
+    const cpx *twx_g = static_cast<const cpx *>(a.tw_x), *twy_g = static_cast<const cpx *>(a.tw_y);
+    for (int i = tid; i < engine_tw_total(NX, 0); i += F2D_TMA_THREADS) tws[i] = __ldg(twx_g + i);
+    if constexpr (NX != NY)
+        for (int i = tid; i < engine_tw_total(NY); i += F2D_TMA_THREADS) tws[engine_tw_total(NX, 0) + i] = __ldg(twy_g + i);
+    const cpx *twx = tws, *twy = NX != NY ? tws + engine_tw_total(NX, 0) : tws;
+    if (tid == 0) {
+        for (int b = 0; b < F2D_TMA_STAGES; b++) {
+            for (int g = 0; g < F2D_TMA_GROUPS; g++) mbar_init(full + b * F2D_TMA_GROUPS + g, 1);
+            mbar_init(staged + b, F2D_TMA_GROUP_THREADS);
+            mbar_init(freed + b, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async_all();
+    }
+    __syncthreads(); // the only CTA-wide barrier
+
+    unsigned *ticket_counter = a.counters;
+    unsigned *produced = a.counters + 1; // [batch] row tiles finished per image
+
+    if (tid < UTIL0) {
+        // ---- compute groups ----------------------------------------------------------------------------------------
+        const int group = tid / F2D_TMA_GROUP_THREADS, gtid = tid % F2D_TMA_GROUP_THREADS;
+        int exits = 0;
+        for (unsigned s = group;; s += F2D_TMA_GROUPS) {
+            const unsigned b = s % F2D_TMA_STAGES, use = s / F2D_TMA_STAGES;
+            cpx *buf = reinterpret_cast<cpx *>(base + b * BUF);
+            F2D_TMA_WAIT(0, full + b * F2D_TMA_GROUPS + group, (s / (F2D_TMA_GROUPS * F2D_TMA_STAGES)) & 1, "full", b, use);
+            const unsigned type = meta[b].x;
+            if (type == F2D_TMA_EXIT) {
+                mbar_arrive(staged + b);
+                if (++exits == F2D_TMA_STAGES) break;
+                continue;
+            }
+            if (MUFFT_TMA_DIAG >= 3) {
+            } else if (type == F2D_TMA_ROWS) {
+                const int slot = gtid / TX, t = gtid % TX;
+                cpx *sm = buf + slot * ROW_PITCH;
+                cpx v[RX];
+#pragma unroll
+                for (int e = 0; e < RX; e++) v[e] = sm[t + e * TX];
+                __syncwarp(); // the row is in registers before the exchange overwrites it
+                engine_run<NX, DIR, 1, TX, ROWS, 0, 0, -1, TWM>(v, sm, twx, t, slot);
+                __syncwarp(); // every lane has gathered
+#pragma unroll
+                for (int e = 0; e < RX; e++) sm[t + e * TX] = v[e];
+            } else {
+                const int c = gtid % COLS, t = gtid / COLS;
+                cpx v[RY];
+#pragma unroll
+                for (int e = 0; e < RY; e++) v[e] = buf[(t + e * TY) * COLS + c];
+                group_barrier(group);
+                engine_run<NY, DIR, COLS, F2D_TMA_GROUP_THREADS, F2D_TMA_GROUPS, 0, 0, -1, TWM>(v, buf + c, twy, t, group);
+                group_barrier(group);
+#pragma unroll
+                for (int e = 0; e < RY; e++) buf[(t + e * TY) * COLS + c] = v[e];
+            }
+            fence_proxy_async_smem(); // this thread's writes, before the TMA unit reads the buffer
+            mbar_arrive(staged + b);
+        }
+    } else if (tid == UTIL0) {
+        // ---- loader ------------------------------------------------------------------------------------------------
+        const unsigned long long total = (unsigned long long)a.batch * (NR + NC);
+        const unsigned lag = a.lag < a.batch ? a.lag : (unsigned)a.batch;
+        const unsigned long long head = (unsigned long long)lag * NR;
+        const unsigned long long body = (unsigned long long)(a.batch - lag) * (NR + NC);
+        const unsigned long long pol_in = l2_policy<MUFFT_TMA_POLICY_IN>(), pol_mid = l2_policy<MUFFT_TMA_POLICY_MID_LD>();
+        auto decode = [&](unsigned k, unsigned &image, unsigned &tile) -> bool { // true = rows
+            if (k < head) {
+                image = k / NR; tile = k % NR;
+                return true;
+            } else if (k - head < body) {
+                const unsigned long long kk = k - head;
+                const unsigned i = lag + (unsigned)(kk / (NR + NC)), j = (unsigned)(kk % (NR + NC));
+                if (j < NR) { image = i; tile = j; return true; }
+                image = i - lag; tile = j - NR;
+                return false;
+            }
+            const unsigned long long kk = k - head - body;
+            image = (unsigned)a.batch - lag + (unsigned)(kk / NC); tile = (unsigned)(kk % NC);
+            return false;
+        };
+        // Tickets are drawn MUFFT_TMA_AHEAD tiles ahead; the input rows of a row ticket are pulled into L2 at once (the
+        // columns read the intermediate: in L2 already).
+        auto draw = [&]() -> unsigned {
+            const unsigned k = atomicAdd(ticket_counter, 1u);
+#if MUFFT_TMA_AHEAD > 0
+            if (k < total) {
+                unsigned image, tile;
+                if (decode(k, image, tile))
+                    prefetch_l2_bulk(static_cast<const cpx *>(a.in) + (size_t)image * a.in_image + (size_t)tile * ROWS * NX, TILE_BYTES);
+            }
+#endif
+            return k;
+        };
+        unsigned t0 = draw();
+#if MUFFT_TMA_AHEAD > 1
+        unsigned t1 = draw();
+#endif
+        int exits = 0;
+        for (unsigned s = 0;; s++) {
+            const unsigned b = s % F2D_TMA_STAGES, use = s / F2D_TMA_STAGES;
+            unsigned char *buf = base + b * BUF;
+            unsigned long long *fb = full + b * F2D_TMA_GROUPS + s % F2D_TMA_GROUPS; // the group that gets this sequence number
+            const unsigned k = t0;
+            if (k >= total) {
+                F2D_TMA_WAIT(MUFFT_TMA_POLL_NS, freed + b, (use & 1) ^ 1, "free(exit)", b, use);
+                meta[b] = make_uint4(F2D_TMA_EXIT, 0, 0, 0);
+                mbar_arrive(fb);
+                if (++exits == F2D_TMA_GROUPS * F2D_TMA_STAGES) break;
+                continue;
+            }
+#if MUFFT_TMA_AHEAD > 1
+            t0 = t1;
+            t1 = draw();
+#else
+            t0 = draw(); // its round trip overlaps the waits below
+#endif
+            unsigned image, tile;
+#if MUFFT_TMA_DIAG == 4
+            decode(k, image, tile);
+            const bool rows = true;
+#elif MUFFT_TMA_DIAG == 5
+            decode(k, image, tile);
+            const bool rows = false;
+#else
+            const bool rows = decode(k, image, tile);
+#endif
+            if (!rows && MUFFT_TMA_DIAG != 5) {
+                // the rows of this image, written by the TMA units of other SMs
+                unsigned ns = 32;
+                const unsigned long long w0 = global_ns();
+                while (ld_relaxed(produced + image) < NR) {
+                    __nanosleep(ns);
+                    if (ns < 1024) ns *= 2;
+                    else if (global_ns() - w0 > 2000000000ull) {
+#ifdef MUFFT_TMA_DEBUG
+                        printf("cta %d loader: timeout rows of image %u: %u of %u (ticket %u)\n", (int)blockIdx.x, image, ld_relaxed(produced + image), NR, k);
+                        return;
+#else
+                        __trap();
+#endif
+                    }
+                }
+                fence_acquire_gpu();
+                fence_proxy_async_all(); // generic-proxy view of the counter, async-proxy reads of the data
+            }
+            F2D_TMA_WAIT(MUFFT_TMA_POLL_NS, freed + b, (use & 1) ^ 1, "free", b, use);
+            meta[b] = make_uint4(rows ? F2D_TMA_ROWS : F2D_TMA_COLS, image, tile, 0);
+            mbar_arrive_expect_tx(fb, TILE_BYTES);
+            if (rows) {
+                const cpx *src = static_cast<const cpx *>(a.in) + (size_t)image * a.in_image + (size_t)tile * ROWS * NX;
+#pragma unroll 1
+                for (int r = 0; r < ROWS; r++)
+                    bulk_load_1d<MUFFT_TMA_POLICY_IN>(buf + (size_t)r * ROW_PITCH * sizeof(cpx), src + (size_t)r * NX, NX * sizeof(cpx), fb, pol_in);
+            } else {
+#pragma unroll 1
+                for (int q = 0; q < NY / F2D_TMA_BOX_ROWS; q++)
+                    tensor_load_2d<MUFFT_TMA_POLICY_MID_LD>(buf + (size_t)q * F2D_TMA_BOX_ROWS * COLS * sizeof(cpx), &p.map, (int)(tile * COLS * 2),
+                                                            (int)(image * NY + q * F2D_TMA_BOX_ROWS), fb, pol_mid);
+            }
+        }
+    } else if (tid >= UTIL0 + 32 && (tid & 31) == 0) {
+        // ---- storers: one per buffer (lane 0 of a warp of its own) --------------------------------------------------------
+        const unsigned b = (tid - (UTIL0 + 32)) / 32;
+        unsigned char *buf = base + b * BUF;
+        const unsigned long long pol_mid = l2_policy<MUFFT_TMA_POLICY_MID_ST>(), pol_out = l2_policy<MUFFT_TMA_POLICY_OUT>();
+        int exits = 0;
+        for (unsigned use = 0;; use++) {
+            F2D_TMA_WAIT(MUFFT_TMA_POLL_NS, staged + b, use & 1, "staged", b, use);
+            const uint4 m = meta[b];
+            if (m.x == F2D_TMA_EXIT) {
+                mbar_arrive(freed + b);
+                if (++exits == F2D_TMA_GROUPS) break;
+                continue;
+            }
+            if (m.x == F2D_TMA_ROWS) {
+                cpx *dst = static_cast<cpx *>(a.out) + (size_t)m.y * a.out_image + (size_t)m.z * ROWS * NX;
+#pragma unroll 1
+                for (int r = 0; r < ROWS; r++)
+                    bulk_store_1d<MUFFT_TMA_POLICY_MID_ST>(dst + (size_t)r * NX, buf + (size_t)r * ROW_PITCH * sizeof(cpx), NX * sizeof(cpx), pol_mid);
+            } else {
+#pragma unroll 1
+                for (int q = 0; q < NY / F2D_TMA_BOX_ROWS; q++)
+                    tensor_store_2d<MUFFT_TMA_POLICY_OUT>(&p.map, (int)(m.z * COLS * 2), (int)(m.y * NY + q * F2D_TMA_BOX_ROWS),
+                                                          buf + (size_t)q * F2D_TMA_BOX_ROWS * COLS * sizeof(cpx), pol_out);
+            }
+            bulk_commit();
+            bulk_wait_read(); // the TMA unit has read the buffer: the loader may refill it
+            mbar_arrive(freed + b);
+            if (m.x == F2D_TMA_ROWS) {
+                bulk_wait_all(); // the writes are complete
+                fence_proxy_async_all();
+                fence_release_gpu();
+                red_relaxed_add(produced + m.y, 1u);
+            }
+        }
+        bulk_wait_all();
+    }
+}
+#endif // MUFFT_EMU
+
+} // namespace mufft
