@@ -32,7 +32,7 @@ static unsigned default_lag(unsigned grid, unsigned per_image) { return 1 + (3 *
 // cuTensorMapEncodeTiled through the runtime's driver entry point query: no link against libcuda.
 typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                     const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static encode_tiled_fn encode_tiled()
+[[maybe_unused]] static encode_tiled_fn encode_tiled()
 {
     static encode_tiled_fn fn = nullptr;
     if (fn == nullptr) {

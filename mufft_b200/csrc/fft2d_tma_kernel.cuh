@@ -250,7 +250,8 @@ fft2d_tma_kernel(const __grid_constant__ f2d_tma_params p)
         const int group = tid / F2D_TMA_GROUP_THREADS, gtid = tid % F2D_TMA_GROUP_THREADS;
         int exits = 0;
         for (unsigned s = group;; s += F2D_TMA_GROUPS) {
-            const unsigned b = s % F2D_TMA_STAGES, use = s / F2D_TMA_STAGES;
+            const unsigned b = s % F2D_TMA_STAGES;
+            [[maybe_unused]] const unsigned use = s / F2D_TMA_STAGES; // (debug message)
             cpx *buf = reinterpret_cast<cpx *>(base + b * BUF);
             F2D_TMA_WAIT(0, full + b * F2D_TMA_GROUPS + group, (s / (F2D_TMA_GROUPS * F2D_TMA_STAGES)) & 1, "full", b, use);
             const unsigned type = meta[b].x;
