@@ -49,7 +49,7 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32
 template <int DIR>
 static bool launch_tma(const mcu_2d_args &a, cudaStream_t stream, cudaError_t *err)
 {
-  if constexpr (!f2d_tma_supported(F2D_NX, F2D_NY)) {
+  if constexpr (!f2d_tma_preferred(F2D_NX, F2D_NY)) {
     (void)a; (void)stream; (void)err;
     return false;
   } else {
@@ -61,6 +61,7 @@ static bool launch_tma(const mcu_2d_args &a, cudaStream_t stream, cudaError_t *e
     static launch_cfg cfg;
     auto kernel = fft2d_tma_kernel<F2D_NX, F2D_NY, DIR, MUFFT_F2D_TMA_TWM>;
     constexpr size_t smem = f2d_tma_smem_bytes(F2D_NX, F2D_NY);
+    constexpr int F2D_TMA_THREADS = f2d_tma_threads(F2D_NX, F2D_NY);
     int ctas = 0;
     if ((*err = launch_prepare(cfg, kernel, smem, F2D_TMA_THREADS, &ctas)) != cudaSuccess) return true;
     f2d_tma_params p;
@@ -81,7 +82,7 @@ static bool launch_tma(const mcu_2d_args &a, cudaStream_t stream, cudaError_t *e
 #ifdef MUFFT_F2D_TMA_LAG
     if (p.a.lag == 0) p.a.lag = MUFFT_F2D_TMA_LAG;
 #endif
-    if (p.a.lag == 0) p.a.lag = default_lag(F2D_TMA_STAGES * grid, per_image); // three tiles in flight per CTA
+    if (p.a.lag == 0) p.a.lag = default_lag(f2d_tma_stages(F2D_NX, F2D_NY) * grid, per_image); // so many tiles in flight per CTA
     kernel<<<grid, F2D_TMA_THREADS, smem, stream>>>(p);
     *err = cudaGetLastError();
     return true;

@@ -13,13 +13,15 @@
 //   groups   (2 x 256)    wait for `full`, pull the tile into registers (natural order: element t + e*T in slot e),
 //                         run the engine with the buffer itself as exchange area, put the result back in natural
 //                         order, fence.proxy.async, arrive on `staged`
-//   storers  (3 threads)  one per buffer, each in a warp of its own: wait for `staged`, hand the buffer to the TMA unit
-//                         (bulk stores), wait until it has been READ (-> `freed`, the loader may refill it) and until
-//                         the writes are COMPLETE (-> release + add on the image's counter: a finished row tile)
+//   storers  (S threads)  one per buffer, each in a warp of its own (as lanes of ONE warp their polls and sleeps serialise:
+//                         measured 1.49 ms instead of 1.06): wait for `staged`, hand the buffer to the TMA unit (bulk
+//                         stores), wait until it has been READ (-> `freed`, the loader may refill it) and until the
+//                         writes are COMPLETE (-> release + add on the image's counter: a finished row tile)
 //
-// Buffer of sequence number s (per CTA) is s % 3, its group s % 2: while two tiles are being computed the third buffer
-// is in flight from or to memory.  Every wait is on work with a smaller ticket number, as in the ticket kernel: no
-// deadlock.  End of work: six EXIT entries (lcm of groups and buffers), so that every group sees three and every storer two.
+// S = 3 buffers of 66 KB for sides of 1024 points, 6 of 33 KB for 512 x 512.  Buffer of sequence number s (per CTA) is
+// s % S, its group s % 2: while two tiles are being computed the other buffers are in flight from or to memory.  Every
+// wait is on work with a smaller ticket number, as in the ticket kernel: no deadlock.  End of work: lcm(2, S) EXIT
+// entries, so that every group and every storer sees the same number of them.
 //
 // L2 policies: the input is read once (evict_first), the row-transformed intermediate must survive in L2 until its
 // columns are read `lag` images later (evict_last), the final store is streaming again (evict_first).  Without them
@@ -32,19 +34,15 @@
 // single-pass 2D transform with the intermediate in L2 cannot exceed 0.67 of the HBM roofline on this chip.
 #pragma once
 
-#include <cuda.h>
-#include <cstdio>
-
 #include "fft2d_kernel.cuh"
+#include "tma_util.cuh"
 
 namespace mufft {
 
 #define F2D_TMA_GROUPS 2
-#define F2D_TMA_STAGES 3
 #define F2D_TMA_GROUP_THREADS 256
-// + a warp for the loader and one per storer
-#define F2D_TMA_THREADS (F2D_TMA_GROUPS * F2D_TMA_GROUP_THREADS + 32 * (1 + F2D_TMA_STAGES))
 #define F2D_TMA_BOX_ROWS 256
+#define F2D_TMA_MAX_STAGES 6
 enum { F2D_TMA_ROWS = 0, F2D_TMA_COLS = 1, F2D_TMA_EXIT = 2 };
 
 struct f2d_tma_params {
@@ -52,22 +50,51 @@ struct f2d_tma_params {
     alignas(64) CUtensorMap map; // output buffer as [batch * NY][2 * NX] floats, boxes of 16 floats x F2D_TMA_BOX_ROWS rows
 };
 
+// Sides whose transforms sit on 32 threads (one warp per row, 8 columns per group): 512 and 1024 points.
 __host__ __device__ constexpr bool f2d_tma_supported(int nx, int ny)
 {
-    return engine_regs(nx) == 32 && engine_regs(ny) == 32 && nx / 32 == 32 && ny / 32 == 32 && engine_num_passes(nx) == 2 && engine_num_passes(ny) == 2 &&
-           ny % F2D_TMA_BOX_ROWS == 0;
+    return engine_regs(nx) > 0 && engine_regs(ny) > 0 && nx / engine_regs(nx) == 32 && ny / engine_regs(ny) == 32 && ny % F2D_TMA_BOX_ROWS == 0;
+}
+// ... and where it is the faster kernel (profiles/r02aa_ab.txt, ms for 2 GiB of images, this kernel / ticket kernel):
+// 1024 x 1024 1.056 / 1.175, 512 x 1024 1.261 / 1.333, 1024 x 512 1.276 / 1.381, but 512 x 512 1.487 / 1.339 (six buffers
+// of 33 KB; four: 1.457) - the ticket kernel holds three CTAs per SM there.
+__host__ __device__ constexpr bool f2d_tma_preferred(int nx, int ny)
+{
+#ifdef MUFFT_F2D_TMA_ALL
+    return f2d_tma_supported(nx, ny);
+#else
+    return f2d_tma_supported(nx, ny) && (nx == 1024 || ny == 1024);
+#endif
 }
 // A row's exchange area inside a buffer; its first nx elements hold the row in natural order (16-byte aligned for the bulk copies).
 __host__ __device__ constexpr int f2d_tma_row_pitch(int nx) { return (engine_smem_elems(nx, 0) + 1) & ~1; }
 __host__ __device__ constexpr size_t f2d_tma_buf_bytes(int nx, int ny)
 {
-    size_t r = (size_t)(F2D_TMA_GROUP_THREADS / (nx / 32)) * f2d_tma_row_pitch(nx), c = (size_t)(F2D_TMA_GROUP_THREADS / (ny / 32)) * engine_smem_elems(ny);
+    size_t r = (size_t)(F2D_TMA_GROUP_THREADS / 32) * f2d_tma_row_pitch(nx), c = (size_t)(F2D_TMA_GROUP_THREADS / 32) * engine_smem_elems(ny);
     return ((r > c ? r : c) * sizeof(float2) + 127) / 128 * 128;
 }
+__host__ __device__ constexpr size_t f2d_tma_fixed_bytes(int nx, int ny, int stages)
+{
+    return (size_t)f2d_tw_elems(nx, ny, 0) * sizeof(float2) + (F2D_TMA_GROUPS + 2) * stages * 8 + stages * 16;
+}
+// As many buffers as 220 KB hold, an even number or 3 (lcm with the two groups stays small), at most 6.
+__host__ __device__ constexpr int f2d_tma_stages(int nx, int ny)
+{
+#ifdef MUFFT_F2D_TMA_STAGES
+    return MUFFT_F2D_TMA_STAGES;
+#else
+    int s = F2D_TMA_MAX_STAGES;
+    while (s > 2 && s * f2d_tma_buf_bytes(nx, ny) + f2d_tma_fixed_bytes(nx, ny, s) > 220 * 1024) s--;
+    return s == 5 ? 4 : s;
+#endif
+}
+__host__ __device__ constexpr int f2d_tma_lcm(int stages) { return stages % F2D_TMA_GROUPS == 0 ? stages : stages * F2D_TMA_GROUPS; }
 __host__ __device__ constexpr size_t f2d_tma_smem_bytes(int nx, int ny)
 {
-    return F2D_TMA_STAGES * f2d_tma_buf_bytes(nx, ny) + (size_t)f2d_tw_elems(nx, ny, 0) * sizeof(float2) + (F2D_TMA_GROUPS + 2) * F2D_TMA_STAGES * 8 + F2D_TMA_STAGES * 16;
+    return f2d_tma_stages(nx, ny) * f2d_tma_buf_bytes(nx, ny) + f2d_tma_fixed_bytes(nx, ny, f2d_tma_stages(nx, ny));
 }
+// the two groups + a warp for the loader and one per storer
+__host__ __device__ constexpr int f2d_tma_threads(int nx, int ny) { return F2D_TMA_GROUPS * F2D_TMA_GROUP_THREADS + 32 * (1 + f2d_tma_stages(nx, ny)); }
 
 #ifndef MUFFT_EMU
 // Timing experiments with WRONG results (never in the product build): 3 = the groups only pass the buffers on,
@@ -99,97 +126,6 @@ __host__ __device__ constexpr size_t f2d_tma_smem_bytes(int nx, int ny)
 #define MUFFT_TMA_POLICY_OUT 1
 #endif
 
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(void *bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
-__device__ __forceinline__ void mbar_arrive(void *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(void *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(void *bar, unsigned parity)
-{
-    unsigned ok;
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ unsigned long long global_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-// A protocol error must not hang the device: two seconds without progress end the wait (false).
-// SLEEP: nanoseconds between polls (0 for the compute warps).
-template <int SLEEP>
-__device__ __forceinline__ bool mbar_wait(void *bar, unsigned parity)
-{
-    if (mbar_try_wait(bar, parity)) return true;
-    const unsigned long long t0 = global_ns();
-    unsigned spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if constexpr (SLEEP > 0) __nanosleep(SLEEP);
-        if ((++spins & (SLEEP > 0 ? 1023u : 65535u)) == 0 && global_ns() - t0 > 2000000000ull) return false;
-    }
-    return true;
-}
-#ifdef MUFFT_TMA_DEBUG
-#define F2D_TMA_WAIT(SLEEP, bar, parity, what, p0_, p1_) do { if (!mbar_wait<SLEEP>(bar, parity)) { if ((threadIdx.x & 31) == 0) printf("cta %d tid %d: timeout %s b=%u use=%u\n", (int)blockIdx.x, (int)threadIdx.x, what, (unsigned)(p0_), (unsigned)(p1_)); return; } } while (0)
-#else
-#define F2D_TMA_WAIT(SLEEP, bar, parity, what, p0_, p1_) do { if (!mbar_wait<SLEEP>(bar, parity)) __trap(); } while (0)
-#endif
-
-template <int KIND>
-__device__ __forceinline__ unsigned long long l2_policy()
-{
-    unsigned long long pol = 0;
-    if constexpr (KIND == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    if constexpr (KIND == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-template <int KIND>
-__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, unsigned bytes, void *bar, unsigned long long pol)
-{
-    if constexpr (KIND == 0)
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-    else
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                     ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
-}
-template <int KIND>
-__device__ __forceinline__ void bulk_store_1d(void *dst, const void *src, unsigned bytes, unsigned long long pol)
-{
-    if constexpr (KIND == 0)
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
-    else
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes), "l"(pol) : "memory");
-}
-template <int KIND>
-__device__ __forceinline__ void tensor_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, void *bar, unsigned long long pol)
-{
-    if constexpr (KIND == 0)
-        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                     ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
-    else
-        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
-                     ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(pol) : "memory");
-}
-template <int KIND>
-__device__ __forceinline__ void tensor_store_2d(const CUtensorMap *map, int c0, int c1, const void *src, unsigned long long pol)
-{
-    if constexpr (KIND == 0)
-        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
-                     ::"l"(map), "r"(c0), "r"(c1), "r"(smem_u32(src)) : "memory");
-    else
-        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;"
-                     ::"l"(map), "r"(c0), "r"(c1), "r"(smem_u32(src)), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void group_barrier(int group)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(F2D_TMA_GROUP_THREADS) : "memory");
@@ -199,18 +135,20 @@ __device__ __forceinline__ void group_barrier(int group)
 // gather of the exchange, was measured too: 1.184 ms against 1.056 ms - the stores stall the compute warps and a finished
 // row can only be announced a tile late.  profiles/r02u_ab.txt.)
 template <int NX, int NY, int DIR, int TWM>
-__global__ void __launch_bounds__(F2D_TMA_THREADS, 1)
+__global__ void __launch_bounds__(f2d_tma_threads(NX, NY), 1)
 fft2d_tma_kernel(const __grid_constant__ f2d_tma_params p)
 {
+    constexpr int F2D_TMA_THREADS = f2d_tma_threads(NX, NY);
     static_assert(f2d_tma_supported(NX, NY), "shape");
-    constexpr int RX = 32, TX = NX / RX, ROWS = F2D_TMA_GROUP_THREADS / TX; // 8 rows per tile, one warp each
-    constexpr int RY = 32, TY = NY / RY, COLS = F2D_TMA_GROUP_THREADS / TY; // 8 columns per tile: 64-byte segments
+    constexpr int RX = engine_regs(NX), TX = NX / RX, ROWS = F2D_TMA_GROUP_THREADS / TX; // 8 rows per tile, one warp each
+    constexpr int RY = engine_regs(NY), TY = NY / RY, COLS = F2D_TMA_GROUP_THREADS / TY; // 8 columns per tile: 64-byte segments
     constexpr unsigned NR = NY / ROWS, NC = NX / COLS;
     constexpr int ROW_PITCH = f2d_tma_row_pitch(NX);
     constexpr size_t BUF = f2d_tma_buf_bytes(NX, NY);
-    constexpr unsigned TILE_BYTES = ROWS * NX * sizeof(cpx);
+    constexpr int F2D_TMA_STAGES = f2d_tma_stages(NX, NY), LCM = f2d_tma_lcm(F2D_TMA_STAGES);
+    constexpr unsigned ROW_TILE_BYTES = ROWS * NX * sizeof(cpx), COL_TILE_BYTES = COLS * NY * sizeof(cpx);
     constexpr int UTIL0 = F2D_TMA_GROUPS * F2D_TMA_GROUP_THREADS; // first thread of the loader's warp
-    static_assert(TILE_BYTES == COLS * NY * sizeof(cpx), "square tiles");
+    static_assert(F2D_TMA_STAGES >= 2 && F2D_TMA_STAGES < 32, "buffers");
     static_assert((size_t)ROWS * ROW_PITCH * sizeof(cpx) <= BUF && (ROW_PITCH * sizeof(cpx)) % 16 == 0, "row tile layout");
     static_assert((f2d_tw_elems(NX, NY, 0) * sizeof(cpx)) % 16 == 0, "meta alignment");
     // Used as it is: pointer arithmetic through integers would turn every LDS / STS below into a generic LD / ST (seen
@@ -253,11 +191,11 @@ fft2d_tma_kernel(const __grid_constant__ f2d_tma_params p)
             const unsigned b = s % F2D_TMA_STAGES;
             [[maybe_unused]] const unsigned use = s / F2D_TMA_STAGES; // (debug message)
             cpx *buf = reinterpret_cast<cpx *>(base + b * BUF);
-            F2D_TMA_WAIT(0, full + b * F2D_TMA_GROUPS + group, (s / (F2D_TMA_GROUPS * F2D_TMA_STAGES)) & 1, "full", b, use);
+            MUFFT_TMA_WAIT(0, full + b * F2D_TMA_GROUPS + group, (s / LCM) & 1, "full", b, use);
             const unsigned type = meta[b].x;
             if (type == F2D_TMA_EXIT) {
                 mbar_arrive(staged + b);
-                if (++exits == F2D_TMA_STAGES) break;
+                if (++exits == LCM / F2D_TMA_GROUPS) break;
                 continue;
             }
             if (MUFFT_TMA_DIAG >= 3) {
@@ -316,7 +254,7 @@ fft2d_tma_kernel(const __grid_constant__ f2d_tma_params p)
             if (k < total) {
                 unsigned image, tile;
                 if (decode(k, image, tile))
-                    prefetch_l2_bulk(static_cast<const cpx *>(a.in) + (size_t)image * a.in_image + (size_t)tile * ROWS * NX, TILE_BYTES);
+                    prefetch_l2_bulk(static_cast<const cpx *>(a.in) + (size_t)image * a.in_image + (size_t)tile * ROWS * NX, ROW_TILE_BYTES);
             }
 #endif
             return k;
@@ -332,10 +270,10 @@ fft2d_tma_kernel(const __grid_constant__ f2d_tma_params p)
             unsigned long long *fb = full + b * F2D_TMA_GROUPS + s % F2D_TMA_GROUPS; // the group that gets this sequence number
             const unsigned k = t0;
             if (k >= total) {
-                F2D_TMA_WAIT(MUFFT_TMA_POLL_NS, freed + b, (use & 1) ^ 1, "free(exit)", b, use);
+                MUFFT_TMA_WAIT(MUFFT_TMA_POLL_NS, freed + b, (use & 1) ^ 1, "free(exit)", b, use);
                 meta[b] = make_uint4(F2D_TMA_EXIT, 0, 0, 0);
                 mbar_arrive(fb);
-                if (++exits == F2D_TMA_GROUPS * F2D_TMA_STAGES) break;
+                if (++exits == LCM) break;
                 continue;
             }
 #if MUFFT_TMA_AHEAD > 1
@@ -373,9 +311,9 @@ fft2d_tma_kernel(const __grid_constant__ f2d_tma_params p)
                 fence_acquire_gpu();
                 fence_proxy_async_all(); // generic-proxy view of the counter, async-proxy reads of the data
             }
-            F2D_TMA_WAIT(MUFFT_TMA_POLL_NS, freed + b, (use & 1) ^ 1, "free", b, use);
+            MUFFT_TMA_WAIT(MUFFT_TMA_POLL_NS, freed + b, (use & 1) ^ 1, "free", b, use);
             meta[b] = make_uint4(rows ? F2D_TMA_ROWS : F2D_TMA_COLS, image, tile, 0);
-            mbar_arrive_expect_tx(fb, TILE_BYTES);
+            mbar_arrive_expect_tx(fb, rows ? ROW_TILE_BYTES : COL_TILE_BYTES);
             if (rows) {
                 const cpx *src = static_cast<const cpx *>(a.in) + (size_t)image * a.in_image + (size_t)tile * ROWS * NX;
 #pragma unroll 1
@@ -395,11 +333,11 @@ fft2d_tma_kernel(const __grid_constant__ f2d_tma_params p)
         const unsigned long long pol_mid = l2_policy<MUFFT_TMA_POLICY_MID_ST>(), pol_out = l2_policy<MUFFT_TMA_POLICY_OUT>();
         int exits = 0;
         for (unsigned use = 0;; use++) {
-            F2D_TMA_WAIT(MUFFT_TMA_POLL_NS, staged + b, use & 1, "staged", b, use);
+            MUFFT_TMA_WAIT(MUFFT_TMA_POLL_NS, staged + b, use & 1, "staged", b, use);
             const uint4 m = meta[b];
             if (m.x == F2D_TMA_EXIT) {
                 mbar_arrive(freed + b);
-                if (++exits == F2D_TMA_GROUPS) break;
+                if (++exits == LCM / F2D_TMA_STAGES) break;
                 continue;
             }
             if (m.x == F2D_TMA_ROWS) {

@@ -715,3 +715,64 @@ def test_library_allocators_and_copy_helpers(m, torch, oracle):
     m.mufft_free_plan_1d(plan)
     m.mufft_cuda_host_free(hin); m.mufft_cuda_host_free(hout)
     m.mufft_cuda_device_free(din); m.mufft_cuda_device_free(dout)
+
+
+@pytest.mark.parametrize("nx,ny", [(1024, 1024), (512, 1024), (1024, 512)])
+def test_c2c_2d_tma_kernel_and_its_fallbacks(m, torch, nx, ny):
+    """Batches of 8 images or more of these shapes run on the warp-specialised TMA kernel (fft2d_tma_kernel.cuh);
+    smaller batches and output buffers that are not 128-byte aligned stay on the ticket kernel.  Every image of an odd
+    batch, both directions, against cuFFT; the two kernels against each other."""
+    batch = 13
+    x = dev_random(torch, (batch, ny, nx, 2), 3 * nx + ny)
+    spare = torch.zeros((batch * ny * nx + 1, 2), dtype=torch.float32, device="cuda")
+    y = torch.zeros_like(x)
+    y_off = spare[1:].view(batch, ny, nx, 2)  # 8 bytes off the allocation: not a TMA destination
+    assert y.data_ptr() % 128 == 0 and y_off.data_ptr() % 128 == 8
+    for direction in (-1, 1):
+        plan = m.mufft_create_plan_2d_c2c(nx, ny, direction, 0)
+        assert plan
+        xc = torch.view_as_complex(x)
+        ref = torch.fft.fft2(xc) if direction < 0 else torch.fft.ifft2(xc, norm="forward")
+        for out, count in ((y, batch), (y_off, batch), (y, 7)):
+            out.zero_()
+            m.mufft_cuda_launch_count(1)
+            assert m.mufft_execute_plan_2d_batch(plan, out.data_ptr(), x.data_ptr(), count) == 0, m.mufft_cuda_last_error()
+            assert m.mufft_cuda_launch_count(1) == 1
+            oc = torch.view_as_complex(out)[:count]
+            err = (torch.linalg.vector_norm((oc - ref[:count]).reshape(count, -1), dim=1) /
+                   torch.linalg.vector_norm(ref[:count].reshape(count, -1), dim=1)).max().item()
+            assert err <= tol(nx * ny)
+        # in place, on the TMA kernel
+        z = x.clone()
+        assert m.mufft_execute_plan_2d_batch(plan, z.data_ptr(), z.data_ptr(), batch) == 0, m.mufft_cuda_last_error()
+        zc = torch.view_as_complex(z)
+        err = (torch.linalg.vector_norm((zc - ref).reshape(batch, -1), dim=1) / torch.linalg.vector_norm(ref.reshape(batch, -1), dim=1)).max().item()
+        assert err <= tol(nx * ny)
+        m.mufft_free_plan_2d(plan)
+
+
+@pytest.mark.parametrize("batch", [1023, 1024, 2500])
+def test_c2c_8192_tma_rows(m, torch, oracle, batch):
+    """8192-point C2C: batches of 1024 transforms or more run on the warp-specialised TMA row kernel
+    (rows_tma_kernel.cuh), smaller ones on the row kernel; same results, checked on every transform."""
+    n = 8192
+    x = dev_random(torch, (batch, 2 * n), batch)
+    for direction in (-1, 1):
+        y = torch.zeros_like(x)
+        plan = m.mufft_create_plan_1d_c2c(n, direction, 0)
+        assert plan
+        m.mufft_cuda_launch_count(1)
+        assert m.mufft_execute_plan_1d_batch(plan, y.data_ptr(), x.data_ptr(), batch, 0, 0) == 0, m.mufft_cuda_last_error()
+        assert m.mufft_cuda_launch_count(1) == 1
+        xc = torch.view_as_complex(x.view(batch, n, 2))
+        ref = torch.fft.fft(xc, dim=1) if direction < 0 else torch.fft.ifft(xc, dim=1, norm="forward")
+        yc = torch.view_as_complex(y.view(batch, n, 2))
+        err = (torch.linalg.vector_norm(yc - ref, dim=1) / torch.linalg.vector_norm(ref, dim=1)).max().item()
+        assert err <= tol(n), f"worst transform rel L2 {err:.3e}"
+        for i in (0, batch - 1):
+            assert rel_l2(y[i].cpu().numpy().view(np.complex64), oracle.c2c(x[i].cpu().numpy().view(np.complex64), direction)) <= tol(n)
+        # in place
+        z = x.clone()
+        assert m.mufft_execute_plan_1d_batch(plan, z.data_ptr(), z.data_ptr(), batch, 0, 0) == 0
+        assert torch.equal(z, y)
+        m.mufft_free_plan_1d(plan)
