@@ -46,28 +46,29 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32
     return fn;
 }
 // true = launched (or failed: *err); false = this call is not for the TMA kernel (alignment, pitch), use the ticket kernel
-template <int DIR>
+template <int DIR, int KIND>
 static bool launch_tma(const mcu_2d_args &a, cudaStream_t stream, cudaError_t *err)
 {
-  if constexpr (!f2d_tma_preferred(F2D_NX, F2D_NY)) {
+  if constexpr (!f2d_tma_preferred(F2D_NX, F2D_NY) || !f2d_tma_kind_supported(F2D_NX, F2D_NY, KIND)) {
     (void)a; (void)stream; (void)err;
     return false;
   } else {
-    if (a.out_image != (size_t)F2D_NX * F2D_NY || (a.in_image & 1) != 0 || (reinterpret_cast<uintptr_t>(a.out) & 127) != 0 ||
+    constexpr int PITCH = f2d_pitch(F2D_NX, KIND), WIDTH = f2d_width(F2D_NX, KIND);
+    if (a.out_image != (size_t)PITCH * F2D_NY || (a.in_image & 1) != 0 || (reinterpret_cast<uintptr_t>(a.out) & 127) != 0 ||
         (reinterpret_cast<uintptr_t>(a.in) & 15) != 0 || a.batch * (size_t)F2D_NY >= 0x7fffffffull || a.batch < 8)
         return false; // (up to 4 images the ticket kernel is the faster one, 34 vs 38 us: profiles/r02y_ab.txt)
     encode_tiled_fn encode = encode_tiled();
     if (encode == nullptr) return false;
     static launch_cfg cfg;
-    auto kernel = fft2d_tma_kernel<F2D_NX, F2D_NY, DIR, MUFFT_F2D_TMA_TWM>;
-    constexpr size_t smem = f2d_tma_smem_bytes(F2D_NX, F2D_NY);
-    constexpr int F2D_TMA_THREADS = f2d_tma_threads(F2D_NX, F2D_NY);
+    auto kernel = fft2d_tma_kernel<F2D_NX, F2D_NY, DIR, MUFFT_F2D_TMA_TWM, KIND>;
+    constexpr size_t smem = f2d_tma_smem_bytes(F2D_NX, F2D_NY, KIND);
+    constexpr int F2D_TMA_THREADS = f2d_tma_threads(F2D_NX, F2D_NY, KIND);
     int ctas = 0;
     if ((*err = launch_prepare(cfg, kernel, smem, F2D_TMA_THREADS, &ctas)) != cudaSuccess) return true;
     f2d_tma_params p;
     p.a = a;
-    const cuuint64_t dims[2] = { 2ull * F2D_NX, (cuuint64_t)a.batch * F2D_NY };
-    const cuuint64_t strides[1] = { (cuuint64_t)F2D_NX * sizeof(float2) };
+    const cuuint64_t dims[2] = { 2ull * WIDTH, (cuuint64_t)a.batch * F2D_NY }; // the columns that carry data
+    const cuuint64_t strides[1] = { (cuuint64_t)PITCH * sizeof(float2) };
     const cuuint32_t box[2] = { 16, F2D_TMA_BOX_ROWS };
     const cuuint32_t estr[2] = { 1, 1 };
     if (encode(&p.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -75,14 +76,14 @@ static bool launch_tma(const mcu_2d_args &a, cudaStream_t stream, cudaError_t *e
         *err = cudaErrorInvalidValue;
         return true;
     }
-    constexpr unsigned per_image = f2d_tickets_per_image(F2D_NX, F2D_NY, F2D_C2C);
+    constexpr unsigned per_image = f2d_tickets_per_image(F2D_NX, F2D_NY, KIND);
     const unsigned long long tickets = (unsigned long long)a.batch * per_image;
     if (tickets + (unsigned long long)ctas >= 0xffffffffull) { *err = cudaErrorInvalidConfiguration; return true; }
     const unsigned grid = (unsigned)ctas;
 #ifdef MUFFT_F2D_TMA_LAG
     if (p.a.lag == 0) p.a.lag = MUFFT_F2D_TMA_LAG;
 #endif
-    if (p.a.lag == 0) p.a.lag = default_lag(f2d_tma_stages(F2D_NX, F2D_NY) * grid, per_image); // so many tiles in flight per CTA
+    if (p.a.lag == 0) p.a.lag = default_lag(f2d_tma_stages(F2D_NX, F2D_NY, KIND) * grid, per_image); // so many tiles in flight per CTA
     kernel<<<grid, F2D_TMA_THREADS, smem, stream>>>(p);
     *err = cudaGetLastError();
     return true;
@@ -110,9 +111,9 @@ static cudaError_t launch_kind(const mcu_2d_args &a, cudaStream_t stream, unsign
     }
     if (a.batch == 0) return cudaSuccess;
 #if MUFFT_F2D_TMA
-    if constexpr (KIND == F2D_C2C) {
+    if constexpr (KIND == F2D_C2C || KIND == F2D_R2C) {
         cudaError_t terr = cudaSuccess;
-        if (launch_tma<DIR>(a, stream, &terr)) return terr;
+        if (launch_tma<DIR, KIND>(a, stream, &terr)) return terr;
     }
 #endif
     const unsigned long long tickets = (unsigned long long)a.batch * per_image;

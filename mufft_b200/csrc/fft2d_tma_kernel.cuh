@@ -66,35 +66,48 @@ __host__ __device__ constexpr bool f2d_tma_preferred(int nx, int ny)
     return f2d_tma_supported(nx, ny) && (nx == 1024 || ny == 1024);
 #endif
 }
-// A row's exchange area inside a buffer; its first nx elements hold the row in natural order (16-byte aligned for the bulk copies).
-__host__ __device__ constexpr int f2d_tma_row_pitch(int nx) { return (engine_smem_elems(nx, 0) + 1) & ~1; }
-__host__ __device__ constexpr size_t f2d_tma_buf_bytes(int nx, int ny)
+// Kinds: C2C, and R2C where the rows have the mirrored-pass engine shape (the resolve then happens in registers, on the way
+// back into the buffer): 512 complex points per row, i.e. real images 1024 wide.
+__host__ __device__ constexpr int f2d_tma_rows_variant(int nx, int kind) { return kind == F2D_R2C ? f2d_rows_variant(nx, kind) : 0; }
+__host__ __device__ constexpr bool f2d_tma_kind_supported(int nx, int ny, int kind)
 {
-    size_t r = (size_t)(F2D_TMA_GROUP_THREADS / 32) * f2d_tma_row_pitch(nx), c = (size_t)(F2D_TMA_GROUP_THREADS / 32) * engine_smem_elems(ny);
+    if (!f2d_tma_supported(nx, ny)) return false;
+    if (kind == F2D_C2C) return true;
+    return kind == F2D_R2C && f2d_tma_rows_variant(nx, kind) == MUFFT_VARIANT_MIRROR_LAST && nx / engine_regs(nx, MUFFT_VARIANT_MIRROR_LAST) == 32;
+}
+// A row's exchange area inside a buffer; its first nx (+ 1) elements hold the row in natural order (16-byte aligned for the bulk copies).
+__host__ __device__ constexpr int f2d_tma_row_pitch(int nx, int kind = F2D_C2C)
+{
+    const int e = engine_smem_elems(nx, f2d_tma_rows_variant(nx, kind));
+    return ((e > nx + 1 ? e : nx + 1) + 1) & ~1;
+}
+__host__ __device__ constexpr size_t f2d_tma_buf_bytes(int nx, int ny, int kind = F2D_C2C)
+{
+    size_t r = (size_t)(F2D_TMA_GROUP_THREADS / 32) * f2d_tma_row_pitch(nx, kind), c = (size_t)(F2D_TMA_GROUP_THREADS / 32) * engine_smem_elems(ny);
     return ((r > c ? r : c) * sizeof(float2) + 127) / 128 * 128;
 }
-__host__ __device__ constexpr size_t f2d_tma_fixed_bytes(int nx, int ny, int stages)
+__host__ __device__ constexpr size_t f2d_tma_fixed_bytes(int nx, int ny, int stages, int kind = F2D_C2C)
 {
-    return (size_t)f2d_tw_elems(nx, ny, 0) * sizeof(float2) + (F2D_TMA_GROUPS + 2) * stages * 8 + stages * 16;
+    return (size_t)f2d_tw_elems(nx, ny, f2d_tma_rows_variant(nx, kind)) * sizeof(float2) + (F2D_TMA_GROUPS + 2) * stages * 8 + stages * 16;
 }
 // As many buffers as 220 KB hold, an even number or 3 (lcm with the two groups stays small), at most 6.
-__host__ __device__ constexpr int f2d_tma_stages(int nx, int ny)
+__host__ __device__ constexpr int f2d_tma_stages(int nx, int ny, int kind = F2D_C2C)
 {
 #ifdef MUFFT_F2D_TMA_STAGES
     return MUFFT_F2D_TMA_STAGES;
 #else
     int s = F2D_TMA_MAX_STAGES;
-    while (s > 2 && s * f2d_tma_buf_bytes(nx, ny) + f2d_tma_fixed_bytes(nx, ny, s) > 220 * 1024) s--;
+    while (s > 2 && s * f2d_tma_buf_bytes(nx, ny, kind) + f2d_tma_fixed_bytes(nx, ny, s, kind) > 220 * 1024) s--;
     return s == 5 ? 4 : s;
 #endif
 }
 __host__ __device__ constexpr int f2d_tma_lcm(int stages) { return stages % F2D_TMA_GROUPS == 0 ? stages : stages * F2D_TMA_GROUPS; }
-__host__ __device__ constexpr size_t f2d_tma_smem_bytes(int nx, int ny)
+__host__ __device__ constexpr size_t f2d_tma_smem_bytes(int nx, int ny, int kind = F2D_C2C)
 {
-    return f2d_tma_stages(nx, ny) * f2d_tma_buf_bytes(nx, ny) + f2d_tma_fixed_bytes(nx, ny, f2d_tma_stages(nx, ny));
+    return f2d_tma_stages(nx, ny, kind) * f2d_tma_buf_bytes(nx, ny, kind) + f2d_tma_fixed_bytes(nx, ny, f2d_tma_stages(nx, ny, kind), kind);
 }
 // the two groups + a warp for the loader and one per storer
-__host__ __device__ constexpr int f2d_tma_threads(int nx, int ny) { return F2D_TMA_GROUPS * F2D_TMA_GROUP_THREADS + 32 * (1 + f2d_tma_stages(nx, ny)); }
+__host__ __device__ constexpr int f2d_tma_threads(int nx, int ny, int kind = F2D_C2C) { return F2D_TMA_GROUPS * F2D_TMA_GROUP_THREADS + 32 * (1 + f2d_tma_stages(nx, ny, kind)); }
 
 #ifndef MUFFT_EMU
 // Timing experiments with WRONG results (never in the product build): 3 = the groups only pass the buffers on,
@@ -134,29 +147,35 @@ __device__ __forceinline__ void group_barrier(int group)
 // (A version whose groups stored their results from registers, handing the buffer back to the loader right after the
 // gather of the exchange, was measured too: 1.184 ms against 1.056 ms - the stores stall the compute warps and a finished
 // row can only be announced a tile late.  profiles/r02u_ab.txt.)
-template <int NX, int NY, int DIR, int TWM>
-__global__ void __launch_bounds__(f2d_tma_threads(NX, NY), 1)
+// KIND = F2D_R2C: NX complex points per row = 2 NX reals in, NX + 1 bins out at a pitch of 2 NX bins (the layout of
+// fft2d_kernel.cuh); the columns that carry data are NX + 1: the tensor map is that wide, and the TMA unit fills what the
+// last column tile reads beyond it with zeros and drops what it would write there.
+template <int NX, int NY, int DIR, int TWM, int KIND>
+__global__ void __launch_bounds__(f2d_tma_threads(NX, NY, KIND), 1)
 fft2d_tma_kernel(const __grid_constant__ f2d_tma_params p)
 {
-    constexpr int F2D_TMA_THREADS = f2d_tma_threads(NX, NY);
-    static_assert(f2d_tma_supported(NX, NY), "shape");
-    constexpr int RX = engine_regs(NX), TX = NX / RX, ROWS = F2D_TMA_GROUP_THREADS / TX; // 8 rows per tile, one warp each
+    constexpr int F2D_TMA_THREADS = f2d_tma_threads(NX, NY, KIND);
+    static_assert(f2d_tma_kind_supported(NX, NY, KIND), "shape / kind");
+    constexpr int VX = f2d_tma_rows_variant(NX, KIND);
+    constexpr int PITCH = f2d_pitch(NX, KIND), WIDTH = f2d_width(NX, KIND);
+    constexpr int RX = engine_regs(NX, VX), TX = NX / RX, ROWS = F2D_TMA_GROUP_THREADS / TX; // 8 rows per tile, one warp each
     constexpr int RY = engine_regs(NY), TY = NY / RY, COLS = F2D_TMA_GROUP_THREADS / TY; // 8 columns per tile: 64-byte segments
-    constexpr unsigned NR = NY / ROWS, NC = NX / COLS;
-    constexpr int ROW_PITCH = f2d_tma_row_pitch(NX);
-    constexpr size_t BUF = f2d_tma_buf_bytes(NX, NY);
-    constexpr int F2D_TMA_STAGES = f2d_tma_stages(NX, NY), LCM = f2d_tma_lcm(F2D_TMA_STAGES);
+    constexpr unsigned NR = NY / ROWS, NC = (WIDTH + COLS - 1) / COLS;
+    constexpr int ROW_PITCH = f2d_tma_row_pitch(NX, KIND);
+    constexpr size_t BUF = f2d_tma_buf_bytes(NX, NY, KIND);
+    constexpr int F2D_TMA_STAGES = f2d_tma_stages(NX, NY, KIND), LCM = f2d_tma_lcm(F2D_TMA_STAGES);
+    static_assert(TX == 32 && TY == 32, "one warp per row, 8 columns per group");
     constexpr unsigned ROW_TILE_BYTES = ROWS * NX * sizeof(cpx), COL_TILE_BYTES = COLS * NY * sizeof(cpx);
     constexpr int UTIL0 = F2D_TMA_GROUPS * F2D_TMA_GROUP_THREADS; // first thread of the loader's warp
     static_assert(F2D_TMA_STAGES >= 2 && F2D_TMA_STAGES < 32, "buffers");
     static_assert((size_t)ROWS * ROW_PITCH * sizeof(cpx) <= BUF && (ROW_PITCH * sizeof(cpx)) % 16 == 0, "row tile layout");
-    static_assert((f2d_tw_elems(NX, NY, 0) * sizeof(cpx)) % 16 == 0, "meta alignment");
+    static_assert((f2d_tw_elems(NX, NY, VX) * sizeof(cpx)) % 16 == 0, "meta alignment");
     // Used as it is: pointer arithmetic through integers would turn every LDS / STS below into a generic LD / ST (seen
     // in the first ncu capture).  The kernel has no static shared memory: offset 0, aligned for the tensor copies.
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *base = smem_raw;
     cpx *tws = reinterpret_cast<cpx *>(base + F2D_TMA_STAGES * BUF);
-    uint4 *meta = reinterpret_cast<uint4 *>(tws + f2d_tw_elems(NX, NY, 0)); // x = type, y = image, z = tile
+    uint4 *meta = reinterpret_cast<uint4 *>(tws + f2d_tw_elems(NX, NY, VX)); // x = type, y = image, z = tile
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(meta + F2D_TMA_STAGES);
     // full[b * GROUPS + g]: one barrier per (buffer, group) - a parity wait only works for a waiter that sees EVERY phase
     // of its barrier, and a group meets a given buffer every second time the buffer is used
@@ -165,10 +184,10 @@ fft2d_tma_kernel(const __grid_constant__ f2d_tma_params p)
     const mcu_2d_args &a = p.a;
     const int tid = threadIdx.x;
     const cpx *twx_g = static_cast<const cpx *>(a.tw_x), *twy_g = static_cast<const cpx *>(a.tw_y);
-    for (int i = tid; i < engine_tw_total(NX, 0); i += F2D_TMA_THREADS) tws[i] = __ldg(twx_g + i);
-    if constexpr (NX != NY)
-        for (int i = tid; i < engine_tw_total(NY); i += F2D_TMA_THREADS) tws[engine_tw_total(NX, 0) + i] = __ldg(twy_g + i);
-    const cpx *twx = tws, *twy = NX != NY ? tws + engine_tw_total(NX, 0) : tws;
+    for (int i = tid; i < engine_tw_total(NX, VX); i += F2D_TMA_THREADS) tws[i] = __ldg(twx_g + i);
+    if constexpr (NX != NY || VX != 0)
+        for (int i = tid; i < engine_tw_total(NY); i += F2D_TMA_THREADS) tws[engine_tw_total(NX, VX) + i] = __ldg(twy_g + i);
+    const cpx *twx = tws, *twy = (NX != NY || VX != 0) ? tws + engine_tw_total(NX, VX) : tws;
     if (tid == 0) {
         for (int b = 0; b < F2D_TMA_STAGES; b++) {
             for (int g = 0; g < F2D_TMA_GROUPS; g++) mbar_init(full + b * F2D_TMA_GROUPS + g, 1);
@@ -206,10 +225,15 @@ fft2d_tma_kernel(const __grid_constant__ f2d_tma_params p)
 #pragma unroll
                 for (int e = 0; e < RX; e++) v[e] = sm[t + e * TX];
                 __syncwarp(); // the row is in registers before the exchange overwrites it
-                engine_run<NX, DIR, 1, TX, ROWS, 0, 0, -1, TWM>(v, sm, twx, t, slot);
+                engine_run<NX, DIR, 1, TX, ROWS, 0, VX, -1, TWM>(v, sm, twx, t, slot);
                 __syncwarp(); // every lane has gathered
+                if constexpr (KIND == F2D_R2C) {
+                    // resolve in registers (mirrored last pass), bins 0 .. NX into the row's natural positions
+                    rows_store_spectrum<NX, MCU_OUT_R2C, TX, ROWS, VX>(v, [sm](int k, cpx val) { sm[k] = val; }, sm, static_cast<const cpx *>(a.rtw), t, slot, true);
+                } else {
 #pragma unroll
-                for (int e = 0; e < RX; e++) sm[t + e * TX] = v[e];
+                    for (int e = 0; e < RX; e++) sm[t + e * TX] = v[e];
+                }
             } else {
                 const int c = gtid % COLS, t = gtid / COLS;
                 cpx v[RY];
@@ -341,10 +365,15 @@ fft2d_tma_kernel(const __grid_constant__ f2d_tma_params p)
                 continue;
             }
             if (m.x == F2D_TMA_ROWS) {
-                cpx *dst = static_cast<cpx *>(a.out) + (size_t)m.y * a.out_image + (size_t)m.z * ROWS * NX;
+                cpx *dst = static_cast<cpx *>(a.out) + (size_t)m.y * a.out_image + (size_t)m.z * ROWS * PITCH;
 #pragma unroll 1
                 for (int r = 0; r < ROWS; r++)
-                    bulk_store_1d<MUFFT_TMA_POLICY_MID_ST>(dst + (size_t)r * NX, buf + (size_t)r * ROW_PITCH * sizeof(cpx), NX * sizeof(cpx), pol_mid);
+                    bulk_store_1d<MUFFT_TMA_POLICY_MID_ST>(dst + (size_t)r * PITCH, buf + (size_t)r * ROW_PITCH * sizeof(cpx), NX * sizeof(cpx), pol_mid);
+                if constexpr (KIND == F2D_R2C) {
+                    // bin NX of every row: 8 bytes, not a bulk copy
+#pragma unroll 1
+                    for (int r = 0; r < ROWS; r++) dst[(size_t)r * PITCH + NX] = reinterpret_cast<const cpx *>(buf)[(size_t)r * ROW_PITCH + NX];
+                }
             } else {
 #pragma unroll 1
                 for (int q = 0; q < NY / F2D_TMA_BOX_ROWS; q++)

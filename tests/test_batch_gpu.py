@@ -776,3 +776,33 @@ def test_c2c_8192_tma_rows(m, torch, oracle, batch):
         assert m.mufft_execute_plan_1d_batch(plan, z.data_ptr(), z.data_ptr(), batch, 0, 0) == 0
         assert torch.equal(z, y)
         m.mufft_free_plan_1d(plan)
+
+
+def test_r2c_2d_tma_kernel(m, torch, oracle):
+    """Real images 1024 wide and 1024 high, 8 or more of them: rows (with the resolve) and columns on the warp-specialised
+    TMA kernel; the last column tile holds ONE column that carries data (bin 512) and seven the tensor map clips.
+    Every image against cuFFT, one against the oracle, the padding columns of the output untouched; a batch of 7 (ticket
+    kernel) gives the same images."""
+    nx, ny, batch = 1024, 1024, 11
+    g = torch.Generator(device="cuda")
+    g.manual_seed(77)
+    x = torch.rand((batch, ny, nx), dtype=torch.float32, device="cuda", generator=g) - 0.5
+    out = torch.full((batch, ny, nx, 2), 7.0, dtype=torch.float32, device="cuda")
+    plan = m.mufft_create_plan_2d_r2c(nx, ny, 0)
+    assert plan
+    m.mufft_cuda_launch_count(1)
+    assert m.mufft_execute_plan_2d_batch(plan, out.data_ptr(), x.data_ptr(), batch) == 0, m.mufft_cuda_last_error()
+    assert m.mufft_cuda_launch_count(1) == 1
+    width = nx // 2 + 1
+    got = torch.view_as_complex(out)
+    ref = torch.fft.fft2(x)[:, :, :width]
+    err = (torch.linalg.vector_norm((got[:, :, :width] - ref).reshape(batch, -1), dim=1) / torch.linalg.vector_norm(ref.reshape(batch, -1), dim=1)).max().item()
+    assert err <= tol(nx * ny)
+    assert bool((out[:, :, width:, :] == 7.0).all()), "columns beyond nx/2 + 1 are padding: never written"
+    want = oracle.r2c_2d(x[3].cpu().numpy(), 0)[:, :width]
+    assert rel_l2(got[3, :, :width].cpu().numpy(), want) <= tol(nx * ny)
+    small = torch.zeros((7, ny, nx, 2), dtype=torch.float32, device="cuda")
+    assert m.mufft_execute_plan_2d_batch(plan, small.data_ptr(), x.data_ptr(), 7) == 0, m.mufft_cuda_last_error()
+    ds = torch.view_as_complex(small)[:, :, :width] - got[:7, :, :width]
+    assert (torch.linalg.vector_norm(ds) / torch.linalg.vector_norm(ref[:7])).item() <= tol(nx * ny)
+    m.mufft_free_plan_2d(plan)
