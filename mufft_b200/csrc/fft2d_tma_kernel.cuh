@@ -241,9 +241,20 @@ fft2d_tma_kernel(const __grid_constant__ f2d_tma_params p)
                 for (int e = 0; e < RY; e++) v[e] = buf[(t + e * TY) * COLS + c];
                 group_barrier(group);
                 engine_run<NY, DIR, COLS, F2D_TMA_GROUP_THREADS, F2D_TMA_GROUPS, 0, 0, -1, TWM>(v, buf + c, twy, t, group);
-                group_barrier(group);
+                if (WIDTH % COLS != 0 && meta[b].z == NC - 1) {
+                    // The last column tile of an R2C image carries WIDTH % COLS columns.  The TMA unit clips a store at the
+                    // edge of the tensor map in units of 16 bytes, i.e. it would write one padding column with zeros (seen:
+                    // column 513): these few columns go out from registers instead, and the storer skips the tile.
+                    if (c < WIDTH % COLS) {
+                        cpx *o = static_cast<cpx *>(a.out) + (size_t)meta[b].y * a.out_image + (size_t)(NC - 1) * COLS + c;
 #pragma unroll
-                for (int e = 0; e < RY; e++) buf[(t + e * TY) * COLS + c] = v[e];
+                        for (int e = 0; e < RY; e++) __stcs(o + (size_t)(t + e * TY) * PITCH, v[e]);
+                    }
+                } else {
+                    group_barrier(group);
+#pragma unroll
+                    for (int e = 0; e < RY; e++) buf[(t + e * TY) * COLS + c] = v[e];
+                }
             }
             fence_proxy_async_smem(); // this thread's writes, before the TMA unit reads the buffer
             mbar_arrive(staged + b);
@@ -362,6 +373,10 @@ fft2d_tma_kernel(const __grid_constant__ f2d_tma_params p)
             if (m.x == F2D_TMA_EXIT) {
                 mbar_arrive(freed + b);
                 if (++exits == LCM / F2D_TMA_STAGES) break;
+                continue;
+            }
+            if (WIDTH % COLS != 0 && m.x == F2D_TMA_COLS && m.z == NC - 1) { // stored by the group itself, from registers
+                mbar_arrive(freed + b);
                 continue;
             }
             if (m.x == F2D_TMA_ROWS) {

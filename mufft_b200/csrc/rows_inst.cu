@@ -4,14 +4,14 @@
 // Every (input mode, output mode) pair the host layer can ask for is a separate kernel instantiation.
 #include "rows_kernel.cuh"
 #include "launch_util.cuh"
-#ifndef MUFFT_ROWS_TMA
-#define MUFFT_ROWS_TMA 1 // large batches of 8192-point C2C transforms go to the warp-specialised kernel (rows_tma_kernel.cuh): 0.88 vs 0.83
+#ifndef MUFFT_ROWS_PREFETCH
+#define MUFFT_ROWS_PREFETCH 1 // large batches of 8192 / 16384-point transforms go to the persistent prefetching kernel (rows_prefetch_kernel.cuh)
 #endif
-#if MUFFT_ROWS_TMA && ROWS_N == 8192
-#include "rows_tma_kernel.cuh"
+#if MUFFT_ROWS_PREFETCH && (ROWS_N == 16384 || ROWS_N == 8192)
+#include "rows_prefetch_kernel.cuh"
 #endif
-#ifndef MUFFT_ROWS_TMA_MIN_BATCH
-#define MUFFT_ROWS_TMA_MIN_BATCH 1024
+#ifndef MUFFT_ROWS_PREFETCH_MIN_BATCH
+#define MUFFT_ROWS_PREFETCH_MIN_BATCH 1024
 #endif
 
 #if !defined(ROWS_N) || !defined(ROWS_DIR)
@@ -33,17 +33,15 @@ static cudaError_t launch_mode(const mcu_rows_args &a, cudaStream_t stream)
     const size_t groups = (a.batch + TPC - 1) / TPC;
     if (groups == 0) return cudaSuccess;
     if (groups > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-#if MUFFT_ROWS_TMA && ROWS_N == 8192
-    if constexpr (rows_tma_supported(N, IN_MODE, OUT_MODE)) {
-        // bulk copies: 16-byte aligned transforms on both sides
-        if (a.batch >= MUFFT_ROWS_TMA_MIN_BATCH && ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.out)) & 15) == 0 &&
-            ((a.in_stride | a.out_stride) & 1) == 0) {
-            static launch_cfg tcfg;
-            auto tkernel = fft_rows_tma_kernel<N, DIR, IN_MODE>;
+#if MUFFT_ROWS_PREFETCH && (ROWS_N == 16384 || ROWS_N == 8192)
+    if constexpr (rows_prefetch_supported(N, IN_MODE, OUT_MODE)) {
+        if (a.batch >= MUFFT_ROWS_PREFETCH_MIN_BATCH && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0 && (a.in_stride & 1) == 0) {
+            static launch_cfg pcfg;
+            auto pkernel = fft_rows_prefetch_kernel<N, DIR, IN_MODE>;
             int ctas = 0;
-            cudaError_t terr = launch_prepare(tcfg, tkernel, rows_tma_smem_bytes(N), ROWS_TMA_THREADS(N), &ctas);
-            if (terr != cudaSuccess) return terr;
-            tkernel<<<(unsigned)ctas, ROWS_TMA_THREADS(N), rows_tma_smem_bytes(N), stream>>>(a);
+            cudaError_t perr = launch_prepare(pcfg, pkernel, rows_prefetch_smem_bytes(N), rows_cta_threads(N, 0), &ctas);
+            if (perr != cudaSuccess) return perr;
+            pkernel<<<(unsigned)ctas, rows_cta_threads(N, 0), rows_prefetch_smem_bytes(N), stream>>>(a);
             return cudaGetLastError();
         }
     }

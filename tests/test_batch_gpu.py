@@ -151,6 +151,39 @@ def test_c2c_batch_host_memory(m, torch, oracle, n, kind):
         assert rel_l2(got[i], oracle.c2c(x[i].view(np.complex64), -1)) <= tol(n)
 
 
+@pytest.mark.parametrize("n,batch", [(8192, 1500), (8192, 1024), (16384, 1100)])
+def test_conv_stereo_large_batch_prefetch_rows(m, torch, oracle, n, batch):
+    """Stereo convolution in batches of 1024 blocks or more: both stages (zero-padded forward transform, spectral multiply
+    + inverse transform) run on the persistent prefetching row kernel (rows_prefetch_kernel.cuh).  Every block against
+    torch's FFT convolution, a sample against the oracle."""
+    method = 1 | 4 | 8
+    plan = m.mufft_create_plan_conv(n, 0, method)
+    assert plan
+    blk = m.mufft_conv_get_transformed_block_size(plan) // 8
+    a = dev_random(torch, (batch, n), 21)            # n/2 complex samples per block
+    filt = dev_random(torch, (1, n // 2), 22)
+    sa = torch.zeros((batch, 2 * blk), dtype=torch.float32, device="cuda")
+    sf = torch.zeros((1, 2 * blk), dtype=torch.float32, device="cuda")
+    out = torch.zeros((batch, 2 * n), dtype=torch.float32, device="cuda")
+    assert m.mufft_execute_conv_input_batch(plan, 1, sf.data_ptr(), filt.data_ptr(), 1) == 0
+    m.mufft_cuda_launch_count(1)
+    assert m.mufft_execute_conv_input_batch(plan, 0, sa.data_ptr(), a.data_ptr(), batch) == 0, m.mufft_cuda_last_error()
+    assert m.mufft_execute_conv_output_batch(plan, out.data_ptr(), sa.data_ptr(), sf.data_ptr(), batch, 0) == 0, m.mufft_cuda_last_error()
+    assert m.mufft_cuda_launch_count(1) == 2
+    m.mufft_free_plan_conv(plan)
+    ac = torch.view_as_complex(a.view(batch, n // 2, 2))
+    fr = filt[0]
+    spec = torch.fft.fft(ac, n=n, dim=1) * torch.fft.fft(fr.to(torch.complex64), n=n)
+    ref = torch.fft.ifft(spec, dim=1)  # the plan normalises by 1/n as ifft does
+    got = torch.view_as_complex(out.view(batch, n, 2))
+    err = (torch.linalg.vector_norm(got - ref, dim=1) / torch.linalg.vector_norm(ref, dim=1)).max().item()
+    assert err <= 2 * tol(n), f"worst block rel L2 {err:.3e}"
+    f = filt[0].cpu().numpy()
+    for i in (0, batch // 2, batch - 1):
+        want, _, _ = oracle.conv(a[i].cpu().numpy().view(np.complex64), f, n, method)
+        assert rel_l2(out[i].cpu().numpy().view(np.complex64), want) <= 2 * tol(n)
+
+
 @pytest.mark.parametrize("n", [64, 2048, 8192, 32768])
 @pytest.mark.parametrize("stereo", [0, 1])
 def test_conv_batch_device(m, torch, oracle, n, stereo):
@@ -751,11 +784,11 @@ def test_c2c_2d_tma_kernel_and_its_fallbacks(m, torch, nx, ny):
         m.mufft_free_plan_2d(plan)
 
 
-@pytest.mark.parametrize("batch", [1023, 1024, 2500])
-def test_c2c_8192_tma_rows(m, torch, oracle, batch):
-    """8192-point C2C: batches of 1024 transforms or more run on the warp-specialised TMA row kernel
-    (rows_tma_kernel.cuh), smaller ones on the row kernel; same results, checked on every transform."""
-    n = 8192
+@pytest.mark.parametrize("n,batch", [(8192, 1023), (8192, 1024), (8192, 2500), (16384, 1023), (16384, 1400)])
+def test_c2c_prefetch_rows(m, torch, oracle, n, batch):
+    """8192 / 16384-point C2C: batches of 1024 transforms or more run on the persistent row kernel that lets the TMA unit
+    fetch the next transform into the exchange area (rows_prefetch_kernel.cuh), smaller ones on the row kernel; same
+    results, checked on every transform, out of place and in place."""
     x = dev_random(torch, (batch, 2 * n), batch)
     for direction in (-1, 1):
         y = torch.zeros_like(x)
@@ -771,7 +804,6 @@ def test_c2c_8192_tma_rows(m, torch, oracle, batch):
         assert err <= tol(n), f"worst transform rel L2 {err:.3e}"
         for i in (0, batch - 1):
             assert rel_l2(y[i].cpu().numpy().view(np.complex64), oracle.c2c(x[i].cpu().numpy().view(np.complex64), direction)) <= tol(n)
-        # in place
         z = x.clone()
         assert m.mufft_execute_plan_1d_batch(plan, z.data_ptr(), z.data_ptr(), batch, 0, 0) == 0
         assert torch.equal(z, y)
