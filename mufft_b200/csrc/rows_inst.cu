@@ -37,11 +37,11 @@ static cudaError_t launch_mode(const mcu_rows_args &a, cudaStream_t stream)
     if constexpr (rows_prefetch_supported(N, IN_MODE, OUT_MODE)) {
         if (a.batch >= MUFFT_ROWS_PREFETCH_MIN_BATCH && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0 && (a.in_stride & 1) == 0) {
             static launch_cfg pcfg;
-            auto pkernel = fft_rows_prefetch_kernel<N, DIR, IN_MODE>;
+            auto pkernel = fft_rows_prefetch_kernel<N, DIR, IN_MODE, OUT_MODE>;
             int ctas = 0;
-            cudaError_t perr = launch_prepare(pcfg, pkernel, rows_prefetch_smem_bytes(N), rows_cta_threads(N, 0), &ctas);
+            cudaError_t perr = launch_prepare(pcfg, pkernel, rows_prefetch_smem_bytes(N, V), rows_cta_threads(N, V), &ctas);
             if (perr != cudaSuccess) return perr;
-            pkernel<<<(unsigned)ctas, rows_cta_threads(N, 0), rows_prefetch_smem_bytes(N), stream>>>(a);
+            pkernel<<<(unsigned)ctas, rows_cta_threads(N, V), rows_prefetch_smem_bytes(N, V), stream>>>(a);
             return cudaGetLastError();
         }
     }

@@ -6,7 +6,8 @@
 // overlaps - 0.62 of the HBM roofline.  Here the exchange area doubles as the landing buffer of the next transform: it is
 // idle from the gather of the last exchange to the scatter of the next transform's first one, which is when the last
 // pass and the stores of this transform run.  Measured (profiles/r02ac_ab.txt, r02ad_ab.txt): 16384 points 0.62 -> 0.77 of
-// the HBM roofline, 8192 points 0.83 -> 0.92, the two stages of the stereo convolution at 8192 points 0.71 -> 0.735.
+// the HBM roofline, 8192 points 0.83 -> 0.92, the two stages of the stereo convolution at 8192 points 0.71 -> 0.735-0.75,
+// R2C of 32768 / 16384 reals 0.56 -> 0.65 / 0.74 -> 0.76 (r02af_ab.txt; R2C of 8192 reals, four CTAs per SM, does not gain).
 // (A warp-specialised version for 8192 points - loader, two compute groups, storers, three buffers, as
 // fft2d_tma_kernel.cuh - reached 0.88 and lost on the convolution stages: profiles/r02aa_ab.txt.  Gone.)
 //
@@ -24,25 +25,33 @@
 
 namespace mufft {
 
+// Complex output with the general engine shape, or an R2C output (half or full spectrum) with the mirrored-last-pass shape,
+// whose resolve happens in registers on the way out: nothing after the last gather touches the buffer.
 __host__ __device__ constexpr bool rows_prefetch_supported(int n, int in_mode, int out_mode)
 {
-    return (n == 8192 || n == 16384) && engine_regs(n) > 0 && rows_per_cta(n, 0) == 1 && engine_num_passes(n, 0) >= 2 && out_mode == MCU_OUT_COMPLEX &&
-           (in_mode == MCU_IN_COMPLEX || in_mode == MCU_IN_HALF || in_mode == MCU_IN_MUL);
+    const int v = rows_variant(n, in_mode, out_mode);
+    if (engine_regs(n, v) == 0 || rows_per_cta(n, v) != 1 || engine_num_passes(n, v) < 2) return false;
+    if (out_mode == MCU_OUT_COMPLEX)
+        return (n == 8192 || n == 16384) && v == 0 && (in_mode == MCU_IN_COMPLEX || in_mode == MCU_IN_HALF || in_mode == MCU_IN_MUL);
+    if (out_mode == MCU_OUT_R2C || out_mode == MCU_OUT_R2C_FULL)
+        return (n == 8192 || n == 16384) && v == MUFFT_VARIANT_MIRROR_LAST && (in_mode == MCU_IN_COMPLEX || in_mode == MCU_IN_HALF);
+    return false;
 }
-__host__ __device__ constexpr size_t rows_prefetch_smem_bytes(int n) { return ((size_t)engine_smem_elems(n, 0) * sizeof(float2) + 127) / 128 * 128 + 16; }
+__host__ __device__ constexpr size_t rows_prefetch_smem_bytes(int n, int v = 0) { return ((size_t)engine_smem_elems(n, v) * sizeof(float2) + 127) / 128 * 128 + 16; }
 
 #ifndef MUFFT_EMU
-template <int N, int DIR, int IN_MODE>
-__global__ void __launch_bounds__(rows_cta_threads(N, 0), engine_min_blocks(N, 0))
+template <int N, int DIR, int IN_MODE, int OUT_MODE>
+__global__ void __launch_bounds__(rows_cta_threads(N, rows_variant(N, IN_MODE, OUT_MODE)), engine_min_blocks(N, rows_variant(N, IN_MODE, OUT_MODE)))
 fft_rows_prefetch_kernel(const mcu_rows_args a)
 {
-    static_assert(rows_prefetch_supported(N, IN_MODE, MCU_OUT_COMPLEX), "shape / mode");
-    constexpr int R = engine_regs(N, 0), T = N / R, NP = engine_num_passes(N, 0);
-    constexpr int PK = rows_packed(N, IN_MODE, MCU_OUT_COMPLEX);
+    static_assert(rows_prefetch_supported(N, IN_MODE, OUT_MODE), "shape / mode");
+    constexpr int V = rows_variant(N, IN_MODE, OUT_MODE);
+    constexpr int R = engine_regs(N, V), T = N / R, NP = engine_num_passes(N, V);
+    constexpr int PK = rows_packed(N, IN_MODE, OUT_MODE);
     constexpr unsigned BYTES = (IN_MODE == MCU_IN_HALF ? N / 2 : N) * sizeof(cpx); // a zero-padded input is half as long
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cpx *buf = reinterpret_cast<cpx *>(smem_raw);
-    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + rows_prefetch_smem_bytes(N) - 16);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + rows_prefetch_smem_bytes(N, V) - 16);
     const int t = threadIdx.x;
     const cpx *__restrict__ tw = static_cast<const cpx *>(a.tw);
     const unsigned long long pol = l2_policy<1>(); // read once
@@ -62,15 +71,15 @@ fft_rows_prefetch_kernel(const mcu_rows_args a)
     for (size_t k = blockIdx.x; k < a.batch; k += gridDim.x, phase ^= 1) {
         MUFFT_TMA_WAIT(0, full, phase, "full", 0, phase);
         cpx v[R];
-        rows_load<N, IN_MODE, 0>(v, static_cast<const cpx *>(buf), static_cast<const cpx *>(a.in2) + k * a.in2_stride, static_cast<const cpx *>(nullptr), a.norm, t);
+        rows_load<N, IN_MODE, V>(v, static_cast<const cpx *>(buf), static_cast<const cpx *>(a.in2) + k * a.in2_stride, static_cast<const cpx *>(nullptr), a.norm, t);
         __syncthreads(); // the transform is in registers before the exchange overwrites it
         static_for<NP - 1>([&](auto pc) {
             constexpr int PASS = decltype(pc)::value;
-            engine_butterflies<N, DIR, PASS, 0, PK>(v, tw, t);
+            engine_butterflies<N, DIR, PASS, V, PK>(v, tw, t);
             if constexpr (PASS > 0) __syncthreads(); // previous gather complete
-            engine_scatter<N, PASS, 1>(v, buf, t);
+            engine_scatter<N, PASS, 1, V>(v, buf, t);
             __syncthreads();
-            engine_gather<N, 1, PASS + 1>(v, buf, t);
+            engine_gather<N, 1, PASS + 1, V>(v, buf, t);
         });
         __syncthreads(); // every thread has gathered: the buffer is free
         if (t == 0 && k + gridDim.x < a.batch) {
@@ -78,10 +87,14 @@ fft_rows_prefetch_kernel(const mcu_rows_args a)
             mbar_arrive_expect_tx(full, BYTES);
             bulk_load_1d<1>(buf, static_cast<const cpx *>(a.in) + (k + gridDim.x) * a.in_stride, BYTES, full, pol);
         }
-        engine_butterflies<N, DIR, NP - 1, 0, PK>(v, tw, t);
+        engine_butterflies<N, DIR, NP - 1, V, PK>(v, tw, t);
         cpx *__restrict__ out = static_cast<cpx *>(a.out) + k * a.out_stride;
+        if constexpr (OUT_MODE == MCU_OUT_COMPLEX) {
 #pragma unroll
-        for (int e = 0; e < R; e++) __stcs(out + t + e * T, v[e]);
+            for (int e = 0; e < R; e++) __stcs(out + t + e * T, v[e]);
+        } else {
+            rows_store<N, OUT_MODE, T, 1, V>(v, out, buf, static_cast<const cpx *>(a.rtw), t, 0, true); // mirrored last pass: registers only
+        }
     }
 }
 #endif // MUFFT_EMU

@@ -838,3 +838,33 @@ def test_r2c_2d_tma_kernel(m, torch, oracle):
     ds = torch.view_as_complex(small)[:, :, :width] - got[:7, :, :width]
     assert (torch.linalg.vector_norm(ds) / torch.linalg.vector_norm(ref[:7])).item() <= tol(nx * ny)
     m.mufft_free_plan_2d(plan)
+
+
+@pytest.mark.parametrize("n", [16384, 32768])
+@pytest.mark.parametrize("flags", [0, FLAG_FULL_R2C, FLAG_ZERO_PAD])
+def test_r2c_large_batch_prefetch_rows(m, torch, oracle, n, flags):
+    """R2C of 16384 / 32768 reals in batches of 1024 or more: the persistent prefetching row kernel with the resolve in the
+    registers of the mirrored last pass (rows_prefetch_kernel.cuh).  Every transform against cuFFT, a sample against the
+    oracle, a batch of 1023 (row kernel) gives the same bits."""
+    batch = 1100
+    n_in = n // 2 if flags & FLAG_ZERO_PAD else n
+    bins = n if flags & FLAG_FULL_R2C else n // 2 + 1
+    pitch = (bins + 3) // 2 * 2
+    x = dev_random(torch, (batch, n_in), n + flags)
+    spec = torch.zeros((batch, 2 * pitch), dtype=torch.float32, device="cuda")
+    fwd = m.mufft_create_plan_1d_r2c(n, flags)
+    assert fwd
+    m.mufft_cuda_launch_count(1)
+    assert m.mufft_execute_plan_1d_batch(fwd, spec.data_ptr(), x.data_ptr(), batch, pitch * 8, 0) == 0, m.mufft_cuda_last_error()
+    assert m.mufft_cuda_launch_count(1) == 1
+    xp = torch.nn.functional.pad(x, (0, n - n_in))
+    ref = torch.fft.fft(xp, dim=1)[:, :bins]
+    got = torch.view_as_complex(spec.view(batch, pitch, 2))[:, :bins]
+    err = (torch.linalg.vector_norm(got - ref, dim=1) / torch.linalg.vector_norm(ref, dim=1)).max().item()
+    assert err <= tol(n), f"worst transform rel L2 {err:.3e}"
+    for i in (0, batch - 1):
+        assert rel_l2(got[i].cpu().numpy(), oracle.r2c(x[i].cpu().numpy(), flags, n=n)) <= tol(n)
+    small = torch.zeros((1023, 2 * pitch), dtype=torch.float32, device="cuda")
+    assert m.mufft_execute_plan_1d_batch(fwd, small.data_ptr(), x.data_ptr(), 1023, pitch * 8, 0) == 0
+    assert torch.equal(small, spec[:1023])
+    m.mufft_free_plan_1d(fwd)
