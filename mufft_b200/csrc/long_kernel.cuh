@@ -26,7 +26,8 @@
 //     dirty lines from L2 without a write-back): the intermediate never reaches HBM and the live footprint
 //     is half a slot per CTA;
 //   * input loads and output stores carry streaming hints.  (Pulling the next transform's input into L2 by a
-//     bulk prefetch during step B was measured too and is a loss, 0.54 -> 0.45: it pushes the scratch out.)
+//     bulk prefetch during step B was measured twice and is a loss: 0.54 -> 0.45, and 0.565 -> 0.495 with the scratch
+//     stored evict_last, profiles/r02ag_ab_long_l2prefetch_rejected.txt.)
 #pragma once
 
 #include "abi.h"
