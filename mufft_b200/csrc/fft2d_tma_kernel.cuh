@@ -334,7 +334,7 @@ fft2d_tma_kernel(const __grid_constant__ f2d_tma_params p)
                 while (ld_relaxed(produced + image) < NR) {
                     __nanosleep(ns);
                     if (ns < 1024) ns *= 2;
-                    else if (global_ns() - w0 > 2000000000ull) {
+                    else if (global_ns() - w0 > MUFFT_TMA_WATCHDOG_NS) {
 #ifdef MUFFT_TMA_DEBUG
                         printf("cta %d loader: timeout rows of image %u: %u of %u (ticket %u)\n", (int)blockIdx.x, image, ld_relaxed(produced + image), NR, k);
                         return;

@@ -10,6 +10,11 @@
 namespace mufft {
 
 #ifndef MUFFT_EMU
+// A wait that sees no progress for this long ends in a trap instead of hanging the device: a protocol error, never a slow
+// memory system (waits are microseconds).  Long enough to survive a preempted context (time slicing, a debugger).
+#ifndef MUFFT_TMA_WATCHDOG_NS
+#define MUFFT_TMA_WATCHDOG_NS 20000000000ull
+#endif
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(void *bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(void *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
@@ -30,7 +35,7 @@ __device__ __forceinline__ unsigned long long global_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-// A protocol error must not hang the device: two seconds without progress end the wait (false).
+// A protocol error must not hang the device: MUFFT_TMA_WATCHDOG_NS without progress end the wait (false).
 // SLEEP: nanoseconds between polls (0 for the compute warps).
 template <int SLEEP>
 __device__ __forceinline__ bool mbar_wait(void *bar, unsigned parity)
@@ -40,7 +45,7 @@ __device__ __forceinline__ bool mbar_wait(void *bar, unsigned parity)
     unsigned spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if constexpr (SLEEP > 0) __nanosleep(SLEEP);
-        if ((++spins & (SLEEP > 0 ? 1023u : 65535u)) == 0 && global_ns() - t0 > 2000000000ull) return false;
+        if ((++spins & (SLEEP > 0 ? 1023u : 65535u)) == 0 && global_ns() - t0 > MUFFT_TMA_WATCHDOG_NS) return false;
     }
     return true;
 }
