@@ -3,6 +3,9 @@
 // long_ctas_<n1>x<n2>() (scratch slots worth allocating on the current device) to dispatch.cu.
 #include "long_kernel.cuh"
 #include "launch_util.cuh"
+#ifndef MUFFT_LONG_TMA_A
+#define MUFFT_LONG_TMA_A 1 // inputs of step A through the TMA unit (long_kernel.cuh): 32768 points 0.575 -> 0.612 (profiles/r02ah_ab.txt)
+#endif
 
 #if !defined(LONG_N1) || !defined(LONG_N2)
 #error "compile with -DLONG_N1=<n1> -DLONG_N2=<n2>"
@@ -36,6 +39,19 @@ static cudaError_t launch_long(const mcu_long_args &a, cudaStream_t stream, int 
     size_t grid = a.batch < (size_t)resident ? a.batch : (size_t)resident;
     if (a.scratch_slots / SLOTS < grid) grid = a.scratch_slots / SLOTS;
     if (grid == 0) return cudaErrorInvalidValue;
+#if MUFFT_LONG_TMA_A
+    // inputs of step A through the TMA unit: 16-byte aligned transforms
+    if ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0 && (a.in_batch & 1) == 0) {
+        static launch_cfg tcfg;
+        auto tkernel = fft_long_kernel<LONG_N1, LONG_N2, DIR, IN_MODE, TO_PEERS, true>;
+        int tres = 0;
+        err = launch_prepare(tcfg, tkernel, smem + 32, THREADS, &tres);
+        if (err != cudaSuccess) return err;
+        if ((size_t)tres < grid) grid = (size_t)tres;
+        tkernel<<<(unsigned)grid, THREADS, smem + 32, stream>>>(a);
+        return cudaGetLastError();
+    }
+#endif
     kernel<<<(unsigned)grid, THREADS, smem, stream>>>(a);
     return cudaGetLastError();
   }

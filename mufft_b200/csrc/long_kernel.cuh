@@ -33,6 +33,7 @@
 #include "abi.h"
 #include "fft_engine.cuh"
 #include "rows_kernel.cuh"
+#include "tma_util.cuh"
 
 namespace mufft {
 
@@ -106,10 +107,22 @@ __host__ __device__ constexpr bool long_supported(int n1, int n2, bool peers = f
            long_tile_rows(n2, peers) <= 15 + (engine_threads(n2) <= 32 ? 64 : 0); // named barriers 1..15 when a row spans several warps
 }
 // ---- step A: N1-point transforms down the columns of the [N1][N2] view, `THREADS` threads -------------------
+// One column: x = its N1 inputs -> transform, inter-stage twiddles w_N^(k1 c), into the scratch slot.
+template <int N1, int N2, int DIR>
+__device__ __forceinline__ void long_step_a_column(cpx (&x)[N1], int c, cpx *__restrict__ scratch, const cpx *__restrict__ roots, unsigned long long policy)
+{
+    constexpr int LG = ilog2(N1);
+    dft_regs<N1, DIR, MUFFT_LONG_PACKED_A != 0>(x);
+    cpx base[LG];
+#pragma unroll
+    for (int j = 0; j < LG; j++) base[j] = __ldg(roots + ((unsigned)c << j));
+    TwTree<N1, LG, LG - 1, 0, true>::run(x, base, make_float2(1.0f, 0.0f));
+#pragma unroll
+    for (int k1 = 0; k1 < N1; k1++) st_scratch(scratch + k1 * N2 + c, x[k1], policy);
+}
 template <int N1, int N2, int DIR, int IN_MODE, int THREADS>
 __device__ __forceinline__ void long_step_a(const cpx *__restrict__ in, cpx *__restrict__ scratch, const cpx *__restrict__ roots, int tid)
 {
-    constexpr int LG = ilog2(N1);
     const unsigned long long policy = scratch_policy();
 #pragma unroll 1
     for (int c = tid; c < N2; c += THREADS) {
@@ -117,19 +130,15 @@ __device__ __forceinline__ void long_step_a(const cpx *__restrict__ in, cpx *__r
 #pragma unroll
         for (int m = 0; m < N1; m++)
             x[m] = (IN_MODE == MCU_IN_HALF && m >= N1 / 2) ? make_float2(0.0f, 0.0f) : __ldcs(in + c + m * N2); // rows >= N1/2 are the zero half: never read
-        dft_regs<N1, DIR, MUFFT_LONG_PACKED_A != 0>(x);
-        cpx base[LG];
-#pragma unroll
-        for (int j = 0; j < LG; j++) base[j] = __ldg(roots + ((unsigned)c << j));
-        TwTree<N1, LG, LG - 1, 0, true>::run(x, base, make_float2(1.0f, 0.0f));
-#pragma unroll
-        for (int k1 = 0; k1 < N1; k1++) st_scratch(scratch + k1 * N2 + c, x[k1], policy);
+        long_step_a_column<N1, N2, DIR>(x, c, scratch, roots, policy);
     }
 }
 
 // ---- step B: N2-point transforms along the rows of Y, TR rows at a time; `sync` = barrier of the THREADS threads
-template <int N1, int N2, int DIR, bool TO_PEERS, typename Sync>
-__device__ __forceinline__ void long_step_b(const mcu_long_args &a, size_t b, cpx *__restrict__ scratch, cpx *smem, const cpx *__restrict__ tw, int tid, Sync sync)
+// `last_gather` runs (every thread) once the last group's rows have left the exchange area for good.
+template <int N1, int N2, int DIR, bool TO_PEERS, typename Sync, typename LastGather>
+__device__ __forceinline__ void long_step_b(const mcu_long_args &a, size_t b, cpx *__restrict__ scratch, cpx *smem, const cpx *__restrict__ tw, int tid, Sync sync,
+                                            LastGather last_gather)
 {
     constexpr int THREADS = long_cta_threads(N2, TO_PEERS);
     constexpr int R = engine_regs(N2);
@@ -169,6 +178,7 @@ __device__ __forceinline__ void long_step_b(const mcu_long_args &a, size_t b, cp
         const cpx *sm2 = smem + slot2 * SE;
 #pragma unroll
         for (int e = 0; e < R; e++) v[e] = sm2[pad_pos<SH>(t2 + e * T)];
+        if (g == N1 / TR - 1) last_gather();
         engine_butterflies<N2, DIR, NP - 1>(v, tw, t2);
         if constexpr (TO_PEERS) {
             // exchange step of a slab 2D transform: X[x] goes to the column slab of device x >> shift
@@ -193,7 +203,12 @@ __device__ __forceinline__ void long_step_b(const mcu_long_args &a, size_t b, cp
 // consumer hand-over by named barriers, two scratch slots per CTA - measured the same 0.54 of the roofline at 32768
 // points as this kernel with 8 or 16 rows per group: with ~110 registers per thread an SM holds 16 warps whichever way
 // they are arranged, and ncu shows them waiting for loads a third of the time.  profiles/README.md keeps the numbers.)
-template <int N1, int N2, int DIR, int IN_MODE, bool TO_PEERS>
+// TMA_A: the inputs of step A arrive through the exchange area, which step A itself does not use.  Thread 0 asks the TMA
+// unit for the N1 segments of the NEXT sweep of columns (THREADS columns, 64 / 128 KB) as soon as every thread has pulled
+// its column of this sweep into registers; the copy lands while the butterflies run and the scratch is written.  The first
+// sweep of the next transform is asked for when the last group of step B has left the exchange area.  HBM loads no longer
+// stall the warps; needs 16-byte aligned transforms.
+template <int N1, int N2, int DIR, int IN_MODE, bool TO_PEERS, bool TMA_A = false>
 __global__ void __launch_bounds__(long_cta_threads(N2, TO_PEERS), long_cta_threads(N2, TO_PEERS) <= 256 ? MUFFT_LONG_MIN_BLOCKS : 1)
 fft_long_kernel(const mcu_long_args a)
 {
@@ -208,11 +223,56 @@ fft_long_kernel(const mcu_long_args a)
     const cpx *__restrict__ roots = static_cast<const cpx *>(a.roots);
     cpx *__restrict__ scratch = static_cast<cpx *>(a.scratch) + (size_t)blockIdx.x * N;
 
-    for (size_t b = blockIdx.x; b < a.batch; b += gridDim.x) {
-        const cpx *__restrict__ in = static_cast<const cpx *>(a.in) + b * a.in_batch;
-        long_step_a<N1, N2, DIR, IN_MODE, THREADS>(in, scratch, roots, tid);
-        __syncthreads(); // Y is complete and visible to the whole CTA (the reads of step B bypass L1)
-        long_step_b<N1, N2, DIR, TO_PEERS>(a, b, scratch, smem, tw, tid, [] { __syncthreads(); });
+#ifndef MUFFT_EMU
+    if constexpr (TMA_A) {
+        constexpr int SWEEPS = N2 / THREADS;
+        constexpr int ROWS_IN = IN_MODE == MCU_IN_HALF ? N1 / 2 : N1; // rows >= N1/2 are the zero half: never read
+        constexpr unsigned SWEEP_BYTES = ROWS_IN * THREADS * sizeof(cpx);
+        static_assert((size_t)N1 * THREADS * sizeof(cpx) <= long_smem_bytes(N2, TO_PEERS), "a sweep of columns fits the exchange area");
+        unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + (long_smem_bytes(N2, TO_PEERS) + 15) / 16 * 16);
+        const unsigned long long pol_in = l2_policy<1>(), policy = scratch_policy();
+        auto ask = [&](size_t b, int sweep) { // thread 0, after a CTA barrier behind the last reads of the exchange area
+            const cpx *src = static_cast<const cpx *>(a.in) + b * a.in_batch + sweep * THREADS;
+            fence_proxy_async_smem();
+            mbar_arrive_expect_tx(full, SWEEP_BYTES);
+#pragma unroll 1
+            for (int m = 0; m < ROWS_IN; m++) bulk_load_1d<1>(smem + m * THREADS, src + (size_t)m * N2, THREADS * sizeof(cpx), full, pol_in);
+        };
+        if (tid == 0) {
+            mbar_init(full, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            fence_proxy_async_all();
+            if (blockIdx.x < a.batch) ask(blockIdx.x, 0);
+        }
+        __syncthreads();
+        unsigned phase = 0;
+        for (size_t b = blockIdx.x; b < a.batch; b += gridDim.x) {
+#pragma unroll 1
+            for (int sweep = 0; sweep < SWEEPS; sweep++) {
+                MUFFT_TMA_WAIT(0, full, phase, "sweep", sweep, phase);
+                phase ^= 1;
+                cpx x[N1];
+#pragma unroll
+                for (int m = 0; m < N1; m++) x[m] = m < ROWS_IN ? smem[m * THREADS + tid] : make_float2(0.0f, 0.0f);
+                __syncthreads(); // every column of the sweep is in registers
+                if (tid == 0 && sweep + 1 < SWEEPS) ask(b, sweep + 1);
+                long_step_a_column<N1, N2, DIR>(x, sweep * THREADS + tid, scratch, roots, policy);
+            }
+            __syncthreads(); // Y is complete and visible to the whole CTA (the reads of step B bypass L1)
+            long_step_b<N1, N2, DIR, TO_PEERS>(a, b, scratch, smem, tw, tid, [] { __syncthreads(); }, [&] {
+                __syncthreads();
+                if (tid == 0 && b + gridDim.x < a.batch) ask(b + gridDim.x, 0);
+            });
+        }
+    } else
+#endif
+    {
+        for (size_t b = blockIdx.x; b < a.batch; b += gridDim.x) {
+            const cpx *__restrict__ in = static_cast<const cpx *>(a.in) + b * a.in_batch;
+            long_step_a<N1, N2, DIR, IN_MODE, THREADS>(in, scratch, roots, tid);
+            __syncthreads(); // Y is complete and visible to the whole CTA (the reads of step B bypass L1)
+            long_step_b<N1, N2, DIR, TO_PEERS>(a, b, scratch, smem, tw, tid, [] { __syncthreads(); }, [] {});
+        }
     }
 }
 

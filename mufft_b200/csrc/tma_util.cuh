@@ -1,15 +1,15 @@
-// Bulk-copy (TMA) and mbarrier helpers shared by the warp-specialised kernels (fft2d_tma_kernel.cuh, rows_tma_kernel.cuh):
+// Bulk-copy (TMA) and mbarrier helpers shared by fft2d_tma_kernel.cuh, rows_prefetch_kernel.cuh and long_kernel.cuh:
 // thin wrappers over the PTX instructions, plus a wait that cannot hang the device.
 #pragma once
 
+#include "fft_engine.cuh"
+
+#ifndef MUFFT_EMU
 #include <cuda.h>
 #include <cstdio>
 
-#include "fft_engine.cuh"
-
 namespace mufft {
 
-#ifndef MUFFT_EMU
 // A wait that sees no progress for this long ends in a trap instead of hanging the device: a protocol error, never a slow
 // memory system (waits are microseconds).  Long enough to survive a preempted context (time slicing, a debugger).
 #ifndef MUFFT_TMA_WATCHDOG_NS
@@ -106,6 +106,5 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-#endif // MUFFT_EMU
-
 } // namespace mufft
+#endif // MUFFT_EMU
