@@ -5,9 +5,9 @@
 #include "rows_kernel.cuh"
 #include "launch_util.cuh"
 #ifndef MUFFT_ROWS_PREFETCH
-#define MUFFT_ROWS_PREFETCH 1 // large batches of 8192 / 16384-point transforms go to the persistent prefetching kernel (rows_prefetch_kernel.cuh)
+#define MUFFT_ROWS_PREFETCH 1 // large batches of 2048 / 8192 / 16384-point transforms go to the persistent prefetching kernel (rows_prefetch_kernel.cuh)
 #endif
-#if MUFFT_ROWS_PREFETCH && (ROWS_N == 16384 || ROWS_N == 8192)
+#if MUFFT_ROWS_PREFETCH && (ROWS_N == 16384 || ROWS_N == 8192 || ROWS_N == 2048)
 #include "rows_prefetch_kernel.cuh"
 #endif
 #ifndef MUFFT_ROWS_PREFETCH_MIN_BATCH
@@ -33,7 +33,7 @@ static cudaError_t launch_mode(const mcu_rows_args &a, cudaStream_t stream)
     const size_t groups = (a.batch + TPC - 1) / TPC;
     if (groups == 0) return cudaSuccess;
     if (groups > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-#if MUFFT_ROWS_PREFETCH && (ROWS_N == 16384 || ROWS_N == 8192)
+#if MUFFT_ROWS_PREFETCH && (ROWS_N == 16384 || ROWS_N == 8192 || ROWS_N == 2048)
     if constexpr (rows_prefetch_supported(N, IN_MODE, OUT_MODE)) {
         if (a.batch >= MUFFT_ROWS_PREFETCH_MIN_BATCH && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0 && (a.in_stride & 1) == 0) {
             static launch_cfg pcfg;

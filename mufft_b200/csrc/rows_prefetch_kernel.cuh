@@ -1,4 +1,4 @@
-// Batched row transforms of 8192 and 16384 points (C2C, and the convolution stages: zero-padded load, spectral multiply):
+// Batched row transforms of 2048, 8192 and 16384 points (C2C, and the convolution stages: zero-padded load, spectral multiply):
 // the row kernel's shapes - one CTA per transform, 32 values per thread, 66 / 132 KB of exchange area, two / one CTA per
 // SM - made PERSISTENT, with the next transform fetched by the TMA unit while this one finishes.
 //
@@ -7,7 +7,9 @@
 // idle from the gather of the last exchange to the scatter of the next transform's first one, which is when the last
 // pass and the stores of this transform run.  Measured (profiles/r02ac_ab.txt, r02ad_ab.txt): 16384 points 0.62 -> 0.77 of
 // the HBM roofline, 8192 points 0.83 -> 0.92, the two stages of the stereo convolution at 8192 points 0.71 -> 0.735-0.75,
-// R2C of 32768 / 16384 reals 0.56 -> 0.65 / 0.74 -> 0.76 (r02af_ab.txt; R2C of 8192 reals, four CTAs per SM, does not gain).
+// R2C of 32768 / 16384 reals 0.56 -> 0.65 / 0.74 -> 0.76 (r02af_ab.txt; R2C of 8192 reals, four CTAs per SM, does not gain),
+// 2048 points (CTAs of 64 threads) 0.854 -> 0.909; 4096 points LOSE, 0.979 -> 0.942 (r02ai_ab.txt): the row kernel with three
+// CTAs of 80 registers per SM already hides its loads there.
 // (A warp-specialised version for 8192 points - loader, two compute groups, storers, three buffers, as
 // fft2d_tma_kernel.cuh - reached 0.88 and lost on the convolution stages: profiles/r02aa_ab.txt.  Gone.)
 //
@@ -32,7 +34,7 @@ __host__ __device__ constexpr bool rows_prefetch_supported(int n, int in_mode, i
     const int v = rows_variant(n, in_mode, out_mode);
     if (engine_regs(n, v) == 0 || rows_per_cta(n, v) != 1 || engine_num_passes(n, v) < 2) return false;
     if (out_mode == MCU_OUT_COMPLEX)
-        return (n == 8192 || n == 16384) && v == 0 && (in_mode == MCU_IN_COMPLEX || in_mode == MCU_IN_HALF || in_mode == MCU_IN_MUL);
+        return (n == 2048 || n == 8192 || n == 16384) && v == 0 && (in_mode == MCU_IN_COMPLEX || in_mode == MCU_IN_HALF || in_mode == MCU_IN_MUL);
     if (out_mode == MCU_OUT_R2C || out_mode == MCU_OUT_R2C_FULL)
         return (n == 8192 || n == 16384) && v == MUFFT_VARIANT_MIRROR_LAST && (in_mode == MCU_IN_COMPLEX || in_mode == MCU_IN_HALF);
     return false;

@@ -784,9 +784,9 @@ def test_c2c_2d_tma_kernel_and_its_fallbacks(m, torch, nx, ny):
         m.mufft_free_plan_2d(plan)
 
 
-@pytest.mark.parametrize("n,batch", [(8192, 1023), (8192, 1024), (8192, 2500), (16384, 1023), (16384, 1400)])
+@pytest.mark.parametrize("n,batch", [(2048, 1023), (2048, 5000), (8192, 1023), (8192, 1024), (8192, 2500), (16384, 1023), (16384, 1400)])
 def test_c2c_prefetch_rows(m, torch, oracle, n, batch):
-    """8192 / 16384-point C2C: batches of 1024 transforms or more run on the persistent row kernel that lets the TMA unit
+    """2048 / 8192 / 16384-point C2C: batches of 1024 transforms or more run on the persistent row kernel that lets the TMA unit
     fetch the next transform into the exchange area (rows_prefetch_kernel.cuh), smaller ones on the row kernel; same
     results, checked on every transform, out of place and in place."""
     x = dev_random(torch, (batch, 2 * n), batch)
