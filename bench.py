@@ -622,7 +622,7 @@ def main():
     ap.add_argument("--units", type=int, default=0, help="override units per GPU (debug; invalidates the headline)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--also", default="r2c4096,c2r4096,conv8192,conv8192_fused,c2c2d1024,c2c64,c2c16384",
+    ap.add_argument("--also", default="r2c4096,c2r4096,conv8192,conv8192_fused,c2c2d1024,r2c2d1024,c2c64,c2c8192,c2c16384,c2c32768",
                     help="comma separated extra workloads reported under 'also' (N=1 only); '' disables")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
