@@ -605,6 +605,23 @@ def test_second_device_after_the_first(m, torch):
                 m.mufft_free_plan_2d(p2)
                 ref2 = torch.fft.fft2(torch.view_as_complex(img))
                 results.append((torch.linalg.vector_norm(torch.view_as_complex(o2) - ref2) / torch.linalg.vector_norm(ref2)).item())
+                # the batch sizes that select the warp-specialised TMA kernel (tensor map, 211 KB of shared memory), the
+                # prefetching row kernel and the four-step kernel with its inputs through the TMA unit
+                img = torch.rand((9, 1024, 1024, 2), dtype=torch.float32, device=f"cuda:{dev}") - 0.5
+                o2 = torch.zeros_like(img)
+                p2 = m.mufft_create_plan_2d_c2c(1024, 1024, -1, 0)
+                assert m.mufft_execute_plan_2d_batch(p2, o2.data_ptr(), img.data_ptr(), 9) == 0, m.mufft_cuda_last_error()
+                m.mufft_free_plan_2d(p2)
+                ref2 = torch.fft.fft2(torch.view_as_complex(img))
+                results.append((torch.linalg.vector_norm(torch.view_as_complex(o2) - ref2) / torch.linalg.vector_norm(ref2)).item())
+                for n, batch in ((16384, 1100), (32768, 300)):
+                    x = torch.rand((batch, 2 * n), dtype=torch.float32, device=f"cuda:{dev}") - 0.5
+                    y = torch.zeros_like(x)
+                    plan = m.mufft_create_plan_1d_c2c(n, -1, 0)
+                    assert m.mufft_execute_plan_1d_batch(plan, y.data_ptr(), x.data_ptr(), batch, 0, 0) == 0, m.mufft_cuda_last_error()
+                    m.mufft_free_plan_1d(plan)
+                    ref = torch.fft.fft(torch.view_as_complex(x.view(batch, n, 2)), dim=1)
+                    results.append((torch.linalg.vector_norm(torch.view_as_complex(y.view(batch, n, 2)) - ref) / torch.linalg.vector_norm(ref)).item())
     finally:
         m.mufft_cuda_set_device(0)
     assert max(results) <= tol(1024 * 1024)
