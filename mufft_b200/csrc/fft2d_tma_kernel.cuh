@@ -28,10 +28,9 @@
 // ncu shows 6.3 GB of DRAM traffic for 4.29 GB of images (profiles/r02r_tma_nohints.txt); with them 4.31 GB.
 //
 // Measured (profiles/README.md R2.12): 1024 x 1024 x 256 in 1.056 ms against 1.176 ms for the ticket kernel.  With the
-// groups doing NOTHING (MUFFT_TMA_DIAG=3: tiles are only moved in and out) the same launch takes 0.985 ms: that is the
-// L2's own limit - every byte crosses it four times on the SM side (in, intermediate out, intermediate in, out) and twice
-// on the DRAM side, 12.9 GB at the 13.1 TB/s the L2 sustains for a plain copy (6.55 TB/s read + written, both sides) - so a
-// single-pass 2D transform with the intermediate in L2 cannot exceed 0.67 of the HBM roofline on this chip.
+// groups doing NOTHING (MUFFT_TMA_DIAG=3: tiles are only moved in and out) the same launch takes 0.985 ms: the round trip
+// of an intermediate of 4 x 8 MB through L2 is not free - the L2 keeps evict_last lines in a set-aside of ~24 MB, and
+// tools/l2_ceiling_probe.cu shows a round trip costing 2-6 % of a copy below that size and 40 % above.
 #pragma once
 
 #include "fft2d_kernel.cuh"
@@ -144,6 +143,10 @@ __device__ __forceinline__ void group_barrier(int group)
     asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(F2D_TMA_GROUP_THREADS) : "memory");
 }
 
+// (A dynamic tile order - loaders take column tiles whenever an image is complete, rows at most n images ahead, to keep the
+// live intermediate under the ~24 MB of L2 that evict_last lines can hold (tools/l2_ceiling_probe.cu) - was measured:
+// 1.24-1.35 ms against 1.055 ms.  All SMs then read L2 at once and DRAM at once; the static order mixes them.
+// profiles/r02al_ab_tma_dynamic_order_rejected.txt.)
 // (A version whose groups stored their results from registers, handing the buffer back to the loader right after the
 // gather of the exchange, was measured too: 1.184 ms against 1.056 ms - the stores stall the compute warps and a finished
 // row can only be announced a tile late.  profiles/r02u_ab.txt.)
