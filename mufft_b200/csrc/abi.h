@@ -163,6 +163,9 @@ typedef struct mcu_long_args {
 
 /* Single-launch four-step COLUMN transforms of n = n1 x 1024 points down a row-major [n][width] matrix
  * (longcols_kernel.cuh): blocks of 32 columns, intermediate in a ring of L2-resident scratch slots. */
+#ifndef MUFFT_LONGCOLS_CB
+#define MUFFT_LONGCOLS_CB 32 /* columns per block of the four-step column kernel (a multiple of 16) */
+#endif
 typedef struct mcu_longcols_args {
     void *out;             /* may equal `in` */
     const void *in;

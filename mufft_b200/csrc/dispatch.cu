@@ -260,7 +260,7 @@ int mcu_launch_long(const mcu_long_args *a, void *stream)
 // 16384 and 32768 rows: 1.1x / 1.66x faster than two sweeps of the column kernel; 4096 / 8192 rows (first factor 4 / 8:
 // too little work per A tile) measured 1.5-2x SLOWER and keep the two sweeps (profiles/r02h_fastbench_cols.jsonl)
 int mcu_longcols_supported(unsigned n) { return n == 16384 || n == 32768; }
-size_t mcu_longcols_slot_elems(unsigned n) { return (size_t)n * 32; } // a block of 32 columns (longcols_kernel.cuh: LONGCOLS_CB)
+size_t mcu_longcols_slot_elems(unsigned n) { return (size_t)n * MUFFT_LONGCOLS_CB; } // one block of columns (longcols_kernel.cuh)
 unsigned mcu_longcols_default_lag(unsigned n)
 {
     if (!mcu_longcols_supported(n)) return 0;

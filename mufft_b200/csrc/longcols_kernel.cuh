@@ -30,7 +30,7 @@
 namespace mufft {
 
 #define LONGCOLS_N2 1024
-#define LONGCOLS_CB 32       // columns per block
+#define LONGCOLS_CB MUFFT_LONGCOLS_CB // columns per block (abi.h)
 #define LONGCOLS_THREADS 256
 __host__ __device__ constexpr bool longcols_supported(int n1) { return n1 == 16 || n1 == 32; } // 4 / 8 work too but lose to two sweeps
 __host__ __device__ constexpr unsigned longcols_a_tiles() { return (LONGCOLS_N2 / 16) * (LONGCOLS_CB / 16); }

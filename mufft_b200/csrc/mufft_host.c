@@ -1448,7 +1448,7 @@ static int run_cols_axis(const axis *ax, scratch *scr_cols, void *out, size_t ou
         return mcu_launch_cols(&a, stream);
     }
     if (ax->long_cols) {
-        const unsigned blocks = (width + 31) / 32;
+        const unsigned blocks = (width + MUFFT_LONGCOLS_CB - 1) / MUFFT_LONGCOLS_CB;
         const unsigned lag = mcu_longcols_default_lag(ax->n);
         size_t ring = (size_t)lag + 3;
         if (ring > blocks) ring = blocks;
