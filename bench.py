@@ -487,9 +487,10 @@ class Job:
             import torch.distributed as dist_mod
             from mufft_b200.slab import SlabFFT2D
             if not dist_mod.is_initialized():  # single GPU: a one-rank group
-                os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-                os.environ.setdefault("MASTER_PORT", "29577")
-                dist_mod.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+                fd, rdzv = tempfile.mkstemp(prefix="mufft_bench_rdzv_")  # a file store: no port to collide on
+                os.close(fd)
+                os.unlink(rdzv)
+                dist_mod.init_process_group("nccl", init_method="file://" + rdzv, rank=0, world_size=1, device_id=dev)
             world = dist_mod.get_world_size()
             self.slab = SlabFFT2D(n, ny, m.MUFFT_FORWARD, device=dev, chunks=int(os.environ.get("MUFFT_SLAB_CHUNKS", "8")),
                                   exchange=os.environ.get("MUFFT_SLAB_EXCHANGE") or None)
@@ -505,9 +506,10 @@ class Job:
             import torch.distributed as dist_mod
             from mufft_b200.slab import SlabRFFT2D
             if not dist_mod.is_initialized():
-                os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-                os.environ.setdefault("MASTER_PORT", "29577")
-                dist_mod.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+                fd, rdzv = tempfile.mkstemp(prefix="mufft_bench_rdzv_")  # a file store: no port to collide on
+                os.close(fd)
+                os.unlink(rdzv)
+                dist_mod.init_process_group("nccl", init_method="file://" + rdzv, rank=0, world_size=1, device_id=dev)
             world = dist_mod.get_world_size()
             # MUFFT_SLAB_R2C_EXCHANGE=p2p: the R2C row kernel scatters the half spectrum into the peers' slabs (opt-in)
             self.slab = SlabRFFT2D(n, ny, device=dev, chunks=int(os.environ.get("MUFFT_SLAB_CHUNKS", "8")),

@@ -3,7 +3,6 @@
 local row/column transforms are injected (torch CPU FFT here); on the GPU box the same class runs
 them through the CUDA library (tests/test_slab_gpu.py)."""
 import os
-import socket
 
 import pytest
 import torch
@@ -12,15 +11,17 @@ import torch.multiprocessing as mp
 
 
 def _free_port():
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        return s.getsockname()[1]
+    """A rendezvous token for one process group: a fresh file for torch's FileStore.  (A TCP port picked here and bound
+    later by rank 0 can be taken in between - seen once on a GPU box as EADDRINUSE, which with `pytest -x` ends the run.)"""
+    import tempfile
+    fd, path = tempfile.mkstemp(prefix="mufft_rdzv_")
+    os.close(fd)
+    os.unlink(path)  # FileStore creates it
+    return path
 
 
 def _worker(rank, world, port, nx, ny, chunks, natural, direction, result):
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dist.init_process_group("gloo", init_method="file://" + port, rank=rank, world_size=world)
     try:
         from mufft_b200.slab import SlabFFT2D
         g = torch.Generator().manual_seed(1234)
@@ -62,9 +63,7 @@ def test_slab_exchange_gloo(world, natural, nx, ny, chunks):
 
 def test_slab_rejects_indivisible_shapes():
     port = _free_port()
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=0, world_size=1)
+    dist.init_process_group("gloo", init_method="file://" + port, rank=0, world_size=1)
     try:
         from mufft_b200.slab import SlabFFT2D
         plan = SlabFFT2D(8, 8, -1, local_rows=lambda o, i: o.copy_(torch.fft.fft(i, dim=1)), local_cols=lambda o, i: o.copy_(torch.fft.fft(i, dim=0)))
@@ -77,9 +76,7 @@ def test_slab_rejects_indivisible_shapes():
 
 
 def _rworker(rank, world, port, nx, ny, chunks, result):
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dist.init_process_group("gloo", init_method="file://" + port, rank=rank, world_size=world)
     try:
         from mufft_b200.slab import SlabRFFT2D
         g = torch.Generator().manual_seed(99)

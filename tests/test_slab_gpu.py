@@ -4,7 +4,6 @@ peer-scatter / column-slab paths still run);
 with two or more the test spawns one process per GPU (up to 4)."""
 import math
 import os
-import socket
 
 import numpy as np
 import pytest
@@ -19,19 +18,21 @@ def tol(n):
 
 
 def _free_port():
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        return s.getsockname()[1]
+    """A rendezvous token for one process group: a fresh file for torch's FileStore.  (A TCP port picked here and bound
+    later by rank 0 can be taken in between - seen once on a GPU box as EADDRINUSE, which with `pytest -x` ends the run.)"""
+    import tempfile
+    fd, path = tempfile.mkstemp(prefix="mufft_rdzv_")
+    os.close(fd)
+    os.unlink(path)  # FileStore creates it
+    return path
 
 
 def _worker(rank, world, port, nx, ny, natural, direction, exchange, result):
     import torch
     import torch.distributed as dist
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    dist.init_process_group("nccl", init_method="file://" + port, rank=rank, world_size=world, device_id=dev)
     try:
         import mufft_b200
         from mufft_b200.slab import SlabFFT2D
@@ -80,11 +81,9 @@ def test_slab_2d(nx, ny, natural, exchange):
 def _rworker(rank, world, port, nx, ny, result):
     import torch
     import torch.distributed as dist
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    dist.init_process_group("nccl", init_method="file://" + port, rank=rank, world_size=world, device_id=dev)
     try:
         import mufft_b200
         from mufft_b200.slab import SlabRFFT2D
