@@ -57,7 +57,7 @@ __device__ __forceinline__ unsigned long long scratch_policy()
 {
 #if MUFFT_SCRATCH_EVICT_LAST && !defined(MUFFT_EMU)
     unsigned long long p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, " MUFFT_STR(MUFFT_EVICT_LAST_FRACTION) ";" : "=l"(p));
     return p;
 #else
     return 0;

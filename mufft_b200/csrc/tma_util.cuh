@@ -8,6 +8,15 @@
 #include <cuda.h>
 #include <cstdio>
 
+// Fraction of the lines stored with the evict_last policy that really get it (the rest: normal).  The L2 keeps evict_last
+// lines in a set-aside of ~24 MB (tools/l2_ceiling_probe.cu): an intermediate larger than that may be better off with
+// only a part of it pinned.
+#ifndef MUFFT_EVICT_LAST_FRACTION
+#define MUFFT_EVICT_LAST_FRACTION 1.0
+#endif
+#define MUFFT_STR_(x) #x
+#define MUFFT_STR(x) MUFFT_STR_(x)
+
 namespace mufft {
 
 // A wait that sees no progress for this long ends in a trap instead of hanging the device: a protocol error, never a slow
@@ -60,7 +69,7 @@ __device__ __forceinline__ unsigned long long l2_policy()
 {
     unsigned long long pol = 0;
     if constexpr (KIND == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    if constexpr (KIND == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    if constexpr (KIND == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, " MUFFT_STR(MUFFT_EVICT_LAST_FRACTION) ";" : "=l"(pol));
     return pol;
 }
 template <int KIND>
