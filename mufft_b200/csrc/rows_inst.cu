@@ -35,7 +35,9 @@ static cudaError_t launch_mode(const mcu_rows_args &a, cudaStream_t stream)
     if (groups > 0x7fffffffull) return cudaErrorInvalidConfiguration;
 #if MUFFT_ROWS_PREFETCH && (ROWS_N == 16384 || ROWS_N == 8192 || ROWS_N == 2048)
     if constexpr (rows_prefetch_supported(N, IN_MODE, OUT_MODE)) {
-        if (a.batch >= MUFFT_ROWS_PREFETCH_MIN_BATCH && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0 && (a.in_stride & 1) == 0) {
+        // bulk copies: 16-byte aligned transforms (the C2R flavour aligns its copies itself: 8 bytes are enough)
+        if (a.batch >= MUFFT_ROWS_PREFETCH_MIN_BATCH &&
+            (reinterpret_cast<uintptr_t>(a.in) & 15) == 0 && (IN_MODE == MCU_IN_C2R || (a.in_stride & 1) == 0)) {
             static launch_cfg pcfg;
             auto pkernel = fft_rows_prefetch_kernel<N, DIR, IN_MODE, OUT_MODE>;
             int ctas = 0;

@@ -8,7 +8,7 @@
 // pass and the stores of this transform run.  Measured (profiles/r02ac_ab.txt, r02ad_ab.txt): 16384 points 0.62 -> 0.77 of
 // the HBM roofline, 8192 points 0.83 -> 0.92, the two stages of the stereo convolution at 8192 points 0.71 -> 0.735-0.75,
 // R2C of 32768 / 16384 reals 0.56 -> 0.65 / 0.74 -> 0.76 (r02af_ab.txt; R2C of 8192 reals, four CTAs per SM, does not gain),
-// 2048 points (CTAs of 64 threads) 0.854 -> 0.909; 4096 points LOSE, 0.979 -> 0.942 (r02ai_ab.txt): the row kernel with three
+// C2R of 4096 / 16384 / 32768 reals 0.87 -> 0.90 / 0.69 -> 0.75 / 0.53 -> 0.62 (r02aq_ab.txt), 2048 points (CTAs of 64 threads) 0.854 -> 0.909; 4096 points LOSE, 0.979 -> 0.942 (r02ai_ab.txt): the row kernel with three
 // CTAs of 80 registers per SM already hides its loads there.
 // (A warp-specialised version for 8192 points - loader, two compute groups, storers, three buffers, as
 // fft2d_tma_kernel.cuh - reached 0.88 and lost on the convolution stages: profiles/r02aa_ab.txt.  Gone.)
@@ -33,6 +33,8 @@ __host__ __device__ constexpr bool rows_prefetch_supported(int n, int in_mode, i
 {
     const int v = rows_variant(n, in_mode, out_mode);
     if (engine_regs(n, v) == 0 || rows_per_cta(n, v) != 1 || engine_num_passes(n, v) < 2) return false;
+    if (out_mode == MCU_OUT_COMPLEX && in_mode == MCU_IN_C2R) // spectrum rows of n + 1 bins, any pitch
+        return (n == 2048 || n == 8192 || n == 16384) && v == MUFFT_VARIANT_MIRROR_FIRST;
     if (out_mode == MCU_OUT_COMPLEX)
         return (n == 2048 || n == 8192 || n == 16384) && v == 0 && (in_mode == MCU_IN_COMPLEX || in_mode == MCU_IN_HALF || in_mode == MCU_IN_MUL);
     if (out_mode == MCU_OUT_R2C || out_mode == MCU_OUT_R2C_FULL)
@@ -50,6 +52,7 @@ fft_rows_prefetch_kernel(const mcu_rows_args a)
     constexpr int V = rows_variant(N, IN_MODE, OUT_MODE);
     constexpr int R = engine_regs(N, V), T = N / R, NP = engine_num_passes(N, V);
     constexpr int PK = rows_packed(N, IN_MODE, OUT_MODE);
+    constexpr bool C2R = IN_MODE == MCU_IN_C2R;
     constexpr unsigned BYTES = (IN_MODE == MCU_IN_HALF ? N / 2 : N) * sizeof(cpx); // a zero-padded input is half as long
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cpx *buf = reinterpret_cast<cpx *>(smem_raw);
@@ -57,23 +60,45 @@ fft_rows_prefetch_kernel(const mcu_rows_args a)
     const int t = threadIdx.x;
     const cpx *__restrict__ tw = static_cast<const cpx *>(a.tw);
     const unsigned long long pol = l2_policy<1>(); // read once
+    // C2R: a spectrum row has N + 1 bins = 8 bytes more than a multiple of 16, so with a tight pitch every other row starts
+    // 8 bytes off.  The bulk copy starts at the 16-byte boundary at or below the row (one bin of the previous row comes
+    // along: `off` = 1) and ends at the last boundary inside it; bin N, which that may leave out, is fetched by thread 0
+    // with an ordinary load when it asks for the copy and put in place when the copy has landed.
+    cpx nyquist = make_float2(0.0f, 0.0f); // thread 0: bin N of the transform in flight
+    auto row_off = [&](size_t k) -> unsigned {
+        return C2R ? (unsigned)((reinterpret_cast<uintptr_t>(static_cast<const cpx *>(a.in) + k * a.in_stride) & 15) / sizeof(cpx)) : 0u;
+    };
+    auto ask = [&](size_t k) { // thread 0
+        const cpx *row = static_cast<const cpx *>(a.in) + k * a.in_stride;
+        if constexpr (C2R) {
+            const unsigned off = row_off(k), bytes = ((off + N + 1) * (unsigned)sizeof(cpx)) & ~15u;
+            mbar_arrive_expect_tx(full, bytes);
+            bulk_load_1d<1>(buf, row - off, bytes, full, pol);
+            nyquist = __ldg(row + N);
+        } else {
+            mbar_arrive_expect_tx(full, BYTES);
+            bulk_load_1d<1>(buf, row, BYTES, full, pol);
+        }
+    };
 
     if (t == 0) {
         mbar_init(full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async_all();
-        if (blockIdx.x < a.batch) {
-            mbar_arrive_expect_tx(full, BYTES);
-            bulk_load_1d<1>(buf, static_cast<const cpx *>(a.in) + (size_t)blockIdx.x * a.in_stride, BYTES, full, pol);
-        }
+        if (blockIdx.x < a.batch) ask(blockIdx.x);
     }
     __syncthreads();
 
     unsigned phase = 0;
     for (size_t k = blockIdx.x; k < a.batch; k += gridDim.x, phase ^= 1) {
         MUFFT_TMA_WAIT(0, full, phase, "full", 0, phase);
+        const unsigned off = row_off(k);
+        if constexpr (C2R) {
+            if (t == 0) buf[off + N] = nyquist;
+            __syncthreads();
+        }
         cpx v[R];
-        rows_load<N, IN_MODE, V>(v, static_cast<const cpx *>(buf), static_cast<const cpx *>(a.in2) + k * a.in2_stride, static_cast<const cpx *>(nullptr), a.norm, t);
+        rows_load<N, IN_MODE, V>(v, static_cast<const cpx *>(buf + off), static_cast<const cpx *>(a.in2) + k * a.in2_stride, static_cast<const cpx *>(a.rtw), a.norm, t);
         __syncthreads(); // the transform is in registers before the exchange overwrites it
         static_for<NP - 1>([&](auto pc) {
             constexpr int PASS = decltype(pc)::value;
@@ -86,8 +111,7 @@ fft_rows_prefetch_kernel(const mcu_rows_args a)
         __syncthreads(); // every thread has gathered: the buffer is free
         if (t == 0 && k + gridDim.x < a.batch) {
             fence_proxy_async_smem();
-            mbar_arrive_expect_tx(full, BYTES);
-            bulk_load_1d<1>(buf, static_cast<const cpx *>(a.in) + (k + gridDim.x) * a.in_stride, BYTES, full, pol);
+            ask(k + gridDim.x);
         }
         engine_butterflies<N, DIR, NP - 1, V, PK>(v, tw, t);
         cpx *__restrict__ out = static_cast<cpx *>(a.out) + k * a.out_stride;

@@ -885,3 +885,33 @@ def test_r2c_large_batch_prefetch_rows(m, torch, oracle, n, flags):
     assert m.mufft_execute_plan_1d_batch(fwd, small.data_ptr(), x.data_ptr(), 1023, pitch * 8, 0) == 0
     assert torch.equal(small, spec[:1023])
     m.mufft_free_plan_1d(fwd)
+
+
+@pytest.mark.parametrize("n", [4096, 16384, 32768])
+@pytest.mark.parametrize("pitch", ["tight", "aligned"])
+def test_c2r_large_batch_prefetch_rows(m, torch, oracle, n, pitch):
+    """C2R of 4096 / 16384 / 32768 reals in batches of 1024 or more on the persistent prefetching row kernel: spectrum rows of
+    n/2 + 1 bins, tightly packed (every other row starts 8 bytes off a 16-byte boundary: the bulk copy starts one bin
+    early) or at an even pitch.  Every transform against the real input it came from, a sample against the oracle, a batch
+    of 1023 (row kernel) gives the same bits."""
+    batch = 1100
+    bins = n // 2 + 1
+    sp = bins if pitch == "tight" else bins + 1
+    x = dev_random(torch, (batch, n), n + 5)
+    spec = torch.zeros((batch, sp), dtype=torch.complex64, device="cuda")
+    spec[:, :bins] = torch.fft.rfft(x.double(), dim=1).to(torch.complex64)
+    back = torch.zeros((batch, n), dtype=torch.float32, device="cuda")
+    inv = m.mufft_create_plan_1d_c2r(n, 0)
+    assert inv
+    m.mufft_cuda_launch_count(1)
+    assert m.mufft_execute_plan_1d_batch(inv, back.data_ptr(), torch.view_as_real(spec).data_ptr(), batch, 0, sp * 8) == 0, m.mufft_cuda_last_error()
+    assert m.mufft_cuda_launch_count(1) == 1
+    err = (torch.linalg.vector_norm(back / n - x, dim=1) / torch.linalg.vector_norm(x, dim=1)).max().item()
+    assert err <= 2 * tol(n), f"worst transform rel L2 {err:.3e}"
+    ss = torch.view_as_real(spec).cpu().numpy().view(np.complex64).reshape(batch, sp)
+    for i in (0, 1, batch - 1):
+        assert rel_l2(back[i].cpu().numpy(), oracle.c2r(ss[i, :bins].copy(), n)) <= tol(n)
+    small = torch.zeros((1023, n), dtype=torch.float32, device="cuda")
+    assert m.mufft_execute_plan_1d_batch(inv, small.data_ptr(), torch.view_as_real(spec).data_ptr(), 1023, 0, sp * 8) == 0
+    assert torch.equal(small, back[:1023])
+    m.mufft_free_plan_1d(inv)
