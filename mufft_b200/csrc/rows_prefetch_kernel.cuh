@@ -27,6 +27,9 @@
 
 namespace mufft {
 
+#ifndef MUFFT_ROWS_PREFETCH_R2C_ALSO
+#define MUFFT_ROWS_PREFETCH_R2C_ALSO 0 // (A/B builds: one more length for the R2C flavour)
+#endif
 // Complex output with the general engine shape, or an R2C output (half or full spectrum) with the mirrored-last-pass shape,
 // whose resolve happens in registers on the way out: nothing after the last gather touches the buffer.
 __host__ __device__ constexpr bool rows_prefetch_supported(int n, int in_mode, int out_mode)
@@ -38,7 +41,7 @@ __host__ __device__ constexpr bool rows_prefetch_supported(int n, int in_mode, i
     if (out_mode == MCU_OUT_COMPLEX)
         return (n == 2048 || n == 8192 || n == 16384) && v == 0 && (in_mode == MCU_IN_COMPLEX || in_mode == MCU_IN_HALF || in_mode == MCU_IN_MUL);
     if (out_mode == MCU_OUT_R2C || out_mode == MCU_OUT_R2C_FULL)
-        return (n == 8192 || n == 16384) && v == MUFFT_VARIANT_MIRROR_LAST && (in_mode == MCU_IN_COMPLEX || in_mode == MCU_IN_HALF);
+        return (n == MUFFT_ROWS_PREFETCH_R2C_ALSO || n == 8192 || n == 16384) && v == MUFFT_VARIANT_MIRROR_LAST && (in_mode == MCU_IN_COMPLEX || in_mode == MCU_IN_HALF);
     return false;
 }
 __host__ __device__ constexpr size_t rows_prefetch_smem_bytes(int n, int v = 0) { return ((size_t)engine_smem_elems(n, v) * sizeof(float2) + 127) / 128 * 128 + 16; }
