@@ -1,17 +1,19 @@
-// Batched row transforms of 2048, 8192 and 16384 points (C2C, and the convolution stages: zero-padded load, spectral multiply):
-// the row kernel's shapes - one CTA per transform, 32 values per thread, 66 / 132 KB of exchange area, two / one CTA per
-// SM - made PERSISTENT, with the next transform fetched by the TMA unit while this one finishes.
+// Batched row transforms of 2048, 8192 and 16384 points - C2C, the convolution stages (zero-padded load, spectral
+// multiply), R2C and C2R: the row kernel's shapes (one CTA per transform) made PERSISTENT, with the next transform fetched
+// by the TMA unit while this one finishes.
 //
 // fft_rows_kernel<16384, ...> is alone on its SM: it loads 128 KB, computes three passes, stores 128 KB, and nothing
 // overlaps - 0.62 of the HBM roofline.  Here the exchange area doubles as the landing buffer of the next transform: it is
 // idle from the gather of the last exchange to the scatter of the next transform's first one, which is when the last
-// pass and the stores of this transform run.  Measured (profiles/r02ac_ab.txt, r02ad_ab.txt): 16384 points 0.62 -> 0.77 of
-// the HBM roofline, 8192 points 0.83 -> 0.92, the two stages of the stereo convolution at 8192 points 0.71 -> 0.735-0.75,
-// R2C of 32768 / 16384 reals 0.56 -> 0.65 / 0.74 -> 0.76 (r02af_ab.txt; R2C of 8192 reals, four CTAs per SM, does not gain),
-// C2R of 4096 / 16384 / 32768 reals 0.87 -> 0.90 / 0.69 -> 0.75 / 0.53 -> 0.62 (r02aq_ab.txt), 2048 points (CTAs of 64 threads) 0.854 -> 0.909; 4096 points LOSE, 0.979 -> 0.942 (r02ai_ab.txt): the row kernel with three
-// CTAs of 80 registers per SM already hides its loads there.
-// (A warp-specialised version for 8192 points - loader, two compute groups, storers, three buffers, as
-// fft2d_tma_kernel.cuh - reached 0.88 and lost on the convolution stages: profiles/r02aa_ab.txt.  Gone.)
+// pass and the stores of this transform run.  Fraction of the HBM roofline, row kernel -> this kernel (profiles/README.md
+// R2.12; r02ac / r02ad / r02af / r02ai / r02aq _ab.txt):
+//   C2C      16384 points 0.62 -> 0.77     8192 points 0.83 -> 0.92     2048 points (CTAs of 64 threads) 0.85 -> 0.91
+//   stereo convolution at 8192 points, both stages   0.71 -> 0.75
+//   R2C      32768 reals 0.56 -> 0.65      16384 reals 0.74 -> 0.76     (mirrored last pass: the resolve stays in registers)
+//   C2R      32768 reals 0.53 -> 0.62      16384 reals 0.69 -> 0.75     4096 reals 0.87 -> 0.90
+// Not used where it loses: C2C at 4096 points (0.98 -> 0.94: three CTAs of 80 registers per SM already hide their loads),
+// R2C of 8192 / 4096 reals (0.81 -> 0.80 / 0.93 -> 0.86).  A warp-specialised version for 8192 points (loader, two compute
+// groups, storers, three buffers, as fft2d_tma_kernel.cuh) reached 0.88 and lost on the convolution stages: gone.
 //
 //   wait for the bulk copy of transform k     (mbarrier)
 //   registers <- buffer, natural order; barrier
