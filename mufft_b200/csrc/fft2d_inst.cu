@@ -83,7 +83,9 @@ static bool launch_tma(const mcu_2d_args &a, cudaStream_t stream, cudaError_t *e
 #ifdef MUFFT_F2D_TMA_LAG
     if (p.a.lag == 0) p.a.lag = MUFFT_F2D_TMA_LAG;
 #endif
-    if (p.a.lag == 0) p.a.lag = default_lag(f2d_tma_stages(F2D_NX, F2D_NY, KIND) * grid, per_image); // so many tiles in flight per CTA
+    // two tiles per CTA are being computed, the others travel: measured optimum (profiles/r02as_ab_tma_lag.txt) 3 images for C2C
+    // 1024^2 (1.045 against 1.058 ms at 4), 4 for R2C 1024^2 and 512 x 1024 (3: 5 % / 3 % slower)
+    if (p.a.lag == 0) p.a.lag = default_lag(2 * grid, per_image);
     kernel<<<grid, F2D_TMA_THREADS, smem, stream>>>(p);
     *err = cudaGetLastError();
     return true;
