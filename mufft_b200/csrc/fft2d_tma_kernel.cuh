@@ -108,7 +108,6 @@ __host__ __device__ constexpr size_t f2d_tma_smem_bytes(int nx, int ny, int kind
 // the two groups + a warp for the loader and one per storer
 __host__ __device__ constexpr int f2d_tma_threads(int nx, int ny, int kind = F2D_C2C) { return F2D_TMA_GROUPS * F2D_TMA_GROUP_THREADS + 32 * (1 + f2d_tma_stages(nx, ny, kind)); }
 
-#ifndef MUFFT_EMU
 // Timing experiments with WRONG results (never in the product build): 3 = the groups only pass the buffers on,
 // 4 = that, and every tile is moved as 8 rows, 5 = every tile as 8 columns.
 #ifndef MUFFT_TMA_DIAG
@@ -140,7 +139,11 @@ __host__ __device__ constexpr int f2d_tma_threads(int nx, int ny, int kind = F2D
 
 __device__ __forceinline__ void group_barrier(int group)
 {
+#ifdef MUFFT_EMU
+    emu::bar_sync(group + 1, F2D_TMA_GROUP_THREADS);
+#else
     asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(F2D_TMA_GROUP_THREADS) : "memory");
+#endif
 }
 
 // (A dynamic tile order - loaders take column tiles whenever an image is complete, rows at most n images ahead, to keep the
@@ -175,7 +178,7 @@ fft2d_tma_kernel(const __grid_constant__ f2d_tma_params p)
     static_assert((f2d_tw_elems(NX, NY, VX) * sizeof(cpx)) % 16 == 0, "meta alignment");
     // Used as it is: pointer arithmetic through integers would turn every LDS / STS below into a generic LD / ST (seen
     // in the first ncu capture).  The kernel has no static shared memory: offset 0, aligned for the tensor copies.
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    MUFFT_DYNAMIC_SMEM(smem_raw);
     unsigned char *base = smem_raw;
     cpx *tws = reinterpret_cast<cpx *>(base + F2D_TMA_STAGES * BUF);
     uint4 *meta = reinterpret_cast<uint4 *>(tws + f2d_tw_elems(NX, NY, VX)); // x = type, y = image, z = tile
@@ -197,8 +200,7 @@ fft2d_tma_kernel(const __grid_constant__ f2d_tma_params p)
             mbar_init(staged + b, F2D_TMA_GROUP_THREADS);
             mbar_init(freed + b, 1);
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        fence_proxy_async_all();
+        mbar_init_fence();
     }
     __syncthreads(); // the only CTA-wide barrier
 
@@ -411,6 +413,5 @@ fft2d_tma_kernel(const __grid_constant__ f2d_tma_params p)
         bulk_wait_all();
     }
 }
-#endif // MUFFT_EMU
 
 } // namespace mufft

@@ -223,7 +223,6 @@ fft_long_kernel(const mcu_long_args a)
     const cpx *__restrict__ roots = static_cast<const cpx *>(a.roots);
     cpx *__restrict__ scratch = static_cast<cpx *>(a.scratch) + (size_t)blockIdx.x * N;
 
-#ifndef MUFFT_EMU
     if constexpr (TMA_A) {
         constexpr int SWEEPS = N2 / THREADS;
         constexpr int ROWS_IN = IN_MODE == MCU_IN_HALF ? N1 / 2 : N1; // rows >= N1/2 are the zero half: never read
@@ -240,8 +239,7 @@ fft_long_kernel(const mcu_long_args a)
         };
         if (tid == 0) {
             mbar_init(full, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            fence_proxy_async_all();
+            mbar_init_fence();
             if (blockIdx.x < a.batch) ask(blockIdx.x, 0);
         }
         __syncthreads();
@@ -264,9 +262,7 @@ fft_long_kernel(const mcu_long_args a)
                 if (tid == 0 && b + gridDim.x < a.batch) ask(b + gridDim.x, 0);
             });
         }
-    } else
-#endif
-    {
+    } else {
         for (size_t b = blockIdx.x; b < a.batch; b += gridDim.x) {
             const cpx *__restrict__ in = static_cast<const cpx *>(a.in) + b * a.in_batch;
             long_step_a<N1, N2, DIR, IN_MODE, THREADS>(in, scratch, roots, tid);

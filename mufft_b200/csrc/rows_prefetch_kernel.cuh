@@ -48,7 +48,6 @@ __host__ __device__ constexpr bool rows_prefetch_supported(int n, int in_mode, i
 }
 __host__ __device__ constexpr size_t rows_prefetch_smem_bytes(int n, int v = 0) { return ((size_t)engine_smem_elems(n, v) * sizeof(float2) + 127) / 128 * 128 + 16; }
 
-#ifndef MUFFT_EMU
 template <int N, int DIR, int IN_MODE, int OUT_MODE>
 __global__ void __launch_bounds__(rows_cta_threads(N, rows_variant(N, IN_MODE, OUT_MODE)), engine_min_blocks(N, rows_variant(N, IN_MODE, OUT_MODE)))
 fft_rows_prefetch_kernel(const mcu_rows_args a)
@@ -59,7 +58,7 @@ fft_rows_prefetch_kernel(const mcu_rows_args a)
     constexpr int PK = rows_packed(N, IN_MODE, OUT_MODE);
     constexpr bool C2R = IN_MODE == MCU_IN_C2R;
     constexpr unsigned BYTES = (IN_MODE == MCU_IN_HALF ? N / 2 : N) * sizeof(cpx); // a zero-padded input is half as long
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    MUFFT_DYNAMIC_SMEM(smem_raw);
     cpx *buf = reinterpret_cast<cpx *>(smem_raw);
     unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + rows_prefetch_smem_bytes(N, V) - 16);
     const int t = threadIdx.x;
@@ -88,8 +87,7 @@ fft_rows_prefetch_kernel(const mcu_rows_args a)
 
     if (t == 0) {
         mbar_init(full, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        fence_proxy_async_all();
+        mbar_init_fence();
         if (blockIdx.x < a.batch) ask(blockIdx.x);
     }
     __syncthreads();
@@ -128,6 +126,5 @@ fft_rows_prefetch_kernel(const mcu_rows_args a)
         }
     }
 }
-#endif // MUFFT_EMU
 
 } // namespace mufft

@@ -17,6 +17,7 @@
 #include <cmath>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -35,6 +36,11 @@ struct alignas(8) float2 {
     float x, y;
 };
 static inline float2 make_float2(float x, float y) { return float2{ x, y }; }
+struct alignas(16) uint4 {
+    unsigned x, y, z, w;
+};
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{ x, y, z, w }; }
+#define __grid_constant__
 
 namespace emu {
 
@@ -146,6 +152,7 @@ void launch(idx3 grid, unsigned block_threads, size_t dyn_smem_bytes, unsigned c
 static inline void __syncthreads() { emu::sync_threads(); }
 static inline void __syncwarp() { emu::sync_warp(); }
 static inline void __nanosleep(unsigned) { std::this_thread::yield(); }
+[[noreturn]] static inline void __trap() { std::abort(); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 template <typename T> static inline T __ldcs(const T *p) { return *p; }
 template <typename T> static inline T __ldcg(const T *p) { return *p; }

@@ -571,3 +571,142 @@ def test_four_step_columns(emu, host, oracle, n1, width, ctas, lag, ring, inplac
     assert cpu_libs.rel_l2(out[:, :width], want) <= tol(n)
     assert np.all(np.isnan(out[:, width:].real)), "nothing is written beyond the last column"
     assert cpu_libs.rel_l2(out[:, 0], oracle.c2c(first_col, direction)) <= tol(n)
+
+
+# ---- the kernels that move data with the TMA unit (tests/emu/emu_tma_inst.cpp; tma_util.cuh, MUFFT_EMU branch) ----------
+class ArgsRows(C.Structure):  # abi.h: mcu_rows_args
+    _fields_ = [("out", vp), ("in_", vp), ("in2", vp), ("tw", vp), ("rtw", vp), ("out_stride", sz), ("in_stride", sz), ("in2_stride", sz),
+                ("batch", sz), ("n", C.c_uint), ("direction", C.c_int), ("in_mode", C.c_int), ("out_mode", C.c_int), ("norm", C.c_float),
+                ("parts", C.c_uint), ("in_part_stride", C.c_longlong), ("in2_part_stride", C.c_longlong), ("peers", PeerDest)]
+
+
+def prefetch_rows(emu, host, n, direction, in_mode, out_mode, xbuf, in_stride, out_elems, batch, ctas, in2=None, norm=1.0, rtw=None):
+    """rows_prefetch_kernel.cuh on `ctas` persistent CTAs; xbuf holds the rows `in_stride` complex elements apart."""
+    fn = getattr(emu, f"emu_launch_rows_prefetch_{n}")
+    fn.restype, fn.argtypes = C.c_int, [C.POINTER(ArgsRows), C.c_uint]
+    tw = engine_table(host, n, direction, host.mcu_rows_variant(n, in_mode, out_mode))
+    out = np.full((batch, out_elems + 3), np.nan + 1j * np.nan, np.complex64)
+    a = ArgsRows(out=out.ctypes.data, in_=xbuf.ctypes.data, in2=None if in2 is None else in2.ctypes.data, tw=tw.ctypes.data,
+                 rtw=None if rtw is None else rtw.ctypes.data, out_stride=out_elems + 3, in_stride=in_stride, batch=batch, n=n,
+                 direction=direction, in_mode=in_mode, out_mode=out_mode, norm=norm)
+    rc = fn(C.byref(a), ctas)
+    assert rc == 0, f"emu_launch_rows_prefetch_{n} returned {rc}"
+    assert np.all(np.isnan(out[:, out_elems:].real)), "nothing is written between the transforms"
+    return out[:, :out_elems]
+
+
+@pytest.mark.parametrize("n", [2048, 8192])
+def test_tma_prefetch_rows(emu, host, oracle, n):
+    """The persistent row kernel that lets the "TMA unit" fetch the next transform into the exchange area: five transforms
+    on two CTAs (so every CTA prefetches, waits on its mbarrier and reuses its buffer), every load mode it takes."""
+    rng = np.random.default_rng(n)
+    batch, ctas = 5, 2
+    x = crnd(rng, batch, n)
+    for direction in (-1, 1):
+        got = prefetch_rows(emu, host, n, direction, IN_COMPLEX, OUT_COMPLEX, x, n, n, batch, ctas)
+        for b in range(batch):
+            assert cpu_libs.rel_l2(got[b], oracle.c2c(x[b], direction)) <= tol(n)
+    half = crnd(rng, batch, n // 2)
+    got = prefetch_rows(emu, host, n, -1, IN_HALF, OUT_COMPLEX, half, n // 2, n, batch, ctas)
+    for b in range(batch):
+        assert cpu_libs.rel_l2(got[b], oracle.c2c(half[b], -1, cpu_libs.FLAG_ZERO_PAD, n=n)) <= tol(n)
+    f = crnd(rng, n)
+    got = prefetch_rows(emu, host, n, 1, IN_MUL, OUT_COMPLEX, x, n, n, batch, ctas, in2=f, norm=1.0 / n)
+    want = np.fft.ifft(x.astype(np.complex128) * f.astype(np.complex128), axis=1)
+    for b in range(batch):
+        assert cpu_libs.rel_l2(got[b], want[b]) <= tol(n)
+    # C2R: spectrum rows of n + 1 bins, tightly packed (every other row 8 bytes off a 16-byte boundary) and at an even pitch
+    spec = np.stack([oracle.r2c(rnd(rng, 2 * n)) for _ in range(batch)])  # [batch][n + 1]
+    for pitch in (n + 1, n + 2):
+        sbuf = np.full((batch, pitch), np.nan, np.complex64)
+        sbuf[:, :n + 1] = spec
+        assert sbuf.ctypes.data % 16 == 0
+        got = prefetch_rows(emu, host, n, 1, IN_C2R, OUT_COMPLEX, sbuf, pitch, n, batch, ctas, rtw=resolve_twiddles(1, n))
+        for b in range(batch):
+            assert cpu_libs.rel_l2(got[b].view(np.float32), oracle.c2r(spec[b], 2 * n)) <= tol(2 * n)
+    if n == 8192:  # R2C with the resolve in the registers of the mirrored last pass
+        r = rnd(rng, batch, 2 * n)
+        for full in (0, 1):
+            elems = 2 * n if full else n + 1
+            got = prefetch_rows(emu, host, n, -1, IN_COMPLEX, OUT_R2C_FULL if full else OUT_R2C, r.view(np.complex64), n, elems, batch, ctas,
+                                rtw=resolve_twiddles(-1, n))
+            for b in range(batch):
+                assert cpu_libs.rel_l2(got[b], oracle.r2c(r[b], cpu_libs.FLAG_FULL_R2C if full else 0)) <= tol(2 * n)
+
+
+@pytest.mark.parametrize("nx,ny,batch,ctas,lag", [
+    (512, 512, 4, 2, 1),    # six buffers, column tiles right behind their rows
+    (512, 512, 3, 3, 2),
+    (512, 1024, 3, 2, 1),   # three buffers (the 1024-point column tile sets the size), two twiddle tables
+])
+@pytest.mark.parametrize("direction", [-1, 1])
+def test_tma_fused_2d(emu, host, oracle, nx, ny, batch, ctas, lag, direction):
+    """fft2d_tma_kernel.cuh with its loader, two compute groups and storers as OS threads: mbarrier hand-overs (one `full`
+    barrier per buffer and group), tickets, the rows-done counter, EXIT entries; bulk copies and tensor boxes emulated."""
+    fn = getattr(emu, f"emu_launch_2d_tma_{nx}x{ny}")
+    fn.restype, fn.argtypes = C.c_int, [C.POINTER(Args2D), C.c_uint]
+    rng = np.random.default_rng(nx + ny + ctas)
+    x = crnd(rng, batch, ny, nx)
+    out = np.full((batch, ny, nx), np.nan, np.complex64)
+    counters = np.zeros(1 + 2 * batch, np.uint32)
+    twx, twy = engine_table(host, nx, direction), engine_table(host, ny, direction)
+    a = Args2D(nx=nx, ny=ny, out=out.ctypes.data, in_=x.ctypes.data, tw_x=twx.ctypes.data, tw_y=twy.ctypes.data, kind=KIND_C2C,
+               counters=counters.ctypes.data, out_image=nx * ny, in_image=nx * ny, batch=batch, direction=direction, lag=lag)
+    assert fn(C.byref(a), ctas) == 0
+    for b in range(batch):
+        assert cpu_libs.rel_l2(out[b], oracle.c2c_2d(x[b], direction)) <= tol(nx * ny)
+    assert list(counters[1:1 + batch]) == [ny // 8] * batch  # row tiles announced per image
+
+
+@pytest.mark.parametrize("ny,ctas", [(512, 2), (1024, 3)])
+def test_tma_fused_2d_r2c(emu, host, oracle, ny, ctas):
+    """Real images 1024 wide on the TMA kernel: rows resolved in registers on the way back into the buffer, bin 512 stored
+    apart, 65 column tiles of which the last carries one column - stored from registers, the padding columns untouched."""
+    nx, batch = 512, 3  # complex points per row
+    fn = getattr(emu, f"emu_launch_2d_tma_{nx}x{ny}")
+    fn.restype, fn.argtypes = C.c_int, [C.POINTER(Args2D), C.c_uint]
+    vfn = getattr(emu, f"emu_2d_rows_variant_512x256")
+    vfn.restype, vfn.argtypes = C.c_int, [C.c_int]
+    rng = np.random.default_rng(ny)
+    x = rnd(rng, batch, ny, 2 * nx)
+    out = np.full((batch, ny, 2 * nx), 7.0 + 7.0j, np.complex64)
+    counters = np.zeros(1 + 2 * batch, np.uint32)
+    twx, twy, rtw = engine_table(host, nx, -1, vfn(KIND_R2C)), engine_table(host, ny, -1), resolve_twiddles(-1, nx)
+    a = Args2D(nx=nx, ny=ny, out=out.ctypes.data, in_=x.ctypes.data, tw_x=twx.ctypes.data, tw_y=twy.ctypes.data, rtw=rtw.ctypes.data,
+               kind=KIND_R2C, counters=counters.ctypes.data, out_image=2 * nx * ny, in_image=nx * ny, batch=batch, direction=-1, lag=1)
+    assert fn(C.byref(a), ctas) == 0
+    for b in range(batch):
+        assert cpu_libs.rel_l2(out[b, :, :nx + 1], oracle.r2c_2d(x[b], 0)[:, :nx + 1]) <= tol(2 * nx * ny)
+    assert np.all(out[:, :, nx + 1:] == 7.0 + 7.0j), "columns beyond nx + 1 are padding: never written"
+
+
+@pytest.mark.parametrize("n1,n2", [(16, 1024), (32, 1024)])
+@pytest.mark.parametrize("case", ["fwd", "inv", "zero_pad"])
+def test_tma_four_step_rows(emu, host, n1, n2, case):
+    """long_kernel.cuh with the inputs of step A arriving through the exchange area (TMA_A): sweeps of 256 columns asked for
+    one ahead, the first sweep of the next transform when step B's last group has left the area."""
+    fn = getattr(emu, f"emu_launch_long_tma_{n1}x{n2}")
+    fn.restype, fn.argtypes = C.c_int, [C.POINTER(ArgsLong), C.c_uint]
+    n = n1 * n2
+    direction = 1 if case == "inv" else -1
+    batch, ctas = 5, 2
+    rng = np.random.default_rng(n + len(case))
+    tw = engine_table(host, n2, direction)
+    j = np.arange(n, dtype=np.float64)
+    roots = (np.cos(2 * np.pi * direction * j / n).astype(np.float32) + 1j * np.sin(2 * np.pi * direction * j / n).astype(np.float32)).astype(np.complex64)
+    scratch = np.full((ctas, n), np.nan, np.complex64)
+    in_len = n // 2 if case == "zero_pad" else n
+    in_stride, out_stride = in_len + 8, n + 4  # even strides: 16-byte aligned transforms
+    xbuf = np.full((batch, in_stride), np.nan, np.complex64)
+    xbuf[:, :in_len] = crnd(rng, batch, in_len)
+    x = np.zeros((batch, n), np.complex128)
+    x[:, :in_len] = xbuf[:, :in_len]
+    want = np.fft.fft(x, axis=1) if direction < 0 else np.fft.ifft(x, axis=1, norm="forward")
+    obuf = np.full((batch, out_stride), np.nan, np.complex64)
+    a = ArgsLong(out=obuf.ctypes.data, in_=xbuf.ctypes.data, tw=tw.ctypes.data, roots=roots.ctypes.data, scratch=scratch.ctypes.data, scratch_slots=ctas,
+                 out_batch=out_stride, in_batch=in_stride, batch=batch, n=n, n1=n1, n2=n2, direction=direction,
+                 in_mode=IN_HALF if case == "zero_pad" else IN_COMPLEX)
+    assert fn(C.byref(a), ctas) == 0
+    assert np.all(np.isnan(obuf[:, n:].real)), "nothing is written between the transforms"
+    for b in range(batch):
+        assert cpu_libs.rel_l2(obuf[b, :n], want[b]) <= tol(n)
