@@ -69,14 +69,14 @@ static bool launch_tma(const mcu_2d_args &a, cudaStream_t stream, cudaError_t *e
     p.a = a;
     const cuuint64_t dims[2] = { 2ull * WIDTH, (cuuint64_t)a.batch * F2D_NY }; // the columns that carry data
     const cuuint64_t strides[1] = { (cuuint64_t)PITCH * sizeof(float2) };
-    const cuuint32_t box[2] = { 16, F2D_TMA_BOX_ROWS };
+    const cuuint32_t box[2] = { 2u * f2d_tma_cols_per_tile(F2D_NY), F2D_TMA_BOX_ROWS }; // the columns of a tile x 256 rows
     const cuuint32_t estr[2] = { 1, 1 };
     if (encode(&p.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
         *err = cudaErrorInvalidValue;
         return true;
     }
-    constexpr unsigned per_image = f2d_tickets_per_image(F2D_NX, F2D_NY, KIND);
+    constexpr unsigned per_image = f2d_tma_row_tiles(F2D_NX, F2D_NY, KIND) + f2d_tma_col_tiles(F2D_NX, F2D_NY, KIND);
     const unsigned long long tickets = (unsigned long long)a.batch * per_image;
     if (tickets + (unsigned long long)ctas >= 0xffffffffull) { *err = cudaErrorInvalidConfiguration; return true; }
     const unsigned grid = (unsigned)ctas;

@@ -74,6 +74,20 @@ __host__ __device__ constexpr bool f2d_tma_kind_supported(int nx, int ny, int ki
     if (kind == F2D_C2C) return true;
     return kind == F2D_R2C && f2d_tma_rows_variant(nx, kind) == MUFFT_VARIANT_MIRROR_LAST && nx / engine_regs(nx, MUFFT_VARIANT_MIRROR_LAST) == 32;
 }
+// Row tiles of 64 KB whatever the row length, for C2C images: 8 rows of 1024 points, 16 rows (two per warp, one after the
+// other) of 512.  Measured (profiles/r02au_ab_tma_64k_tiles.txt): 512 x 1024 1.258 -> 1.170 ms.  The same for the columns
+// (16 columns of 512 points per tile, two per thread, 128-byte segments) LOSES, 1024 x 512 1.281 -> 1.372 ms, and so do 16-row
+// tiles for R2C rows (0.672 -> 0.691 ms): columns and R2C rows stay at 8 per tile.  The code below is written for UY columns
+// per thread all the same.
+#ifndef MUFFT_F2D_TMA_UNITS
+#define MUFFT_F2D_TMA_UNITS 2
+#endif
+__host__ __device__ constexpr int f2d_tma_units_x(int nx, int kind) { return nx <= 512 && kind == F2D_C2C ? MUFFT_F2D_TMA_UNITS : 1; }
+__host__ __device__ constexpr int f2d_tma_units_y(int ny) { (void)ny; return 1; }
+__host__ __device__ constexpr int f2d_tma_rows_per_tile(int nx, int kind) { return (F2D_TMA_GROUP_THREADS / 32) * f2d_tma_units_x(nx, kind); }
+__host__ __device__ constexpr int f2d_tma_cols_per_tile(int ny) { return (F2D_TMA_GROUP_THREADS / 32) * f2d_tma_units_y(ny); }
+__host__ __device__ constexpr unsigned f2d_tma_row_tiles(int nx, int ny, int kind) { return ny / f2d_tma_rows_per_tile(nx, kind); }
+__host__ __device__ constexpr unsigned f2d_tma_col_tiles(int nx, int ny, int kind) { return (f2d_width(nx, kind) + f2d_tma_cols_per_tile(ny) - 1) / f2d_tma_cols_per_tile(ny); }
 // A row's exchange area inside a buffer; its first nx (+ 1) elements hold the row in natural order (16-byte aligned for the bulk copies).
 __host__ __device__ constexpr int f2d_tma_row_pitch(int nx, int kind = F2D_C2C)
 {
@@ -82,7 +96,7 @@ __host__ __device__ constexpr int f2d_tma_row_pitch(int nx, int kind = F2D_C2C)
 }
 __host__ __device__ constexpr size_t f2d_tma_buf_bytes(int nx, int ny, int kind = F2D_C2C)
 {
-    size_t r = (size_t)(F2D_TMA_GROUP_THREADS / 32) * f2d_tma_row_pitch(nx, kind), c = (size_t)(F2D_TMA_GROUP_THREADS / 32) * engine_smem_elems(ny);
+    size_t r = (size_t)f2d_tma_rows_per_tile(nx, kind) * f2d_tma_row_pitch(nx, kind), c = (size_t)f2d_tma_cols_per_tile(ny) * engine_smem_elems(ny);
     return ((r > c ? r : c) * sizeof(float2) + 127) / 128 * 128;
 }
 __host__ __device__ constexpr size_t f2d_tma_fixed_bytes(int nx, int ny, int stages, int kind = F2D_C2C)
@@ -164,9 +178,10 @@ fft2d_tma_kernel(const __grid_constant__ f2d_tma_params p)
     static_assert(f2d_tma_kind_supported(NX, NY, KIND), "shape / kind");
     constexpr int VX = f2d_tma_rows_variant(NX, KIND);
     constexpr int PITCH = f2d_pitch(NX, KIND), WIDTH = f2d_width(NX, KIND);
-    constexpr int RX = engine_regs(NX, VX), TX = NX / RX, ROWS = F2D_TMA_GROUP_THREADS / TX; // 8 rows per tile, one warp each
-    constexpr int RY = engine_regs(NY), TY = NY / RY, COLS = F2D_TMA_GROUP_THREADS / TY; // 8 columns per tile: 64-byte segments
-    constexpr unsigned NR = NY / ROWS, NC = (WIDTH + COLS - 1) / COLS;
+    constexpr int UX = f2d_tma_units_x(NX, KIND), UY = f2d_tma_units_y(NY); // rows per warp, columns per thread of a tile
+    constexpr int RX = engine_regs(NX, VX), TX = NX / RX, ROWS = f2d_tma_rows_per_tile(NX, KIND), WARPS = F2D_TMA_GROUP_THREADS / 32;
+    constexpr int RY = engine_regs(NY), TY = NY / RY, COLS = f2d_tma_cols_per_tile(NY), C8 = F2D_TMA_GROUP_THREADS / TY;
+    constexpr unsigned NR = f2d_tma_row_tiles(NX, NY, KIND), NC = f2d_tma_col_tiles(NX, NY, KIND);
     constexpr int ROW_PITCH = f2d_tma_row_pitch(NX, KIND);
     constexpr size_t BUF = f2d_tma_buf_bytes(NX, NY, KIND);
     constexpr int F2D_TMA_STAGES = f2d_tma_stages(NX, NY, KIND), LCM = f2d_tma_lcm(F2D_TMA_STAGES);
@@ -224,41 +239,53 @@ fft2d_tma_kernel(const __grid_constant__ f2d_tma_params p)
             }
             if (MUFFT_TMA_DIAG >= 3) {
             } else if (type == F2D_TMA_ROWS) {
-                const int slot = gtid / TX, t = gtid % TX;
-                cpx *sm = buf + slot * ROW_PITCH;
-                cpx v[RX];
+                const int t = gtid % TX;
+#pragma unroll 1
+                for (int u = 0; u < UX; u++) { // the warp's rows, one after the other: each in its own part of the buffer
+                    const int slot = gtid / TX + u * WARPS;
+                    cpx *sm = buf + slot * ROW_PITCH;
+                    cpx v[RX];
 #pragma unroll
-                for (int e = 0; e < RX; e++) v[e] = sm[t + e * TX];
-                __syncwarp(); // the row is in registers before the exchange overwrites it
-                engine_run<NX, DIR, 1, TX, ROWS, 0, VX, -1, TWM>(v, sm, twx, t, slot);
-                __syncwarp(); // every lane has gathered
-                if constexpr (KIND == F2D_R2C) {
-                    // resolve in registers (mirrored last pass), bins 0 .. NX into the row's natural positions
-                    rows_store_spectrum<NX, MCU_OUT_R2C, TX, ROWS, VX>(v, [sm](int k, cpx val) { sm[k] = val; }, sm, static_cast<const cpx *>(a.rtw), t, slot, true);
-                } else {
+                    for (int e = 0; e < RX; e++) v[e] = sm[t + e * TX];
+                    __syncwarp(); // the row is in registers before the exchange overwrites it
+                    engine_run<NX, DIR, 1, TX, ROWS, 0, VX, -1, TWM>(v, sm, twx, t, slot);
+                    __syncwarp(); // every lane has gathered
+                    if constexpr (KIND == F2D_R2C) {
+                        // resolve in registers (mirrored last pass), bins 0 .. NX into the row's natural positions
+                        rows_store_spectrum<NX, MCU_OUT_R2C, TX, ROWS, VX>(v, [sm](int k, cpx val) { sm[k] = val; }, sm, static_cast<const cpx *>(a.rtw), t, slot, true);
+                    } else {
 #pragma unroll
-                    for (int e = 0; e < RX; e++) sm[t + e * TX] = v[e];
+                        for (int e = 0; e < RX; e++) sm[t + e * TX] = v[e];
+                    }
                 }
             } else {
-                const int c = gtid % COLS, t = gtid / COLS;
-                cpx v[RY];
+                const int c = gtid % C8, t = gtid / C8;
+                cpx v[UY][RY]; // the thread's columns c, c + 8: all in registers before the first exchange overwrites the tile
 #pragma unroll
-                for (int e = 0; e < RY; e++) v[e] = buf[(t + e * TY) * COLS + c];
+                for (int u = 0; u < UY; u++)
+#pragma unroll
+                    for (int e = 0; e < RY; e++) v[u][e] = buf[(t + e * TY) * COLS + c + u * C8];
                 group_barrier(group);
-                engine_run<NY, DIR, COLS, F2D_TMA_GROUP_THREADS, F2D_TMA_GROUPS, 0, 0, -1, TWM>(v, buf + c, twy, t, group);
+#pragma unroll
+                for (int u = 0; u < UY; u++) // exchange areas of different columns are disjoint
+                    engine_run<NY, DIR, COLS, F2D_TMA_GROUP_THREADS, F2D_TMA_GROUPS, 0, 0, -1, TWM>(v[u], buf + c + u * C8, twy, t, group);
                 if (WIDTH % COLS != 0 && meta[b].z == NC - 1) {
                     // The last column tile of an R2C image carries WIDTH % COLS columns.  The TMA unit clips a store at the
                     // edge of the tensor map in units of 16 bytes, i.e. it would write one padding column with zeros (seen:
                     // column 513): these few columns go out from registers instead, and the storer skips the tile.
-                    if (c < WIDTH % COLS) {
-                        cpx *o = static_cast<cpx *>(a.out) + (size_t)meta[b].y * a.out_image + (size_t)(NC - 1) * COLS + c;
 #pragma unroll
-                        for (int e = 0; e < RY; e++) __stcs(o + (size_t)(t + e * TY) * PITCH, v[e]);
-                    }
+                    for (int u = 0; u < UY; u++)
+                        if (c + u * C8 < WIDTH % COLS) {
+                            cpx *o = static_cast<cpx *>(a.out) + (size_t)meta[b].y * a.out_image + (size_t)(NC - 1) * COLS + c + u * C8;
+#pragma unroll
+                            for (int e = 0; e < RY; e++) __stcs(o + (size_t)(t + e * TY) * PITCH, v[u][e]);
+                        }
                 } else {
                     group_barrier(group);
 #pragma unroll
-                    for (int e = 0; e < RY; e++) buf[(t + e * TY) * COLS + c] = v[e];
+                    for (int u = 0; u < UY; u++)
+#pragma unroll
+                        for (int e = 0; e < RY; e++) buf[(t + e * TY) * COLS + c + u * C8] = v[u][e];
                 }
             }
             fence_proxy_async_smem(); // this thread's writes, before the TMA unit reads the buffer

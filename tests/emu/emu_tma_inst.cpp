@@ -31,7 +31,7 @@ static int run_2d(const mcu_2d_args &a, unsigned ctas)
         p.map.dims[0] = 2ull * f2d_width(NX, KIND); // the columns that carry data, as fft2d_inst.cu encodes them
         p.map.dims[1] = (unsigned long long)a.batch * NY;
         p.map.row_bytes = (unsigned long long)f2d_pitch(NX, KIND) * sizeof(cpx);
-        p.map.box[0] = 16;
+        p.map.box[0] = 2u * f2d_tma_cols_per_tile(NY);
         p.map.box[1] = F2D_TMA_BOX_ROWS;
         const emu::idx3 grid{ ctas, 1, 1 };
         emu::launch(grid, f2d_tma_threads(NX, NY, KIND), f2d_tma_smem_bytes(NX, NY, KIND), ctas, 1, [&] { fft2d_tma_kernel<NX, NY, DIR, MUFFT_TW_SMEM | MUFFT_TW_DERIVE, KIND>(p); });
@@ -50,6 +50,7 @@ extern "C" int EMU_CAT(emu_launch_2d_tma_, EMU_NX, x, EMU_NY)(const mcu_2d_args 
     }
 }
 extern "C" int EMU_CAT(emu_2d_tma_stages_, EMU_NX, x, EMU_NY)(int kind) { return f2d_tma_stages(EMU_NX, EMU_NY, kind); }
+extern "C" unsigned EMU_CAT(emu_2d_tma_row_tiles_, EMU_NX, x, EMU_NY)() { return f2d_tma_row_tiles(EMU_NX, EMU_NY, F2D_C2C); }
 
 // ---- rows: every mode pair the prefetching kernel takes at this length -------------------------------------------
 template <int DIR, int IN_MODE, int OUT_MODE>

@@ -655,7 +655,7 @@ def test_tma_fused_2d(emu, host, oracle, nx, ny, batch, ctas, lag, direction):
     assert fn(C.byref(a), ctas) == 0
     for b in range(batch):
         assert cpu_libs.rel_l2(out[b], oracle.c2c_2d(x[b], direction)) <= tol(nx * ny)
-    assert list(counters[1:1 + batch]) == [ny // 8] * batch  # row tiles announced per image
+    assert list(counters[1:1 + batch]) == [getattr(emu, f"emu_2d_tma_row_tiles_{nx}x{ny}")()] * batch  # row tiles announced per image
 
 
 @pytest.mark.parametrize("ny,ctas", [(512, 2), (1024, 3)])
